@@ -1,0 +1,166 @@
+/* ssgpu.h -- C ABI of libssgpu.so: the B200 (sm_100a) implementation of statespacer's Kalman hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain pointers and sizes (no R, Rcpp,
+ * Armadillo or torch types) and returns an int status (0 = ok, see SSGPU_E_*); the message of the
+ * last failure on the calling thread is available from ssgpu_last_error().  Numerical degeneracy is
+ * NOT an error: like the reference, LogLikC yields NaN (R's NA_real_) and KalmanC writes NaN into
+ * loglik[index] (src/LogLikC.cpp:210-213, src/KalmanC.cpp:194,239,335).
+ *
+ * Layouts follow R / Armadillo exactly for the five legacy entry points (column-major; 3-D system
+ * matrices are rows x cols x n_slices with n_slices in {1, N}, "time-varying" iff n_slices > 1,
+ * src/LogLikC.cpp:37-38).  The batched entry points define their own batch-contiguous layout.
+ *
+ * Reference interface replaced (all in /root/reference):
+ *   ssgpu_LogLikC            <- _statespacer_LogLikC            src/RcppExports.cpp:68-84,  src/LogLikC.cpp:20-28
+ *   ssgpu_KalmanC            <- _statespacer_KalmanC            src/RcppExports.cpp:48-65,  src/KalmanC.cpp:21-30
+ *   ssgpu_FastSmootherC      <- _statespacer_FastSmootherC      src/RcppExports.cpp:28-45,  src/FastSmootherC.cpp:23-32
+ *   ssgpu_SimulateC          <- _statespacer_SimulateC          src/RcppExports.cpp:87-106, src/SimulateC.cpp:26-37
+ *   ssgpu_ExtractComponentC  <- _statespacer_ExtractComponentC  src/RcppExports.cpp:16-25,  src/ExtractComponentC.cpp:12-13
+ *   ssgpu_loglik_batch[_dev] <- (new) the sequential LogLikC calls of the optim loop, R/statespacer.R:917-927,977-982
+ *
+ * Threading: entry points may be called from any host thread but serialise on one internal CUDA
+ * stream per device; every host-pointer entry point synchronises before returning (R's .Call
+ * contract).  There is no CPU fallback: without a CUDA device every compute entry
+ * point returns SSGPU_E_CUDA.
+ */
+#ifndef SSGPU_H
+#define SSGPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSGPU_OK 0
+#define SSGPU_E_ARG 1     /* inconsistent sizes / null pointers / unsupported shape (m > SSGPU_MAX_M ...) */
+#define SSGPU_E_CUDA 2    /* CUDA runtime failure (no device, out of memory, launch failure) */
+#define SSGPU_E_DRAWS 3   /* injected normal variates: wrong count */
+
+#define SSGPU_MAX_M 64    /* largest supported state dimension (incl. the p residual states) */
+
+/* Library / device management -------------------------------------------------------------- */
+int ssgpu_version(void);                     /* 100*major + minor */
+const char* ssgpu_last_error(void);          /* thread-local, never NULL */
+int ssgpu_set_device(int device);            /* device used by subsequent calls of this process */
+int ssgpu_device_count(int* count);
+int ssgpu_release(void);                     /* free cached device workspaces and pinned staging */
+/* number of kernels this library launched since process start (bench.py's gpu_launches) */
+long long ssgpu_launch_count(void);
+
+/* ---- 1. LogLikC ---------------------------------------------------------------------------
+ * y N x p (NaN where missing), y_isna N x p (int, non-zero = missing; may be NULL -> derived from
+ * isnan(y)), a[m], P_inf[m*m], P_star[m*m], Z p x m x nZ, T m x m x nT, R m x r x nR, Q r x r x nQ.
+ * *loglik = loglik / N, or NaN if F_star < 1e-7 at every post-initialisation step. */
+int ssgpu_LogLikC(const double* y, const int* y_isna, int N, int p, int m, int r,
+                  const double* a, const double* P_inf, const double* P_star,
+                  const double* Z, int nZ, const double* T, int nT,
+                  const double* R, int nR, const double* Q, int nQ, double* loglik);
+
+/* ---- 2. KalmanC ---------------------------------------------------------------------------
+ * Outputs mirror the list returned at src/KalmanC.cpp:563-593; any pointer may be NULL (skipped).
+ * Shapes (column-major): loglik[N*p] (index = t*p + j); a_pred,a_fil,a_smooth N x m;
+ * P_pred,P_fil,V,P_inf_pred,P_star_pred,P_inf_fil,P_star_fil m x m x N; yfit,v,v_norm,e N x p;
+ * eta N x r; Fmat,D p x p x N; eta_var r x r x N; a_fc[m]; P_inf_fc,P_star_fc,P_fc m x m;
+ * Tstat_observation N x p; Tstat_state (N+1) x m (row 0 is not written, as in the reference);
+ * r_vec (N+1) x m; Nmat m x m x (N+1). */
+typedef struct ssgpu_kalman_out {
+  int* initialisation_steps;
+  double *loglik, *a_pred, *a_fil, *a_smooth, *P_pred, *P_fil, *V, *P_inf_pred, *P_star_pred,
+      *P_inf_fil, *P_star_fil, *yfit, *v, *v_norm, *eta, *e, *Fmat, *eta_var, *D, *a_fc,
+      *P_inf_fc, *P_star_fc, *P_fc, *Tstat_observation, *Tstat_state, *r_vec, *Nmat;
+} ssgpu_kalman_out;
+
+int ssgpu_KalmanC(const double* y, const int* y_isna, int N, int p, int m, int r,
+                  const double* a, const double* P_inf, const double* P_star,
+                  const double* Z, int nZ, const double* T, int nT,
+                  const double* R, int nR, const double* Q, int nQ,
+                  int diagnostics, ssgpu_kalman_out* out);
+
+/* ---- 3. FastSmootherC ---------------------------------------------------------------------
+ * y N x p x nsim (no missing values, src/FastSmootherC.cpp:23-32).  a_smooth N x m x nsim,
+ * a_t m x nsim x N (written only if transposed_state; may be NULL otherwise), eta N x r x nsim
+ * (row N-1 = 0). */
+int ssgpu_FastSmootherC(const double* y, int N, int p, int nsim, int m, int r,
+                        const double* a, const double* P_inf, const double* P_star,
+                        const double* Z, int nZ, const double* T, int nT,
+                        const double* R, int nR, const double* Q, int nQ,
+                        int initialisation_steps, int transposed_state,
+                        double* a_smooth, double* a_t, double* eta);
+
+/* ---- 4. SimulateC -------------------------------------------------------------------------
+ * Z p x m x nZ, T m x m x nT, R m x rR x nR, Q r x r x nQ (block-repeated repeat_Q times,
+ * r_tot = r*repeat_Q), P_star mP x mP (read only if draw_initial).  With eta_only the caller passes
+ * 1 x 1 x 1 dummies for Z, T, R exactly like R/SimSmoother.R:559-573 and only `eta` is written.
+ * `draws` are the standard normal variates the reference would obtain from Rcpp::rnorm, in its call
+ * order (src/SimulateC.cpp:75,112): [m*nsim initial draws if draw_initial] then, for every time
+ * point, r_tot*nsim draws (r_tot fastest); n_draws must equal that count exactly.
+ * Outputs: y N x p x nsim, a N x m x nsim, a_t m x nsim x N (only if transposed_state),
+ * eta N x r_tot x nsim.  Any output pointer may be NULL.
+ * Q_root / P_root: optional precomputed symmetric roots U sqrt(S) U' (r x r x nQ, mP x mP); when
+ * NULL they are computed on the host by a Jacobi eigen-decomposition (src/SimulateC.cpp:73-74,84-85). */
+int ssgpu_SimulateC(int nsim, int repeat_Q, int N, int p, int m, int rR, int r, int mP,
+                    const double* a, const double* Z, int nZ, const double* T, int nT,
+                    const double* R, int nR, const double* Q, int nQ, const double* P_star,
+                    int draw_initial, int eta_only, int transposed_state,
+                    const double* draws, long long n_draws,
+                    const double* Q_root, const double* P_root,
+                    double* y, double* a_out, double* a_t, double* eta);
+
+/* ---- 5. ExtractComponentC -----------------------------------------------------------------
+ * a m x nsim x N, Z p x m x nZ  ->  out N x p x nsim. */
+int ssgpu_ExtractComponentC(const double* a, int m, int nsim, int N,
+                            const double* Z, int p, int nZ, double* out);
+
+/* ---- 6. Batched loglikelihood (new) -------------------------------------------------------
+ * E = B * V evaluations: B series x V parameter vectors ("variants": finite-difference points,
+ * multistart candidates); evaluation e = v * B + b.
+ * y is time-major and batch-contiguous: y[(t*p + j) * B + b], NaN = missing.
+ * Every system matrix is described by an ssgpu_matrix: dense column-major (rows x cols) or, with
+ * diag != 0, only its diagonal (rows doubles per slice); n_slices in {1, N}; the element offset of
+ * the block used by evaluation (b, v) is b*stride_series + v*stride_variant (0/0 = shared by the
+ * whole batch), slices of one block are contiguous.
+ * out[e] = loglik/N or NaN, exactly as ssgpu_LogLikC would return for that evaluation. */
+typedef struct ssgpu_matrix {
+  const double* data;
+  int rows, cols;
+  int diag;
+  int n_slices;
+  long long stride_series;
+  long long stride_variant;
+} ssgpu_matrix;
+
+typedef struct ssgpu_model {
+  int N, p, m, r;
+  ssgpu_matrix a;       /* m x 1 */
+  ssgpu_matrix P_inf;   /* m x m */
+  ssgpu_matrix P_star;  /* m x m */
+  ssgpu_matrix Z;       /* p x m */
+  ssgpu_matrix T;       /* m x m */
+  ssgpu_matrix R;       /* m x r */
+  ssgpu_matrix Q;       /* r x r */
+} ssgpu_model;
+
+/* kernel selection for the batched path */
+#define SSGPU_KERNEL_AUTO 0     /* column kernel when the model qualifies, generic otherwise */
+#define SSGPU_KERNEL_GENERIC 1  /* one CTA per evaluation, any shape */
+#define SSGPU_KERNEL_COLS 2     /* column-per-thread register kernel; SSGPU_E_ARG if not eligible */
+
+/* host pointers everywhere (y, the matrices' data, out); copies in, runs, copies out, synchronises */
+int ssgpu_loglik_batch(const double* y, long long B, int V, const ssgpu_model* model, int kernel,
+                       double* out);
+/* device pointers everywhere; asynchronous on `stream` (a cudaStream_t, NULL = the library's
+ * stream); `out` may be read after the stream is synchronised. */
+int ssgpu_loglik_batch_dev(const double* y, long long B, int V, const ssgpu_model* model, int kernel,
+                           double* out, void* stream);
+/* name of the kernel the last ssgpu_loglik_batch[_dev] call on this thread launched */
+const char* ssgpu_last_kernel(void);
+
+/* ---- 7. Measurement helpers ---------------------------------------------------------------
+ * FP64 FMA-pipe peak of the current device, measured with a register-resident DFMA chain kernel
+ * (`iters` x 256 dependent-free DFMAs per thread, grid = SMs x 8 CTAs x 256 threads): *tflops is
+ * 2 * DFMAs / elapsed.  mode 0 = DFMA, 1 = DMMA (mma.sync.m8n8k4.f64), 2 = both interleaved. */
+int ssgpu_fp64_peak(int mode, int iters, int repeats, double* tflops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSGPU_H */

@@ -1,0 +1,392 @@
+// C ABI of libssgpu (include/ssgpu.h): argument checks, host<->device staging, kernel dispatch.
+#include <atomic>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ssgpu {
+
+// ---- error / bookkeeping ---------------------------------------------------------------------
+static thread_local std::string g_err;
+static thread_local const char* g_last_kernel = "";
+static std::atomic<long long> g_launches{0};
+static std::mutex g_mu;
+static cudaStream_t g_stream = nullptr;
+static int g_device = 0;
+static bool g_ready = false;
+
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch(int n) { g_launches += n; }
+void set_last_kernel(const char* name) { g_last_kernel = name; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  g_err = buf;
+  cudaGetLastError();  // clear sticky-less errors
+  return SSGPU_E_CUDA;
+}
+
+int ensure_device() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_ready) {
+    SS_CUDA(cudaSetDevice(g_device));
+    return SSGPU_OK;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    g_err = "no CUDA device available (libssgpu has no CPU fallback)";
+    return SSGPU_E_CUDA;
+  }
+  SS_CUDA(cudaSetDevice(g_device));
+  SS_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  SS_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_device));
+  unsigned long long thr = ~0ULL;  // keep freed blocks cached in the pool
+  SS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  g_ready = true;
+  return SSGPU_OK;
+}
+
+cudaStream_t lib_stream() { return g_stream; }
+
+int DevBuf::alloc(size_t bytes, cudaStream_t st) {
+  free();
+  st_ = st;
+  if (bytes == 0) bytes = 8;
+  SS_CUDA(cudaMallocAsync(&p_, bytes, st));
+  return SSGPU_OK;
+}
+void DevBuf::free() {
+  if (p_) cudaFreeAsync(p_, st_);
+  p_ = nullptr;
+}
+
+// ---- host-side packing of many small arrays into one H2D copy ------------------------------
+class Packer {
+ public:
+  // returns the element offset (in doubles) of the copied block
+  size_t add(const double* src, size_t n) {
+    const size_t off = buf_.size();
+    const size_t padded = (n + 31) / 32 * 32;  // keep every block 256-byte aligned
+    buf_.resize(off + padded, 0.0);
+    if (n) std::memcpy(buf_.data() + off, src, n * sizeof(double));
+    return off;
+  }
+  size_t reserve(size_t n) {
+    const size_t off = buf_.size();
+    buf_.resize(off + (n + 31) / 32 * 32, 0.0);
+    return off;
+  }
+  double* host(size_t off) { return buf_.data() + off; }
+  size_t size() const { return buf_.size(); }
+  int upload(DevBuf& d, cudaStream_t st) {
+    SS_TRY(d.alloc(buf_.size() * sizeof(double), st));
+    SS_CUDA(cudaMemcpyAsync(d.get(), buf_.data(), buf_.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    return SSGPU_OK;
+  }
+
+ private:
+  std::vector<double> buf_;
+};
+
+static DMat make_dmat(const double* dev, int rows, int cols, int n_slices) {
+  DMat d{};
+  d.p = dev;
+  d.rows = rows;
+  d.cols = cols;
+  d.diag = 0;
+  d.sb = d.sv = 0;
+  d.st = n_slices > 1 ? (long long)rows * cols : 0;
+  return d;
+}
+
+static int check_single(int N, int p, int m, int r, int nZ, int nT, int nR, int nQ) {
+  SS_ARG(N >= 1 && p >= 1 && m >= 1 && r >= 1, "N, p, m, r must be positive");
+  SS_ARG(m <= SSGPU_MAX_M, "state dimension m exceeds SSGPU_MAX_M");
+  SS_ARG((nZ == 1 || nZ == N) && (nT == 1 || nT == N) && (nR == 1 || nR == N) && (nQ == 1 || nQ == N),
+         "system matrices must have 1 or N slices");
+  return SSGPU_OK;
+}
+
+// y (N x p column-major, optional mask) -> time-major [t*p + j] with NaN for missing
+static void pack_y_single(const double* y, const int* isna, int N, int p, double* dst) {
+  for (int t = 0; t < N; t++)
+    for (int j = 0; j < p; j++) {
+      const double v = y[t + (size_t)N * j];
+      dst[(size_t)t * p + j] = (isna && isna[t + (size_t)N * j]) ? nan("") : v;
+    }
+}
+
+struct SingleModel {
+  Packer pk;
+  DevBuf dev;
+  DModel md;
+  size_t oy = 0;
+};
+
+// uploads y + the 7 matrices of one model, fills md with device pointers
+static int stage_single(SingleModel& S, const double* y, const int* y_isna, int N, int p, int m, int r, const double* a,
+                        const double* P_inf, const double* P_star, const double* Z, int nZ, const double* T, int nT,
+                        const double* R, int nR, const double* Q, int nQ, cudaStream_t st) {
+  Packer& pk = S.pk;
+  S.oy = pk.reserve((size_t)N * p);
+  pack_y_single(y, y_isna, N, p, pk.host(S.oy));
+  const size_t oa = pk.add(a, m), opi = pk.add(P_inf, (size_t)m * m), ops = pk.add(P_star, (size_t)m * m);
+  const size_t oz = pk.add(Z, (size_t)p * m * nZ), ot = pk.add(T, (size_t)m * m * nT);
+  const size_t orr = pk.add(R, (size_t)m * r * nR), oq = pk.add(Q, (size_t)r * r * nQ);
+  SS_TRY(pk.upload(S.dev, st));
+  const double* d = S.dev.as<double>();
+  DModel& md = S.md;
+  md.N = N;
+  md.p = p;
+  md.m = m;
+  md.r = r;
+  md.a = make_dmat(d + oa, m, 1, 1);
+  md.P_inf = make_dmat(d + opi, m, m, 1);
+  md.P_star = make_dmat(d + ops, m, m, 1);
+  md.Z = make_dmat(d + oz, p, m, nZ);
+  md.T = make_dmat(d + ot, m, m, nT);
+  md.R = make_dmat(d + orr, m, r, nR);
+  md.Q = make_dmat(d + oq, r, r, nQ);
+  return SSGPU_OK;
+}
+
+// ---- ssgpu_matrix (public) -> DMat ------------------------------------------------------------
+static int to_dmat(const ssgpu_matrix& M, int rows, int cols, int N, const char* name, DMat* out) {
+  std::string nm(name);
+  SS_ARG(M.data != nullptr, nm + ": null data pointer");
+  SS_ARG(M.rows == rows && M.cols == cols, nm + ": unexpected dimensions");
+  SS_ARG(M.n_slices == 1 || M.n_slices == N, nm + ": n_slices must be 1 or N");
+  SS_ARG(!M.diag || rows == cols, nm + ": diag storage needs a square matrix");
+  SS_ARG(M.stride_series >= 0 && M.stride_variant >= 0, nm + ": negative strides are not supported");
+  out->p = M.data;
+  out->rows = rows;
+  out->cols = cols;
+  out->diag = M.diag ? 1 : 0;
+  out->sb = M.stride_series;
+  out->sv = M.stride_variant;
+  out->st = M.n_slices > 1 ? (M.diag ? rows : (long long)rows * cols) : 0;
+  return SSGPU_OK;
+}
+
+static int to_dmodel(const ssgpu_model* mo, DModel* md) {
+  SS_ARG(mo != nullptr, "null model");
+  SS_ARG(mo->N >= 1 && mo->p >= 1 && mo->m >= 1 && mo->r >= 1, "N, p, m, r must be positive");
+  SS_ARG(mo->m <= SSGPU_MAX_M, "state dimension m exceeds SSGPU_MAX_M");
+  md->N = mo->N;
+  md->p = mo->p;
+  md->m = mo->m;
+  md->r = mo->r;
+  SS_TRY(to_dmat(mo->a, mo->m, 1, mo->N, "a", &md->a));
+  SS_ARG(mo->a.n_slices == 1 && !mo->a.diag, "a: must be a plain vector");
+  SS_TRY(to_dmat(mo->P_inf, mo->m, mo->m, mo->N, "P_inf", &md->P_inf));
+  SS_TRY(to_dmat(mo->P_star, mo->m, mo->m, mo->N, "P_star", &md->P_star));
+  SS_ARG(mo->P_inf.n_slices == 1 && mo->P_star.n_slices == 1, "P_inf / P_star cannot be time-varying");
+  SS_TRY(to_dmat(mo->Z, mo->p, mo->m, mo->N, "Z", &md->Z));
+  SS_ARG(!mo->Z.diag, "Z: diag storage is not supported");
+  SS_TRY(to_dmat(mo->T, mo->m, mo->m, mo->N, "T", &md->T));
+  SS_TRY(to_dmat(mo->R, mo->m, mo->r, mo->N, "R", &md->R));
+  SS_TRY(to_dmat(mo->Q, mo->r, mo->r, mo->N, "Q", &md->Q));
+  return SSGPU_OK;
+}
+
+static size_t extent(const ssgpu_matrix& M, long long B, int V) {
+  const size_t slice = M.diag ? (size_t)M.rows : (size_t)M.rows * M.cols;
+  return (size_t)((B - 1) * M.stride_series + (V - 1) * M.stride_variant) + slice * M.n_slices;
+}
+
+static int dispatch_batch(const DModel& md, const double* y_dev, long long B, int V, int kernel, double* out_dev,
+                          cudaStream_t st) {
+  SS_ARG(B >= 1 && V >= 1, "B and V must be positive");
+  std::string why;
+  const bool ok = cols_eligible(md, &why);
+  if (kernel == SSGPU_KERNEL_COLS) SS_ARG(ok, "column kernel not eligible: " + why);
+  if (kernel == SSGPU_KERNEL_COLS || (kernel == SSGPU_KERNEL_AUTO && ok))
+    return launch_loglik_cols(md, y_dev, B, V, out_dev, st);
+  SS_ARG(kernel == SSGPU_KERNEL_AUTO || kernel == SSGPU_KERNEL_GENERIC, "unknown kernel selector");
+  return launch_fwd_generic(md, y_dev, B, V, out_dev, nullptr, nullptr, st);
+}
+
+}  // namespace ssgpu
+
+using namespace ssgpu;
+
+extern "C" {
+
+int ssgpu_version(void) { return 100; }
+const char* ssgpu_last_error(void) { return g_err.c_str(); }
+const char* ssgpu_last_kernel(void) { return g_last_kernel; }
+long long ssgpu_launch_count(void) { return g_launches.load(); }
+
+int ssgpu_set_device(int device) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    SS_ARG(!g_ready || device == g_device, "ssgpu_set_device must be called before the first compute call");
+    g_device = device;
+  }
+  return ensure_device();
+}
+
+int ssgpu_device_count(int* count) {
+  SS_ARG(count != nullptr, "null count");
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    cudaGetLastError();
+  }
+  return SSGPU_OK;
+}
+
+int ssgpu_release(void) {
+  if (!g_ready) return SSGPU_OK;
+  SS_CUDA(cudaStreamSynchronize(g_stream));
+  cudaMemPool_t pool;
+  SS_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_device));
+  SS_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return SSGPU_OK;
+}
+
+int ssgpu_LogLikC(const double* y, const int* y_isna, int N, int p, int m, int r, const double* a, const double* P_inf,
+                  const double* P_star, const double* Z, int nZ, const double* T, int nT, const double* R, int nR,
+                  const double* Q, int nQ, double* loglik) {
+  SS_ARG(y && a && P_inf && P_star && Z && T && R && Q && loglik, "null pointer argument");
+  SS_TRY(check_single(N, p, m, r, nZ, nT, nR, nQ));
+  SS_TRY(ensure_device());
+  cudaStream_t st = lib_stream();
+  SingleModel S;
+  SS_TRY(stage_single(S, y, y_isna, N, p, m, r, a, P_inf, P_star, Z, nZ, T, nT, R, nR, Q, nQ, st));
+  DevBuf out;
+  SS_TRY(out.alloc(sizeof(double), st));
+  SS_TRY(launch_fwd_generic(S.md, S.dev.as<double>() + S.oy, 1, 1, out.as<double>(), nullptr, nullptr, st));
+  SS_CUDA(cudaMemcpyAsync(loglik, out.get(), sizeof(double), cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  return SSGPU_OK;
+}
+
+int ssgpu_KalmanC(const double* y, const int* y_isna, int N, int p, int m, int r, const double* a, const double* P_inf,
+                  const double* P_star, const double* Z, int nZ, const double* T, int nT, const double* R, int nR,
+                  const double* Q, int nQ, int diagnostics, ssgpu_kalman_out* out) {
+  SS_ARG(y && a && P_inf && P_star && Z && T && R && Q && out, "null pointer argument");
+  SS_TRY(check_single(N, p, m, r, nZ, nT, nR, nQ));
+  SS_ARG(!diagnostics, "KalmanC diagnostics (v_norm, e, D, Tstat_*) are not implemented yet");
+  SS_TRY(ensure_device());
+  cudaStream_t st = lib_stream();
+  SingleModel S;
+  SS_TRY(stage_single(S, y, y_isna, N, p, m, r, a, P_inf, P_star, Z, nZ, T, nT, R, nR, Q, nQ, st));
+
+  // one device block for every output + the backward-pass scratch
+  const size_t Np = (size_t)N * p, mm = (size_t)m * m;
+  struct Field {
+    double** host;
+    double** dev;
+    size_t n;
+  };
+  ssgpu_kalman_out d{};
+  std::vector<Field> f = {
+      {&out->loglik, &d.loglik, Np},
+      {&out->a_pred, &d.a_pred, (size_t)N * m},
+      {&out->a_fil, &d.a_fil, (size_t)N * m},
+      {&out->a_smooth, &d.a_smooth, (size_t)N * m},
+      {&out->P_pred, &d.P_pred, mm * N},
+      {&out->P_fil, &d.P_fil, mm * N},
+      {&out->V, &d.V, mm * N},
+      {&out->P_inf_pred, &d.P_inf_pred, mm * N},
+      {&out->P_star_pred, &d.P_star_pred, mm * N},
+      {&out->P_inf_fil, &d.P_inf_fil, mm * N},
+      {&out->P_star_fil, &d.P_star_fil, mm * N},
+      {&out->yfit, &d.yfit, Np},
+      {&out->v, &d.v, Np},
+      {&out->eta, &d.eta, (size_t)N * r},
+      {&out->Fmat, &d.Fmat, (size_t)p * p * N},
+      {&out->eta_var, &d.eta_var, (size_t)r * r * N},
+      {&out->a_fc, &d.a_fc, (size_t)m},
+      {&out->P_inf_fc, &d.P_inf_fc, mm},
+      {&out->P_star_fc, &d.P_star_fc, mm},
+      {&out->P_fc, &d.P_fc, mm},
+      {&out->r_vec, &d.r_vec, (size_t)(N + 1) * m},
+      {&out->Nmat, &d.Nmat, mm * (N + 1)},
+  };
+  size_t total = 0;
+  auto pad = [](size_t n) { return (n + 31) / 32 * 32; };
+  for (auto& x : f) total += pad(x.n);
+  const bool qtr_tv = nQ > 1 || nR > 1;
+  const size_t n_scr = pad(Np) * 3 + pad(Np * m) * 2 + pad((size_t)(qtr_tv ? N : 1) * r * m) + pad(Np) + 32;
+  DevBuf blk;
+  SS_TRY(blk.alloc((total + n_scr) * sizeof(double), st));
+  double* base = blk.as<double>();
+  size_t off = 0;
+  for (auto& x : f) {
+    *x.dev = base + off;
+    off += pad(x.n);
+  }
+  KalmanScratch s{};
+  s.F1 = base + off; off += pad(Np);
+  s.F2 = base + off; off += pad(Np);
+  s.v = base + off; off += pad(Np);
+  s.K0 = base + off; off += pad(Np * m);
+  s.K1 = base + off; off += pad(Np * m);
+  s.QtR = base + off; off += pad((size_t)(qtr_tv ? N : 1) * r * m);
+  s.code = reinterpret_cast<int*>(base + off); off += pad(Np);
+  d.initialisation_steps = reinterpret_cast<int*>(base + off); off += 32;
+
+  const double* yd = S.dev.as<double>() + S.oy;
+  SS_TRY(launch_fwd_generic(S.md, yd, 1, 1, nullptr, &d, &s, st));
+  SS_TRY(launch_bwd_generic(S.md, &d, &s, st));
+  for (auto& x : f)
+    if (*x.host)
+      SS_CUDA(cudaMemcpyAsync(*x.host, *x.dev, x.n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (out->initialisation_steps)
+    SS_CUDA(cudaMemcpyAsync(out->initialisation_steps, d.initialisation_steps, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  return SSGPU_OK;
+}
+
+int ssgpu_loglik_batch_dev(const double* y, long long B, int V, const ssgpu_model* model, int kernel, double* out,
+                           void* stream) {
+  SS_ARG(y && out, "null pointer argument");
+  DModel md{};
+  SS_TRY(to_dmodel(model, &md));
+  SS_TRY(ensure_device());
+  cudaStream_t st = stream ? (cudaStream_t)stream : lib_stream();
+  return dispatch_batch(md, y, B, V, kernel, out, st);
+}
+
+int ssgpu_loglik_batch(const double* y, long long B, int V, const ssgpu_model* model, int kernel, double* out) {
+  SS_ARG(y && out, "null pointer argument");
+  DModel md{};
+  SS_TRY(to_dmodel(model, &md));
+  SS_ARG(B >= 1 && V >= 1, "B and V must be positive");
+  SS_TRY(ensure_device());
+  cudaStream_t st = lib_stream();
+  const ssgpu_matrix* src[7] = {&model->a, &model->P_inf, &model->P_star, &model->Z, &model->T, &model->R, &model->Q};
+  DMat* dst[7] = {&md.a, &md.P_inf, &md.P_star, &md.Z, &md.T, &md.R, &md.Q};
+  auto pad = [](size_t n) { return (n + 31) / 32 * 32; };
+  size_t n_y = (size_t)model->N * model->p * (size_t)B, total = pad(n_y) + pad((size_t)B * V);
+  size_t ext[7];
+  for (int i = 0; i < 7; i++) {
+    ext[i] = extent(*src[i], B, V);
+    total += pad(ext[i]);
+  }
+  DevBuf blk;
+  SS_TRY(blk.alloc(total * sizeof(double), st));
+  double* base = blk.as<double>();
+  size_t off = 0;
+  SS_CUDA(cudaMemcpyAsync(base, y, n_y * sizeof(double), cudaMemcpyHostToDevice, st));
+  off += pad(n_y);
+  for (int i = 0; i < 7; i++) {
+    SS_CUDA(cudaMemcpyAsync(base + off, src[i]->data, ext[i] * sizeof(double), cudaMemcpyHostToDevice, st));
+    dst[i]->p = base + off;
+    off += pad(ext[i]);
+  }
+  double* out_dev = base + off;
+  SS_TRY(dispatch_batch(md, base, B, V, kernel, out_dev, st));
+  SS_CUDA(cudaMemcpyAsync(out, out_dev, (size_t)B * V * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  return SSGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,379 @@
+// Generic forward filter: univariate-treatment Kalman filter with exact diffuse initialisation,
+// one CTA per evaluation, any (m <= 64, p, r), time-varying or per-evaluation system matrices.
+//
+// Restates the recursion of src/LogLikC.cpp:68-208 (KALMAN = false) and of the forward loop of
+// src/KalmanC.cpp:122-409 (KALMAN = true, which additionally stores every intermediate the backward
+// pass and the R caller need).  The covariance lives in shared memory; work inside a CTA is
+// element-parallel (thread e owns elements e, e+NT, ... of every m x m object), all scalar decisions
+// (F_inf / F_star thresholds, P_inf ~ 0 test) are block-uniform.
+//
+// This is the "any shape" kernel: the throughput kernel for the batched headline workload is
+// loglik_cols.cu.  Rank-1 forms are used for the measurement update:
+//   P* L0' = P* - (P* z) K0'            (src/LogLikC.cpp:129,193)
+//   P_inf L1' + P* L0' = P* - M* K0' - M_inf K1'   (:151),  P_inf L0' = P_inf - M_inf K0' (:152)
+// which equal the reference's GEMM forms exactly in real arithmetic and to O(eps) in FP64.
+#include "common.cuh"
+
+namespace ssgpu {
+
+struct FwdArgs {
+  DModel md;
+  const double* y;  // [(t*p + j) * B + b]
+  long long B;
+  int V;
+  double* out;  // [E] loglik / N (LOGLIK mode)
+  ssgpu_kalman_out k;  // device pointers (KALMAN mode)
+  KalmanScratch s;
+};
+
+__device__ __forceinline__ void load_mat(double* dst, const double* blk, int diag, int rows, int cols, int tid,
+                                         int NT) {
+  const int n = rows * cols;
+  for (int e = tid; e < n; e += NT) {
+    if (diag) {
+      const int i = e % rows, j = e / rows;
+      dst[e] = i == j ? blk[i] : 0.0;
+    } else {
+      dst[e] = blk[e];
+    }
+  }
+}
+
+// C (m x m) = A (m x m) * B (m x m), all column-major in shared memory
+__device__ __forceinline__ void mm_nn(double* C, const double* A, const double* Bm, int m, int tid, int NT) {
+  for (int e = tid; e < m * m; e += NT) {
+    const int i = e % m, j = e / m;
+    double acc = 0.0;
+    for (int k = 0; k < m; k++) acc = fma(A[i + k * m], Bm[k + j * m], acc);
+    C[e] = acc;
+  }
+}
+// C = add + A * B'   (add may be nullptr)
+__device__ __forceinline__ void mm_nt(double* C, const double* A, const double* Bm, const double* add, int m, int tid,
+                                      int NT) {
+  for (int e = tid; e < m * m; e += NT) {
+    const int i = e % m, j = e / m;
+    double acc = 0.0;
+    for (int k = 0; k < m; k++) acc = fma(A[i + k * m], Bm[j + k * m], acc);
+    C[e] = add ? acc + add[e] : acc;
+  }
+}
+
+template <bool KALMAN>
+__global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
+  extern __shared__ double sm[];
+  const DModel& md = A.md;
+  const int m = md.m, p = md.p, r = md.r, N = md.N;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const long long e = blockIdx.x;
+  const long long b = e % A.B, v = e / A.B;
+  const int mm = m * m;
+  int wsz = mm;
+  if (m * r > wsz) wsz = m * r;
+  if (p * m > wsz) wsz = p * m;
+  double* Ps = sm;
+  double* Pi = Ps + mm;
+  double* W = Pi + mm;
+  double* Ts = W + wsz;
+  double* RQR = Ts + mm;
+  double* Zs = RQR + mm;
+  double* av = Zs + p * m;
+  double* av2 = av + m;
+  double* Ms = av2 + m;
+  double* Mi = Ms + m;
+
+  load_mat(av, md.a.block(b, v, 0), 0, m, 1, tid, NT);
+  load_mat(Pi, md.P_inf.block(b, v, 0), md.P_inf.diag, m, m, tid, NT);
+  load_mat(Ps, md.P_star.block(b, v, 0), md.P_star.diag, m, m, tid, NT);
+  load_mat(Zs, md.Z.block(b, v, 0), 0, p, m, tid, NT);
+  load_mat(Ts, md.T.block(b, v, 0), md.T.diag, m, m, tid, NT);
+  __syncthreads();
+
+  // initialisation = !all(|P_inf| < 1e-7)   (src/LogLikC.cpp:49)
+  auto pinf_small = [&]() {
+    int ok = 1;
+    for (int q = tid; q < mm; q += NT) ok &= (fabs(Pi[q]) < kEps) ? 1 : 0;
+    return __syncthreads_and(ok);
+  };
+  bool init = !pinf_small();
+
+  // Q_t R_t' (r x m, into W) then R_t (Q_t R_t')  -> RQR   (src/KalmanC.cpp:108,385)
+  auto build_rqr = [&](int t) {
+    const double* Qb = md.Q.block(b, v, md.Q.tv() ? t : 0);
+    const double* Rb = md.R.block(b, v, md.R.tv() ? t : 0);
+    for (int q = tid; q < r * m; q += NT) {
+      const int k = q % r, j = q / r;
+      double acc = 0.0;
+      if (md.Q.diag) {
+        acc = Qb[k] * mat_get(Rb, md.R.diag, m, j, k);
+      } else {
+        for (int l = 0; l < r; l++) acc = fma(Qb[k + l * r], mat_get(Rb, md.R.diag, m, j, l), acc);
+      }
+      W[q] = acc;
+      if (KALMAN) A.s.QtR[(long long)((md.Q.tv() || md.R.tv()) ? t : 0) * r * m + q] = acc;
+    }
+    __syncthreads();
+    for (int q = tid; q < mm; q += NT) {
+      const int i = q % m, j = q / m;
+      double acc = 0.0;
+      if (md.R.diag) {
+        acc = i < r ? Rb[i] * W[i + j * r] : 0.0;
+      } else {
+        for (int k = 0; k < r; k++) acc = fma(Rb[i + (long long)k * m], W[k + j * r], acc);
+      }
+      RQR[q] = acc;
+    }
+    __syncthreads();
+  };
+  build_rqr(0);
+
+  double loglik = 0.0;
+  int non_init = 0, F_eq0 = 0, init_steps = 0;
+  const bool rq_tv = md.Q.tv() || md.R.tv();
+
+  for (int t = 0; t < N; t++) {
+    if (t > 0) {
+      if (md.Z.tv()) load_mat(Zs, md.Z.block(b, v, t), 0, p, m, tid, NT);
+      if (md.T.tv()) load_mat(Ts, md.T.block(b, v, t), md.T.diag, m, m, tid, NT);
+      if (md.Z.tv() || md.T.tv()) __syncthreads();
+      if (rq_tv) build_rqr(t);
+    }
+
+    if (KALMAN) {
+      // predicted quantities (src/KalmanC.cpp:145-162)
+      const ssgpu_kalman_out& K = A.k;
+      for (int q = tid; q < m; q += NT)
+        if (K.a_pred) K.a_pred[t + (long long)N * q] = av[q];
+      for (int q = tid; q < mm; q += NT) {
+        const double ps = Ps[q], pi = init ? Pi[q] : 0.0;
+        const long long o = (long long)t * mm + q;
+        if (K.P_star_pred) K.P_star_pred[o] = ps;
+        if (K.P_inf_pred) K.P_inf_pred[o] = pi;
+        if (K.P_pred) K.P_pred[o] = init ? ps + kKappa * pi : ps;
+      }
+      // yfit = Z a_pred ; v = y - yfit
+      for (int j = tid; j < p; j += NT) {
+        double acc = 0.0;
+        for (int k = 0; k < m; k++) acc = fma(Zs[j + k * p], av[k], acc);
+        if (K.yfit) K.yfit[t + (long long)N * j] = acc;
+        if (K.v) K.v[t + (long long)N * j] = A.y[((long long)t * p + j) * A.B + b] - acc;
+      }
+      // Fmat = Z P_pred Z'   via ZP (p x m) in W
+      if (K.Fmat) {
+        for (int q = tid; q < p * m; q += NT) {
+          const int i = q % p, l = q / p;
+          double acc = 0.0;
+          for (int k = 0; k < m; k++) {
+            const double pp = init ? Ps[k + l * m] + kKappa * Pi[k + l * m] : Ps[k + l * m];
+            acc = fma(Zs[i + k * p], pp, acc);
+          }
+          W[q] = acc;
+        }
+        __syncthreads();
+        for (int q = tid; q < p * p; q += NT) {
+          const int i = q % p, j = q / p;
+          double acc = 0.0;
+          for (int l = 0; l < m; l++) acc = fma(W[i + l * p], Zs[j + l * p], acc);
+          K.Fmat[(long long)t * p * p + q] = acc;
+        }
+        __syncthreads();
+      }
+    }
+
+    for (int j = 0; j < p; j++) {
+      const int index = t * p + j;
+      const double yv = A.y[((long long)t * p + j) * A.B + b];
+      if (isnan(yv)) {  // src/LogLikC.cpp:88-90, src/KalmanC.cpp:193-211
+        if (KALMAN) {
+          if (init) init_steps++;
+          if (tid == 0) {
+            if (A.k.loglik) A.k.loglik[index] = nan("");
+            A.s.code[index] = 0;
+          }
+        }
+        continue;
+      }
+      // M = P z
+      for (int i = tid; i < m; i += NT) {
+        double as = 0.0, ai = 0.0;
+        for (int k = 0; k < m; k++) {
+          const double z = Zs[j + k * p];
+          as = fma(Ps[i + k * m], z, as);
+          if (init) ai = fma(Pi[i + k * m], z, ai);
+        }
+        Ms[i] = as;
+        Mi[i] = ai;
+      }
+      __syncthreads();
+      double F_star = 0.0, F_inf = 0.0, za = 0.0;
+      for (int k = 0; k < m; k++) {
+        const double z = Zs[j + k * p];
+        F_star = fma(z, Ms[k], F_star);
+        F_inf = fma(z, Mi[k], F_inf);
+        za = fma(z, av[k], za);
+      }
+      int code = 0;
+      double F1 = 0.0, F2 = 0.0, vv = 0.0, ll = nan("");
+      if (init) {
+        if (KALMAN) init_steps++;
+        if (F_inf < kEps) {
+          if (F_star >= kEps) code = 1;
+        } else {
+          code = 2;
+        }
+      } else {
+        non_init++;
+        if (F_star < kEps)
+          F_eq0++;
+        else
+          code = 1;
+      }
+      if (code == 1) {
+        F1 = 1.0 / F_star;
+        vv = yv - za;
+        ll = kLogConst - (log(F_star) + vv * vv * F1) / 2;
+        loglik += ll;
+      } else if (code == 2) {
+        F1 = 1.0 / F_inf;
+        F2 = -(F1 * F1) * F_star;
+        vv = yv - za;
+        ll = kLogConst - log(F_inf) / 2;
+        loglik += ll;
+      }
+      if (KALMAN && tid == 0) {
+        if (A.k.loglik) A.k.loglik[index] = ll;
+        A.s.code[index] = code | (init ? 256 : 0);
+        A.s.F1[index] = F1;
+        A.s.F2[index] = F2;
+        A.s.v[index] = vv;
+      }
+      if (code == 0) {
+        __syncthreads();  // Ms/Mi are rewritten by the next step
+        continue;
+      }
+      // K0 = M F1 (code 1: M*, code 2: M_inf); K1 = M* F1 + M_inf F2 (code 2 only)
+      if (KALMAN) {
+        for (int i = tid; i < m; i += NT) {
+          A.s.K0[(long long)index * m + i] = (code == 1 ? Ms[i] : Mi[i]) * F1;
+          A.s.K1[(long long)index * m + i] = code == 2 ? Ms[i] * F1 + Mi[i] * F2 : 0.0;
+        }
+      }
+      for (int q = tid; q < mm; q += NT) {
+        const int i = q % m, c = q / m;
+        if (code == 1) {
+          Ps[q] = Ps[q] - Ms[i] * (Ms[c] * F1);
+        } else {
+          const double k0 = Mi[c] * F1;
+          const double k1 = Ms[c] * F1 + Mi[c] * F2;
+          Ps[q] = (Ps[q] - Ms[i] * k0) - Mi[i] * k1;
+          Pi[q] = Pi[q] - Mi[i] * k0;
+        }
+      }
+      __syncthreads();  // all reads of av (za) are done before av is updated
+      for (int i = tid; i < m; i += NT) av[i] = av[i] + ((code == 1 ? Ms[i] : Mi[i]) * F1) * vv;
+      __syncthreads();
+      if (code == 2 && j < p - 1) init = !pinf_small();  // src/LogLikC.cpp:157-159
+    }
+
+    if (KALMAN) {
+      // filtered quantities (src/KalmanC.cpp:375-382,394-400)
+      const ssgpu_kalman_out& K = A.k;
+      for (int q = tid; q < m; q += NT)
+        if (K.a_fil) K.a_fil[t + (long long)N * q] = av[q];
+      for (int q = tid; q < mm; q += NT) {
+        const double ps = Ps[q], pi = init ? Pi[q] : 0.0;
+        const long long o = (long long)t * mm + q;
+        if (K.P_star_fil) K.P_star_fil[o] = ps;
+        if (K.P_inf_fil) K.P_inf_fil[o] = pi;
+        if (K.P_fil) K.P_fil[o] = init ? ps + kKappa * pi : ps;
+      }
+    }
+
+    // transition to the next time point (src/LogLikC.cpp:200-207; KalmanC also forecasts after t = N-1)
+    if (t < N - 1 || KALMAN) {
+      for (int i = tid; i < m; i += NT) {
+        double acc = 0.0;
+        for (int k = 0; k < m; k++) acc = fma(Ts[i + k * m], av[k], acc);
+        av2[i] = acc;
+      }
+      mm_nn(W, Ts, Ps, m, tid, NT);
+      __syncthreads();
+      mm_nt(Ps, W, Ts, RQR, m, tid, NT);
+      for (int i = tid; i < m; i += NT) av[i] = av2[i];
+      __syncthreads();
+      if (init) {
+        mm_nn(W, Ts, Pi, m, tid, NT);
+        __syncthreads();
+        mm_nt(Pi, W, Ts, nullptr, m, tid, NT);
+        __syncthreads();
+        if (t < N - 1) init = !pinf_small();
+      }
+      if (KALMAN && t == N - 1) {
+        const ssgpu_kalman_out& K = A.k;
+        for (int q = tid; q < m; q += NT)
+          if (K.a_fc) K.a_fc[q] = av[q];
+        for (int q = tid; q < mm; q += NT) {
+          const double ps = Ps[q], pi = init ? Pi[q] : 0.0;
+          if (K.P_star_fc) K.P_star_fc[q] = ps;
+          if (K.P_inf_fc) K.P_inf_fc[q] = pi;
+          if (K.P_fc) K.P_fc[q] = init ? ps + kKappa * pi : ps;
+        }
+      }
+    }
+  }
+
+  if (tid == 0) {
+    if (KALMAN) {
+      if (A.k.initialisation_steps) *A.k.initialisation_steps = init_steps;
+    } else {
+      A.out[e] = (non_init == F_eq0) ? nan("") : loglik / N;  // src/LogLikC.cpp:211-214
+    }
+  }
+}
+
+static size_t fwd_smem_bytes(const DModel& md) {
+  const int m = md.m, p = md.p, r = md.r;
+  size_t wsz = (size_t)m * m;
+  if ((size_t)m * r > wsz) wsz = (size_t)m * r;
+  if ((size_t)p * m > wsz) wsz = (size_t)p * m;
+  return sizeof(double) * (4 * (size_t)m * m + wsz + (size_t)p * m + 4 * (size_t)m);
+}
+
+static int pick_threads(int m) {
+  int nt = ((m * m + 31) / 32) * 32;
+  if (nt < 32) nt = 32;
+  if (nt > 512) nt = 512;
+  return nt;
+}
+
+int launch_fwd_generic(const DModel& md, const double* y, long long B, int V, double* out_loglik,
+                       const ssgpu_kalman_out* kout, const KalmanScratch* scratch, cudaStream_t st) {
+  FwdArgs A{};
+  A.md = md;
+  A.y = y;
+  A.B = B;
+  A.V = V;
+  A.out = out_loglik;
+  const size_t smem = fwd_smem_bytes(md);
+  SS_ARG(smem <= 227 * 1024, "generic filter: model does not fit in shared memory (m, p or r too large)");
+  const long long E = B * V;
+  SS_ARG(E > 0 && E < (1LL << 31), "generic filter: batch size out of range");
+  const int nt = pick_threads(md.m);
+  if (kout) {
+    SS_ARG(B == 1 && V == 1 && scratch, "KalmanC runs one series per call");
+    A.k = *kout;
+    A.s = *scratch;
+    SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fwd_generic_kernel<true><<<1, nt, smem, st>>>(A);
+    set_last_kernel("fwd_generic_kernel<KALMAN>");
+  } else {
+    SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fwd_generic_kernel<false><<<(unsigned)E, nt, smem, st>>>(A);
+    set_last_kernel("fwd_generic_kernel<LOGLIK>");
+  }
+  count_launch();
+  SS_CUDA(cudaGetLastError());
+  return SSGPU_OK;
+}
+
+}  // namespace ssgpu
