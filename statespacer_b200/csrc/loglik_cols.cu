@@ -1,0 +1,380 @@
+// Batched loglikelihood, "column-per-lane" register kernel -- the throughput path behind
+// ssgpu_loglik_batch[_dev] for models whose Z, T, R are shared by the whole batch and
+// time-invariant (per-evaluation a, P_inf, P_star, Q are allowed), m <= 15.
+//
+// Restates the recursion of src/LogLikC.cpp:68-214 (univariate treatment, exact diffuse
+// initialisation, NaN = missing).  Mapping:
+//   * one evaluation (series b, parameter vector v) per group of G = pow2 >= m+1 lanes;
+//   * lane c < m keeps column c of P_star (and of P_inf while the filter is diffuse) in registers,
+//     lane m keeps the state vector a as an extra column: with the columns side by side
+//         M = [P a]' z           gives  P z  and  z'a   in one sweep,
+//         [P a] -= M g'          is the rank-1 covariance update and  a += K v  at once
+//                                (g_c = M_c / F for c < m, g_m = -v / F),
+//         [P a] <- T [P a]       is the first half of T P T' and the whole of  a <- T a;
+//   * T, Z, R live in __constant__ memory, so every DFMA of the two T-products takes its matrix
+//     operand straight from the constant bank (no load instruction, no register);
+//   * T P T' = T (T P)' needs the transpose of T P: lanes exchange it through a padded,
+//     conflict-free shared-memory tile; P z is all-gathered through shared memory as well;
+//   * sum(log F) is carried as (mantissa product, exponent sum): one log() per evaluation.
+// The measurement update is applied as the rank-1 forms P - M K0' (src/LogLikC.cpp:129,193) and
+// P* - M* K0' - M_inf K1', P_inf - M_inf K0' (:151-152): equal to the reference's GEMM forms in
+// real arithmetic, O(eps) apart in FP64.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace ssgpu {
+
+constexpr int kColsMaxM = 15;
+constexpr int kColsThreads = 128;
+// __constant__ layout (doubles): T column-major, even pitch [k*ldt(M) + i] | Z [j*M + k] | R [k*M + i]
+constexpr int kOffT = 0, kOffZ = 1024, kOffR = 3072, kConstDoubles = 4096;
+constexpr int kColsMaxP = 2048 / 16, kColsMaxR = 32;
+
+__constant__ __align__(16) double cMat[kConstDoubles];
+__host__ __device__ constexpr int ldt(int m) { return m + (m & 1); }
+
+struct ColsArgs {
+  DModel md;
+  const double* y;  // [(t*p + j) * B + b]
+  long long B;
+  long long E;  // B * V
+  double* out;
+};
+
+// repack the shared matrices for the constant bank (one tiny launch per batch call)
+__global__ void cols_pack_kernel(DModel md, double* dst) {
+  const int m = md.m, p = md.p, r = md.r;
+  const double* Tb = md.T.block(0, 0, 0);
+  const double* Zb = md.Z.block(0, 0, 0);
+  const double* Rb = md.R.block(0, 0, 0);
+  for (int q = threadIdx.x; q < kConstDoubles; q += blockDim.x) dst[q] = 0.0;
+  __syncthreads();
+  for (int q = threadIdx.x; q < m * m; q += blockDim.x) {
+    const int i = q % m, k = q / m;
+    dst[kOffT + k * ldt(m) + i] = mat_get(Tb, md.T.diag, m, i, k);
+  }
+  for (int q = threadIdx.x; q < p * m; q += blockDim.x) {
+    const int j = q / m, k = q % m;
+    dst[kOffZ + q] = Zb[j + (long long)k * p];
+  }
+  for (int q = threadIdx.x; q < r * m; q += blockDim.x) {
+    const int k = q / m, i = q % m;
+    dst[kOffR + q] = md.R.diag ? (i == k ? Rb[i] : 0.0) : Rb[i + (long long)k * m];
+  }
+}
+
+// y = init + T x, T from the constant bank.  k outermost: M independent accumulator chains, x[k]
+// reused M times, T[.,k] arrives through the uniform datapath (LDCU -> UR operand of the DFMA).
+// Each y[i] is still summed over k in ascending order.
+template <int M, bool INIT>
+__device__ __forceinline__ void mul_T(const double (&x)[M], double (&y)[M], const double (&init)[M]) {
+#pragma unroll
+  for (int i = 0; i < M; i++) y[i] = INIT ? init[i] : 0.0;
+#pragma unroll
+  for (int k = 0; k < M; k++) {
+#pragma unroll
+    for (int i = 0; i < M; i++) y[i] = fma(cMat[kOffT + k * ldt(M) + i], x[k], y[i]);
+  }
+}
+
+template <int M, int G, bool P1, int MINB>
+__global__ void __launch_bounds__(kColsThreads, MINB) loglik_cols_kernel(const ColsArgs A) {
+  constexpr int LD = G + 1;                   // padded tile pitch: conflict-free both ways
+  constexpr int GROUP_SMEM = M * LD + 4 * G;  // transpose tile + 2 double-buffered gather vectors
+  constexpr int GPB = kColsThreads / G;
+  extern __shared__ double smem[];
+
+  const DModel& md = A.md;
+  const int N = md.N, p = P1 ? 1 : md.p, r = md.r;
+  const int tid = threadIdx.x;
+  const int gi = tid / G, c = tid % G;
+  const long long e = (long long)blockIdx.x * GPB + gi;
+  if (e >= A.E) return;  // whole group leaves together
+  const long long b = e % A.B, v = e / A.B;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((tid % 32) / G * G));
+  double* S = smem + gi * GROUP_SMEM;
+  double* Mv = S + M * LD;  // [2 parities][2 (star, inf)][G]
+  const bool is_col = c < M, is_a = c == M;
+  const int cc = is_col ? c : M - 1;  // row this lane reads back from the transpose tile
+
+  // ---- the evaluation's own a / P_star column and its column of R Q R' ------------------------
+  double col[M], rqr[M];
+  {
+    const double* ab = md.a.block(b, v, 0);
+    const double* Ps = md.P_star.block(b, v, 0);
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+      col[k] = is_col ? mat_get(Ps, md.P_star.diag, M, k, c) : (is_a ? ab[k] : 0.0);
+      rqr[k] = 0.0;
+    }
+    // rqr[i] = sum_k R[i,k] (Q R')[k,c]   (src/LogLikC.cpp:202, hoisted: Q and R are time-invariant here)
+    const double* Qb = md.Q.block(b, v, 0);
+    if (is_col) {
+      for (int k = 0; k < r; k++) {
+        double qr;
+        if (md.Q.diag) {
+          qr = Qb[k] * cMat[kOffR + k * M + c];
+        } else {
+          qr = 0.0;
+          for (int l = 0; l < r; l++) qr = fma(Qb[k + (long long)l * r], cMat[kOffR + l * M + c], qr);
+        }
+#pragma unroll
+        for (int i = 0; i < M; i++) rqr[i] = fma(cMat[kOffR + k * M + i], qr, rqr[i]);
+      }
+    }
+  }
+
+  // loglik = n_terms*const - (sum log F + sum v^2/F)/2, log F accumulated as mantissa * 2^esum
+  double prod = 1.0, sumq = 0.0;
+  int esum = 0, n_terms = 0, non_init = 0, F_eq0 = 0, par = 0;
+  auto acc_log = [&](double F) {
+    prod *= F;
+    const int hi = __double2hiint(prod);
+    const int ex = ((hi >> 20) & 0x7ff) - 1023;
+    esum += ex;
+    prod = __hiloint2double(hi - (ex << 20), __double2loint(prod));
+    n_terms++;
+  };
+
+  // y is read G flat indices (q = t*p + j) at a time, one per lane, one chunk ahead
+  const long long Np = (long long)N * p;
+  auto load_y = [&](long long qq) { return qq < Np ? A.y[qq * A.B + b] : 0.0; };
+  double ybuf = 0.0, ynext = load_y(c);
+  long long q = 0;
+  auto next_y = [&]() {
+    const int ql = (int)(q & (G - 1));
+    if (ql == 0) {
+      ybuf = ynext;
+      ynext = load_y(q + G + c);
+    }
+    q++;
+    return __shfl_sync(gmask, ybuf, ql, G);
+  };
+
+  // M = [P a]' z into the gather buffer; returns this lane's entry
+  auto sweep = [&](const double (&x)[M], const double* z, double* dst) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; k++) acc = fma(x[k], z[k], acc);
+    dst[c] = acc;
+    return acc;
+  };
+
+  // regular (non-diffuse) scalar update, src/LogLikC.cpp:161-196; ms already in mv[0..M]
+  auto regular_obs = [&](double yv, const double* z, const double* mv, double ms) {
+    non_init++;
+    double Ms[M];
+    double F_star = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+      Ms[k] = mv[k];
+      F_star = fma(z[k], Ms[k], F_star);
+    }
+    const double za = mv[M];
+    if (F_star < kEps) {
+      F_eq0++;  // :173-176
+    } else {
+      const double F1 = __drcp_rn(F_star), vv = yv - za;
+      const double g = is_col ? ms * F1 : (is_a ? -(F1 * vv) : 0.0);
+#pragma unroll
+      for (int k = 0; k < M; k++) col[k] = fma(-Ms[k], g, col[k]);
+      acc_log(F_star);
+      sumq = fma(vv * vv, F1, sumq);
+    }
+  };
+
+  // x <- T x T' (+ R Q R'), columns exchanged through the shared tile.  For the [P a] block lane m
+  // keeps T a (the first product) instead of the second one.
+  auto sandwich = [&](double (&x)[M], auto with_rqr, auto keep_first) {
+    double w[M], u[M], pn[M];
+    mul_T<M, false>(x, w, w);  // lanes < m: column c of T X;  lane m: T a
+#pragma unroll
+    for (int i = 0; i < M; i++) S[i * LD + c] = w[i];
+    __syncwarp(gmask);
+#pragma unroll
+    for (int k = 0; k < M; k++) u[k] = S[cc * LD + k];  // row c of T X
+    __syncwarp(gmask);
+    mul_T<M, decltype(with_rqr)::value>(u, pn, rqr);  // column c of T (T X)' [+ R Q R']
+#pragma unroll
+    for (int k = 0; k < M; k++) x[k] = is_col ? pn[k] : (decltype(keep_first)::value ? w[k] : 0.0);
+  };
+  using yes = std::true_type;
+  using no = std::false_type;
+
+  int t = 0;
+  {
+    // ---- exact diffuse phase: P_inf columns live only in this block -----------------------------
+    double pin[M];
+    const double* Pi = md.P_inf.block(b, v, 0);
+#pragma unroll
+    for (int k = 0; k < M; k++) pin[k] = is_col ? mat_get(Pi, md.P_inf.diag, M, k, c) : 0.0;
+    auto pinf_small = [&]() {
+      bool ok = true;
+#pragma unroll
+      for (int k = 0; k < M; k++) ok = ok && (fabs(pin[k]) < kEps);
+      return __all_sync(gmask, ok) != 0;
+    };
+    bool init = !pinf_small();  // src/LogLikC.cpp:49
+
+    for (; t < N && init; t++) {
+      for (int j = 0; j < p; j++) {
+        const double yv = next_y();
+        if (isnan(yv)) continue;  // :88-90
+        const double* z = cMat + kOffZ + (P1 ? 0 : j * M);
+        double* mv = Mv + par * 2 * G;
+        par ^= 1;
+        const double ms = sweep(col, z, mv);
+        if (!init) {  // P_inf vanished earlier in this time point (p > 1)
+          __syncwarp(gmask);
+          regular_obs(yv, z, mv, ms);
+          continue;
+        }
+        const double mi = sweep(pin, z, mv + G);
+        __syncwarp(gmask);
+        double Ms[M], Mi[M];
+        double F_star = 0.0, F_inf = 0.0;
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+          Ms[k] = mv[k];
+          Mi[k] = mv[G + k];
+          F_star = fma(z[k], Ms[k], F_star);
+          F_inf = fma(z[k], Mi[k], F_inf);
+        }
+        const double za = mv[M];
+        if (F_inf < kEps) {
+          if (F_star < kEps) continue;  // :112-113
+          // :117-131  a += K0 v, P* -= M* K0', K0 = M*/F*
+          const double F1 = __drcp_rn(F_star), vv = yv - za;
+          const double g = is_col ? ms * F1 : (is_a ? -(F1 * vv) : 0.0);
+#pragma unroll
+          for (int k = 0; k < M; k++) col[k] = fma(-Ms[k], g, col[k]);
+          acc_log(F_star);
+          sumq = fma(vv * vv, F1, sumq);
+          continue;
+        }
+        // :136-153  K0 = M_inf F1, K1 = M* F1 + M_inf F2
+        const double F1 = __drcp_rn(F_inf), F2 = -(F1 * F1) * F_star, vv = yv - za;
+        const double k0 = is_col ? mi * F1 : (is_a ? -(F1 * vv) : 0.0);
+        const double k1 = is_col ? ms * F1 + mi * F2 : 0.0;
+        const double k0p = is_col ? k0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+          // lanes < m: P*[k,c] - M*[k] K0[c] - M_inf[k] K1[c];  lane m: a[k] + (M_inf[k] F1) v
+          col[k] = is_a ? fma(-Mi[k], k0, col[k]) : fma(-Mi[k], k1, fma(-Ms[k], k0, col[k]));
+          pin[k] = fma(-Mi[k], k0p, pin[k]);
+        }
+        acc_log(F_inf);
+        if (j < p - 1) init = !pinf_small();  // :157-159
+      }
+      if (t < N - 1) {  // :200-207
+        sandwich(col, yes{}, yes{});
+        if (init) {
+          sandwich(pin, no{}, no{});
+          init = !pinf_small();
+        }
+      }
+    }
+  }
+
+  // ---- regular phase: the hot loop ----------------------------------------------------------------
+  for (; t < N; t++) {
+    for (int j = 0; j < p; j++) {
+      const double yv = next_y();
+      if (isnan(yv)) continue;
+      const double* z = cMat + kOffZ + (P1 ? 0 : j * M);
+      double* mv = Mv + par * 2 * G;
+      par ^= 1;
+      const double ms = sweep(col, z, mv);
+      __syncwarp(gmask);
+      regular_obs(yv, z, mv, ms);
+    }
+    if (t < N - 1) sandwich(col, yes{}, yes{});
+  }
+
+  if (c == 0) {
+    double res;
+    if (non_init == F_eq0) {
+      res = nan("");  // src/LogLikC.cpp:211-213
+    } else {
+      const double sumlog = (double)esum * 0.69314718055994530942 + log(prod);
+      res = ((double)n_terms * kLogConst - 0.5 * (sumlog + sumq)) / (double)N;
+    }
+    A.out[e] = res;
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static int group_lanes(int m) {
+  int g = 2;
+  while (g < m + 1) g *= 2;
+  return g;
+}
+
+bool cols_eligible(const DModel& md, std::string* why) {
+  auto no = [&](const char* s) {
+    if (why) *why = s;
+    return false;
+  };
+  if (md.m > kColsMaxM) return no("m > 15");
+  if (md.r > kColsMaxR) return no("r > 32");
+  if (md.p > kColsMaxP) return no("p too large for the constant bank");
+  if (!md.Z.shared() || !md.T.shared() || !md.R.shared()) return no("Z, T, R must be shared by the batch");
+  if (md.Z.tv() || md.T.tv() || md.R.tv() || md.Q.tv()) return no("time-varying system matrices");
+  return true;
+}
+
+template <int M, int G, bool P1>
+static int launch_cols_inst(const ColsArgs& A, cudaStream_t st) {
+  constexpr int GPB = kColsThreads / G;
+  constexpr size_t smem = sizeof(double) * GPB * (M * (G + 1) + 4 * G);
+  const long long blocks = (A.E + GPB - 1) / GPB;
+  SS_ARG(blocks < (1LL << 31), "column kernel: batch too large for one launch");
+  loglik_cols_kernel<M, G, P1, 3><<<(unsigned)blocks, kColsThreads, smem, st>>>(A);
+  return SSGPU_OK;
+}
+
+template <int M>
+static int launch_cols_m(const ColsArgs& A, cudaStream_t st) {
+  constexpr int G = M + 1 <= 2 ? 2 : M + 1 <= 4 ? 4 : M + 1 <= 8 ? 8 : 16;
+  if (A.md.p == 1) return launch_cols_inst<M, G, true>(A, st);
+  return launch_cols_inst<M, G, false>(A, st);
+}
+
+static double* g_pack = nullptr;
+
+int launch_loglik_cols(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st) {
+  std::string why;
+  SS_ARG(cols_eligible(md, &why), "column kernel not eligible: " + why);
+  if (!g_pack) SS_CUDA(cudaMalloc(&g_pack, sizeof(double) * kConstDoubles));
+  cols_pack_kernel<<<1, 256, 0, st>>>(md, g_pack);
+  SS_CUDA(cudaGetLastError());
+  SS_CUDA(cudaMemcpyToSymbolAsync(cMat, g_pack, sizeof(double) * kConstDoubles, 0, cudaMemcpyDeviceToDevice, st));
+  ColsArgs A{};
+  A.md = md;
+  A.y = y;
+  A.B = B;
+  A.E = B * V;
+  A.out = out;
+  (void)group_lanes;
+  int rc = SSGPU_E_ARG;
+  switch (md.m) {
+#define SS_CASE(MM) \
+  case MM:          \
+    rc = launch_cols_m<MM>(A, st); \
+    break;
+    SS_CASE(1) SS_CASE(2) SS_CASE(3) SS_CASE(4) SS_CASE(5) SS_CASE(6) SS_CASE(7) SS_CASE(8)
+    SS_CASE(9) SS_CASE(10) SS_CASE(11) SS_CASE(12) SS_CASE(13) SS_CASE(14) SS_CASE(15)
+#undef SS_CASE
+    default:
+      set_error("column kernel: unsupported m");
+      return SSGPU_E_ARG;
+  }
+  SS_TRY(rc);
+  SS_CUDA(cudaGetLastError());
+  count_launch(2);
+  set_last_kernel("loglik_cols_kernel");
+  return SSGPU_OK;
+}
+
+}  // namespace ssgpu
