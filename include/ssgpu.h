@@ -105,6 +105,10 @@ int ssgpu_SimulateC(int nsim, int repeat_Q, int N, int p, int m, int rR, int r, 
                     const double* Q_root, const double* P_root,
                     double* y, double* a_out, double* a_t, double* eta);
 
+/* U diag(sqrt(|lambda|)) U' of a symmetric n x n matrix (host, cyclic Jacobi): the root SimulateC takes of
+ * Q and P_star when Q_root / P_root are NULL. */
+int ssgpu_sym_root(const double* A, int n, double* out);
+
 /* ---- 5. ExtractComponentC -----------------------------------------------------------------
  * a m x nsim x N, Z p x m x nZ  ->  out N x p x nsim. */
 int ssgpu_ExtractComponentC(const double* a, int m, int nsim, int N,

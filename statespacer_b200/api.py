@@ -1,0 +1,322 @@
+"""Host-side mirror of the reference's native interface (R/RcppExports.R:11-99) on top of libssgpu.
+
+The five functions keep the reference's names, argument order and meaning (arrays in R's shapes:
+3-D system matrices are (rows, cols, 1|N)); results come back as NumPy arrays / dicts keyed like the
+lists the reference returns (src/KalmanC.cpp:563-593, src/FastSmootherC.cpp:370-374,
+src/SimulateC.cpp:133-138).  `loglik_batch` / `loglik_batch_dev` are the new batched entry points that
+replace the sequential LogLikC calls of the optim loop (R/statespacer.R:917-927,977-982).
+
+Errors: inconsistent shapes raise (the reference throws through BEGIN_RCPP/END_RCPP); numerical
+degeneracy is not an error (NaN where the reference returns NA).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import native
+from .native import KERNEL_AUTO, KERNEL_COLS, KERNEL_GENERIC  # noqa: F401
+
+_KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "cols": KERNEL_COLS}
+
+
+def _f(x):
+    return np.asfortranarray(np.asarray(x, dtype=np.float64))
+
+
+def _cube(x, name):
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 2:
+        x = x[:, :, None]
+    if x.ndim != 3:
+        raise ValueError(f"{name} must be a matrix or a 3-D array")
+    return np.asfortranarray(x)
+
+
+def _ptr(x):
+    return None if x is None else x.ctypes.data
+
+
+def _dims(a, P_inf, P_star, Z, T, R, Q, N):
+    m = a.shape[0]
+    p, r = Z.shape[0], R.shape[1]
+    ok = (P_inf.shape == (m, m) and P_star.shape == (m, m) and Z.shape[:2] == (p, m) and T.shape[:2] == (m, m)
+          and R.shape[0] == m and Q.shape[:2] == (r, r))
+    if not ok:
+        raise ValueError("inconsistent system matrix dimensions")
+    for X, nm in ((Z, "Z"), (T, "T"), (R, "R"), (Q, "Q")):
+        if X.shape[2] not in (1, N):
+            raise ValueError(f"{nm} must have 1 or N slices")
+    return m, p, r
+
+
+def _prep(a, P_inf, P_star, Z, T, R, Q):
+    a = _f(np.asarray(a, dtype=np.float64).reshape(-1))
+    return a, _f(P_inf), _f(P_star), _cube(Z, "Z"), _cube(T, "T"), _cube(R, "R"), _cube(Q, "Q")
+
+
+def last_kernel() -> str:
+    return native.lib().ssgpu_last_kernel().decode()
+
+
+def launch_count() -> int:
+    return int(native.lib().ssgpu_launch_count())
+
+
+def set_device(device: int) -> None:
+    native.check(native.lib().ssgpu_set_device(int(device)))
+
+
+def fp64_peak(mode=0, iters=2000, repeats=5):
+    """Measured FP64 peak of the current device in TFLOP/s (mode 0 DFMA, 1 DMMA, 2 both)."""
+    tf, ms = C.c_double(), C.c_double()
+    native.check(native.lib().ssgpu_fp64_peak(mode, iters, repeats, C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value
+
+
+# ---- the five reference routines ------------------------------------------------------------------
+def LogLikC(y, y_isna, a, P_inf, P_star, Z, T, R, Q):
+    """src/LogLikC.cpp:20-215: loglik / N, NaN where the reference returns NA_REAL."""
+    y = _f(y)
+    if y.ndim != 2:
+        raise ValueError("y must be an N x p matrix")
+    isna = None if y_isna is None else np.asfortranarray(np.asarray(y_isna).astype(np.int32))
+    a, P_inf, P_star, Z, T, R, Q = _prep(a, P_inf, P_star, Z, T, R, Q)
+    N = y.shape[0]
+    m, p, r = _dims(a, P_inf, P_star, Z, T, R, Q, N)
+    if y.shape[1] != p or (isna is not None and isna.shape != y.shape):
+        raise ValueError("y / y_isna do not match Z")
+    out = C.c_double()
+    native.check(native.lib().ssgpu_LogLikC(_ptr(y), _ptr(isna), N, p, m, r, _ptr(a), _ptr(P_inf), _ptr(P_star),
+                                            _ptr(Z), Z.shape[2], _ptr(T), T.shape[2], _ptr(R), R.shape[2],
+                                            _ptr(Q), Q.shape[2], C.byref(out)))
+    return out.value
+
+
+def kalman_shapes(N, p, m, r):
+    return {
+        "loglik": (N * p,), "a_pred": (N, m), "a_fil": (N, m), "a_smooth": (N, m),
+        "P_pred": (m, m, N), "P_fil": (m, m, N), "V": (m, m, N), "P_inf_pred": (m, m, N),
+        "P_star_pred": (m, m, N), "P_inf_fil": (m, m, N), "P_star_fil": (m, m, N),
+        "yfit": (N, p), "v": (N, p), "eta": (N, r), "Fmat": (p, p, N), "eta_var": (r, r, N), "a_fc": (m,),
+        "P_inf_fc": (m, m), "P_star_fc": (m, m), "P_fc": (m, m), "r_vec": (N + 1, m), "Nmat": (m, m, N + 1),
+    }
+
+
+def KalmanC(y, y_isna, a, P_inf, P_star, Z, T, R, Q, diagnostics=False):
+    """src/KalmanC.cpp:21-594 (diagnostics = FALSE): filter + smoother for one series."""
+    y = _f(y)
+    isna = None if y_isna is None else np.asfortranarray(np.asarray(y_isna).astype(np.int32))
+    a, P_inf, P_star, Z, T, R, Q = _prep(a, P_inf, P_star, Z, T, R, Q)
+    N = y.shape[0]
+    m, p, r = _dims(a, P_inf, P_star, Z, T, R, Q, N)
+    if y.shape[1] != p:
+        raise ValueError("y does not match Z")
+    out = {k: np.zeros(s, order="F") for k, s in kalman_shapes(N, p, m, r).items()}
+    steps = C.c_int()
+    st = native.KalmanOut()
+    st.initialisation_steps = C.pointer(steps)
+    for k, arr in out.items():
+        setattr(st, k, arr.ctypes.data_as(native.dp))
+    native.check(native.lib().ssgpu_KalmanC(_ptr(y), _ptr(isna), N, p, m, r, _ptr(a), _ptr(P_inf), _ptr(P_star),
+                                            _ptr(Z), Z.shape[2], _ptr(T), T.shape[2], _ptr(R), R.shape[2],
+                                            _ptr(Q), Q.shape[2], int(bool(diagnostics)), C.byref(st)))
+    out["initialisation_steps"] = steps.value
+    return out
+
+
+def FastSmootherC(y, a, P_inf, P_star, Z, T, R, Q, initialisation_steps, transposed_state):
+    """src/FastSmootherC.cpp:23-375: y is N x p x nsim."""
+    y = np.asfortranarray(np.asarray(y, dtype=np.float64))
+    if y.ndim != 3:
+        raise ValueError("y must be N x p x nsim")
+    a, P_inf, P_star, Z, T, R, Q = _prep(a, P_inf, P_star, Z, T, R, Q)
+    N, p_y, nsim = y.shape
+    m, p, r = _dims(a, P_inf, P_star, Z, T, R, Q, N)
+    if p_y != p:
+        raise ValueError("y does not match Z")
+    a_smooth = np.zeros((N, m, nsim), order="F")
+    a_t = np.zeros((m, nsim, N), order="F")
+    eta = np.zeros((N, r, nsim), order="F")
+    native.check(native.lib().ssgpu_FastSmootherC(
+        _ptr(y), N, p, nsim, m, r, _ptr(a), _ptr(P_inf), _ptr(P_star), _ptr(Z), Z.shape[2], _ptr(T), T.shape[2],
+        _ptr(R), R.shape[2], _ptr(Q), Q.shape[2], int(initialisation_steps), int(bool(transposed_state)),
+        _ptr(a_smooth), _ptr(a_t) if transposed_state else None, _ptr(eta)))
+    return {"a_smooth": a_smooth, "a_t": a_t, "eta": eta}
+
+
+def sym_root(A):
+    A = _f(np.atleast_2d(A))
+    out = np.zeros_like(A, order="F")
+    native.check(native.lib().ssgpu_sym_root(_ptr(A), A.shape[0], _ptr(out)))
+    return out
+
+
+def SimulateC(nsim, repeat_Q, N, a, Z, T, R, Q, P_star, draw_initial, eta_only, transposed_state, draws,
+              Q_root=None, P_root=None):
+    """src/SimulateC.cpp:26-139 with the normal variates injected: `draws` are the values Rcpp::rnorm
+    would return, in the reference's call order ([m*nsim initial draws], then r_tot*nsim per time point)."""
+    a = _f(np.asarray(a, dtype=np.float64).reshape(-1))
+    Z, T, R, Q = _cube(Z, "Z"), _cube(T, "T"), _cube(R, "R"), _cube(Q, "Q")
+    P_star = _f(np.atleast_2d(P_star))
+    draws = np.ascontiguousarray(draws, dtype=np.float64).reshape(-1)
+    p, m, r = Z.shape[0], a.shape[0], Q.shape[0]
+    r_tot = r * repeat_Q
+    Q_root = None if Q_root is None else _cube(Q_root, "Q_root")
+    P_root = None if P_root is None else _f(P_root)
+    y = np.zeros((N, p, nsim), order="F")
+    a_out = np.zeros((N, m, nsim), order="F")
+    a_t = np.zeros((m, nsim, N), order="F")
+    eta = np.zeros((N, r_tot, nsim), order="F")
+    native.check(native.lib().ssgpu_SimulateC(
+        nsim, repeat_Q, N, p, m, R.shape[1], r, P_star.shape[0], _ptr(a), _ptr(Z), Z.shape[2], _ptr(T), T.shape[2],
+        _ptr(R), R.shape[2], _ptr(Q), Q.shape[2], _ptr(P_star), int(bool(draw_initial)), int(bool(eta_only)),
+        int(bool(transposed_state)), _ptr(draws), draws.shape[0], _ptr(Q_root), _ptr(P_root), _ptr(y), _ptr(a_out),
+        _ptr(a_t) if transposed_state else None, _ptr(eta)))
+    return {"y": y, "a": a_out, "a_t": a_t, "eta": eta}
+
+
+def ExtractComponentC(a, Z):
+    """src/ExtractComponentC.cpp:12-40: a is m x nsim x N."""
+    a = np.asfortranarray(np.asarray(a, dtype=np.float64))
+    Z = _cube(Z, "Z")
+    if a.ndim != 3 or Z.shape[1] != a.shape[0] or Z.shape[2] not in (1, a.shape[2]):
+        raise ValueError("a must be m x nsim x N and match Z")
+    m, nsim, N = a.shape
+    p = Z.shape[0]
+    out = np.zeros((N, p, nsim), order="F")
+    native.check(native.lib().ssgpu_ExtractComponentC(_ptr(a), m, nsim, N, _ptr(Z), p, Z.shape[2], _ptr(out)))
+    return out
+
+
+# ---- batched loglikelihood ----------------------------------------------------------------------------
+class BatchModel:
+    """An ssgpu_model plus the arrays that keep its pointers alive.
+
+    Shared matrices come from `sm` (a sysmat.SysMat); per-evaluation overrides are arrays whose leading
+    dimensions are (V, B) or (B,): `P_star_diag` / `Q_diag` (..., m) / (..., r) hold diagonals only,
+    `P_star` / `Q` / `P_inf` (..., k, k) dense symmetric blocks, `a` (..., m).  Arrays are NumPy (host
+    entry point) or torch CUDA tensors (device entry point) -- never mixed."""
+
+    def __init__(self, sm, N, B, V=1, a=None, P_inf=None, P_star=None, Q=None, P_star_diag=None, Q_diag=None,
+                 device=None):
+        self.keep = []
+        self.device = device
+        Z, T, R, Qs = (_cube(x, n) for x, n in ((sm.Z, "Z"), (sm.T, "T"), (sm.R, "R"), (sm.Q, "Q")))
+        a0 = _f(np.asarray(sm.a, dtype=np.float64).reshape(-1))
+        m, p, r = _dims(a0, _f(sm.P_inf), _f(sm.P_star), Z, T, R, Qs, N)
+        self.N, self.p, self.m, self.r, self.B, self.V = N, p, m, r, B, V
+        mo = native.Model()
+        mo.N, mo.p, mo.m, mo.r = N, p, m, r
+        mo.Z = self._shared(Z, p, m)
+        mo.T = self._shared(T, m, m)
+        mo.R = self._shared(R, m, r)
+        mo.a = self._per_eval(a, m, 1, False) if a is not None else self._shared(a0.reshape(m, 1, 1), m, 1)
+        mo.P_inf = (self._per_eval(P_inf, m, m, False) if P_inf is not None
+                    else self._shared(_f(sm.P_inf)[:, :, None], m, m))
+        if P_star_diag is not None:
+            mo.P_star = self._per_eval(P_star_diag, m, m, True)
+        elif P_star is not None:
+            mo.P_star = self._per_eval(P_star, m, m, False)
+        else:
+            mo.P_star = self._shared(_f(sm.P_star)[:, :, None], m, m)
+        if Q_diag is not None:
+            mo.Q = self._per_eval(Q_diag, r, r, True)
+        elif Q is not None:
+            mo.Q = self._per_eval(Q, r, r, False)
+        else:
+            mo.Q = self._shared(Qs, r, r)
+        self.c = mo
+
+    def _shared(self, cube, rows, cols):
+        flat = np.asfortranarray(cube).reshape(-1, order="F")
+        if self.device is None:
+            self.keep.append(flat)
+            ptr = flat.ctypes.data
+        else:
+            import torch
+            t = torch.from_numpy(flat.copy()).to(self.device)
+            self.keep.append(t)
+            ptr = t.data_ptr()
+        return native.Matrix(ptr, rows, cols, 0, cube.shape[2], 0, 0)
+
+    def _per_eval(self, x, rows, cols, diag):
+        block = rows if diag else rows * cols
+        is_torch = not isinstance(x, np.ndarray) and hasattr(x, "data_ptr")
+        shape = tuple(x.shape)
+        tail = 1 if (diag or cols == 1) else 2
+        lead = shape[:len(shape) - tail]
+        if int(np.prod(shape[len(lead):])) != block:
+            raise ValueError("per-evaluation block has the wrong size")
+        if lead == (self.B,):
+            sv = 0
+        elif lead == (self.V, self.B):
+            sv = self.B * block
+        else:
+            raise ValueError(f"per-evaluation arrays must lead with (B,) or (V, B); got {shape}")
+        if is_torch:
+            if self.device is None:
+                raise ValueError("torch tensors need device=...")
+            t = x.contiguous()
+            if str(t.dtype) != "torch.float64" or not t.is_cuda:
+                raise ValueError("device arrays must be float64 CUDA tensors")
+            self.keep.append(t)
+            ptr = t.data_ptr()
+        else:
+            arr = np.ascontiguousarray(x, dtype=np.float64)
+            if self.device is None:
+                self.keep.append(arr)
+                ptr = arr.ctypes.data
+            else:
+                import torch
+                t = torch.from_numpy(arr).to(self.device)
+                self.keep.append(t)
+                ptr = t.data_ptr()
+        # dense per-evaluation blocks are symmetric (covariances), so C order == column-major
+        return native.Matrix(ptr, rows, cols, 1 if diag else 0, 1, block, sv)
+
+
+def _y_dims(y, p):
+    shape = tuple(y.shape)
+    if len(shape) == 2:
+        Np, B = shape
+    elif len(shape) == 3:
+        Np, B = shape[0] * shape[1], shape[2]
+        if shape[1] != p:
+            raise ValueError("y must be (N, p, B)")
+    else:
+        raise ValueError("y must be (N*p, B) or (N, p, B), time-major and batch-contiguous")
+    if Np % p:
+        raise ValueError("y rows must be a multiple of p")
+    return Np // p, B
+
+
+def loglik_batch(y, sm, V=1, kernel="auto", **per_eval):
+    """Batched LogLikC on host arrays.  y: (N, B) or (N, p, B) C-contiguous (time-major, batch-contiguous),
+    NaN = missing.  Returns (B,) for V == 1 else (V, B): loglik / N per evaluation."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    N, B = _y_dims(y, np.asarray(sm.Z).shape[0])
+    model = BatchModel(sm, N, B, V, **per_eval)
+    out = np.zeros((V, B))
+    native.check(native.lib().ssgpu_loglik_batch(y.ctypes.data, B, V, C.byref(model.c), _KERNELS[kernel],
+                                                 out.ctypes.data))
+    return out[0] if V == 1 else out
+
+
+def loglik_batch_dev(y, model: BatchModel, out, kernel="auto", stream=None):
+    """Batched LogLikC on device-resident data (torch CUDA float64 tensors); asynchronous on `stream`
+    (a torch.cuda.Stream, default: the current one)."""
+    import torch
+    if not (y.is_cuda and y.dtype == torch.float64 and y.is_contiguous() and out.is_cuda
+            and out.dtype == torch.float64 and out.is_contiguous()):
+        raise ValueError("y and out must be contiguous float64 CUDA tensors")
+    if out.numel() != model.B * model.V:
+        raise ValueError("out must hold B * V values")
+    s = stream if stream is not None else torch.cuda.current_stream(y.device)
+    # torch's default stream has handle 0, which the C ABI reads as "the library's own stream": name the
+    # legacy default stream explicitly (cudaStreamLegacy == 0x1) so that the launch is ordered after torch's work
+    handle = s.cuda_stream or 1
+    native.check(native.lib().ssgpu_loglik_batch_dev(y.data_ptr(), model.B, model.V, C.byref(model.c),
+                                                     _KERNELS[kernel], out.data_ptr(), handle))
+    return out

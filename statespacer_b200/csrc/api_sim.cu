@@ -1,0 +1,285 @@
+// C ABI of libssgpu, simulation smoother part: ssgpu_FastSmootherC, ssgpu_SimulateC,
+// ssgpu_ExtractComponentC (include/ssgpu.h sections 3-5) -- host staging around the kernels of sim.cu.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace ssgpu {
+
+static int upload(DevBuf& d, const double* src, size_t n, cudaStream_t st) {
+  SS_TRY(d.alloc(n * sizeof(double), st));
+  if (n) SS_CUDA(cudaMemcpyAsync(d.get(), src, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  return SSGPU_OK;
+}
+
+static DMat dmat3(const double* dev, int rows, int cols, int n_slices) {
+  DMat d{};
+  d.p = dev;
+  d.rows = rows;
+  d.cols = cols;
+  d.st = n_slices > 1 ? (long long)rows * cols : 0;
+  return d;
+}
+
+// U diag(sqrt(|lambda|)) U' of a symmetric matrix by cyclic Jacobi rotations: the matrix that
+// src/SimulateC.cpp:73-74,84-85 obtains from arma::svd (U diag(sqrt(s)) U', s = |lambda|).
+static void sym_root_host(const double* A, int n, double* out) {
+  const size_t N = (size_t)n;
+  std::vector<double> a(A, A + N * N), v(N * N, 0.0);
+  for (size_t i = 0; i < N; i++) v[i + i * N] = 1.0;
+  for (size_t i = 0; i < N; i++)
+    for (size_t j = i + 1; j < N; j++) a[i + j * N] = a[j + i * N] = 0.5 * (a[i + j * N] + a[j + i * N]);
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0.0, diag = 0.0;
+    for (size_t i = 0; i < N; i++)
+      for (size_t j = 0; j < N; j++) (i == j ? diag : off) += a[i + j * N] * a[i + j * N];
+    if (off == 0.0 || off <= 1e-32 * diag) break;
+    for (size_t p = 0; p + 1 < N; p++)
+      for (size_t q = p + 1; q < N; q++) {
+        const double apq = a[p + q * N];
+        if (apq == 0.0) continue;
+        const double theta = (a[q + q * N] - a[p + p * N]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (size_t k = 0; k < N; k++) {
+          const double akp = a[k + p * N], akq = a[k + q * N];
+          a[k + p * N] = c * akp - sn * akq;
+          a[k + q * N] = sn * akp + c * akq;
+        }
+        for (size_t k = 0; k < N; k++) {
+          const double apk = a[p + k * N], aqk = a[q + k * N];
+          a[p + k * N] = c * apk - sn * aqk;
+          a[q + k * N] = sn * apk + c * aqk;
+        }
+        for (size_t k = 0; k < N; k++) {
+          const double vkp = v[k + p * N], vkq = v[k + q * N];
+          v[k + p * N] = c * vkp - sn * vkq;
+          v[k + q * N] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  for (size_t i = 0; i < N; i++)
+    for (size_t j = 0; j < N; j++) {
+      double acc = 0.0;
+      for (size_t k = 0; k < N; k++) acc += v[i + k * N] * std::sqrt(std::fabs(a[k + k * N])) * v[j + k * N];
+      out[i + j * N] = acc;
+    }
+}
+
+// pads every block to 32 doubles so device sub-buffers stay 256-byte aligned
+struct HostPack {
+  std::vector<double> buf;
+  size_t add(const double* src, size_t n) {
+    const size_t off = buf.size();
+    buf.resize(off + (n + 31) / 32 * 32, 0.0);
+    if (n) std::memcpy(buf.data() + off, src, n * sizeof(double));
+    return off;
+  }
+};
+
+}  // namespace ssgpu
+
+using namespace ssgpu;
+
+extern "C" int ssgpu_sym_root(const double* A, int n, double* out) {
+  SS_ARG(A && out && n >= 1, "sym_root: bad arguments");
+  sym_root_host(A, n, out);
+  return SSGPU_OK;
+}
+
+extern "C" int ssgpu_FastSmootherC(const double* y, int N, int p, int nsim, int m, int r, const double* a,
+                                   const double* P_inf, const double* P_star, const double* Z, int nZ, const double* T,
+                                   int nT, const double* R, int nR, const double* Q, int nQ, int initialisation_steps,
+                                   int transposed_state, double* a_smooth, double* a_t, double* eta) {
+  SS_ARG(y && a && P_inf && P_star && Z && T && R && Q, "null pointer argument");
+  SS_ARG(N >= 1 && p >= 1 && m >= 1 && r >= 1 && nsim >= 1, "N, p, m, r, nsim must be positive");
+  SS_ARG(m <= SSGPU_MAX_M, "state dimension m exceeds SSGPU_MAX_M");
+  SS_ARG((nZ == 1 || nZ == N) && (nT == 1 || nT == N) && (nR == 1 || nR == N) && (nQ == 1 || nQ == N),
+         "system matrices must have 1 or N slices");
+  SS_TRY(ensure_device());
+  cudaStream_t st = lib_stream();
+  HostPack pk;
+  const size_t oa = pk.add(a, m), opi = pk.add(P_inf, (size_t)m * m), ops = pk.add(P_star, (size_t)m * m);
+  const size_t oz = pk.add(Z, (size_t)p * m * nZ), ot = pk.add(T, (size_t)m * m * nT);
+  const size_t orr = pk.add(R, (size_t)m * r * nR), oq = pk.add(Q, (size_t)r * r * nQ);
+  DevBuf mats;
+  SS_TRY(upload(mats, pk.buf.data(), pk.buf.size(), st));
+  const double* d = mats.as<double>();
+  DModel md{};
+  md.N = N; md.p = p; md.m = m; md.r = r;
+  md.a = dmat3(d + oa, m, 1, 1);
+  md.P_inf = dmat3(d + opi, m, m, 1);
+  md.P_star = dmat3(d + ops, m, m, 1);
+  md.Z = dmat3(d + oz, p, m, nZ);
+  md.T = dmat3(d + ot, m, m, nT);
+  md.R = dmat3(d + orr, m, r, nR);
+  md.Q = dmat3(d + oq, r, r, nQ);
+
+  const size_t Np = (size_t)N * p, ns = (size_t)nsim;
+  auto pad = [](size_t n) { return (n + 31) / 32 * 32; };
+  // gain sequence shared by all draws
+  const bool qtr_tv = nQ > 1 || nR > 1;
+  DevBuf gb;
+  SS_TRY(gb.alloc(sizeof(double) * (pad(Np) * 2 + pad(Np * m) * 2 + pad((size_t)(qtr_tv ? N : 1) * r * m)), st));
+  KalmanScratch g{};
+  double* base = gb.as<double>();
+  g.F1 = base; base += pad(Np);
+  g.code = reinterpret_cast<int*>(base); base += pad(Np);
+  g.K0 = base; base += pad(Np * m);
+  g.K1 = base; base += pad(Np * m);
+  g.QtR = base;
+  SS_TRY(launch_gains_generic(md, initialisation_steps, &g, st));
+  // per-draw arrays in the draw-contiguous layout
+  DevBuf yR, yN, vN, aN, eN, outR;
+  SS_TRY(upload(yR, y, Np * ns, st));
+  SS_TRY(yN.alloc(sizeof(double) * Np * ns, st));
+  SS_TRY(launch_permute_tks(yR.as<double>(), yN.as<double>(), N, p, nsim, false, st));
+  SS_TRY(vN.alloc(sizeof(double) * Np * ns, st));
+  SS_TRY(aN.alloc(sizeof(double) * (size_t)N * m * ns, st));
+  SS_TRY(eN.alloc(sizeof(double) * (size_t)N * r * ns, st));
+  FsArgs A{};
+  A.S = nsim; A.N = N; A.p = p; A.m = m; A.r = r;
+  A.init_steps = initialisation_steps;
+  A.qtr_tv = qtr_tv;
+  A.a0 = md.a.p; A.P_inf = md.P_inf.p; A.P_star = md.P_star.p;
+  A.Z = md.Z; A.T = md.T; A.R = md.R;
+  A.g = g;
+  A.y = yN.as<double>(); A.v = vN.as<double>(); A.a_smooth = aN.as<double>(); A.eta = eN.as<double>();
+  SS_TRY(launch_fs_draws(A, st));
+  SS_TRY(outR.alloc(sizeof(double) * (size_t)N * (m > r ? m : r) * ns, st));
+  if (a_smooth) {
+    SS_TRY(launch_permute_tks(aN.as<double>(), outR.as<double>(), N, m, nsim, true, st));
+    SS_CUDA(cudaMemcpyAsync(a_smooth, outR.get(), sizeof(double) * (size_t)N * m * ns, cudaMemcpyDeviceToHost, st));
+  }
+  if (transposed_state && a_t) {
+    SS_TRY(launch_permute_at(aN.as<double>(), outR.as<double>(), N, m, nsim, st));
+    SS_CUDA(cudaMemcpyAsync(a_t, outR.get(), sizeof(double) * (size_t)N * m * ns, cudaMemcpyDeviceToHost, st));
+  }
+  if (eta) {
+    SS_TRY(launch_permute_tks(eN.as<double>(), outR.as<double>(), N, r, nsim, true, st));
+    SS_CUDA(cudaMemcpyAsync(eta, outR.get(), sizeof(double) * (size_t)N * r * ns, cudaMemcpyDeviceToHost, st));
+  }
+  SS_CUDA(cudaStreamSynchronize(st));
+  return SSGPU_OK;
+}
+
+extern "C" int ssgpu_SimulateC(int nsim, int repeat_Q, int N, int p, int m, int rR, int r, int mP, const double* a,
+                               const double* Z, int nZ, const double* T, int nT, const double* R, int nR,
+                               const double* Q, int nQ, const double* P_star, int draw_initial, int eta_only,
+                               int transposed_state, const double* draws, long long n_draws, const double* Q_root,
+                               const double* P_root, double* y, double* a_out, double* a_t, double* eta) {
+  SS_ARG(nsim >= 1 && repeat_Q >= 1 && N >= 1 && r >= 1 && m >= 1, "nsim, repeat_Q, N, r, m must be positive");
+  SS_ARG(Q && draws, "null pointer argument");
+  SS_ARG(nQ == 1 || nQ == N, "Q must have 1 or N slices");
+  const int r_tot = r * repeat_Q;
+  const size_t ns = (size_t)nsim, total = (size_t)r_tot * ns;
+  // the reference draws the initial state whenever draw_initial is set, eta_only or not (src/SimulateC.cpp:72-76)
+  const size_t n_init = draw_initial ? (size_t)m * ns : 0;
+  if (n_draws != (long long)(n_init + total * N)) {
+    set_error("SimulateC: n_draws does not match the reference's consumption ([m*nsim] + N*r_tot*nsim)");
+    return SSGPU_E_DRAWS;
+  }
+  if (!eta_only) {
+    SS_ARG(a && Z && T && R, "null pointer argument");
+    SS_ARG(p >= 1 && m <= SSGPU_MAX_M, "p, m out of range");
+    SS_ARG(rR == r_tot, "R must have r * repeat_Q columns");
+    SS_ARG((nZ == 1 || nZ == N) && (nT == 1 || nT == N) && (nR == 1 || nR == N),
+           "system matrices must have 1 or N slices");
+    SS_ARG(!draw_initial || P_root || (P_star && mP == m), "draw_initial needs an m x m P_star");
+  }
+  SS_TRY(ensure_device());
+  cudaStream_t st = lib_stream();
+  // symmetric roots (host, once) unless supplied
+  std::vector<double> qroot((size_t)r * r * nQ), proot;
+  for (int i = 0; i < nQ; i++) {
+    double* dst = qroot.data() + (size_t)i * r * r;
+    if (Q_root)
+      std::memcpy(dst, Q_root + (size_t)i * r * r, sizeof(double) * r * r);
+    else
+      sym_root_host(Q + (size_t)i * r * r, r, dst);
+  }
+  HostPack pk;
+  const size_t oq = pk.add(qroot.data(), qroot.size());
+  size_t oa = 0, oz = 0, ot = 0, orr = 0, op = 0;
+  if (!eta_only) {
+    oa = pk.add(a, m);
+    oz = pk.add(Z, (size_t)p * m * nZ);
+    ot = pk.add(T, (size_t)m * m * nT);
+    orr = pk.add(R, (size_t)m * rR * nR);
+    if (draw_initial) {
+      proot.resize((size_t)m * m);
+      if (P_root)
+        std::memcpy(proot.data(), P_root, sizeof(double) * m * m);
+      else
+        sym_root_host(P_star, m, proot.data());
+      op = pk.add(proot.data(), proot.size());
+    }
+  }
+  DevBuf mats, dr, yN, aN, eN, outR;
+  SS_TRY(upload(mats, pk.buf.data(), pk.buf.size(), st));
+  SS_TRY(upload(dr, draws, (size_t)n_draws, st));
+  const double* d = mats.as<double>();
+  SimArgs A{};
+  A.S = nsim; A.N = N; A.p = eta_only ? 1 : p; A.m = eta_only ? 1 : m; A.rR = rR; A.r = r; A.repeat_Q = repeat_Q;
+  A.nQ = nQ; A.draw_initial = draw_initial; A.eta_only = eta_only;
+  A.Q_root = d + oq;
+  A.d0 = dr.as<double>();
+  A.dt = dr.as<double>() + n_init;
+  size_t biggest = (size_t)N * r_tot * ns;
+  if (!eta_only) {
+    A.a0 = d + oa;
+    A.Z = dmat3(d + oz, p, m, nZ);
+    A.T = dmat3(d + ot, m, m, nT);
+    A.R = dmat3(d + orr, m, rR, nR);
+    A.P_root = d + op;
+    SS_TRY(yN.alloc(sizeof(double) * (size_t)N * p * ns, st));
+    SS_TRY(aN.alloc(sizeof(double) * (size_t)N * m * ns, st));
+    A.y = yN.as<double>();
+    A.a = aN.as<double>();
+    if ((size_t)N * m * ns > biggest) biggest = (size_t)N * m * ns;
+    if ((size_t)N * p * ns > biggest) biggest = (size_t)N * p * ns;
+  }
+  SS_TRY(eN.alloc(sizeof(double) * (size_t)N * r_tot * ns, st));
+  A.eta = eN.as<double>();
+  SS_TRY(launch_simulate(A, st));
+  SS_TRY(outR.alloc(sizeof(double) * biggest, st));
+  if (eta) {
+    SS_TRY(launch_permute_tks(eN.as<double>(), outR.as<double>(), N, r_tot, nsim, true, st));
+    SS_CUDA(cudaMemcpyAsync(eta, outR.get(), sizeof(double) * (size_t)N * r_tot * ns, cudaMemcpyDeviceToHost, st));
+  }
+  if (!eta_only) {
+    if (y) {
+      SS_TRY(launch_permute_tks(yN.as<double>(), outR.as<double>(), N, p, nsim, true, st));
+      SS_CUDA(cudaMemcpyAsync(y, outR.get(), sizeof(double) * (size_t)N * p * ns, cudaMemcpyDeviceToHost, st));
+    }
+    if (a_out) {
+      SS_TRY(launch_permute_tks(aN.as<double>(), outR.as<double>(), N, m, nsim, true, st));
+      SS_CUDA(cudaMemcpyAsync(a_out, outR.get(), sizeof(double) * (size_t)N * m * ns, cudaMemcpyDeviceToHost, st));
+    }
+    if (transposed_state && a_t) {
+      SS_TRY(launch_permute_at(aN.as<double>(), outR.as<double>(), N, m, nsim, st));
+      SS_CUDA(cudaMemcpyAsync(a_t, outR.get(), sizeof(double) * (size_t)N * m * ns, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  SS_CUDA(cudaStreamSynchronize(st));
+  return SSGPU_OK;
+}
+
+extern "C" int ssgpu_ExtractComponentC(const double* a, int m, int nsim, int N, const double* Z, int p, int nZ,
+                                       double* out) {
+  SS_ARG(a && Z && out, "null pointer argument");
+  SS_ARG(m >= 1 && nsim >= 1 && N >= 1 && p >= 1 && (nZ == 1 || nZ == N), "bad dimensions");
+  SS_TRY(ensure_device());
+  cudaStream_t st = lib_stream();
+  DevBuf aD, zD, oN, oR;
+  const size_t ns = (size_t)nsim;
+  SS_TRY(upload(aD, a, (size_t)m * ns * N, st));
+  SS_TRY(upload(zD, Z, (size_t)p * m * nZ, st));
+  SS_TRY(oN.alloc(sizeof(double) * (size_t)N * p * ns, st));
+  SS_TRY(oR.alloc(sizeof(double) * (size_t)N * p * ns, st));
+  SS_TRY(launch_extract(aD.as<double>(), 0, dmat3(zD.as<double>(), p, m, nZ), m, p, nsim, N, oN.as<double>(), st));
+  SS_TRY(launch_permute_tks(oN.as<double>(), oR.as<double>(), N, p, nsim, true, st));
+  SS_CUDA(cudaMemcpyAsync(out, oR.get(), sizeof(double) * (size_t)N * p * ns, cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  return SSGPU_OK;
+}

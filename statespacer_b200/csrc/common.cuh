@@ -106,8 +106,44 @@ class DevBuf {
 // (out_loglik[e]); otherwise B = V = 1 and every non-null member of kout (DEVICE pointers) is filled.
 int launch_fwd_generic(const DModel& md, const double* y, long long B, int V, double* out_loglik,
                        const ssgpu_kalman_out* kout, const KalmanScratch* scratch, cudaStream_t st);
+int launch_gains_generic(const DModel& md, int init_steps, const KalmanScratch* scratch, cudaStream_t st);
 int launch_bwd_generic(const DModel& md, const ssgpu_kalman_out* kout, const KalmanScratch* scratch,
                        cudaStream_t st);
+
+// ---- simulation smoother (sim.cu) --------------------------------------------------------------
+struct SimArgs {
+  int S, N, p, m, rR, r, repeat_Q, nQ;
+  int draw_initial, eta_only;
+  const double* a0;
+  DMat Z, T, R;
+  const double* Q_root;  // r x r x nQ
+  const double* P_root;  // m x m
+  const double* d0;      // [k + m*s]
+  const double* dt;      // [t][kk + r_tot*s]
+  double *y, *a, *eta;   // native layouts, may be null
+};
+
+struct FsArgs {
+  int S, N, p, m, r, init_steps, qtr_tv;
+  const double* a0;
+  const double* P_inf;
+  const double* P_star;
+  DMat Z, T, R;
+  KalmanScratch g;   // code, F1, K0, K1, QtR
+  const double* y;   // native [(t*p+j)*S + s]
+  double* v;         // scratch, native [(t*p+j)*S + s]
+  double* a_smooth;  // native [(t*m+k)*S + s]; holds r_t between the backward and the last pass
+  double* eta;       // native [(t*r+kk)*S + s]
+};
+
+int launch_simulate(const SimArgs& A, cudaStream_t st);
+int launch_fs_draws(const FsArgs& A, cudaStream_t st);
+int launch_extract(const double* a, int a_native, const DMat& Z, int m, int p, int S, int N, double* out,
+                   cudaStream_t st);
+// native X[(t*K+k)*S+s] <-> R array [t + N*(k + K*s)]
+int launch_permute_tks(const double* src, double* dst, int N, int K, long long S, bool to_r, cudaStream_t st);
+// native X[(t*m+k)*S+s] -> a_t [k + m*(s + S*t)]
+int launch_permute_at(const double* src, double* dst, int N, int m, long long S, cudaStream_t st);
 
 // Column-per-thread register kernel (loglik_cols.cu)
 bool cols_eligible(const DModel& md, std::string* why);

@@ -1,9 +1,11 @@
 // Generic forward filter: univariate-treatment Kalman filter with exact diffuse initialisation,
 // one CTA per evaluation, any (m <= 64, p, r), time-varying or per-evaluation system matrices.
 //
-// Restates the recursion of src/LogLikC.cpp:68-208 (KALMAN = false) and of the forward loop of
-// src/KalmanC.cpp:122-409 (KALMAN = true, which additionally stores every intermediate the backward
-// pass and the R caller need).  The covariance lives in shared memory; work inside a CTA is
+// Restates the recursion of src/LogLikC.cpp:68-208 (MODE_LOGLIK), of the forward loop of
+// src/KalmanC.cpp:122-409 (MODE_KALMAN, which additionally stores every intermediate the backward
+// pass and the R caller need) and the y-independent part of src/FastSmootherC.cpp:103-252
+// (MODE_GAINS: regime chosen by index < initialisation_steps, gains written once for all draws).
+// The arithmetic order is the pinned one of oracle/kalman_c.c (explicit fma chains, k ascending).  The covariance lives in shared memory; work inside a CTA is
 // element-parallel (thread e owns elements e, e+NT, ... of every m x m object), all scalar decisions
 // (F_inf / F_star thresholds, P_inf ~ 0 test) are block-uniform.
 //
@@ -24,7 +26,10 @@ struct FwdArgs {
   double* out;  // [E] loglik / N (LOGLIK mode)
   ssgpu_kalman_out k;  // device pointers (KALMAN mode)
   KalmanScratch s;
+  int init_steps;  // MODE_GAINS: src/FastSmootherC.cpp:147
 };
+
+constexpr int MODE_LOGLIK = 0, MODE_KALMAN = 1, MODE_GAINS = 2;
 
 __device__ __forceinline__ void load_mat(double* dst, const double* blk, int diag, int rows, int cols, int tid,
                                          int NT) {
@@ -59,8 +64,9 @@ __device__ __forceinline__ void mm_nt(double* C, const double* A, const double* 
   }
 }
 
-template <bool KALMAN>
+template <int MODE>
 __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
+  constexpr bool KALMAN = MODE == MODE_KALMAN, GAINS = MODE == MODE_GAINS;
   extern __shared__ double sm[];
   const DModel& md = A.md;
   const int m = md.m, p = md.p, r = md.r, N = md.N;
@@ -81,8 +87,10 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
   double* av2 = av + m;
   double* Ms = av2 + m;
   double* Mi = Ms + m;
+  double* k0v = Mi + m;
+  double* k1v = k0v + m;
 
-  load_mat(av, md.a.block(b, v, 0), 0, m, 1, tid, NT);
+  if (!GAINS) load_mat(av, md.a.block(b, v, 0), 0, m, 1, tid, NT);
   load_mat(Pi, md.P_inf.block(b, v, 0), md.P_inf.diag, m, m, tid, NT);
   load_mat(Ps, md.P_star.block(b, v, 0), md.P_star.diag, m, m, tid, NT);
   load_mat(Zs, md.Z.block(b, v, 0), 0, p, m, tid, NT);
@@ -95,7 +103,7 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
     for (int q = tid; q < mm; q += NT) ok &= (fabs(Pi[q]) < kEps) ? 1 : 0;
     return __syncthreads_and(ok);
   };
-  bool init = !pinf_small();
+  bool init = GAINS ? true : !pinf_small();
 
   // Q_t R_t' (r x m, into W) then R_t (Q_t R_t')  -> RQR   (src/KalmanC.cpp:108,385)
   auto build_rqr = [&](int t) {
@@ -110,7 +118,7 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
         for (int l = 0; l < r; l++) acc = fma(Qb[k + l * r], mat_get(Rb, md.R.diag, m, j, l), acc);
       }
       W[q] = acc;
-      if (KALMAN) A.s.QtR[(long long)((md.Q.tv() || md.R.tv()) ? t : 0) * r * m + q] = acc;
+      if (KALMAN || GAINS) A.s.QtR[(long long)((md.Q.tv() || md.R.tv()) ? t : 0) * r * m + q] = acc;
     }
     __syncthreads();
     for (int q = tid; q < mm; q += NT) {
@@ -182,8 +190,9 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
 
     for (int j = 0; j < p; j++) {
       const int index = t * p + j;
-      const double yv = A.y[((long long)t * p + j) * A.B + b];
-      if (isnan(yv)) {  // src/LogLikC.cpp:88-90, src/KalmanC.cpp:193-211
+      const double yv = GAINS ? 0.0 : A.y[((long long)t * p + j) * A.B + b];
+      if (GAINS) init = index < A.init_steps;
+      if (!GAINS && isnan(yv)) {  // src/LogLikC.cpp:88-90, src/KalmanC.cpp:193-211
         if (KALMAN) {
           if (init) init_steps++;
           if (tid == 0) {
@@ -210,14 +219,14 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
         const double z = Zs[j + k * p];
         F_star = fma(z, Ms[k], F_star);
         F_inf = fma(z, Mi[k], F_inf);
-        za = fma(z, av[k], za);
+        if (!GAINS) za = fma(z, av[k], za);
       }
       int code = 0;
       double F1 = 0.0, F2 = 0.0, vv = 0.0, ll = nan("");
       if (init) {
         if (KALMAN) init_steps++;
         if (F_inf < kEps) {
-          if (F_star >= kEps) code = 1;
+          if (!(F_star < kEps)) code = 1;  // NaN takes the update branch, like the reference's else
         } else {
           code = 2;
         }
@@ -240,39 +249,41 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
         ll = kLogConst - log(F_inf) / 2;
         loglik += ll;
       }
-      if (KALMAN && tid == 0) {
-        if (A.k.loglik) A.k.loglik[index] = ll;
+      if ((KALMAN || GAINS) && tid == 0) {
+        if (KALMAN && A.k.loglik) A.k.loglik[index] = ll;
         A.s.code[index] = code | (init ? 256 : 0);
         A.s.F1[index] = F1;
-        A.s.F2[index] = F2;
-        A.s.v[index] = vv;
-      }
-      if (code == 0) {
-        __syncthreads();  // Ms/Mi are rewritten by the next step
-        continue;
-      }
-      // K0 = M F1 (code 1: M*, code 2: M_inf); K1 = M* F1 + M_inf F2 (code 2 only)
-      if (KALMAN) {
-        for (int i = tid; i < m; i += NT) {
-          A.s.K0[(long long)index * m + i] = (code == 1 ? Ms[i] : Mi[i]) * F1;
-          A.s.K1[(long long)index * m + i] = code == 2 ? Ms[i] * F1 + Mi[i] * F2 : 0.0;
+        if (KALMAN) {
+          A.s.F2[index] = F2;
+          A.s.v[index] = vv;
         }
       }
+      // K0 = M F1 (code 1: M*, code 2: M_inf); K1 = M* F1 + M_inf F2 (code 2 only)
+      for (int i = tid; i < m; i += NT) {
+        const double k0 = code == 0 ? 0.0 : (code == 1 ? Ms[i] : Mi[i]) * F1;
+        const double k1 = code == 2 ? Ms[i] * F1 + Mi[i] * F2 : 0.0;
+        k0v[i] = k0;
+        k1v[i] = k1;
+        if (KALMAN || GAINS) {
+          A.s.K0[(long long)index * m + i] = k0;
+          A.s.K1[(long long)index * m + i] = k1;
+        }
+      }
+      __syncthreads();
+      if (code == 0) continue;  // block-uniform
       for (int q = tid; q < mm; q += NT) {
         const int i = q % m, c = q / m;
         if (code == 1) {
-          Ps[q] = Ps[q] - Ms[i] * (Ms[c] * F1);
+          Ps[q] = Ps[q] - Ms[i] * k0v[c];
         } else {
-          const double k0 = Mi[c] * F1;
-          const double k1 = Ms[c] * F1 + Mi[c] * F2;
-          Ps[q] = (Ps[q] - Ms[i] * k0) - Mi[i] * k1;
-          Pi[q] = Pi[q] - Mi[i] * k0;
+          Ps[q] = (Ps[q] - Ms[i] * k0v[c]) - Mi[i] * k1v[c];
+          Pi[q] = Pi[q] - Mi[i] * k0v[c];
         }
       }
-      __syncthreads();  // all reads of av (za) are done before av is updated
-      for (int i = tid; i < m; i += NT) av[i] = av[i] + ((code == 1 ? Ms[i] : Mi[i]) * F1) * vv;
+      if (!GAINS)
+        for (int i = tid; i < m; i += NT) av[i] = fma(k0v[i], vv, av[i]);
       __syncthreads();
-      if (code == 2 && j < p - 1) init = !pinf_small();  // src/LogLikC.cpp:157-159
+      if (!GAINS && code == 2 && j < p - 1) init = !pinf_small();  // src/LogLikC.cpp:157-159
     }
 
     if (KALMAN) {
@@ -291,22 +302,25 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
 
     // transition to the next time point (src/LogLikC.cpp:200-207; KalmanC also forecasts after t = N-1)
     if (t < N - 1 || KALMAN) {
-      for (int i = tid; i < m; i += NT) {
-        double acc = 0.0;
-        for (int k = 0; k < m; k++) acc = fma(Ts[i + k * m], av[k], acc);
-        av2[i] = acc;
-      }
+      if (!GAINS)
+        for (int i = tid; i < m; i += NT) {
+          double acc = 0.0;
+          for (int k = 0; k < m; k++) acc = fma(Ts[i + k * m], av[k], acc);
+          av2[i] = acc;
+        }
       mm_nn(W, Ts, Ps, m, tid, NT);
       __syncthreads();
       mm_nt(Ps, W, Ts, RQR, m, tid, NT);
-      for (int i = tid; i < m; i += NT) av[i] = av2[i];
+      if (!GAINS)
+        for (int i = tid; i < m; i += NT) av[i] = av2[i];
       __syncthreads();
+      if (GAINS) init = (t * p + p - 1) < A.init_steps;  // src/FastSmootherC.cpp:248
       if (init) {
         mm_nn(W, Ts, Pi, m, tid, NT);
         __syncthreads();
         mm_nt(Pi, W, Ts, nullptr, m, tid, NT);
         __syncthreads();
-        if (t < N - 1) init = !pinf_small();
+        if (!GAINS && t < N - 1) init = !pinf_small();
       }
       if (KALMAN && t == N - 1) {
         const ssgpu_kalman_out& K = A.k;
@@ -325,7 +339,7 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
   if (tid == 0) {
     if (KALMAN) {
       if (A.k.initialisation_steps) *A.k.initialisation_steps = init_steps;
-    } else {
+    } else if (!GAINS) {
       A.out[e] = (non_init == F_eq0) ? nan("") : loglik / N;  // src/LogLikC.cpp:211-214
     }
   }
@@ -336,7 +350,7 @@ static size_t fwd_smem_bytes(const DModel& md) {
   size_t wsz = (size_t)m * m;
   if ((size_t)m * r > wsz) wsz = (size_t)m * r;
   if ((size_t)p * m > wsz) wsz = (size_t)p * m;
-  return sizeof(double) * (4 * (size_t)m * m + wsz + (size_t)p * m + 4 * (size_t)m);
+  return sizeof(double) * (4 * (size_t)m * m + wsz + (size_t)p * m + 6 * (size_t)m);
 }
 
 static int pick_threads(int m) {
@@ -363,14 +377,33 @@ int launch_fwd_generic(const DModel& md, const double* y, long long B, int V, do
     SS_ARG(B == 1 && V == 1 && scratch, "KalmanC runs one series per call");
     A.k = *kout;
     A.s = *scratch;
-    SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fwd_generic_kernel<true><<<1, nt, smem, st>>>(A);
+    SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<MODE_KALMAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    fwd_generic_kernel<MODE_KALMAN><<<1, nt, smem, st>>>(A);
     set_last_kernel("fwd_generic_kernel<KALMAN>");
   } else {
-    SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fwd_generic_kernel<false><<<(unsigned)E, nt, smem, st>>>(A);
+    SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<MODE_LOGLIK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    fwd_generic_kernel<MODE_LOGLIK><<<(unsigned)E, nt, smem, st>>>(A);
     set_last_kernel("fwd_generic_kernel<LOGLIK>");
   }
+  count_launch();
+  SS_CUDA(cudaGetLastError());
+  return SSGPU_OK;
+}
+
+// FastSmootherC gain sequence: code / F1 / K0 / K1 / QtR of `scratch` (F2, v unused)
+int launch_gains_generic(const DModel& md, int init_steps, const KalmanScratch* scratch, cudaStream_t st) {
+  FwdArgs A{};
+  A.md = md;
+  A.B = 1;
+  A.V = 1;
+  A.s = *scratch;
+  A.init_steps = init_steps;
+  const size_t smem = fwd_smem_bytes(md);
+  SS_ARG(smem <= 227 * 1024, "generic filter: model does not fit in shared memory (m, p or r too large)");
+  SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<MODE_GAINS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fwd_generic_kernel<MODE_GAINS><<<1, pick_threads(md.m), smem, st>>>(A);
   count_launch();
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;

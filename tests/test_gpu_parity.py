@@ -1,0 +1,337 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU checkers.  Needs a B200: -m gpu.
+
+Tolerances: 1e-9 relative on loglikelihoods and on smoothed states / variances (north star);
+simulation smoother draws bit-exact against the pinned-order C oracle given the same variates."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import Case, DNS_PARAM, load_fed, load_series, random_model, simulate_y
+from oracle import cport, kalman_np, ref
+from statespacer_b200 import api, native, sysmat
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
+    if a.size == 0:
+        return 0.0
+    scale = max(1.0, float(np.nanmax(np.abs(b), initial=0.0)))
+    return float(np.nanmax(np.abs(a - b), initial=0.0)) / scale
+
+
+# ---- LogLikC ------------------------------------------------------------------------------------------
+def test_loglik_golden(kats):
+    for c in kats:
+        got = api.LogLikC(*c.args())
+        assert abs(got - c.expect) < 6e-7 * max(1, abs(c.expect)), (c.name, got)
+        assert abs(got - cport.LogLikC(*c.args())) <= RTOL * max(1, abs(got)), c.name
+
+
+SHAPES = [
+    dict(m=1, p=1, d=0, tv=()),
+    dict(m=2, p=1, d=1, tv=()),
+    dict(m=5, p=2, d=2, tv=("Z",)),
+    dict(m=8, p=3, d=3, tv=("T", "Q")),
+    dict(m=6, p=2, d=0, tv=("R",)),
+    dict(m=20, p=4, d=2, tv=("Z", "T", "R", "Q")),
+    dict(m=40, p=2, d=1, tv=()),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_loglik_random_models(shape):
+    for seed in range(3):
+        rng = np.random.default_rng(100 + seed)
+        N = 35
+        sm = random_model(rng, shape["m"], shape["p"], d=shape["d"], tv=shape["tv"], N=N)
+        c = Case("r", simulate_y(rng, sm, N, missing=0.15), sm)
+        want = cport.LogLikC(*c.args())
+        got = api.LogLikC(*c.args())
+        assert abs(got - want) <= RTOL * max(1, abs(want)), (shape, seed, got, want)
+        # mask given separately from the values (R passes y_isna next to y)
+        y0 = np.where(c.isna, 0.0, c.y)
+        assert api.LogLikC(y0, c.isna, *sm.args()) == got
+
+
+def test_loglik_edge_cases():
+    sm = sysmat.nile_local_level(2.0, 1.0)
+    y = np.full((6, 1), np.nan)
+    assert math.isnan(api.LogLikC(y, np.isnan(y), *sm.args()))           # all missing -> NA (src/LogLikC.cpp:211)
+    y1 = np.array([[3.0]])
+    assert abs(api.LogLikC(y1, np.isnan(y1), *sm.args()) - cport.LogLikC(y1, np.isnan(y1), *sm.args())) < 1e-12
+    sm0 = sysmat.nile_local_level(0.0, 0.0)                               # F = 0 everywhere after init -> NA
+    y2 = np.ones((5, 1))
+    assert math.isnan(api.LogLikC(y2, np.isnan(y2), *sm0.args())) == math.isnan(
+        cport.LogLikC(y2, np.isnan(y2), *sm0.args()))
+    with pytest.raises(ValueError):
+        api.LogLikC(np.ones((5, 2)), np.zeros((5, 2), bool), *sm.args())
+    with pytest.raises(native.SsgpuError):
+        big = random_model(np.random.default_rng(0), 65, 1)
+        api.LogLikC(np.ones((3, 1)), np.zeros((3, 1), bool), *big.args())
+
+
+# ---- KalmanC ------------------------------------------------------------------------------------------
+KALMAN_KEYS = ("loglik", "a_pred", "a_fil", "a_smooth", "P_pred", "P_fil", "V", "P_inf_pred", "P_star_pred",
+               "P_inf_fil", "P_star_fil", "yfit", "v", "eta", "Fmat", "eta_var", "a_fc", "P_inf_fc", "P_star_fc",
+               "P_fc", "r_vec", "Nmat")
+
+
+def _kalman_check(c, tol=RTOL):
+    want = ref.KalmanC(*c.args(), False) if ref.available() else kalman_np.KalmanC(*c.args(), False)
+    got = api.KalmanC(*c.args(), False)
+    assert got["initialisation_steps"] == want["initialisation_steps"]
+    for k in KALMAN_KEYS:
+        e = rel(got[k], want[k])
+        assert e <= tol, (c.name, k, e)
+
+
+def test_kalman_golden_models(kats):
+    for c in kats:
+        _kalman_check(c)
+    air = np.log(load_series("airpassengers.txt"))
+    def raw(t):
+        return -t / math.sqrt(1 - t * t)
+    sm = sysmat.airline([0.5 * math.log(0.001347882), raw(-0.55694248), raw(-0.40188859)])
+    got = api.KalmanC(air[:, None], np.isnan(air[:, None]), *sm.args(), False)
+    assert got["initialisation_steps"] == 13
+    assert abs(np.nansum(got["loglik"]) - 232.750284785) < 2e-5      # docs/articles/boxjenkins.html:269-271
+
+
+@pytest.mark.parametrize("shape", SHAPES[:6])
+def test_kalman_random_models(shape):
+    rng = np.random.default_rng(7)
+    N = 30
+    sm = random_model(rng, shape["m"], shape["p"], d=shape["d"], tv=shape["tv"], N=N)
+    _kalman_check(Case("r", simulate_y(rng, sm, N, missing=0.1), sm), tol=1e-8 if shape["d"] else RTOL)
+
+
+def test_kalman_missing_airline():
+    """SURVEY.md appendix C probe: airline with 6 NaNs -> initialisation_steps = 19."""
+    air = np.log(load_series("airpassengers.txt")).copy()
+    air[[5, 6, 50, 51, 52, 100]] = np.nan
+    sm = sysmat.airline([0.5 * math.log(0.00135), 0.3, 0.4])
+    c = Case("air-na", air, sm)
+    got = api.KalmanC(*c.args(), False)
+    assert got["initialisation_steps"] == 19
+    assert abs(np.nansum(got["loglik"]) - api.LogLikC(*c.args()) * len(air)) < 1e-9 * 300
+    _kalman_check(c)
+
+
+# ---- batched loglikelihood ---------------------------------------------------------------------------
+def _bsm_batch(rng, B, N, V, missing):
+    thetas = 0.5 * np.log([1.0, 0.1, 0.01, 0.05]) + 0.25 * rng.normal(size=(V, B, 4))
+    var = np.exp(2 * thetas)
+    Qd = np.concatenate([var[..., :3], np.repeat(var[..., 3:4], 11, axis=-1)], axis=-1)   # (V, B, 14)
+    Pd = np.zeros((V, B, 14))
+    Pd[..., 0] = var[..., 0]
+    y = np.cumsum(rng.normal(size=(N, B)), axis=0) + 3 * np.sin(np.arange(N) * 2 * np.pi / 12)[:, None]
+    y[rng.uniform(size=y.shape) < missing] = np.nan
+    return thetas, Qd, Pd, y
+
+
+@pytest.mark.parametrize("kernel", ["cols", "generic"])
+def test_batch_config5_shape(kernel):
+    rng = np.random.default_rng(5)
+    B, N, V = 70, 60, 3
+    thetas, Qd, Pd, y = _bsm_batch(rng, B, N, V, 0.05)
+    got = api.loglik_batch(y, sysmat.bsm12(thetas[0, 0]), V=V, Q_diag=Qd, P_star_diag=Pd, kernel=kernel)
+    assert api.last_kernel().startswith("loglik_cols" if kernel == "cols" else "fwd_generic")
+    assert got.shape == (V, B)
+    for v in range(V):
+        for b in range(0, B, 7):
+            sm = sysmat.bsm12(thetas[v, b])
+            want = cport.LogLikC(y[:, b:b + 1], np.isnan(y[:, b:b + 1]), *sm.args())
+            assert abs(got[v, b] - want) <= RTOL * max(1, abs(want)), (v, b, got[v, b], want)
+
+
+@pytest.mark.parametrize("m", list(range(1, 16)))
+def test_batch_cols_every_state_dim(m):
+    rng = np.random.default_rng(40 + m)
+    B, N, p = 9, 25, 1 if m % 3 else 2
+    d = min(m - 1, 2) if m > 1 else 0
+    sm = random_model(rng, m, p, d=d, N=N)
+    y = np.stack([simulate_y(rng, sm, N, missing=0.1) for _ in range(B)], axis=2)       # (N, p, B)
+    # per-series dense Q and P_star, a, P_inf
+    Qb = np.stack([sm.Q[:, :, 0] * (1 + 0.1 * b) for b in range(B)])
+    Pb = np.stack([sm.P_star * (1 + 0.05 * b) for b in range(B)])
+    ab = np.stack([sm.a + 0.01 * b for b in range(B)])
+    got = api.loglik_batch(y, sm, Q=Qb, P_star=Pb, a=ab, kernel="cols")
+    gen = api.loglik_batch(y, sm, Q=Qb, P_star=Pb, a=ab, kernel="generic")
+    for b in range(B):
+        smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=Qb[b][:, :, None], a=ab[b], P_inf=sm.P_inf, P_star=Pb[b])
+        yb = y[:, :, b]
+        want = cport.LogLikC(yb, np.isnan(yb), *smb.args())
+        tol = (1e-8 if d else RTOL) * max(1, abs(want))
+        assert abs(got[b] - want) <= tol, (m, b, got[b], want)
+        assert abs(gen[b] - want) <= tol, (m, b, gen[b], want)
+
+
+def test_batch_multivariate_dns():
+    """Config 3 shape (p = 8, m = 14) replicated with noise; all matrices shared."""
+    fed = load_fed()
+    sm, _ = sysmat.dns_yield_curve(DNS_PARAM)
+    rng = np.random.default_rng(1)
+    B = 12
+    y = np.stack([fed + (0.01 * rng.normal(size=fed.shape) if b else 0.0) for b in range(B)], axis=2)
+    y[rng.uniform(size=y.shape) < 0.03] = np.nan
+    y[:, :, 0] = fed
+    got = api.loglik_batch(y, sm, kernel="auto")
+    assert api.last_kernel().startswith("loglik_cols")
+    assert abs(got[0] - 7.005830) < 6e-7 * 7                               # docs/articles/selfspec.html:306-307
+    for b in range(B):
+        yb = y[:, :, b]
+        want = cport.LogLikC(yb, np.isnan(yb), *sm.args())
+        assert abs(got[b] - want) <= RTOL * max(1, abs(want)), (b, got[b], want)
+
+
+def test_batch_generic_time_varying_and_per_series():
+    rng = np.random.default_rng(3)
+    N, B, m, p = 20, 6, 7, 2
+    sm = random_model(rng, m, p, d=1, tv=("Z", "T"), N=N)
+    y = np.stack([simulate_y(rng, sm, N, missing=0.1) for _ in range(B)], axis=2)
+    got = api.loglik_batch(y, sm)
+    assert api.last_kernel().startswith("fwd_generic")
+    for b in range(B):
+        want = cport.LogLikC(y[:, :, b], np.isnan(y[:, :, b]), *sm.args())
+        assert abs(got[b] - want) <= 1e-8 * max(1, abs(want))
+
+
+def test_batch_properties_large():
+    """Size-independent properties at a size the oracle would not finish: (i) replicated series give
+    identical values, (ii) scaling y by c and all variances by c^2 shifts loglik by -n_obs*log(c)/N."""
+    rng = np.random.default_rng(9)
+    B, N, V = 20000, 100, 1
+    thetas, Qd, Pd, y = _bsm_batch(rng, 64, N, V, 0.02)
+    reps = B // 64 + 1
+    yB = np.tile(y, (1, reps))[:, :B].copy()
+    QB = np.tile(Qd[0], (reps, 1))[:B].copy()
+    PB = np.tile(Pd[0], (reps, 1))[:B].copy()
+    sm = sysmat.bsm12(thetas[0, 0])
+    got = api.loglik_batch(yB, sm, Q_diag=QB, P_star_diag=PB)
+    assert np.array_equal(got[:64], got[64:128]) and np.array_equal(got[:B % 64], got[B - B % 64:])
+    c = 3.0
+    got_c = api.loglik_batch(c * yB, sm, Q_diag=c * c * QB, P_star_diag=c * c * PB)
+    n_obs = np.sum(~np.isnan(yB), axis=0)
+    assert np.max(np.abs(got_c - (got - n_obs * math.log(c) / N))) < 1e-9 * np.max(np.abs(got))
+    want = cport.LogLikC(y[:, 5:6], np.isnan(y[:, 5:6]), *sysmat.bsm12(thetas[0, 5]).args())
+    assert abs(got[5] - want) <= RTOL * abs(want)
+
+
+# ---- simulation smoother -----------------------------------------------------------------------------
+def _sim_case(rng, m, p, r, N, tv=()):
+    sm = random_model(rng, m, p, r=r, d=0, tv=tv, N=N)
+    return sm
+
+
+@pytest.mark.parametrize("repeat_Q,draw_initial,eta_only,tv", [(1, False, False, ()), (3, True, False, ("T",)),
+                                                               (1, False, True, ()), (2, True, False, ("Z", "R"))])
+def test_simulate_bit_exact(repeat_Q, draw_initial, eta_only, tv):
+    rng = np.random.default_rng(3)
+    N, nsim, r = 15, 37, 2
+    r_tot = r * repeat_Q
+    m, p = 5, 2
+    sm = random_model(rng, m, p, r=r_tot, N=N, tv=tv)
+    A = rng.normal(size=(r, r))
+    Q = A @ A.T + 0.1 * np.eye(r)
+    n = (m * nsim if draw_initial else 0) + N * r_tot * nsim
+    draws = rng.normal(size=n)
+    P = sm.P_star + 0.01 * np.eye(m)
+    Q_root = cport.sym_root(Q)[:, :, None]
+    P_root = cport.sym_root(P)
+    if eta_only:
+        Z = T = R = np.zeros((1, 1, 1))
+        a = np.zeros(1)
+        n = N * r_tot * nsim
+        draws = draws[:n]
+        args = (nsim, repeat_Q, N, a, Z, T, R, Q, np.zeros((1, 1)), False, True, True, draws)
+    else:
+        args = (nsim, repeat_Q, N, sm.a, sm.Z, sm.T, sm.R, Q, P, draw_initial, False, True, draws)
+    want = cport.SimulateC(*args, Q_root=Q_root, P_root=P_root)
+    got = api.SimulateC(*args, Q_root=Q_root, P_root=P_root)
+    keys = ("eta",) if eta_only else ("y", "a", "a_t", "eta")
+    for k in keys:
+        assert np.array_equal(got[k], want[k]), k                         # bit-exact
+    if ref.available():
+        r0 = ref.SimulateC(*args)
+        got2 = api.SimulateC(*args)                                       # library's own Jacobi roots
+        for k in keys:
+            assert rel(got2[k], r0[k]) < 1e-10, k
+
+
+def test_simulate_wrong_draw_count():
+    rng = np.random.default_rng(0)
+    sm = random_model(rng, 3, 1, r=2, N=5)
+    with pytest.raises(native.SsgpuError) as e:
+        api.SimulateC(4, 1, 5, sm.a, sm.Z, sm.T, sm.R, np.eye(2), sm.P_star, False, False, False, np.zeros(7))
+    assert e.value.status == 3
+
+
+@pytest.mark.parametrize("shape", [dict(m=2, p=1, d=1, tv=()), dict(m=5, p=2, d=2, tv=("Z",)),
+                                   dict(m=8, p=3, d=3, tv=("T", "Q")), dict(m=28, p=1, d=0, tv=()),
+                                   dict(m=6, p=2, d=0, tv=("R",))])
+def test_fast_smoother(shape):
+    rng = np.random.default_rng(5)
+    N, nsim = 30, 41
+    sm = random_model(rng, shape["m"], shape["p"], d=shape["d"], tv=shape["tv"], N=N)
+    c = Case("fs", simulate_y(rng, sm, N, missing=0.0), sm)
+    steps = kalman_np.KalmanC(*c.args(), False)["initialisation_steps"]
+    y3 = np.stack([c.y + 0.1 * rng.normal(size=c.y.shape) * (s > 0) for s in range(nsim)], axis=2)
+    want = cport.FastSmootherC(y3, *sm.args(), steps, True)
+    got = api.FastSmootherC(y3, *sm.args(), steps, True)
+    for k in ("a_smooth", "a_t", "eta"):
+        assert np.array_equal(got[k], want[k]), (k, rel(got[k], want[k]))  # bit-exact vs the pinned-order oracle
+    if ref.available():
+        r0 = ref.FastSmootherC(y3, *sm.args(), steps, True)
+        for k in ("a_smooth", "a_t", "eta"):
+            assert rel(got[k], r0[k]) <= (1e-8 if shape["d"] else RTOL), k
+    # reference-internal identity: draw 0 is the data -> KalmanC's smoothed state
+    ks = api.KalmanC(*c.args(), False)
+    assert rel(got["a_smooth"][:, :, 0], ks["a_smooth"]) < 1e-8
+
+
+def test_fast_smoother_airline_sim_smoother_pipeline():
+    """Config 4 in small: SimulateC -> FastSmootherC -> mean correction -> ExtractComponentC
+    (R/SimSmoother.R:53-769) on the airline model, bit-exact against the C oracle."""
+    air = np.log(load_series("airpassengers.txt"))[:, None]
+    sm = sysmat.airline([0.5 * math.log(0.00135), 0.4, 0.55])
+    N, nsim = len(air), 64
+    steps = api.KalmanC(air, np.isnan(air), *sm.args(), False)["initialisation_steps"]
+    rng = np.random.default_rng(4)
+    comp_m = sm.m - 1
+    Qc = sm.Q[1:, 1:, :]
+    draws = rng.normal(size=N * 1 * nsim)
+    Zc, Tc, Rc = sm.Z[:, 1:, :], sm.T[1:, 1:, :], sm.R[1:, 1:, :]
+    Q_root = cport.sym_root(Qc[:, :, 0])[:, :, None]
+    sims = {}
+    for name, mod in (("gpu", api), ("cpu", cport)):
+        s = mod.SimulateC(nsim, 1, N, np.zeros(comp_m), Zc, Tc, Rc, Qc, np.zeros((comp_m, comp_m)), False, False,
+                          True, draws, Q_root=Q_root)
+        fs = mod.FastSmootherC(s["y"], *sm.args(), steps, True)
+        comp = mod.ExtractComponentC(fs["a_t"], sm.Z)
+        sims[name] = (s, fs, comp)
+    for k in ("y", "a", "a_t", "eta"):
+        assert np.array_equal(sims["gpu"][0][k], sims["cpu"][0][k]), k
+    for k in ("a_smooth", "a_t", "eta"):
+        assert np.array_equal(sims["gpu"][1][k], sims["cpu"][1][k]), k
+    assert np.array_equal(sims["gpu"][2], sims["cpu"][2])
+
+
+def test_extract_component():
+    rng = np.random.default_rng(9)
+    m, nsim, N, p = 5, 70, 9, 2
+    a = rng.normal(size=(m, nsim, N))
+    for Z in (rng.normal(size=(p, m, 1)), rng.normal(size=(p, m, N))):
+        assert np.array_equal(api.ExtractComponentC(a, Z), cport.ExtractComponentC(a, Z))
+    with pytest.raises(ValueError):
+        api.ExtractComponentC(a, rng.normal(size=(p, m + 1, 1)))
+
+
+def test_fp64_peak_probe():
+    tf, ms = api.fp64_peak(0, 200, 2)
+    assert 5 < tf < 80 and ms > 0
