@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched Kalman loglikelihood + finite-difference gradient (BASELINE.json config 5).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload per GPU (weak scaling): 125,000 series (1M / 8) of length T = 1000 from the
+local level + slope + trigonometric seasonal (s = 12) model, m = r = 14 incl. the residual state, 13
+exactly-diffuse states; per-series parameters theta_b in R^4; one step = the loglikelihood at theta_b and
+at the 2k = 8 central-difference points (h = 1e-3) for every series = 9 filter runs per series =
+1.125e9 series*timesteps per GPU, plus (N > 1) the NCCL gather of per-series loglik + gradient.
+
+metric   series*timesteps / s, FP64, whole job, inputs resident in HBM (CUDA events on the launch stream)
+e2e      the same through the host-pointer C ABI (ssgpu_loglik_batch): pinned host y / parameters are
+         copied in and the (V, B) result copied out inside the timed region
+roofline dominant kernel loglik_cols_kernel against the FP64 FMA-pipe peak measured in this run by
+         ssgpu_fp64_peak (MEASURED_PEAKS.json carries no FP64 figure), algorithmic flops of SURVEY.md 8d
+cpu_baseline  the reference's own LogLikC.cpp (oracle/_ref, compiled unmodified) on all host cores over a
+         bounded sample of the same workload; --impl reference runs only that and prints its own line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MU = 0.5 * np.log(np.array([1.0, 0.1, 0.01, 0.05]))
+T_STEPS = 1000
+M = 14
+K_PAR = 4
+V = 1 + 2 * K_PAR
+H_FD = 1e-3
+B_PER_GPU = 125_000
+METRIC = "kalman_loglik_series_timesteps_per_s"
+UNIT = "series*timesteps/s"
+
+
+def f_alg(m, p):
+    """Algorithmic flops per series*timestep, dense generic algorithm."""
+    return 4 * m ** 3 + (4 * p + 3) * m ** 2 + 7 * p * m
+
+
+def variants(theta):
+    """(V, B, 4): theta, theta + h e_i, theta - h e_i  (stats::optim central differences, ndeps = 1e-3)."""
+    out = [theta]
+    for i in range(K_PAR):
+        for sgn in (1.0, -1.0):
+            t = theta.copy()
+            t[:, i] += sgn * H_FD
+            out.append(t)
+    return np.stack(out)
+
+
+def diag_params(theta_v):
+    """Q and P_star diagonals (V, B, 14) of the config-5 model from theta (R/Cholesky.R:158: var = exp(2 theta))."""
+    var = np.exp(2 * theta_v)
+    Qd = np.concatenate([var[..., :3], np.repeat(var[..., 3:4], 11, axis=-1)], axis=-1)
+    Pd = np.zeros_like(Qd)
+    Pd[..., 0] = var[..., 0]
+    return np.ascontiguousarray(Qd), np.ascontiguousarray(Pd)
+
+
+def config(n_gpus, B, extra=None):
+    c = {"workload": "config5: local level + slope + trig seasonal(12), m=r=14, d=13 diffuse, T=1000, "
+                     "loglik + central-difference gradient (9 parameter vectors per series)",
+         "series_per_gpu": B, "series_total": B * n_gpus, "timesteps": T_STEPS, "param_vectors": V,
+         "l2": "inputs larger than L2 (y = %.2f GB per GPU), no flush" % (B * T_STEPS * 8 / 1e9),
+         "parallelism": f"series sharded over {n_gpus} GPU(s), no data-path collective"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---- the reference / CPU arm ----------------------------------------------------------------------------
+def cpu_sample(n_series, seed=0):
+    """A bounded sample of the workload in the CPU checkers' layout."""
+    from statespacer_b200 import sysmat
+    rng = np.random.default_rng(20240501 + seed)
+    theta = MU + 0.25 * rng.normal(size=(n_series, 4))
+    sm = sysmat.bsm12(MU)
+    Tm, Zm = sm.T[:, :, 0], sm.Z[0, :, 0]
+    var = np.exp(2 * theta)
+    sd = np.sqrt(np.concatenate([var[:, :3], np.repeat(var[:, 3:4], 11, axis=1)], axis=1))
+    a = np.zeros((n_series, M))
+    a[:, 1] = rng.normal(size=n_series)
+    a[:, 0] = rng.normal(size=n_series) * sd[:, 0]
+    y = np.zeros((n_series, T_STEPS))
+    for t in range(T_STEPS):
+        y[:, t] = a @ Zm
+        a = a @ Tm.T + rng.normal(size=(n_series, M)) * sd
+    tv = variants(theta)                                  # (V, n, 4)
+    Qd, Pd = diag_params(tv)
+    yy = np.tile(y, (V, 1))                               # evaluation e = v * n + b
+    Qfull = np.zeros((V * n_series, M, M))
+    Pfull = np.zeros((V * n_series, M, M))
+    idx = np.arange(M)
+    Qfull[:, idx, idx] = Qd.reshape(-1, M)
+    Pfull[:, idx, idx] = Pd.reshape(-1, M)
+    return sm, yy, Pfull, Qfull
+
+
+def time_cpu(mod, sm, yy, Pfull, Qfull, threads=0):
+    t0 = time.perf_counter()
+    out = mod.loglik_batch(yy, sm.a, sm.P_inf, Pfull, sm.Z[:, :, 0], sm.T[:, :, 0], sm.R[:, :, 0], Qfull, threads)
+    dt = time.perf_counter() - t0
+    return yy.shape[0] * T_STEPS / dt, dt, out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cport, ref
+    mod, kind = (ref, "reference") if ref.available() else (cport, "port")
+    cores = mod.num_threads()
+    n_series = max(16, 32 * cores)
+    sm, yy, Pfull, Qfull = cpu_sample(n_series)
+    for _ in range(args.warmup):
+        time_cpu(mod, sm, yy, Pfull, Qfull)
+    times = []
+    for _ in range(args.steps):
+        _, dt, _ = time_cpu(mod, sm, yy, Pfull, Qfull)
+        times.append(dt)
+    total = sum(times)
+    value = args.steps * yy.shape[0] * T_STEPS / total
+    sample = f"{n_series} series x {V} parameter vectors x {T_STEPS} timesteps per step"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config(args.gpus, B_PER_GPU, {"cpu_sample": sample}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "what": "src/LogLikC.cpp compiled unmodified (oracle/_ref), OpenMP over series"
+                             if kind == "reference" else "oracle/kalman_c.c"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---- the GPU arm ----------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_shard(torch, dev, B, seed):
+    """Synthetic shard generated on the device: y (T, B) time-major, theta (B, 4)."""
+    from statespacer_b200 import sysmat
+    g = torch.Generator(device=dev)
+    g.manual_seed(20240501 + seed)
+    theta = torch.tensor(MU, device=dev) + 0.25 * torch.randn(B, 4, generator=g, device=dev, dtype=torch.float64)
+    sm = sysmat.bsm12(MU)
+    Tm = torch.tensor(sm.T[:, :, 0], device=dev)
+    Zm = torch.tensor(sm.Z[0, :, 0], device=dev)
+    var = torch.exp(2 * theta)
+    sd = torch.sqrt(torch.cat([var[:, :3], var[:, 3:4].expand(B, 11)], dim=1))
+    g.manual_seed(77 + seed)
+    a = torch.zeros(B, M, device=dev, dtype=torch.float64)
+    a[:, 1] = torch.randn(B, generator=g, device=dev, dtype=torch.float64)
+    a[:, 0] = torch.randn(B, generator=g, device=dev, dtype=torch.float64) * sd[:, 0]
+    y = torch.empty(T_STEPS, B, device=dev, dtype=torch.float64)
+    for t in range(T_STEPS):
+        y[t] = a @ Zm
+        a = a @ Tm.T + torch.randn(B, M, generator=g, device=dev, dtype=torch.float64) * sd
+    return sm, y, theta
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from statespacer_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (statespacer_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    api.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.series
+    sm, y, theta = make_shard(torch, dev, B, rank)
+    if args.missing > 0:
+        g = torch.Generator(device=dev)
+        g.manual_seed(5 + rank)
+        y[torch.rand(y.shape, generator=g, device=dev) < args.missing] = float("nan")
+    theta_v = variants(theta.cpu().numpy())
+    Qd_h, Pd_h = diag_params(theta_v)
+    Qd, Pd = torch.from_numpy(Qd_h).to(dev), torch.from_numpy(Pd_h).to(dev)
+    model = api.BatchModel(sm, T_STEPS, B, V, Q_diag=Qd, P_star_diag=Pd, device=dev)
+    out = torch.empty(V, B, device=dev, dtype=torch.float64)
+    gathered = torch.empty(world, B, 1 + K_PAR, device=dev, dtype=torch.float64) if world > 1 else None
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        api.loglik_batch_dev(y, model, out, kernel=args.kernel, stream=stream)
+        if world > 1:
+            grad = (out[1::2] - out[2::2]).T / (2 * H_FD)                  # (B, k): formed locally on each rank
+            dist.all_gather_into_tensor(gathered, torch.cat([out[0][:, None], grad], dim=1).contiguous())
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    # FP64 roofline denominator, measured on this device in this run
+    peak_tf, _ = api.fp64_peak(0, 4000, 5)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = api.launch_count()
+    kern_ms = []
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        api.loglik_batch_dev(y, model, out, kernel=args.kernel, stream=stream)
+        k1.record(stream)
+        kern_ms.append((k0, k1))
+        if world > 1:
+            grad = (out[1::2] - out[2::2]).T / (2 * H_FD)
+            dist.all_gather_into_tensor(gathered, torch.cat([out[0][:, None], grad], dim=1).contiguous())
+    e1.record(stream)
+    sync()
+    launches = api.launch_count() - l0
+    clocks = sampler.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kern_ms)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    units_per_step = B * V * T_STEPS * world
+    value = units_per_step * args.steps / (elapsed_ms * 1e-3)
+    finite = bool(torch.isfinite(out).all().item())
+
+    # ---- end to end through the host-pointer C ABI (pinned host buffers) ----
+    e2e_steps = max(1, min(args.steps, 3))
+    y_h = torch.empty(y.shape, dtype=torch.float64, pin_memory=True)
+    y_h.copy_(y)
+    Q_h = torch.from_numpy(Qd_h).pin_memory()
+    P_h = torch.from_numpy(Pd_h).pin_memory()
+    out_h = torch.empty(V, B, dtype=torch.float64, pin_memory=True)
+    import ctypes as C
+    from statespacer_b200 import native
+    hmodel = api.BatchModel(sm, T_STEPS, B, V, Q_diag=Q_h.numpy(), P_star_diag=P_h.numpy())
+
+    def e2e_step():
+        native.check(native.lib().ssgpu_loglik_batch(y_h.data_ptr(), B, V, C.byref(hmodel.c),
+                                                     api._KERNELS[args.kernel], out_h.data_ptr()))
+
+    e2e_step()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    sync()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = units_per_step * e2e_steps / e2e_s
+    e2e_match = bool(np.allclose(out_h.numpy(), out.cpu().numpy(), rtol=0, atol=0, equal_nan=True))
+    h2d = y_h.numel() * 8 + Q_h.numel() * 8 + P_h.numel() * 8 + 8 * (M * M * 3 + M * 3)
+    d2h = out_h.numel() * 8
+
+    if rank == 0:
+        flops = f_alg(M, 1) * B * V * T_STEPS
+        achieved = flops / (kernel_ms * 1e-3) / 1e12
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config(world, B, {"kernel": api.last_kernel(), "missing_fraction": args.missing,
+                                            "results_finite": finite}),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "bit_identical_to_resident_path": e2e_match},
+                "gpu_launches": launches,
+                "roofline": {"bound": "fp64", "kernel": "loglik_cols_kernel<14,16>", "achieved": achieved,
+                             "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                             "flops_per_series_timestep": f_alg(M, 1), "kernel_ms": kernel_ms,
+                             "peak_source": "ssgpu_fp64_peak DFMA chains, measured in this run (MEASURED_PEAKS.json "
+                                            "has no FP64 figure)",
+                             "hbm_algorithmic_gbs": 8.0 * B * T_STEPS / (kernel_ms * 1e-3) / 1e9,
+                             "hbm_peak_gbs": hbm_peak}}
+        if world == 1 and not args.no_cpu:
+            from oracle import cport, ref
+            mod, kind = (ref, "reference") if ref.available() else (cport, "port")
+            cores = mod.num_threads()
+            n_series = 16 * cores
+            smc, yy, Pfull, Qfull = cpu_sample(n_series)
+            v_ref, dt, o_ref = time_cpu(mod, smc, yy, Pfull, Qfull)
+            v_port, _, o_port = time_cpu(cport, smc, yy, Pfull, Qfull)
+            line["cpu_baseline"] = {"value": v_ref, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{n_series} series x {V} parameter vectors x {T_STEPS} timesteps "
+                                              f"({dt:.1f} s)",
+                                    "port_value": v_port,
+                                    "port_vs_reference_max_abs_diff": float(np.max(np.abs(o_ref - o_port)))}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--series", type=int, default=B_PER_GPU, help="series per GPU")
+    ap.add_argument("--missing", type=float, default=0.0, help="fraction of NaN observations (variant B: 0.02)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "cols", "generic"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -212,7 +212,7 @@ class BatchModel:
         mo.Z = self._shared(Z, p, m)
         mo.T = self._shared(T, m, m)
         mo.R = self._shared(R, m, r)
-        mo.a = self._per_eval(a, m, 1, False) if a is not None else self._shared(a0.reshape(m, 1, 1), m, 1)
+        mo.a = self._per_eval(a, m, 1, False, vec=True) if a is not None else self._shared(a0.reshape(m, 1, 1), m, 1)
         mo.P_inf = (self._per_eval(P_inf, m, m, False) if P_inf is not None
                     else self._shared(_f(sm.P_inf)[:, :, None], m, m))
         if P_star_diag is not None:
@@ -241,11 +241,11 @@ class BatchModel:
             ptr = t.data_ptr()
         return native.Matrix(ptr, rows, cols, 0, cube.shape[2], 0, 0)
 
-    def _per_eval(self, x, rows, cols, diag):
+    def _per_eval(self, x, rows, cols, diag, vec=False):
         block = rows if diag else rows * cols
         is_torch = not isinstance(x, np.ndarray) and hasattr(x, "data_ptr")
         shape = tuple(x.shape)
-        tail = 1 if (diag or cols == 1) else 2
+        tail = 1 if (diag or vec) else 2
         lead = shape[:len(shape) - tail]
         if int(np.prod(shape[len(lead):])) != block:
             raise ValueError("per-evaluation block has the wrong size")

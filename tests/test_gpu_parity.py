@@ -63,8 +63,11 @@ def test_loglik_edge_cases():
     sm = sysmat.nile_local_level(2.0, 1.0)
     y = np.full((6, 1), np.nan)
     assert math.isnan(api.LogLikC(y, np.isnan(y), *sm.args()))           # all missing -> NA (src/LogLikC.cpp:211)
-    y1 = np.array([[3.0]])
-    assert abs(api.LogLikC(y1, np.isnan(y1), *sm.args()) - cport.LogLikC(y1, np.isnan(y1), *sm.args())) < 1e-12
+    y1 = np.array([[3.0]])                                                # N = 1: only a diffuse step -> NA
+    assert math.isnan(api.LogLikC(y1, np.isnan(y1), *sm.args())) and math.isnan(
+        cport.LogLikC(y1, np.isnan(y1), *sm.args()))
+    y3 = np.array([[3.0], [np.nan], [2.5]])
+    assert abs(api.LogLikC(y3, np.isnan(y3), *sm.args()) - cport.LogLikC(y3, np.isnan(y3), *sm.args())) < 1e-12
     sm0 = sysmat.nile_local_level(0.0, 0.0)                               # F = 0 everywhere after init -> NA
     y2 = np.ones((5, 1))
     assert math.isnan(api.LogLikC(y2, np.isnan(y2), *sm0.args())) == math.isnan(
@@ -204,7 +207,8 @@ def test_batch_generic_time_varying_and_per_series():
 
 def test_batch_properties_large():
     """Size-independent properties at a size the oracle would not finish: (i) replicated series give
-    identical values, (ii) scaling y by c and all variances by c^2 shifts loglik by -n_obs*log(c)/N."""
+    identical values, (ii) scaling y by c and all variances by c^2 shifts loglik by -(n_obs - d)*log(c)/N
+    (the d = 13 exact-diffuse steps contribute -log(F_inf)/2, which does not scale: src/LogLikC.cpp:153)."""
     rng = np.random.default_rng(9)
     B, N, V = 20000, 100, 1
     thetas, Qd, Pd, y = _bsm_batch(rng, 64, N, V, 0.02)
@@ -218,7 +222,7 @@ def test_batch_properties_large():
     c = 3.0
     got_c = api.loglik_batch(c * yB, sm, Q_diag=c * c * QB, P_star_diag=c * c * PB)
     n_obs = np.sum(~np.isnan(yB), axis=0)
-    assert np.max(np.abs(got_c - (got - n_obs * math.log(c) / N))) < 1e-9 * np.max(np.abs(got))
+    assert np.max(np.abs(got_c - (got - (n_obs - 13) * math.log(c) / N))) < 1e-9 * np.max(np.abs(got))
     want = cport.LogLikC(y[:, 5:6], np.isnan(y[:, 5:6]), *sysmat.bsm12(thetas[0, 5]).args())
     assert abs(got[5] - want) <= RTOL * abs(want)
 
