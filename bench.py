@@ -336,7 +336,7 @@ def run_gpu(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "bit_identical_to_resident_path": e2e_match},
                 "gpu_launches": launches,
-                "roofline": {"bound": "fp64", "kernel": "loglik_cols_kernel<14,16>", "achieved": achieved,
+                "roofline": {"bound": "fp64", "kernel": api.last_kernel(), "achieved": achieved,
                              "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
                              "flops_per_series_timestep": f_alg(M, 1), "kernel_ms": kernel_ms,
                              "peak_source": "ssgpu_fp64_peak DFMA chains, measured in this run (MEASURED_PEAKS.json "
@@ -369,7 +369,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--series", type=int, default=B_PER_GPU, help="series per GPU")
     ap.add_argument("--missing", type=float, default=0.0, help="fraction of NaN observations (variant B: 0.02)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "cols", "generic"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "mma", "cols", "generic"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

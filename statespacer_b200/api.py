@@ -16,9 +16,9 @@ import ctypes as C
 import numpy as np
 
 from . import native
-from .native import KERNEL_AUTO, KERNEL_COLS, KERNEL_GENERIC  # noqa: F401
+from .native import KERNEL_AUTO, KERNEL_COLS, KERNEL_GENERIC, KERNEL_MMA  # noqa: F401
 
-_KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "cols": KERNEL_COLS}
+_KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "cols": KERNEL_COLS, "mma": KERNEL_MMA}
 
 
 def _f(x):

@@ -145,6 +145,10 @@ int launch_permute_tks(const double* src, double* dst, int N, int K, long long S
 // native X[(t*m+k)*S+s] -> a_t [k + m*(s + S*t)]
 int launch_permute_at(const double* src, double* dst, int N, int m, long long S, cudaStream_t st);
 
+// Warp-per-evaluation FP64 tensor kernel (loglik_mma.cu)
+bool mma_eligible(const DModel& md, std::string* why);
+int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st);
+
 // Column-per-thread register kernel (loglik_cols.cu)
 bool cols_eligible(const DModel& md, std::string* why);
 int launch_loglik_cols(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st);

@@ -1,0 +1,421 @@
+// Batched loglikelihood on the FP64 tensor path: one evaluation (series b, parameter vector v) per
+// warp, every m x m object held in registers as mma.sync.m8n8k4.f64 accumulator fragments.
+//
+// Restates the recursion of src/LogLikC.cpp:68-214 (univariate treatment, exact diffuse
+// initialisation, NaN = missing) for models whose Z, T, R are shared by the batch and time-invariant
+// (per-evaluation a, P_inf, P_star, Q allowed), m <= 23.
+//
+// Why this shape.  The time update  P <- T P T' + R Q R'  (src/LogLikC.cpp:202) is 4 m^3 of the
+// 4 m^3 + 7 m^2 flops of a step: a dense FP64 contraction.  sm_100 has no tcgen05 kind for f64; its FP64
+// tensor path is DMMA (mma.sync.m8n8k4.f64), measured at the same 37 TFLOP/s as the DFMA pipe
+// (ssgpu_fp64_peak mode 1) but needing 1/32 of the instructions and no operand traffic at all:
+//   * a D x D matrix X (D = 8 ceil((m+1)/8)) lives in "C layout": lane (g = lane/4, q = lane%4) holds
+//     X[8rt+g][8ct+2q+e], e = 0,1 -- the accumulator fragment of tile (rt, ct);
+//   * with the k index of the contraction permuted as k = 8ct + 2q + e  <->  (k-step (ct,e), slot q),
+//     those same registers ARE the A fragment of X and the B fragment of X': any product  X W'  of two
+//     C-layout matrices is 2 TT^3 DMMAs with no shuffle, no shared memory, no constant load;
+//   * the state vector rides along as row m of  G = [P ; a'] :
+//         Y  = T G'              = [T P , T a]            (a-row of G becomes column m of Y, unused)
+//         G' = [Y ; a'] T' + RQR' = [T P T' + R Q R' ; (T a)']
+//     (column m of Y meets the zero padding column m of T, so it drops out);
+//   * the measurement update is a rank-1 correction in place: row sums by two quad shuffles, F = z'Pz and
+//     the gather of M[c] by a few more; v, K, a += K v come out of the same formulas through row m.
+// One evaluation per warp makes every branch of the recursion (diffuse / regular / skipped step) warp
+// uniform: there is no divergence and no predication anywhere.
+// Measurement update in the rank-1 forms P - M K0' (src/LogLikC.cpp:129,193), P* - M* K0' - M_inf K1',
+// P_inf - M_inf K0' (:151-152); sum(log F) carried as (mantissa product, exponent sum).
+#include "common.cuh"
+
+namespace ssgpu {
+
+constexpr int kMmaThreads = 128;  // 4 warps = 4 evaluations per CTA
+constexpr int kMmaMaxM = 23;
+
+struct MmaArgs {
+  DModel md;
+  const double* y;  // [(t*p + j) * B + b]
+  long long B;
+  long long E;  // B * V
+  double* out;
+};
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// D x D matrix in C layout: c[rt][ct][e] = X[8rt+g][8ct+2q+e]
+template <int TT>
+struct Frag {
+  double c[TT][TT][2];
+};
+
+// Z = init + X W'   (all C layout)
+template <int TT>
+__device__ __forceinline__ void mul_xwt(Frag<TT>& Z, const Frag<TT>& X, const Frag<TT>& W) {
+#pragma unroll
+  for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+      for (int rt = 0; rt < TT; rt++)
+#pragma unroll
+        for (int nt = 0; nt < TT; nt++) dmma(Z.c[rt][nt][0], Z.c[rt][nt][1], X.c[rt][ct][e], W.c[nt][ct][e]);
+}
+
+template <int TT, bool P1>
+__global__ void __launch_bounds__(kMmaThreads) loglik_mma_kernel(const MmaArgs A) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const DModel& md = A.md;
+  const int N = md.N, p = P1 ? 1 : md.p, M = md.m, r = md.r;
+  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const long long e_id = (long long)blockIdx.x * (kMmaThreads / 32) + (threadIdx.x >> 5);
+  if (e_id >= A.E) return;  // whole warp
+  const long long b = e_id % A.B, v = e_id / A.B;
+  const int rt_a = M >> 3, g_a = M & 7;  // the state vector is row M
+
+  auto row_of = [&](int rt) { return 8 * rt + g; };
+  auto col_of = [&](int ct, int e) { return 8 * ct + 2 * q + e; };
+
+  // ---- shared matrices into fragments: T (zero padded), z --------------------------------------
+  Frag<TT> T, G, RQR;
+  {
+    const double* Tb = md.T.block(0, 0, 0);
+    const double* ab = md.a.block(b, v, 0);
+    const double* Ps = md.P_star.block(b, v, 0);
+#pragma unroll
+    for (int rt = 0; rt < TT; rt++)
+#pragma unroll
+      for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int i = row_of(rt), k = col_of(ct, e);
+          const bool in = i < M && k < M;
+          T.c[rt][ct][e] = in ? mat_get(Tb, md.T.diag, M, i, k) : 0.0;
+          G.c[rt][ct][e] = in ? mat_get(Ps, md.P_star.diag, M, i, k) : ((i == M && k < M) ? ab[k] : 0.0);
+          RQR.c[rt][ct][e] = 0.0;
+        }
+    // R Q R' (src/LogLikC.cpp:202, hoisted: Q and R are time-invariant here)
+    const double* Qb = md.Q.block(b, v, 0);
+    const double* Rb = md.R.block(0, 0, 0);
+#pragma unroll
+    for (int rt = 0; rt < TT; rt++)
+#pragma unroll
+      for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int i = row_of(rt), cidx = col_of(ct, e);
+          if (i < M && cidx < M) {
+            double acc = 0.0;
+            for (int k = 0; k < r; k++) {
+              const double rik = mat_get(Rb, md.R.diag, M, i, k);
+              if (rik == 0.0) continue;
+              double qr;
+              if (md.Q.diag) {
+                qr = Qb[k] * mat_get(Rb, md.R.diag, M, cidx, k);
+              } else {
+                qr = 0.0;
+                for (int l = 0; l < r; l++) qr = fma(Qb[k + (long long)l * r], mat_get(Rb, md.R.diag, M, cidx, l), qr);
+              }
+              acc = fma(rik, qr, acc);
+            }
+            RQR.c[rt][ct][e] = acc;
+          }
+        }
+  }
+  // row j of Z as column values zc[ct][e] = z[col] and row values zr[rt] = z[row] (rows >= M: 0)
+  double zc[TT][2], zr[TT];
+  auto load_z = [&](int j) {
+    const double* Zb = md.Z.block(0, 0, 0);
+#pragma unroll
+    for (int ct = 0; ct < TT; ct++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int k = col_of(ct, e);
+        zc[ct][e] = k < M ? Zb[j + (long long)k * p] : 0.0;
+      }
+      const int i = row_of(ct);
+      zr[ct] = i < M ? Zb[j + (long long)i * p] : 0.0;
+    }
+  };
+  if (P1) load_z(0);
+
+  // sum over the quad (columns) / over the 8 quads (rows)
+  auto quad_sum = [&](double x) {
+    x += __shfl_xor_sync(FULL, x, 1);
+    x += __shfl_xor_sync(FULL, x, 2);
+    return x;
+  };
+  auto rows_sum = [&](double x) {
+    x += __shfl_xor_sync(FULL, x, 4);
+    x += __shfl_xor_sync(FULL, x, 8);
+    x += __shfl_xor_sync(FULL, x, 16);
+    return x;
+  };
+  // m[rt] = (X z)[row]: known to the 4 lanes of the quad that owns the row
+  auto row_dots = [&](const Frag<TT>& X, double (&m)[TT]) {
+#pragma unroll
+    for (int rt = 0; rt < TT; rt++) {
+      double acc = 0.0;
+#pragma unroll
+      for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) acc = fma(X.c[rt][ct][e], zc[ct][e], acc);
+      m[rt] = quad_sum(acc);
+    }
+  };
+  // mc[ct][e] = m[col] for col < M (else 0): row `col` belongs to quad (2q+e), slot ct
+  auto to_cols = [&](const double (&m)[TT], double (&mc)[TT][2]) {
+#pragma unroll
+    for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const double x = __shfl_sync(FULL, m[ct], (2 * q + e) * 4);
+        mc[ct][e] = col_of(ct, e) < M ? x : 0.0;
+      }
+  };
+  // m[rt_a] without dynamic register indexing
+  auto pick = [&](const double (&m)[TT]) {
+    double x = m[0];
+#pragma unroll
+    for (int rt = 1; rt < TT; rt++) x = rt_a == rt ? m[rt] : x;
+    return x;
+  };
+  auto abs_small = [&](const Frag<TT>& X) {
+    bool ok = true;
+#pragma unroll
+    for (int rt = 0; rt < TT; rt++)
+#pragma unroll
+      for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) ok = ok && (fabs(X.c[rt][ct][e]) < kEps);
+    return __all_sync(FULL, ok) != 0;
+  };
+
+  // loglik = n_terms*const - (sum log F + sum v^2/F)/2, log F accumulated as mantissa * 2^esum
+  double prod = 1.0, sumq = 0.0;
+  int esum = 0, n_terms = 0, non_init = 0, F_eq0 = 0;
+  auto acc_log = [&](double F) {
+    prod *= F;
+    const int hi = __double2hiint(prod);
+    const int ex = ((hi >> 20) & 0x7ff) - 1023;
+    esum += ex;
+    prod = __hiloint2double(hi - (ex << 20), __double2loint(prod));
+    n_terms++;
+  };
+
+  // y: 32 flat indices (t*p + j) at a time, one per lane, one chunk ahead
+  const long long Np = (long long)N * p;
+  auto load_y = [&](long long qq) { return qq < Np ? A.y[qq * A.B + b] : 0.0; };
+  double ybuf = 0.0, ynext = load_y(lane);
+  long long qi = 0;
+  auto next_y = [&]() {
+    const int ql = (int)(qi & 31);
+    if (ql == 0) {
+      ybuf = ynext;
+      ynext = load_y(qi + 32 + lane);
+    }
+    qi++;
+    return __shfl_sync(FULL, ybuf, ql);
+  };
+
+  // P* L0' = P* - M K0' applied to G = [P* ; a'] (src/LogLikC.cpp:181-194 / 117-130)
+  auto update_star = [&](const double (&ms)[TT], double F_star, double yv) {
+    const double F1 = __drcp_rn(F_star);
+    const double za = __shfl_sync(FULL, pick(ms), g_a * 4);
+    const double vv = yv - za;
+    double mc[TT][2];
+    to_cols(ms, mc);
+#pragma unroll
+    for (int rt = 0; rt < TT; rt++) {
+      const int i = row_of(rt);
+      const double rc = i < M ? ms[rt] : (i == M ? -vv : 0.0);  // row M: a += K0 v
+#pragma unroll
+      for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) G.c[rt][ct][e] = fma(-rc, mc[ct][e] * F1, G.c[rt][ct][e]);
+    }
+    acc_log(F_star);
+    sumq = fma(vv * vv, F1, sumq);
+  };
+
+  // [Y ; a'] T' with Y = T G'  (+ R Q R')
+  auto time_update = [&](Frag<TT>& X, bool with_rqr, bool keep_a) {
+    Frag<TT> Y;
+#pragma unroll
+    for (int rt = 0; rt < TT; rt++)
+#pragma unroll
+      for (int ct = 0; ct < TT; ct++) Y.c[rt][ct][0] = Y.c[rt][ct][1] = 0.0;
+    mul_xwt<TT>(Y, T, X);  // T X' = [T P , T a]
+#pragma unroll
+    for (int rt = 0; rt < TT; rt++)
+#pragma unroll
+      for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          if (keep_a && row_of(rt) == M) Y.c[rt][ct][e] = X.c[rt][ct][e];  // row M of Y <- a'
+          X.c[rt][ct][e] = with_rqr ? RQR.c[rt][ct][e] : 0.0;
+        }
+    mul_xwt<TT>(X, Y, T);  // [T P ; a'] T' = [T P T' ; (T a)']
+  };
+
+  int t = 0;
+  {
+    // ---- exact diffuse phase (src/LogLikC.cpp:98-159) ------------------------------------------
+    Frag<TT> Ginf;
+    const double* Pi = md.P_inf.block(b, v, 0);
+#pragma unroll
+    for (int rt = 0; rt < TT; rt++)
+#pragma unroll
+      for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int i = row_of(rt), k = col_of(ct, e);
+          Ginf.c[rt][ct][e] = (i < M && k < M) ? mat_get(Pi, md.P_inf.diag, M, i, k) : 0.0;
+        }
+    bool init = !abs_small(Ginf);  // :49
+    for (; t < N && init; t++) {
+      for (int j = 0; j < p; j++) {
+        const double yv = next_y();
+        if (isnan(yv)) continue;  // :88-90
+        if (!P1) load_z(j);
+        double ms[TT];
+        row_dots(G, ms);
+        double fs = 0.0;
+#pragma unroll
+        for (int rt = 0; rt < TT; rt++) fs = fma(zr[rt], ms[rt], fs);
+        const double F_star = rows_sum(fs);  // lanes of equal q: every row once
+        if (!init) {  // P_inf vanished earlier in this time point (p > 1): regular step
+          non_init++;
+          if (F_star < kEps)
+            F_eq0++;
+          else
+            update_star(ms, F_star, yv);
+          continue;
+        }
+        double mi[TT];
+        row_dots(Ginf, mi);
+        double fi = 0.0;
+#pragma unroll
+        for (int rt = 0; rt < TT; rt++) fi = fma(zr[rt], mi[rt], fi);
+        const double F_inf = rows_sum(fi);
+        if (F_inf < kEps) {
+          if (F_star < kEps) continue;  // :112-113
+          update_star(ms, F_star, yv);  // :117-131
+          continue;
+        }
+        // :136-153  K0 = M_inf F1, K1 = M* F1 + M_inf F2
+        const double F1 = __drcp_rn(F_inf), F2 = -(F1 * F1) * F_star;
+        const double za = __shfl_sync(FULL, pick(ms), g_a * 4);
+        const double vv = yv - za;
+        double msc[TT][2], mic[TT][2];
+        to_cols(ms, msc);
+        to_cols(mi, mic);
+#pragma unroll
+        for (int rt = 0; rt < TT; rt++) {
+          const int i = row_of(rt);
+          const double rs = i < M ? ms[rt] : (i == M ? -vv : 0.0);  // row M: a += K0 v
+          const double ri = i < M ? mi[rt] : 0.0;
+#pragma unroll
+          for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const double k0 = mic[ct][e] * F1, k1 = msc[ct][e] * F1 + mic[ct][e] * F2;
+              // P* - M* K0' - M_inf K1'  (row M: M* -> -v, M_inf -> 0)
+              G.c[rt][ct][e] = fma(-ri, k1, fma(-rs, k0, G.c[rt][ct][e]));
+              Ginf.c[rt][ct][e] = fma(-ri, k0, Ginf.c[rt][ct][e]);
+            }
+        }
+        acc_log(F_inf);  // no v^2 term (:153)
+        if (j < p - 1) init = !abs_small(Ginf);  // :157-159
+      }
+      if (t < N - 1) {  // :200-207
+        time_update(G, true, true);
+        if (init) {
+          time_update(Ginf, false, false);
+          init = !abs_small(Ginf);
+        }
+      }
+    }
+  }
+
+  // ---- regular phase: the hot loop ---------------------------------------------------------------
+  for (; t < N; t++) {
+    for (int j = 0; j < p; j++) {
+      const double yv = next_y();
+      if (isnan(yv)) continue;
+      if (!P1) load_z(j);
+      non_init++;
+      double ms[TT];
+      row_dots(G, ms);
+      double fs = 0.0;
+#pragma unroll
+      for (int rt = 0; rt < TT; rt++) fs = fma(zr[rt], ms[rt], fs);
+      const double F_star = rows_sum(fs);
+      if (F_star < kEps)
+        F_eq0++;  // :173-176
+      else
+        update_star(ms, F_star, yv);
+    }
+    if (t < N - 1) time_update(G, true, true);
+  }
+
+  if (lane == 0) {
+    double res;
+    if (non_init == F_eq0) {
+      res = nan("");  // src/LogLikC.cpp:211-213
+    } else {
+      const double sumlog = (double)esum * 0.69314718055994530942 + log(prod);
+      res = ((double)n_terms * kLogConst - 0.5 * (sumlog + sumq)) / (double)N;
+    }
+    A.out[e_id] = res;
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+bool mma_eligible(const DModel& md, std::string* why) {
+  auto no = [&](const char* s) {
+    if (why) *why = s;
+    return false;
+  };
+  if (md.m > kMmaMaxM) return no("m > 23");
+  if (!md.Z.shared() || !md.T.shared() || !md.R.shared()) return no("Z, T, R must be shared by the batch");
+  if (md.Z.tv() || md.T.tv() || md.R.tv() || md.Q.tv()) return no("time-varying system matrices");
+  return true;
+}
+
+template <int TT>
+static void launch_mma_tt(const MmaArgs& A, unsigned blocks, cudaStream_t st) {
+  if (A.md.p == 1)
+    loglik_mma_kernel<TT, true><<<blocks, kMmaThreads, 0, st>>>(A);
+  else
+    loglik_mma_kernel<TT, false><<<blocks, kMmaThreads, 0, st>>>(A);
+}
+
+int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st) {
+  std::string why;
+  SS_ARG(mma_eligible(md, &why), "tensor kernel not eligible: " + why);
+  MmaArgs A{};
+  A.md = md;
+  A.y = y;
+  A.B = B;
+  A.E = B * V;
+  A.out = out;
+  const int wpb = kMmaThreads / 32;
+  const long long blocks = (A.E + wpb - 1) / wpb;
+  SS_ARG(blocks < (1LL << 31), "tensor kernel: batch too large for one launch");
+  const int tt = (md.m + 1 + 7) / 8;
+  if (tt == 1)
+    launch_mma_tt<1>(A, (unsigned)blocks, st);
+  else if (tt == 2)
+    launch_mma_tt<2>(A, (unsigned)blocks, st);
+  else
+    launch_mma_tt<3>(A, (unsigned)blocks, st);
+  SS_CUDA(cudaGetLastError());
+  count_launch();
+  set_last_kernel("loglik_mma_kernel");
+  return SSGPU_OK;
+}
+
+}  // namespace ssgpu

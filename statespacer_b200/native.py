@@ -48,7 +48,7 @@ SYMBOLS = ["ssgpu_version", "ssgpu_last_error", "ssgpu_set_device", "ssgpu_devic
            "ssgpu_sym_root", "ssgpu_ExtractComponentC", "ssgpu_loglik_batch", "ssgpu_loglik_batch_dev",
            "ssgpu_last_kernel", "ssgpu_fp64_peak"]
 
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS = 0, 1, 2
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS, KERNEL_MMA = 0, 1, 2, 3
 
 
 def lib():

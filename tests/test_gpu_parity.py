@@ -138,13 +138,16 @@ def _bsm_batch(rng, B, N, V, missing):
     return thetas, Qd, Pd, y
 
 
-@pytest.mark.parametrize("kernel", ["cols", "generic"])
+KERNEL_NAMES = {"mma": "loglik_mma", "cols": "loglik_cols", "generic": "fwd_generic"}
+
+
+@pytest.mark.parametrize("kernel", ["mma", "cols", "generic"])
 def test_batch_config5_shape(kernel):
     rng = np.random.default_rng(5)
     B, N, V = 70, 60, 3
     thetas, Qd, Pd, y = _bsm_batch(rng, B, N, V, 0.05)
     got = api.loglik_batch(y, sysmat.bsm12(thetas[0, 0]), V=V, Q_diag=Qd, P_star_diag=Pd, kernel=kernel)
-    assert api.last_kernel().startswith("loglik_cols" if kernel == "cols" else "fwd_generic")
+    assert api.last_kernel().startswith(KERNEL_NAMES[kernel])
     assert got.shape == (V, B)
     for v in range(V):
         for b in range(0, B, 7):
@@ -153,8 +156,10 @@ def test_batch_config5_shape(kernel):
             assert abs(got[v, b] - want) <= RTOL * max(1, abs(want)), (v, b, got[v, b], want)
 
 
-@pytest.mark.parametrize("m", list(range(1, 16)))
-def test_batch_cols_every_state_dim(m):
+@pytest.mark.parametrize("m", list(range(1, 24)))
+def test_batch_every_state_dim(m):
+    """Register kernels at every supported state dimension (tensor kernel m <= 23, column kernel m <= 15),
+    per-series dense Q / P_star / a, p in {1, 2}, diffuse states, missing values."""
     rng = np.random.default_rng(40 + m)
     B, N, p = 9, 25, 1 if m % 3 else 2
     d = min(m - 1, 2) if m > 1 else 0
@@ -164,8 +169,9 @@ def test_batch_cols_every_state_dim(m):
     Qb = np.stack([sm.Q[:, :, 0] * (1 + 0.1 * b) for b in range(B)])
     Pb = np.stack([sm.P_star * (1 + 0.05 * b) for b in range(B)])
     ab = np.stack([sm.a + 0.01 * b for b in range(B)])
-    got = api.loglik_batch(y, sm, Q=Qb, P_star=Pb, a=ab, kernel="cols")
+    got = api.loglik_batch(y, sm, Q=Qb, P_star=Pb, a=ab, kernel="mma")
     gen = api.loglik_batch(y, sm, Q=Qb, P_star=Pb, a=ab, kernel="generic")
+    cols = api.loglik_batch(y, sm, Q=Qb, P_star=Pb, a=ab, kernel="cols") if m <= 15 else got
     for b in range(B):
         smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=Qb[b][:, :, None], a=ab[b], P_inf=sm.P_inf, P_star=Pb[b])
         yb = y[:, :, b]
@@ -173,6 +179,7 @@ def test_batch_cols_every_state_dim(m):
         tol = (1e-8 if d else RTOL) * max(1, abs(want))
         assert abs(got[b] - want) <= tol, (m, b, got[b], want)
         assert abs(gen[b] - want) <= tol, (m, b, gen[b], want)
+        assert abs(cols[b] - want) <= tol, (m, b, cols[b], want)
 
 
 def test_batch_multivariate_dns():
@@ -185,12 +192,14 @@ def test_batch_multivariate_dns():
     y[rng.uniform(size=y.shape) < 0.03] = np.nan
     y[:, :, 0] = fed
     got = api.loglik_batch(y, sm, kernel="auto")
-    assert api.last_kernel().startswith("loglik_cols")
+    assert api.last_kernel().startswith("loglik_mma")
     assert abs(got[0] - 7.005830) < 6e-7 * 7                               # docs/articles/selfspec.html:306-307
+    cols = api.loglik_batch(y, sm, kernel="cols")
     for b in range(B):
         yb = y[:, :, b]
         want = cport.LogLikC(yb, np.isnan(yb), *sm.args())
         assert abs(got[b] - want) <= RTOL * max(1, abs(want)), (b, got[b], want)
+        assert abs(cols[b] - want) <= RTOL * max(1, abs(want)), (b, cols[b], want)
 
 
 def test_batch_generic_time_varying_and_per_series():
