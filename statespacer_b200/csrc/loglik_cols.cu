@@ -102,8 +102,11 @@ __global__ void __launch_bounds__(kColsThreads, MINB) loglik_cols_kernel(const C
   // operand of the DFMA).  Tail groups recompute the last evaluation and skip the store.
   const long long e_raw = (long long)blockIdx.x * GPB + gi;
   const bool live = e_raw < A.E;
-  const long long e = live ? e_raw : A.E - 1;
-  const long long b = e % A.B, v = e / A.B;
+  const long long w_id = live ? e_raw : A.E - 1;
+  // groups are numbered series-major (w = b*V + v): the V parameter vectors of a series run side by side
+  // and share its y through L1/L2; results keep the public order e = v*B + b
+  const long long V = A.E / A.B, b = w_id / V, v = w_id % V;
+  const long long e = v * A.B + b;
   const unsigned gshift = (tid % 32) / G * G, gbits = (G == 32) ? FULL : ((1u << G) - 1u);
   double* S = smem + gi * GROUP_SMEM;
   double* X = S + M * LD + c * LD;  // this lane's private row

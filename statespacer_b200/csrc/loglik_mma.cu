@@ -24,6 +24,8 @@
 // uniform: there is no divergence and no predication anywhere.
 // Measurement update in the rank-1 forms P - M K0' (src/LogLikC.cpp:129,193), P* - M* K0' - M_inf K1',
 // P_inf - M_inf K0' (:151-152); sum(log F) carried as (mantissa product, exponent sum).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ssgpu {
@@ -64,22 +66,28 @@ __device__ __forceinline__ void mul_xwt(Frag<TT>& Z, const Frag<TT>& X, const Fr
         for (int nt = 0; nt < TT; nt++) dmma(Z.c[rt][nt][0], Z.c[rt][nt][1], X.c[rt][ct][e], W.c[nt][ct][e]);
 }
 
-template <int TT, bool P1>
-__global__ void __launch_bounds__(kMmaThreads) loglik_mma_kernel(const MmaArgs A) {
+template <int TT, bool P1, int MINB>
+__global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const MmaArgs A) {
   constexpr unsigned FULL = 0xffffffffu;
   const DModel& md = A.md;
   const int N = md.N, p = P1 ? 1 : md.p, M = md.m, r = md.r;
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-  const long long e_id = (long long)blockIdx.x * (kMmaThreads / 32) + (threadIdx.x >> 5);
-  if (e_id >= A.E) return;  // whole warp
-  const long long b = e_id % A.B, v = e_id / A.B;
+  // warps are numbered series-major (w = b*V + v) so that the V parameter vectors of a series run side by
+  // side and share its y through L1/L2; results keep the public order e = v*B + b
+  const long long w_id = (long long)blockIdx.x * (kMmaThreads / 32) + (threadIdx.x >> 5);
+  if (w_id >= A.E) return;  // whole warp
+  const long long V = A.E / A.B, b = w_id / V, v = w_id % V;
+  const long long e_id = v * A.B + b;
   const int rt_a = M >> 3, g_a = M & 7;  // the state vector is row M
 
   auto row_of = [&](int rt) { return 8 * rt + g; };
   auto col_of = [&](int ct, int e) { return 8 * ct + 2 * q + e; };
 
   // ---- shared matrices into fragments: T (zero padded), z --------------------------------------
-  Frag<TT> T, G, RQR;
+  Frag<TT> T, G;
+  // R Q R' (accumulator init of the second product) waits in shared memory: [element][lane], conflict-free
+  __shared__ double rqr_s[kMmaThreads / 32][TT * TT * 2][32];
+  double(*rqr)[32] = rqr_s[threadIdx.x >> 5];
   {
     const double* Tb = md.T.block(0, 0, 0);
     const double* ab = md.a.block(b, v, 0);
@@ -94,7 +102,6 @@ __global__ void __launch_bounds__(kMmaThreads) loglik_mma_kernel(const MmaArgs A
           const bool in = i < M && k < M;
           T.c[rt][ct][e] = in ? mat_get(Tb, md.T.diag, M, i, k) : 0.0;
           G.c[rt][ct][e] = in ? mat_get(Ps, md.P_star.diag, M, i, k) : ((i == M && k < M) ? ab[k] : 0.0);
-          RQR.c[rt][ct][e] = 0.0;
         }
     // R Q R' (src/LogLikC.cpp:202, hoisted: Q and R are time-invariant here)
     const double* Qb = md.Q.block(b, v, 0);
@@ -106,8 +113,8 @@ __global__ void __launch_bounds__(kMmaThreads) loglik_mma_kernel(const MmaArgs A
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int i = row_of(rt), cidx = col_of(ct, e);
+          double acc = 0.0;
           if (i < M && cidx < M) {
-            double acc = 0.0;
             for (int k = 0; k < r; k++) {
               const double rik = mat_get(Rb, md.R.diag, M, i, k);
               if (rik == 0.0) continue;
@@ -120,8 +127,8 @@ __global__ void __launch_bounds__(kMmaThreads) loglik_mma_kernel(const MmaArgs A
               }
               acc = fma(rik, qr, acc);
             }
-            RQR.c[rt][ct][e] = acc;
           }
+          rqr[(rt * TT + ct) * 2 + e][lane] = acc;
         }
   }
   // row j of Z as column values zc[ct][e] = z[col] and row values zr[rt] = z[row] (rows >= M: 0)
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(kMmaThreads) loglik_mma_kernel(const MmaArgs A
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           if (keep_a && row_of(rt) == M) Y.c[rt][ct][e] = X.c[rt][ct][e];  // row M of Y <- a'
-          X.c[rt][ct][e] = with_rqr ? RQR.c[rt][ct][e] : 0.0;
+          X.c[rt][ct][e] = with_rqr ? rqr[(rt * TT + ct) * 2 + e][lane] : 0.0;
         }
     mul_xwt<TT>(X, Y, T);  // [T P ; a'] T' = [T P T' ; (T a)']
   };
@@ -341,24 +348,124 @@ __global__ void __launch_bounds__(kMmaThreads) loglik_mma_kernel(const MmaArgs A
   }
 
   // ---- regular phase: the hot loop ---------------------------------------------------------------
-  for (; t < N; t++) {
-    for (int j = 0; j < p; j++) {
-      const double yv = next_y();
-      if (isnan(yv)) continue;
-      if (!P1) load_z(j);
-      non_init++;
-      double ms[TT];
-      row_dots(G, ms);
+  if constexpr (P1) {
+    // Software-pipelined form for p = 1.  With P+ = T P T' + R Q R' (the second product below),
+    //     M+ = P+ z = [T P] (T'z) + (R Q R') z,        z'a+ = a'(T'z):
+    // the next observation's M, F = z'M, 1/F, v and the gathered M[c] only need the FIRST product
+    // Y = [T P ; a'], so their shuffle / reciprocal chain (about 350 cycles of latency) is issued next to
+    // the 2 TT^3 DMMAs of the second product instead of after them.
+    double wc[TT][2], c0[TT];
+    {
+      const double* Tb = md.T.block(0, 0, 0);
+      const double* Zb = md.Z.block(0, 0, 0);
+#pragma unroll
+      for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {  // w = T'z
+          const int k = col_of(ct, e);
+          double acc = 0.0;
+          if (k < M)
+            for (int i = 0; i < M; i++) acc = fma(mat_get(Tb, md.T.diag, M, i, k), Zb[(long long)i], acc);
+          wc[ct][e] = acc;
+        }
+#pragma unroll
+      for (int rt = 0; rt < TT; rt++) {  // c0 = (R Q R') z
+        double acc = 0.0;
+#pragma unroll
+        for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) acc = fma(rqr[(rt * TT + ct) * 2 + e][lane], zc[ct][e], acc);
+        c0[rt] = quad_sum(acc);
+      }
+    }
+    // everything the update of one observation needs, prepared one step ahead
+    double ms[TT], mc[TT][2], F_star, F1, vv;
+    bool obs, upd;
+    auto prepare = [&](double yv) {  // from ms: branch-free
       double fs = 0.0;
 #pragma unroll
       for (int rt = 0; rt < TT; rt++) fs = fma(zr[rt], ms[rt], fs);
-      const double F_star = rows_sum(fs);
-      if (F_star < kEps)
-        F_eq0++;  // :173-176
-      else
-        update_star(ms, F_star, yv);
+      F_star = rows_sum(fs);
+      obs = !isnan(yv);                 // :88-90
+      upd = obs && !(F_star < kEps);    // :173
+      F1 = __drcp_rn(upd ? F_star : 1.0);
+      vv = yv - __shfl_sync(FULL, pick(ms), g_a * 4);
+      to_cols(ms, mc);
+    };
+    if (t < N) {
+      row_dots(G, ms);
+      prepare(next_y());
     }
-    if (t < N - 1) time_update(G, true, true);
+    for (; t < N; t++) {
+      if (obs) {
+        non_init++;
+        if (upd) {  // :181-194
+#pragma unroll
+          for (int rt = 0; rt < TT; rt++) {
+            const int i = row_of(rt);
+            const double rc = i < M ? ms[rt] : (i == M ? -vv : 0.0);  // row M: a += K0 v
+#pragma unroll
+            for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+              for (int e = 0; e < 2; e++) G.c[rt][ct][e] = fma(-rc, mc[ct][e] * F1, G.c[rt][ct][e]);
+          }
+          acc_log(F_star);
+          sumq = fma(vv * vv, F1, sumq);
+        } else {
+          F_eq0++;  // :173-176
+        }
+      }
+      if (t < N - 1) {  // :200-207
+        Frag<TT> Y;
+#pragma unroll
+        for (int rt = 0; rt < TT; rt++)
+#pragma unroll
+          for (int ct = 0; ct < TT; ct++) Y.c[rt][ct][0] = Y.c[rt][ct][1] = 0.0;
+        mul_xwt<TT>(Y, T, G);  // T G' = [T P , T a]
+#pragma unroll
+        for (int rt = 0; rt < TT; rt++)
+#pragma unroll
+          for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              if (row_of(rt) == M) Y.c[rt][ct][e] = G.c[rt][ct][e];  // row M of Y <- a'
+              G.c[rt][ct][e] = rqr[(rt * TT + ct) * 2 + e][lane];
+            }
+        // next observation's M (rows < M) and z'a (row M) from Y
+#pragma unroll
+        for (int rt = 0; rt < TT; rt++) {
+          double acc = 0.0;
+#pragma unroll
+          for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) acc = fma(Y.c[rt][ct][e], wc[ct][e], acc);
+          ms[rt] = quad_sum(acc) + c0[rt];
+        }
+        const double y_next = next_y();
+        mul_xwt<TT>(G, Y, T);  // [T P ; a'] T' + R Q R'
+        prepare(y_next);
+      }
+    }
+  } else {
+    for (; t < N; t++) {
+      for (int j = 0; j < p; j++) {
+        const double yv = next_y();
+        if (isnan(yv)) continue;
+        load_z(j);
+        non_init++;
+        double ms[TT];
+        row_dots(G, ms);
+        double fs = 0.0;
+#pragma unroll
+        for (int rt = 0; rt < TT; rt++) fs = fma(zr[rt], ms[rt], fs);
+        const double F_star = rows_sum(fs);
+        if (F_star < kEps)
+          F_eq0++;  // :173-176
+        else
+          update_star(ms, F_star, yv);
+      }
+      if (t < N - 1) time_update(G, true, true);
+    }
   }
 
   if (lane == 0) {
@@ -385,12 +492,12 @@ bool mma_eligible(const DModel& md, std::string* why) {
   return true;
 }
 
-template <int TT>
+template <int TT, int MINB>
 static void launch_mma_tt(const MmaArgs& A, unsigned blocks, cudaStream_t st) {
   if (A.md.p == 1)
-    loglik_mma_kernel<TT, true><<<blocks, kMmaThreads, 0, st>>>(A);
+    loglik_mma_kernel<TT, true, MINB><<<blocks, kMmaThreads, 0, st>>>(A);
   else
-    loglik_mma_kernel<TT, false><<<blocks, kMmaThreads, 0, st>>>(A);
+    loglik_mma_kernel<TT, false, MINB><<<blocks, kMmaThreads, 0, st>>>(A);
 }
 
 int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st) {
@@ -406,12 +513,22 @@ int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, dou
   const long long blocks = (A.E + wpb - 1) / wpb;
   SS_ARG(blocks < (1LL << 31), "tensor kernel: batch too large for one launch");
   const int tt = (md.m + 1 + 7) / 8;
+  // resident CTAs per SM the register budget is sized for (tuning knob)
+  static const int minb = [] {
+    const char* e = getenv("SSGPU_MMA_MINB");
+    return e ? atoi(e) : 4;  // 128 registers: measured best on B200 (profiles/README.md)
+  }();
   if (tt == 1)
-    launch_mma_tt<1>(A, (unsigned)blocks, st);
-  else if (tt == 2)
-    launch_mma_tt<2>(A, (unsigned)blocks, st);
-  else
-    launch_mma_tt<3>(A, (unsigned)blocks, st);
+    launch_mma_tt<1, 6>(A, (unsigned)blocks, st);
+  else if (tt == 2) {
+    if (minb <= 3)
+      launch_mma_tt<2, 3>(A, (unsigned)blocks, st);
+    else if (minb == 4)
+      launch_mma_tt<2, 4>(A, (unsigned)blocks, st);
+    else
+      launch_mma_tt<2, 5>(A, (unsigned)blocks, st);
+  } else
+    launch_mma_tt<3, 2>(A, (unsigned)blocks, st);
   SS_CUDA(cudaGetLastError());
   count_launch();
   set_last_kernel("loglik_mma_kernel");
