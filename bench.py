@@ -73,7 +73,8 @@ def config(n_gpus, B, extra=None):
                      "loglik + central-difference gradient (9 parameter vectors per series)",
          "series_per_gpu": B, "series_total": B * n_gpus, "timesteps": T_STEPS, "param_vectors": V,
          "l2": "inputs larger than L2 (y = %.2f GB per GPU), no flush" % (B * T_STEPS * 8 / 1e9),
-         "parallelism": f"series sharded over {n_gpus} GPU(s), no data-path collective"}
+         "parallelism": f"series sharded over {n_gpus} GPU(s), no collective in the recursion; one all-gather of "
+                        "per-series [loglik, gradient] per step when n_gpus > 1"}
     if extra:
         c.update(extra)
     return c
@@ -238,14 +239,18 @@ def run_gpu(args):
     Qd, Pd = torch.from_numpy(Qd_h).to(dev), torch.from_numpy(Pd_h).to(dev)
     model = api.BatchModel(sm, T_STEPS, B, V, Q_diag=Qd, P_star_diag=Pd, device=dev)
     out = torch.empty(V, B, device=dev, dtype=torch.float64)
-    gathered = torch.empty(world, B, 1 + K_PAR, device=dev, dtype=torch.float64) if world > 1 else None
+    from statespacer_b200 import shard
     stream = torch.cuda.current_stream(dev)
+
+    def gather():
+        # per-series [loglik, gradient] formed locally, then the one collective of the path (NCCL all-gather)
+        local = torch.cat([out[0][:, None], shard.fd_gradient(out, H_FD)], dim=1)
+        return shard.gather_series(local, B * world)
 
     def step():
         api.loglik_batch_dev(y, model, out, kernel=args.kernel, stream=stream)
         if world > 1:
-            grad = (out[1::2] - out[2::2]).T / (2 * H_FD)                  # (B, k): formed locally on each rank
-            dist.all_gather_into_tensor(gathered, torch.cat([out[0][:, None], grad], dim=1).contiguous())
+            gather()
 
     def sync():
         if world > 1:
@@ -272,8 +277,7 @@ def run_gpu(args):
         k1.record(stream)
         kern_ms.append((k0, k1))
         if world > 1:
-            grad = (out[1::2] - out[2::2]).T / (2 * H_FD)
-            dist.all_gather_into_tensor(gathered, torch.cat([out[0][:, None], grad], dim=1).contiguous())
+            gather()
     e1.record(stream)
     sync()
     launches = api.launch_count() - l0
@@ -347,7 +351,7 @@ def run_gpu(args):
             from oracle import cport, ref
             mod, kind = (ref, "reference") if ref.available() else (cport, "port")
             cores = mod.num_threads()
-            n_series = 16 * cores
+            n_series = 256 * cores
             smc, yy, Pfull, Qfull = cpu_sample(n_series)
             v_ref, dt, o_ref = time_cpu(mod, smc, yy, Pfull, Qfull)
             v_port, _, o_port = time_cpu(cport, smc, yy, Pfull, Qfull)
