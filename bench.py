@@ -108,6 +108,15 @@ def cpu_sample(n_series, seed=0):
     return sm, yy, Pfull, Qfull
 
 
+def host_cores():
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1; the CPU arm is told the
+    real count explicitly (omp_set_num_threads inside the checkers)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def time_cpu(mod, sm, yy, Pfull, Qfull, threads=0):
     t0 = time.perf_counter()
     out = mod.loglik_batch(yy, sm.a, sm.P_inf, Pfull, sm.Z[:, :, 0], sm.T[:, :, 0], sm.R[:, :, 0], Qfull, threads)
@@ -121,14 +130,14 @@ def run_reference(args):
         return
     from oracle import cport, ref
     mod, kind = (ref, "reference") if ref.available() else (cport, "port")
-    cores = mod.num_threads()
+    cores = host_cores()
     n_series = max(16, 32 * cores)
     sm, yy, Pfull, Qfull = cpu_sample(n_series)
     for _ in range(args.warmup):
-        time_cpu(mod, sm, yy, Pfull, Qfull)
+        time_cpu(mod, sm, yy, Pfull, Qfull, cores)
     times = []
     for _ in range(args.steps):
-        _, dt, _ = time_cpu(mod, sm, yy, Pfull, Qfull)
+        _, dt, _ = time_cpu(mod, sm, yy, Pfull, Qfull, cores)
         times.append(dt)
     total = sum(times)
     value = args.steps * yy.shape[0] * T_STEPS / total
@@ -350,11 +359,11 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu:
             from oracle import cport, ref
             mod, kind = (ref, "reference") if ref.available() else (cport, "port")
-            cores = mod.num_threads()
+            cores = host_cores()
             n_series = 256 * cores
             smc, yy, Pfull, Qfull = cpu_sample(n_series)
-            v_ref, dt, o_ref = time_cpu(mod, smc, yy, Pfull, Qfull)
-            v_port, _, o_port = time_cpu(cport, smc, yy, Pfull, Qfull)
+            v_ref, dt, o_ref = time_cpu(mod, smc, yy, Pfull, Qfull, cores)
+            v_port, _, o_port = time_cpu(cport, smc, yy, Pfull, Qfull, cores)
             line["cpu_baseline"] = {"value": v_ref, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"{n_series} series x {V} parameter vectors x {T_STEPS} timesteps "
                                               f"({dt:.1f} s)",

@@ -1,0 +1,45 @@
+# R-side glue for the GPU shim (replaces R/RcppExports.R of statespacer; same five stubs, same arguments --
+# R/RcppExports.R:11-99 -- plus the batched objective).  Not run in this repository's image (no R there).
+
+LogLikC <- function(y, y_isna, a, P_inf, P_star, Z, T, R, Q) {
+  .Call(`_statespacer_LogLikC`, y, y_isna, a, P_inf, P_star, Z, T, R, Q)
+}
+KalmanC <- function(y, y_isna, a, P_inf, P_star, Z, T, R, Q, diagnostics) {
+  .Call(`_statespacer_KalmanC`, y, y_isna, a, P_inf, P_star, Z, T, R, Q, diagnostics)
+}
+FastSmootherC <- function(y, a, P_inf, P_star, Z, T, R, Q, initialisation_steps, transposed_state) {
+  .Call(`_statespacer_FastSmootherC`, y, a, P_inf, P_star, Z, T, R, Q, initialisation_steps, transposed_state)
+}
+SimulateC <- function(nsim, repeat_Q, N, a, Z, T, R, Q, P_star, draw_initial, eta_only, transposed_state) {
+  .Call(`_statespacer_SimulateC`, nsim, repeat_Q, N, a, Z, T, R, Q, P_star, draw_initial, eta_only,
+        transposed_state)
+}
+ExtractComponentC <- function(a, Z) {
+  .Call(`_statespacer_ExtractComponentC`, a, Z)
+}
+
+#' Batched loglikelihood: B series x V parameter vectors in one launch.
+#'
+#' @param Y B x N matrix (one series per row, p = 1) or B x (N*p) with the p observations of a time point
+#'   adjacent; NA = missing.  Stored column-major by R, i.e. already time-major and batch-contiguous.
+#' @param V number of parameter vectors per series (1 + 2k for a central-difference gradient).
+#' @param Q_diag,P_star_diag r x (B*V) and m x (B*V) matrices of per-evaluation diagonals
+#'   (column e = (v-1)*B + b), or NULL for the shared Q / P_star of the system matrices.
+#' @return B x V matrix of loglik / N (NA where LogLikC would return NA).
+LogLikBatchC <- function(Y, V, a, P_inf, P_star, Z, T, R, Q, Q_diag = NULL, P_star_diag = NULL) {
+  Y[is.na(Y)] <- NaN
+  .Call(`_statespacer_LogLikBatchC`, Y, as.integer(V), a, P_inf, P_star, Z, T, R, Q, Q_diag, P_star_diag)
+}
+
+#' Objective + central-difference gradient for optim(gr = ...) from ONE launch (replaces the 2k sequential
+#' objective calls stats::optim makes per gradient, R/statespacer.R:977-982).  `sysmat_diag(theta)` returns the
+#' Q and P_star diagonals of the model at theta (e.g. exp(2 * theta) placed per R/statespacer.R:444-509).
+loglik_and_gradient <- function(theta, y, sysmat, sysmat_diag, h = 1e-3) {
+  k <- length(theta)
+  thetas <- cbind(theta, do.call(cbind, lapply(seq_len(k), function(i) {
+    e <- replace(numeric(k), i, h); cbind(theta + e, theta - e) })))
+  d <- lapply(seq_len(ncol(thetas)), function(j) sysmat_diag(thetas[, j]))
+  ll <- LogLikBatchC(matrix(y, nrow = 1), ncol(thetas), sysmat$a, sysmat$P_inf, sysmat$P_star, sysmat$Z, sysmat$T,
+                     sysmat$R, sysmat$Q, Q_diag = sapply(d, `[[`, "Q"), P_star_diag = sapply(d, `[[`, "P_star"))
+  list(value = ll[1, 1], gradient = (ll[1, seq(2, 2 * k, 2)] - ll[1, seq(3, 2 * k + 1, 2)]) / (2 * h))
+}

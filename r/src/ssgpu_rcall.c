@@ -1,0 +1,241 @@
+/* .Call shim: the five registered native routines of statespacer (src/RcppExports.cpp:108-115, same
+ * names, same arity) plus `_statespacer_LogLikBatchC`, implemented on libssgpu (include/ssgpu.h) with
+ * R's plain C API -- no Rcpp, no Armadillo.
+ *
+ * Build inside the package (src/Makevars):
+ *     PKG_CPPFLAGS = -I$(SSGPU_HOME)/include
+ *     PKG_LIBS     = -L$(SSGPU_HOME)/statespacer_b200 -lssgpu -Wl,-rpath,$(SSGPU_HOME)/statespacer_b200
+ * and delete LogLikC.cpp, KalmanC.cpp, FastSmootherC.cpp, SimulateC.cpp, ExtractComponentC.cpp and
+ * RcppExports.cpp from src/.  R is not installed in the image this repository is developed in, so this file
+ * is NOT compiled or tested there: everything below the boundary is exercised through the same C ABI from
+ * Python (tests/test_gpu_parity.py).
+ *
+ * Contract kept from the reference: inputs are read-only; results are freshly allocated and
+ * PROTECTed; 3-D arguments carry a length-3 dim; the RNG state is read/written around SimulateC exactly like
+ * Rcpp::RNGScope does, and the normal variates are drawn on the host with norm_rand() in the reference's
+ * order (src/SimulateC.cpp:75,112) so that R's random stream is unchanged; every call synchronises before
+ * returning; a non-zero status becomes an R error after all device work of the call has been released.
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+
+#include "ssgpu.h"
+
+static void chk(int rc) {
+  if (rc != SSGPU_OK) Rf_error("libssgpu: %s", ssgpu_last_error());
+}
+
+/* dims of a matrix / 3-D array argument: rows, cols, slices (1 if 2-D) */
+static void dims3(SEXP x, int* r, int* c, int* s) {
+  SEXP d = Rf_getAttrib(x, R_DimSymbol);
+  if (d == R_NilValue) {
+    *r = Rf_length(x); *c = 1; *s = 1;
+  } else {
+    *r = INTEGER(d)[0];
+    *c = Rf_length(d) > 1 ? INTEGER(d)[1] : 1;
+    *s = Rf_length(d) > 2 ? INTEGER(d)[2] : 1;
+  }
+}
+
+static SEXP alloc3(int a, int b, int c) {
+  SEXP x = PROTECT(Rf_alloc3DArray(REALSXP, a, b, c));
+  return x;
+}
+
+SEXP _statespacer_LogLikC(SEXP y, SEXP y_isna, SEXP a, SEXP P_inf, SEXP P_star, SEXP Z, SEXP T, SEXP R, SEXP Q) {
+  int N, p, one, m, mc, ms, zr, zc, nZ, tr, tc, nT, rr, r, nR, qr, qc, nQ;
+  dims3(y, &N, &p, &one);
+  dims3(P_star, &m, &mc, &ms);
+  dims3(Z, &zr, &zc, &nZ);
+  dims3(T, &tr, &tc, &nT);
+  dims3(R, &rr, &r, &nR);
+  dims3(Q, &qr, &qc, &nQ);
+  double out = NA_REAL;
+  chk(ssgpu_LogLikC(REAL(y), LOGICAL(y_isna), N, p, m, r, REAL(a), REAL(P_inf), REAL(P_star), REAL(Z), nZ,
+                    REAL(T), nT, REAL(R), nR, REAL(Q), nQ, &out));
+  return Rf_ScalarReal(ISNAN(out) ? NA_REAL : out); /* src/LogLikC.cpp:211-213 */
+}
+
+SEXP _statespacer_KalmanC(SEXP y, SEXP y_isna, SEXP a, SEXP P_inf, SEXP P_star, SEXP Z, SEXP T, SEXP R, SEXP Q,
+                          SEXP diagnostics) {
+  int N, p, one, m, mc, ms, zr, zc, nZ, tr, tc, nT, rr, r, nR, qr, qc, nQ, np = 0;
+  dims3(y, &N, &p, &one);
+  dims3(P_star, &m, &mc, &ms);
+  dims3(Z, &zr, &zc, &nZ);
+  dims3(T, &tr, &tc, &nT);
+  dims3(R, &rr, &r, &nR);
+  dims3(Q, &qr, &qc, &nQ);
+  ssgpu_kalman_out o;
+  memset(&o, 0, sizeof o);
+  int steps = 0;
+  o.initialisation_steps = &steps;
+  /* the list of src/KalmanC.cpp:563-593 */
+  SEXP loglik = PROTECT(Rf_allocVector(REALSXP, (R_xlen_t)N * p)); np++;
+  SEXP a_pred = PROTECT(Rf_allocMatrix(REALSXP, N, m)); np++;
+  SEXP a_fil = PROTECT(Rf_allocMatrix(REALSXP, N, m)); np++;
+  SEXP a_smooth = PROTECT(Rf_allocMatrix(REALSXP, N, m)); np++;
+  SEXP P_pred = alloc3(m, m, N); np++;
+  SEXP P_fil = alloc3(m, m, N); np++;
+  SEXP V = alloc3(m, m, N); np++;
+  SEXP P_inf_pred = alloc3(m, m, N); np++;
+  SEXP P_star_pred = alloc3(m, m, N); np++;
+  SEXP P_inf_fil = alloc3(m, m, N); np++;
+  SEXP P_star_fil = alloc3(m, m, N); np++;
+  SEXP yfit = PROTECT(Rf_allocMatrix(REALSXP, N, p)); np++;
+  SEXP v = PROTECT(Rf_allocMatrix(REALSXP, N, p)); np++;
+  SEXP eta = PROTECT(Rf_allocMatrix(REALSXP, N, r)); np++;
+  SEXP Fmat = alloc3(p, p, N); np++;
+  SEXP eta_var = alloc3(r, r, N); np++;
+  SEXP a_fc = PROTECT(Rf_allocVector(REALSXP, m)); np++;
+  SEXP P_inf_fc = PROTECT(Rf_allocMatrix(REALSXP, m, m)); np++;
+  SEXP P_star_fc = PROTECT(Rf_allocMatrix(REALSXP, m, m)); np++;
+  SEXP P_fc = PROTECT(Rf_allocMatrix(REALSXP, m, m)); np++;
+  SEXP r_vec = PROTECT(Rf_allocMatrix(REALSXP, N + 1, m)); np++;
+  SEXP Nmat = alloc3(m, m, N + 1); np++;
+  o.loglik = REAL(loglik); o.a_pred = REAL(a_pred); o.a_fil = REAL(a_fil); o.a_smooth = REAL(a_smooth);
+  o.P_pred = REAL(P_pred); o.P_fil = REAL(P_fil); o.V = REAL(V); o.P_inf_pred = REAL(P_inf_pred);
+  o.P_star_pred = REAL(P_star_pred); o.P_inf_fil = REAL(P_inf_fil); o.P_star_fil = REAL(P_star_fil);
+  o.yfit = REAL(yfit); o.v = REAL(v); o.eta = REAL(eta); o.Fmat = REAL(Fmat); o.eta_var = REAL(eta_var);
+  o.a_fc = REAL(a_fc); o.P_inf_fc = REAL(P_inf_fc); o.P_star_fc = REAL(P_star_fc); o.P_fc = REAL(P_fc);
+  o.r_vec = REAL(r_vec); o.Nmat = REAL(Nmat);
+  int rc = ssgpu_KalmanC(REAL(y), LOGICAL(y_isna), N, p, m, r, REAL(a), REAL(P_inf), REAL(P_star), REAL(Z), nZ,
+                         REAL(T), nT, REAL(R), nR, REAL(Q), nQ, Rf_asLogical(diagnostics), &o);
+  if (rc != SSGPU_OK) { UNPROTECT(np); chk(rc); }
+  for (R_xlen_t i = 0; i < (R_xlen_t)N * p; i++)
+    if (ISNAN(REAL(loglik)[i])) REAL(loglik)[i] = NA_REAL; /* src/KalmanC.cpp:194 */
+  const char* nested_names[] = {"initialisation_steps", "loglik", "a_pred", "a_fil", "a_smooth", "P_pred", "P_fil",
+                                "V", "P_inf_pred", ""};
+  SEXP nested = PROTECT(Rf_mkNamed(VECSXP, nested_names)); np++;
+  SET_VECTOR_ELT(nested, 0, Rf_ScalarInteger(steps));
+  SET_VECTOR_ELT(nested, 1, loglik); SET_VECTOR_ELT(nested, 2, a_pred); SET_VECTOR_ELT(nested, 3, a_fil);
+  SET_VECTOR_ELT(nested, 4, a_smooth); SET_VECTOR_ELT(nested, 5, P_pred); SET_VECTOR_ELT(nested, 6, P_fil);
+  SET_VECTOR_ELT(nested, 7, V); SET_VECTOR_ELT(nested, 8, P_inf_pred);
+  const char* names[] = {"nested", "P_star_pred", "P_inf_fil", "P_star_fil", "yfit", "v", "eta", "Fmat", "eta_var",
+                         "a_fc", "P_inf_fc", "P_star_fc", "P_fc", "r_vec", "Nmat", ""};
+  SEXP res = PROTECT(Rf_mkNamed(VECSXP, names)); np++;
+  SEXP vals[] = {nested, P_star_pred, P_inf_fil, P_star_fil, yfit, v, eta, Fmat, eta_var, a_fc, P_inf_fc, P_star_fc,
+                 P_fc, r_vec, Nmat};
+  for (int i = 0; i < 15; i++) SET_VECTOR_ELT(res, i, vals[i]);
+  UNPROTECT(np);
+  return res;
+}
+
+SEXP _statespacer_FastSmootherC(SEXP y, SEXP a, SEXP P_inf, SEXP P_star, SEXP Z, SEXP T, SEXP R, SEXP Q,
+                                SEXP initialisation_steps, SEXP transposed_state) {
+  int N, p, nsim, m, mc, ms, zr, zc, nZ, tr, tc, nT, rr, r, nR, qr, qc, nQ;
+  dims3(y, &N, &p, &nsim);
+  dims3(P_star, &m, &mc, &ms);
+  dims3(Z, &zr, &zc, &nZ);
+  dims3(T, &tr, &tc, &nT);
+  dims3(R, &rr, &r, &nR);
+  dims3(Q, &qr, &qc, &nQ);
+  const int tst = Rf_asLogical(transposed_state);
+  SEXP a_smooth = alloc3(N, m, nsim), a_t = alloc3(m, nsim, N), eta = alloc3(N, r, nsim);
+  if (!tst) memset(REAL(a_t), 0, sizeof(double) * (size_t)m * nsim * N);
+  int rc = ssgpu_FastSmootherC(REAL(y), N, p, nsim, m, r, REAL(a), REAL(P_inf), REAL(P_star), REAL(Z), nZ, REAL(T),
+                               nT, REAL(R), nR, REAL(Q), nQ, Rf_asInteger(initialisation_steps), tst, REAL(a_smooth),
+                               tst ? REAL(a_t) : NULL, REAL(eta));
+  if (rc != SSGPU_OK) { UNPROTECT(3); chk(rc); }
+  const char* names[] = {"a_smooth", "a_t", "eta", ""}; /* src/FastSmootherC.cpp:370-374 */
+  SEXP res = PROTECT(Rf_mkNamed(VECSXP, names));
+  SET_VECTOR_ELT(res, 0, a_smooth); SET_VECTOR_ELT(res, 1, a_t); SET_VECTOR_ELT(res, 2, eta);
+  UNPROTECT(4);
+  return res;
+}
+
+SEXP _statespacer_SimulateC(SEXP nsim_, SEXP repeat_Q_, SEXP N_, SEXP a, SEXP Z, SEXP T, SEXP R, SEXP Q, SEXP P_star,
+                            SEXP draw_initial_, SEXP eta_only_, SEXP transposed_state_) {
+  const int nsim = Rf_asInteger(nsim_), repeat_Q = Rf_asInteger(repeat_Q_), N = Rf_asInteger(N_);
+  const int draw_initial = Rf_asLogical(draw_initial_), eta_only = Rf_asLogical(eta_only_),
+            tst = Rf_asLogical(transposed_state_);
+  int p, zc, nZ, tr, tc, nT, rr, rR, nR, r, qc, nQ, mP, mPc, mPs;
+  const int m = Rf_length(a);
+  dims3(Z, &p, &zc, &nZ);
+  dims3(T, &tr, &tc, &nT);
+  dims3(R, &rr, &rR, &nR);
+  dims3(Q, &r, &qc, &nQ);
+  dims3(P_star, &mP, &mPc, &mPs);
+  const int r_tot = r * repeat_Q;
+  /* the variates Rcpp::rnorm would return, in the reference's call order (src/SimulateC.cpp:75,112) */
+  const R_xlen_t n_draws = (draw_initial ? (R_xlen_t)m * nsim : 0) + (R_xlen_t)N * r_tot * nsim;
+  double* draws = (double*)R_alloc(n_draws, sizeof(double));
+  GetRNGstate();
+  for (R_xlen_t i = 0; i < n_draws; i++) draws[i] = norm_rand();
+  PutRNGstate();
+  SEXP y = alloc3(N, p, nsim), a_out = alloc3(N, m, nsim), a_t = alloc3(m, nsim, N), eta = alloc3(N, r_tot, nsim);
+  if (!tst || eta_only) memset(REAL(a_t), 0, sizeof(double) * (size_t)m * nsim * N);
+  if (eta_only) {
+    memset(REAL(y), 0, sizeof(double) * (size_t)N * p * nsim);
+    memset(REAL(a_out), 0, sizeof(double) * (size_t)N * m * nsim);
+  }
+  int rc = ssgpu_SimulateC(nsim, repeat_Q, N, p, m, rR, r, mP, REAL(a), REAL(Z), nZ, REAL(T), nT, REAL(R), nR, REAL(Q),
+                           nQ, REAL(P_star), draw_initial, eta_only, tst, draws, (long long)n_draws, NULL, NULL, REAL(y),
+                           REAL(a_out), tst ? REAL(a_t) : NULL, REAL(eta));
+  if (rc != SSGPU_OK) { UNPROTECT(4); chk(rc); }
+  const char* names[] = {"y", "a", "a_t", "eta", ""}; /* src/SimulateC.cpp:133-138 */
+  SEXP res = PROTECT(Rf_mkNamed(VECSXP, names));
+  SET_VECTOR_ELT(res, 0, y); SET_VECTOR_ELT(res, 1, a_out); SET_VECTOR_ELT(res, 2, a_t); SET_VECTOR_ELT(res, 3, eta);
+  UNPROTECT(5);
+  return res;
+}
+
+SEXP _statespacer_ExtractComponentC(SEXP a, SEXP Z) {
+  int m, nsim, N, p, zc, nZ;
+  dims3(a, &m, &nsim, &N);
+  dims3(Z, &p, &zc, &nZ);
+  SEXP out = alloc3(N, p, nsim);
+  int rc = ssgpu_ExtractComponentC(REAL(a), m, nsim, N, REAL(Z), p, nZ, REAL(out));
+  if (rc != SSGPU_OK) { UNPROTECT(1); chk(rc); }
+  UNPROTECT(1);
+  return out;
+}
+
+/* New: E = B x V evaluations in one launch.  y: (N*p) x B matrix (time-major rows, one column per series:
+ * R's column-major storage of t(y_b) stacked is NOT batch-contiguous, so the R glue passes t(Y) with Y the
+ * B x (N*p) matrix -- see r/R/ssgpu_glue.R).  Q_diag, P_star_diag: r x (B*V) and m x (B*V) matrices of
+ * per-evaluation diagonals (evaluation e = v*B + b), or NULL to use the shared Q / P_star. */
+SEXP _statespacer_LogLikBatchC(SEXP yt, SEXP V_, SEXP a, SEXP P_inf, SEXP P_star, SEXP Z, SEXP T, SEXP R, SEXP Q,
+                               SEXP Q_diag, SEXP P_star_diag) {
+  int B, Np, one, m, mc, ms, p, zc, nZ, tr, tc, nT, rr, r, nR, qr, qc, nQ;
+  const int V = Rf_asInteger(V_);
+  dims3(yt, &B, &Np, &one); /* B x (N*p): element [b + B*q] = y_b[q]  == y[q*B + b] */
+  dims3(P_star, &m, &mc, &ms);
+  dims3(Z, &p, &zc, &nZ);
+  dims3(T, &tr, &tc, &nT);
+  dims3(R, &rr, &r, &nR);
+  dims3(Q, &qr, &qc, &nQ);
+  ssgpu_model mo;
+  memset(&mo, 0, sizeof mo);
+  mo.N = Np / p; mo.p = p; mo.m = m; mo.r = r;
+  mo.a = (ssgpu_matrix){REAL(a), m, 1, 0, 1, 0, 0};
+  mo.P_inf = (ssgpu_matrix){REAL(P_inf), m, m, 0, 1, 0, 0};
+  mo.P_star = P_star_diag == R_NilValue ? (ssgpu_matrix){REAL(P_star), m, m, 0, 1, 0, 0}
+                                        : (ssgpu_matrix){REAL(P_star_diag), m, m, 1, 1, m, (long long)m * B};
+  mo.Z = (ssgpu_matrix){REAL(Z), p, m, 0, nZ, 0, 0};
+  mo.T = (ssgpu_matrix){REAL(T), m, m, 0, nT, 0, 0};
+  mo.R = (ssgpu_matrix){REAL(R), m, r, 0, nR, 0, 0};
+  mo.Q = Q_diag == R_NilValue ? (ssgpu_matrix){REAL(Q), r, r, 0, nQ, 0, 0}
+                              : (ssgpu_matrix){REAL(Q_diag), r, r, 1, 1, r, (long long)r * B};
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, B, V));
+  int rc = ssgpu_loglik_batch(REAL(yt), B, V, &mo, SSGPU_KERNEL_AUTO, REAL(out));
+  if (rc != SSGPU_OK) { UNPROTECT(1); chk(rc); }
+  for (R_xlen_t i = 0; i < (R_xlen_t)B * V; i++)
+    if (ISNAN(REAL(out)[i])) REAL(out)[i] = NA_REAL;
+  UNPROTECT(1);
+  return out;
+}
+
+static const R_CallMethodDef CallEntries[] = {
+    {"_statespacer_ExtractComponentC", (DL_FUNC)&_statespacer_ExtractComponentC, 2},
+    {"_statespacer_FastSmootherC", (DL_FUNC)&_statespacer_FastSmootherC, 10},
+    {"_statespacer_KalmanC", (DL_FUNC)&_statespacer_KalmanC, 10},
+    {"_statespacer_LogLikC", (DL_FUNC)&_statespacer_LogLikC, 9},
+    {"_statespacer_SimulateC", (DL_FUNC)&_statespacer_SimulateC, 12},
+    {"_statespacer_LogLikBatchC", (DL_FUNC)&_statespacer_LogLikBatchC, 11},
+    {NULL, NULL, 0}};
+
+void R_init_statespacer(DllInfo* dll) {
+  R_registerRoutines(dll, NULL, CallEntries, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}
