@@ -66,6 +66,20 @@ __device__ __forceinline__ void mul_xwt(Frag<TT>& Z, const Frag<TT>& X, const Fr
         for (int nt = 0; nt < TT; nt++) dmma(Z.c[rt][nt][0], Z.c[rt][nt][1], X.c[rt][ct][e], W.c[nt][ct][e]);
 }
 
+// Same, but only the tiles on or above the diagonal (rt <= nt): for a symmetric result the rest is mirrored
+// by the caller -- TT(TT-1) TT fewer DMMAs, paid with a few shuffles on otherwise idle pipes.
+template <int TT>
+__device__ __forceinline__ void mul_xwt_upper(Frag<TT>& Z, const Frag<TT>& X, const Frag<TT>& W) {
+#pragma unroll
+  for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+      for (int rt = 0; rt < TT; rt++)
+#pragma unroll
+        for (int nt = rt; nt < TT; nt++) dmma(Z.c[rt][nt][0], Z.c[rt][nt][1], X.c[rt][ct][e], W.c[nt][ct][e]);
+}
+
 template <int TT, bool P1, int MINB>
 __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const MmaArgs A) {
   constexpr unsigned FULL = 0xffffffffu;
@@ -237,14 +251,47 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
 #pragma unroll
     for (int rt = 0; rt < TT; rt++) {
       const int i = row_of(rt);
-      const double rc = i < M ? ms[rt] : (i == M ? -vv : 0.0);  // row M: a += K0 v
+      const double rc = (i < M ? ms[rt] : (i == M ? -vv : 0.0)) * F1;  // row M: a += K0 v
 #pragma unroll
       for (int ct = 0; ct < TT; ct++)
 #pragma unroll
-        for (int e = 0; e < 2; e++) G.c[rt][ct][e] = fma(-rc, mc[ct][e] * F1, G.c[rt][ct][e]);
+        for (int e = 0; e < 2; e++) G.c[rt][ct][e] = fma(-rc, mc[ct][e], G.c[rt][ct][e]);
     }
     acc_log(F_star);
     sumq = fma(vv * vv, F1, sumq);
+  };
+
+  // Second product of the time update, X = init + [Y ; a'] T', exploiting the symmetry of T P T' + R Q R':
+  // tiles below the diagonal are not multiplied but mirrored from above (8x8 tile transpose in accumulator
+  // layout: element (2q+e, g) sits in lane (2q+e)*4 + g/2, half g%2), and the part of the state row that
+  // falls into them, (T a)[n], is fetched from column M of Y = [T P , T a] where the first product left it.
+  auto second_product = [&](Frag<TT>& X, const Frag<TT>& Y, bool keep_a) {
+    mul_xwt_upper<TT>(X, Y, T);
+    if constexpr (TT > 1) {
+      const int ct_m = M >> 3, q_m = (M & 7) >> 1, e_m = M & 1;  // where column M of Y lives
+#pragma unroll
+      for (int rt = 1; rt < TT; rt++)
+#pragma unroll
+        for (int nt = 0; nt < rt; nt++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const int src = (2 * q + e) * 4 + (g >> 1);
+            const double lo = __shfl_sync(FULL, X.c[nt][rt][0], src);
+            const double hi = __shfl_sync(FULL, X.c[nt][rt][1], src);
+            double val = (g & 1) ? hi : lo;  // X[8nt + 2q+e][8rt + g]
+            if (keep_a) {
+              // (T a)[8nt + 2q + e] = Y[8nt+2q+e][M]
+              double ya = Y.c[nt][0][0];
+#pragma unroll
+              for (int ct = 0; ct < TT; ct++) {
+                if (ct == ct_m) ya = e_m ? Y.c[nt][ct][1] : Y.c[nt][ct][0];
+              }
+              const double ta = __shfl_sync(FULL, ya, (2 * q + e) * 4 + q_m);
+              if (row_of(rt) == M) val = ta;
+            }
+            X.c[rt][nt][e] = val;
+          }
+    }
   };
 
   // [Y ; a'] T' with Y = T G'  (+ R Q R')
@@ -264,7 +311,7 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
           if (keep_a && row_of(rt) == M) Y.c[rt][ct][e] = X.c[rt][ct][e];  // row M of Y <- a'
           X.c[rt][ct][e] = with_rqr ? rqr[(rt * TT + ct) * 2 + e][lane] : 0.0;
         }
-    mul_xwt<TT>(X, Y, T);  // [T P ; a'] T' = [T P T' ; (T a)']
+    second_product(X, Y, keep_a);  // [T P ; a'] T' = [T P T' ; (T a)']
   };
 
   int t = 0;
@@ -403,11 +450,11 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
 #pragma unroll
           for (int rt = 0; rt < TT; rt++) {
             const int i = row_of(rt);
-            const double rc = i < M ? ms[rt] : (i == M ? -vv : 0.0);  // row M: a += K0 v
+            const double rc = (i < M ? ms[rt] : (i == M ? -vv : 0.0)) * F1;  // row M: a += K0 v
 #pragma unroll
             for (int ct = 0; ct < TT; ct++)
 #pragma unroll
-              for (int e = 0; e < 2; e++) G.c[rt][ct][e] = fma(-rc, mc[ct][e] * F1, G.c[rt][ct][e]);
+              for (int e = 0; e < 2; e++) G.c[rt][ct][e] = fma(-rc, mc[ct][e], G.c[rt][ct][e]);
           }
           acc_log(F_star);
           sumq = fma(vv * vv, F1, sumq);
@@ -442,7 +489,7 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
           ms[rt] = quad_sum(acc) + c0[rt];
         }
         const double y_next = next_y();
-        mul_xwt<TT>(G, Y, T);  // [T P ; a'] T' + R Q R'
+        second_product(G, Y, true);  // [T P ; a'] T' + R Q R'
         prepare(y_next);
       }
     }
