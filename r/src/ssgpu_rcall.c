@@ -93,6 +93,19 @@ SEXP _statespacer_KalmanC(SEXP y, SEXP y_isna, SEXP a, SEXP P_inf, SEXP P_star, 
   SEXP P_fc = PROTECT(Rf_allocMatrix(REALSXP, m, m)); np++;
   SEXP r_vec = PROTECT(Rf_allocMatrix(REALSXP, N + 1, m)); np++;
   SEXP Nmat = alloc3(m, m, N + 1); np++;
+  /* diagnostics arrays exist in the list either way (src/KalmanC.cpp:563-593); v_norm defaults to NA (:81) */
+  SEXP v_norm = PROTECT(Rf_allocMatrix(REALSXP, N, p)); np++;
+  SEXP e = PROTECT(Rf_allocMatrix(REALSXP, N, p)); np++;
+  SEXP D = alloc3(p, p, N); np++;
+  SEXP Tstat_observation = PROTECT(Rf_allocMatrix(REALSXP, N, p)); np++;
+  SEXP Tstat_state = PROTECT(Rf_allocMatrix(REALSXP, N + 1, m)); np++;
+  for (R_xlen_t i = 0; i < (R_xlen_t)N * p; i++) { REAL(v_norm)[i] = NA_REAL; REAL(e)[i] = 0; REAL(Tstat_observation)[i] = 0; }
+  memset(REAL(D), 0, sizeof(double) * (size_t)p * p * N);
+  memset(REAL(Tstat_state), 0, sizeof(double) * (size_t)(N + 1) * m);
+  if (Rf_asLogical(diagnostics)) {
+    o.v_norm = REAL(v_norm); o.e = REAL(e); o.D = REAL(D);
+    o.Tstat_observation = REAL(Tstat_observation); o.Tstat_state = REAL(Tstat_state);
+  }
   o.loglik = REAL(loglik); o.a_pred = REAL(a_pred); o.a_fil = REAL(a_fil); o.a_smooth = REAL(a_smooth);
   o.P_pred = REAL(P_pred); o.P_fil = REAL(P_fil); o.V = REAL(V); o.P_inf_pred = REAL(P_inf_pred);
   o.P_star_pred = REAL(P_star_pred); o.P_inf_fil = REAL(P_inf_fil); o.P_star_fil = REAL(P_star_fil);
@@ -111,12 +124,18 @@ SEXP _statespacer_KalmanC(SEXP y, SEXP y_isna, SEXP a, SEXP P_inf, SEXP P_star, 
   SET_VECTOR_ELT(nested, 1, loglik); SET_VECTOR_ELT(nested, 2, a_pred); SET_VECTOR_ELT(nested, 3, a_fil);
   SET_VECTOR_ELT(nested, 4, a_smooth); SET_VECTOR_ELT(nested, 5, P_pred); SET_VECTOR_ELT(nested, 6, P_fil);
   SET_VECTOR_ELT(nested, 7, V); SET_VECTOR_ELT(nested, 8, P_inf_pred);
-  const char* names[] = {"nested", "P_star_pred", "P_inf_fil", "P_star_fil", "yfit", "v", "eta", "Fmat", "eta_var",
-                         "a_fc", "P_inf_fc", "P_star_fc", "P_fc", "r_vec", "Nmat", ""};
+  if (Rf_asLogical(diagnostics))
+    for (R_xlen_t i = 0; i < (R_xlen_t)N * p; i++) {
+      if (ISNAN(REAL(v_norm)[i])) REAL(v_norm)[i] = NA_REAL;
+      if (ISNAN(REAL(e)[i])) REAL(e)[i] = NA_REAL;
+    }
+  const char* names[] = {"nested", "P_star_pred", "P_inf_fil", "P_star_fil", "yfit", "v", "v_norm", "eta", "e", "Fmat",
+                         "eta_var", "D", "a_fc", "P_inf_fc", "P_star_fc", "P_fc", "Tstat_observation", "Tstat_state",
+                         "r_vec", "Nmat", ""};
   SEXP res = PROTECT(Rf_mkNamed(VECSXP, names)); np++;
-  SEXP vals[] = {nested, P_star_pred, P_inf_fil, P_star_fil, yfit, v, eta, Fmat, eta_var, a_fc, P_inf_fc, P_star_fc,
-                 P_fc, r_vec, Nmat};
-  for (int i = 0; i < 15; i++) SET_VECTOR_ELT(res, i, vals[i]);
+  SEXP vals[] = {nested, P_star_pred, P_inf_fil, P_star_fil, yfit, v, v_norm, eta, e, Fmat, eta_var, D, a_fc, P_inf_fc,
+                 P_star_fc, P_fc, Tstat_observation, Tstat_state, r_vec, Nmat};
+  for (int i = 0; i < 20; i++) SET_VECTOR_ELT(res, i, vals[i]);
   UNPROTECT(np);
   return res;
 }

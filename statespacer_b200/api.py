@@ -94,8 +94,10 @@ def LogLikC(y, y_isna, a, P_inf, P_star, Z, T, R, Q):
     return out.value
 
 
-def kalman_shapes(N, p, m, r):
-    return {
+def kalman_shapes(N, p, m, r, diagnostics=False):
+    extra = {"v_norm": (N, p), "e": (N, p), "D": (p, p, N), "Tstat_observation": (N, p),
+             "Tstat_state": (N + 1, m)} if diagnostics else {}
+    return {**extra,
         "loglik": (N * p,), "a_pred": (N, m), "a_fil": (N, m), "a_smooth": (N, m),
         "P_pred": (m, m, N), "P_fil": (m, m, N), "V": (m, m, N), "P_inf_pred": (m, m, N),
         "P_star_pred": (m, m, N), "P_inf_fil": (m, m, N), "P_star_fil": (m, m, N),
@@ -105,7 +107,7 @@ def kalman_shapes(N, p, m, r):
 
 
 def KalmanC(y, y_isna, a, P_inf, P_star, Z, T, R, Q, diagnostics=False):
-    """src/KalmanC.cpp:21-594 (diagnostics = FALSE): filter + smoother for one series."""
+    """src/KalmanC.cpp:21-594: filter + smoother (+ diagnostics) for one series."""
     y = _f(y)
     isna = None if y_isna is None else np.asfortranarray(np.asarray(y_isna).astype(np.int32))
     a, P_inf, P_star, Z, T, R, Q = _prep(a, P_inf, P_star, Z, T, R, Q)
@@ -113,7 +115,7 @@ def KalmanC(y, y_isna, a, P_inf, P_star, Z, T, R, Q, diagnostics=False):
     m, p, r = _dims(a, P_inf, P_star, Z, T, R, Q, N)
     if y.shape[1] != p:
         raise ValueError("y does not match Z")
-    out = {k: np.zeros(s, order="F") for k, s in kalman_shapes(N, p, m, r).items()}
+    out = {k: np.zeros(s, order="F") for k, s in kalman_shapes(N, p, m, r, diagnostics).items()}
     steps = C.c_int()
     st = native.KalmanOut()
     st.initialisation_steps = C.pointer(steps)

@@ -276,7 +276,6 @@ int ssgpu_KalmanC(const double* y, const int* y_isna, int N, int p, int m, int r
                   const double* Q, int nQ, int diagnostics, ssgpu_kalman_out* out) {
   SS_ARG(y && a && P_inf && P_star && Z && T && R && Q && out, "null pointer argument");
   SS_TRY(check_single(N, p, m, r, nZ, nT, nR, nQ));
-  SS_ARG(!diagnostics, "KalmanC diagnostics (v_norm, e, D, Tstat_*) are not implemented yet");
   SS_TRY(ensure_device());
   cudaStream_t st = lib_stream();
   SingleModel S;
@@ -313,12 +312,18 @@ int ssgpu_KalmanC(const double* y, const int* y_isna, int N, int p, int m, int r
       {&out->P_fc, &d.P_fc, mm},
       {&out->r_vec, &d.r_vec, (size_t)(N + 1) * m},
       {&out->Nmat, &d.Nmat, mm * (N + 1)},
+      {&out->v_norm, &d.v_norm, diagnostics ? Np : 0},
+      {&out->e, &d.e, diagnostics ? Np : 0},
+      {&out->D, &d.D, diagnostics ? (size_t)p * p * N : 0},
+      {&out->Tstat_observation, &d.Tstat_observation, diagnostics ? Np : 0},
+      {&out->Tstat_state, &d.Tstat_state, diagnostics ? (size_t)(N + 1) * m : 0},
   };
   size_t total = 0;
   auto pad = [](size_t n) { return (n + 31) / 32 * 32; };
   for (auto& x : f) total += pad(x.n);
   const bool qtr_tv = nQ > 1 || nR > 1;
-  const size_t n_scr = pad(Np) * 3 + pad(Np * m) * 2 + pad((size_t)(qtr_tv ? N : 1) * r * m) + pad(Np) + 32;
+  const size_t n_diag = diagnostics ? pad(2 * (size_t)N * m * p) : 0;
+  const size_t n_scr = pad(Np) * 3 + pad(Np * m) * 2 + pad((size_t)(qtr_tv ? N : 1) * r * m) + pad(Np) + 32 + n_diag;
   DevBuf blk;
   SS_TRY(blk.alloc((total + n_scr) * sizeof(double), st));
   double* base = blk.as<double>();
@@ -336,12 +341,14 @@ int ssgpu_KalmanC(const double* y, const int* y_isna, int N, int p, int m, int r
   s.QtR = base + off; off += pad((size_t)(qtr_tv ? N : 1) * r * m);
   s.code = reinterpret_cast<int*>(base + off); off += pad(Np);
   d.initialisation_steps = reinterpret_cast<int*>(base + off); off += 32;
+  double* diag_scr = base + off; off += n_diag;
 
   const double* yd = S.dev.as<double>() + S.oy;
   SS_TRY(launch_fwd_generic(S.md, yd, 1, 1, nullptr, &d, &s, st));
   SS_TRY(launch_bwd_generic(S.md, &d, &s, st));
+  if (diagnostics) SS_TRY(launch_kalman_diag(S.md, &d, s.code, diag_scr, st));
   for (auto& x : f)
-    if (*x.host)
+    if (*x.host && x.n)
       SS_CUDA(cudaMemcpyAsync(*x.host, *x.dev, x.n * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (out->initialisation_steps)
     SS_CUDA(cudaMemcpyAsync(out->initialisation_steps, d.initialisation_steps, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -107,6 +107,9 @@ class DevBuf {
 int launch_fwd_generic(const DModel& md, const double* y, long long B, int V, double* out_loglik,
                        const ssgpu_kalman_out* kout, const KalmanScratch* scratch, cudaStream_t st);
 int launch_gains_generic(const DModel& md, int init_steps, const KalmanScratch* scratch, cudaStream_t st);
+// KalmanC diagnostics (kalman_diag.cu); scratch: 2*N*m*p doubles; needs P_pred, P_inf_pred, Fmat, v, r_vec, Nmat
+int launch_kalman_diag(const DModel& md, const ssgpu_kalman_out* kout, const int* code, double* scratch,
+                       cudaStream_t st);
 int launch_bwd_generic(const DModel& md, const ssgpu_kalman_out* kout, const KalmanScratch* scratch,
                        cudaStream_t st);
 

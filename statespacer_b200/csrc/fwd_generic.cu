@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
           if (init) init_steps++;
           if (tid == 0) {
             if (A.k.loglik) A.k.loglik[index] = nan("");
-            A.s.code[index] = 0;
+            A.s.code[index] = init ? 256 : 0;
           }
         }
         continue;

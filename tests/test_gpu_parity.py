@@ -114,6 +114,33 @@ def test_kalman_random_models(shape):
     _kalman_check(Case("r", simulate_y(rng, sm, N, missing=0.1), sm), tol=1e-8 if shape["d"] else RTOL)
 
 
+@pytest.mark.parametrize("shape", [dict(m=2, p=1, d=1, tv=()), dict(m=5, p=2, d=2, tv=("Z",)),
+                                   dict(m=8, p=3, d=0, tv=("T", "Q")), dict(m=14, p=8, d=0, tv=())])
+def test_kalman_diagnostics(shape):
+    """diagnostics = TRUE: v_norm, e, D, Tstat_* (src/KalmanC.cpp:164-187,528-544)."""
+    rng = np.random.default_rng(21)
+    N = 30
+    sm = random_model(rng, shape["m"], shape["p"], d=shape["d"], tv=shape["tv"], N=N)
+    c = Case("diag", simulate_y(rng, sm, N, missing=0.1), sm)
+    want = ref.KalmanC(*c.args(), True) if ref.available() else kalman_np.KalmanC(*c.args(), True)
+    got = api.KalmanC(*c.args(), True)
+    for k in ("v_norm", "e", "D", "Tstat_observation"):
+        assert rel(got[k], want[k]) <= 1e-7, (k, rel(got[k], want[k]))
+    assert rel(got["Tstat_state"][1:], want["Tstat_state"][1:]) <= 1e-7
+    for k in KALMAN_KEYS:
+        assert rel(got[k], want[k]) <= (1e-8 if shape["d"] else RTOL), k
+
+
+def test_kalman_diagnostics_nile():
+    nile = load_series("nile.txt")[:, None]
+    sm = sysmat.nile_local_level(15100.252, 1468.724)
+    got = api.KalmanC(nile, np.isnan(nile), *sm.args(), True)
+    want = kalman_np.KalmanC(nile, np.isnan(nile), *sm.args(), True)
+    for k in ("v_norm", "e", "D", "Tstat_observation"):
+        assert rel(got[k], want[k]) <= 1e-8, k
+    assert math.isnan(got["v_norm"][0, 0]) and not math.isnan(got["v_norm"][1, 0])   # diffuse first step
+
+
 def test_kalman_missing_airline():
     """SURVEY.md appendix C probe: airline with 6 NaNs -> initialisation_steps = 19."""
     air = np.log(load_series("airpassengers.txt")).copy()
