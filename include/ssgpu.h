@@ -147,7 +147,10 @@ typedef struct ssgpu_model {
 #define SSGPU_KERNEL_AUTO 0     /* tensor kernel when the model qualifies, else column kernel, else generic */
 #define SSGPU_KERNEL_GENERIC 1  /* one CTA per evaluation, any shape */
 #define SSGPU_KERNEL_COLS 2     /* column-per-lane DFMA kernel (m <= 15); SSGPU_E_ARG if not eligible */
-#define SSGPU_KERNEL_MMA 3      /* warp-per-evaluation FP64 tensor (DMMA) kernel (m <= 23); SSGPU_E_ARG if not eligible */
+#define SSGPU_KERNEL_MMA 3      /* warp-per-evaluation FP64 tensor (DMMA) kernel (m <= 23); SSGPU_E_ARG if not eligible.
+                                   States are re-ordered internally so that the all-zero 8 x 8 tiles of a block-
+                                   diagonal T are skipped (results equal up to summation order) */
+#define SSGPU_KERNEL_MMA_DENSE 4 /* same kernel, caller's state order, every tile multiplied */
 
 /* host pointers everywhere (y, the matrices' data, out); copies in, runs, copies out, synchronises */
 int ssgpu_loglik_batch(const double* y, long long B, int V, const ssgpu_model* model, int kernel,
@@ -158,6 +161,13 @@ int ssgpu_loglik_batch_dev(const double* y, long long B, int V, const ssgpu_mode
                            double* out, void* stream);
 /* name of the kernel the last ssgpu_loglik_batch[_dev] call on this thread launched */
 const char* ssgpu_last_kernel(void);
+
+/* Host-only helper (no device needed): the internal state order the tensor kernel would use for a shared
+ * m x m transition matrix T (column-major, m <= 23).  perm[i] = caller's index of the state at internal
+ * position i; *tile_mask has bit rt*TT + ct set when the 8 x 8 tile (rt, ct) of the re-ordered T holds a
+ * non-zero (TT = ceil((m+1)/8)); *dmma_per_step = DMMA instructions one time update then issues.  Any output
+ * pointer may be NULL. */
+int ssgpu_plan_state_order(const double* T, int m, int* perm, unsigned* tile_mask, int* dmma_per_step);
 
 /* ---- 7. Measurement helpers ---------------------------------------------------------------
  * FP64 FMA-pipe peak of the current device, measured with a register-resident DFMA chain kernel

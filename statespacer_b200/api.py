@@ -16,9 +16,10 @@ import ctypes as C
 import numpy as np
 
 from . import native
-from .native import KERNEL_AUTO, KERNEL_COLS, KERNEL_GENERIC, KERNEL_MMA  # noqa: F401
+from .native import KERNEL_AUTO, KERNEL_COLS, KERNEL_GENERIC, KERNEL_MMA, KERNEL_MMA_DENSE  # noqa: F401
 
-_KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "cols": KERNEL_COLS, "mma": KERNEL_MMA}
+_KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "cols": KERNEL_COLS, "mma": KERNEL_MMA,
+            "mma_dense": KERNEL_MMA_DENSE}
 
 
 def _f(x):
@@ -73,6 +74,17 @@ def fp64_peak(mode=0, iters=2000, repeats=5):
     tf, ms = C.c_double(), C.c_double()
     native.check(native.lib().ssgpu_fp64_peak(mode, iters, repeats, C.byref(tf), C.byref(ms)))
     return tf.value, ms.value
+
+
+def plan_state_order(T):
+    """Internal state order of the tensor kernel for a shared transition matrix T (host-only helper):
+    (perm, tile_mask, dmma_per_step), see include/ssgpu.h."""
+    T = _f(np.asarray(T, dtype=np.float64).reshape(np.shape(T)[0], np.shape(T)[1]))
+    m = T.shape[0]
+    perm = np.zeros(m, dtype=np.int32)
+    mask, n = C.c_uint(), C.c_int()
+    native.check(native.lib().ssgpu_plan_state_order(T.ctypes.data, m, perm.ctypes.data, C.byref(mask), C.byref(n)))
+    return perm, mask.value, n.value
 
 
 # ---- the five reference routines ------------------------------------------------------------------

@@ -204,9 +204,10 @@ static int dispatch_batch(const DModel& md, const double* y_dev, long long B, in
   SS_ARG(B >= 1 && V >= 1, "B and V must be positive");
   std::string why;
   const bool mma_ok = mma_eligible(md, &why);
-  if (kernel == SSGPU_KERNEL_MMA) SS_ARG(mma_ok, "tensor kernel not eligible: " + why);
-  if (kernel == SSGPU_KERNEL_MMA || (kernel == SSGPU_KERNEL_AUTO && mma_ok))
-    return launch_loglik_mma(md, y_dev, B, V, out_dev, st);
+  if (kernel == SSGPU_KERNEL_MMA || kernel == SSGPU_KERNEL_MMA_DENSE)
+    SS_ARG(mma_ok, "tensor kernel not eligible: " + why);
+  if (kernel == SSGPU_KERNEL_MMA || kernel == SSGPU_KERNEL_MMA_DENSE || (kernel == SSGPU_KERNEL_AUTO && mma_ok))
+    return launch_loglik_mma(md, y_dev, B, V, out_dev, kernel != SSGPU_KERNEL_MMA_DENSE, st);
   const bool cols_ok = cols_eligible(md, &why);
   if (kernel == SSGPU_KERNEL_COLS) SS_ARG(cols_ok, "column kernel not eligible: " + why);
   if (kernel == SSGPU_KERNEL_COLS || (kernel == SSGPU_KERNEL_AUTO && cols_ok))

@@ -150,7 +150,8 @@ int launch_permute_at(const double* src, double* dst, int N, int m, long long S,
 
 // Warp-per-evaluation FP64 tensor kernel (loglik_mma.cu)
 bool mma_eligible(const DModel& md, std::string* why);
-int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st);
+int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, double* out, bool tile_sparse,
+                      cudaStream_t st);
 
 // Column-per-thread register kernel (loglik_cols.cu)
 bool cols_eligible(const DModel& md, std::string* why);

@@ -24,6 +24,7 @@
 // uniform: there is no divergence and no predication anywhere.
 // Measurement update in the rank-1 forms P - M K0' (src/LogLikC.cpp:129,193), P* - M* K0' - M_inf K1',
 // P_inf - M_inf K0' (:151-152); sum(log F) carried as (mantissa product, exponent sum).
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -39,6 +40,7 @@ struct MmaArgs {
   long long B;
   long long E;  // B * V
   double* out;
+  signed char perm[24];  // internal state order: position i holds state perm[i] (plan_tiles)
 };
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -53,9 +55,18 @@ struct Frag {
   double c[TT][TT][2];
 };
 
-// Z = init + X W'   (all C layout)
-template <int TT>
-__device__ __forceinline__ void mul_xwt(Frag<TT>& Z, const Frag<TT>& X, const Frag<TT>& W) {
+// TM: which 8 x 8 tiles of the (padded, internally ordered) T hold a non-zero, bit rt*TT + ct.  The host orders
+// the states so that T becomes as tile-sparse as its coupling graph allows (plan_tiles below: statespacer's
+// T is block diagonal by construction, R/GetSysMat.R:1388-1426) and the DMMAs of all-zero tiles are not
+// compiled in -- a template parameter, not a branch, so the DMMA stream stays one straight-line block.
+template <int TT, unsigned TM>
+__device__ __forceinline__ constexpr bool tile_on(int rt, int ct) {
+  return (TM >> (rt * TT + ct)) & 1u;
+}
+
+// Y = init + T W'   (all C layout): tile (rt, nt) += T(rt, ct) W(nt, ct)'
+template <int TT, unsigned TM>
+__device__ __forceinline__ void mul_t_wt(Frag<TT>& Y, const Frag<TT>& T, const Frag<TT>& W) {
 #pragma unroll
   for (int ct = 0; ct < TT; ct++)
 #pragma unroll
@@ -63,13 +74,14 @@ __device__ __forceinline__ void mul_xwt(Frag<TT>& Z, const Frag<TT>& X, const Fr
 #pragma unroll
       for (int rt = 0; rt < TT; rt++)
 #pragma unroll
-        for (int nt = 0; nt < TT; nt++) dmma(Z.c[rt][nt][0], Z.c[rt][nt][1], X.c[rt][ct][e], W.c[nt][ct][e]);
+        for (int nt = 0; nt < TT; nt++)
+          if (tile_on<TT, TM>(rt, ct)) dmma(Y.c[rt][nt][0], Y.c[rt][nt][1], T.c[rt][ct][e], W.c[nt][ct][e]);
 }
 
-// Same, but only the tiles on or above the diagonal (rt <= nt): for a symmetric result the rest is mirrored
-// by the caller -- TT(TT-1) TT fewer DMMAs, paid with a few shuffles on otherwise idle pipes.
-template <int TT>
-__device__ __forceinline__ void mul_xwt_upper(Frag<TT>& Z, const Frag<TT>& X, const Frag<TT>& W) {
+// Z = init + Y T', only the tiles on or above the diagonal (rt <= nt): for a symmetric result the rest is
+// mirrored by the caller -- TT(TT-1) TT fewer DMMAs, paid with a few shuffles on otherwise idle pipes.
+template <int TT, unsigned TM>
+__device__ __forceinline__ void mul_y_tt_upper(Frag<TT>& Z, const Frag<TT>& Y, const Frag<TT>& T) {
 #pragma unroll
   for (int ct = 0; ct < TT; ct++)
 #pragma unroll
@@ -77,10 +89,11 @@ __device__ __forceinline__ void mul_xwt_upper(Frag<TT>& Z, const Frag<TT>& X, co
 #pragma unroll
       for (int rt = 0; rt < TT; rt++)
 #pragma unroll
-        for (int nt = rt; nt < TT; nt++) dmma(Z.c[rt][nt][0], Z.c[rt][nt][1], X.c[rt][ct][e], W.c[nt][ct][e]);
+        for (int nt = rt; nt < TT; nt++)
+          if (tile_on<TT, TM>(nt, ct)) dmma(Z.c[rt][nt][0], Z.c[rt][nt][1], Y.c[rt][ct][e], T.c[nt][ct][e]);
 }
 
-template <int TT, bool P1, int MINB>
+template <int TT, unsigned TM, bool P1, int MINB>
 __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const MmaArgs A) {
   constexpr unsigned FULL = 0xffffffffu;
   const DModel& md = A.md;
@@ -96,6 +109,7 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
 
   auto row_of = [&](int rt) { return 8 * rt + g; };
   auto col_of = [&](int ct, int e) { return 8 * ct + 2 * q + e; };
+  auto pm = [&](int i) { return (int)A.perm[i]; };  // internal position -> state index of the caller
 
   // ---- shared matrices into fragments: T (zero padded), z --------------------------------------
   Frag<TT> T, G;
@@ -114,8 +128,8 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
         for (int e = 0; e < 2; e++) {
           const int i = row_of(rt), k = col_of(ct, e);
           const bool in = i < M && k < M;
-          T.c[rt][ct][e] = in ? mat_get(Tb, md.T.diag, M, i, k) : 0.0;
-          G.c[rt][ct][e] = in ? mat_get(Ps, md.P_star.diag, M, i, k) : ((i == M && k < M) ? ab[k] : 0.0);
+          T.c[rt][ct][e] = in ? mat_get(Tb, md.T.diag, M, pm(i), pm(k)) : 0.0;
+          G.c[rt][ct][e] = in ? mat_get(Ps, md.P_star.diag, M, pm(i), pm(k)) : ((i == M && k < M) ? ab[pm(k)] : 0.0);
         }
     // R Q R' (src/LogLikC.cpp:202, hoisted: Q and R are time-invariant here)
     const double* Qb = md.Q.block(b, v, 0);
@@ -129,15 +143,16 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
           const int i = row_of(rt), cidx = col_of(ct, e);
           double acc = 0.0;
           if (i < M && cidx < M) {
+            const int pi = pm(i), pc = pm(cidx);
             for (int k = 0; k < r; k++) {
-              const double rik = mat_get(Rb, md.R.diag, M, i, k);
+              const double rik = mat_get(Rb, md.R.diag, M, pi, k);
               if (rik == 0.0) continue;
               double qr;
               if (md.Q.diag) {
-                qr = Qb[k] * mat_get(Rb, md.R.diag, M, cidx, k);
+                qr = Qb[k] * mat_get(Rb, md.R.diag, M, pc, k);
               } else {
                 qr = 0.0;
-                for (int l = 0; l < r; l++) qr = fma(Qb[k + (long long)l * r], mat_get(Rb, md.R.diag, M, cidx, l), qr);
+                for (int l = 0; l < r; l++) qr = fma(Qb[k + (long long)l * r], mat_get(Rb, md.R.diag, M, pc, l), qr);
               }
               acc = fma(rik, qr, acc);
             }
@@ -154,10 +169,10 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
 #pragma unroll
       for (int e = 0; e < 2; e++) {
         const int k = col_of(ct, e);
-        zc[ct][e] = k < M ? Zb[j + (long long)k * p] : 0.0;
+        zc[ct][e] = k < M ? Zb[j + (long long)pm(k) * p] : 0.0;
       }
       const int i = row_of(ct);
-      zr[ct] = i < M ? Zb[j + (long long)i * p] : 0.0;
+      zr[ct] = i < M ? Zb[j + (long long)pm(i) * p] : 0.0;
     }
   };
   if (P1) load_z(0);
@@ -266,7 +281,7 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
   // layout: element (2q+e, g) sits in lane (2q+e)*4 + g/2, half g%2), and the part of the state row that
   // falls into them, (T a)[n], is fetched from column M of Y = [T P , T a] where the first product left it.
   auto second_product = [&](Frag<TT>& X, const Frag<TT>& Y, bool keep_a) {
-    mul_xwt_upper<TT>(X, Y, T);
+    mul_y_tt_upper<TT, TM>(X, Y, T);
     if constexpr (TT > 1) {
       const int ct_m = M >> 3, q_m = (M & 7) >> 1, e_m = M & 1;  // where column M of Y lives
 #pragma unroll
@@ -301,7 +316,7 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
     for (int rt = 0; rt < TT; rt++)
 #pragma unroll
       for (int ct = 0; ct < TT; ct++) Y.c[rt][ct][0] = Y.c[rt][ct][1] = 0.0;
-    mul_xwt<TT>(Y, T, X);  // T X' = [T P , T a]
+    mul_t_wt<TT, TM>(Y, T, X);  // T X' = [T P , T a]
 #pragma unroll
     for (int rt = 0; rt < TT; rt++)
 #pragma unroll
@@ -326,7 +341,7 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
 #pragma unroll
         for (int e = 0; e < 2; e++) {
           const int i = row_of(rt), k = col_of(ct, e);
-          Ginf.c[rt][ct][e] = (i < M && k < M) ? mat_get(Pi, md.P_inf.diag, M, i, k) : 0.0;
+          Ginf.c[rt][ct][e] = (i < M && k < M) ? mat_get(Pi, md.P_inf.diag, M, pm(i), pm(k)) : 0.0;
         }
     bool init = !abs_small(Ginf);  // :49
     for (; t < N && init; t++) {
@@ -412,7 +427,7 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
           const int k = col_of(ct, e);
           double acc = 0.0;
           if (k < M)
-            for (int i = 0; i < M; i++) acc = fma(mat_get(Tb, md.T.diag, M, i, k), Zb[(long long)i], acc);
+            for (int i = 0; i < M; i++) acc = fma(mat_get(Tb, md.T.diag, M, i, pm(k)), Zb[(long long)i], acc);
           wc[ct][e] = acc;
         }
 #pragma unroll
@@ -468,7 +483,7 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
         for (int rt = 0; rt < TT; rt++)
 #pragma unroll
           for (int ct = 0; ct < TT; ct++) Y.c[rt][ct][0] = Y.c[rt][ct][1] = 0.0;
-        mul_xwt<TT>(Y, T, G);  // T G' = [T P , T a]
+        mul_t_wt<TT, TM>(Y, T, G);  // T G' = [T P , T a]
 #pragma unroll
         for (int rt = 0; rt < TT; rt++)
 #pragma unroll
@@ -539,15 +554,108 @@ bool mma_eligible(const DModel& md, std::string* why) {
   return true;
 }
 
-template <int TT, int MINB>
-static void launch_mma_tt(const MmaArgs& A, unsigned blocks, cudaStream_t st) {
-  if (A.md.p == 1)
-    loglik_mma_kernel<TT, true, MINB><<<blocks, kMmaThreads, 0, st>>>(A);
-  else
-    loglik_mma_kernel<TT, false, MINB><<<blocks, kMmaThreads, 0, st>>>(A);
+// ---- state ordering that makes T tile-sparse ------------------------------------------------------
+// States i, k are coupled when T[i][k] or T[k][i] is non-zero.  Coupled components are packed whole into the
+// 8-state tiles (exact search: at most 23 components, 3 tiles); inside a tile the caller's order is kept.
+// statespacer models are block diagonal in T by construction (residuals: zero rows/columns, level, slope,
+// trigonometric seasonal / cycle pairs, regressor coefficients: blocks of size 1-2), so they pack; a SARIMA
+// companion block larger than a tile does not and runs dense in the caller's order.
+struct TilePlan {
+  signed char perm[24];
+  unsigned mask;  // bit rt*TT + ct of the ordered T
+};
+
+static bool pack_components(const std::vector<std::vector<int>>& comps, size_t idx, int* cap, int n_bins,
+                            std::vector<int>& bin_of) {
+  if (idx == comps.size()) return true;
+  const int sz = (int)comps[idx].size();
+  for (int b = 0; b < n_bins; b++) {
+    if (cap[b] < sz) continue;
+    bool dup = false;  // bins with equal remaining capacity are interchangeable
+    for (int b2 = 0; b2 < b; b2++) dup = dup || (cap[b2] == cap[b]);
+    if (dup) continue;
+    cap[b] -= sz;
+    bin_of[idx] = b;
+    if (pack_components(comps, idx + 1, cap, n_bins, bin_of)) return true;
+    cap[b] += sz;
+  }
+  return false;
 }
 
-int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st) {
+static unsigned tile_mask_of(const std::vector<double>& Th, int diag, int m, int tt, const signed char* perm) {
+  unsigned mask = 0;
+  for (int i = 0; i < m; i++)
+    for (int k = 0; k < m; k++)
+      if (mat_get(Th.data(), diag, m, perm[i], perm[k]) != 0.0) mask |= 1u << ((i >> 3) * tt + (k >> 3));
+  return mask;
+}
+
+static TilePlan plan_tiles(const std::vector<double>& Th, int diag, int m, int tt, bool allow_reorder) {
+  TilePlan pl{};
+  for (int i = 0; i < 24; i++) pl.perm[i] = (signed char)(i < m ? i : 0);
+  const unsigned dense = (1u << (tt * tt)) - 1u;
+  pl.mask = dense;
+  if (!allow_reorder || tt == 1) return pl;
+  // components of the coupling graph (union-find)
+  std::vector<int> root(m);
+  for (int i = 0; i < m; i++) root[i] = i;
+  auto find = [&](int x) {
+    while (root[x] != x) x = root[x] = root[root[x]];
+    return x;
+  };
+  for (int i = 0; i < m; i++)
+    for (int k = 0; k < m; k++)
+      if (i != k && mat_get(Th.data(), diag, m, i, k) != 0.0) root[find(i)] = find(k);
+  std::vector<std::vector<int>> comps;
+  {
+    std::vector<int> id(m, -1);
+    for (int i = 0; i < m; i++) {
+      const int rr = find(i);
+      if (id[rr] < 0) {
+        id[rr] = (int)comps.size();
+        comps.emplace_back();
+      }
+      comps[id[rr]].push_back(i);
+    }
+  }
+  std::stable_sort(comps.begin(), comps.end(),
+                   [](const std::vector<int>& x, const std::vector<int>& y) { return x.size() > y.size(); });
+  int cap[3] = {0, 0, 0};
+  const int n_bins = (m + 7) / 8;
+  for (int b = 0; b < n_bins; b++) cap[b] = std::min(8, m - 8 * b);
+  std::vector<int> bin_of(comps.size(), 0);
+  if (!pack_components(comps, 0, cap, n_bins, bin_of)) return pl;  // a component larger than a tile: dense
+  int pos = 0;
+  for (int b = 0; b < n_bins; b++) {
+    std::vector<int> members;
+    for (size_t c = 0; c < comps.size(); c++)
+      if (bin_of[c] == b) members.insert(members.end(), comps[c].begin(), comps[c].end());
+    std::sort(members.begin(), members.end());
+    for (int s : members) pl.perm[pos++] = (signed char)s;
+  }
+  pl.mask = tile_mask_of(Th, diag, m, tt, pl.perm);
+  return pl;
+}
+
+template <int TT, unsigned TM, int MINB>
+static void launch_mma_tt(const MmaArgs& A, unsigned blocks, cudaStream_t st) {
+  if (A.md.p == 1)
+    loglik_mma_kernel<TT, TM, true, MINB><<<blocks, kMmaThreads, 0, st>>>(A);
+  else
+    loglik_mma_kernel<TT, TM, false, MINB><<<blocks, kMmaThreads, 0, st>>>(A);
+}
+
+// DMMAs per time update for tile mask `mask` (first product: all column tiles; second: upper tiles only)
+int mma_dmma_per_step(int tt, unsigned mask) {
+  int n = 0;
+  for (int rt = 0; rt < tt; rt++)
+    for (int ct = 0; ct < tt; ct++)
+      if ((mask >> (rt * tt + ct)) & 1u) n += 2 * tt + 2 * (rt + 1);  // T(rt,ct): tt tiles of Y; T(nt=rt,ct): rt+1 tiles
+  return n;
+}
+
+int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, double* out, bool tile_sparse,
+                      cudaStream_t st) {
   std::string why;
   SS_ARG(mma_eligible(md, &why), "tensor kernel not eligible: " + why);
   MmaArgs A{};
@@ -560,26 +668,65 @@ int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, dou
   const long long blocks = (A.E + wpb - 1) / wpb;
   SS_ARG(blocks < (1LL << 31), "tensor kernel: batch too large for one launch");
   const int tt = (md.m + 1 + 7) / 8;
+  // T is shared and small: fetch it to plan the state order (a few microseconds next to a batched launch)
+  std::vector<double> Th((size_t)(md.T.diag ? md.m : md.m * md.m));
+  if (tile_sparse && tt > 1) {
+    SS_CUDA(cudaMemcpyAsync(Th.data(), md.T.p, Th.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
+  }
+  TilePlan pl = plan_tiles(Th, md.T.diag, md.m, tt, tile_sparse);
+  const unsigned dense = (1u << (tt * tt)) - 1u;
+  constexpr unsigned kDiag2 = 0x9u, kDiag3 = 0x111u;
+  unsigned use = dense;
+  if (tt == 2 && (pl.mask & ~kDiag2) == 0) use = kDiag2;
+  if (tt == 3 && (pl.mask & ~kDiag3) == 0) use = kDiag3;
+  if (use == dense)  // nothing to gain: keep the caller's order
+    for (int i = 0; i < 24; i++) pl.perm[i] = (signed char)(i < md.m ? i : 0);
+  for (int i = 0; i < 24; i++) A.perm[i] = pl.perm[i];
   // resident CTAs per SM the register budget is sized for (tuning knob)
   static const int minb = [] {
     const char* e = getenv("SSGPU_MMA_MINB");
     return e ? atoi(e) : 4;  // 128 registers: measured best on B200 (profiles/README.md)
   }();
   if (tt == 1)
-    launch_mma_tt<1, 6>(A, (unsigned)blocks, st);
+    launch_mma_tt<1, 0x1u, 6>(A, (unsigned)blocks, st);
   else if (tt == 2) {
-    if (minb <= 3)
-      launch_mma_tt<2, 3>(A, (unsigned)blocks, st);
-    else if (minb == 4)
-      launch_mma_tt<2, 4>(A, (unsigned)blocks, st);
+    if (use == kDiag2) {
+      if (minb <= 3)
+        launch_mma_tt<2, kDiag2, 3>(A, (unsigned)blocks, st);
+      else if (minb == 4)
+        launch_mma_tt<2, kDiag2, 4>(A, (unsigned)blocks, st);
+      else
+        launch_mma_tt<2, kDiag2, 5>(A, (unsigned)blocks, st);
+    } else {
+      launch_mma_tt<2, 0xFu, 4>(A, (unsigned)blocks, st);
+    }
+  } else {
+    if (use == kDiag3)
+      launch_mma_tt<3, kDiag3, 2>(A, (unsigned)blocks, st);
     else
-      launch_mma_tt<2, 5>(A, (unsigned)blocks, st);
-  } else
-    launch_mma_tt<3, 2>(A, (unsigned)blocks, st);
+      launch_mma_tt<3, 0x1FFu, 2>(A, (unsigned)blocks, st);
+  }
   SS_CUDA(cudaGetLastError());
   count_launch();
-  set_last_kernel("loglik_mma_kernel");
+  static thread_local char name[96];
+  snprintf(name, sizeof name, "loglik_mma_kernel<TT=%d,tiles=0x%x,dmma_per_step=%d>", tt, use,
+           mma_dmma_per_step(tt, use));
+  set_last_kernel(name);
   return SSGPU_OK;
 }
 
 }  // namespace ssgpu
+
+extern "C" int ssgpu_plan_state_order(const double* T, int m, int* perm, unsigned* tile_mask, int* dmma_per_step) {
+  using namespace ssgpu;
+  SS_ARG(T != nullptr && m >= 1 && m <= kMmaMaxM, "ssgpu_plan_state_order: need T and 1 <= m <= 23");
+  const int tt = (m + 1 + 7) / 8;
+  std::vector<double> Th(T, T + (size_t)m * m);
+  const TilePlan pl = plan_tiles(Th, 0, m, tt, true);
+  if (perm)
+    for (int i = 0; i < m; i++) perm[i] = pl.perm[i];
+  if (tile_mask) *tile_mask = pl.mask;
+  if (dmma_per_step) *dmma_per_step = mma_dmma_per_step(tt, pl.mask);
+  return SSGPU_OK;
+}

@@ -46,9 +46,9 @@ class KalmanOut(C.Structure):
 SYMBOLS = ["ssgpu_version", "ssgpu_last_error", "ssgpu_set_device", "ssgpu_device_count", "ssgpu_release",
            "ssgpu_launch_count", "ssgpu_LogLikC", "ssgpu_KalmanC", "ssgpu_FastSmootherC", "ssgpu_SimulateC",
            "ssgpu_sym_root", "ssgpu_ExtractComponentC", "ssgpu_loglik_batch", "ssgpu_loglik_batch_dev",
-           "ssgpu_last_kernel", "ssgpu_fp64_peak"]
+           "ssgpu_last_kernel", "ssgpu_fp64_peak", "ssgpu_plan_state_order"]
 
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS, KERNEL_MMA = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS, KERNEL_MMA, KERNEL_MMA_DENSE = 0, 1, 2, 3, 4
 
 
 def lib():
@@ -73,6 +73,7 @@ def lib():
         L.ssgpu_loglik_batch.argtypes = [vp, ll, i, C.POINTER(Model), i, vp]
         L.ssgpu_loglik_batch_dev.argtypes = [vp, ll, i, C.POINTER(Model), i, vp, vp]
         L.ssgpu_fp64_peak.argtypes = [i, i, i, dp, dp]
+        L.ssgpu_plan_state_order.argtypes = [vp, i, vp, vp, vp]
         L.ssgpu_device_count.argtypes = [ip]
         L.ssgpu_set_device.argtypes = [i]
         _lib = L

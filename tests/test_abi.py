@@ -55,3 +55,65 @@ def test_no_cpu_fallback():
     with pytest.raises(native.SsgpuError) as e:
         api.LogLikC(y, np.isnan(y), *sm.args())
     assert e.value.status == 2
+
+
+# ---- host logic of the tensor kernel: state order that makes T tile-sparse (no device needed) ----------------
+def _tile_mask(T, perm):
+    m = T.shape[0]
+    tt = (m + 1 + 7) // 8
+    Tp = T[np.ix_(perm, perm)]
+    mask = 0
+    for i in range(m):
+        for k in range(m):
+            if Tp[i, k] != 0:
+                mask |= 1 << ((i // 8) * tt + k // 8)
+    return mask
+
+
+def test_state_order_config5_is_tile_diagonal():
+    """Config 5 (R/Components-Unobserved.R:150-159,504-519): the trigonometric pairs (j, j+5) straddle the two
+    8-state tiles in the caller's order; re-ordered, T is tile diagonal and a time update needs 14 DMMAs, not 28."""
+    from statespacer_b200 import api, sysmat
+    T = sysmat.bsm12(np.zeros(4)).T[:, :, 0]
+    ident = np.arange(14)
+    assert _tile_mask(T, ident) == 0xF
+    perm, mask, n = api.plan_state_order(T)
+    assert sorted(perm) == list(range(14))
+    assert mask == 0x9 and _tile_mask(T, perm) == 0x9 and n == 14
+    # coupled states stay in one tile
+    for i in range(14):
+        for k in range(14):
+            if T[perm[i], perm[k]] != 0:
+                assert i // 8 == k // 8
+
+
+def test_state_order_dense_and_oversized_components():
+    from statespacer_b200 import api, sysmat
+    rng = np.random.default_rng(0)
+    T = rng.normal(size=(12, 12))
+    perm, mask, n = api.plan_state_order(T)
+    assert list(perm) == list(range(12)) and mask == 0xF and n == 28
+    # airline model: one 27-state companion component cannot be packed, m = 28 is outside the kernel anyway
+    T = np.zeros((20, 20))
+    T[np.arange(19), np.arange(1, 20)] = 1.0          # a 20-state shift chain: one component > 8
+    perm, mask, n = api.plan_state_order(T)
+    assert list(perm) == list(range(20)) and mask == 0x1FF
+    # three tiles, components of size 3 + 3 + 3 + 2 + 2 + 2 + 1 + 1 = 17 pack into 8 / 8 / 1
+    T = np.zeros((17, 17))
+    blocks = [[0, 9, 16], [1, 2, 3], [4, 10, 11], [5, 6], [7, 8], [12, 13], [14], [15]]
+    for blk in blocks:
+        for i in blk:
+            for k in blk:
+                T[i, k] = rng.normal()
+    perm, mask, n = api.plan_state_order(T)
+    assert sorted(perm) == list(range(17)) and mask == 0x111 and _tile_mask(T, perm) == 0x111
+    # diagonal T (regression coefficients, local levels): already tile diagonal, caller's order kept
+    perm, mask, n = api.plan_state_order(np.eye(10))
+    assert list(perm) == list(range(10)) and mask == 0x9
+
+
+def test_state_order_rejects_bad_arguments():
+    L = native.lib()
+    assert L.ssgpu_plan_state_order(None, 5, None, None, None) == 1
+    T = np.eye(30)
+    assert L.ssgpu_plan_state_order(T.ctypes.data, 30, None, None, None) == 1

@@ -165,10 +165,11 @@ def _bsm_batch(rng, B, N, V, missing):
     return thetas, Qd, Pd, y
 
 
-KERNEL_NAMES = {"mma": "loglik_mma", "cols": "loglik_cols", "generic": "fwd_generic"}
+KERNEL_NAMES = {"mma": "loglik_mma_kernel<TT=2,tiles=0x9,", "mma_dense": "loglik_mma_kernel<TT=2,tiles=0xf,",
+                "cols": "loglik_cols", "generic": "fwd_generic"}
 
 
-@pytest.mark.parametrize("kernel", ["mma", "cols", "generic"])
+@pytest.mark.parametrize("kernel", ["mma", "mma_dense", "cols", "generic"])
 def test_batch_config5_shape(kernel):
     rng = np.random.default_rng(5)
     B, N, V = 70, 60, 3
@@ -207,6 +208,48 @@ def test_batch_every_state_dim(m):
         assert abs(got[b] - want) <= tol, (m, b, got[b], want)
         assert abs(gen[b] - want) <= tol, (m, b, gen[b], want)
         assert abs(cols[b] - want) <= tol, (m, b, cols[b], want)
+
+
+def _block_diagonal_model(rng, m, p, d, N, scatter=True):
+    """Random model whose T is block diagonal with blocks of size 1-3 scattered over the state vector, so
+    that the tensor kernel has to re-order the states to reach a tile-diagonal T."""
+    sm = random_model(rng, m, p, d=d, N=N)
+    order = rng.permutation(m) if scatter else np.arange(m)
+    T = np.zeros((m, m))
+    i = 0
+    while i < m:
+        k = min(m - i, int(rng.integers(1, 4)))
+        idx = order[i:i + k]
+        blk = rng.normal(size=(k, k)) * 0.4 + 0.6 * np.eye(k)
+        T[np.ix_(idx, idx)] = blk
+        i += k
+    return sysmat.SysMat(Z=sm.Z, T=T[:, :, None], R=sm.R, Q=sm.Q, a=sm.a, P_inf=sm.P_inf, P_star=sm.P_star)
+
+
+@pytest.mark.parametrize("m,p", [(9, 1), (10, 2), (14, 1), (15, 1), (16, 2), (17, 1), (20, 1), (23, 3)])
+def test_batch_tile_sparse_state_order(m, p):
+    """Tensor kernel with the states re-ordered internally (block-diagonal T -> all-zero tiles skipped) against
+    the same kernel in the caller's order with every tile multiplied, and against the oracle."""
+    rng = np.random.default_rng(700 + m)
+    B, N = 10, 40
+    sm = _block_diagonal_model(rng, m, p, d=min(3, m - 1), N=N)
+    perm, mask, n_dmma = api.plan_state_order(sm.T[:, :, 0])
+    tt = (m + 1 + 7) // 8
+    use = 0x9 if tt == 2 else 0x111                      # the tile-diagonal instantiation
+    assert mask & ~use == 0, hex(mask)
+    y = np.stack([simulate_y(rng, sm, N, missing=0.1) for _ in range(B)], axis=2)
+    Qb = np.stack([sm.Q[:, :, 0] * (1 + 0.1 * b) for b in range(B)])
+    got = api.loglik_batch(y, sm, Q=Qb, kernel="mma")
+    assert f"tiles={hex(use)}," in api.last_kernel(), api.last_kernel()
+    dense = api.loglik_batch(y, sm, Q=Qb, kernel="mma_dense")
+    assert f"tiles={hex((1 << tt * tt) - 1)}," in api.last_kernel()
+    for b in range(B):
+        smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=Qb[b][:, :, None], a=sm.a, P_inf=sm.P_inf, P_star=sm.P_star)
+        yb = y[:, :, b]
+        want = cport.LogLikC(yb, np.isnan(yb), *smb.args())
+        tol = 1e-8 * max(1, abs(want))
+        assert abs(got[b] - want) <= tol, (m, b, got[b], want)
+        assert abs(dense[b] - want) <= tol, (m, b, dense[b], want)
 
 
 def test_batch_multivariate_dns():
