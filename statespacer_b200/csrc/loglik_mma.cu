@@ -44,7 +44,7 @@ struct MmaArgs {
 };
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
@@ -67,10 +67,11 @@ __device__ __forceinline__ constexpr bool tile_on(int rt, int ct) {
 // Y = init + T W'   (all C layout): tile (rt, nt) += T(rt, ct) W(nt, ct)'
 template <int TT, unsigned TM>
 __device__ __forceinline__ void mul_t_wt(Frag<TT>& Y, const Frag<TT>& T, const Frag<TT>& W) {
+  // k-steps outermost: the DMMAs that accumulate into one tile are as far apart as the tile count allows
 #pragma unroll
-  for (int ct = 0; ct < TT; ct++)
+  for (int e = 0; e < 2; e++)
 #pragma unroll
-    for (int e = 0; e < 2; e++)
+    for (int ct = 0; ct < TT; ct++)
 #pragma unroll
       for (int rt = 0; rt < TT; rt++)
 #pragma unroll
@@ -83,9 +84,9 @@ __device__ __forceinline__ void mul_t_wt(Frag<TT>& Y, const Frag<TT>& T, const F
 template <int TT, unsigned TM>
 __device__ __forceinline__ void mul_y_tt_upper(Frag<TT>& Z, const Frag<TT>& Y, const Frag<TT>& T) {
 #pragma unroll
-  for (int ct = 0; ct < TT; ct++)
+  for (int e = 0; e < 2; e++)
 #pragma unroll
-    for (int e = 0; e < 2; e++)
+    for (int ct = 0; ct < TT; ct++)
 #pragma unroll
       for (int rt = 0; rt < TT; rt++)
 #pragma unroll
@@ -93,19 +94,34 @@ __device__ __forceinline__ void mul_y_tt_upper(Frag<TT>& Z, const Frag<TT>& Y, c
           if (tile_on<TT, TM>(nt, ct)) dmma(Z.c[rt][nt][0], Z.c[rt][nt][1], Y.c[rt][ct][e], T.c[nt][ct][e]);
 }
 
+// 1 / x for a finite, normal x well inside the exponent range (F >= 1e-7 here): MUFU.RCP64H seed (about 20
+// bits) and two Newton steps; no special-case branch, the result is within an ulp or two of the rounded one.
+__device__ __forceinline__ double rcp_newton(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
 template <int TT, unsigned TM, bool P1, int MINB>
 __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const MmaArgs A) {
   constexpr unsigned FULL = 0xffffffffu;
+  // The state vector rides along as the LAST row of the D x D fragment matrix (row MA = D - 1, a compile-time
+  // position: tile row TT-1, g = 7; as a column: tile TT-1, q = 3, e = 1).  Rows / columns M .. MA-1 are zero
+  // padding and stay exactly zero through every operation below, so the hot loop carries no "i < M" masks.
+  constexpr int MA = 8 * TT - 1, LA = TT - 1;
   const DModel& md = A.md;
   const int N = md.N, p = P1 ? 1 : md.p, M = md.m, r = md.r;
   const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const bool lane_a = g == 7;  // this lane holds row MA in the fragments of tile row LA
   // warps are numbered series-major (w = b*V + v) so that the V parameter vectors of a series run side by
   // side and share its y through L1/L2; results keep the public order e = v*B + b
   const long long w_id = (long long)blockIdx.x * (kMmaThreads / 32) + (threadIdx.x >> 5);
   if (w_id >= A.E) return;  // whole warp
   const long long V = A.E / A.B, b = w_id / V, v = w_id % V;
   const long long e_id = v * A.B + b;
-  const int rt_a = M >> 3, g_a = M & 7;  // the state vector is row M
 
   auto row_of = [&](int rt) { return 8 * rt + g; };
   auto col_of = [&](int ct, int e) { return 8 * ct + 2 * q + e; };
@@ -129,7 +145,7 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
           const int i = row_of(rt), k = col_of(ct, e);
           const bool in = i < M && k < M;
           T.c[rt][ct][e] = in ? mat_get(Tb, md.T.diag, M, pm(i), pm(k)) : 0.0;
-          G.c[rt][ct][e] = in ? mat_get(Ps, md.P_star.diag, M, pm(i), pm(k)) : ((i == M && k < M) ? ab[pm(k)] : 0.0);
+          G.c[rt][ct][e] = in ? mat_get(Ps, md.P_star.diag, M, pm(i), pm(k)) : ((i == MA && k < M) ? ab[pm(k)] : 0.0);
         }
     // R Q R' (src/LogLikC.cpp:202, hoisted: Q and R are time-invariant here)
     const double* Qb = md.Q.block(b, v, 0);
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
     x += __shfl_xor_sync(FULL, x, 16);
     return x;
   };
-  // m[rt] = (X z)[row]: known to the 4 lanes of the quad that owns the row
+  // m[rt] = (X z)[row]: known to the 4 lanes of the quad that owns the row (row MA: z'a)
   auto row_dots = [&](const Frag<TT>& X, double (&m)[TT]) {
 #pragma unroll
     for (int rt = 0; rt < TT; rt++) {
@@ -201,23 +217,16 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
       m[rt] = quad_sum(acc);
     }
   };
-  // mc[ct][e] = m[col] for col < M (else 0): row `col` belongs to quad (2q+e), slot ct
+  // mc[ct][e] = m[col]: row `col` belongs to quad (2q+e), slot ct.  Column MA receives z'a instead of a zero;
+  // it only ever meets the zero column MA of T and is overwritten by the next time update.
   auto to_cols = [&](const double (&m)[TT], double (&mc)[TT][2]) {
 #pragma unroll
     for (int ct = 0; ct < TT; ct++)
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const double x = __shfl_sync(FULL, m[ct], (2 * q + e) * 4);
-        mc[ct][e] = col_of(ct, e) < M ? x : 0.0;
-      }
+      for (int e = 0; e < 2; e++) mc[ct][e] = __shfl_sync(FULL, m[ct], (2 * q + e) * 4);
   };
-  // m[rt_a] without dynamic register indexing
-  auto pick = [&](const double (&m)[TT]) {
-    double x = m[0];
-#pragma unroll
-    for (int rt = 1; rt < TT; rt++) x = rt_a == rt ? m[rt] : x;
-    return x;
-  };
+  // z'a = entry MA of m
+  auto z_dot_a = [&](const double (&m)[TT]) { return __shfl_sync(FULL, m[LA], 7 * 4); };
   auto abs_small = [&](const Frag<TT>& X) {
     bool ok = true;
 #pragma unroll
@@ -238,7 +247,6 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
     const int ex = ((hi >> 20) & 0x7ff) - 1023;
     esum += ex;
     prod = __hiloint2double(hi - (ex << 20), __double2loint(prod));
-    n_terms++;
   };
 
   // y: 32 flat indices (t*p + j) at a time, one per lane, one chunk ahead
@@ -256,34 +264,38 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
     return __shfl_sync(FULL, ybuf, ql);
   };
 
-  // P* L0' = P* - M K0' applied to G = [P* ; a'] (src/LogLikC.cpp:181-194 / 117-130)
-  auto update_star = [&](const double (&ms)[TT], double F_star, double yv) {
-    const double F1 = __drcp_rn(F_star);
-    const double za = __shfl_sync(FULL, pick(ms), g_a * 4);
-    const double vv = yv - za;
+  // rank-1 measurement update G <- G - rc mc' with rc = M F1 on the state rows and -v F1 on row MA (a += K0 v)
+  auto rank1 = [&](const double (&ms)[TT], double F1, double vv) {
     double mc[TT][2];
     to_cols(ms, mc);
 #pragma unroll
     for (int rt = 0; rt < TT; rt++) {
-      const int i = row_of(rt);
-      const double rc = (i < M ? ms[rt] : (i == M ? -vv : 0.0)) * F1;  // row M: a += K0 v
+      double rc = ms[rt] * F1;
+      if (rt == LA) rc = lane_a ? -vv * F1 : rc;
 #pragma unroll
       for (int ct = 0; ct < TT; ct++)
 #pragma unroll
         for (int e = 0; e < 2; e++) G.c[rt][ct][e] = fma(-rc, mc[ct][e], G.c[rt][ct][e]);
     }
+  };
+
+  // P* L0' = P* - M K0' applied to G = [P* ; a'] (src/LogLikC.cpp:181-194 / 117-130)
+  auto update_star = [&](const double (&ms)[TT], double F_star, double yv) {
+    const double F1 = __drcp_rn(F_star);
+    const double vv = yv - z_dot_a(ms);
+    rank1(ms, F1, vv);
     acc_log(F_star);
+    n_terms++;
     sumq = fma(vv * vv, F1, sumq);
   };
 
   // Second product of the time update, X = init + [Y ; a'] T', exploiting the symmetry of T P T' + R Q R':
   // tiles below the diagonal are not multiplied but mirrored from above (8x8 tile transpose in accumulator
   // layout: element (2q+e, g) sits in lane (2q+e)*4 + g/2, half g%2), and the part of the state row that
-  // falls into them, (T a)[n], is fetched from column M of Y = [T P , T a] where the first product left it.
+  // falls into them, (T a)[n], is fetched from column MA of Y = [T P , T a] where the first product left it.
   auto second_product = [&](Frag<TT>& X, const Frag<TT>& Y, bool keep_a) {
     mul_y_tt_upper<TT, TM>(X, Y, T);
     if constexpr (TT > 1) {
-      const int ct_m = M >> 3, q_m = (M & 7) >> 1, e_m = M & 1;  // where column M of Y lives
 #pragma unroll
       for (int rt = 1; rt < TT; rt++)
 #pragma unroll
@@ -294,15 +306,10 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
             const double lo = __shfl_sync(FULL, X.c[nt][rt][0], src);
             const double hi = __shfl_sync(FULL, X.c[nt][rt][1], src);
             double val = (g & 1) ? hi : lo;  // X[8nt + 2q+e][8rt + g]
-            if (keep_a) {
-              // (T a)[8nt + 2q + e] = Y[8nt+2q+e][M]
-              double ya = Y.c[nt][0][0];
-#pragma unroll
-              for (int ct = 0; ct < TT; ct++) {
-                if (ct == ct_m) ya = e_m ? Y.c[nt][ct][1] : Y.c[nt][ct][0];
-              }
-              const double ta = __shfl_sync(FULL, ya, (2 * q + e) * 4 + q_m);
-              if (row_of(rt) == M) val = ta;
+            if (rt == LA) {
+              // (T a)[8nt + 2q + e] = Y[8nt+2q+e][MA]
+              const double ta = __shfl_sync(FULL, Y.c[nt][LA][1], (2 * q + e) * 4 + 3);
+              if (keep_a && lane_a) val = ta;
             }
             X.c[rt][nt][e] = val;
           }
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
       for (int ct = 0; ct < TT; ct++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-          if (keep_a && row_of(rt) == M) Y.c[rt][ct][e] = X.c[rt][ct][e];  // row M of Y <- a'
+          if (rt == LA && keep_a && lane_a) Y.c[rt][ct][e] = X.c[rt][ct][e];  // row MA of Y <- a'
           X.c[rt][ct][e] = with_rqr ? rqr[(rt * TT + ct) * 2 + e][lane] : 0.0;
         }
     second_product(X, Y, keep_a);  // [T P ; a'] T' = [T P T' ; (T a)']
@@ -376,27 +383,27 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
         }
         // :136-153  K0 = M_inf F1, K1 = M* F1 + M_inf F2
         const double F1 = __drcp_rn(F_inf), F2 = -(F1 * F1) * F_star;
-        const double za = __shfl_sync(FULL, pick(ms), g_a * 4);
-        const double vv = yv - za;
+        const double vv = yv - z_dot_a(ms);
         double msc[TT][2], mic[TT][2];
         to_cols(ms, msc);
         to_cols(mi, mic);
 #pragma unroll
         for (int rt = 0; rt < TT; rt++) {
-          const int i = row_of(rt);
-          const double rs = i < M ? ms[rt] : (i == M ? -vv : 0.0);  // row M: a += K0 v
-          const double ri = i < M ? mi[rt] : 0.0;
+          // row MA: M* -> -v, M_inf -> 0  (a += K0 v)
+          const double rs = (rt == LA && lane_a) ? -vv : ms[rt];
+          const double ri = (rt == LA && lane_a) ? 0.0 : mi[rt];
 #pragma unroll
           for (int ct = 0; ct < TT; ct++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
               const double k0 = mic[ct][e] * F1, k1 = msc[ct][e] * F1 + mic[ct][e] * F2;
-              // P* - M* K0' - M_inf K1'  (row M: M* -> -v, M_inf -> 0)
+              // P* - M* K0' - M_inf K1'
               G.c[rt][ct][e] = fma(-ri, k1, fma(-rs, k0, G.c[rt][ct][e]));
               Ginf.c[rt][ct][e] = fma(-ri, k0, Ginf.c[rt][ct][e]);
             }
         }
         acc_log(F_inf);  // no v^2 term (:153)
+        n_terms++;
         if (j < p - 1) init = !abs_small(Ginf);  // :157-159
       }
       if (t < N - 1) {  // :200-207
@@ -411,11 +418,12 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
 
   // ---- regular phase: the hot loop ---------------------------------------------------------------
   if constexpr (P1) {
-    // Software-pipelined form for p = 1.  With P+ = T P T' + R Q R' (the second product below),
+    // Software-pipelined, branch-free form for p = 1.  With P+ = T P T' + R Q R' (the second product below),
     //     M+ = P+ z = [T P] (T'z) + (R Q R') z,        z'a+ = a'(T'z):
-    // the next observation's M, F = z'M, 1/F, v and the gathered M[c] only need the FIRST product
-    // Y = [T P ; a'], so their shuffle / reciprocal chain (about 350 cycles of latency) is issued next to
-    // the 2 TT^3 DMMAs of the second product instead of after them.
+    // the next observation's M, F = z'M and 1/F only need the FIRST product Y = [T P ; a'], so their shuffle /
+    // reciprocal chain is issued next to the DMMAs of the second product instead of after them.  A missing
+    // observation or F < 1e-7 (src/LogLikC.cpp:88-90,173-176) turns the update into a no-op through
+    // F1 = v = 0 rather than through a branch, so that the whole step is one straight-line block.
     double wc[TT][2], c0[TT];
     {
       const double* Tb = md.T.block(0, 0, 0);
@@ -440,73 +448,75 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
         c0[rt] = quad_sum(acc);
       }
     }
-    // everything the update of one observation needs, prepared one step ahead
-    double ms[TT], mc[TT][2], F_star, F1, vv;
-    bool obs, upd;
-    auto prepare = [&](double yv) {  // from ms: branch-free
+    double ms[TT], F_star = 1.0, F1 = 1.0, zat = 0.0;
+    // F = z'M, 1/F, z'a from ms
+    auto prepare = [&]() {
       double fs = 0.0;
 #pragma unroll
       for (int rt = 0; rt < TT; rt++) fs = fma(zr[rt], ms[rt], fs);
       F_star = rows_sum(fs);
-      obs = !isnan(yv);                 // :88-90
-      upd = obs && !(F_star < kEps);    // :173
-      F1 = __drcp_rn(upd ? F_star : 1.0);
-      vv = yv - __shfl_sync(FULL, pick(ms), g_a * 4);
-      to_cols(ms, mc);
+      F1 = rcp_newton(F_star < kEps ? 1.0 : F_star);
+      zat = z_dot_a(ms);
+    };
+    auto measure = [&](double yv) {  // :88-90, :173-195
+      const bool obs = !isnan(yv);
+      const bool upd = obs && !(F_star < kEps);
+      const double F1e = upd ? F1 : 0.0;
+      const double vv = upd ? yv - zat : 0.0;
+      rank1(ms, F1e, vv);
+      acc_log(upd ? F_star : 1.0);
+      n_terms += upd;
+      non_init += obs;
+      F_eq0 += obs && !upd;
+      sumq = fma(vv * vv, F1e, sumq);
     };
     if (t < N) {
       row_dots(G, ms);
-      prepare(next_y());
+      prepare();
     }
-    for (; t < N; t++) {
-      if (obs) {
-        non_init++;
-        if (upd) {  // :181-194
+    // y in chunks of 32 time points, one chunk ahead
+    int t0 = t;
+    double ycur, ynxt = load_y(t0 + lane);
+    while (t0 < N) {
+      ycur = ynxt;
+      ynxt = load_y((long long)t0 + 32 + lane);
+      const int nl = min(32, N - t0);
+      for (int l = 0; l < nl; l++) {
+        measure(__shfl_sync(FULL, ycur, l));
+        if (t0 + l < N - 1) {  // :200-207
+          Frag<TT> Y;
+#pragma unroll
+          for (int rt = 0; rt < TT; rt++)
+#pragma unroll
+            for (int ct = 0; ct < TT; ct++) Y.c[rt][ct][0] = Y.c[rt][ct][1] = 0.0;
+          mul_t_wt<TT, TM>(Y, T, G);  // T G' = [T P , T a]
+#pragma unroll
+          for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+              if (lane_a) Y.c[LA][ct][e] = G.c[LA][ct][e];  // row MA of Y <- a'
+          // next observation's M (state rows) and z'a (row MA) from Y
 #pragma unroll
           for (int rt = 0; rt < TT; rt++) {
-            const int i = row_of(rt);
-            const double rc = (i < M ? ms[rt] : (i == M ? -vv : 0.0)) * F1;  // row M: a += K0 v
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+            for (int ct = 0; ct < TT; ct++) {
+              acc0 = fma(Y.c[rt][ct][0], wc[ct][0], acc0);
+              acc1 = fma(Y.c[rt][ct][1], wc[ct][1], acc1);
+            }
+            ms[rt] = quad_sum(acc0 + acc1) + c0[rt];
+          }
+#pragma unroll
+          for (int rt = 0; rt < TT; rt++)
 #pragma unroll
             for (int ct = 0; ct < TT; ct++)
 #pragma unroll
-              for (int e = 0; e < 2; e++) G.c[rt][ct][e] = fma(-rc, mc[ct][e], G.c[rt][ct][e]);
-          }
-          acc_log(F_star);
-          sumq = fma(vv * vv, F1, sumq);
-        } else {
-          F_eq0++;  // :173-176
+              for (int e = 0; e < 2; e++) G.c[rt][ct][e] = rqr[(rt * TT + ct) * 2 + e][lane];
+          second_product(G, Y, true);  // [T P ; a'] T' + R Q R'
+          prepare();
         }
       }
-      if (t < N - 1) {  // :200-207
-        Frag<TT> Y;
-#pragma unroll
-        for (int rt = 0; rt < TT; rt++)
-#pragma unroll
-          for (int ct = 0; ct < TT; ct++) Y.c[rt][ct][0] = Y.c[rt][ct][1] = 0.0;
-        mul_t_wt<TT, TM>(Y, T, G);  // T G' = [T P , T a]
-#pragma unroll
-        for (int rt = 0; rt < TT; rt++)
-#pragma unroll
-          for (int ct = 0; ct < TT; ct++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-              if (row_of(rt) == M) Y.c[rt][ct][e] = G.c[rt][ct][e];  // row M of Y <- a'
-              G.c[rt][ct][e] = rqr[(rt * TT + ct) * 2 + e][lane];
-            }
-        // next observation's M (rows < M) and z'a (row M) from Y
-#pragma unroll
-        for (int rt = 0; rt < TT; rt++) {
-          double acc = 0.0;
-#pragma unroll
-          for (int ct = 0; ct < TT; ct++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) acc = fma(Y.c[rt][ct][e], wc[ct][e], acc);
-          ms[rt] = quad_sum(acc) + c0[rt];
-        }
-        const double y_next = next_y();
-        second_product(G, Y, true);  // [T P ; a'] T' + R Q R'
-        prepare(y_next);
-      }
+      t0 += nl;
     }
   } else {
     for (; t < N; t++) {

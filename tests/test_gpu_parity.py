@@ -221,6 +221,7 @@ def _block_diagonal_model(rng, m, p, d, N, scatter=True):
         k = min(m - i, int(rng.integers(1, 4)))
         idx = order[i:i + k]
         blk = rng.normal(size=(k, k)) * 0.4 + 0.6 * np.eye(k)
+        blk *= 0.95 / max(0.95, np.max(np.abs(np.linalg.eigvals(blk))))      # keep the recursion well conditioned
         T[np.ix_(idx, idx)] = blk
         i += k
     return sysmat.SysMat(Z=sm.Z, T=T[:, :, None], R=sm.R, Q=sm.Q, a=sm.a, P_inf=sm.P_inf, P_star=sm.P_star)
