@@ -48,6 +48,19 @@ def f_alg(m, p):
     return 4 * m ** 3 + (4 * p + 3) * m ** 2 + 7 * p * m
 
 
+# Scalar FP64 instructions per warp and time step in the p = 1 hot loop of loglik_mma_kernel (cuobjdump -sass and
+# ncu smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on, profiles/README.md): 23 DFMA, 11 DADD, 4 DMUL
+SCALAR_FLOPS_PER_STEP = (23 * 2 + 11 + 4) * 32
+
+
+def executed_flops(kernel_name):
+    """Flops the tensor kernel issues per series*timestep: DMMAs (8x8x4: 512 flops each, padding included) + scalar
+    FP64.  None for the other kernels."""
+    import re
+    m = re.search(r"dmma_per_step=(\d+)", kernel_name or "")
+    return int(m.group(1)) * 512 + SCALAR_FLOPS_PER_STEP if m else None
+
+
 def variants(theta):
     """(V, B, 4): theta, theta + h e_i, theta - h e_i  (stats::optim central differences, ndeps = 1e-3)."""
     out = [theta]
@@ -335,6 +348,8 @@ def run_gpu(args):
     if rank == 0:
         flops = f_alg(M, 1) * B * V * T_STEPS
         achieved = flops / (kernel_ms * 1e-3) / 1e12
+        f_exec = executed_flops(api.last_kernel())
+        executed = f_exec * B * V * T_STEPS / (kernel_ms * 1e-3) / 1e12 if f_exec else None
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -352,6 +367,12 @@ def run_gpu(args):
                 "roofline": {"bound": "fp64", "kernel": api.last_kernel(), "achieved": achieved,
                              "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
                              "flops_per_series_timestep": f_alg(M, 1), "kernel_ms": kernel_ms,
+                             "flops_executed_per_series_timestep": f_exec, "executed_tflops": executed,
+                             "executed_frac": executed / peak_tf if executed else None,
+                             "note": "achieved/frac count the dense algorithm of SURVEY.md 8d (4m^3 + 7m^2 + 7m); the "
+                                     "kernel skips the all-zero 8x8 tiles of the block-diagonal T, so the flops it "
+                                     "issues (executed_*: DMMA incl. padding + scalar FP64) are fewer; executed_frac "
+                                     "is the FP64 datapath utilisation",
                              "peak_source": "ssgpu_fp64_peak DFMA chains, measured in this run (MEASURED_PEAKS.json "
                                             "has no FP64 figure)",
                              "hbm_algorithmic_gbs": 8.0 * B * T_STEPS / (kernel_ms * 1e-3) / 1e9,

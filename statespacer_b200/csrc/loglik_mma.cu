@@ -448,22 +448,35 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
         c0[rt] = quad_sum(acc);
       }
     }
+    // the per-lane constants of the hot loop wait in shared memory like R Q R' (registers are what limits the
+    // number of resident warps): [w (2 TT) | c0 (TT) | z rows (TT)][lane]
+    __shared__ double cst_s[kMmaThreads / 32][4 * TT][32];
+    double(*cst)[32] = cst_s[threadIdx.x >> 5];
+#pragma unroll
+    for (int ct = 0; ct < TT; ct++) {
+      cst[2 * ct][lane] = wc[ct][0];
+      cst[2 * ct + 1][lane] = wc[ct][1];
+      cst[2 * TT + ct][lane] = 0.25 * c0[ct];  // a quarter per lane of the quad: the quad sum adds it back
+      cst[3 * TT + ct][lane] = zr[ct];
+    }
+    __syncwarp();
     double ms[TT], F_star = 1.0, F1 = 1.0, zat = 0.0;
     // F = z'M, 1/F, z'a from ms
     auto prepare = [&]() {
       double fs = 0.0;
 #pragma unroll
-      for (int rt = 0; rt < TT; rt++) fs = fma(zr[rt], ms[rt], fs);
+      for (int rt = 0; rt < TT; rt++) fs = fma(cst[3 * TT + rt][lane], ms[rt], fs);
       F_star = rows_sum(fs);
       F1 = rcp_newton(F_star < kEps ? 1.0 : F_star);
       zat = z_dot_a(ms);
     };
-    auto measure = [&](double yv) {  // :88-90, :173-195
+    // loglik terms of one observation (:88-90, :173-195); returns the update's 1/F and v, both 0 for a no-op
+    double F1e, vv;
+    auto observe = [&](double yv) {
       const bool obs = !isnan(yv);
       const bool upd = obs && !(F_star < kEps);
-      const double F1e = upd ? F1 : 0.0;
-      const double vv = upd ? yv - zat : 0.0;
-      rank1(ms, F1e, vv);
+      F1e = upd ? F1 : 0.0;
+      vv = upd ? yv - zat : 0.0;
       acc_log(upd ? F_star : 1.0);
       n_terms += upd;
       non_init += obs;
@@ -482,8 +495,9 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
       ynxt = load_y((long long)t0 + 32 + lane);
       const int nl = min(32, N - t0);
       for (int l = 0; l < nl; l++) {
-        measure(__shfl_sync(FULL, ycur, l));
-        if (t0 + l < N - 1) {  // :200-207
+        observe(__shfl_sync(FULL, ycur, l));
+        if (t0 + l < N - 1) {  // :200-207 (after the last observation P and a are not needed any more)
+          rank1(ms, F1e, vv);
           Frag<TT> Y;
 #pragma unroll
           for (int rt = 0; rt < TT; rt++)
@@ -498,13 +512,13 @@ __global__ void __launch_bounds__(kMmaThreads, MINB) loglik_mma_kernel(const Mma
           // next observation's M (state rows) and z'a (row MA) from Y
 #pragma unroll
           for (int rt = 0; rt < TT; rt++) {
-            double acc0 = 0.0, acc1 = 0.0;
+            double acc = cst[2 * TT + rt][lane];
 #pragma unroll
             for (int ct = 0; ct < TT; ct++) {
-              acc0 = fma(Y.c[rt][ct][0], wc[ct][0], acc0);
-              acc1 = fma(Y.c[rt][ct][1], wc[ct][1], acc1);
+              acc = fma(Y.c[rt][ct][0], cst[2 * ct][lane], acc);
+              acc = fma(Y.c[rt][ct][1], cst[2 * ct + 1][lane], acc);
             }
-            ms[rt] = quad_sum(acc0 + acc1) + c0[rt];
+            ms[rt] = quad_sum(acc);
           }
 #pragma unroll
           for (int rt = 0; rt < TT; rt++)
@@ -696,18 +710,18 @@ int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, dou
   // resident CTAs per SM the register budget is sized for (tuning knob)
   static const int minb = [] {
     const char* e = getenv("SSGPU_MMA_MINB");
-    return e ? atoi(e) : 4;  // 128 registers: measured best on B200 (profiles/README.md)
+    return e ? atoi(e) : 5;  // 96 registers, 5 warps per sub-partition: measured best on B200 (profiles/README.md)
   }();
   if (tt == 1)
     launch_mma_tt<1, 0x1u, 6>(A, (unsigned)blocks, st);
   else if (tt == 2) {
     if (use == kDiag2) {
-      if (minb <= 3)
-        launch_mma_tt<2, kDiag2, 3>(A, (unsigned)blocks, st);
-      else if (minb == 4)
+      if (minb <= 4)
         launch_mma_tt<2, kDiag2, 4>(A, (unsigned)blocks, st);
-      else
+      else if (minb == 5)
         launch_mma_tt<2, kDiag2, 5>(A, (unsigned)blocks, st);
+      else
+        launch_mma_tt<2, kDiag2, 6>(A, (unsigned)blocks, st);
     } else {
       launch_mma_tt<2, 0xFu, 4>(A, (unsigned)blocks, st);
     }
