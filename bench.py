@@ -395,6 +395,234 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ---- config 4: simulation smoother draws (--workload sim) ---------------------------------------------
+SIM_METRIC = "sim_smoother_draw_timesteps_per_s"
+SIM_UNIT = "draws*timesteps/s"
+NSIM_PER_GPU = 12_500          # 100,000 draws over 8 GPUs (BASELINE.json config 4)
+
+
+def sim_model():
+    """SARIMA(1,1,1)(0,1,1)_12 on log AirPassengers: N = 144, m = 28 incl. the residual state."""
+    import math
+    from statespacer_b200 import sysmat
+    air = np.log(np.loadtxt(os.path.join(ROOT, "tests", "golden", "airpassengers.txt"), comments="#"))[:, None]
+    sm = sysmat.airline([0.5 * math.log(0.00135), 0.3, -0.4, -0.55], s=(12, 1), ar=(0, 1), i=(1, 1), ma=(1, 1))
+    return air, sm
+
+
+def sim_bytes(N, p, m, r, mc, rc):
+    """Mandatory HBM bytes per draw*timestep of the three kernels, draw-contiguous layout, no a_t copy."""
+    simulate = 8 * (rc + p + mc + rc) + 8 * (p + p)        # component + residual (eta_only) call
+    smoother = 8 * (p + m + r)
+    extract = 8 * (m + p)
+    return simulate, smoother, extract
+
+
+def sim_config(n_gpus, nsim, extra=None):
+    c = {"workload": "config4: SimSmoother draws, SARIMA(1,1,1)(0,1,1)12 on log AirPassengers, N=144, m=28, d=13 "
+                     "diffuse: SimulateC (component + residual) -> FastSmootherC -> ExtractComponentC per draw",
+         "nsim_per_gpu": nsim, "nsim_total": nsim * n_gpus, "timesteps": 144,
+         "l2": "per-draw arrays larger than L2 (%.2f GB of outputs per GPU), no flush" % (nsim * 144 * 8 * 90 / 1e9),
+         "parallelism": f"draws sharded over {n_gpus} GPU(s), no collective"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def run_sim_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import cport, ref
+    mod, kind = (ref, "reference") if ref.available() else (cport, "port")
+    cores = host_cores()
+    air, sm = sim_model()
+    N = len(air)
+    from oracle import kalman_np
+    steps0 = int(kalman_np.KalmanC(air, np.isnan(air), *sm.args(), False)["initialisation_steps"])
+    per_thread = args.cpu_draws
+    mc = sm.m - 1
+    Zc, Tc, Rc, Qc = sm.Z[:, 1:, :], sm.T[1:, 1:, :], sm.R[1:, 1:, :], sm.Q[1:, 1:, :]
+    Qe = sm.Q[:1, :1, :]
+    one = np.zeros((1, 1, 1))
+
+    def chunk(seed):
+        rng = np.random.default_rng(seed)
+        d1, d2 = rng.normal(size=N * per_thread), rng.normal(size=N * per_thread)
+        s1 = mod.SimulateC(per_thread, 1, N, np.zeros(mc), Zc, Tc, Rc, Qc, np.zeros((mc, mc)), False, False, True, d1)
+        s2 = mod.SimulateC(per_thread, 1, N, np.zeros(1), one, one, one, Qe, np.zeros((1, 1)), False, True, False, d2)
+        y = s1["y"] + s2["eta"]
+        fs = mod.FastSmootherC(y, *sm.args(), steps0, True)
+        return mod.ExtractComponentC(fs["a_t"], sm.Z)
+
+    def step():
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            list(ex.map(chunk, range(cores)))
+        return time.perf_counter() - t0
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    times = [step() for _ in range(args.steps)]
+    value = cores * per_thread * N * args.steps / sum(times)
+    sample = f"{cores} threads x {per_thread} draws x {N} timesteps per step (one chunk per thread)"
+    print(json.dumps({"impl": "reference", "metric": SIM_METRIC, "value": value, "unit": SIM_UNIT, "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / args.steps,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                      "data": "synthetic", "config": sim_config(args.gpus, args.nsim, {"cpu_sample": sample}),
+                      "cpu_baseline": {"value": value, "unit": SIM_UNIT, "cores": cores, "kind": kind, "sample": sample},
+                      "e2e": {"value": value, "unit": SIM_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+
+
+def run_sim_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from statespacer_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (statespacer_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    api.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    air, sm = sim_model()
+    N, S = len(air), args.nsim
+    steps0 = int(api.KalmanC(air, np.isnan(air), *sm.args(), False)["initialisation_steps"])
+    mc = sm.m - 1
+    Zc, Tc, Rc, Qc = sm.Z[:, 1:, :], sm.T[1:, 1:, :], sm.R[1:, 1:, :], sm.Q[1:, 1:, :]
+    Qe = sm.Q[:1, :1, :]
+    one = np.zeros((1, 1, 1))
+    g = torch.Generator(device=dev)
+    g.manual_seed(4 + rank)
+    d1 = torch.randn(N * S, generator=g, device=dev, dtype=torch.float64)
+    d2 = torch.randn(N * S, generator=g, device=dev, dtype=torch.float64)
+    stream = torch.cuda.current_stream(dev)
+    kt = {"simulate": [], "smoother": [], "extract": []}
+
+    def step(record=False):
+        s1 = api.SimulateC_dev(S, 1, N, np.zeros(mc), Zc, Tc, Rc, Qc, np.zeros((mc, mc)), False, False, d1)
+        if record:
+            kt["simulate"].append(api.last_sim_kernel_ms()[0])
+        s2 = api.SimulateC_dev(S, 1, N, np.zeros(1), one, one, one, Qe, np.zeros((1, 1)), False, True, d2,
+                               want=("eta",))
+        y = s1["y"] + s2["eta"]
+        fs = api.FastSmootherC_dev(y, *sm.args(), steps0)
+        comp = api.ExtractComponentC_dev(fs["a_smooth"], sm.Z)
+        if record:
+            ms = api.last_sim_kernel_ms()
+            kt["smoother"].append(ms[1])
+            kt["extract"].append(ms[2])
+        return s1, fs, comp
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    l0 = api.launch_count()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        out = step(record=True)
+    e1.record(stream)
+    sync()
+    launches = api.launch_count() - l0
+    clocks = sampler.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    units = S * N * world
+    value = units * args.steps / (elapsed_ms * 1e-3)
+    finite = bool(torch.isfinite(out[2]).all().item() and torch.isfinite(out[1]["a_smooth"]).all().item())
+    del out
+
+    # ---- end to end through the host-pointer C ABI (R's array layouts in host memory) ----
+    Se = min(S, args.e2e_nsim)
+    d1h, d2h = d1[:N * Se].cpu().numpy(), d2[:N * Se].cpu().numpy()
+
+    def e2e_step():
+        s1 = api.SimulateC(Se, 1, N, np.zeros(mc), Zc, Tc, Rc, Qc, np.zeros((mc, mc)), False, False, True, d1h)
+        s2 = api.SimulateC(Se, 1, N, np.zeros(1), one, one, one, Qe, np.zeros((1, 1)), False, True, False, d2h)
+        fs = api.FastSmootherC(s1["y"] + s2["eta"], *sm.args(), steps0, True)
+        return api.ExtractComponentC(fs["a_t"], sm.Z)
+
+    e2e_step()
+    sync()
+    t0 = time.perf_counter()
+    e2e_step()
+    sync()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = Se * N * world / e2e_s
+    m, r, p = sm.m, sm.r, 1
+    h2d = 8 * Se * N * (1 + 1 + p + m)                       # variates x2, y, a_t
+    d2h = 8 * Se * N * ((p + 2 * mc + 1) + 1 + (2 * m + r) + p)
+
+    if rank == 0:
+        b_sim, b_fs, b_ext = sim_bytes(N, p, m, r, mc, 1)
+        hbm_peak, peak_src = 6545.3, "fallback"
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            peak_src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+        fs_ms = statistics.mean(kt["smoother"])
+        achieved = b_fs * S * N / (fs_ms * 1e-3) / 1e9
+        line = {"metric": SIM_METRIC, "value": value, "unit": SIM_UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": sim_config(world, S, {"results_finite": finite}),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": SIM_UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": 1, "nsim": Se, "note": "host-pointer C ABI, R array layouts, pageable host memory"},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "fs_draw_kernel", "achieved": achieved, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "bytes_per_draw_timestep": b_fs, "kernel_ms": fs_ms,
+                             "other_kernels": {
+                                 "simulate_kernel": {"kernel_ms": statistics.mean(kt["simulate"]),
+                                                     "bytes_per_draw_timestep": 8 * (1 + p + mc + 1),
+                                                     "achieved": 8 * (1 + p + mc + 1) * S * N
+                                                     / (statistics.mean(kt["simulate"]) * 1e-3) / 1e9},
+                                 "extract_kernel": {"kernel_ms": statistics.mean(kt["extract"]),
+                                                    "bytes_per_draw_timestep": b_ext,
+                                                    "achieved": b_ext * S * N
+                                                    / (statistics.mean(kt["extract"]) * 1e-3) / 1e9}},
+                             "pipeline_bytes_per_draw_timestep": b_sim + b_fs + b_ext,
+                             "pipeline_achieved": (b_sim + b_fs + b_ext) * S * N * args.steps
+                             / (elapsed_ms * 1e-3) / 1e9}}
+        if world == 1 and not args.no_cpu:
+            import contextlib
+            import io
+            buf = io.StringIO()
+            a2 = argparse.Namespace(**vars(args))
+            a2.steps, a2.warmup = 1, 0
+            with contextlib.redirect_stdout(buf):
+                run_sim_reference(a2)
+            line["cpu_baseline"] = json.loads(buf.getvalue())["cpu_baseline"]
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -405,8 +633,15 @@ def main():
     ap.add_argument("--missing", type=float, default=0.0, help="fraction of NaN observations (variant B: 0.02)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "mma", "mma_dense", "cols", "generic"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="loglik", choices=["loglik", "sim"],
+                    help="loglik: config 5 (headline, default); sim: config 4 simulation smoother draws")
+    ap.add_argument("--nsim", type=int, default=NSIM_PER_GPU, help="draws per GPU (--workload sim)")
+    ap.add_argument("--e2e-nsim", type=int, default=NSIM_PER_GPU, help="draws of the end-to-end leg (--workload sim)")
+    ap.add_argument("--cpu-draws", type=int, default=128, help="draws per host thread of the CPU arm (--workload sim)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "sim":
+        run_sim_reference(args) if args.impl == "reference" else run_sim_gpu(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

@@ -162,6 +162,34 @@ int ssgpu_loglik_batch_dev(const double* y, long long B, int V, const ssgpu_mode
 /* name of the kernel the last ssgpu_loglik_batch[_dev] call on this thread launched */
 const char* ssgpu_last_kernel(void);
 
+/* ---- 6b. Simulation smoother on device-resident draws (new) ---------------------------------
+ * The three per-draw routines again, for callers that keep the draws on the GPU between the steps of
+ * R/SimSmoother.R:91-769 (simulate every component -> add -> smooth -> extract) instead of round-tripping
+ * N x m x nsim arrays through host memory.  Per-draw arrays are DEVICE pointers in the draw-contiguous layout the
+ * kernels use, X[(t*K + k)*nsim + s] (K = p, m, r or r_tot); `draws` is a device pointer in the reference's
+ * consumption order (as for ssgpu_SimulateC); system matrices stay HOST pointers (a few KB, copied before the call
+ * returns).  Work is enqueued on `stream` (a cudaStream_t, NULL = the library's stream); the calls return after
+ * the kernels have completed.  Arithmetic is identical to the host-pointer entry points (bit-exact).
+ * ssgpu_draw_layout_dev converts between the draw-contiguous layout and R's N x K x nsim array on the device
+ * (to_r != 0: draw-contiguous -> R). */
+int ssgpu_SimulateC_dev(int nsim, int repeat_Q, int N, int p, int m, int rR, int r, int mP,
+                        const double* a, const double* Z, int nZ, const double* T, int nT,
+                        const double* R, int nR, const double* Q, int nQ, const double* P_star,
+                        int draw_initial, int eta_only, const double* draws, long long n_draws,
+                        const double* Q_root, const double* P_root,
+                        double* y, double* a_out, double* eta, void* stream);
+int ssgpu_FastSmootherC_dev(const double* y, int N, int p, int nsim, int m, int r,
+                            const double* a, const double* P_inf, const double* P_star,
+                            const double* Z, int nZ, const double* T, int nT,
+                            const double* R, int nR, const double* Q, int nQ,
+                            int initialisation_steps, double* a_smooth, double* eta, void* stream);
+int ssgpu_ExtractComponentC_dev(const double* a, int m, int nsim, int N,
+                                const double* Z, int p, int nZ, double* out, void* stream);
+int ssgpu_draw_layout_dev(const double* src, double* dst, int N, int K, long long nsim, int to_r, void* stream);
+/* device time (ms, CUDA events on the launching stream) of the last simulate / per-draw smoother / extract kernel
+ * this process launched; -1 if none yet.  Waits for that kernel. */
+int ssgpu_last_sim_kernel_ms(double* simulate_ms, double* fast_smoother_ms, double* extract_ms);
+
 /* Host-only helper (no device needed): the internal state order the tensor kernel would use for a shared
  * m x m transition matrix T (column-major, m <= 23).  perm[i] = caller's index of the state at internal
  * position i; *tile_mask has bit rt*TT + ct set when the 8 x 8 tile (rt, ct) of the re-ordered T holds a

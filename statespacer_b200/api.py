@@ -204,6 +204,90 @@ def ExtractComponentC(a, Z):
     return out
 
 
+# ---- simulation smoother on device-resident draws (torch CUDA float64 tensors, draw-contiguous layout) -----
+def _stream_handle(stream):
+    import torch
+    st = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(st.cuda_stream)
+
+
+def SimulateC_dev(nsim, repeat_Q, N, a, Z, T, R, Q, P_star, draw_initial, eta_only, draws, Q_root=None, P_root=None,
+                  stream=None, want=("y", "a", "eta")):
+    """SimulateC on the device: `draws` is a CUDA tensor in the reference's consumption order; returns CUDA
+    tensors y (N, p, nsim), a (N, m, nsim), eta (N, r_tot, nsim) -- C-contiguous, i.e. draws fastest."""
+    import torch
+    a = _f(np.asarray(a, dtype=np.float64).reshape(-1))
+    Z, T, R, Q = _cube(Z, "Z"), _cube(T, "T"), _cube(R, "R"), _cube(Q, "Q")
+    P_star = _f(np.atleast_2d(P_star))
+    p, m, r = Z.shape[0], a.shape[0], Q.shape[0]
+    r_tot = r * repeat_Q
+    Q_root = None if Q_root is None else _cube(Q_root, "Q_root")
+    P_root = None if P_root is None else _f(P_root)
+    dev = draws.device
+    mk = lambda k: torch.empty(N, k, nsim, device=dev, dtype=torch.float64)
+    y = mk(p) if ("y" in want and not eta_only) else None
+    ao = mk(m) if ("a" in want and not eta_only) else None
+    eta = mk(r_tot) if "eta" in want else None
+    dp_ = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    native.check(native.lib().ssgpu_SimulateC_dev(
+        nsim, repeat_Q, N, p, m, R.shape[1], r, P_star.shape[0], _ptr(a), _ptr(Z), Z.shape[2], _ptr(T), T.shape[2],
+        _ptr(R), R.shape[2], _ptr(Q), Q.shape[2], _ptr(P_star), int(bool(draw_initial)), int(bool(eta_only)),
+        dp_(draws), draws.numel(), _ptr(Q_root), _ptr(P_root), dp_(y), dp_(ao), dp_(eta), _stream_handle(stream)))
+    return {"y": y, "a": ao, "eta": eta}
+
+
+def FastSmootherC_dev(y, a, P_inf, P_star, Z, T, R, Q, initialisation_steps, stream=None):
+    """FastSmootherC on the device: y is a CUDA tensor (N, p, nsim), draws fastest; returns a_smooth (N, m, nsim)
+    and eta (N, r, nsim) in the same layout."""
+    import torch
+    a = _f(np.asarray(a, dtype=np.float64).reshape(-1))
+    P_inf, P_star = _f(P_inf), _f(P_star)
+    Z, T, R, Q = _cube(Z, "Z"), _cube(T, "T"), _cube(R, "R"), _cube(Q, "Q")
+    N, p, nsim = y.shape
+    m, r = a.shape[0], Q.shape[0]
+    if not y.is_contiguous():
+        raise ValueError("y must be contiguous (N, p, nsim)")
+    a_s = torch.empty(N, m, nsim, device=y.device, dtype=torch.float64)
+    eta = torch.empty(N, r, nsim, device=y.device, dtype=torch.float64)
+    native.check(native.lib().ssgpu_FastSmootherC_dev(
+        C.c_void_p(y.data_ptr()), N, p, nsim, m, r, _ptr(a), _ptr(P_inf), _ptr(P_star), _ptr(Z), Z.shape[2], _ptr(T),
+        T.shape[2], _ptr(R), R.shape[2], _ptr(Q), Q.shape[2], int(initialisation_steps), C.c_void_p(a_s.data_ptr()),
+        C.c_void_p(eta.data_ptr()), _stream_handle(stream)))
+    return {"a_smooth": a_s, "eta": eta}
+
+
+def ExtractComponentC_dev(a, Z, stream=None):
+    """ExtractComponentC on the device: a is a CUDA tensor (N, m, nsim), draws fastest -> (N, p, nsim)."""
+    import torch
+    Z = _cube(Z, "Z")
+    N, m, nsim = a.shape
+    p = Z.shape[0]
+    out = torch.empty(N, p, nsim, device=a.device, dtype=torch.float64)
+    native.check(native.lib().ssgpu_ExtractComponentC_dev(C.c_void_p(a.data_ptr()), m, nsim, N, _ptr(Z), p, Z.shape[2],
+                                                          C.c_void_p(out.data_ptr()), _stream_handle(stream)))
+    return out
+
+
+def last_sim_kernel_ms():
+    """(simulate, fast smoother per-draw, extract) kernel times of the last launches, ms."""
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    native.check(native.lib().ssgpu_last_sim_kernel_ms(C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
+def draw_layout_dev(x, to_r, stream=None):
+    """(N, K, nsim) draws-fastest CUDA tensor <-> R's column-major N x K x nsim array (returned as a flat tensor)."""
+    import torch
+    if to_r:
+        N, K, nsim = x.shape
+        out = torch.empty(N * K * nsim, device=x.device, dtype=torch.float64)
+    else:
+        raise ValueError("use to_r=True; the reverse direction needs the shape: call native.lib() directly")
+    native.check(native.lib().ssgpu_draw_layout_dev(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), N, K, nsim,
+                                                    1, _stream_handle(stream)))
+    return out
+
+
 # ---- batched loglikelihood ----------------------------------------------------------------------------
 class BatchModel:
     """An ssgpu_model plus the arrays that keep its pointers alive.

@@ -87,17 +87,26 @@ extern "C" int ssgpu_sym_root(const double* A, int n, double* out) {
   return SSGPU_OK;
 }
 
-extern "C" int ssgpu_FastSmootherC(const double* y, int N, int p, int nsim, int m, int r, const double* a,
-                                   const double* P_inf, const double* P_star, const double* Z, int nZ, const double* T,
-                                   int nT, const double* R, int nR, const double* Q, int nQ, int initialisation_steps,
-                                   int transposed_state, double* a_smooth, double* a_t, double* eta) {
+namespace ssgpu {
+
+static int check_fs(const void* y, int N, int p, int nsim, int m, int r, const double* a, const double* P_inf,
+                    const double* P_star, const double* Z, int nZ, const double* T, int nT, const double* R, int nR,
+                    const double* Q, int nQ) {
   SS_ARG(y && a && P_inf && P_star && Z && T && R && Q, "null pointer argument");
   SS_ARG(N >= 1 && p >= 1 && m >= 1 && r >= 1 && nsim >= 1, "N, p, m, r, nsim must be positive");
   SS_ARG(m <= SSGPU_MAX_M, "state dimension m exceeds SSGPU_MAX_M");
   SS_ARG((nZ == 1 || nZ == N) && (nT == 1 || nT == N) && (nR == 1 || nR == N) && (nQ == 1 || nQ == N),
          "system matrices must have 1 or N slices");
-  SS_TRY(ensure_device());
-  cudaStream_t st = lib_stream();
+  return SSGPU_OK;
+}
+
+// FastSmootherC on device-resident draws in the draw-contiguous layout: yN [(t*p+j)*S+s] -> aN [(t*m+k)*S+s],
+// eN [(t*r+kk)*S+s].  System matrices are host pointers.  Everything is enqueued on st; the temporaries are
+// stream-ordered allocations released behind the kernels.
+static int fast_smoother_core(const double* yN, int N, int p, int nsim, int m, int r, const double* a,
+                              const double* P_inf, const double* P_star, const double* Z, int nZ, const double* T, int nT,
+                              const double* R, int nR, const double* Q, int nQ, int initialisation_steps, double* aN,
+                              double* eN, cudaStream_t st) {
   HostPack pk;
   const size_t oa = pk.add(a, m), opi = pk.add(P_inf, (size_t)m * m), ops = pk.add(P_star, (size_t)m * m);
   const size_t oz = pk.add(Z, (size_t)p * m * nZ), ot = pk.add(T, (size_t)m * m * nT);
@@ -129,23 +138,70 @@ extern "C" int ssgpu_FastSmootherC(const double* y, int N, int p, int nsim, int 
   g.K1 = base; base += pad(Np * m);
   g.QtR = base;
   SS_TRY(launch_gains_generic(md, initialisation_steps, &g, st));
-  // per-draw arrays in the draw-contiguous layout
-  DevBuf yR, yN, vN, aN, eN, outR;
-  SS_TRY(upload(yR, y, Np * ns, st));
-  SS_TRY(yN.alloc(sizeof(double) * Np * ns, st));
-  SS_TRY(launch_permute_tks(yR.as<double>(), yN.as<double>(), N, p, nsim, false, st));
+  DevBuf vN, pats;
   SS_TRY(vN.alloc(sizeof(double) * Np * ns, st));
-  SS_TRY(aN.alloc(sizeof(double) * (size_t)N * m * ns, st));
-  SS_TRY(eN.alloc(sizeof(double) * (size_t)N * r * ns, st));
   FsArgs A{};
   A.S = nsim; A.N = N; A.p = p; A.m = m; A.r = r;
   A.init_steps = initialisation_steps;
   A.qtr_tv = qtr_tv;
   A.a0 = md.a.p; A.P_inf = md.P_inf.p; A.P_star = md.P_star.p;
   A.Z = md.Z; A.T = md.T; A.R = md.R;
+  PatPack pp;
+  const size_t pz = pp.rows_of(Z, p, m, nZ), pq = pp.qtr_of(Q, nQ, R, nR, m, r);
+  SS_TRY(pats.alloc(pp.words().size() * sizeof(int), st));
+  SS_CUDA(cudaMemcpyAsync(pats.get(), pp.words().data(), pp.words().size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  const int* pb = pats.as<int>();
+  A.Zp = pp.at(pb, pz, p);
+  A.Qp = pp.at(pb, pq, r);
+  EllPack ep;
+  const EllPack::Ref et = ep.add(T, m, m, nT, false), etc = ep.add(T, m, m, nT, true), er = ep.add(R, m, r, nR, false);
+  DevBuf elli, ellv;
+  SS_TRY(elli.alloc(ep.ints().size() * sizeof(int), st));
+  SS_TRY(ellv.alloc(ep.vals().size() * sizeof(double), st));
+  SS_CUDA(cudaMemcpyAsync(elli.get(), ep.ints().data(), ep.ints().size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaMemcpyAsync(ellv.get(), ep.vals().data(), ep.vals().size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  A.Te = ep.at(et, elli.as<int>(), ellv.as<double>());
+  A.Tce = ep.at(etc, elli.as<int>(), ellv.as<double>());
+  A.Re = ep.at(er, elli.as<int>(), ellv.as<double>());
   A.g = g;
-  A.y = yN.as<double>(); A.v = vN.as<double>(); A.a_smooth = aN.as<double>(); A.eta = eN.as<double>();
+  A.y = yN; A.v = vN.as<double>(); A.a_smooth = aN; A.eta = eN;
   SS_TRY(launch_fs_draws(A, st));
+  // the host staging vectors die with this frame: make sure the (pageable) copies have been consumed
+  SS_CUDA(cudaStreamSynchronize(st));
+  return SSGPU_OK;
+}
+
+}  // namespace ssgpu
+
+extern "C" int ssgpu_FastSmootherC_dev(const double* y, int N, int p, int nsim, int m, int r, const double* a,
+                                       const double* P_inf, const double* P_star, const double* Z, int nZ,
+                                       const double* T, int nT, const double* R, int nR, const double* Q, int nQ,
+                                       int initialisation_steps, double* a_smooth, double* eta, void* stream) {
+  SS_TRY(check_fs(y, N, p, nsim, m, r, a, P_inf, P_star, Z, nZ, T, nT, R, nR, Q, nQ));
+  SS_ARG(a_smooth && eta, "null output pointer");
+  SS_TRY(ensure_device());
+  cudaStream_t st = stream ? (cudaStream_t)stream : lib_stream();
+  return fast_smoother_core(y, N, p, nsim, m, r, a, P_inf, P_star, Z, nZ, T, nT, R, nR, Q, nQ, initialisation_steps,
+                            a_smooth, eta, st);
+}
+
+extern "C" int ssgpu_FastSmootherC(const double* y, int N, int p, int nsim, int m, int r, const double* a,
+                                   const double* P_inf, const double* P_star, const double* Z, int nZ, const double* T,
+                                   int nT, const double* R, int nR, const double* Q, int nQ, int initialisation_steps,
+                                   int transposed_state, double* a_smooth, double* a_t, double* eta) {
+  SS_TRY(check_fs(y, N, p, nsim, m, r, a, P_inf, P_star, Z, nZ, T, nT, R, nR, Q, nQ));
+  SS_TRY(ensure_device());
+  cudaStream_t st = lib_stream();
+  const size_t Np = (size_t)N * p, ns = (size_t)nsim;
+  // per-draw arrays in the draw-contiguous layout
+  DevBuf yR, yN, aN, eN, outR;
+  SS_TRY(upload(yR, y, Np * ns, st));
+  SS_TRY(yN.alloc(sizeof(double) * Np * ns, st));
+  SS_TRY(launch_permute_tks(yR.as<double>(), yN.as<double>(), N, p, nsim, false, st));
+  SS_TRY(aN.alloc(sizeof(double) * (size_t)N * m * ns, st));
+  SS_TRY(eN.alloc(sizeof(double) * (size_t)N * r * ns, st));
+  SS_TRY(fast_smoother_core(yN.as<double>(), N, p, nsim, m, r, a, P_inf, P_star, Z, nZ, T, nT, R, nR, Q, nQ,
+                            initialisation_steps, aN.as<double>(), eN.as<double>(), st));
   SS_TRY(outR.alloc(sizeof(double) * (size_t)N * (m > r ? m : r) * ns, st));
   if (a_smooth) {
     SS_TRY(launch_permute_tks(aN.as<double>(), outR.as<double>(), N, m, nsim, true, st));
@@ -163,11 +219,12 @@ extern "C" int ssgpu_FastSmootherC(const double* y, int N, int p, int nsim, int 
   return SSGPU_OK;
 }
 
-extern "C" int ssgpu_SimulateC(int nsim, int repeat_Q, int N, int p, int m, int rR, int r, int mP, const double* a,
-                               const double* Z, int nZ, const double* T, int nT, const double* R, int nR,
-                               const double* Q, int nQ, const double* P_star, int draw_initial, int eta_only,
-                               int transposed_state, const double* draws, long long n_draws, const double* Q_root,
-                               const double* P_root, double* y, double* a_out, double* a_t, double* eta) {
+namespace ssgpu {
+
+static int check_sim(int nsim, int repeat_Q, int N, int p, int m, int rR, int r, int mP, const double* a,
+                     const double* Z, int nZ, const double* T, int nT, const double* R, int nR, const double* Q, int nQ,
+                     const double* P_star, int draw_initial, int eta_only, const double* draws, long long n_draws,
+                     const double* P_root) {
   SS_ARG(nsim >= 1 && repeat_Q >= 1 && N >= 1 && r >= 1 && m >= 1, "nsim, repeat_Q, N, r, m must be positive");
   SS_ARG(Q && draws, "null pointer argument");
   SS_ARG(nQ == 1 || nQ == N, "Q must have 1 or N slices");
@@ -187,8 +244,18 @@ extern "C" int ssgpu_SimulateC(int nsim, int repeat_Q, int N, int p, int m, int 
            "system matrices must have 1 or N slices");
     SS_ARG(!draw_initial || P_root || (P_star && mP == m), "draw_initial needs an m x m P_star");
   }
-  SS_TRY(ensure_device());
-  cudaStream_t st = lib_stream();
+  return SSGPU_OK;
+}
+
+// SimulateC on device-resident variates (reference order) writing the draw-contiguous layout; yN / aN / eN may be
+// null.  System matrices are host pointers.
+static int simulate_core(int nsim, int repeat_Q, int N, int p, int m, int rR, int r, const double* a, const double* Z,
+                         int nZ, const double* T, int nT, const double* R, int nR, const double* Q, int nQ,
+                         const double* P_star, int draw_initial, int eta_only, const double* draws_dev,
+                         const double* Q_root, const double* P_root, double* yN, double* aN, double* eN,
+                         cudaStream_t st) {
+  const size_t ns = (size_t)nsim;
+  const size_t n_init = draw_initial ? (size_t)m * ns : 0;
   // symmetric roots (host, once) unless supplied
   std::vector<double> qroot((size_t)r * r * nQ), proot;
   for (int i = 0; i < nQ; i++) {
@@ -215,33 +282,82 @@ extern "C" int ssgpu_SimulateC(int nsim, int repeat_Q, int N, int p, int m, int 
       op = pk.add(proot.data(), proot.size());
     }
   }
-  DevBuf mats, dr, yN, aN, eN, outR;
+  DevBuf mats, pats, elli, ellv;
   SS_TRY(upload(mats, pk.buf.data(), pk.buf.size(), st));
-  SS_TRY(upload(dr, draws, (size_t)n_draws, st));
+  PatPack pp;
+  EllPack ep;
   const double* d = mats.as<double>();
   SimArgs A{};
   A.S = nsim; A.N = N; A.p = eta_only ? 1 : p; A.m = eta_only ? 1 : m; A.rR = rR; A.r = r; A.repeat_Q = repeat_Q;
   A.nQ = nQ; A.draw_initial = draw_initial; A.eta_only = eta_only;
   A.Q_root = d + oq;
-  A.d0 = dr.as<double>();
-  A.dt = dr.as<double>() + n_init;
-  size_t biggest = (size_t)N * r_tot * ns;
+  A.d0 = draws_dev;
+  A.dt = draws_dev + n_init;
   if (!eta_only) {
     A.a0 = d + oa;
     A.Z = dmat3(d + oz, p, m, nZ);
     A.T = dmat3(d + ot, m, m, nT);
     A.R = dmat3(d + orr, m, rR, nR);
     A.P_root = d + op;
+    const size_t pz = pp.rows_of(Z, p, m, nZ);
+    SS_TRY(pats.alloc(pp.words().size() * sizeof(int), st));
+    SS_CUDA(cudaMemcpyAsync(pats.get(), pp.words().data(), pp.words().size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    A.Zp = pp.at(pats.as<int>(), pz, p);
+    const EllPack::Ref et = ep.add(T, m, m, nT, false), er = ep.add(R, m, rR, nR, false);
+    SS_TRY(elli.alloc(ep.ints().size() * sizeof(int), st));
+    SS_TRY(ellv.alloc(ep.vals().size() * sizeof(double), st));
+    SS_CUDA(cudaMemcpyAsync(elli.get(), ep.ints().data(), ep.ints().size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    SS_CUDA(cudaMemcpyAsync(ellv.get(), ep.vals().data(), ep.vals().size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    A.Te = ep.at(et, elli.as<int>(), ellv.as<double>());
+    A.Re = ep.at(er, elli.as<int>(), ellv.as<double>());
+    A.y = yN;
+    A.a = aN;
+  }
+  A.eta = eN;
+  SS_TRY(launch_simulate(A, st));
+  SS_CUDA(cudaStreamSynchronize(st));  // host staging vectors die with this frame
+  return SSGPU_OK;
+}
+
+}  // namespace ssgpu
+
+extern "C" int ssgpu_SimulateC_dev(int nsim, int repeat_Q, int N, int p, int m, int rR, int r, int mP, const double* a,
+                                   const double* Z, int nZ, const double* T, int nT, const double* R, int nR,
+                                   const double* Q, int nQ, const double* P_star, int draw_initial, int eta_only,
+                                   const double* draws, long long n_draws, const double* Q_root, const double* P_root,
+                                   double* y, double* a_out, double* eta, void* stream) {
+  SS_TRY(check_sim(nsim, repeat_Q, N, p, m, rR, r, mP, a, Z, nZ, T, nT, R, nR, Q, nQ, P_star, draw_initial, eta_only,
+                   draws, n_draws, P_root));
+  SS_TRY(ensure_device());
+  cudaStream_t st = stream ? (cudaStream_t)stream : lib_stream();
+  return simulate_core(nsim, repeat_Q, N, p, m, rR, r, a, Z, nZ, T, nT, R, nR, Q, nQ, P_star, draw_initial, eta_only,
+                       draws, Q_root, P_root, y, a_out, eta, st);
+}
+
+extern "C" int ssgpu_SimulateC(int nsim, int repeat_Q, int N, int p, int m, int rR, int r, int mP, const double* a,
+                               const double* Z, int nZ, const double* T, int nT, const double* R, int nR,
+                               const double* Q, int nQ, const double* P_star, int draw_initial, int eta_only,
+                               int transposed_state, const double* draws, long long n_draws, const double* Q_root,
+                               const double* P_root, double* y, double* a_out, double* a_t, double* eta) {
+  SS_TRY(check_sim(nsim, repeat_Q, N, p, m, rR, r, mP, a, Z, nZ, T, nT, R, nR, Q, nQ, P_star, draw_initial, eta_only,
+                   draws, n_draws, P_root));
+  SS_TRY(ensure_device());
+  cudaStream_t st = lib_stream();
+  const int r_tot = r * repeat_Q;
+  const size_t ns = (size_t)nsim;
+  DevBuf dr, yN, aN, eN, outR;
+  SS_TRY(upload(dr, draws, (size_t)n_draws, st));
+  size_t biggest = (size_t)N * r_tot * ns;
+  if (!eta_only) {
     SS_TRY(yN.alloc(sizeof(double) * (size_t)N * p * ns, st));
     SS_TRY(aN.alloc(sizeof(double) * (size_t)N * m * ns, st));
-    A.y = yN.as<double>();
-    A.a = aN.as<double>();
     if ((size_t)N * m * ns > biggest) biggest = (size_t)N * m * ns;
     if ((size_t)N * p * ns > biggest) biggest = (size_t)N * p * ns;
   }
   SS_TRY(eN.alloc(sizeof(double) * (size_t)N * r_tot * ns, st));
-  A.eta = eN.as<double>();
-  SS_TRY(launch_simulate(A, st));
+  SS_TRY(simulate_core(nsim, repeat_Q, N, p, m, rR, r, a, Z, nZ, T, nT, R, nR, Q, nQ, P_star, draw_initial, eta_only,
+                       dr.as<double>(), Q_root, P_root, eta_only ? nullptr : yN.as<double>(),
+                       eta_only ? nullptr : aN.as<double>(), eN.as<double>(), st));
   SS_TRY(outR.alloc(sizeof(double) * biggest, st));
   if (eta) {
     SS_TRY(launch_permute_tks(eN.as<double>(), outR.as<double>(), N, r_tot, nsim, true, st));
@@ -263,6 +379,31 @@ extern "C" int ssgpu_SimulateC(int nsim, int repeat_Q, int N, int p, int m, int 
   }
   SS_CUDA(cudaStreamSynchronize(st));
   return SSGPU_OK;
+}
+
+extern "C" int ssgpu_ExtractComponentC_dev(const double* a, int m, int nsim, int N, const double* Z, int p, int nZ,
+                                           double* out, void* stream) {
+  SS_ARG(a && Z && out, "null pointer argument");
+  SS_ARG(m >= 1 && nsim >= 1 && N >= 1 && p >= 1 && (nZ == 1 || nZ == N), "bad dimensions");
+  SS_TRY(ensure_device());
+  cudaStream_t st = stream ? (cudaStream_t)stream : lib_stream();
+  DevBuf zD;
+  SS_TRY(upload(zD, Z, (size_t)p * m * nZ, st));
+  SS_TRY(launch_extract(a, 1, dmat3(zD.as<double>(), p, m, nZ), m, p, nsim, N, out, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  return SSGPU_OK;
+}
+
+extern "C" int ssgpu_last_sim_kernel_ms(double* simulate_ms, double* fast_smoother_ms, double* extract_ms) {
+  last_sim_kernel_ms(simulate_ms, fast_smoother_ms, extract_ms);
+  return SSGPU_OK;
+}
+
+extern "C" int ssgpu_draw_layout_dev(const double* src, double* dst, int N, int K, long long nsim, int to_r, void* stream) {
+  SS_ARG(src && dst && N >= 1 && K >= 1 && nsim >= 1, "bad arguments");
+  SS_TRY(ensure_device());
+  cudaStream_t st = stream ? (cudaStream_t)stream : lib_stream();
+  return launch_permute_tks(src, dst, N, K, nsim, to_r != 0, st);
 }
 
 extern "C" int ssgpu_ExtractComponentC(const double* a, int m, int nsim, int N, const double* Z, int p, int nZ,

@@ -114,11 +114,69 @@ int launch_bwd_generic(const DModel& md, const ssgpu_kalman_out* kout, const Kal
                        cudaStream_t st);
 
 // ---- simulation smoother (sim.cu) --------------------------------------------------------------
+// Non-zero pattern of a (possibly time-varying) matrix, the union over its slices: the entries of row i (or of
+// column i for a by-columns pattern) are idx[ptr[i]] .. idx[ptr[i+1]-1], ascending.  Values are read from the
+// dense matrix itself.  Skipping an exact zero leaves an fma chain bit-identical (fma(0, x, acc) == acc for
+// finite x), so the per-draw kernels stay bit-exact against the dense-loop oracle while a SARIMA companion
+// matrix costs its ~30 non-zeros instead of m^2 = 784 multiply-adds.
+struct SpPat {
+  const int* ptr;
+  const int* idx;
+};
+
+// host-side builder: all patterns of one call are packed into one int buffer and uploaded together
+class PatPack {
+ public:
+  // by rows of a rows x cols x n_slices column-major array; returns the offset of the pattern
+  size_t rows_of(const double* M, int rows, int cols, int n_slices);
+  size_t cols_of(const double* M, int rows, int cols, int n_slices);
+  // structural pattern of Q_t R_t' (r x m) by rows
+  size_t qtr_of(const double* Q, int nQ, const double* R, int nR, int m, int r);
+  size_t dense(int rows, int cols);
+  const std::vector<int>& words() const { return w_; }
+  SpPat at(const int* dev_base, size_t off, int n_rows) const { return SpPat{dev_base + off, dev_base + off + n_rows + 1}; }
+
+ private:
+  size_t finish(const std::vector<std::vector<int>>& lists);
+  std::vector<int> w_;
+};
+
+// Fixed-width (ELL) form of a sparse matrix for the per-draw kernels: row i (or column i of the matrix for a
+// by-columns build) holds W (index, value) pairs, k ascending, padded with (0, 0.0) -- fma(0, x[0], acc) == acc, so
+// padding changes no bit.  W is the largest non-zero count of a row over all slices' union pattern; a uniform W
+// lets the inner loop be unrolled with independent loads.  Time-varying matrices carry one value block per slice.
+struct Ell {
+  const int* idx;     // [rows * W]
+  const double* val;  // [n_slices][rows * W]
+  int W;
+  long long st;       // value stride between slices (0 = time-invariant)
+  __host__ __device__ const double* vals(int t) const { return val + (st ? (long long)t * st : 0); }
+};
+
+class EllPack {
+ public:
+  struct Ref {
+    size_t io, vo;
+    int W, rows;
+    long long st;
+  };
+  Ref add(const double* M, int rows, int cols, int n_slices, bool by_cols);
+  const std::vector<int>& ints() const { return i_; }
+  const std::vector<double>& vals() const { return v_; }
+  Ell at(const Ref& r, const int* ib, const double* vb) const { return Ell{ib + r.io, vb + r.vo, r.W, r.st}; }
+
+ private:
+  std::vector<int> i_;
+  std::vector<double> v_;
+};
+
 struct SimArgs {
   int S, N, p, m, rR, r, repeat_Q, nQ;
   int draw_initial, eta_only;
   const double* a0;
   DMat Z, T, R;
+  SpPat Zp;              // by rows
+  Ell Te, Re;            // by rows
   const double* Q_root;  // r x r x nQ
   const double* P_root;  // m x m
   const double* d0;      // [k + m*s]
@@ -132,6 +190,8 @@ struct FsArgs {
   const double* P_inf;
   const double* P_star;
   DMat Z, T, R;
+  SpPat Zp, Qp;      // Z, QtR by rows
+  Ell Te, Tce, Re;   // T, R by rows; T by columns (Tce)
   KalmanScratch g;   // code, F1, K0, K1, QtR
   const double* y;   // native [(t*p+j)*S + s]
   double* v;         // scratch, native [(t*p+j)*S + s]
@@ -139,6 +199,7 @@ struct FsArgs {
   double* eta;       // native [(t*r+kk)*S + s]
 };
 
+void last_sim_kernel_ms(double* sim, double* fs, double* ext);
 int launch_simulate(const SimArgs& A, cudaStream_t st);
 int launch_fs_draws(const FsArgs& A, cudaStream_t st);
 int launch_extract(const double* a, int a_native, const DMat& Z, int m, int p, int S, int N, double* out,

@@ -18,25 +18,50 @@
 
 namespace ssgpu {
 
-constexpr int kSimThreads = 128;
+constexpr int kSimThreads = 128;  // extract kernel; the per-draw kernels pick 32 / 64 / 128 (launchers below)
 
-// per-thread vector v[k] kept in shared memory as sh[k*blockDim.x + tid]: conflict-free
+// per-thread vector v[k] kept in shared memory as sh[k*BT + tid]: conflict-free
+template <int BT>
 struct ShVec {
   double* p;
-  __device__ __forceinline__ double& operator[](int k) const { return p[k * kSimThreads]; }
+  __device__ __forceinline__ double& operator[](int k) const { return p[k * BT]; }
 };
 
 __device__ __forceinline__ const double* slice_of(const DMat& M, int t) { return M.block(0, 0, M.tv() ? t : 0); }
 
+// sum over the pattern entries k of row i: Mt[i + k*ld] * x[k], k ascending, starting from +0
+template <class Vec>
+__device__ __forceinline__ double sp_row_dot(const SpPat& P, int i, const double* Mt, int ld, const Vec& x) {
+  double acc = 0.0;
+  const int e1 = P.ptr[i + 1];
+  for (int e = P.ptr[i]; e < e1; e++) {
+    const int k = P.idx[e];
+    acc = fma(Mt[i + k * ld], x[k], acc);
+  }
+  return acc;
+}
+
+// sum over the W entries of ELL row i: val[i*W + w] * x[idx[i*W + w]], k ascending, starting from +0
+template <class Vec>
+__device__ __forceinline__ double ell_row_dot(const Ell& E, const double* vt, int i, const Vec& x) {
+  double acc = 0.0;
+  const int* id = E.idx + i * E.W;
+  const double* vl = vt + i * E.W;
+#pragma unroll 4
+  for (int w = 0; w < E.W; w++) acc = fma(vl[w], x[id[w]], acc);
+  return acc;
+}
+
 // ---- SimulateC (SimArgs in common.cuh) ----------------------------------------------------------
-__global__ void __launch_bounds__(kSimThreads) simulate_kernel(const SimArgs A) {
+template <int BT>
+__global__ void __launch_bounds__(BT) simulate_kernel(const SimArgs A) {
   extern __shared__ double sh[];
   const int tid = threadIdx.x;
-  const long long s = (long long)blockIdx.x * kSimThreads + tid;
+  const long long s = (long long)blockIdx.x * BT + tid;
   if (s >= A.S) return;
-  const int m = A.m, p = A.p, r = A.r, r_tot = A.r * A.repeat_Q, rR = A.rR, N = A.N;
+  const int m = A.m, p = A.p, r = A.r, r_tot = A.r * A.repeat_Q, N = A.N;
   const long long S = A.S;
-  ShVec av{sh + tid}, a2{sh + (size_t)m * kSimThreads + tid}, et{sh + (size_t)2 * m * kSimThreads + tid};
+  ShVec<BT> av{sh + tid}, a2{sh + (size_t)m * BT + tid}, et{sh + (size_t)2 * m * BT + tid};
   if (!A.eta_only) {
     for (int i = 0; i < m; i++) {
       if (A.draw_initial) {
@@ -61,60 +86,51 @@ __global__ void __launch_bounds__(kSimThreads) simulate_kernel(const SimArgs A) 
       }
     if (A.eta_only) continue;
     const double* Zt = slice_of(A.Z, t);
-    const double* Tt = slice_of(A.T, t);
-    const double* Rt = slice_of(A.R, t);
+    const double* Tt = A.Te.vals(t);
+    const double* Rt = A.Re.vals(t);
     if (A.a)
       for (int k = 0; k < m; k++) A.a[((long long)t * m + k) * S + s] = av[k];
     for (int j = 0; j < p; j++) {
-      double acc = 0.0;
-      for (int k = 0; k < m; k++) acc = fma(Zt[j + k * p], av[k], acc);
+      const double acc = sp_row_dot(A.Zp, j, Zt, p, av);
       if (A.y) A.y[((long long)t * p + j) * S + s] = acc;
     }
     if (t < N - 1) {
-      for (int i = 0; i < m; i++) {
-        double acc = 0.0, acc1 = 0.0;
-        for (int k = 0; k < m; k++) acc = fma(Tt[i + k * m], av[k], acc);
-        for (int k = 0; k < rR; k++) acc1 = fma(Rt[i + k * m], et[k], acc1);
-        a2[i] = acc + acc1;
-      }
+      for (int i = 0; i < m; i++) a2[i] = ell_row_dot(A.Te, Tt, i, av) + ell_row_dot(A.Re, Rt, i, et);
       for (int i = 0; i < m; i++) av[i] = a2[i];
     }
   }
 }
 
 // ---- FastSmootherC per-draw passes ----------------------------------------------------------------
-__global__ void __launch_bounds__(kSimThreads) fs_draw_kernel(const FsArgs A) {
+template <int BT>
+__global__ void __launch_bounds__(BT) fs_draw_kernel(const FsArgs A) {
   extern __shared__ double sh[];
   const int tid = threadIdx.x;
-  const long long s = (long long)blockIdx.x * kSimThreads + tid;
+  const long long s = (long long)blockIdx.x * BT + tid;
   if (s >= A.S) return;
   const int m = A.m, p = A.p, r = A.r, N = A.N;
   const long long S = A.S;
-  const size_t vs = (size_t)m * kSimThreads;
-  ShVec av{sh + tid}, a2{sh + vs + tid}, rr{sh + 2 * vs + tid}, r1{sh + 3 * vs + tid}, r2{sh + 4 * vs + tid},
-      et{sh + 5 * vs + tid};
+  const size_t vs = (size_t)m * BT;
+  // r2 (backward pass only) shares its storage with av (forward passes only)
+  ShVec<BT> av{sh + tid}, a2{sh + vs + tid}, rr{sh + 2 * vs + tid}, r1{sh + 3 * vs + tid}, r2{sh + tid},
+      et{sh + 4 * vs + tid};
 
   // forward: innovations v = y - z'a with the shared gains (src/FastSmootherC.cpp:139-251)
   for (int k = 0; k < m; k++) av[k] = A.a0[k];
   for (int t = 0; t < N; t++) {
     const double* Zt = slice_of(A.Z, t);
-    const double* Tt = slice_of(A.T, t);
+    const double* Tt = A.Te.vals(t);
     for (int j = 0; j < p; j++) {
       const long long index = (long long)t * p + j;
       if ((A.g.code[index] & 255) == 0) continue;
-      double za = 0.0;
-      for (int k = 0; k < m; k++) za = fma(Zt[j + k * p], av[k], za);
+      const double za = sp_row_dot(A.Zp, j, Zt, p, av);
       const double vv = A.y[index * S + s] - za;
       A.v[index * S + s] = vv;
       const double* k0 = A.g.K0 + index * m;
       for (int k = 0; k < m; k++) av[k] = fma(k0[k], vv, av[k]);
     }
     if (t < N - 1) {
-      for (int i = 0; i < m; i++) {
-        double acc = 0.0;
-        for (int k = 0; k < m; k++) acc = fma(Tt[i + k * m], av[k], acc);
-        a2[i] = acc;
-      }
+      for (int i = 0; i < m; i++) a2[i] = ell_row_dot(A.Te, Tt, i, av);
       for (int i = 0; i < m; i++) av[i] = a2[i];
     }
   }
@@ -135,9 +151,13 @@ __global__ void __launch_bounds__(kSimThreads) fs_draw_kernel(const FsArgs A) {
       const double c1 = A.g.F1[index] * A.v[index * S + s];
       double d0 = 0.0;
       for (int k = 0; k < m; k++) d0 = fma(k0[k], rr[k], d0);
+      const int z0 = A.Zp.ptr[j], z1 = A.Zp.ptr[j + 1];
       if (c == 1) {
         const double sc = c1 - d0;
-        for (int k = 0; k < m; k++) rr[k] = fma(Zt[j + k * p], sc, rr[k]);
+        for (int e = z0; e < z1; e++) {
+          const int k = A.Zp.idx[e];
+          rr[k] = fma(Zt[j + k * p], sc, rr[k]);
+        }
       } else {
         double d1 = 0.0, d2 = 0.0;
         for (int k = 0; k < m; k++) {
@@ -145,7 +165,8 @@ __global__ void __launch_bounds__(kSimThreads) fs_draw_kernel(const FsArgs A) {
           d2 = fma(k1[k], rr[k], d2);
         }
         const double s1 = (c1 - d1) - d2, s0 = -d0;
-        for (int k = 0; k < m; k++) {
+        for (int e = z0; e < z1; e++) {
+          const int k = A.Zp.idx[e];
           const double z = Zt[j + k * p];
           r1[k] = fma(z, s1, r1[k]);
           rr[k] = fma(z, s0, rr[k]);
@@ -154,16 +175,11 @@ __global__ void __launch_bounds__(kSimThreads) fs_draw_kernel(const FsArgs A) {
     }
     for (int k = 0; k < m; k++) A.a_smooth[((long long)t * m + k) * S + s] = rr[k];
     if (t > 0) {
-      const double* Tp = slice_of(A.T, t - 1);
+      const double* Tp = A.Tce.vals(t - 1);
       const bool both = ((long long)t * p) < A.init_steps;
-      for (int jj = 0; jj < m; jj++) {
-        double acc = 0.0, acc1 = 0.0;
-        for (int k = 0; k < m; k++) {
-          acc = fma(Tp[k + jj * m], rr[k], acc);
-          if (both) acc1 = fma(Tp[k + jj * m], r1[k], acc1);
-        }
-        r2[jj] = acc;
-        a2[jj] = acc1;
+      for (int jj = 0; jj < m; jj++) {  // T' r: column jj of T
+        r2[jj] = ell_row_dot(A.Tce, Tp, jj, rr);
+        a2[jj] = both ? ell_row_dot(A.Tce, Tp, jj, r1) : 0.0;
       }
       for (int k = 0; k < m; k++) {
         rr[k] = r2[k];
@@ -183,22 +199,16 @@ __global__ void __launch_bounds__(kSimThreads) fs_draw_kernel(const FsArgs A) {
   }
   for (int t = 0; t < N; t++) {
     if (t > 0) {
-      const double* Tp = slice_of(A.T, t - 1);
-      const double* Rp = slice_of(A.R, t - 1);
+      const double* Tp = A.Te.vals(t - 1);
+      const double* Rp = A.Re.vals(t - 1);
       const double* Qp = A.g.QtR + (A.qtr_tv ? (long long)(t - 1) * r * m : 0);
       for (int k = 0; k < m; k++) rr[k] = A.a_smooth[((long long)t * m + k) * S + s];  // r_t
       for (int kk = 0; kk < r; kk++) {
-        double acc = 0.0;
-        for (int k = 0; k < m; k++) acc = fma(Qp[kk + k * r], rr[k], acc);
+        const double acc = sp_row_dot(A.Qp, kk, Qp, r, rr);
         et[kk] = acc;
         A.eta[((long long)(t - 1) * r + kk) * S + s] = acc;
       }
-      for (int i = 0; i < m; i++) {
-        double acc = 0.0, acc1 = 0.0;
-        for (int k = 0; k < m; k++) acc = fma(Tp[i + k * m], av[k], acc);
-        for (int k = 0; k < r; k++) acc1 = fma(Rp[i + k * m], et[k], acc1);
-        a2[i] = acc + acc1;
-      }
+      for (int i = 0; i < m; i++) a2[i] = ell_row_dot(A.Te, Tp, i, av) + ell_row_dot(A.Re, Rp, i, et);
       for (int i = 0; i < m; i++) av[i] = a2[i];
     }
     for (int k = 0; k < m; k++) A.a_smooth[((long long)t * m + k) * S + s] = av[k];
@@ -280,33 +290,182 @@ __global__ void permute_at_kernel(const double* src, double* dst, int m, long lo
   }
 }
 
+// ---- non-zero patterns (host) -----------------------------------------------------------------------
+size_t PatPack::finish(const std::vector<std::vector<int>>& lists) {
+  const size_t off = w_.size();
+  int run = 0;
+  for (const auto& l : lists) {
+    w_.push_back(run);
+    run += (int)l.size();
+  }
+  w_.push_back(run);
+  for (const auto& l : lists) w_.insert(w_.end(), l.begin(), l.end());
+  return off;
+}
+
+size_t PatPack::rows_of(const double* M, int rows, int cols, int n_slices) {
+  std::vector<std::vector<int>> lists(rows);
+  const size_t sl = (size_t)rows * cols;
+  for (int i = 0; i < rows; i++)
+    for (int k = 0; k < cols; k++) {
+      bool nz = false;
+      for (int t = 0; t < n_slices && !nz; t++) nz = M[i + (size_t)k * rows + t * sl] != 0.0;
+      if (nz) lists[i].push_back(k);
+    }
+  return finish(lists);
+}
+
+size_t PatPack::cols_of(const double* M, int rows, int cols, int n_slices) {
+  std::vector<std::vector<int>> lists(cols);
+  const size_t sl = (size_t)rows * cols;
+  for (int j = 0; j < cols; j++)
+    for (int k = 0; k < rows; k++) {
+      bool nz = false;
+      for (int t = 0; t < n_slices && !nz; t++) nz = M[k + (size_t)j * rows + t * sl] != 0.0;
+      if (nz) lists[j].push_back(k);
+    }
+  return finish(lists);
+}
+
+// (Q_t R_t')[kk][k] = sum_l Q_t[kk][l] R_t[k][l] can only be non-zero where some l has both factors non-zero
+size_t PatPack::qtr_of(const double* Q, int nQ, const double* R, int nR, int m, int r) {
+  std::vector<std::vector<int>> lists(r);
+  const int n = nQ > nR ? nQ : nR;
+  for (int kk = 0; kk < r; kk++)
+    for (int k = 0; k < m; k++) {
+      bool nz = false;
+      for (int t = 0; t < n && !nz; t++) {
+        const double* Qt = Q + (size_t)(nQ > 1 ? t : 0) * r * r;
+        const double* Rt = R + (size_t)(nR > 1 ? t : 0) * m * r;
+        for (int l = 0; l < r && !nz; l++) nz = Qt[kk + (size_t)l * r] != 0.0 && Rt[k + (size_t)l * m] != 0.0;
+      }
+      if (nz) lists[kk].push_back(k);
+    }
+  return finish(lists);
+}
+
+EllPack::Ref EllPack::add(const double* M, int rows, int cols, int n_slices, bool by_cols) {
+  const int nr = by_cols ? cols : rows, nc = by_cols ? rows : cols;
+  const size_t sl = (size_t)rows * cols;
+  auto at = [&](int i, int k, int t) { return by_cols ? M[k + (size_t)i * rows + t * sl] : M[i + (size_t)k * rows + t * sl]; };
+  std::vector<std::vector<int>> lists(nr);
+  int W = 1;
+  for (int i = 0; i < nr; i++) {
+    for (int k = 0; k < nc; k++) {
+      bool nz = false;
+      for (int t = 0; t < n_slices && !nz; t++) nz = at(i, k, t) != 0.0;
+      if (nz) lists[i].push_back(k);
+    }
+    if ((int)lists[i].size() > W) W = (int)lists[i].size();
+  }
+  Ref r{i_.size(), v_.size(), W, nr, n_slices > 1 ? (long long)nr * W : 0};
+  for (int i = 0; i < nr; i++)
+    for (int w = 0; w < W; w++) i_.push_back(w < (int)lists[i].size() ? lists[i][w] : 0);
+  for (int t = 0; t < n_slices; t++)
+    for (int i = 0; i < nr; i++)
+      for (int w = 0; w < W; w++) v_.push_back(w < (int)lists[i].size() ? at(i, lists[i][w], t) : 0.0);
+  while (v_.size() % 32) v_.push_back(0.0);
+  while (i_.size() % 32) i_.push_back(0);
+  return r;
+}
+
+size_t PatPack::dense(int rows, int cols) {
+  std::vector<std::vector<int>> lists(rows);
+  for (int i = 0; i < rows; i++)
+    for (int k = 0; k < cols; k++) lists[i].push_back(k);
+  return finish(lists);
+}
+
 // ---- launchers --------------------------------------------------------------------------------------
 static unsigned nblk(long long n, int b) { return (unsigned)((n + b - 1) / b); }
 
-int launch_simulate(const SimArgs& A, cudaStream_t st) {
-  const size_t smem = sizeof(double) * kSimThreads * (2 * (size_t)A.m + (size_t)A.r * A.repeat_Q);
+// Threads per CTA of the per-draw kernels: small CTAs keep every SM busy when a GPU's share of the draws is small
+// (nsim = 1e5 over 8 GPUs is 12,500 draws = 98 CTAs of 128 threads on 148 SMs, but 391 CTAs of 32)
+// Also, the per-thread state vectors live in shared memory ((4m + r) doubles for the smoother): 32-thread CTAs pack
+// an SM's 227 KB more tightly than 128-thread ones once m is large.
+static int pick_bt(long long S, size_t doubles_per_thread) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  if (doubles_per_thread * 8 > 256) return 32;
+  if (S >= (long long)sms * 128 * 4) return 128;
+  if (S >= (long long)sms * 64 * 4) return 64;
+  return 32;
+}
+
+// CUDA events around the last launch of each per-draw kernel (ssgpu_last_sim_kernel_ms: bench.py's live
+// per-kernel time on the launching stream)
+struct KernelTimer {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool used = false;
+  void start(cudaStream_t st) {
+    if (!e0) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+    }
+    cudaEventRecord(e0, st);
+  }
+  void stop(cudaStream_t st) {
+    cudaEventRecord(e1, st);
+    used = true;
+  }
+  double ms() {
+    if (!used) return -1.0;
+    float f = 0.f;
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&f, e0, e1);
+    return f;
+  }
+};
+static KernelTimer g_t_sim, g_t_fs, g_t_ext;
+
+void last_sim_kernel_ms(double* sim, double* fs, double* ext) {
+  if (sim) *sim = g_t_sim.ms();
+  if (fs) *fs = g_t_fs.ms();
+  if (ext) *ext = g_t_ext.ms();
+}
+
+template <int BT>
+static int launch_simulate_bt(const SimArgs& A, cudaStream_t st) {
+  const size_t smem = sizeof(double) * BT * (2 * (size_t)A.m + (size_t)A.r * A.repeat_Q);
   SS_ARG(smem <= 227 * 1024, "SimulateC: state too large for shared memory");
-  SS_CUDA(cudaFuncSetAttribute(simulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  simulate_kernel<<<nblk(A.S, kSimThreads), kSimThreads, smem, st>>>(A);
+  SS_CUDA(cudaFuncSetAttribute(simulate_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  g_t_sim.start(st);
+  simulate_kernel<BT><<<nblk(A.S, BT), BT, smem, st>>>(A);
+  g_t_sim.stop(st);
+  count_launch();
+  SS_CUDA(cudaGetLastError());
+  return SSGPU_OK;
+}
+
+int launch_simulate(const SimArgs& A, cudaStream_t st) {
+  const int bt = pick_bt(A.S, 2 * (size_t)A.m + (size_t)A.r * A.repeat_Q);
+  return bt == 128 ? launch_simulate_bt<128>(A, st) : bt == 64 ? launch_simulate_bt<64>(A, st) : launch_simulate_bt<32>(A, st);
+}
+
+template <int BT>
+static int launch_fs_bt(const FsArgs& A, cudaStream_t st) {
+  const size_t smem = sizeof(double) * BT * (4 * (size_t)A.m + (size_t)A.r);
+  SS_ARG(smem <= 227 * 1024, "FastSmootherC: state too large for shared memory");
+  SS_CUDA(cudaFuncSetAttribute(fs_draw_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  g_t_fs.start(st);
+  fs_draw_kernel<BT><<<nblk(A.S, BT), BT, smem, st>>>(A);
+  g_t_fs.stop(st);
   count_launch();
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;
 }
 
 int launch_fs_draws(const FsArgs& A, cudaStream_t st) {
-  const size_t smem = sizeof(double) * kSimThreads * (5 * (size_t)A.m + (size_t)A.r);
-  SS_ARG(smem <= 227 * 1024, "FastSmootherC: state too large for shared memory (m > 44)");
-  SS_CUDA(cudaFuncSetAttribute(fs_draw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  fs_draw_kernel<<<nblk(A.S, kSimThreads), kSimThreads, smem, st>>>(A);
-  count_launch();
-  SS_CUDA(cudaGetLastError());
-  return SSGPU_OK;
+  const int bt = pick_bt(A.S, 4 * (size_t)A.m + (size_t)A.r);
+  return bt == 128 ? launch_fs_bt<128>(A, st) : bt == 64 ? launch_fs_bt<64>(A, st) : launch_fs_bt<32>(A, st);
 }
 
 int launch_extract(const double* a, int a_native, const DMat& Z, int m, int p, int S, int N, double* out,
                    cudaStream_t st) {
   SS_ARG(N <= 65535, "ExtractComponentC: N too large");
+  g_t_ext.start(st);
   extract_kernel<<<dim3(nblk(S, kSimThreads), N), kSimThreads, 0, st>>>(a, a_native, Z, m, p, S, N, out);
+  g_t_ext.stop(st);
   count_launch();
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;

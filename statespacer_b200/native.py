@@ -46,7 +46,8 @@ class KalmanOut(C.Structure):
 SYMBOLS = ["ssgpu_version", "ssgpu_last_error", "ssgpu_set_device", "ssgpu_device_count", "ssgpu_release",
            "ssgpu_launch_count", "ssgpu_LogLikC", "ssgpu_KalmanC", "ssgpu_FastSmootherC", "ssgpu_SimulateC",
            "ssgpu_sym_root", "ssgpu_ExtractComponentC", "ssgpu_loglik_batch", "ssgpu_loglik_batch_dev",
-           "ssgpu_last_kernel", "ssgpu_fp64_peak", "ssgpu_plan_state_order"]
+           "ssgpu_last_kernel", "ssgpu_fp64_peak", "ssgpu_plan_state_order", "ssgpu_SimulateC_dev",
+           "ssgpu_FastSmootherC_dev", "ssgpu_ExtractComponentC_dev", "ssgpu_draw_layout_dev", "ssgpu_last_sim_kernel_ms"]
 
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS, KERNEL_MMA, KERNEL_MMA_DENSE = 0, 1, 2, 3, 4
 
@@ -68,6 +69,12 @@ def lib():
         L.ssgpu_FastSmootherC.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp, i, vp, i, vp, i, vp, i, i, i, vp, vp, vp]
         L.ssgpu_SimulateC.argtypes = [i] * 8 + [vp, vp, i, vp, i, vp, i, vp, i, vp, i, i, i, vp, ll, vp, vp,
                                                 vp, vp, vp, vp]
+        L.ssgpu_SimulateC_dev.argtypes = [i] * 8 + [vp, vp, i, vp, i, vp, i, vp, i, vp, i, i, vp, ll, vp, vp,
+                                                    vp, vp, vp, vp]
+        L.ssgpu_FastSmootherC_dev.argtypes = [vp, i, i, i, i, i, vp, vp, vp, vp, i, vp, i, vp, i, vp, i, i, vp, vp, vp]
+        L.ssgpu_ExtractComponentC_dev.argtypes = [vp, i, i, i, vp, i, i, vp, vp]
+        L.ssgpu_draw_layout_dev.argtypes = [vp, vp, i, i, ll, i, vp]
+        L.ssgpu_last_sim_kernel_ms.argtypes = [dp, dp, dp]
         L.ssgpu_sym_root.argtypes = [vp, i, vp]
         L.ssgpu_ExtractComponentC.argtypes = [vp, i, i, i, vp, i, i, vp]
         L.ssgpu_loglik_batch.argtypes = [vp, ll, i, C.POINTER(Model), i, vp]

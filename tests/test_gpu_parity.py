@@ -406,6 +406,48 @@ def test_fast_smoother_airline_sim_smoother_pipeline():
     assert np.array_equal(sims["gpu"][2], sims["cpu"][2])
 
 
+@pytest.mark.parametrize("nsim", [100, 40000, 80000])
+def test_sim_smoother_device_resident_pipeline(nsim):
+    """The *_dev entry points (draws stay on the GPU in the draw-contiguous layout) give the same bits as the
+    host-pointer entry points; nsim picks the 32-, 64- and 128-thread variants of the per-draw kernels.  A small
+    prefix of the draws is also checked against the C oracle."""
+    import torch
+    rng = np.random.default_rng(11)
+    N, m, p, r = 12, 6, 2, 3
+    sm = random_model(rng, m, p, r=r, d=2, N=N)
+    sm.T[:, :, 0][np.abs(sm.T[:, :, 0]) < 0.25] = 0.0            # some structural zeros for the sparse loops
+    y_obs = simulate_y(rng, sm, N)
+    steps = api.KalmanC(y_obs, np.isnan(y_obs), *sm.args(), False)["initialisation_steps"]
+    draws = rng.normal(size=m * nsim + N * r * nsim)
+    Q_root = cport.sym_root(sm.Q[:, :, 0])[:, :, None]
+    P_root = cport.sym_root(sm.P_star)
+    host = api.SimulateC(nsim, 1, N, sm.a, sm.Z, sm.T, sm.R, sm.Q, sm.P_star, True, False, False, draws,
+                         Q_root=Q_root, P_root=P_root)
+    fs_h = api.FastSmootherC(host["y"], *sm.args(), steps, False)
+    dev = api.SimulateC_dev(nsim, 1, N, sm.a, sm.Z, sm.T, sm.R, sm.Q, sm.P_star, True, False,
+                            torch.from_numpy(draws).cuda(), Q_root=Q_root, P_root=P_root)
+    fs_d = api.FastSmootherC_dev(dev["y"], *sm.args(), steps)
+    comp_d = api.ExtractComponentC_dev(fs_d["a_smooth"], sm.Z)
+    to_np = lambda t: t.cpu().numpy().transpose(0, 1, 2)          # (N, K, nsim), same index order as R's array
+    for k in ("y", "a", "eta"):
+        assert np.array_equal(to_np(dev[k]), host[k]), k
+    for k in ("a_smooth", "eta"):
+        assert np.array_equal(to_np(fs_d[k]), fs_h[k]), k
+    comp_h = np.einsum("pk,tks->tps", sm.Z[:, :, 0], fs_h["a_smooth"])
+    assert np.allclose(to_np(comp_d), comp_h, rtol=1e-12, atol=1e-12)
+    flat = api.draw_layout_dev(fs_d["a_smooth"], True).cpu().numpy()
+    assert np.array_equal(flat, fs_h["a_smooth"].ravel(order="F"))
+    k = 16                                                        # oracle on the first draws
+    sub = np.concatenate([draws[:m * nsim].reshape(nsim, m)[:k].ravel(),
+                          draws[m * nsim:].reshape(N, nsim, r)[:, :k].ravel()])
+    ref = cport.SimulateC(k, 1, N, sm.a, sm.Z, sm.T, sm.R, sm.Q, sm.P_star, True, False, False, sub, Q_root=Q_root,
+                          P_root=P_root)
+    assert np.array_equal(ref["y"], host["y"][:, :, :k]) and np.array_equal(ref["a"], host["a"][:, :, :k])
+    fs_r = cport.FastSmootherC(ref["y"], *sm.args(), steps, False)
+    assert np.array_equal(fs_r["a_smooth"], fs_h["a_smooth"][:, :, :k])
+    assert np.array_equal(fs_r["eta"], fs_h["eta"][:, :, :k])
+
+
 def test_extract_component():
     rng = np.random.default_rng(9)
     m, nsim, N, p = 5, 70, 9, 2
