@@ -146,9 +146,9 @@ class PatPack {
 // padding changes no bit.  W is the largest non-zero count of a row over all slices' union pattern; a uniform W
 // lets the inner loop be unrolled with independent loads.  Time-varying matrices carry one value block per slice.
 struct Ell {
-  const int* idx;     // [rows * W]
-  const double* val;  // [n_slices][rows * W]
-  int W;
+  const int* idx;     // [W][rows]: entry w of row i at w*rows + i
+  const double* val;  // [n_slices][W][rows]
+  int W, rows;
   long long st;       // value stride between slices (0 = time-invariant)
   __host__ __device__ const double* vals(int t) const { return val + (st ? (long long)t * st : 0); }
 };
@@ -163,7 +163,7 @@ class EllPack {
   Ref add(const double* M, int rows, int cols, int n_slices, bool by_cols);
   const std::vector<int>& ints() const { return i_; }
   const std::vector<double>& vals() const { return v_; }
-  Ell at(const Ref& r, const int* ib, const double* vb) const { return Ell{ib + r.io, vb + r.vo, r.W, r.st}; }
+  Ell at(const Ref& r, const int* ib, const double* vb) const { return Ell{ib + r.io, vb + r.vo, r.W, r.rows, r.st}; }
 
  private:
   std::vector<int> i_;

@@ -14,6 +14,8 @@
 // whole covariance recursion for every draw (src/FastSmootherC.cpp:88,150-251).
 // Arithmetic follows the pinned order of oracle/kalman_c.c exactly (fma chains, k ascending): the
 // draws are bit-identical to the C oracle's given the same variates.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ssgpu {
@@ -45,10 +47,8 @@ __device__ __forceinline__ double sp_row_dot(const SpPat& P, int i, const double
 template <class Vec>
 __device__ __forceinline__ double ell_row_dot(const Ell& E, const double* vt, int i, const Vec& x) {
   double acc = 0.0;
-  const int* id = E.idx + i * E.W;
-  const double* vl = vt + i * E.W;
 #pragma unroll 4
-  for (int w = 0; w < E.W; w++) acc = fma(vl[w], x[id[w]], acc);
+  for (int w = 0; w < E.W; w++) acc = fma(vt[w * E.rows + i], x[E.idx[w * E.rows + i]], acc);
   return acc;
 }
 
@@ -216,6 +216,236 @@ __global__ void __launch_bounds__(BT) fs_draw_kernel(const FsArgs A) {
   for (int kk = 0; kk < r; kk++) A.eta[((long long)(N - 1) * r + kk) * S + s] = 0.0;  // :81
 }
 
+
+// ---- register-resident variants (m <= 32, r_tot <= 32) -------------------------------------------------
+// The state vectors live in registers (MP = 8 / 16 / 32 padded entries, every loop over the state fully unrolled);
+// shared memory only holds the gather source of the sparse products: x is parked once per product in xs[k][tid]
+// and row i accumulates  sum_w val[w][i] * xs[idx[w][i]]  with w (dynamic, = k ascending) OUTSIDE the unrolled row
+// loop, so the MP accumulators advance side by side and every load of a sweep is independent.  The operations and
+// their order per result are those of the shared-memory kernels above and of oracle/kalman_c.c: same bits.
+constexpr int kRegBT = 32;
+
+template <int MP>
+__device__ __forceinline__ void ell_apply(const Ell& E, const double* vt, const ShVec<kRegBT>& xs, int m, double (&out)[MP]) {
+#pragma unroll
+  for (int i = 0; i < MP; i++) out[i] = 0.0;
+  for (int w = 0; w < E.W; w++) {
+    const int* id = E.idx + w * E.rows;
+    const double* vl = vt + w * E.rows;
+#pragma unroll
+    for (int i = 0; i < MP; i++)
+      if (i < m) out[i] = fma(vl[i], xs[id[i]], out[i]);
+  }
+}
+
+template <int MP>
+__device__ __forceinline__ void park(const double (&x)[MP], const ShVec<kRegBT>& xs) {
+#pragma unroll
+  for (int k = 0; k < MP; k++) xs[k] = x[k];
+}
+
+template <int MP>
+__global__ void __launch_bounds__(kRegBT) simulate_reg_kernel(const SimArgs A) {
+  extern __shared__ double sh[];
+  const int tid = threadIdx.x;
+  const long long s = (long long)blockIdx.x * kRegBT + tid;
+  if (s >= A.S) return;
+  const int m = A.m, p = A.p, r = A.r, r_tot = A.r * A.repeat_Q, N = A.N;
+  const long long S = A.S;
+  ShVec<kRegBT> xs{sh + tid}, es{sh + (size_t)MP * kRegBT + tid};
+  double av[MP];
+#pragma unroll
+  for (int i = 0; i < MP; i++) av[i] = 0.0;
+  if (!A.eta_only) {
+    if (A.draw_initial) {
+      for (int k = 0; k < m; k++) {
+        const double dk = A.d0[k + (long long)m * s];
+#pragma unroll
+        for (int i = 0; i < MP; i++)
+          if (i < m) av[i] = fma(A.P_root[i + k * m], dk, av[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MP; i++)
+      if (i < m) av[i] = A.a0[i] + av[i];
+  }
+  const long long total = (long long)r_tot * S;
+  for (int t = 0; t < N; t++) {
+    const double* Qr = A.Q_root + (A.nQ > 1 ? (long long)t * r * r : 0);
+    const double* dd = A.dt + total * t + (long long)r_tot * s;
+    for (int q = 0; q < A.repeat_Q; q++)
+      for (int rr = 0; rr < r; rr++) {
+        double acc = 0.0;
+        for (int l = 0; l < r; l++) acc = fma(Qr[rr + l * r], dd[l + r * q], acc);
+        es[rr + r * q] = acc;
+        if (A.eta) A.eta[((long long)t * r_tot + rr + r * q) * S + s] = acc;
+      }
+    if (A.eta_only) continue;
+    const double* Zt = slice_of(A.Z, t);
+    if (A.a) {
+#pragma unroll
+      for (int k = 0; k < MP; k++)
+        if (k < m) A.a[((long long)t * m + k) * S + s] = av[k];
+    }
+    for (int j = 0; j < p; j++) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < MP; k++)
+        if (k < m) {
+          const double z = Zt[j + k * p];
+          if (z != 0.0) acc = fma(z, av[k], acc);
+        }
+      if (A.y) A.y[((long long)t * p + j) * S + s] = acc;
+    }
+    if (t < N - 1) {
+      double o2[MP];
+      park<MP>(av, xs);
+      ell_apply<MP>(A.Te, A.Te.vals(t), xs, m, av);
+      ell_apply<MP>(A.Re, A.Re.vals(t), es, m, o2);
+#pragma unroll
+      for (int i = 0; i < MP; i++) av[i] = av[i] + o2[i];
+    }
+  }
+}
+
+template <int MP>
+__global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
+  extern __shared__ double sh[];
+  const int tid = threadIdx.x;
+  const long long s = (long long)blockIdx.x * kRegBT + tid;
+  if (s >= A.S) return;
+  const int m = A.m, p = A.p, r = A.r, N = A.N;
+  const long long S = A.S;
+  // xs: gather source; es: eta_t for R eta; r1: the diffuse-phase vector r^(1) (touched on d of the N steps only)
+  ShVec<kRegBT> xs{sh + tid}, es{sh + (size_t)MP * kRegBT + tid}, r1{sh + (size_t)2 * MP * kRegBT + tid};
+  double av[MP];
+
+  // forward: innovations v = y - z'a with the shared gains (src/FastSmootherC.cpp:139-251)
+#pragma unroll
+  for (int k = 0; k < MP; k++) av[k] = k < m ? A.a0[k] : 0.0;
+  for (int t = 0; t < N; t++) {
+    const double* Zt = slice_of(A.Z, t);
+    for (int j = 0; j < p; j++) {
+      const long long index = (long long)t * p + j;
+      if ((A.g.code[index] & 255) == 0) continue;
+      double za = 0.0;
+#pragma unroll
+      for (int k = 0; k < MP; k++)
+        if (k < m) {
+          const double z = Zt[j + k * p];
+          if (z != 0.0) za = fma(z, av[k], za);
+        }
+      const double vv = A.y[index * S + s] - za;
+      A.v[index * S + s] = vv;
+      const double* k0 = A.g.K0 + index * m;
+#pragma unroll
+      for (int k = 0; k < MP; k++)
+        if (k < m) av[k] = fma(k0[k], vv, av[k]);
+    }
+    if (t < N - 1) {
+      park<MP>(av, xs);
+      ell_apply<MP>(A.Te, A.Te.vals(t), xs, m, av);
+    }
+  }
+
+  // backward: r_t (and r^(1) while diffuse), src/FastSmootherC.cpp:259-334
+  double rr[MP];
+#pragma unroll
+  for (int k = 0; k < MP; k++) rr[k] = 0.0;
+  for (int k = 0; k < m; k++) r1[k] = 0.0;
+  for (int t = N - 1; t >= 0; t--) {
+    const double* Zt = slice_of(A.Z, t);
+    for (int j = p - 1; j >= 0; j--) {
+      const long long index = (long long)t * p + j;
+      const int c = A.g.code[index] & 255;
+      if (c == 0) continue;
+      const double* k0 = A.g.K0 + index * m;
+      const double c1 = A.g.F1[index] * A.v[index * S + s];
+      double d0 = 0.0;
+#pragma unroll
+      for (int k = 0; k < MP; k++)
+        if (k < m) d0 = fma(k0[k], rr[k], d0);
+      if (c == 1) {
+        const double sc = c1 - d0;
+#pragma unroll
+        for (int k = 0; k < MP; k++)
+          if (k < m) {
+            const double z = Zt[j + k * p];
+            if (z != 0.0) rr[k] = fma(z, sc, rr[k]);
+          }
+      } else {
+        const double* k1 = A.g.K1 + index * m;
+        double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < MP; k++)
+          if (k < m) {
+            d1 = fma(k0[k], r1[k], d1);
+            d2 = fma(k1[k], rr[k], d2);
+          }
+        const double s1 = (c1 - d1) - d2, s0 = -d0;
+#pragma unroll
+        for (int k = 0; k < MP; k++)
+          if (k < m) {
+            const double z = Zt[j + k * p];
+            if (z != 0.0) {
+              r1[k] = fma(z, s1, r1[k]);
+              rr[k] = fma(z, s0, rr[k]);
+            }
+          }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < MP; k++)
+      if (k < m) A.a_smooth[((long long)t * m + k) * S + s] = rr[k];
+    if (t > 0) {
+      const double* Tp = A.Tce.vals(t - 1);
+      const bool both = ((long long)t * p) < A.init_steps;
+      park<MP>(rr, xs);
+      ell_apply<MP>(A.Tce, Tp, xs, m, rr);  // T' r
+      if (both) {  // T' r^(1): rare (the d diffuse steps), kept out of the registers
+        for (int i = 0; i < m; i++) es[i] = ell_row_dot(A.Tce, Tp, i, r1);
+        for (int i = 0; i < m; i++) r1[i] = es[i];
+      }
+    }
+  }
+
+  // forward reconstruction (src/FastSmootherC.cpp:338-367); rr still holds r_0
+  park<MP>(rr, xs);
+#pragma unroll
+  for (int i = 0; i < MP; i++) {
+    av[i] = 0.0;
+    if (i < m) {
+      double acc = 0.0, acc1 = 0.0;
+      for (int k = 0; k < m; k++) {
+        acc = fma(A.P_star[i + k * m], xs[k], acc);
+        acc1 = fma(A.P_inf[i + k * m], r1[k], acc1);
+      }
+      av[i] = (A.a0[i] + acc) + acc1;
+    }
+  }
+  for (int t = 0; t < N; t++) {
+    if (t > 0) {
+      const double* Qp = A.g.QtR + (A.qtr_tv ? (long long)(t - 1) * r * m : 0);
+      for (int k = 0; k < m; k++) xs[k] = A.a_smooth[((long long)t * m + k) * S + s];  // r_t
+      for (int kk = 0; kk < r; kk++) {
+        const double acc = sp_row_dot(A.Qp, kk, Qp, r, xs);
+        es[kk] = acc;
+        A.eta[((long long)(t - 1) * r + kk) * S + s] = acc;
+      }
+      double o2[MP];
+      park<MP>(av, xs);
+      ell_apply<MP>(A.Te, A.Te.vals(t - 1), xs, m, av);
+      ell_apply<MP>(A.Re, A.Re.vals(t - 1), es, m, o2);
+#pragma unroll
+      for (int i = 0; i < MP; i++) av[i] = av[i] + o2[i];
+    }
+#pragma unroll
+    for (int k = 0; k < MP; k++)
+      if (k < m) A.a_smooth[((long long)t * m + k) * S + s] = av[k];
+  }
+  for (int kk = 0; kk < r; kk++) A.eta[((long long)(N - 1) * r + kk) * S + s] = 0.0;  // :81
+}
+
 // ---- ExtractComponentC ----------------------------------------------------------------------------
 // a: R layout m x nsim x N (a_native == 0) or native [(t*m+k)*S+s]; out native [(t*p+j)*S+s]
 __global__ void __launch_bounds__(kSimThreads) extract_kernel(const double* a, int a_native, DMat Z, int m, int p, int S,
@@ -359,11 +589,11 @@ EllPack::Ref EllPack::add(const double* M, int rows, int cols, int n_slices, boo
     if ((int)lists[i].size() > W) W = (int)lists[i].size();
   }
   Ref r{i_.size(), v_.size(), W, nr, n_slices > 1 ? (long long)nr * W : 0};
-  for (int i = 0; i < nr; i++)
-    for (int w = 0; w < W; w++) i_.push_back(w < (int)lists[i].size() ? lists[i][w] : 0);
+  for (int w = 0; w < W; w++)
+    for (int i = 0; i < nr; i++) i_.push_back(w < (int)lists[i].size() ? lists[i][w] : 0);
   for (int t = 0; t < n_slices; t++)
-    for (int i = 0; i < nr; i++)
-      for (int w = 0; w < W; w++) v_.push_back(w < (int)lists[i].size() ? at(i, lists[i][w], t) : 0.0);
+    for (int w = 0; w < W; w++)
+      for (int i = 0; i < nr; i++) v_.push_back(w < (int)lists[i].size() ? at(i, lists[i][w], t) : 0.0);
   while (v_.size() % 32) v_.push_back(0.0);
   while (i_.size() % 32) i_.push_back(0);
   return r;
@@ -437,7 +667,32 @@ static int launch_simulate_bt(const SimArgs& A, cudaStream_t st) {
   return SSGPU_OK;
 }
 
+template <int MP>
+static int launch_simulate_reg(const SimArgs& A, cudaStream_t st) {
+  const size_t smem = sizeof(double) * kRegBT * 2 * MP;
+  g_t_sim.start(st);
+  simulate_reg_kernel<MP><<<nblk(A.S, kRegBT), kRegBT, smem, st>>>(A);
+  g_t_sim.stop(st);
+  count_launch();
+  SS_CUDA(cudaGetLastError());
+  return SSGPU_OK;
+}
+
+static bool reg_variant_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SSGPU_SIM_REG");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+
 int launch_simulate(const SimArgs& A, cudaStream_t st) {
+  const int r_tot = A.r * A.repeat_Q;
+  if (reg_variant_enabled() && A.m <= 32 && r_tot <= 32) {
+    const int need = A.m > r_tot ? A.m : r_tot;
+    return need <= 8 ? launch_simulate_reg<8>(A, st) : need <= 16 ? launch_simulate_reg<16>(A, st)
+                                                                   : launch_simulate_reg<32>(A, st);
+  }
   const int bt = pick_bt(A.S, 2 * (size_t)A.m + (size_t)A.r * A.repeat_Q);
   return bt == 128 ? launch_simulate_bt<128>(A, st) : bt == 64 ? launch_simulate_bt<64>(A, st) : launch_simulate_bt<32>(A, st);
 }
@@ -455,7 +710,22 @@ static int launch_fs_bt(const FsArgs& A, cudaStream_t st) {
   return SSGPU_OK;
 }
 
+template <int MP>
+static int launch_fs_reg(const FsArgs& A, cudaStream_t st) {
+  const size_t smem = sizeof(double) * kRegBT * 3 * MP;
+  g_t_fs.start(st);
+  fs_draw_reg_kernel<MP><<<nblk(A.S, kRegBT), kRegBT, smem, st>>>(A);
+  g_t_fs.stop(st);
+  count_launch();
+  SS_CUDA(cudaGetLastError());
+  return SSGPU_OK;
+}
+
 int launch_fs_draws(const FsArgs& A, cudaStream_t st) {
+  if (reg_variant_enabled() && A.m <= 32 && A.r <= 32) {
+    const int need = A.m > A.r ? A.m : A.r;
+    return need <= 8 ? launch_fs_reg<8>(A, st) : need <= 16 ? launch_fs_reg<16>(A, st) : launch_fs_reg<32>(A, st);
+  }
   const int bt = pick_bt(A.S, 4 * (size_t)A.m + (size_t)A.r);
   return bt == 128 ? launch_fs_bt<128>(A, st) : bt == 64 ? launch_fs_bt<64>(A, st) : launch_fs_bt<32>(A, st);
 }

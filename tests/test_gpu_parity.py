@@ -448,6 +448,29 @@ def test_sim_smoother_device_resident_pipeline(nsim):
     assert np.array_equal(fs_r["eta"], fs_h["eta"][:, :, :k])
 
 
+def test_sim_smoother_large_state_shared_memory_kernels():
+    """m = 36 > 32: the per-draw kernels that keep the state vectors in shared memory (the register variants stop
+    at m = 32), bit-exact against the C oracle."""
+    rng = np.random.default_rng(21)
+    N, m, p, r, nsim = 9, 36, 2, 4, 70
+    sm = random_model(rng, m, p, r=r, d=2, N=N)
+    sm.T[:, :, 0][np.abs(sm.T[:, :, 0]) < 0.12] = 0.0
+    y_obs = simulate_y(rng, sm, N)
+    steps = api.KalmanC(y_obs, np.isnan(y_obs), *sm.args(), False)["initialisation_steps"]
+    draws = rng.normal(size=m * nsim + N * r * nsim)
+    Q_root = cport.sym_root(sm.Q[:, :, 0])[:, :, None]
+    P_root = cport.sym_root(sm.P_star)
+    out = {}
+    for name, mod in (("gpu", api), ("cpu", cport)):
+        s_ = mod.SimulateC(nsim, 1, N, sm.a, sm.Z, sm.T, sm.R, sm.Q, sm.P_star, True, False, True, draws,
+                           Q_root=Q_root, P_root=P_root)
+        out[name] = (s_, mod.FastSmootherC(s_["y"], *sm.args(), steps, True))
+    for k in ("y", "a", "a_t", "eta"):
+        assert np.array_equal(out["gpu"][0][k], out["cpu"][0][k]), k
+    for k in ("a_smooth", "a_t", "eta"):
+        assert np.array_equal(out["gpu"][1][k], out["cpu"][1][k]), k
+
+
 def test_extract_component():
     rng = np.random.default_rng(9)
     m, nsim, N, p = 5, 70, 9, 2
