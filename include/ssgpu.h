@@ -162,6 +162,30 @@ int ssgpu_loglik_batch_dev(const double* y, long long B, int V, const ssgpu_mode
 /* name of the kernel the last ssgpu_loglik_batch[_dev] call on this thread launched */
 const char* ssgpu_last_kernel(void);
 
+/* ---- 6c. Batched loglikelihood and gradient from parameter vectors (new) ---------------------
+ * The objective of the optim loop (R/statespacer.R:917-927) rebuilds the system matrices from theta in R for
+ * every call, and stats::optim takes 2k further calls per gradient (R/statespacer.R:977-982).  For models whose
+ * parameters enter as variances exp(2 theta_i) on the diagonals of Q and P_star (the default univariate
+ * parameterisation, R/Cholesky.R:148-167 -- local level, slope, trigonometric seasonal) the matrices are built on
+ * the device from theta itself: q_index[r] / p_star_index[m] give, per diagonal entry, the parameter it is the
+ * variance of, or -1 to keep the entry of the model's (shared, diagonal) Q / P_star.  a, P_inf, Z, T, R are the
+ * shared matrices of `model`.
+ *   ssgpu_loglik_grad_batch      host pointers; theta [b*k + i]; loglik[b] and the central-difference gradient
+ *                                grad[b*k + i] = (l(theta + h e_i) - l(theta - h e_i)) / 2h from ONE launch of
+ *                                1 + 2k evaluations per series (h = 1e-3 is stats::optim's ndeps default)
+ *   ssgpu_loglik_grad_batch_dev  the same on device pointers (y, theta, loglik, grad), asynchronous on `stream`
+ *   ssgpu_loglik_theta_batch_dev V arbitrary parameter vectors per series, theta [(v*B + b)*k + i] -> out[v*B + b]
+ *                                (multistart candidates, the points of a numDeriv Hessian sweep) */
+int ssgpu_loglik_grad_batch(const double* y, long long B, const ssgpu_model* model, const double* theta, int k,
+                            const int* q_index, const int* p_star_index, double h, int kernel,
+                            double* loglik, double* grad);
+int ssgpu_loglik_grad_batch_dev(const double* y, long long B, const ssgpu_model* model, const double* theta, int k,
+                                const int* q_index, const int* p_star_index, double h, int kernel,
+                                double* loglik, double* grad, void* stream);
+int ssgpu_loglik_theta_batch_dev(const double* y, long long B, int V, const ssgpu_model* model, const double* theta,
+                                 int k, const int* q_index, const int* p_star_index, int kernel, double* out,
+                                 void* stream);
+
 /* ---- 6b. Simulation smoother on device-resident draws (new) ---------------------------------
  * The three per-draw routines again, for callers that keep the draws on the GPU between the steps of
  * R/SimSmoother.R:91-769 (simulate every component -> add -> smooth -> extract) instead of round-tripping

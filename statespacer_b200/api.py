@@ -208,7 +208,9 @@ def ExtractComponentC(a, Z):
 def _stream_handle(stream):
     import torch
     st = stream if stream is not None else torch.cuda.current_stream()
-    return C.c_void_p(st.cuda_stream)
+    # torch's default stream has handle 0, which the C ABI reads as "the library's own stream": name the legacy
+    # default stream explicitly (cudaStreamLegacy == 0x1) so that the work is ordered with torch's
+    return C.c_void_p(st.cuda_stream or 1)
 
 
 def SimulateC_dev(nsim, repeat_Q, N, a, Z, T, R, Q, P_star, draw_initial, eta_only, draws, Q_root=None, P_root=None,
@@ -417,4 +419,55 @@ def loglik_batch_dev(y, model: BatchModel, out, kernel="auto", stream=None):
     handle = s.cuda_stream or 1
     native.check(native.lib().ssgpu_loglik_batch_dev(y.data_ptr(), model.B, model.V, C.byref(model.c),
                                                      _KERNELS[kernel], out.data_ptr(), handle))
+    return out
+
+
+# ---- theta-driven objective / gradient (include/ssgpu.h section 6c) ---------------------------------------
+def _index_vec(x, n, name):
+    v = np.ascontiguousarray(x, dtype=np.int32).reshape(-1)
+    if v.shape[0] != n:
+        raise ValueError(f"{name} must have {n} entries")
+    return v
+
+
+def loglik_grad_batch(y, sm, theta, q_index, p_star_index, h=1e-3, kernel="auto"):
+    """Loglikelihood and central-difference gradient for B series from one launch of 1 + 2k evaluations per
+    series; variances exp(2 theta[q_index[j]]) are placed on the diagonals of Q / P_star on the device
+    (-1 keeps the entry of sm.Q / sm.P_star).  y (N, B) or (N, p, B); theta (B, k).  Returns (loglik (B,), grad (B, k))."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    N, B = _y_dims(y, np.asarray(sm.Z).shape[0])
+    theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(B, -1)
+    k = theta.shape[1]
+    model = BatchModel(sm, N, B, 1)
+    qi, pi = _index_vec(q_index, model.r, "q_index"), _index_vec(p_star_index, model.m, "p_star_index")
+    ll, gr = np.zeros(B), np.zeros((B, k))
+    native.check(native.lib().ssgpu_loglik_grad_batch(y.ctypes.data, B, C.byref(model.c), theta.ctypes.data, k,
+                                                      qi.ctypes.data, pi.ctypes.data, float(h), _KERNELS[kernel],
+                                                      ll.ctypes.data, gr.ctypes.data))
+    return ll, gr
+
+
+def loglik_grad_batch_dev(y, model: BatchModel, theta, q_index, p_star_index, h=1e-3, kernel="auto", stream=None):
+    """The same on device-resident data: y, theta (B, k) are torch CUDA float64 tensors, `model` a BatchModel
+    built with device=... (shared matrices only).  Returns CUDA tensors (loglik (B,), grad (B, k))."""
+    import torch
+    B, k = theta.shape
+    qi, pi = _index_vec(q_index, model.r, "q_index"), _index_vec(p_star_index, model.m, "p_star_index")
+    ll = torch.empty(B, device=y.device, dtype=torch.float64)
+    gr = torch.empty(B, k, device=y.device, dtype=torch.float64)
+    native.check(native.lib().ssgpu_loglik_grad_batch_dev(
+        C.c_void_p(y.data_ptr()), B, C.byref(model.c), C.c_void_p(theta.data_ptr()), k, qi.ctypes.data, pi.ctypes.data,
+        float(h), _KERNELS[kernel], C.c_void_p(ll.data_ptr()), C.c_void_p(gr.data_ptr()), _stream_handle(stream)))
+    return ll, gr
+
+
+def loglik_theta_batch_dev(y, model: BatchModel, theta, q_index, p_star_index, kernel="auto", stream=None):
+    """V arbitrary parameter vectors per series: theta (V, B, k) CUDA tensor -> (V, B) loglik / N."""
+    import torch
+    V, B, k = theta.shape
+    qi, pi = _index_vec(q_index, model.r, "q_index"), _index_vec(p_star_index, model.m, "p_star_index")
+    out = torch.empty(V, B, device=y.device, dtype=torch.float64)
+    native.check(native.lib().ssgpu_loglik_theta_batch_dev(
+        C.c_void_p(y.data_ptr()), B, V, C.byref(model.c), C.c_void_p(theta.contiguous().data_ptr()), k,
+        qi.ctypes.data, pi.ctypes.data, _KERNELS[kernel], C.c_void_p(out.data_ptr()), _stream_handle(stream)))
     return out

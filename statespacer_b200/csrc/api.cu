@@ -401,4 +401,142 @@ int ssgpu_loglik_batch(const double* y, long long B, int V, const ssgpu_model* m
   return SSGPU_OK;
 }
 
+// ---- theta-driven batched loglikelihood / gradient (include/ssgpu.h section 6c) ---------------------------
+namespace {
+
+// The shared parts of `model` (host or device pointers, see `on_device`) -> device; Q and P_star become
+// per-evaluation diagonals built from theta.  Everything allocated here is released stream-ordered.
+struct ThetaWork {
+  DevBuf shared, maps, Qd, Pd, out;
+  DModel md;
+};
+
+int theta_setup(const ssgpu_model* model, bool on_device, long long B, int V, int k, const double* theta_dev,
+                const int* q_index, const int* p_index, double h, int fd, ThetaWork& W, cudaStream_t st) {
+  SS_TRY(to_dmodel(model, &W.md));
+  DModel& md = W.md;
+  const int m = md.m, r = md.r;
+  SS_ARG(q_index && p_index, "null index vector");
+  SS_ARG(k >= 1, "k must be positive");
+  for (int j = 0; j < r; j++) SS_ARG(q_index[j] < k, "q_index entry out of range");
+  for (int j = 0; j < m; j++) SS_ARG(p_index[j] < k, "p_star_index entry out of range");
+  SS_ARG(md.Q.shared() && md.P_star.shared() && !md.Q.tv(), "Q / P_star of the model must be the shared templates");
+  SS_ARG(md.a.shared() && md.P_inf.shared() && md.Z.shared() && md.T.shared() && md.R.shared(),
+         "theta-driven entry points take shared a, P_inf, Z, T, R");
+  // fixed diagonal entries of Q and P_star (host copy), index vectors
+  std::vector<double> qf(r), pf(m);
+  {
+    const size_t nq = md.Q.diag ? r : (size_t)r * r, np = md.P_star.diag ? m : (size_t)m * m;
+    std::vector<double> qh(nq), ph(np);
+    if (on_device) {
+      SS_CUDA(cudaMemcpyAsync(qh.data(), md.Q.p, nq * sizeof(double), cudaMemcpyDeviceToHost, st));
+      SS_CUDA(cudaMemcpyAsync(ph.data(), md.P_star.p, np * sizeof(double), cudaMemcpyDeviceToHost, st));
+      SS_CUDA(cudaStreamSynchronize(st));
+    } else {
+      std::memcpy(qh.data(), md.Q.p, nq * sizeof(double));
+      std::memcpy(ph.data(), md.P_star.p, np * sizeof(double));
+    }
+    for (int j = 0; j < r; j++) {
+      qf[j] = md.Q.diag ? qh[j] : qh[j + (size_t)j * r];
+      if (!md.Q.diag)
+        for (int l = 0; l < r; l++) SS_ARG(l == j || qh[j + (size_t)l * r] == 0.0, "Q template must be diagonal");
+    }
+    for (int j = 0; j < m; j++) {
+      pf[j] = md.P_star.diag ? ph[j] : ph[j + (size_t)j * m];
+      if (!md.P_star.diag)
+        for (int l = 0; l < m; l++) SS_ARG(l == j || ph[j + (size_t)l * m] == 0.0, "P_star template must be diagonal");
+    }
+  }
+  auto pad = [](size_t n) { return (n + 31) / 32 * 32; };
+  if (!on_device) {  // a, P_inf, Z, T, R: host -> device in one block
+    const ssgpu_matrix* src[5] = {&model->a, &model->P_inf, &model->Z, &model->T, &model->R};
+    DMat* dst[5] = {&md.a, &md.P_inf, &md.Z, &md.T, &md.R};
+    size_t total = 0, ext[5];
+    for (int i = 0; i < 5; i++) {
+      ext[i] = extent(*src[i], 1, 1);
+      total += pad(ext[i]);
+    }
+    SS_TRY(W.shared.alloc(total * sizeof(double), st));
+    size_t off = 0;
+    for (int i = 0; i < 5; i++) {
+      SS_CUDA(cudaMemcpyAsync(W.shared.as<double>() + off, src[i]->data, ext[i] * sizeof(double), cudaMemcpyHostToDevice, st));
+      dst[i]->p = W.shared.as<double>() + off;
+      off += pad(ext[i]);
+    }
+  }
+  // index vectors + fixed entries
+  const size_t n_maps = pad((size_t)r + m) /* ints, 4 B */ + pad((size_t)r) + pad((size_t)m);
+  SS_TRY(W.maps.alloc(n_maps * sizeof(double), st));
+  int* qi = W.maps.as<int>();
+  int* pi = qi + r;
+  double* qfd = W.maps.as<double>() + pad((size_t)r + m);
+  double* pfd = qfd + pad((size_t)r);
+  SS_CUDA(cudaMemcpyAsync(qi, q_index, r * sizeof(int), cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaMemcpyAsync(pi, p_index, m * sizeof(int), cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaMemcpyAsync(qfd, qf.data(), r * sizeof(double), cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaMemcpyAsync(pfd, pf.data(), m * sizeof(double), cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaStreamSynchronize(st));  // the host vectors above die with this frame
+  const size_t E = (size_t)B * V;
+  SS_TRY(W.Qd.alloc(E * r * sizeof(double), st));
+  SS_TRY(W.Pd.alloc(E * m * sizeof(double), st));
+  SS_TRY(launch_expand_theta(theta_dev, B, V, k, r, m, qi, pi, qfd, pfd, h, fd, W.Qd.as<double>(), W.Pd.as<double>(), st));
+  md.Q = DMat{W.Qd.as<double>(), (long long)r, (long long)B * r, 0, r, r, 1};
+  md.P_star = DMat{W.Pd.as<double>(), (long long)m, (long long)B * m, 0, m, m, 1};
+  return SSGPU_OK;
+}
+
+}  // namespace
+
+int ssgpu_loglik_theta_batch_dev(const double* y, long long B, int V, const ssgpu_model* model, const double* theta,
+                                 int k, const int* q_index, const int* p_star_index, int kernel, double* out,
+                                 void* stream) {
+  SS_ARG(y && theta && out && B >= 1 && V >= 1, "bad arguments");
+  SS_TRY(ensure_device());
+  cudaStream_t st = stream ? (cudaStream_t)stream : lib_stream();
+  ThetaWork W;
+  SS_TRY(theta_setup(model, true, B, V, k, theta, q_index, p_star_index, 0.0, 0, W, st));
+  return dispatch_batch(W.md, y, B, V, kernel, out, st);
+}
+
+int ssgpu_loglik_grad_batch_dev(const double* y, long long B, const ssgpu_model* model, const double* theta, int k,
+                                const int* q_index, const int* p_star_index, double h, int kernel, double* loglik,
+                                double* grad, void* stream) {
+  SS_ARG(y && theta && loglik && grad && B >= 1 && h > 0.0, "bad arguments");
+  SS_TRY(ensure_device());
+  cudaStream_t st = stream ? (cudaStream_t)stream : lib_stream();
+  ThetaWork W;
+  const int V = 1 + 2 * k;
+  SS_TRY(theta_setup(model, true, B, V, k, theta, q_index, p_star_index, h, 1, W, st));
+  SS_TRY(W.out.alloc((size_t)B * V * sizeof(double), st));
+  SS_TRY(dispatch_batch(W.md, y, B, V, kernel, W.out.as<double>(), st));
+  return launch_fd_gradient(W.out.as<double>(), B, k, h, loglik, grad, st);
+}
+
+int ssgpu_loglik_grad_batch(const double* y, long long B, const ssgpu_model* model, const double* theta, int k,
+                            const int* q_index, const int* p_star_index, double h, int kernel, double* loglik,
+                            double* grad) {
+  SS_ARG(y && theta && loglik && grad && B >= 1 && h > 0.0 && model, "bad arguments");
+  SS_TRY(ensure_device());
+  cudaStream_t st = lib_stream();
+  const size_t n_y = (size_t)model->N * model->p * (size_t)B;
+  DevBuf yd, thd, res;
+  SS_TRY(yd.alloc(n_y * sizeof(double), st));
+  SS_TRY(thd.alloc((size_t)B * k * sizeof(double), st));
+  SS_TRY(res.alloc((size_t)B * (1 + k) * sizeof(double), st));
+  SS_CUDA(cudaMemcpyAsync(yd.get(), y, n_y * sizeof(double), cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaMemcpyAsync(thd.get(), theta, (size_t)B * k * sizeof(double), cudaMemcpyHostToDevice, st));
+  ThetaWork W;
+  const int V = 1 + 2 * k;
+  SS_TRY(theta_setup(model, false, B, V, k, thd.as<double>(), q_index, p_star_index, h, 1, W, st));
+  SS_TRY(W.out.alloc((size_t)B * V * sizeof(double), st));
+  SS_TRY(dispatch_batch(W.md, yd.as<double>(), B, V, kernel, W.out.as<double>(), st));
+  double* ll = res.as<double>();
+  double* gr = ll + B;
+  SS_TRY(launch_fd_gradient(W.out.as<double>(), B, k, h, ll, gr, st));
+  SS_CUDA(cudaMemcpyAsync(loglik, ll, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaMemcpyAsync(grad, gr, (size_t)B * k * sizeof(double), cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  return SSGPU_OK;
+}
+
 }  // extern "C"

@@ -47,7 +47,8 @@ SYMBOLS = ["ssgpu_version", "ssgpu_last_error", "ssgpu_set_device", "ssgpu_devic
            "ssgpu_launch_count", "ssgpu_LogLikC", "ssgpu_KalmanC", "ssgpu_FastSmootherC", "ssgpu_SimulateC",
            "ssgpu_sym_root", "ssgpu_ExtractComponentC", "ssgpu_loglik_batch", "ssgpu_loglik_batch_dev",
            "ssgpu_last_kernel", "ssgpu_fp64_peak", "ssgpu_plan_state_order", "ssgpu_SimulateC_dev",
-           "ssgpu_FastSmootherC_dev", "ssgpu_ExtractComponentC_dev", "ssgpu_draw_layout_dev", "ssgpu_last_sim_kernel_ms"]
+           "ssgpu_FastSmootherC_dev", "ssgpu_ExtractComponentC_dev", "ssgpu_draw_layout_dev", "ssgpu_last_sim_kernel_ms",
+           "ssgpu_loglik_grad_batch", "ssgpu_loglik_grad_batch_dev", "ssgpu_loglik_theta_batch_dev"]
 
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS, KERNEL_MMA, KERNEL_MMA_DENSE = 0, 1, 2, 3, 4
 
@@ -80,6 +81,10 @@ def lib():
         L.ssgpu_loglik_batch.argtypes = [vp, ll, i, C.POINTER(Model), i, vp]
         L.ssgpu_loglik_batch_dev.argtypes = [vp, ll, i, C.POINTER(Model), i, vp, vp]
         L.ssgpu_fp64_peak.argtypes = [i, i, i, dp, dp]
+        d = C.c_double
+        L.ssgpu_loglik_grad_batch.argtypes = [vp, ll, C.POINTER(Model), vp, i, vp, vp, d, i, vp, vp]
+        L.ssgpu_loglik_grad_batch_dev.argtypes = [vp, ll, C.POINTER(Model), vp, i, vp, vp, d, i, vp, vp, vp]
+        L.ssgpu_loglik_theta_batch_dev.argtypes = [vp, ll, i, C.POINTER(Model), vp, i, vp, vp, i, vp, vp]
         L.ssgpu_plan_state_order.argtypes = [vp, i, vp, vp, vp]
         L.ssgpu_device_count.argtypes = [ip]
         L.ssgpu_set_device.argtypes = [i]

@@ -210,6 +210,48 @@ def test_batch_every_state_dim(m):
         assert abs(cols[b] - want) <= tol, (m, b, cols[b], want)
 
 
+BSM_Q_INDEX = [0, 1, 2] + [3] * 11       # config 5: Q = diag(s2_eps, s2_level, s2_slope, s2_seas x 11)
+BSM_P_INDEX = [0] + [-1] * 13            # P_star = diag(s2_eps, 0, ...)
+
+
+def test_loglik_grad_batch_from_theta():
+    """theta -> variances on the device + central-difference gradient from one launch
+    against the oracle evaluated at the same 1 + 2k parameter vectors with matrices built on the host."""
+    import torch
+    rng = np.random.default_rng(31)
+    B, N, k, h = 40, 80, 4, 1e-3
+    thetas, _, _, y = _bsm_batch(rng, B, N, 1, 0.03)
+    theta = thetas[0]                                                   # (B, 4)
+    sm0 = sysmat.bsm12(theta[0])
+    ll, gr = api.loglik_grad_batch(y, sm0, theta, BSM_Q_INDEX, BSM_P_INDEX, h=h)
+    assert api.last_kernel().startswith("loglik_mma")
+    for b in range(0, B, 5):
+        yb = y[:, b:b + 1]
+        f = lambda th: cport.LogLikC(yb, np.isnan(yb), *sysmat.bsm12(th).args())
+        want = f(theta[b])
+        assert abs(ll[b] - want) <= RTOL * max(1, abs(want))
+        for i in range(k):
+            e = np.zeros(k)
+            e[i] = h
+            g = (f(theta[b] + e) - f(theta[b] - e)) / (2 * h)
+            assert abs(gr[b, i] - g) <= 1e-9 * max(1, abs(want)) / h * 2 + 1e-9 * abs(g), (b, i, gr[b, i], g)
+    # device-resident variants, bit-identical to the host-pointer entry point
+    dev = torch.device("cuda")
+    model = api.BatchModel(sm0, N, B, 1, device=dev)
+    y_d, th_d = torch.from_numpy(y).to(dev), torch.from_numpy(theta).to(dev)
+    ll_d, gr_d = api.loglik_grad_batch_dev(y_d, model, th_d, BSM_Q_INDEX, BSM_P_INDEX, h=h)
+    assert np.array_equal(ll_d.cpu().numpy(), ll) and np.array_equal(gr_d.cpu().numpy(), gr)
+    pts = torch.stack([th_d, th_d + 0.1, th_d - 0.2])
+    out = api.loglik_theta_batch_dev(y_d, model, pts, BSM_Q_INDEX, BSM_P_INDEX).cpu().numpy()
+    assert np.array_equal(out[0], ll)
+    yb = y[:, 7:8]
+    want = cport.LogLikC(yb, np.isnan(yb), *sysmat.bsm12(theta[7] - 0.2).args())
+    assert abs(out[2, 7] - want) <= RTOL * max(1, abs(want))
+    # argument errors
+    with pytest.raises(api.native.SsgpuError):
+        api.loglik_grad_batch(y, sm0, theta, [9] * 14, BSM_P_INDEX)
+
+
 def _block_diagonal_model(rng, m, p, d, N, scatter=True):
     """Random model whose T is block diagonal with blocks of size 1-3 scattered over the state vector, so
     that the tensor kernel has to re-order the states to reach a tile-diagonal T."""
