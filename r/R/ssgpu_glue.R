@@ -43,3 +43,16 @@ loglik_and_gradient <- function(theta, y, sysmat, sysmat_diag, h = 1e-3) {
                      sysmat$R, sysmat$Q, Q_diag = sapply(d, `[[`, "Q"), P_star_diag = sapply(d, `[[`, "P_star"))
   list(value = ll[1, 1], gradient = (ll[1, seq(2, 2 * k, 2)] - ll[1, seq(3, 2 * k + 1, 2)]) / (2 * h))
 }
+
+#' Objective and gradient straight from parameter vectors: the variances exp(2 * theta) are placed on the
+#' diagonals of Q / P_star on the GPU (q_index / p_star_index: 1-based parameter index per diagonal entry, 0 = keep
+#' the entry of the shared matrix), so R neither rebuilds system matrices nor ships them per evaluation.
+#' With one series this is optim(fn =, gr =) for statespacer()'s loop (R/statespacer.R:917-982); with B series it
+#' fits B models at once.
+#' @param Y B x (N*p) matrix as for LogLikBatchC; @param theta k x B matrix.
+#' @return list(value = numeric(B), gradient = k x B matrix), both of loglik / N.
+LogLikGradBatchC <- function(Y, theta, q_index, p_star_index, sysmat, h = 1e-3) {
+  Y[is.na(Y)] <- NaN
+  .Call(`_statespacer_LogLikGradBatchC`, Y, as.matrix(theta), as.integer(q_index) - 1L, as.integer(p_star_index) - 1L,
+        as.numeric(h), sysmat$a, sysmat$P_inf, sysmat$P_star, sysmat$Z, sysmat$T, sysmat$R, sysmat$Q)
+}

@@ -1,14 +1,14 @@
 /* .Call shim: the five registered native routines of statespacer (src/RcppExports.cpp:108-115, same
- * names, same arity) plus `_statespacer_LogLikBatchC`, implemented on libssgpu (include/ssgpu.h) with
+ * names, same arity) plus `_statespacer_LogLikBatchC` and `_statespacer_LogLikGradBatchC`, implemented on libssgpu (include/ssgpu.h) with
  * R's plain C API -- no Rcpp, no Armadillo.
  *
  * Build inside the package (src/Makevars):
  *     PKG_CPPFLAGS = -I$(SSGPU_HOME)/include
  *     PKG_LIBS     = -L$(SSGPU_HOME)/statespacer_b200 -lssgpu -Wl,-rpath,$(SSGPU_HOME)/statespacer_b200
  * and delete LogLikC.cpp, KalmanC.cpp, FastSmootherC.cpp, SimulateC.cpp, ExtractComponentC.cpp and
- * RcppExports.cpp from src/.  R is not installed in the image this repository is developed in, so this file
- * is NOT compiled or tested there: everything below the boundary is exercised through the same C ABI from
- * Python (tests/test_gpu_parity.py).
+ * RcppExports.cpp from src/.  R is not installed in the image this repository is developed in: there this file
+ * is only type-checked against declaration-only stand-ins of R's headers (tests/rstub, tests/test_abi.py);
+ * everything below the boundary is exercised through the same C ABI from Python (tests/test_gpu_parity.py).
  *
  * Contract kept from the reference: inputs are read-only; results are freshly allocated and
  * PROTECTed; 3-D arguments carry a length-3 dim; the RNG state is read/written around SimulateC exactly like
@@ -19,6 +19,7 @@
 #include <R.h>
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
+#include <string.h>
 
 #include "ssgpu.h"
 
@@ -245,6 +246,47 @@ SEXP _statespacer_LogLikBatchC(SEXP yt, SEXP V_, SEXP a, SEXP P_inf, SEXP P_star
   return out;
 }
 
+/* New: objective and central-difference gradient for B series from parameter vectors (ssgpu.h section 6c).
+ * yt: B x (N*p) as for LogLikBatchC; theta: k x B matrix (column b = theta of series b, i.e. [b*k + i]);
+ * q_index / p_star_index: integer vectors (0-based parameter index per diagonal entry of Q / P_star, -1 = keep
+ * the entry of the shared matrix).  Returns list(value = numeric(B), gradient = k x B matrix). */
+SEXP _statespacer_LogLikGradBatchC(SEXP yt, SEXP theta, SEXP q_index, SEXP p_star_index, SEXP h_, SEXP a, SEXP P_inf,
+                                   SEXP P_star, SEXP Z, SEXP T, SEXP R, SEXP Q) {
+  int B, Np, one, m, mc, ms, p, zc, nZ, tr, tc, nT, rr, r, nR, qr, qc, nQ, k, Bt, one2;
+  dims3(yt, &B, &Np, &one);
+  dims3(theta, &k, &Bt, &one2);
+  dims3(P_star, &m, &mc, &ms);
+  dims3(Z, &p, &zc, &nZ);
+  dims3(T, &tr, &tc, &nT);
+  dims3(R, &rr, &r, &nR);
+  dims3(Q, &qr, &qc, &nQ);
+  if (Bt != B || LENGTH(q_index) != r || LENGTH(p_star_index) != m) Rf_error("LogLikGradBatchC: inconsistent sizes");
+  ssgpu_model mo;
+  memset(&mo, 0, sizeof mo);
+  mo.N = Np / p; mo.p = p; mo.m = m; mo.r = r;
+  mo.a = (ssgpu_matrix){REAL(a), m, 1, 0, 1, 0, 0};
+  mo.P_inf = (ssgpu_matrix){REAL(P_inf), m, m, 0, 1, 0, 0};
+  mo.P_star = (ssgpu_matrix){REAL(P_star), m, m, 0, 1, 0, 0};
+  mo.Z = (ssgpu_matrix){REAL(Z), p, m, 0, nZ, 0, 0};
+  mo.T = (ssgpu_matrix){REAL(T), m, m, 0, nT, 0, 0};
+  mo.R = (ssgpu_matrix){REAL(R), m, r, 0, nR, 0, 0};
+  mo.Q = (ssgpu_matrix){REAL(Q), r, r, 0, nQ, 0, 0};
+  SEXP value = PROTECT(Rf_allocVector(REALSXP, B));
+  SEXP grad = PROTECT(Rf_allocMatrix(REALSXP, k, B));
+  int rc = ssgpu_loglik_grad_batch(REAL(yt), B, &mo, REAL(theta), k, INTEGER(q_index), INTEGER(p_star_index),
+                                   Rf_asReal(h_), SSGPU_KERNEL_AUTO, REAL(value), REAL(grad));
+  if (rc != SSGPU_OK) { UNPROTECT(2); chk(rc); }
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SEXP names = PROTECT(Rf_allocVector(STRSXP, 2));
+  SET_STRING_ELT(names, 0, Rf_mkChar("value"));
+  SET_STRING_ELT(names, 1, Rf_mkChar("gradient"));
+  SET_VECTOR_ELT(out, 0, value);
+  SET_VECTOR_ELT(out, 1, grad);
+  Rf_setAttrib(out, R_NamesSymbol, names);
+  UNPROTECT(4);
+  return out;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_statespacer_ExtractComponentC", (DL_FUNC)&_statespacer_ExtractComponentC, 2},
     {"_statespacer_FastSmootherC", (DL_FUNC)&_statespacer_FastSmootherC, 10},
@@ -252,6 +294,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_statespacer_LogLikC", (DL_FUNC)&_statespacer_LogLikC, 9},
     {"_statespacer_SimulateC", (DL_FUNC)&_statespacer_SimulateC, 12},
     {"_statespacer_LogLikBatchC", (DL_FUNC)&_statespacer_LogLikBatchC, 11},
+    {"_statespacer_LogLikGradBatchC", (DL_FUNC)&_statespacer_LogLikGradBatchC, 12},
     {NULL, NULL, 0}};
 
 void R_init_statespacer(DllInfo* dll) {

@@ -117,3 +117,17 @@ def test_state_order_rejects_bad_arguments():
     assert L.ssgpu_plan_state_order(None, 5, None, None, None) == 1
     T = np.eye(30)
     assert L.ssgpu_plan_state_order(T.ctypes.data, 30, None, None, None) == 1
+
+
+def test_r_call_shim_type_checks():
+    """r/src/ssgpu_rcall.c (the .Call shim a maintainer drops into the package) against declaration-only stand-ins
+    of R's headers: catches signature drift between the shim and include/ssgpu.h in an image without R."""
+    import subprocess
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-std=c11", "-I", os.path.join(ROOT, "tests", "rstub"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "r", "src", "ssgpu_rcall.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(ROOT, "r", "src", "ssgpu_rcall.c")).read()
+    for name, arity in (("ExtractComponentC", 2), ("FastSmootherC", 10), ("KalmanC", 10), ("LogLikC", 9),
+                        ("SimulateC", 12)):                       # src/RcppExports.cpp:108-115
+        assert f'{{"_statespacer_{name}", (DL_FUNC)&_statespacer_{name}, {arity}}}' in src
