@@ -195,7 +195,7 @@ struct FsArgs {
   KalmanScratch g;   // code, F1, K0, K1, QtR
   const double* y;   // native [(t*p+j)*S + s]
   double* v;         // scratch, native [(t*p+j)*S + s]
-  double* a_smooth;  // native [(t*m+k)*S + s]; holds r_t between the backward and the last pass
+  double* a_smooth;  // native [(t*m+k)*S + s]
   double* eta;       // native [(t*r+kk)*S + s]
 };
 

@@ -173,8 +173,11 @@ __global__ void __launch_bounds__(BT) fs_draw_kernel(const FsArgs A) {
         }
       }
     }
-    for (int k = 0; k < m; k++) A.a_smooth[((long long)t * m + k) * S + s] = rr[k];
     if (t > 0) {
+      // eta_{t-1} = Q_{t-1} R_{t-1}' r_t (src/FastSmootherC.cpp:345-352) is formed here, while r_t is at hand:
+      // the forward reconstruction then needs r doubles per step instead of a stored N x m array of r_t
+      const double* Qp = A.g.QtR + (A.qtr_tv ? (long long)(t - 1) * r * m : 0);
+      for (int kk = 0; kk < r; kk++) A.eta[((long long)(t - 1) * r + kk) * S + s] = sp_row_dot(A.Qp, kk, Qp, r, rr);
       const double* Tp = A.Tce.vals(t - 1);
       const bool both = ((long long)t * p) < A.init_steps;
       for (int jj = 0; jj < m; jj++) {  // T' r: column jj of T
@@ -201,13 +204,7 @@ __global__ void __launch_bounds__(BT) fs_draw_kernel(const FsArgs A) {
     if (t > 0) {
       const double* Tp = A.Te.vals(t - 1);
       const double* Rp = A.Re.vals(t - 1);
-      const double* Qp = A.g.QtR + (A.qtr_tv ? (long long)(t - 1) * r * m : 0);
-      for (int k = 0; k < m; k++) rr[k] = A.a_smooth[((long long)t * m + k) * S + s];  // r_t
-      for (int kk = 0; kk < r; kk++) {
-        const double acc = sp_row_dot(A.Qp, kk, Qp, r, rr);
-        et[kk] = acc;
-        A.eta[((long long)(t - 1) * r + kk) * S + s] = acc;
-      }
+      for (int kk = 0; kk < r; kk++) et[kk] = A.eta[((long long)(t - 1) * r + kk) * S + s];
       for (int i = 0; i < m; i++) a2[i] = ell_row_dot(A.Te, Tp, i, av) + ell_row_dot(A.Re, Rp, i, et);
       for (int i = 0; i < m; i++) av[i] = a2[i];
     }
@@ -323,10 +320,14 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
   // forward: innovations v = y - z'a with the shared gains (src/FastSmootherC.cpp:139-251)
 #pragma unroll
   for (int k = 0; k < MP; k++) av[k] = k < m ? A.a0[k] : 0.0;
+  const long long Np = (long long)N * p;
+  double y_next = A.y[s];  // observations are fetched one univariate step ahead of their use
   for (int t = 0; t < N; t++) {
     const double* Zt = slice_of(A.Z, t);
     for (int j = 0; j < p; j++) {
       const long long index = (long long)t * p + j;
+      const double y_now = y_next;
+      if (index + 1 < Np) y_next = A.y[(index + 1) * S + s];
       if ((A.g.code[index] & 255) == 0) continue;
       double za = 0.0;
 #pragma unroll
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
           const double z = Zt[j + k * p];
           if (z != 0.0) za = fma(z, av[k], za);
         }
-      const double vv = A.y[index * S + s] - za;
+      const double vv = y_now - za;
       A.v[index * S + s] = vv;
       const double* k0 = A.g.K0 + index * m;
 #pragma unroll
@@ -353,14 +354,17 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
 #pragma unroll
   for (int k = 0; k < MP; k++) rr[k] = 0.0;
   for (int k = 0; k < m; k++) r1[k] = 0.0;
+  double v_next = A.v[(Np - 1) * S + s];  // innovations, one univariate step ahead (steps without one read junk)
   for (int t = N - 1; t >= 0; t--) {
     const double* Zt = slice_of(A.Z, t);
     for (int j = p - 1; j >= 0; j--) {
       const long long index = (long long)t * p + j;
+      const double v_now = v_next;
+      if (index > 0) v_next = A.v[(index - 1) * S + s];
       const int c = A.g.code[index] & 255;
       if (c == 0) continue;
       const double* k0 = A.g.K0 + index * m;
-      const double c1 = A.g.F1[index] * A.v[index * S + s];
+      const double c1 = A.g.F1[index] * v_now;
       double d0 = 0.0;
 #pragma unroll
       for (int k = 0; k < MP; k++)
@@ -394,13 +398,13 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
           }
       }
     }
-#pragma unroll
-    for (int k = 0; k < MP; k++)
-      if (k < m) A.a_smooth[((long long)t * m + k) * S + s] = rr[k];
     if (t > 0) {
       const double* Tp = A.Tce.vals(t - 1);
       const bool both = ((long long)t * p) < A.init_steps;
       park<MP>(rr, xs);
+      // eta_{t-1} = Q_{t-1} R_{t-1}' r_t right away (src/FastSmootherC.cpp:345-352): no N x m array of r_t
+      const double* Qp = A.g.QtR + (A.qtr_tv ? (long long)(t - 1) * r * m : 0);
+      for (int kk = 0; kk < r; kk++) A.eta[((long long)(t - 1) * r + kk) * S + s] = sp_row_dot(A.Qp, kk, Qp, r, xs);
       ell_apply<MP>(A.Tce, Tp, xs, m, rr);  // T' r
       if (both) {  // T' r^(1): rare (the d diffuse steps), kept out of the registers
         for (int i = 0; i < m; i++) es[i] = ell_row_dot(A.Tce, Tp, i, r1);
@@ -425,13 +429,7 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
   }
   for (int t = 0; t < N; t++) {
     if (t > 0) {
-      const double* Qp = A.g.QtR + (A.qtr_tv ? (long long)(t - 1) * r * m : 0);
-      for (int k = 0; k < m; k++) xs[k] = A.a_smooth[((long long)t * m + k) * S + s];  // r_t
-      for (int kk = 0; kk < r; kk++) {
-        const double acc = sp_row_dot(A.Qp, kk, Qp, r, xs);
-        es[kk] = acc;
-        A.eta[((long long)(t - 1) * r + kk) * S + s] = acc;
-      }
+      for (int kk = 0; kk < r; kk++) es[kk] = A.eta[((long long)(t - 1) * r + kk) * S + s];
       double o2[MP];
       park<MP>(av, xs);
       ell_apply<MP>(A.Te, A.Te.vals(t - 1), xs, m, av);
