@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: batched Kalman loglikelihood + finite-difference gradient (BASELINE.json config 5).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload loglik|sim]
 
 Workload per GPU (weak scaling): 125,000 series (1M / 8) of length T = 1000 from the
 local level + slope + trigonometric seasonal (s = 12) model, m = r = 14 incl. the residual state, 13
@@ -9,13 +9,18 @@ exactly-diffuse states; per-series parameters theta_b in R^4; one step = the log
 at the 2k = 8 central-difference points (h = 1e-3) for every series = 9 filter runs per series =
 1.125e9 series*timesteps per GPU, plus (N > 1) the NCCL gather of per-series loglik + gradient.
 
-metric   series*timesteps / s, FP64, whole job, inputs resident in HBM (CUDA events on the launch stream)
-e2e      the same through the host-pointer C ABI (ssgpu_loglik_batch): pinned host y / parameters are
-         copied in and the (V, B) result copied out inside the timed region
-roofline dominant kernel loglik_cols_kernel against the FP64 FMA-pipe peak measured in this run by
-         ssgpu_fp64_peak (MEASURED_PEAKS.json carries no FP64 figure), algorithmic flops of SURVEY.md 8d
+metric   series*timesteps / s, FP64, whole job, inputs resident in HBM (CUDA events on the launch stream); the
+         step is the public call api.loglik_grad_batch_dev (ssgpu_loglik_grad_batch_dev): theta in, loglik +
+         gradient out, the 9 variance sets per series built on the device
+e2e      the same through the host-pointer C ABI (ssgpu_loglik_grad_batch): pinned host y / theta are copied in
+         and loglik + gradient copied out inside the timed region
+roofline dominant kernel loglik_mma_kernel against the FP64 peak measured in this run by ssgpu_fp64_peak
+         (MEASURED_PEAKS.json carries no FP64 figure): algorithmic flops of SURVEY.md 8d (frac) and the flops
+         the tile-sparse kernel issues (executed_frac)
 cpu_baseline  the reference's own LogLikC.cpp (oracle/_ref, compiled unmodified) on all host cores over a
          bounded sample of the same workload; --impl reference runs only that and prints its own line.
+
+--workload sim runs BASELINE.json config 4 instead (simulation smoother draws, see the section below).
 """
 from __future__ import annotations
 
