@@ -144,7 +144,8 @@ typedef struct ssgpu_model {
 } ssgpu_model;
 
 /* kernel selection for the batched path */
-#define SSGPU_KERNEL_AUTO 0     /* tensor kernel when the model qualifies, else column kernel, else generic */
+#define SSGPU_KERNEL_AUTO 0     /* tensor kernel when the model qualifies (column kernel first when p >= 4 and it
+                                   qualifies), else column kernel, else generic */
 #define SSGPU_KERNEL_GENERIC 1  /* one CTA per evaluation, any shape */
 #define SSGPU_KERNEL_COLS 2     /* column-per-lane DFMA kernel (m <= 15); SSGPU_E_ARG if not eligible */
 #define SSGPU_KERNEL_MMA 3      /* warp-per-evaluation FP64 tensor (DMMA) kernel (m <= 23); SSGPU_E_ARG if not eligible.

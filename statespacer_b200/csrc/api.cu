@@ -206,9 +206,13 @@ static int dispatch_batch(const DModel& md, const double* y_dev, long long B, in
   const bool mma_ok = mma_eligible(md, &why);
   if (kernel == SSGPU_KERNEL_MMA || kernel == SSGPU_KERNEL_MMA_DENSE)
     SS_ARG(mma_ok, "tensor kernel not eligible: " + why);
-  if (kernel == SSGPU_KERNEL_MMA || kernel == SSGPU_KERNEL_MMA_DENSE || (kernel == SSGPU_KERNEL_AUTO && mma_ok))
-    return launch_loglik_mma(md, y_dev, B, V, out_dev, kernel != SSGPU_KERNEL_MMA_DENSE, st);
   const bool cols_ok = cols_eligible(md, &why);
+  // many observations per time point: the measurement updates dominate and the column kernel's single-sweep update
+  // beats the tensor kernel's shuffle-based one (config 3, p = 8, m = 14: 5.0e8 vs 3.6e8 series*timesteps/s)
+  const bool prefer_cols = kernel == SSGPU_KERNEL_AUTO && cols_ok && md.p >= 4;
+  if (!prefer_cols &&
+      (kernel == SSGPU_KERNEL_MMA || kernel == SSGPU_KERNEL_MMA_DENSE || (kernel == SSGPU_KERNEL_AUTO && mma_ok)))
+    return launch_loglik_mma(md, y_dev, B, V, out_dev, kernel != SSGPU_KERNEL_MMA_DENSE, st);
   if (kernel == SSGPU_KERNEL_COLS) SS_ARG(cols_ok, "column kernel not eligible: " + why);
   if (kernel == SSGPU_KERNEL_COLS || (kernel == SSGPU_KERNEL_AUTO && cols_ok))
     return launch_loglik_cols(md, y_dev, B, V, out_dev, st);

@@ -10,6 +10,7 @@
 // F_inf < eps <= F_star branch (:464-468); N_2 uses the already updated N_1 (:483-487); eta_var uses
 // the Q slice left over from the forward loop (:548); the regime test is index < initialisation_steps.
 #include "common.cuh"
+#include "mm_dmma.cuh"
 
 namespace ssgpu {
 
@@ -45,21 +46,11 @@ __device__ void sandwich_L0(double* X, const double* k0, const double* z, double
   __syncthreads();
 }
 
-// X <- T' X T (in place) using tmp
+// X <- T' X T (in place) using tmp; DMMA tiles (mm_dmma.cuh), same bits as the scalar k-ascending fma loops
 __device__ void sandwich_T(double* X, const double* Ts, double* tmp, int m, int tid, int NT) {
-  for (int q = tid; q < m * m; q += NT) {  // tmp = X T
-    const int i = q % m, j = q / m;
-    double acc = 0.0;
-    for (int k = 0; k < m; k++) acc = fma(X[i + k * m], Ts[k + j * m], acc);
-    tmp[q] = acc;
-  }
+  mm_dmma<false, false>(tmp, X, Ts, nullptr, m, tid, NT);  // tmp = X T
   __syncthreads();
-  for (int q = tid; q < m * m; q += NT) {  // X = T' tmp
-    const int i = q % m, j = q / m;
-    double acc = 0.0;
-    for (int k = 0; k < m; k++) acc = fma(Ts[k + i * m], tmp[k + j * m], acc);
-    X[q] = acc;
-  }
+  mm_dmma<true, false>(X, Ts, tmp, nullptr, m, tid, NT);  // X = T' tmp
   __syncthreads();
 }
 

@@ -15,6 +15,7 @@
 //   P_inf L1' + P* L0' = P* - M* K0' - M_inf K1'   (:151),  P_inf L0' = P_inf - M_inf K0' (:152)
 // which equal the reference's GEMM forms exactly in real arithmetic and to O(eps) in FP64.
 #include "common.cuh"
+#include "mm_dmma.cuh"
 
 namespace ssgpu {
 
@@ -44,24 +45,15 @@ __device__ __forceinline__ void load_mat(double* dst, const double* blk, int dia
   }
 }
 
-// C (m x m) = A (m x m) * B (m x m), all column-major in shared memory
+// C (m x m) = A (m x m) * B (m x m), all column-major in shared memory: DMMA tiles (mm_dmma.cuh), same bits as
+// the scalar loop  acc = fma(A[i + k m], B[k + j m], acc), k ascending
 __device__ __forceinline__ void mm_nn(double* C, const double* A, const double* Bm, int m, int tid, int NT) {
-  for (int e = tid; e < m * m; e += NT) {
-    const int i = e % m, j = e / m;
-    double acc = 0.0;
-    for (int k = 0; k < m; k++) acc = fma(A[i + k * m], Bm[k + j * m], acc);
-    C[e] = acc;
-  }
+  mm_dmma<false, false>(C, A, Bm, nullptr, m, tid, NT);
 }
 // C = add + A * B'   (add may be nullptr)
 __device__ __forceinline__ void mm_nt(double* C, const double* A, const double* Bm, const double* add, int m, int tid,
                                       int NT) {
-  for (int e = tid; e < m * m; e += NT) {
-    const int i = e % m, j = e / m;
-    double acc = 0.0;
-    for (int k = 0; k < m; k++) acc = fma(A[i + k * m], Bm[j + k * m], acc);
-    C[e] = add ? acc + add[e] : acc;
-  }
+  mm_dmma<false, true>(C, A, Bm, add, m, tid, NT);
 }
 
 template <int MODE>
@@ -202,17 +194,10 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
         }
         continue;
       }
-      // M = P z
-      for (int i = tid; i < m; i += NT) {
-        double as = 0.0, ai = 0.0;
-        for (int k = 0; k < m; k++) {
-          const double z = Zs[j + k * p];
-          as = fma(Ps[i + k * m], z, as);
-          if (init) ai = fma(Pi[i + k * m], z, ai);
-        }
-        Ms[i] = as;
-        Mi[i] = ai;
-      }
+      // M = P z (M* and, while diffuse, M_inf): DMMA chains, one 8-row tile per warp (mm_dmma.cuh)
+      if (!init)
+        for (int i = tid; i < m; i += NT) Mi[i] = 0.0;
+      mv_dmma2(Ms, Ps, Mi, init ? Pi : nullptr, Zs + j, p, m, tid, NT);
       __syncthreads();
       double F_star = 0.0, F_inf = 0.0, za = 0.0;
       for (int k = 0; k < m; k++) {

@@ -304,10 +304,13 @@ def test_batch_multivariate_dns():
     y = np.stack([fed + (0.01 * rng.normal(size=fed.shape) if b else 0.0) for b in range(B)], axis=2)
     y[rng.uniform(size=y.shape) < 0.03] = np.nan
     y[:, :, 0] = fed
-    got = api.loglik_batch(y, sm, kernel="auto")
+    auto = api.loglik_batch(y, sm, kernel="auto")
+    assert api.last_kernel().startswith("loglik_cols")                     # p = 8: the column kernel is preferred
+    got = api.loglik_batch(y, sm, kernel="mma")
     assert api.last_kernel().startswith("loglik_mma")
     assert abs(got[0] - 7.005830) < 6e-7 * 7                               # docs/articles/selfspec.html:306-307
     cols = api.loglik_batch(y, sm, kernel="cols")
+    assert np.array_equal(auto, cols)
     for b in range(B):
         yb = y[:, :, b]
         want = cport.LogLikC(yb, np.isnan(yb), *sm.args())
