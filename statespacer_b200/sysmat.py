@@ -297,3 +297,44 @@ def dns_yield_curve(param):
         a=np.concatenate([param[17:20], param[17:20]]),
         P_inf=np.zeros((6, 6)), P_star=block_diag(Pst, np.zeros((3, 3))))
     return _combine(8, H, [comp]), Phi
+
+
+def bsm_multivariate_regressors(X_list, H, Q_level, Q_slope, Q_seas, s=12):
+    """Config 2 shape (Seatbelts-style): p dependent variables with local level + slope
+    (R/Components-Unobserved.R:138-184), trigonometric seasonal (:476-536) and explanatory variables with
+    time-varying Z (R/Components-Regressors.R:40-90).  X_list[i] is the N x k_i regressor matrix of series i.
+    State = [eps (p) | level (p) | slope (p) | seasonal ((s-1) p, frequency-major) | coefficients (sum k_i)];
+    H, Q_level, Q_slope, Q_seas are p x p covariances (the seasonal one repeated for its s-1 blocks,
+    R/Components-Unobserved.R:560-575)."""
+    p = len(X_list)
+    N = X_list[0].shape[0]
+    I = np.eye(p)
+    even = s % 2 == 0
+    ln = s // 2 - 1 if even else s // 2
+    lam = 2 * math.pi * np.arange(1, ln + 1) / s
+    T1 = block_diag(*[math.cos(x) * I for x in lam])
+    T2 = block_diag(*[math.sin(x) * I for x in lam])
+    Ts = np.block([[T1, T2], [-T2, T1]])
+    Zs = np.concatenate([np.tile(I, (1, ln)), np.zeros((p, ln * p))], axis=1)
+    if even:
+        Ts = block_diag(Ts, -I)
+        Zs = np.concatenate([Zs, I], axis=1)
+    ks = (s - 1) * p
+    kx = sum(x.shape[1] for x in X_list)
+    Tl = np.block([[I, I], [np.zeros((p, p)), I]])
+    Zl = np.concatenate([I, np.zeros((p, p))], axis=1)
+    T = block_diag(np.zeros((p, p)), Tl, Ts, np.eye(kx))
+    m = T.shape[0]
+    Z = np.zeros((p, m, N))
+    Z[:, :p, :] = I[:, :, None]
+    Z[:, p:3 * p, :] = Zl[:, :, None]
+    Z[:, 3 * p:3 * p + ks, :] = Zs[:, :, None]
+    off = 3 * p + ks
+    for i, X in enumerate(X_list):
+        Z[i, off:off + X.shape[1], :] = X.T
+        off += X.shape[1]
+    Q = block_diag(np.asarray(H, dtype=np.float64), Q_level, Q_slope, *([np.asarray(Q_seas)] * (s - 1)),
+                   np.zeros((kx, kx)))
+    P_inf = block_diag(np.zeros((p, p)), np.eye(m - p))
+    P_star = block_diag(np.asarray(H, dtype=np.float64), np.zeros((m - p, m - p)))
+    return SysMat(Z, T[:, :, None], np.eye(m)[:, :, None], Q[:, :, None], np.zeros(m), P_inf, P_star)

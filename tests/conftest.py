@@ -121,6 +121,30 @@ def simulate_y(rng, sm, N, missing=0.0):
     return y
 
 
+def config2_standin(seed=2, N=192, missing=0.05):
+    """Synthetic stand-in for BASELINE.json config 2 (the Seatbelts data are not available offline; SURVEY.md
+    8d): bivariate local level + slope + trigonometric seasonal(12) + three shared regressors, m = 34 incl. the two
+    residual states, 32 exactly-diffuse states, time-varying Z, 5 % missing observations."""
+    rng = np.random.default_rng(seed)
+    X = rng.normal(size=(N, 3))
+
+    def cov(scale):
+        A = rng.normal(size=(2, 2))
+        return scale * (A @ A.T / 2 + 0.5 * np.eye(2))
+
+    sm = sysmat.bsm_multivariate_regressors([X, X], cov(1.0), cov(0.1), cov(0.01), cov(0.05))
+    a = np.zeros(sm.m)
+    a[2:4] = rng.normal(size=2) * 3
+    a[-6:] = rng.normal(size=6)
+    y = np.zeros((N, 2))
+    Lq = np.linalg.cholesky(sm.Q[:, :, 0] + 1e-12 * np.eye(sm.m))
+    for t in range(N):
+        y[t] = sm.Z[:, :, t] @ a
+        a = sm.T[:, :, 0] @ a + Lq @ rng.normal(size=sm.m)
+    y[rng.uniform(size=y.shape) < missing] = np.nan
+    return Case("config2", y, sm)
+
+
 @pytest.fixture(scope="session")
 def kats():
     return kat_cases()

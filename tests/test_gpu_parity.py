@@ -7,7 +7,7 @@ import math
 import numpy as np
 import pytest
 
-from conftest import Case, DNS_PARAM, load_fed, load_series, random_model, simulate_y
+from conftest import Case, DNS_PARAM, config2_standin, load_fed, load_series, random_model, simulate_y
 from oracle import cport, kalman_np, ref
 from statespacer_b200 import api, native, sysmat
 
@@ -151,6 +151,28 @@ def test_kalman_missing_airline():
     assert got["initialisation_steps"] == 19
     assert abs(np.nansum(got["loglik"]) - api.LogLikC(*c.args()) * len(air)) < 1e-9 * 300
     _kalman_check(c)
+
+
+def test_config2_shape_seatbelts_standin():
+    """BASELINE.json config 2 (synthetic stand-in): bivariate BSM + regressors, p = 2, N = 192,
+    m = 34, 32 exactly-diffuse states, time-varying Z, 5 % missing -- LogLikC, the whole KalmanC output and a small
+    batch (generic kernel: m > 23, time-varying Z) against the oracle / the compiled reference."""
+    c = config2_standin()
+    want = cport.LogLikC(*c.args())
+    got = api.LogLikC(*c.args())
+    assert abs(got - want) <= 1e-8 * max(1, abs(want)), (got, want)
+    _kalman_check(c, tol=1e-7)
+    k = api.KalmanC(*c.args(), False)
+    assert abs(np.nansum(k["loglik"]) - got * len(c.y)) <= 1e-8 * abs(got * len(c.y))
+    # a batch: the same series scaled (scale c: loglik shifts by -(n_obs - d_obs) log(c) / N, see the properties test)
+    ys = np.stack([c.y, 2.0 * c.y, c.y], axis=2)
+    Qb = np.stack([c.sm.Q[:, :, 0], 4.0 * c.sm.Q[:, :, 0], c.sm.Q[:, :, 0]])
+    Pb = np.stack([c.sm.P_star, 4.0 * c.sm.P_star, c.sm.P_star])
+    out = api.loglik_batch(ys, c.sm, Q=Qb, P_star=Pb)
+    assert api.last_kernel().startswith("fwd_generic")
+    assert out[0] == out[2] and abs(out[0] - want) <= 1e-8 * max(1, abs(want))
+    n_obs = int(np.sum(~np.isnan(c.y)))
+    assert abs(out[1] - (out[0] - (n_obs - 32) * math.log(2.0) / len(c.y))) <= 1e-8 * abs(out[0])
 
 
 # ---- batched loglikelihood ---------------------------------------------------------------------------

@@ -5,7 +5,7 @@ state."""
 import numpy as np
 import pytest
 
-from conftest import Case, random_model, simulate_y
+from conftest import Case, config2_standin, random_model, simulate_y
 from oracle import cport, kalman_np, ref
 
 needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libssref.so not built")
@@ -114,3 +114,20 @@ def test_extract_checkers():
         b = ref.ExtractComponentC(a, Z)
         _close(kalman_np.ExtractComponentC(a, Z), b, 1e-12)
         _close(cport.ExtractComponentC(a, Z), b, 1e-12)
+
+
+@needs_ref
+def test_config2_shape_all_checkers():
+    """BASELINE.json config 2 in its synthetic stand-in (p = 2, N = 192, m = 34, 32 diffuse states, time-varying Z,
+    missing observations): the three CPU checkers agree on the loglikelihood, the diffuse period and the smoothed
+    state."""
+    c = config2_standin()
+    assert c.sm.m == 34 and c.sm.Z.shape == (2, 34, 192)
+    r = ref.LogLikC(*c.args())
+    assert np.isfinite(r)
+    assert abs(cport.LogLikC(*c.args()) - r) <= 1e-9 * max(1, abs(r))
+    assert abs(kalman_np.LogLikC(*c.args()) - r) <= 1e-9 * max(1, abs(r))
+    a, b = kalman_np.KalmanC(*c.args(), False), ref.KalmanC(*c.args(), False)
+    assert a["initialisation_steps"] == b["initialisation_steps"] >= 32
+    for k in ("loglik", "a_smooth", "V", "eta", "a_fc"):
+        _close(a[k], b[k], 1e-7)
