@@ -145,13 +145,15 @@ typedef struct ssgpu_model {
 
 /* kernel selection for the batched path */
 #define SSGPU_KERNEL_AUTO 0     /* tensor kernel when the model qualifies (column kernel first when p >= 4 and it
-                                   qualifies), else column kernel, else generic */
+                                   qualifies), else column kernel, else the warp/shared-memory kernel, else generic */
 #define SSGPU_KERNEL_GENERIC 1  /* one CTA per evaluation, any shape */
 #define SSGPU_KERNEL_COLS 2     /* column-per-lane DFMA kernel (m <= 15); SSGPU_E_ARG if not eligible */
 #define SSGPU_KERNEL_MMA 3      /* warp-per-evaluation FP64 tensor (DMMA) kernel (m <= 23); SSGPU_E_ARG if not eligible.
                                    States are re-ordered internally so that the all-zero 8 x 8 tiles of a block-
                                    diagonal T are skipped (results equal up to summation order) */
 #define SSGPU_KERNEL_MMA_DENSE 4 /* same kernel, caller's state order, every tile multiplied */
+#define SSGPU_KERNEL_WSM 5      /* warp per evaluation, covariance in shared memory, FP64 tensor time update (m <= 63,
+                                   shared Z / T / R, Z may be time-varying); SSGPU_E_ARG if not eligible */
 
 /* host pointers everywhere (y, the matrices' data, out); copies in, runs, copies out, synchronises */
 int ssgpu_loglik_batch(const double* y, long long B, int V, const ssgpu_model* model, int kernel,

@@ -41,3 +41,11 @@ yd = np.repeat(fed[:, :, None], B, axis=2) + 0.01 * rng.normal(size=fed.shape + 
 run("config3 DNS p=8 m=14 (mma)", smd, yd)
 run("config3 DNS (cols)", smd, yd, kernel="cols")
 run("config3 DNS (generic)", smd, yd[:, :, :4096], kernel="generic")
+run("config2 shape (wsm forced)", sm, y, kernel="wsm")
+run("config2 shape (generic)", sm, y, kernel="generic")
+from conftest import config2_standin
+c2 = config2_standin()
+B = 32768
+y2 = np.repeat(c2.y[:, :, None], B, axis=2) * (1 + 0.01 * rng.normal(size=(1, 1, B)))
+run("config2 stand-in BSM+regressors", c2.sm, y2)
+run("config2 stand-in (generic)", c2.sm, y2[:, :, :2048], kernel="generic")

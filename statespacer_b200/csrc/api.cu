@@ -216,6 +216,10 @@ static int dispatch_batch(const DModel& md, const double* y_dev, long long B, in
   if (kernel == SSGPU_KERNEL_COLS) SS_ARG(cols_ok, "column kernel not eligible: " + why);
   if (kernel == SSGPU_KERNEL_COLS || (kernel == SSGPU_KERNEL_AUTO && cols_ok))
     return launch_loglik_cols(md, y_dev, B, V, out_dev, st);
+  const bool wsm_ok = wsm_eligible(md, &why);
+  if (kernel == SSGPU_KERNEL_WSM) SS_ARG(wsm_ok, "warp/shared-memory kernel not eligible: " + why);
+  if (kernel == SSGPU_KERNEL_WSM || (kernel == SSGPU_KERNEL_AUTO && wsm_ok))
+    return launch_loglik_wsm(md, y_dev, B, V, out_dev, st);
   SS_ARG(kernel == SSGPU_KERNEL_AUTO || kernel == SSGPU_KERNEL_GENERIC, "unknown kernel selector");
   return launch_fwd_generic(md, y_dev, B, V, out_dev, nullptr, nullptr, st);
 }

@@ -214,6 +214,10 @@ bool mma_eligible(const DModel& md, std::string* why);
 int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, double* out, bool tile_sparse,
                       cudaStream_t st);
 
+// Warp-per-evaluation kernel with the covariance in shared memory, m <= 63 (loglik_wsm.cu)
+bool wsm_eligible(const DModel& md, std::string* why);
+int launch_loglik_wsm(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st);
+
 // theta -> variances on the device, finite-difference gradient (theta.cu)
 int launch_expand_theta(const double* theta, long long B, int V, int k, int r, int m, const int* q_index,
                         const int* p_index, const double* q_fixed, const double* p_fixed, double h, int fd, double* Qd,

@@ -14,6 +14,8 @@
 //   P* L0' = P* - (P* z) K0'            (src/LogLikC.cpp:129,193)
 //   P_inf L1' + P* L0' = P* - M* K0' - M_inf K1'   (:151),  P_inf L0' = P_inf - M_inf K0' (:152)
 // which equal the reference's GEMM forms exactly in real arithmetic and to O(eps) in FP64.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mm_dmma.cuh"
 
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
   double* Mi = Ms + m;
   double* k0v = Mi + m;
   double* k1v = k0v + m;
+  double* scal = k1v + m;  // F_star, F_inf, z'a of the current observation
 
   if (!GAINS) load_mat(av, md.a.block(b, v, 0), 0, m, 1, tid, NT);
   load_mat(Pi, md.P_inf.block(b, v, 0), md.P_inf.diag, m, m, tid, NT);
@@ -199,13 +202,24 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
         for (int i = tid; i < m; i += NT) Mi[i] = 0.0;
       mv_dmma2(Ms, Ps, Mi, init ? Pi : nullptr, Zs + j, p, m, tid, NT);
       __syncthreads();
-      double F_star = 0.0, F_inf = 0.0, za = 0.0;
-      for (int k = 0; k < m; k++) {
-        const double z = Zs[j + k * p];
-        F_star = fma(z, Ms[k], F_star);
-        F_inf = fma(z, Mi[k], F_inf);
-        if (!GAINS) za = fma(z, av[k], za);
+      // F = z'M and z'a: one warp runs the three chains (k ascending) and publishes them -- every warp doing so
+      // for itself is 4 m broadcast loads per warp and makes the shared-memory pipe the bottleneck of the kernel
+      if (tid < 32) {
+        double fs = 0.0, fi = 0.0, zz = 0.0;
+        for (int k = 0; k < m; k++) {
+          const double z = Zs[j + k * p];
+          fs = fma(z, Ms[k], fs);
+          fi = fma(z, Mi[k], fi);
+          if (!GAINS) zz = fma(z, av[k], zz);
+        }
+        if (tid == 0) {
+          scal[0] = fs;
+          scal[1] = fi;
+          scal[2] = zz;
+        }
       }
+      __syncthreads();
+      const double F_star = scal[0], F_inf = scal[1], za = scal[2];
       int code = 0;
       double F1 = 0.0, F2 = 0.0, vv = 0.0, ll = nan("");
       if (init) {
@@ -335,13 +349,23 @@ static size_t fwd_smem_bytes(const DModel& md) {
   size_t wsz = (size_t)m * m;
   if ((size_t)m * r > wsz) wsz = (size_t)m * r;
   if ((size_t)p * m > wsz) wsz = (size_t)p * m;
-  return sizeof(double) * (4 * (size_t)m * m + wsz + (size_t)p * m + 6 * (size_t)m);
+  return sizeof(double) * (4 * (size_t)m * m + wsz + (size_t)p * m + 6 * (size_t)m + 8);
 }
 
-static int pick_threads(int m) {
-  int nt = ((m * m + 31) / 32) * 32;
-  if (nt < 32) nt = 32;
-  if (nt > 512) nt = 512;
+// Threads per CTA.  One series: as many as there are matrix elements (latency).  A batch: a quarter of that, capped
+// at 256 -- barriers and the per-warp bookkeeping grow with the warp count while the SM is filled by other CTAs
+// anyway (measured at m = 34: 64 / 128 / 256 / 512 threads -> 2.3 / 3.1 / 3.4 / 2.5 e7 series*timesteps/s; at
+// m = 14: 5.7 / 5.1 / 3.2 / 3.2 e7).
+static int pick_threads(int m, bool batched = false) {
+  static const int forced = [] {
+    const char* e = getenv("SSGPU_GENERIC_NT");
+    return e ? atoi(e) : 0;
+  }();
+  int nt = batched ? ((m * m / 4 + 31) / 32) * 32 : ((m * m + 31) / 32) * 32;
+  const int lo = batched ? 64 : 32, hi = batched ? 256 : 512;
+  if (nt < lo) nt = lo;
+  if (nt > hi) nt = hi;
+  if (forced > 0) nt = forced;
   return nt;
 }
 
@@ -357,7 +381,7 @@ int launch_fwd_generic(const DModel& md, const double* y, long long B, int V, do
   SS_ARG(smem <= 227 * 1024, "generic filter: model does not fit in shared memory (m, p or r too large)");
   const long long E = B * V;
   SS_ARG(E > 0 && E < (1LL << 31), "generic filter: batch size out of range");
-  const int nt = pick_threads(md.m);
+  const int nt = pick_threads(md.m, E > 1);
   if (kout) {
     SS_ARG(B == 1 && V == 1 && scratch, "KalmanC runs one series per call");
     A.k = *kout;

@@ -28,6 +28,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "tile_plan.cuh"
 
 namespace ssgpu {
 
@@ -578,89 +579,6 @@ bool mma_eligible(const DModel& md, std::string* why) {
   return true;
 }
 
-// ---- state ordering that makes T tile-sparse ------------------------------------------------------
-// States i, k are coupled when T[i][k] or T[k][i] is non-zero.  Coupled components are packed whole into the
-// 8-state tiles (exact search: at most 23 components, 3 tiles); inside a tile the caller's order is kept.
-// statespacer models are block diagonal in T by construction (residuals: zero rows/columns, level, slope,
-// trigonometric seasonal / cycle pairs, regressor coefficients: blocks of size 1-2), so they pack; a SARIMA
-// companion block larger than a tile does not and runs dense in the caller's order.
-struct TilePlan {
-  signed char perm[24];
-  unsigned mask;  // bit rt*TT + ct of the ordered T
-};
-
-static bool pack_components(const std::vector<std::vector<int>>& comps, size_t idx, int* cap, int n_bins,
-                            std::vector<int>& bin_of) {
-  if (idx == comps.size()) return true;
-  const int sz = (int)comps[idx].size();
-  for (int b = 0; b < n_bins; b++) {
-    if (cap[b] < sz) continue;
-    bool dup = false;  // bins with equal remaining capacity are interchangeable
-    for (int b2 = 0; b2 < b; b2++) dup = dup || (cap[b2] == cap[b]);
-    if (dup) continue;
-    cap[b] -= sz;
-    bin_of[idx] = b;
-    if (pack_components(comps, idx + 1, cap, n_bins, bin_of)) return true;
-    cap[b] += sz;
-  }
-  return false;
-}
-
-static unsigned tile_mask_of(const std::vector<double>& Th, int diag, int m, int tt, const signed char* perm) {
-  unsigned mask = 0;
-  for (int i = 0; i < m; i++)
-    for (int k = 0; k < m; k++)
-      if (mat_get(Th.data(), diag, m, perm[i], perm[k]) != 0.0) mask |= 1u << ((i >> 3) * tt + (k >> 3));
-  return mask;
-}
-
-static TilePlan plan_tiles(const std::vector<double>& Th, int diag, int m, int tt, bool allow_reorder) {
-  TilePlan pl{};
-  for (int i = 0; i < 24; i++) pl.perm[i] = (signed char)(i < m ? i : 0);
-  const unsigned dense = (1u << (tt * tt)) - 1u;
-  pl.mask = dense;
-  if (!allow_reorder || tt == 1) return pl;
-  // components of the coupling graph (union-find)
-  std::vector<int> root(m);
-  for (int i = 0; i < m; i++) root[i] = i;
-  auto find = [&](int x) {
-    while (root[x] != x) x = root[x] = root[root[x]];
-    return x;
-  };
-  for (int i = 0; i < m; i++)
-    for (int k = 0; k < m; k++)
-      if (i != k && mat_get(Th.data(), diag, m, i, k) != 0.0) root[find(i)] = find(k);
-  std::vector<std::vector<int>> comps;
-  {
-    std::vector<int> id(m, -1);
-    for (int i = 0; i < m; i++) {
-      const int rr = find(i);
-      if (id[rr] < 0) {
-        id[rr] = (int)comps.size();
-        comps.emplace_back();
-      }
-      comps[id[rr]].push_back(i);
-    }
-  }
-  std::stable_sort(comps.begin(), comps.end(),
-                   [](const std::vector<int>& x, const std::vector<int>& y) { return x.size() > y.size(); });
-  int cap[3] = {0, 0, 0};
-  const int n_bins = (m + 7) / 8;
-  for (int b = 0; b < n_bins; b++) cap[b] = std::min(8, m - 8 * b);
-  std::vector<int> bin_of(comps.size(), 0);
-  if (!pack_components(comps, 0, cap, n_bins, bin_of)) return pl;  // a component larger than a tile: dense
-  int pos = 0;
-  for (int b = 0; b < n_bins; b++) {
-    std::vector<int> members;
-    for (size_t c = 0; c < comps.size(); c++)
-      if (bin_of[c] == b) members.insert(members.end(), comps[c].begin(), comps[c].end());
-    std::sort(members.begin(), members.end());
-    for (int s : members) pl.perm[pos++] = (signed char)s;
-  }
-  pl.mask = tile_mask_of(Th, diag, m, tt, pl.perm);
-  return pl;
-}
-
 template <int TT, unsigned TM, int MINB>
 static void launch_mma_tt(const MmaArgs& A, unsigned blocks, cudaStream_t st) {
   if (A.md.p == 1)
@@ -701,9 +619,10 @@ int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, dou
   TilePlan pl = plan_tiles(Th, md.T.diag, md.m, tt, tile_sparse);
   const unsigned dense = (1u << (tt * tt)) - 1u;
   constexpr unsigned kDiag2 = 0x9u, kDiag3 = 0x111u;
+  const unsigned plmask = (unsigned)pl.mask;
   unsigned use = dense;
-  if (tt == 2 && (pl.mask & ~kDiag2) == 0) use = kDiag2;
-  if (tt == 3 && (pl.mask & ~kDiag3) == 0) use = kDiag3;
+  if (tt == 2 && (plmask & ~kDiag2) == 0) use = kDiag2;
+  if (tt == 3 && (plmask & ~kDiag3) == 0) use = kDiag3;
   if (use == dense)  // nothing to gain: keep the caller's order
     for (int i = 0; i < 24; i++) pl.perm[i] = (signed char)(i < md.m ? i : 0);
   for (int i = 0; i < 24; i++) A.perm[i] = pl.perm[i];
@@ -750,7 +669,7 @@ extern "C" int ssgpu_plan_state_order(const double* T, int m, int* perm, unsigne
   const TilePlan pl = plan_tiles(Th, 0, m, tt, true);
   if (perm)
     for (int i = 0; i < m; i++) perm[i] = pl.perm[i];
-  if (tile_mask) *tile_mask = pl.mask;
-  if (dmma_per_step) *dmma_per_step = mma_dmma_per_step(tt, pl.mask);
+  if (tile_mask) *tile_mask = (unsigned)pl.mask;
+  if (dmma_per_step) *dmma_per_step = mma_dmma_per_step(tt, (unsigned)pl.mask);
   return SSGPU_OK;
 }

@@ -169,7 +169,9 @@ def test_config2_shape_seatbelts_standin():
     Qb = np.stack([c.sm.Q[:, :, 0], 4.0 * c.sm.Q[:, :, 0], c.sm.Q[:, :, 0]])
     Pb = np.stack([c.sm.P_star, 4.0 * c.sm.P_star, c.sm.P_star])
     out = api.loglik_batch(ys, c.sm, Q=Qb, P_star=Pb)
-    assert api.last_kernel().startswith("fwd_generic")
+    assert api.last_kernel().startswith("loglik_wsm_kernel<TT=5")       # m = 34: warp + shared-memory kernel
+    gen = api.loglik_batch(ys, c.sm, Q=Qb, P_star=Pb, kernel="generic")
+    assert np.max(np.abs(out - gen)) <= 1e-8 * abs(want)
     assert out[0] == out[2] and abs(out[0] - want) <= 1e-8 * max(1, abs(want))
     n_obs = int(np.sum(~np.isnan(c.y)))
     assert abs(out[1] - (out[0] - (n_obs - 32) * math.log(2.0) / len(c.y))) <= 1e-8 * abs(out[0])
@@ -315,6 +317,39 @@ def test_batch_tile_sparse_state_order(m, p):
         tol = 1e-8 * max(1, abs(want))
         assert abs(got[b] - want) <= tol, (m, b, got[b], want)
         assert abs(dense[b] - want) <= tol, (m, b, dense[b], want)
+
+
+@pytest.mark.parametrize("m,p,tvz,block", [(9, 1, True, False), (24, 1, False, False), (31, 2, True, True),
+                                             (34, 2, True, True), (40, 1, False, True), (47, 3, True, False),
+                                             (56, 1, False, True), (63, 2, True, True)])
+def test_batch_wsm_kernel(m, p, tvz, block):
+    """Warp-per-evaluation kernel with the covariance in shared memory (24 <= m <= 63, or time-varying Z at any m):
+    dense and block-diagonal T (re-ordered to tile-sparse), per-series Q / P_star / a, diffuse states, missing
+    values, against the oracle and the generic kernel."""
+    rng = np.random.default_rng(900 + m)
+    B, N = 6, 24
+    d = 3
+    sm = _block_diagonal_model(rng, m, p, d=d, N=N) if block else random_model(rng, m, p, d=d, N=N)
+    if tvz:
+        Zt = np.stack([sm.Z[:, :, 0] + 0.05 * rng.normal(size=(p, m)) for _ in range(N)], axis=2)
+        sm = sysmat.SysMat(Z=Zt, T=sm.T, R=sm.R, Q=sm.Q, a=sm.a, P_inf=sm.P_inf, P_star=sm.P_star)
+    y = np.stack([simulate_y(rng, sm, N, missing=0.1) for _ in range(B)], axis=2)
+    Qb = np.stack([sm.Q[:, :, 0] * (1 + 0.1 * b) for b in range(B)])
+    Pb = np.stack([sm.P_star * (1 + 0.05 * b) for b in range(B)])
+    ab = np.stack([sm.a + 0.01 * b for b in range(B)])
+    got = api.loglik_batch(y, sm, Q=Qb, P_star=Pb, a=ab, kernel="wsm")
+    assert api.last_kernel().startswith(f"loglik_wsm_kernel<TT={(m + 8) // 8},"), api.last_kernel()
+    gen = api.loglik_batch(y, sm, Q=Qb, P_star=Pb, a=ab, kernel="generic")
+    if m > 23 or tvz:
+        auto = api.loglik_batch(y, sm, Q=Qb, P_star=Pb, a=ab)
+        assert api.last_kernel().startswith("loglik_wsm") and np.array_equal(auto, got)
+    for b in range(B):
+        smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=Qb[b][:, :, None], a=ab[b], P_inf=sm.P_inf, P_star=Pb[b])
+        yb = y[:, :, b]
+        want = cport.LogLikC(yb, np.isnan(yb), *smb.args())
+        tol = 1e-8 * max(1, abs(want))
+        assert abs(got[b] - want) <= tol, (m, b, got[b], want)
+        assert abs(gen[b] - want) <= tol, (m, b, gen[b], want)
 
 
 def test_batch_multivariate_dns():
