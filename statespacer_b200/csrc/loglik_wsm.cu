@@ -36,7 +36,10 @@ struct WsmArgs {
   signed char perm[64];
 };
 
-template <int TT>
+// DIAG: T is tile diagonal in the internal state order -- the common case after re-ordering, compiled without any
+// mask test (ptxas turns the warp-uniform test of the general path into PREDICATED DMMAs in the fully unrolled second
+// product, and a predicated-off DMMA still occupies the FP64 datapath).
+template <int TT, bool DIAG>
 __global__ void __launch_bounds__(256) loglik_wsm_kernel(const WsmArgs A) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int NF = TT * TT * 2;  // fragment slots per matrix
@@ -248,15 +251,24 @@ __global__ void __launch_bounds__(256) loglik_wsm_kernel(const WsmArgs A) {
 #pragma unroll
         for (int nt = 0; nt < TT; nt++) yv_[nt][0] = yv_[nt][1] = 0.0;
         // Y(rt, nt) = sum_ct T(rt, ct) X(nt, ct)'
+        if constexpr (DIAG) {
 #pragma unroll
-        for (int e = 0; e < 2; e++)
+          for (int e = 0; e < 2; e++) {
+            const double a = Tf[fi(rt, rt, e)];
 #pragma unroll
-          for (int ct = 0; ct < TT; ct++)
-            if (t_on(rt, ct)) {
-              const double a = Tf[fi(rt, ct, e)];
+            for (int nt = 0; nt < TT; nt++) dmma_884(yv_[nt][0], yv_[nt][1], a, X[fi(nt, rt, e)]);
+          }
+        } else {
 #pragma unroll
-              for (int nt = 0; nt < TT; nt++) dmma_884(yv_[nt][0], yv_[nt][1], a, X[fi(nt, ct, e)]);
-            }
+          for (int e = 0; e < 2; e++)
+#pragma unroll
+            for (int ct = 0; ct < TT; ct++)
+              if (t_on(rt, ct)) {
+                const double a = Tf[fi(rt, ct, e)];
+#pragma unroll
+                for (int nt = 0; nt < TT; nt++) dmma_884(yv_[nt][0], yv_[nt][1], a, X[fi(nt, ct, e)]);
+              }
+        }
         if (keep_a && rt == LA) {
 #pragma unroll
           for (int nt = 0; nt < TT; nt++)
@@ -265,13 +277,20 @@ __global__ void __launch_bounds__(256) loglik_wsm_kernel(const WsmArgs A) {
               if (lane_a) yv_[nt][e] = X[fi(LA, nt, e)];  // row MA of Y <- a'
         }
         // X'(rt, nt) = init + sum_ct Y(rt, ct) T(nt, ct)'
+        if constexpr (DIAG) {
 #pragma unroll
-        for (int e = 0; e < 2; e++)
+          for (int e = 0; e < 2; e++)
 #pragma unroll
-          for (int ct = 0; ct < TT; ct++)
+            for (int nt = 0; nt < TT; nt++) dmma_884(xv[nt][0], xv[nt][1], yv_[nt][e], Tf[fi(nt, nt, e)]);
+        } else {
 #pragma unroll
-            for (int nt = 0; nt < TT; nt++)
-              if (t_on(nt, ct)) dmma_884(xv[nt][0], xv[nt][1], yv_[ct][e], Tf[fi(nt, ct, e)]);
+          for (int e = 0; e < 2; e++)
+#pragma unroll
+            for (int ct = 0; ct < TT; ct++)
+#pragma unroll
+              for (int nt = 0; nt < TT; nt++)
+                if (t_on(nt, ct)) dmma_884(xv[nt][0], xv[nt][1], yv_[ct][e], Tf[fi(nt, ct, e)]);
+        }
 #pragma unroll
         for (int nt = 0; nt < TT; nt++)
 #pragma unroll
@@ -374,6 +393,9 @@ bool wsm_eligible(const DModel& md, std::string* why) {
 
 template <int TT>
 static int launch_wsm_tt(WsmArgs& A, cudaStream_t st, DevBuf& scratch) {
+  unsigned long long diag = 0;
+  for (int t = 0; t < TT; t++) diag |= 1ull << (t * TT + t);
+  const bool is_diag = (A.mask & ~diag) == 0;
   constexpr size_t frag = (size_t)TT * TT * 2 * 32 * sizeof(double);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -392,8 +414,13 @@ static int launch_wsm_tt(WsmArgs& A, cudaStream_t st, DevBuf& scratch) {
   A.wpb = wpb;
   SS_TRY(scratch.alloc((size_t)blocks * wpb * 2 * frag, st));
   A.scratch = scratch.as<double>();
-  SS_CUDA(cudaFuncSetAttribute(loglik_wsm_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  loglik_wsm_kernel<TT><<<(unsigned)blocks, wpb * 32, smem, st>>>(A);
+  if (is_diag) {
+    SS_CUDA(cudaFuncSetAttribute(loglik_wsm_kernel<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    loglik_wsm_kernel<TT, true><<<(unsigned)blocks, wpb * 32, smem, st>>>(A);
+  } else {
+    SS_CUDA(cudaFuncSetAttribute(loglik_wsm_kernel<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    loglik_wsm_kernel<TT, false><<<(unsigned)blocks, wpb * 32, smem, st>>>(A);
+  }
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;
 }
