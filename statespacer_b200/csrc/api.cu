@@ -200,7 +200,7 @@ static size_t extent(const ssgpu_matrix& M, long long B, int V) {
 }
 
 static int dispatch_batch(const DModel& md, const double* y_dev, long long B, int V, int kernel, double* out_dev,
-                          cudaStream_t st) {
+                          cudaStream_t st, const double* T_host = nullptr) {
   SS_ARG(B >= 1 && V >= 1, "B and V must be positive");
   std::string why;
   const bool mma_ok = mma_eligible(md, &why);
@@ -212,14 +212,14 @@ static int dispatch_batch(const DModel& md, const double* y_dev, long long B, in
   const bool prefer_cols = kernel == SSGPU_KERNEL_AUTO && cols_ok && md.p >= 4;
   if (!prefer_cols &&
       (kernel == SSGPU_KERNEL_MMA || kernel == SSGPU_KERNEL_MMA_DENSE || (kernel == SSGPU_KERNEL_AUTO && mma_ok)))
-    return launch_loglik_mma(md, y_dev, B, V, out_dev, kernel != SSGPU_KERNEL_MMA_DENSE, st);
+    return launch_loglik_mma(md, y_dev, B, V, out_dev, kernel != SSGPU_KERNEL_MMA_DENSE, st, T_host);
   if (kernel == SSGPU_KERNEL_COLS) SS_ARG(cols_ok, "column kernel not eligible: " + why);
   if (kernel == SSGPU_KERNEL_COLS || (kernel == SSGPU_KERNEL_AUTO && cols_ok))
     return launch_loglik_cols(md, y_dev, B, V, out_dev, st);
   const bool wsm_ok = wsm_eligible(md, &why);
   if (kernel == SSGPU_KERNEL_WSM) SS_ARG(wsm_ok, "warp/shared-memory kernel not eligible: " + why);
   if (kernel == SSGPU_KERNEL_WSM || (kernel == SSGPU_KERNEL_AUTO && wsm_ok))
-    return launch_loglik_wsm(md, y_dev, B, V, out_dev, st);
+    return launch_loglik_wsm(md, y_dev, B, V, out_dev, st, T_host);
   SS_ARG(kernel == SSGPU_KERNEL_AUTO || kernel == SSGPU_KERNEL_GENERIC, "unknown kernel selector");
   return launch_fwd_generic(md, y_dev, B, V, out_dev, nullptr, nullptr, st);
 }
@@ -274,7 +274,10 @@ int ssgpu_LogLikC(const double* y, const int* y_isna, int N, int p, int m, int r
   SS_TRY(stage_single(S, y, y_isna, N, p, m, r, a, P_inf, P_star, Z, nZ, T, nT, R, nR, Q, nQ, st));
   DevBuf out;
   SS_TRY(out.alloc(sizeof(double), st));
-  SS_TRY(launch_fwd_generic(S.md, S.dev.as<double>() + S.oy, 1, 1, out.as<double>(), nullptr, nullptr, st));
+  // one series is a batch of one: the warp-level kernels serve it when the model qualifies (a few hundred cycles
+  // per observation instead of the CTA kernel's barriers), the generic kernel otherwise
+  SS_TRY(dispatch_batch(S.md, S.dev.as<double>() + S.oy, 1, 1, SSGPU_KERNEL_AUTO, out.as<double>(), st,
+                        nT == 1 ? T : nullptr));
   SS_CUDA(cudaMemcpyAsync(loglik, out.get(), sizeof(double), cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));
   return SSGPU_OK;

@@ -211,12 +211,14 @@ int launch_permute_at(const double* src, double* dst, int N, int m, long long S,
 
 // Warp-per-evaluation FP64 tensor kernel (loglik_mma.cu)
 bool mma_eligible(const DModel& md, std::string* why);
+// T_host: optional host copy of the shared T (saves the device-to-host fetch the state-order planner needs)
 int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, double* out, bool tile_sparse,
-                      cudaStream_t st);
+                      cudaStream_t st, const double* T_host = nullptr);
 
 // Warp-per-evaluation kernel with the covariance in shared memory, m <= 63 (loglik_wsm.cu)
 bool wsm_eligible(const DModel& md, std::string* why);
-int launch_loglik_wsm(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st);
+int launch_loglik_wsm(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
+                      const double* T_host = nullptr);
 
 // theta -> variances on the device, finite-difference gradient (theta.cu)
 int launch_expand_theta(const double* theta, long long B, int V, int k, int r, int m, const int* q_index,

@@ -597,7 +597,7 @@ int mma_dmma_per_step(int tt, unsigned mask) {
 }
 
 int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, double* out, bool tile_sparse,
-                      cudaStream_t st) {
+                      cudaStream_t st, const double* T_host) {
   std::string why;
   SS_ARG(mma_eligible(md, &why), "tensor kernel not eligible: " + why);
   MmaArgs A{};
@@ -613,8 +613,12 @@ int launch_loglik_mma(const DModel& md, const double* y, long long B, int V, dou
   // T is shared and small: fetch it to plan the state order (a few microseconds next to a batched launch)
   std::vector<double> Th((size_t)(md.T.diag ? md.m : md.m * md.m));
   if (tile_sparse && tt > 1) {
-    SS_CUDA(cudaMemcpyAsync(Th.data(), md.T.p, Th.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-    SS_CUDA(cudaStreamSynchronize(st));
+    if (T_host) {
+      std::copy(T_host, T_host + Th.size(), Th.begin());
+    } else {
+      SS_CUDA(cudaMemcpyAsync(Th.data(), md.T.p, Th.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+      SS_CUDA(cudaStreamSynchronize(st));
+    }
   }
   TilePlan pl = plan_tiles(Th, md.T.diag, md.m, tt, tile_sparse);
   const unsigned dense = (1u << (tt * tt)) - 1u;

@@ -425,7 +425,8 @@ static int launch_wsm_tt(WsmArgs& A, cudaStream_t st, DevBuf& scratch) {
   return SSGPU_OK;
 }
 
-int launch_loglik_wsm(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st) {
+int launch_loglik_wsm(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
+                      const double* T_host) {
   std::string why;
   SS_ARG(wsm_eligible(md, &why), "warp/shared-memory kernel not eligible: " + why);
   WsmArgs A{};
@@ -436,8 +437,12 @@ int launch_loglik_wsm(const DModel& md, const double* y, long long B, int V, dou
   A.out = out;
   const int tt = (md.m + 1 + 7) / 8;
   std::vector<double> Th((size_t)(md.T.diag ? md.m : md.m * md.m));
-  SS_CUDA(cudaMemcpyAsync(Th.data(), md.T.p, Th.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-  SS_CUDA(cudaStreamSynchronize(st));
+  if (T_host) {
+    std::copy(T_host, T_host + Th.size(), Th.begin());
+  } else {
+    SS_CUDA(cudaMemcpyAsync(Th.data(), md.T.p, Th.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
+  }
   static const bool reorder = [] {
     const char* e = getenv("SSGPU_WSM_REORDER");
     return e ? atoi(e) != 0 : true;
