@@ -59,6 +59,10 @@ def f_alg(m, p):
 # Scalar FP64 instructions per warp and time step in the p = 1 hot loop of loglik_mma_kernel (cuobjdump -sass and
 # ncu smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on, profiles/README.md): 23 DFMA, 11 DADD, 4 DMUL
 SCALAR_FLOPS_PER_STEP = (23 * 2 + 11 + 4) * 32
+# dram__bytes_read.sum + dram__bytes_write.sum of one loglik_mma_kernel launch at the default size (125,000 series x 9
+# parameter vectors x 1000 steps), from the `ncu --set full` capture summarised in
+# profiles/ncu_mma_r1_fullsize_summary.csv (1.289 GB + 21.2 MB); algorithmic: y 1.0 GB + variance sets 0.252 GB + out
+NCU_TRAFFIC_BYTES = {("loglik_mma_kernel<TT=2,tiles=0x9,dmma_per_step=14>", 125_000): 1.289423e9 + 21.163008e6}
 
 
 def executed_flops(kernel_name):
@@ -380,7 +384,9 @@ def run_gpu(args):
                         "steps": e2e_steps, "bit_identical_to_resident_path": e2e_match},
                 "gpu_launches": launches,
                 "roofline": {"bound": "fp64", "kernel": kernel_name, "achieved": achieved,
-                             "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                             "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                             "traffic": NCU_TRAFFIC_BYTES.get((kernel_name, B)),
+                             "traffic_algorithmic": 8.0 * B * T_STEPS + 8.0 * B * V * 2 * M + 8.0 * B * V,
                              "flops_per_series_timestep": f_alg(M, 1), "kernel_ms": kernel_ms,
                              "flops_executed_per_series_timestep": f_exec, "executed_tflops": executed,
                              "executed_frac": executed / peak_tf if executed else None,
@@ -609,8 +615,12 @@ def run_sim_gpu(args):
                 "e2e": {"value": e2e_value, "unit": SIM_UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": 1, "nsim": Se, "note": "host-pointer C ABI, R array layouts, pageable host memory"},
                 "gpu_launches": launches,
-                "roofline": {"bound": "hbm", "kernel": "fs_draw_kernel", "achieved": achieved, "peak": hbm_peak,
-                             "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "roofline": {"bound": "hbm", "kernel": "fs_draw_reg_kernel", "achieved": achieved, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": achieved / hbm_peak,
+                             # ncu --set full at 100,000 draws: 0.382 GB read + 3.514 GB written
+                             # (profiles/ncu_sim_r1_summary.csv) against 3.571 GB algorithmic
+                             "traffic": 0.381991936e9 + 3.513818e9 if S == 100_000 else None,
+                             "peak_source": peak_src,
                              "bytes_per_draw_timestep": b_fs, "kernel_ms": fs_ms,
                              "other_kernels": {
                                  "simulate_kernel": {"kernel_ms": statistics.mean(kt["simulate"]),
