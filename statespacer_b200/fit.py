@@ -1,0 +1,85 @@
+"""Batched maximum-likelihood fits: the caller of the batched loglikelihood path.
+
+statespacer() hands the objective LogLikC to stats::optim / optimx with method "BFGS" and numerical gradients
+(R/statespacer.R:917-982): per series, per iteration, 1 + 2k + (line search) sequential objective calls.  Here all
+B series advance in lock-step: one launch of ssgpu_loglik_grad_batch_dev gives every series its value and
+central-difference gradient, one launch of ssgpu_loglik_theta_batch_dev evaluates every series' line-search
+candidates, and the BFGS bookkeeping (k x k per series) is a handful of batched torch operations.  Series are
+independent, so a multi-GPU fit is a shard per rank (statespacer_b200.shard) with nothing to exchange.
+
+Only host-side orchestration lives here; the arithmetic of the objective is the CUDA path of include/ssgpu.h.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+from . import api
+
+
+@dataclass
+class FitResult:
+    theta: "torch.Tensor"       # (B, k) parameters at the optimum
+    loglik: "torch.Tensor"      # (B,)  loglik / N there (what LogLikC returns)
+    grad: "torch.Tensor"        # (B, k) central-difference gradient there
+    iterations: int
+    converged: "torch.Tensor"   # (B,) bool: max |grad| < gtol or no candidate improved
+    evaluations: int            # filter runs per series (for the series*timesteps bookkeeping)
+
+
+def fit_batch(y, model, theta0, q_index, p_star_index, max_iter=60, h=1e-3, gtol=1e-5, kernel="auto",
+              steps=(1.0, 0.5, 0.25, 0.125, 0.0625, 1.0 / 64, 1.0 / 256), max_step=2.0, c1=1e-4):
+    """Maximise loglik / N over theta for every series of the batch (BFGS, backtracking line search).
+
+    y (N, B) or (N, p, B) CUDA float64 tensor, `model` an api.BatchModel built with device=... (shared matrices),
+    theta0 (B, k) CUDA tensor of start values, q_index / p_star_index as for api.loglik_grad_batch_dev."""
+    import torch
+
+    B, k = theta0.shape
+    dev = theta0.device
+    theta = theta0.clone()
+    eye = torch.eye(k, device=dev, dtype=torch.float64).expand(B, k, k)
+    H = eye.clone()                                               # inverse-Hessian approximation of -loglik
+    alphas = torch.tensor(steps, device=dev, dtype=torch.float64)
+    L = alphas.numel()
+    ll, gr = api.loglik_grad_batch_dev(y, model, theta, q_index, p_star_index, h=h, kernel=kernel)
+    f, g = -ll, -gr
+    n_eval = 1 + 2 * k
+    done = ~torch.isfinite(f)
+    it = 0
+    for it in range(1, max_iter + 1):
+        d = -torch.bmm(H, g.unsqueeze(2)).squeeze(2)
+        slope = (g * d).sum(1)
+        bad = ~(slope < 0)                                        # not a descent direction: steepest descent
+        if bad.any():
+            H = torch.where(bad[:, None, None], eye, H)
+            d = torch.where(bad[:, None], -g, d)
+            slope = (g * d).sum(1)
+        scale = torch.clamp(max_step / d.abs().amax(1).clamp_min(1e-300), max=1.0)   # variances are exp(2 theta)
+        d = d * scale[:, None]
+        slope = slope * scale
+        cand = theta[None] + alphas[:, None, None] * d[None]      # (L, B, k)
+        fc = -api.loglik_theta_batch_dev(y, model, cand.contiguous(), q_index, p_star_index, kernel=kernel)
+        n_eval += L
+        fc = torch.where(torch.isfinite(fc), fc, torch.full_like(fc, float("inf")))
+        armijo = fc <= f[None] + c1 * alphas[:, None] * slope[None]
+        first = torch.where(armijo.any(0), armijo.float().argmax(0), fc.argmin(0))   # largest step passing, else best
+        f_new = fc.gather(0, first[None]).squeeze(0)
+        improved = (f_new < f) & ~done
+        a_sel = alphas[first]
+        theta_new = torch.where(improved[:, None], theta + a_sel[:, None] * d, theta)
+        ll_new, gr_new = api.loglik_grad_batch_dev(y, model, theta_new, q_index, p_star_index, h=h, kernel=kernel)
+        n_eval += 1 + 2 * k
+        g_new = -gr_new
+        s = theta_new - theta
+        yv = g_new - g
+        sy = (s * yv).sum(1)
+        upd = improved & (sy > 1e-12)
+        rho = torch.where(upd, 1.0 / sy.clamp_min(1e-300), torch.zeros_like(sy))
+        I_rsy = eye - rho[:, None, None] * s.unsqueeze(2) * yv.unsqueeze(1)
+        H_new = torch.bmm(torch.bmm(I_rsy, H), I_rsy.transpose(1, 2)) + rho[:, None, None] * s.unsqueeze(2) * s.unsqueeze(1)
+        H = torch.where(upd[:, None, None], H_new, H)
+        theta, f, g = theta_new, torch.where(improved, -ll_new, f), torch.where(improved[:, None], g_new, g)
+        done = done | ~improved | (g.abs().amax(1) < gtol)
+        if bool(done.all()):
+            break
+    return FitResult(theta=theta, loglik=-f, grad=-g, iterations=it, converged=done, evaluations=n_eval)

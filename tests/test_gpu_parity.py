@@ -276,6 +276,39 @@ def test_loglik_grad_batch_from_theta():
         api.loglik_grad_batch(y, sm0, theta, [9] * 14, BSM_P_INDEX)
 
 
+def test_fit_batch_bfgs():
+    """The batched caller of the path (statespacer_b200/fit.py): every series' loglikelihood ends no lower than at
+    its start values and no lower than at the data-generating parameters (up to optimiser tolerance), gradients
+    vanish, and for a few series the optimum agrees with scipy's BFGS on the oracle objective."""
+    import torch
+    from scipy.optimize import minimize
+    from statespacer_b200 import fit
+    rng = np.random.default_rng(77)
+    B, N, k = 48, 120, 4
+    truth = 0.5 * np.log([1.0, 0.1, 0.01, 0.05]) + 0.2 * rng.normal(size=(B, k))
+    y = np.zeros((N, B))
+    for b in range(B):
+        y[:, b] = simulate_y(rng, sysmat.bsm12(truth[b]), N)[:, 0]
+    dev = torch.device("cuda")
+    sm0 = sysmat.bsm12(truth[0])
+    model = api.BatchModel(sm0, N, B, 1, device=dev)
+    y_d = torch.from_numpy(y).to(dev)
+    start = torch.from_numpy(np.tile(0.5 * np.log([0.5, 0.5, 0.05, 0.05]), (B, 1))).to(dev)
+    ll0, _ = api.loglik_grad_batch_dev(y_d, model, start, BSM_Q_INDEX, BSM_P_INDEX)
+    ll_true, _ = api.loglik_grad_batch_dev(y_d, model, torch.from_numpy(truth).to(dev), BSM_Q_INDEX, BSM_P_INDEX)
+    res = fit.fit_batch(y_d, model, start, BSM_Q_INDEX, BSM_P_INDEX, max_iter=80)
+    ll = res.loglik.cpu().numpy()
+    assert np.all(np.isfinite(ll)) and np.all(ll >= ll0.cpu().numpy() - 1e-12)
+    assert np.mean(ll >= ll_true.cpu().numpy() - 1e-6) > 0.9
+    # a variance that wants to be zero runs off to theta -> -inf along a flat ridge: judge convergence by the value
+    for b in (0, 7, 19):
+        yb = y[:, b:b + 1]
+        obj = lambda th: -cport.LogLikC(yb, np.isnan(yb), *sysmat.bsm12(th).args())
+        ref_opt = minimize(obj, start[b].cpu().numpy(), method="BFGS", options={"gtol": 1e-6, "eps": 1e-3})
+        assert ll[b] >= -ref_opt.fun - 5e-5 * max(1.0, abs(ref_opt.fun)), (b, ll[b], -ref_opt.fun)
+    assert res.evaluations == (1 + 2 * k) * (res.iterations + 1) + 7 * res.iterations
+
+
 def _block_diagonal_model(rng, m, p, d, N, scatter=True):
     """Random model whose T is block diagonal with blocks of size 1-3 scattered over the state vector, so
     that the tensor kernel has to re-order the states to reach a tile-diagonal T."""
