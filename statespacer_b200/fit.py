@@ -83,3 +83,41 @@ def fit_batch(y, model, theta0, q_index, p_star_index, max_iter=60, h=1e-3, gtol
         if bool(done.all()):
             break
     return FitResult(theta=theta, loglik=-f, grad=-g, iterations=it, converged=done, evaluations=n_eval)
+
+
+def hessian_batch(y, model, theta, q_index, p_star_index, h=1e-2, kernel="auto"):
+    """Central-difference Hessian of loglik / N at theta for every series from ONE launch of 1 + 2k + 2k(k-1)
+    parameter vectors per series (the points of the sweep statespacer() hands to numDeriv::hessian for the standard
+    errors, R/statespacer.R:1057-1062; numDeriv refines them by Richardson extrapolation, this is the plain second
+    difference).  Returns (B, k, k)."""
+    import torch
+
+    B, k = theta.shape
+    dev = theta.device
+    offsets = [torch.zeros(k, device=dev, dtype=torch.float64)]
+    index = {}
+    for i in range(k):
+        for sgn in (1.0, -1.0):
+            e = torch.zeros(k, device=dev, dtype=torch.float64)
+            e[i] = sgn * h
+            index[(i, sgn)] = len(offsets)
+            offsets.append(e)
+    for i in range(k):
+        for j in range(i + 1, k):
+            for si in (1.0, -1.0):
+                for sj in (1.0, -1.0):
+                    e = torch.zeros(k, device=dev, dtype=torch.float64)
+                    e[i], e[j] = si * h, sj * h
+                    index[(i, j, si, sj)] = len(offsets)
+                    offsets.append(e)
+    pts = theta[None] + torch.stack(offsets)[:, None, :]          # (V, B, k)
+    f = api.loglik_theta_batch_dev(y, model, pts.contiguous(), q_index, p_star_index, kernel=kernel)
+    Hm = torch.empty(B, k, k, device=dev, dtype=torch.float64)
+    for i in range(k):
+        Hm[:, i, i] = (f[index[(i, 1.0)]] - 2.0 * f[0] + f[index[(i, -1.0)]]) / (h * h)
+        for j in range(i + 1, k):
+            v = (f[index[(i, j, 1.0, 1.0)]] - f[index[(i, j, 1.0, -1.0)]] - f[index[(i, j, -1.0, 1.0)]]
+                 + f[index[(i, j, -1.0, -1.0)]]) / (4.0 * h * h)
+            Hm[:, i, j] = v
+            Hm[:, j, i] = v
+    return Hm

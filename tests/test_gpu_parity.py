@@ -309,6 +309,32 @@ def test_fit_batch_bfgs():
     assert res.evaluations == (1 + 2 * k) * (res.iterations + 1) + 7 * res.iterations
 
 
+def test_hessian_batch():
+    """One-launch central-difference Hessian (the sweep behind statespacer()'s standard errors) against the same
+    differences of the oracle objective."""
+    import torch
+    from statespacer_b200 import fit
+    rng = np.random.default_rng(5)
+    B, N, k, h = 6, 90, 4, 1e-2
+    thetas, _, _, y = _bsm_batch(rng, B, N, 1, 0.0)
+    theta = thetas[0]
+    dev = torch.device("cuda")
+    model = api.BatchModel(sysmat.bsm12(theta[0]), N, B, 1, device=dev)
+    Hm = fit.hessian_batch(torch.from_numpy(y).to(dev), model, torch.from_numpy(theta).to(dev), BSM_Q_INDEX,
+                           BSM_P_INDEX, h=h).cpu().numpy()
+    assert np.allclose(Hm, Hm.transpose(0, 2, 1))
+    b = 3
+    yb = y[:, b:b + 1]
+    f = lambda th: cport.LogLikC(yb, np.isnan(yb), *sysmat.bsm12(th).args())
+    E = np.eye(k) * h
+    for i in range(k):
+        want = (f(theta[b] + E[i]) - 2 * f(theta[b]) + f(theta[b] - E[i])) / h ** 2
+        assert abs(Hm[b, i, i] - want) <= 1e-6 * max(1.0, abs(want)), (i, Hm[b, i, i], want)
+    want = (f(theta[b] + E[0] + E[2]) - f(theta[b] + E[0] - E[2]) - f(theta[b] - E[0] + E[2])
+            + f(theta[b] - E[0] - E[2])) / (4 * h * h)
+    assert abs(Hm[b, 0, 2] - want) <= 1e-6 * max(1.0, abs(want))
+
+
 def _block_diagonal_model(rng, m, p, d, N, scatter=True):
     """Random model whose T is block diagonal with blocks of size 1-3 scattered over the state vector, so
     that the tensor kernel has to re-order the states to reach a tile-diagonal T."""
