@@ -185,14 +185,15 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, interval_ms=250):
         self.index = index
+        self.interval_ms = interval_ms
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "250", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", str(self.interval_ms), "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -549,9 +550,11 @@ def run_sim_gpu(args):
     for _ in range(args.warmup):
         step()
     sync()
-    sampler = ClockSampler(local)
+    # a step is a few ms of kernels between short host-synchronous calls: poll nvidia-smi rarely, its queries
+    # stall the driver for milliseconds
+    sampler = ClockSampler(local, interval_ms=500)
     sampler.start()
-    time.sleep(0.3)
+    time.sleep(0.6)
     l0 = api.launch_count()
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -235,6 +235,50 @@ __device__ __forceinline__ void ell_apply(const Ell& E, const double* vt, const 
   }
 }
 
+// ELL table staged in shared memory once per CTA: byte offsets of the gather source instead of indices, and the
+// values too when the matrix is time-invariant -- the inner loop is then two broadcast shared-memory loads, the
+// gather and the fma, with no 64-bit address arithmetic and no global load
+struct EllS {
+  const double* v;  // shared memory (st == 0) or the global per-slice blocks
+  const int* off;   // shared memory: idx * kRegBT * 8
+  int W, rows;
+  long long st;
+};
+
+__device__ __forceinline__ EllS stage_ell(const Ell& E, double*& dcur, int*& icur, int tid) {
+  const int n = E.W * E.rows;
+  EllS s;
+  s.W = E.W;
+  s.rows = E.rows;
+  s.st = E.st;
+  for (int e = tid; e < n; e += kRegBT) icur[e] = E.idx[e] * kRegBT * 8;
+  s.off = icur;
+  icur += n;
+  if (E.st == 0) {
+    for (int e = tid; e < n; e += kRegBT) dcur[e] = E.val[e];
+    s.v = dcur;
+    dcur += n;
+  } else {
+    s.v = E.val;
+  }
+  return s;
+}
+
+template <int MP>
+__device__ __forceinline__ void ell_apply_s(const EllS& E, int t, const double* x0, int m, double (&out)[MP]) {
+#pragma unroll
+  for (int i = 0; i < MP; i++) out[i] = 0.0;
+  const double* vt = E.v + (E.st ? (long long)t * E.st : 0);
+  for (int w = 0; w < E.W; w++) {
+    const int* of = E.off + w * E.rows;
+    const double* vl = vt + w * E.rows;
+#pragma unroll
+    for (int i = 0; i < MP; i++)
+      if (i < m)
+        out[i] = fma(vl[i], *reinterpret_cast<const double*>(reinterpret_cast<const char*>(x0) + of[i]), out[i]);
+  }
+}
+
 template <int MP>
 __device__ __forceinline__ void park(const double (&x)[MP], const ShVec<kRegBT>& xs) {
 #pragma unroll
@@ -246,10 +290,18 @@ __global__ void __launch_bounds__(kRegBT) simulate_reg_kernel(const SimArgs A) {
   extern __shared__ double sh[];
   const int tid = threadIdx.x;
   const long long s = (long long)blockIdx.x * kRegBT + tid;
-  if (s >= A.S) return;
   const int m = A.m, p = A.p, r = A.r, r_tot = A.r * A.repeat_Q, N = A.N;
   const long long S = A.S;
   ShVec<kRegBT> xs{sh + tid}, es{sh + (size_t)MP * kRegBT + tid};
+  EllS Te{}, Re{};
+  if (!A.eta_only) {
+    double* dcur = sh + (size_t)2 * MP * kRegBT;
+    int* icur = reinterpret_cast<int*>(dcur + (A.Te.st ? 0 : A.Te.W * A.Te.rows) + (A.Re.st ? 0 : A.Re.W * A.Re.rows));
+    Te = stage_ell(A.Te, dcur, icur, tid);
+    Re = stage_ell(A.Re, dcur, icur, tid);
+  }
+  __syncwarp();
+  if (s >= A.S) return;
   double av[MP];
 #pragma unroll
   for (int i = 0; i < MP; i++) av[i] = 0.0;
@@ -297,8 +349,8 @@ __global__ void __launch_bounds__(kRegBT) simulate_reg_kernel(const SimArgs A) {
     if (t < N - 1) {
       double o2[MP];
       park<MP>(av, xs);
-      ell_apply<MP>(A.Te, A.Te.vals(t), xs, m, av);
-      ell_apply<MP>(A.Re, A.Re.vals(t), es, m, o2);
+      ell_apply_s<MP>(Te, t, &xs[0], m, av);
+      ell_apply_s<MP>(Re, t, &es[0], m, o2);
 #pragma unroll
       for (int i = 0; i < MP; i++) av[i] = av[i] + o2[i];
     }
@@ -310,11 +362,18 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
   extern __shared__ double sh[];
   const int tid = threadIdx.x;
   const long long s = (long long)blockIdx.x * kRegBT + tid;
-  if (s >= A.S) return;
   const int m = A.m, p = A.p, r = A.r, N = A.N;
   const long long S = A.S;
   // xs: gather source; es: eta_t for R eta; r1: the diffuse-phase vector r^(1) (touched on d of the N steps only)
   ShVec<kRegBT> xs{sh + tid}, es{sh + (size_t)MP * kRegBT + tid}, r1{sh + (size_t)2 * MP * kRegBT + tid};
+  double* dcur = sh + (size_t)3 * MP * kRegBT;
+  int* icur = reinterpret_cast<int*>(dcur + (A.Te.st ? 0 : A.Te.W * A.Te.rows) + (A.Tce.st ? 0 : A.Tce.W * A.Tce.rows) +
+                                     (A.Re.st ? 0 : A.Re.W * A.Re.rows));
+  const EllS Te = stage_ell(A.Te, dcur, icur, tid);
+  const EllS Tce = stage_ell(A.Tce, dcur, icur, tid);
+  const EllS Re = stage_ell(A.Re, dcur, icur, tid);
+  __syncwarp();
+  if (s >= A.S) return;
   double av[MP];
 
   // forward: innovations v = y - z'a with the shared gains (src/FastSmootherC.cpp:139-251)
@@ -345,7 +404,7 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
     }
     if (t < N - 1) {
       park<MP>(av, xs);
-      ell_apply<MP>(A.Te, A.Te.vals(t), xs, m, av);
+      ell_apply_s<MP>(Te, t, &xs[0], m, av);
     }
   }
 
@@ -405,7 +464,7 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
       // eta_{t-1} = Q_{t-1} R_{t-1}' r_t right away (src/FastSmootherC.cpp:345-352): no N x m array of r_t
       const double* Qp = A.g.QtR + (A.qtr_tv ? (long long)(t - 1) * r * m : 0);
       for (int kk = 0; kk < r; kk++) A.eta[((long long)(t - 1) * r + kk) * S + s] = sp_row_dot(A.Qp, kk, Qp, r, xs);
-      ell_apply<MP>(A.Tce, Tp, xs, m, rr);  // T' r
+      ell_apply_s<MP>(Tce, t - 1, &xs[0], m, rr);  // T' r
       if (both) {  // T' r^(1): rare (the d diffuse steps), kept out of the registers
         for (int i = 0; i < m; i++) es[i] = ell_row_dot(A.Tce, Tp, i, r1);
         for (int i = 0; i < m; i++) r1[i] = es[i];
@@ -432,8 +491,8 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
       for (int kk = 0; kk < r; kk++) es[kk] = A.eta[((long long)(t - 1) * r + kk) * S + s];
       double o2[MP];
       park<MP>(av, xs);
-      ell_apply<MP>(A.Te, A.Te.vals(t - 1), xs, m, av);
-      ell_apply<MP>(A.Re, A.Re.vals(t - 1), es, m, o2);
+      ell_apply_s<MP>(Te, t - 1, &xs[0], m, av);
+      ell_apply_s<MP>(Re, t - 1, &es[0], m, o2);
 #pragma unroll
       for (int i = 0; i < MP; i++) av[i] = av[i] + o2[i];
     }
@@ -667,7 +726,9 @@ static int launch_simulate_bt(const SimArgs& A, cudaStream_t st) {
 
 template <int MP>
 static int launch_simulate_reg(const SimArgs& A, cudaStream_t st) {
-  const size_t smem = sizeof(double) * kRegBT * 2 * MP;
+  auto tab = [](const Ell& E) { return (size_t)E.W * E.rows * ((E.st ? 0 : sizeof(double)) + sizeof(int)); };
+  const size_t smem = sizeof(double) * kRegBT * 2 * MP + (A.eta_only ? 0 : tab(A.Te) + tab(A.Re)) + 16;
+  SS_CUDA(cudaFuncSetAttribute(simulate_reg_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_t_sim.start(st);
   simulate_reg_kernel<MP><<<nblk(A.S, kRegBT), kRegBT, smem, st>>>(A);
   g_t_sim.stop(st);
@@ -710,7 +771,10 @@ static int launch_fs_bt(const FsArgs& A, cudaStream_t st) {
 
 template <int MP>
 static int launch_fs_reg(const FsArgs& A, cudaStream_t st) {
-  const size_t smem = sizeof(double) * kRegBT * 3 * MP;
+  auto tab = [](const Ell& E) { return (size_t)E.W * E.rows * ((E.st ? 0 : sizeof(double)) + sizeof(int)); };
+  const size_t smem = sizeof(double) * kRegBT * 3 * MP + tab(A.Te) + tab(A.Tce) + tab(A.Re) + 16;
+  SS_ARG(smem <= 200 * 1024, "FastSmootherC: sparse tables too large for shared memory");
+  SS_CUDA(cudaFuncSetAttribute(fs_draw_reg_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_t_fs.start(st);
   fs_draw_reg_kernel<MP><<<nblk(A.S, kRegBT), kRegBT, smem, st>>>(A);
   g_t_fs.stop(st);
