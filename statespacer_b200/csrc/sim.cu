@@ -235,32 +235,34 @@ __device__ __forceinline__ void ell_apply(const Ell& E, const double* vt, const 
   }
 }
 
-// ELL table staged in shared memory once per CTA: byte offsets of the gather source instead of indices, and the
-// values too when the matrix is time-invariant -- the inner loop is then two broadcast shared-memory loads, the
-// gather and the fma, with no 64-bit address arithmetic and no global load
+// ELL table staged in shared memory once per CTA, rows padded to MP with (offset 0, value 0.0): byte offsets of the
+// gather source instead of indices, and the values too when the matrix is time-invariant.  The inner loop is then
+// two broadcast shared-memory loads at immediate offsets, the gather and the fma -- no bounds predicate, no 64-bit
+// address arithmetic, no global load.  (Time-varying matrices keep their values in global memory.)
 struct EllS {
-  const double* v;  // shared memory (st == 0) or the global per-slice blocks
-  const int* off;   // shared memory: idx * kRegBT * 8
+  const double* vs;  // shared memory [W][MP], valid when st == 0
+  const double* vg;  // global per-slice blocks [W][rows], used when st != 0
+  const int* off;    // shared memory [W][MP]: idx * kRegBT * 8
   int W, rows;
   long long st;
 };
 
+template <int MP>
 __device__ __forceinline__ EllS stage_ell(const Ell& E, double*& dcur, int*& icur, int tid) {
-  const int n = E.W * E.rows;
   EllS s;
   s.W = E.W;
   s.rows = E.rows;
   s.st = E.st;
-  for (int e = tid; e < n; e += kRegBT) icur[e] = E.idx[e] * kRegBT * 8;
-  s.off = icur;
-  icur += n;
-  if (E.st == 0) {
-    for (int e = tid; e < n; e += kRegBT) dcur[e] = E.val[e];
-    s.v = dcur;
-    dcur += n;
-  } else {
-    s.v = E.val;
+  s.vg = E.val;
+  for (int e = tid; e < E.W * MP; e += kRegBT) {
+    const int w = e / MP, i = e % MP;
+    icur[e] = i < E.rows ? E.idx[w * E.rows + i] * kRegBT * 8 : 0;
+    if (E.st == 0) dcur[e] = i < E.rows ? E.val[w * E.rows + i] : 0.0;
   }
+  s.off = icur;
+  icur += E.W * MP;
+  s.vs = dcur;
+  if (E.st == 0) dcur += E.W * MP;
   return s;
 }
 
@@ -268,14 +270,23 @@ template <int MP>
 __device__ __forceinline__ void ell_apply_s(const EllS& E, int t, const double* x0, int m, double (&out)[MP]) {
 #pragma unroll
   for (int i = 0; i < MP; i++) out[i] = 0.0;
-  const double* vt = E.v + (E.st ? (long long)t * E.st : 0);
-  for (int w = 0; w < E.W; w++) {
-    const int* of = E.off + w * E.rows;
-    const double* vl = vt + w * E.rows;
+  const char* xb = reinterpret_cast<const char*>(x0);
+  if (E.st == 0) {
+    for (int w = 0; w < E.W; w++) {
+      const int* of = E.off + w * MP;
+      const double* vl = E.vs + w * MP;
 #pragma unroll
-    for (int i = 0; i < MP; i++)
-      if (i < m)
-        out[i] = fma(vl[i], *reinterpret_cast<const double*>(reinterpret_cast<const char*>(x0) + of[i]), out[i]);
+      for (int i = 0; i < MP; i++) out[i] = fma(vl[i], *reinterpret_cast<const double*>(xb + of[i]), out[i]);
+    }
+  } else {
+    const double* vt = E.vg + (long long)t * E.st;
+    for (int w = 0; w < E.W; w++) {
+      const int* of = E.off + w * MP;
+      const double* vl = vt + w * E.rows;
+#pragma unroll
+      for (int i = 0; i < MP; i++)
+        if (i < m) out[i] = fma(vl[i], *reinterpret_cast<const double*>(xb + of[i]), out[i]);
+    }
   }
 }
 
@@ -296,9 +307,9 @@ __global__ void __launch_bounds__(kRegBT) simulate_reg_kernel(const SimArgs A) {
   EllS Te{}, Re{};
   if (!A.eta_only) {
     double* dcur = sh + (size_t)2 * MP * kRegBT;
-    int* icur = reinterpret_cast<int*>(dcur + (A.Te.st ? 0 : A.Te.W * A.Te.rows) + (A.Re.st ? 0 : A.Re.W * A.Re.rows));
-    Te = stage_ell(A.Te, dcur, icur, tid);
-    Re = stage_ell(A.Re, dcur, icur, tid);
+    int* icur = reinterpret_cast<int*>(dcur + (A.Te.st ? 0 : A.Te.W * MP) + (A.Re.st ? 0 : A.Re.W * MP));
+    Te = stage_ell<MP>(A.Te, dcur, icur, tid);
+    Re = stage_ell<MP>(A.Re, dcur, icur, tid);
   }
   __syncwarp();
   if (s >= A.S) return;
@@ -361,46 +372,72 @@ template <int MP>
 __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
   extern __shared__ double sh[];
   const int tid = threadIdx.x;
-  const long long s = (long long)blockIdx.x * kRegBT + tid;
   const int m = A.m, p = A.p, r = A.r, N = A.N;
   const long long S = A.S;
+  // every lane stays alive (the rows below are fetched cooperatively); lanes beyond the last draw shadow draw S-1
+  // and do not store
+  const long long s_raw = (long long)blockIdx.x * kRegBT + tid;
+  const bool live = s_raw < S;
+  const long long s = live ? s_raw : S - 1;
   // xs: gather source; es: eta_t for R eta; r1: the diffuse-phase vector r^(1) (touched on d of the N steps only)
   ShVec<kRegBT> xs{sh + tid}, es{sh + (size_t)MP * kRegBT + tid}, r1{sh + (size_t)2 * MP * kRegBT + tid};
   double* dcur = sh + (size_t)3 * MP * kRegBT;
-  int* icur = reinterpret_cast<int*>(dcur + (A.Te.st ? 0 : A.Te.W * A.Te.rows) + (A.Tce.st ? 0 : A.Tce.W * A.Tce.rows) +
-                                     (A.Re.st ? 0 : A.Re.W * A.Re.rows));
-  const EllS Te = stage_ell(A.Te, dcur, icur, tid);
-  const EllS Tce = stage_ell(A.Tce, dcur, icur, tid);
-  const EllS Re = stage_ell(A.Re, dcur, icur, tid);
-  __syncwarp();
-  if (s >= A.S) return;
+  // the gain row K0 and the row of Z of an observation are the same for all draws: lane k fetches element k one
+  // observation ahead and parks it in shared memory (two buffers), every lane then reads the m values as broadcast
+  // loads at immediate offsets -- one global load per lane and step instead of 2 m uniform ones in the chain
+  double* kb = dcur;          // [2][MP]
+  double* zb = dcur + 2 * MP; // [2][MP]
+  dcur += 4 * MP;
+  int* icur = reinterpret_cast<int*>(dcur + (A.Te.st ? 0 : A.Te.W * MP) + (A.Tce.st ? 0 : A.Tce.W * MP) +
+                                     (A.Re.st ? 0 : A.Re.W * MP));
+  const EllS Te = stage_ell<MP>(A.Te, dcur, icur, tid);
+  const EllS Tce = stage_ell<MP>(A.Tce, dcur, icur, tid);
+  const EllS Re = stage_ell<MP>(A.Re, dcur, icur, tid);
+  const long long Np = (long long)N * p;
+  auto fetch_k = [&](long long index) { return (tid < m && index >= 0 && index < Np) ? A.g.K0[index * m + tid] : 0.0; };
+  auto fetch_z = [&](long long index) {
+    if (!(tid < m && index >= 0 && index < Np)) return 0.0;
+    const int t = (int)(index / p), j = (int)(index % p);
+    return slice_of(A.Z, t)[j + tid * p];
+  };
   double av[MP];
 
   // forward: innovations v = y - z'a with the shared gains (src/FastSmootherC.cpp:139-251)
 #pragma unroll
   for (int k = 0; k < MP; k++) av[k] = k < m ? A.a0[k] : 0.0;
-  const long long Np = (long long)N * p;
   double y_next = A.y[s];  // observations are fetched one univariate step ahead of their use
+  if (tid < MP) {
+    kb[tid] = fetch_k(0);
+    zb[tid] = fetch_z(0);
+  }
+  __syncwarp();
+  int cur = 0;
   for (int t = 0; t < N; t++) {
-    const double* Zt = slice_of(A.Z, t);
     for (int j = 0; j < p; j++) {
       const long long index = (long long)t * p + j;
       const double y_now = y_next;
       if (index + 1 < Np) y_next = A.y[(index + 1) * S + s];
-      if ((A.g.code[index] & 255) == 0) continue;
-      double za = 0.0;
+      const double k_n = fetch_k(index + 1), z_n = fetch_z(index + 1);  // in flight during this observation
+      const double* kc = kb + cur * MP;
+      const double* zc = zb + cur * MP;
+      if ((A.g.code[index] & 255) != 0) {
+        double za = 0.0;
 #pragma unroll
-      for (int k = 0; k < MP; k++)
-        if (k < m) {
-          const double z = Zt[j + k * p];
+        for (int k = 0; k < MP; k++) {
+          const double z = zc[k];
           if (z != 0.0) za = fma(z, av[k], za);
         }
-      const double vv = y_now - za;
-      A.v[index * S + s] = vv;
-      const double* k0 = A.g.K0 + index * m;
+        const double vv = y_now - za;
+        if (live) A.v[index * S + s] = vv;
 #pragma unroll
-      for (int k = 0; k < MP; k++)
-        if (k < m) av[k] = fma(k0[k], vv, av[k]);
+        for (int k = 0; k < MP; k++) av[k] = fma(kc[k], vv, av[k]);
+      }
+      if (tid < MP) {
+        kb[(cur ^ 1) * MP + tid] = k_n;
+        zb[(cur ^ 1) * MP + tid] = z_n;
+      }
+      __syncwarp();
+      cur ^= 1;
     }
     if (t < N - 1) {
       park<MP>(av, xs);
@@ -414,48 +451,61 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
   for (int k = 0; k < MP; k++) rr[k] = 0.0;
   for (int k = 0; k < m; k++) r1[k] = 0.0;
   double v_next = A.v[(Np - 1) * S + s];  // innovations, one univariate step ahead (steps without one read junk)
+  __syncwarp();
+  if (tid < MP) {
+    kb[tid] = fetch_k(Np - 1);
+    zb[tid] = fetch_z(Np - 1);
+  }
+  __syncwarp();
+  cur = 0;
   for (int t = N - 1; t >= 0; t--) {
-    const double* Zt = slice_of(A.Z, t);
     for (int j = p - 1; j >= 0; j--) {
       const long long index = (long long)t * p + j;
       const double v_now = v_next;
       if (index > 0) v_next = A.v[(index - 1) * S + s];
+      const double k_n = fetch_k(index - 1), z_n = fetch_z(index - 1);
+      const double* kc = kb + cur * MP;
+      const double* zc = zb + cur * MP;
       const int c = A.g.code[index] & 255;
-      if (c == 0) continue;
-      const double* k0 = A.g.K0 + index * m;
-      const double c1 = A.g.F1[index] * v_now;
-      double d0 = 0.0;
+      if (c != 0) {
+        const double c1 = A.g.F1[index] * v_now;
+        double d0 = 0.0;
 #pragma unroll
-      for (int k = 0; k < MP; k++)
-        if (k < m) d0 = fma(k0[k], rr[k], d0);
-      if (c == 1) {
-        const double sc = c1 - d0;
+        for (int k = 0; k < MP; k++) d0 = fma(kc[k], rr[k], d0);
+        if (c == 1) {
+          const double sc = c1 - d0;
 #pragma unroll
-        for (int k = 0; k < MP; k++)
-          if (k < m) {
-            const double z = Zt[j + k * p];
+          for (int k = 0; k < MP; k++) {
+            const double z = zc[k];
             if (z != 0.0) rr[k] = fma(z, sc, rr[k]);
           }
-      } else {
-        const double* k1 = A.g.K1 + index * m;
-        double d1 = 0.0, d2 = 0.0;
+        } else {
+          const double* k1 = A.g.K1 + index * m;
+          double d1 = 0.0, d2 = 0.0;
 #pragma unroll
-        for (int k = 0; k < MP; k++)
-          if (k < m) {
-            d1 = fma(k0[k], r1[k], d1);
-            d2 = fma(k1[k], rr[k], d2);
-          }
-        const double s1 = (c1 - d1) - d2, s0 = -d0;
-#pragma unroll
-        for (int k = 0; k < MP; k++)
-          if (k < m) {
-            const double z = Zt[j + k * p];
-            if (z != 0.0) {
-              r1[k] = fma(z, s1, r1[k]);
-              rr[k] = fma(z, s0, rr[k]);
+          for (int k = 0; k < MP; k++)
+            if (k < m) {
+              d1 = fma(kc[k], r1[k], d1);
+              d2 = fma(k1[k], rr[k], d2);
             }
-          }
+          const double s1 = (c1 - d1) - d2, s0 = -d0;
+#pragma unroll
+          for (int k = 0; k < MP; k++)
+            if (k < m) {
+              const double z = zc[k];
+              if (z != 0.0) {
+                r1[k] = fma(z, s1, r1[k]);
+                rr[k] = fma(z, s0, rr[k]);
+              }
+            }
+        }
       }
+      if (tid < MP) {
+        kb[(cur ^ 1) * MP + tid] = k_n;
+        zb[(cur ^ 1) * MP + tid] = z_n;
+      }
+      __syncwarp();
+      cur ^= 1;
     }
     if (t > 0) {
       const double* Tp = A.Tce.vals(t - 1);
@@ -463,7 +513,10 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
       park<MP>(rr, xs);
       // eta_{t-1} = Q_{t-1} R_{t-1}' r_t right away (src/FastSmootherC.cpp:345-352): no N x m array of r_t
       const double* Qp = A.g.QtR + (A.qtr_tv ? (long long)(t - 1) * r * m : 0);
-      for (int kk = 0; kk < r; kk++) A.eta[((long long)(t - 1) * r + kk) * S + s] = sp_row_dot(A.Qp, kk, Qp, r, xs);
+      for (int kk = 0; kk < r; kk++) {
+        const double ev = sp_row_dot(A.Qp, kk, Qp, r, xs);
+        if (live) A.eta[((long long)(t - 1) * r + kk) * S + s] = ev;
+      }
       ell_apply_s<MP>(Tce, t - 1, &xs[0], m, rr);  // T' r
       if (both) {  // T' r^(1): rare (the d diffuse steps), kept out of the registers
         for (int i = 0; i < m; i++) es[i] = ell_row_dot(A.Tce, Tp, i, r1);
@@ -496,11 +549,14 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
 #pragma unroll
       for (int i = 0; i < MP; i++) av[i] = av[i] + o2[i];
     }
+    if (live) {
 #pragma unroll
-    for (int k = 0; k < MP; k++)
-      if (k < m) A.a_smooth[((long long)t * m + k) * S + s] = av[k];
+      for (int k = 0; k < MP; k++)
+        if (k < m) A.a_smooth[((long long)t * m + k) * S + s] = av[k];
+    }
   }
-  for (int kk = 0; kk < r; kk++) A.eta[((long long)(N - 1) * r + kk) * S + s] = 0.0;  // :81
+  if (live)
+    for (int kk = 0; kk < r; kk++) A.eta[((long long)(N - 1) * r + kk) * S + s] = 0.0;  // :81
 }
 
 // ---- ExtractComponentC ----------------------------------------------------------------------------
@@ -726,7 +782,7 @@ static int launch_simulate_bt(const SimArgs& A, cudaStream_t st) {
 
 template <int MP>
 static int launch_simulate_reg(const SimArgs& A, cudaStream_t st) {
-  auto tab = [](const Ell& E) { return (size_t)E.W * E.rows * ((E.st ? 0 : sizeof(double)) + sizeof(int)); };
+  auto tab = [](const Ell& E) { return (size_t)E.W * MP * ((E.st ? 0 : sizeof(double)) + sizeof(int)); };
   const size_t smem = sizeof(double) * kRegBT * 2 * MP + (A.eta_only ? 0 : tab(A.Te) + tab(A.Re)) + 16;
   SS_CUDA(cudaFuncSetAttribute(simulate_reg_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_t_sim.start(st);
@@ -771,8 +827,8 @@ static int launch_fs_bt(const FsArgs& A, cudaStream_t st) {
 
 template <int MP>
 static int launch_fs_reg(const FsArgs& A, cudaStream_t st) {
-  auto tab = [](const Ell& E) { return (size_t)E.W * E.rows * ((E.st ? 0 : sizeof(double)) + sizeof(int)); };
-  const size_t smem = sizeof(double) * kRegBT * 3 * MP + tab(A.Te) + tab(A.Tce) + tab(A.Re) + 16;
+  auto tab = [](const Ell& E) { return (size_t)E.W * MP * ((E.st ? 0 : sizeof(double)) + sizeof(int)); };
+  const size_t smem = sizeof(double) * (kRegBT * 3 * MP + 4 * MP) + tab(A.Te) + tab(A.Tce) + tab(A.Re) + 16;
   SS_ARG(smem <= 200 * 1024, "FastSmootherC: sparse tables too large for shared memory");
   SS_CUDA(cudaFuncSetAttribute(fs_draw_reg_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_t_fs.start(st);
