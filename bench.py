@@ -70,7 +70,10 @@ def executed_flops(kernel_name):
     FP64.  None for the other kernels."""
     import re
     m = re.search(r"dmma_per_step=(\d+)", kernel_name or "")
-    return int(m.group(1)) * 512 + SCALAR_FLOPS_PER_STEP if m else None
+    if m:
+        return int(m.group(1)) * 512 + SCALAR_FLOPS_PER_STEP
+    m = re.search(r"flop_per_step=(\d+)", kernel_name or "")     # block-row kernel: counted by the library itself
+    return int(m.group(1)) if m else None
 
 
 def variants(theta):
@@ -659,7 +662,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--series", type=int, default=B_PER_GPU, help="series per GPU")
     ap.add_argument("--missing", type=float, default=0.0, help="fraction of NaN observations (variant B: 0.02)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "mma", "mma_dense", "cols", "wsm", "generic"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "blk", "mma", "mma_dense", "cols", "wsm", "generic"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="loglik", choices=["loglik", "sim"],
                     help="loglik: config 5 (headline, default); sim: config 4 simulation smoother draws")

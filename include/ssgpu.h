@@ -144,8 +144,9 @@ typedef struct ssgpu_model {
 } ssgpu_model;
 
 /* kernel selection for the batched path */
-#define SSGPU_KERNEL_AUTO 0     /* tensor kernel when the model qualifies (column kernel first when p >= 4 and it
-                                   qualifies), else column kernel, else the warp/shared-memory kernel, else generic */
+#define SSGPU_KERNEL_AUTO 0     /* block-row kernel when the model qualifies, else the tensor kernel (column kernel first
+                                   when p >= 4 and it qualifies), else column kernel, else the warp/shared-memory
+                                   kernel, else generic */
 #define SSGPU_KERNEL_GENERIC 1  /* one CTA per evaluation, any shape */
 #define SSGPU_KERNEL_COLS 2     /* column-per-lane DFMA kernel (m <= 15); SSGPU_E_ARG if not eligible */
 #define SSGPU_KERNEL_MMA 3      /* warp-per-evaluation FP64 tensor (DMMA) kernel (m <= 23); SSGPU_E_ARG if not eligible.
@@ -154,6 +155,11 @@ typedef struct ssgpu_model {
 #define SSGPU_KERNEL_MMA_DENSE 4 /* same kernel, caller's state order, every tile multiplied */
 #define SSGPU_KERNEL_WSM 5      /* warp per evaluation, covariance in shared memory, FP64 tensor time update (m <= 63,
                                    shared Z / T / R, Z may be time-varying); SSGPU_E_ARG if not eligible */
+
+#define SSGPU_KERNEL_BLK 6      /* block-row DFMA kernel: T block diagonal with blocks of at most 2 x 2 after re-ordering
+                                   the states (residuals, level, slope, trigonometric seasonals, cycles, regression
+                                   coefficients), at most 8 blocks (m <= 16), p <= 8, R Q R' inside the blocks;
+                                   SSGPU_E_ARG if not eligible.  AUTO tries it first */
 
 /* host pointers everywhere (y, the matrices' data, out); copies in, runs, copies out, synchronises */
 int ssgpu_loglik_batch(const double* y, long long B, int V, const ssgpu_model* model, int kernel,

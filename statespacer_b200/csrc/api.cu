@@ -199,10 +199,27 @@ static size_t extent(const ssgpu_matrix& M, long long B, int V) {
   return (size_t)((B - 1) * M.stride_series + (V - 1) * M.stride_variant) + slice * M.n_slices;
 }
 
+static bool auto_blk_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SSGPU_AUTO_BLK");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+
 static int dispatch_batch(const DModel& md, const double* y_dev, long long B, int V, int kernel, double* out_dev,
-                          cudaStream_t st, const double* T_host = nullptr) {
+                          cudaStream_t st, const HostShared* hs = nullptr) {
   SS_ARG(B >= 1 && V >= 1, "B and V must be positive");
   std::string why;
+  const double* T_host = hs ? hs->T : nullptr;
+  // block-diagonal T with blocks of at most 2 x 2 (structural models): the block-row kernel issues 4 m^2 instead of
+  // 4 m^3 multiply-adds per time update
+  if (kernel == SSGPU_KERNEL_BLK) return launch_loglik_blk(md, y_dev, B, V, out_dev, st, hs);
+  if (kernel == SSGPU_KERNEL_AUTO && auto_blk_enabled() && blk_eligible(md, &why)) {
+    bool ran = true;
+    SS_TRY(launch_loglik_blk(md, y_dev, B, V, out_dev, st, hs, &ran));
+    if (ran) return SSGPU_OK;
+  }
   const bool mma_ok = mma_eligible(md, &why);
   if (kernel == SSGPU_KERNEL_MMA || kernel == SSGPU_KERNEL_MMA_DENSE)
     SS_ARG(mma_ok, "tensor kernel not eligible: " + why);
@@ -276,8 +293,8 @@ int ssgpu_LogLikC(const double* y, const int* y_isna, int N, int p, int m, int r
   SS_TRY(out.alloc(sizeof(double), st));
   // one series is a batch of one: the warp-level kernels serve it when the model qualifies (a few hundred cycles
   // per observation instead of the CTA kernel's barriers), the generic kernel otherwise
-  SS_TRY(dispatch_batch(S.md, S.dev.as<double>() + S.oy, 1, 1, SSGPU_KERNEL_AUTO, out.as<double>(), st,
-                        nT == 1 ? T : nullptr));
+  const HostShared hs{nT == 1 ? T : nullptr, nR == 1 ? R : nullptr, nZ == 1 ? Z : nullptr, nQ == 1 ? Q : nullptr};
+  SS_TRY(dispatch_batch(S.md, S.dev.as<double>() + S.oy, 1, 1, SSGPU_KERNEL_AUTO, out.as<double>(), st, &hs));
   SS_CUDA(cudaMemcpyAsync(loglik, out.get(), sizeof(double), cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));
   return SSGPU_OK;

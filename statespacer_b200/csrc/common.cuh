@@ -226,6 +226,24 @@ int launch_expand_theta(const double* theta, long long B, int V, int k, int r, i
                         double* Pd, cudaStream_t st);
 int launch_fd_gradient(const double* out, long long B, int k, double h, double* loglik, double* grad, cudaStream_t st);
 
+// Block-row DFMA kernel for transition matrices that are block diagonal with blocks of at most 2 x 2 (loglik_blk.cu)
+struct HostShared {  // optional host copies of the shared, time-invariant matrices (null = fetch from the device)
+  const double *T, *R, *Z, *Q;
+};
+struct BlkPlan {
+  int nb;                // number of 2 x 2 blocks (a lone state is padded with an empty partner)
+  signed char perm[16];  // internal position 2I+e holds state perm[2I+e] of the caller, -1 = padding
+  double Tb[8][4];       // T_J[row][col] at [2*row + col]
+};
+bool plan_blocks(const double* Th, int t_diag, const double* Rh, int r_diag, const unsigned char* qpat, int m, int r,
+                 BlkPlan* pl, std::string* why);
+bool blk_eligible(const DModel& md, std::string* why);
+int blk_lanes(int nb);
+int blk_flops_per_step(int nb, int p);
+// applicable != null: a model whose T / R Q R' does not decompose is not an error; *applicable = false, nothing runs
+int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
+                      const HostShared* hs = nullptr, bool* applicable = nullptr);
+
 // Column-per-thread register kernel (loglik_cols.cu)
 bool cols_eligible(const DModel& md, std::string* why);
 int launch_loglik_cols(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st);

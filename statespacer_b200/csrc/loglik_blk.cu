@@ -1,0 +1,531 @@
+// Batched loglikelihood for models whose transition matrix is block diagonal with blocks of at most 2 x 2:
+// structure-exploiting DFMA kernel, L lanes per evaluation, the covariance distributed by block rows.
+//
+// Restates the recursion of src/LogLikC.cpp:68-214 (univariate treatment, exact diffuse initialisation,
+// NaN = missing) for models whose Z, T, R are shared by the batch and time-invariant (per-evaluation
+// a, P_inf, P_star, Q allowed) and whose T, after re-ordering the states, is  blkdiag(T_0, ..., T_{NB-1})  with
+// 1 x 1 or 2 x 2 blocks, NB <= 8 (m <= 16), and whose R Q R' has no entry outside those blocks.  That is every
+// structural model statespacer builds from residuals, level, slope, trigonometric seasonals, cycles and
+// regression coefficients (R/GetSysMat.R:1388-1426, R/Components-Unobserved.R:143-159,491-519): T couples a state
+// with at most one partner.  BASELINE.json config 5 (m = 14) is 7 such blocks.
+//
+// Why this shape.  With P cut into 2 x 2 blocks P_IJ the time update  P <- T P T' + R Q R'  (src/LogLikC.cpp:202)
+// is  P_IJ <- T_I P_IJ T_J' (+ (RQR')_II)  block by block: 16 multiply-adds per block, 4 m^2 per step instead of the
+// 4 m^3 of the dense product (the FP64 tensor kernel of loglik_mma.cu multiplies whole 8 x 8 tiles: 7,168 flop per
+// step at m = 14 where this kernel issues about 1,800), and it needs NO data from any other block.  Lane I of a
+// group of L lanes therefore owns block row I (NB blocks, 8 NB registers) and runs the whole time update from its
+// own registers; T_J and z are the same for every evaluation and come from the kernel parameters (constant bank).
+// Only the measurement update couples the block rows:  M = P z  is computed row-wise in place, all-gathered through
+// a few hundred bytes of shared memory (one 16-byte store and NB broadcast 16-byte loads per lane), F = z'M and z'a
+// are xor-butterfly sums over the group (bit-identical in every lane), and  P_IJ -= (M_I / F) M_J'  is local again.
+// 32 / L evaluations share a warp; the exact diffuse phase (about d of the N steps) runs in a select-based
+// loop that all groups of the warp execute until the last of them has left it, with P_inf parked in shared memory
+// so that the registers are sized for the regular phase.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace ssgpu {
+
+constexpr int kBlkThreads = 128;
+constexpr int kBlkMaxNB = 8;
+constexpr int kBlkMaxP = 8;
+
+struct BlkArgs {
+  DModel md;
+  const double* y;  // [(t*p + j) * B + b]
+  long long B;
+  long long E;  // B * V
+  double* out;
+  signed char perm[2 * kBlkMaxNB];     // internal position 2I+e holds state perm[2I+e] of the caller, -1 = padding
+  double Tb[kBlkMaxNB][4];             // T_J[row][col] at [2*row + col], internal order
+  double z[kBlkMaxP][2 * kBlkMaxNB];   // row j of Z, internal order
+};
+
+__device__ __forceinline__ double blk_rcp(double x) {
+  // MUFU.RCP64H seed and two Newton steps (x is finite, normal and >= 1e-7 here)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
+template <int L, int NB, bool P1, int MINB>
+__global__ void __launch_bounds__(kBlkThreads, MINB) loglik_blk_kernel(const BlkArgs A) {
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int G = 32 / L;  // evaluations per warp
+  const DModel& md = A.md;
+  const int N = md.N, p = P1 ? 1 : md.p, M = md.m, r = md.r;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int I = lane % L, g = lane / L;
+  // evaluations are numbered series-major (w = b*V + v) so that the V parameter vectors of a series run side by
+  // side and share its y through L1/L2; results keep the public order e = v*B + b
+  // T_J and the rows of Z are the same for every evaluation.  They are read from shared memory (broadcast 16-byte
+  // loads) rather than from the parameter bank: ptxas hoists constant-bank operands of a loop this size into
+  // uniform registers, runs out of them and spills (measured: 300 extra instructions per step).
+  __shared__ double2 tb_s[kBlkMaxNB][2];       // [J][c] = (T_J[c][0], T_J[c][1])
+  __shared__ double2 z_s[kBlkMaxP][kBlkMaxNB]; // [j][J] = (z[2J], z[2J+1])
+  for (int e = threadIdx.x; e < kBlkMaxNB * 2; e += kBlkThreads)
+    tb_s[e >> 1][e & 1] = make_double2(A.Tb[e >> 1][2 * (e & 1)], A.Tb[e >> 1][2 * (e & 1) + 1]);
+  for (int e = threadIdx.x; e < p * kBlkMaxNB; e += kBlkThreads)
+    z_s[e / kBlkMaxNB][e % kBlkMaxNB] = make_double2(A.z[e / kBlkMaxNB][2 * (e % kBlkMaxNB)], A.z[e / kBlkMaxNB][2 * (e % kBlkMaxNB) + 1]);
+  __syncthreads();
+  const long long w0 = ((long long)blockIdx.x * (kBlkThreads / 32) + warp) * G;
+  if (w0 >= A.E) return;  // whole warp
+  // every lane stays alive (shuffles, __syncwarp): groups beyond the last evaluation shadow it and do not store
+  const bool live = w0 + g < A.E;
+  const long long w_id = live ? w0 + g : A.E - 1;
+  const long long V = A.E / A.B, b = w_id / V, v = w_id % V;
+  const long long e_id = v * A.B + b;
+  const bool own = I < NB;  // L > NB: the surplus lanes carry zero blocks
+
+  __shared__ double2 xch_s[kBlkThreads / 32][2][NB][G];
+  __shared__ double pinf_s[NB * 4][kBlkThreads];
+  double2(*xch)[NB][G] = xch_s[warp];
+  double(*pinf)[kBlkThreads] = pinf_s;
+  const int tx = threadIdx.x;
+
+  // ---- own block row of P_star, P_inf, own T block, own part of a and z, own diagonal block of R Q R' ------------
+  const int i0 = own ? (int)A.perm[2 * I] : -1, i1 = own ? (int)A.perm[2 * I + 1] : -1;
+  auto elem = [&](const double* blk, int diag, int i, int k) { return (i >= 0 && k >= 0) ? mat_get(blk, diag, M, i, k) : 0.0; };
+  double P[NB][4];
+  {
+    const double* Ps = md.P_star.block(b, v, 0);
+    const double* Pi = md.P_inf.block(b, v, 0);
+#pragma unroll
+    for (int J = 0; J < NB; J++) {
+      const int k0 = A.perm[2 * J], k1 = A.perm[2 * J + 1];
+      P[J][0] = elem(Ps, md.P_star.diag, i0, k0);
+      P[J][1] = elem(Ps, md.P_star.diag, i0, k1);
+      P[J][2] = elem(Ps, md.P_star.diag, i1, k0);
+      P[J][3] = elem(Ps, md.P_star.diag, i1, k1);
+      pinf[J * 4 + 0][tx] = elem(Pi, md.P_inf.diag, i0, k0);
+      pinf[J * 4 + 1][tx] = elem(Pi, md.P_inf.diag, i0, k1);
+      pinf[J * 4 + 2][tx] = elem(Pi, md.P_inf.diag, i1, k0);
+      pinf[J * 4 + 3][tx] = elem(Pi, md.P_inf.diag, i1, k1);
+    }
+  }
+  double a0, a1;
+  {
+    const double* ab = md.a.block(b, v, 0);
+    a0 = i0 >= 0 ? ab[i0] : 0.0;
+    a1 = i1 >= 0 ? ab[i1] : 0.0;
+  }
+  const double t00 = tb_s[I][0].x, t01 = tb_s[I][0].y, t10 = tb_s[I][1].x, t11 = tb_s[I][1].y;  // zero beyond NB
+  // (R Q R')[i][c] for the own diagonal block (src/LogLikC.cpp:202, hoisted: Q and R are time-invariant here; the
+  // host has checked that R Q R' has no entry outside the diagonal blocks)
+  double q0, q1, q2, q3;
+  {
+    const double* Qb = md.Q.block(b, v, 0);
+    const double* Rb = md.R.block(0, 0, 0);
+    auto rqr = [&](int i, int c) {
+      double acc = 0.0;
+      if (i < 0 || c < 0) return acc;
+      for (int k = 0; k < r; k++) {
+        const double rik = mat_get(Rb, md.R.diag, M, i, k);
+        if (rik == 0.0) continue;
+        double qr;
+        if (md.Q.diag) {
+          qr = Qb[k] * mat_get(Rb, md.R.diag, M, c, k);
+        } else {
+          qr = 0.0;
+          for (int l = 0; l < r; l++) qr = fma(Qb[k + (long long)l * r], mat_get(Rb, md.R.diag, M, c, l), qr);
+        }
+        acc = fma(rik, qr, acc);
+      }
+      return acc;
+    };
+    q0 = rqr(i0, i0);
+    q1 = rqr(i0, i1);
+    q2 = rqr(i1, i0);
+    q3 = rqr(i1, i1);
+  }
+
+  auto group_sum = [&](double x) {
+#pragma unroll
+    for (int o = 1; o < L; o <<= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+  };
+  auto group_all = [&](bool ok) {
+    const unsigned bal = __ballot_sync(FULL, ok);
+    const unsigned gm = (L == 32 ? FULL : ((1u << L) - 1u)) << (g * L);
+    return (bal & gm) == gm;
+  };
+
+  // loglik = n_terms*const - (sum log F + sum v^2/F)/2, log F accumulated as mantissa * 2^esum
+  double prod = 1.0, sumq = 0.0;
+  int esum = 0, n_terms = 0, non_init = 0, F_eq0 = 0;
+  auto acc_log = [&](double F) {
+    prod *= F;
+    const int hi = __double2hiint(prod);
+    const int ex = ((hi >> 20) & 0x7ff) - 1023;
+    esum += ex;
+    prod = __hiloint2double(hi - (ex << 20), __double2loint(prod));
+  };
+
+  // P_IJ <- T_I P_IJ T_J' (+ the own diagonal block of R Q R' when J == I); X[r][c] = sum_k Y[r][k] T_J[c][k]
+  auto time_block = [&](int J, double& p0, double& p1, double& p2, double& p3, bool with_q) {
+    const double y00 = fma(t01, p2, t00 * p0), y01 = fma(t01, p3, t00 * p1);
+    const double y10 = fma(t11, p2, t10 * p0), y11 = fma(t11, p3, t10 * p1);
+    const bool dg = with_q && J == I;
+    const double2 tc0 = tb_s[J][0], tc1 = tb_s[J][1];
+    p0 = fma(y01, tc0.y, fma(y00, tc0.x, dg ? q0 : 0.0));
+    p1 = fma(y01, tc1.y, fma(y00, tc1.x, dg ? q1 : 0.0));
+    p2 = fma(y11, tc0.y, fma(y10, tc0.x, dg ? q2 : 0.0));
+    p3 = fma(y11, tc1.y, fma(y10, tc1.x, dg ? q3 : 0.0));
+  };
+
+  const long long Np = (long long)N * p;
+  int buf = 0;
+  int t = 0;
+  {
+    // ---- exact diffuse phase (src/LogLikC.cpp:98-159), select-based: the groups of a warp may leave it at
+    // different time points (missing observations), so every group runs this loop until the last one is done ----
+    bool small = true;
+#pragma unroll
+    for (int e = 0; e < NB * 4; e++) small = small && (fabs(pinf[e][tx]) < kEps);
+    bool init = !group_all(small);  // :49
+    while (t < N && __any_sync(FULL, init)) {
+      for (int j = 0; j < p; j++) {
+        const double yv = A.y[((long long)t * p + j) * A.B + b];
+        const bool obs = !isnan(yv);  // :88-90
+        const double zi0 = z_s[j][I].x, zi1 = z_s[j][I].y;
+        double ms0 = 0.0, ms1 = 0.0, mi0 = 0.0, mi1 = 0.0;
+#pragma unroll
+        for (int J = 0; J < NB; J++) {
+          const double z0 = z_s[j][J].x, z1 = z_s[j][J].y;
+          ms0 = fma(P[J][1], z1, fma(P[J][0], z0, ms0));
+          ms1 = fma(P[J][3], z1, fma(P[J][2], z0, ms1));
+          mi0 = fma(pinf[J * 4 + 1][tx], z1, fma(pinf[J * 4 + 0][tx], z0, mi0));
+          mi1 = fma(pinf[J * 4 + 3][tx], z1, fma(pinf[J * 4 + 2][tx], z0, mi1));
+        }
+        const double F_star = group_sum(fma(zi1, ms1, zi0 * ms0));
+        const double F_inf = group_sum(fma(zi1, mi1, zi0 * mi0));
+        const double za = group_sum(fma(zi1, a1, zi0 * a0));
+        // the three outcomes of :109-153 and the regular step of :162-195 (a group whose P_inf has vanished)
+        const bool dif = init && obs && !(F_inf < kEps);
+        const bool star = obs && !dif && !(F_star < kEps);
+        non_init += obs && !init;
+        F_eq0 += obs && !init && !star;
+        const double F1i = dif ? 1.0 / F_inf : 0.0, F2 = dif ? -(F1i * F1i) * F_star : 0.0;
+        const double F1s = star ? 1.0 / F_star : 0.0;
+        const double vv = (dif || star) ? yv - za : 0.0;
+        if (dif) acc_log(F_inf);  // no v^2 term (:153)
+        if (star) acc_log(F_star);
+        n_terms += dif || star;
+        sumq = fma(vv * vv, F1s, sumq);
+        // K0 = M_inf F1 (diffuse) or M_star F1 (star); K1 = M_star F1 + M_inf F2 (diffuse only)
+        // P*_IJ -= M*_I K0_J' + M_inf,I K1_J';  P_inf,IJ -= M_inf,I K0_J' (diffuse only)
+        if (own) xch[buf][I][g] = make_double2(ms0, ms1);
+        if (own) xch[buf ^ 1][I][g] = make_double2(mi0, mi1);
+        __syncwarp();
+#pragma unroll
+        for (int J = 0; J < NB; J++) {
+          const double2 sJ = xch[buf][J][g], iJ = xch[buf ^ 1][J][g];
+          const double k00 = fma(F1s, sJ.x, F1i * iJ.x), k01 = fma(F1s, sJ.y, F1i * iJ.y);    // K0_J
+          const double k10 = fma(F2, iJ.x, F1i * sJ.x), k11 = fma(F2, iJ.y, F1i * sJ.y);      // K1_J
+          P[J][0] = fma(-mi0, k10, fma(-ms0, k00, P[J][0]));
+          P[J][1] = fma(-mi0, k11, fma(-ms0, k01, P[J][1]));
+          P[J][2] = fma(-mi1, k10, fma(-ms1, k00, P[J][2]));
+          P[J][3] = fma(-mi1, k11, fma(-ms1, k01, P[J][3]));
+          const double c0 = F1i * iJ.x, c1 = F1i * iJ.y;
+          pinf[J * 4 + 0][tx] = fma(-mi0, c0, pinf[J * 4 + 0][tx]);
+          pinf[J * 4 + 1][tx] = fma(-mi0, c1, pinf[J * 4 + 1][tx]);
+          pinf[J * 4 + 2][tx] = fma(-mi1, c0, pinf[J * 4 + 2][tx]);
+          pinf[J * 4 + 3][tx] = fma(-mi1, c1, pinf[J * 4 + 3][tx]);
+        }
+        __syncwarp();  // both buffers are rewritten by the next observation
+        a0 = fma(fma(F1s, ms0, F1i * mi0), vv, a0);
+        a1 = fma(fma(F1s, ms1, F1i * mi1), vv, a1);
+        if (j < p - 1) {  // :157-159 (only after a diffuse update)
+          small = true;
+#pragma unroll
+          for (int e = 0; e < NB * 4; e++) small = small && (fabs(pinf[e][tx]) < kEps);
+          const bool gone = group_all(small);
+          if (dif && gone) init = false;
+        }
+      }
+      if (t < N - 1) {  // :200-207
+        small = true;
+#pragma unroll
+        for (int J = 0; J < NB; J++) {
+          time_block(J, P[J][0], P[J][1], P[J][2], P[J][3], true);
+          double i0v = pinf[J * 4 + 0][tx], i1v = pinf[J * 4 + 1][tx], i2v = pinf[J * 4 + 2][tx], i3v = pinf[J * 4 + 3][tx];
+          time_block(J, i0v, i1v, i2v, i3v, false);
+          pinf[J * 4 + 0][tx] = i0v;
+          pinf[J * 4 + 1][tx] = i1v;
+          pinf[J * 4 + 2][tx] = i2v;
+          pinf[J * 4 + 3][tx] = i3v;
+          small = small && (fabs(i0v) < kEps) && (fabs(i1v) < kEps) && (fabs(i2v) < kEps) && (fabs(i3v) < kEps);
+        }
+        const double na0 = fma(t01, a1, t00 * a0), na1 = fma(t11, a1, t10 * a0);
+        a0 = na0;
+        a1 = na1;
+        const bool gone = group_all(small);
+        if (init && gone) init = false;
+      }
+      t++;
+    }
+  }
+
+  // ---- regular phase: the hot loop (src/LogLikC.cpp:162-207), branch-free ------------------------------------
+  // A missing observation or F < 1e-7 (:88-90, :173-176) makes the update a no-op through 1/F := v := 0.
+  if (t < N) {
+    long long idx = (long long)t * p;
+    double ynext = A.y[idx * A.B + b];  // observations are fetched one univariate step ahead of their use
+    for (; t < N; t++) {
+#pragma unroll 1
+      for (int j = 0; j < p; j++, idx++) {
+        const double yv = ynext;
+        if (idx + 1 < Np) ynext = A.y[(idx + 1) * A.B + b];
+        const double zi0 = z_s[j][I].x, zi1 = z_s[j][I].y;
+        // M_I = sum_J P_IJ z_J: two chains per row
+        double m0a = 0.0, m0b = 0.0, m1a = 0.0, m1b = 0.0;
+#pragma unroll
+        for (int J = 0; J < NB; J++) {
+          const double2 zJ = z_s[j][J];
+          const double z0 = zJ.x, z1 = zJ.y;
+          m0a = fma(P[J][0], z0, m0a);
+          m0b = fma(P[J][1], z1, m0b);
+          m1a = fma(P[J][2], z0, m1a);
+          m1b = fma(P[J][3], z1, m1b);
+        }
+        const double m0 = m0a + m0b, m1 = m1a + m1b;
+        if (own) xch[buf][I][g] = make_double2(m0, m1);
+        const double F_star = group_sum(fma(zi1, m1, zi0 * m0));
+        const double za = group_sum(fma(zi1, a1, zi0 * a0));
+        __syncwarp();
+        const bool obs = !isnan(yv);
+        const bool upd = obs && !(F_star < kEps);
+        const double F1 = upd ? blk_rcp(F_star) : 0.0;
+        const double vv = upd ? yv - za : 0.0;
+        acc_log(upd ? F_star : 1.0);
+        n_terms += upd;
+        non_init += obs;
+        F_eq0 += obs && !upd;
+        sumq = fma(vv * vv, F1, sumq);
+        const double k0 = m0 * F1, k1 = m1 * F1;
+#pragma unroll
+        for (int J = 0; J < NB; J++) {
+          const double2 mJ = xch[buf][J][g];
+          P[J][0] = fma(-k0, mJ.x, P[J][0]);
+          P[J][1] = fma(-k0, mJ.y, P[J][1]);
+          P[J][2] = fma(-k1, mJ.x, P[J][2]);
+          P[J][3] = fma(-k1, mJ.y, P[J][3]);
+        }
+        buf ^= 1;
+        a0 = fma(k0, vv, a0);
+        a1 = fma(k1, vv, a1);
+      }
+      if (t < N - 1) {  // :200-204 (after the last observation P and a are not needed any more)
+#pragma unroll
+        for (int J = 0; J < NB; J++) time_block(J, P[J][0], P[J][1], P[J][2], P[J][3], true);
+        const double na0 = fma(t01, a1, t00 * a0), na1 = fma(t11, a1, t10 * a0);
+        a0 = na0;
+        a1 = na1;
+      }
+    }
+  }
+
+  if (I == 0 && live) {
+    double res;
+    if (non_init == F_eq0) {
+      res = nan("");  // src/LogLikC.cpp:211-213
+    } else {
+      const double sumlog = (double)esum * 0.69314718055994530942 + log(prod);
+      res = ((double)n_terms * kLogConst - 0.5 * (sumlog + sumq)) / (double)N;
+    }
+    A.out[e_id] = res;
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+// States i, k share a block when T or R Q R' couples them.  `Rh` m x r, `qpat` r x r (non-zero pattern of Q as 0/1,
+// null = diagonal).  Pairs first (ascending), then the uncoupled states two by two.
+bool plan_blocks(const double* Th, int t_diag, const double* Rh, int r_diag, const unsigned char* qpat, int m, int r,
+                 BlkPlan* pl, std::string* why) {
+  auto no = [&](const char* s) {
+    if (why) *why = s;
+    return false;
+  };
+  std::vector<int> partner(m, -1);
+  auto couple = [&](int i, int k) {
+    if (i == k) return true;
+    if (partner[i] == k && partner[k] == i) return true;
+    if (partner[i] >= 0 || partner[k] >= 0) return false;
+    partner[i] = k;
+    partner[k] = i;
+    return true;
+  };
+  for (int i = 0; i < m; i++)
+    for (int k = 0; k < m; k++)
+      if (i != k && mat_get(Th, t_diag, m, i, k) != 0.0 && !couple(i, k)) return no("T couples a state with two others");
+  // R Q R' [i][c] != 0 needs k, l with R[i][k], Q[k][l], R[c][l] all non-zero
+  for (int i = 0; i < m; i++)
+    for (int c = 0; c < m; c++) {
+      if (i == c) continue;
+      bool nz = false;
+      for (int k = 0; k < r && !nz; k++) {
+        if (mat_get(Rh, r_diag, m, i, k) == 0.0) continue;
+        for (int l = 0; l < r && !nz; l++) {
+          const bool q = qpat ? qpat[k + (size_t)l * r] != 0 : k == l;
+          nz = q && mat_get(Rh, r_diag, m, c, l) != 0.0;
+        }
+      }
+      if (nz && !couple(i, c)) return no("R Q R' couples a state with two others");
+    }
+  int nb = 0;
+  std::memset(pl, 0, sizeof *pl);
+  for (int i = 0; i < 2 * kBlkMaxNB; i++) pl->perm[i] = -1;
+  auto put = [&](int i, int k) {
+    if (nb >= kBlkMaxNB) return false;
+    pl->perm[2 * nb] = (signed char)i;
+    pl->perm[2 * nb + 1] = (signed char)k;
+    nb++;
+    return true;
+  };
+  for (int i = 0; i < m; i++)
+    if (partner[i] > i && !put(i, partner[i])) return no("more than 8 blocks");
+  int pend = -1;
+  for (int i = 0; i < m; i++) {
+    if (partner[i] >= 0) continue;
+    if (pend < 0) {
+      pend = i;
+    } else {
+      if (!put(pend, i)) return no("more than 8 blocks");
+      pend = -1;
+    }
+  }
+  if (pend >= 0 && !put(pend, -1)) return no("more than 8 blocks");
+  pl->nb = nb;
+  for (int J = 0; J < nb; J++)
+    for (int rr = 0; rr < 2; rr++)
+      for (int cc = 0; cc < 2; cc++) {
+        const int i = pl->perm[2 * J + rr], k = pl->perm[2 * J + cc];
+        pl->Tb[J][2 * rr + cc] = (i >= 0 && k >= 0) ? mat_get(Th, t_diag, m, i, k) : 0.0;
+      }
+  return true;
+}
+
+bool blk_eligible(const DModel& md, std::string* why) {
+  auto no = [&](const char* s) {
+    if (why) *why = s;
+    return false;
+  };
+  if (md.m > 2 * kBlkMaxNB) return no("m > 16");
+  if (md.p > kBlkMaxP) return no("p > 8");
+  if (!md.Z.shared() || !md.T.shared() || !md.R.shared()) return no("Z, T, R must be shared by the batch");
+  if (md.Z.tv() || md.T.tv() || md.R.tv() || md.Q.tv()) return no("time-varying system matrices");
+  if (!md.Q.diag && !md.Q.shared()) return no("per-evaluation Q must be stored as a diagonal");
+  return true;
+}
+
+template <int L, int NB, int MINB>
+static void launch_blk_mb(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
+  if (A.md.p == 1)
+    loglik_blk_kernel<L, NB, true, MINB><<<blocks, kBlkThreads, 0, st>>>(A);
+  else
+    loglik_blk_kernel<L, NB, false, MINB><<<blocks, kBlkThreads, 0, st>>>(A);
+}
+
+template <int L, int NB>
+static void launch_blk_nb(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
+  // resident CTAs per SM the register budget is sized for (tuning knob): 4 = 128 registers, 3 = 168
+  static const int minb = [] {
+    const char* e = getenv("SSGPU_BLK_MINB");
+    return e ? atoi(e) : 4;
+  }();
+  if (L == 8 && minb <= 3)
+    launch_blk_mb<L, NB, (L == 8 ? 3 : 4)>(A, blocks, st);
+  else
+    launch_blk_mb<L, NB, 4>(A, blocks, st);
+}
+
+int blk_lanes(int nb) { return nb > 4 ? 8 : nb > 2 ? 4 : nb > 1 ? 2 : 1; }
+
+// FP64 operations (fma = 2) the kernel issues per series and time step in the regular phase, all L lanes counted
+int blk_flops_per_step(int nb, int p) {
+  const int L = blk_lanes(nb);
+  int lg = 0;
+  while ((1 << lg) < L) lg++;
+  const int fma_obs = 4 * nb + 2 + 4 + 4 * nb + 2 + 1, mul_obs = 2 + 2 + 3, add_obs = 2 + 2 * lg;
+  const int fma_t = 12 * nb + 2, mul_t = 4 * nb + 2;
+  return L * (p * (2 * fma_obs + mul_obs + add_obs) + 2 * fma_t + mul_t);
+}
+
+int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
+                      const HostShared* hs, bool* applicable) {
+  std::string why;
+  if (applicable) *applicable = true;
+  SS_ARG(blk_eligible(md, &why), "block kernel not eligible: " + why);
+  const int m = md.m, r = md.r, p = md.p;
+  // the shared matrices are a few hundred bytes: fetch what the caller has not passed along (host copies)
+  std::vector<double> Th((size_t)(md.T.diag ? m : m * m)), Rh((size_t)(md.R.diag ? m : m * r)), Zh((size_t)p * m), Qh;
+  std::vector<unsigned char> qpat;
+  bool need_sync = false;
+  auto fetch = [&](std::vector<double>& dst, const double* host, const double* dev) -> int {
+    if (host) {
+      std::copy(host, host + dst.size(), dst.begin());
+    } else {
+      SS_CUDA(cudaMemcpyAsync(dst.data(), dev, dst.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+      need_sync = true;
+    }
+    return SSGPU_OK;
+  };
+  SS_TRY(fetch(Th, hs ? hs->T : nullptr, md.T.p));
+  SS_TRY(fetch(Rh, hs ? hs->R : nullptr, md.R.p));
+  SS_TRY(fetch(Zh, hs ? hs->Z : nullptr, md.Z.p));
+  if (!md.Q.diag) {
+    Qh.resize((size_t)r * r);
+    SS_TRY(fetch(Qh, hs ? hs->Q : nullptr, md.Q.p));
+  }
+  if (need_sync) SS_CUDA(cudaStreamSynchronize(st));
+  if (!md.Q.diag) {
+    qpat.resize((size_t)r * r);
+    for (size_t i = 0; i < qpat.size(); i++) qpat[i] = Qh[i] != 0.0;
+  }
+  BlkPlan pl;
+  const bool planned = plan_blocks(Th.data(), md.T.diag, Rh.data(), md.R.diag, qpat.empty() ? nullptr : qpat.data(), m, r,
+                                   &pl, &why);
+  if (!planned && applicable) {  // automatic dispatch: the caller moves on to the next kernel
+    *applicable = false;
+    return SSGPU_OK;
+  }
+  SS_ARG(planned, "block kernel not eligible: " + why);
+  BlkArgs A{};
+  A.md = md;
+  A.y = y;
+  A.B = B;
+  A.E = B * V;
+  A.out = out;
+  for (int i = 0; i < 2 * kBlkMaxNB; i++) A.perm[i] = pl.perm[i];
+  std::memcpy(A.Tb, pl.Tb, sizeof A.Tb);
+  for (int j = 0; j < p; j++)
+    for (int i = 0; i < 2 * kBlkMaxNB; i++) A.z[j][i] = pl.perm[i] >= 0 ? Zh[j + (size_t)pl.perm[i] * p] : 0.0;
+  const int L = blk_lanes(pl.nb), G = 32 / L, wpb = kBlkThreads / 32;
+  const long long blocks = (A.E + (long long)wpb * G - 1) / ((long long)wpb * G);
+  SS_ARG(blocks < (1LL << 31), "block kernel: batch too large for one launch");
+  const unsigned nblk = (unsigned)blocks;
+  switch (pl.nb) {
+    case 1: launch_blk_nb<1, 1>(A, nblk, st); break;
+    case 2: launch_blk_nb<2, 2>(A, nblk, st); break;
+    case 3: launch_blk_nb<4, 3>(A, nblk, st); break;
+    case 4: launch_blk_nb<4, 4>(A, nblk, st); break;
+    case 5: launch_blk_nb<8, 5>(A, nblk, st); break;
+    case 6: launch_blk_nb<8, 6>(A, nblk, st); break;
+    case 7: launch_blk_nb<8, 7>(A, nblk, st); break;
+    default: launch_blk_nb<8, 8>(A, nblk, st); break;
+  }
+  SS_CUDA(cudaGetLastError());
+  count_launch();
+  static thread_local char name[96];
+  snprintf(name, sizeof name, "loglik_blk_kernel<L=%d,NB=%d,flop_per_step=%d>", L, pl.nb, blk_flops_per_step(pl.nb, p));
+  set_last_kernel(name);
+  return SSGPU_OK;
+}
+
+}  // namespace ssgpu

@@ -50,7 +50,7 @@ SYMBOLS = ["ssgpu_version", "ssgpu_last_error", "ssgpu_set_device", "ssgpu_devic
            "ssgpu_FastSmootherC_dev", "ssgpu_ExtractComponentC_dev", "ssgpu_draw_layout_dev", "ssgpu_last_sim_kernel_ms",
            "ssgpu_loglik_grad_batch", "ssgpu_loglik_grad_batch_dev", "ssgpu_loglik_theta_batch_dev"]
 
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS, KERNEL_MMA, KERNEL_MMA_DENSE, KERNEL_WSM = 0, 1, 2, 3, 4, 5
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS, KERNEL_MMA, KERNEL_MMA_DENSE, KERNEL_WSM, KERNEL_BLK = 0, 1, 2, 3, 4, 5, 6
 
 
 def lib():

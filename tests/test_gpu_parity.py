@@ -190,10 +190,11 @@ def _bsm_batch(rng, B, N, V, missing):
 
 
 KERNEL_NAMES = {"mma": "loglik_mma_kernel<TT=2,tiles=0x9,", "mma_dense": "loglik_mma_kernel<TT=2,tiles=0xf,",
-                "cols": "loglik_cols", "generic": "fwd_generic"}
+                "cols": "loglik_cols", "generic": "fwd_generic", "blk": "loglik_blk_kernel<L=8,NB=7,",
+                "auto": "loglik_blk_kernel<L=8,NB=7,"}
 
 
-@pytest.mark.parametrize("kernel", ["mma", "mma_dense", "cols", "generic"])
+@pytest.mark.parametrize("kernel", ["mma", "mma_dense", "cols", "generic", "blk", "auto"])
 def test_batch_config5_shape(kernel):
     rng = np.random.default_rng(5)
     B, N, V = 70, 60, 3
@@ -234,6 +235,91 @@ def test_batch_every_state_dim(m):
         assert abs(cols[b] - want) <= tol, (m, b, cols[b], want)
 
 
+def _cycle(rho, lam, var):
+    """Stationary stochastic cycle (R/Components-Unobserved.R: cycle, damping rho < 1): a 2 x 2 block of T, proper
+    initial covariance var / (1 - rho^2) I."""
+    c, s = rho * math.cos(lam), rho * math.sin(lam)
+    return dict(Z=np.array([[1.0, 0.0]]), T=np.array([[c, s], [-s, c]]), R=np.eye(2), Q=var * np.eye(2), a=np.zeros(2),
+                P_inf=np.zeros((2, 2)), P_star=var / (1 - rho * rho) * np.eye(2))
+
+
+def _structural_models():
+    S = sysmat
+    return {
+        "level (m=2, 1 block)": S._combine(1, [[0.7]], [S.comp_local_level(0.3)]),
+        "level+slope (m=3, 2 blocks)": S._combine(1, [[0.7]], [S.comp_level_slope(0.3, 0.02)]),
+        "level+seasonal4 (m=5, 3 blocks)": S._combine(1, [[0.5]], [S.comp_local_level(0.2), S.comp_bsm_trig(4, 0.05)]),
+        "slope+seasonal7 (m=9, 5 blocks)": S._combine(1, [[0.5]], [S.comp_level_slope(0.2, 0.01), S.comp_bsm_trig(7, 0.05)]),
+        "slope+seasonal12 (m=14, 7 blocks)": S.bsm12(0.5 * np.log([1.0, 0.1, 0.01, 0.05])),
+        "slope+seasonal12+cycle (m=16, 8 blocks)": S._combine(
+            1, [[1.0]], [S.comp_level_slope(0.1, 0.01), S.comp_bsm_trig(12, 0.05), _cycle(0.9, 0.4, 0.3)]),
+    }
+
+
+@pytest.mark.parametrize("name", list(_structural_models()))
+def test_batch_blk_kernel(name):
+    """Block-row kernel (T block diagonal with blocks of at most 2 x 2 after re-ordering the states) at every lane
+    count, per-evaluation diagonal Q / P_star and a, exactly diffuse states, missing values (groups of one warp
+    leave the diffuse phase at different time points), against the oracle and the generic kernel."""
+    sm = _structural_models()[name]
+    rng = np.random.default_rng(len(name))
+    B, N, m = 37, 45, sm.m
+    y = np.stack([simulate_y(rng, sm, N, missing=0.12)[:, 0] for _ in range(B)], axis=1)      # (N, B)
+    y[:3, 5] = np.nan                                                   # a series that starts with missing values
+    scale = rng.uniform(0.5, 2.0, size=(B, 1))
+    Qd = np.diag(sm.Q[:, :, 0])[None, :] * scale
+    Pd = np.diag(sm.P_star)[None, :] * scale
+    ab = rng.normal(size=(B, m)) * 0.1
+    got = api.loglik_batch(y, sm, Q_diag=Qd, P_star_diag=Pd, a=ab, kernel="blk")
+    assert api.last_kernel().startswith("loglik_blk_kernel<"), api.last_kernel()
+    gen = api.loglik_batch(y, sm, Q_diag=Qd, P_star_diag=Pd, a=ab, kernel="generic")
+    auto = api.loglik_batch(y, sm, Q_diag=Qd, P_star_diag=Pd, a=ab)
+    assert api.last_kernel().startswith("loglik_blk_kernel<") and np.array_equal(auto, got)
+    for b in range(B):
+        smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=np.diag(Qd[b])[:, :, None], a=ab[b], P_inf=sm.P_inf,
+                            P_star=np.diag(Pd[b]))
+        yb = y[:, b:b + 1]
+        want = cport.LogLikC(yb, np.isnan(yb), *smb.args())
+        assert abs(got[b] - want) <= RTOL * max(1, abs(want)), (name, b, got[b], want)
+        assert abs(gen[b] - want) <= RTOL * max(1, abs(want)), (name, b, gen[b], want)
+
+
+def test_batch_blk_kernel_bivariate_dense_blocks():
+    """p = 2: two local levels with correlated disturbances.  T = diag(0, 0, 1, 1); R Q R' = blkdiag(H, Q_level) has
+    dense 2 x 2 blocks, which pairs the residuals and the levels; shared dense Q, per-series dense P_star and a."""
+    rng = np.random.default_rng(77)
+    H = np.array([[1.0, 0.3], [0.3, 0.5]])
+    Ql = np.array([[0.2, -0.05], [-0.05, 0.1]])
+    sm = sysmat.SysMat(Z=np.concatenate([np.eye(2), np.eye(2)], axis=1)[:, :, None],
+                       T=np.diag([0.0, 0.0, 1.0, 1.0])[:, :, None], R=np.eye(4)[:, :, None],
+                       Q=sysmat.block_diag(H, Ql)[:, :, None], a=np.zeros(4),
+                       P_inf=np.diag([0.0, 0.0, 1.0, 1.0]), P_star=sysmat.block_diag(H, np.zeros((2, 2))))
+    B, N = 21, 40
+    y = np.stack([simulate_y(rng, sm, N, missing=0.15) for _ in range(B)], axis=2)            # (N, 2, B)
+    Pb = np.stack([sm.P_star * (1 + 0.05 * b) for b in range(B)])
+    ab = rng.normal(size=(B, 4)) * 0.1
+    got = api.loglik_batch(y, sm, P_star=Pb, a=ab, kernel="blk")
+    assert api.last_kernel().startswith("loglik_blk_kernel<L=2,NB=2,"), api.last_kernel()
+    for b in range(B):
+        smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=sm.Q, a=ab[b], P_inf=sm.P_inf, P_star=Pb[b])
+        yb = y[:, :, b]
+        want = cport.LogLikC(yb, np.isnan(yb), *smb.args())
+        assert abs(got[b] - want) <= RTOL * max(1, abs(want)), (b, got[b], want)
+
+
+def test_batch_blk_kernel_not_eligible():
+    """A transition matrix that couples a state with two others (SARIMA companion block, dense T) is refused by
+    the explicit selector and passed on by the automatic dispatch."""
+    rng = np.random.default_rng(3)
+    sm = random_model(rng, 6, 1, d=1, N=20, dense_q=False)
+    y = np.stack([simulate_y(rng, sm, 20)[:, 0] for _ in range(4)], axis=1)
+    with pytest.raises(RuntimeError, match="block kernel not eligible"):
+        api.loglik_batch(y, sm, kernel="blk")
+    auto = api.loglik_batch(y, sm)
+    assert not api.last_kernel().startswith("loglik_blk")
+    assert np.all(np.isfinite(auto))
+
+
 BSM_Q_INDEX = [0, 1, 2] + [3] * 11       # config 5: Q = diag(s2_eps, s2_level, s2_slope, s2_seas x 11)
 BSM_P_INDEX = [0] + [-1] * 13            # P_star = diag(s2_eps, 0, ...)
 
@@ -248,7 +334,7 @@ def test_loglik_grad_batch_from_theta():
     theta = thetas[0]                                                   # (B, 4)
     sm0 = sysmat.bsm12(theta[0])
     ll, gr = api.loglik_grad_batch(y, sm0, theta, BSM_Q_INDEX, BSM_P_INDEX, h=h)
-    assert api.last_kernel().startswith("loglik_mma")
+    assert api.last_kernel().startswith("loglik_blk")
     for b in range(0, B, 5):
         yb = y[:, b:b + 1]
         f = lambda th: cport.LogLikC(yb, np.isnan(yb), *sysmat.bsm12(th).args())
