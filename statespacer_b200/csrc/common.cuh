@@ -232,6 +232,7 @@ struct HostShared {  // optional host copies of the shared, time-invariant matri
 };
 struct BlkPlan {
   int nb;                // number of 2 x 2 blocks (a lone state is padded with an empty partner)
+  int q_offdiag;         // R Q R' has off-diagonal entries inside the blocks
   signed char perm[16];  // internal position 2I+e holds state perm[2I+e] of the caller, -1 = padding
   double Tb[8][4];       // T_J[row][col] at [2*row + col]
 };

@@ -29,6 +29,9 @@
 
 namespace ssgpu {
 
+#ifndef SSGPU_BLK_MINB
+#define SSGPU_BLK_MINB 2  // resident CTAs per SM the register budget is sized for (2: 255 registers, 3: 168, 4: 128)
+#endif
 constexpr int kBlkThreads = 128;
 constexpr int kBlkMaxNB = 8;
 constexpr int kBlkMaxP = 8;
@@ -54,8 +57,9 @@ __device__ __forceinline__ double blk_rcp(double x) {
   return fma(r, e, r);
 }
 
-template <int L, int NB, bool P1, int MINB>
-__global__ void __launch_bounds__(kBlkThreads, MINB) loglik_blk_kernel(const BlkArgs A) {
+// QOFF: the diagonal blocks of R Q R' have off-diagonal entries (correlated disturbances of a multivariate model)
+template <int L, int NB, bool P1, bool QOFF>
+__global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel(const BlkArgs A) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int G = 32 / L;  // evaluations per warp
   const DModel& md = A.md;
@@ -64,16 +68,6 @@ __global__ void __launch_bounds__(kBlkThreads, MINB) loglik_blk_kernel(const Blk
   const int I = lane % L, g = lane / L;
   // evaluations are numbered series-major (w = b*V + v) so that the V parameter vectors of a series run side by
   // side and share its y through L1/L2; results keep the public order e = v*B + b
-  // T_J and the rows of Z are the same for every evaluation.  They are read from shared memory (broadcast 16-byte
-  // loads) rather than from the parameter bank: ptxas hoists constant-bank operands of a loop this size into
-  // uniform registers, runs out of them and spills (measured: 300 extra instructions per step).
-  __shared__ double2 tb_s[kBlkMaxNB][2];       // [J][c] = (T_J[c][0], T_J[c][1])
-  __shared__ double2 z_s[kBlkMaxP][kBlkMaxNB]; // [j][J] = (z[2J], z[2J+1])
-  for (int e = threadIdx.x; e < kBlkMaxNB * 2; e += kBlkThreads)
-    tb_s[e >> 1][e & 1] = make_double2(A.Tb[e >> 1][2 * (e & 1)], A.Tb[e >> 1][2 * (e & 1) + 1]);
-  for (int e = threadIdx.x; e < p * kBlkMaxNB; e += kBlkThreads)
-    z_s[e / kBlkMaxNB][e % kBlkMaxNB] = make_double2(A.z[e / kBlkMaxNB][2 * (e % kBlkMaxNB)], A.z[e / kBlkMaxNB][2 * (e % kBlkMaxNB) + 1]);
-  __syncthreads();
   const long long w0 = ((long long)blockIdx.x * (kBlkThreads / 32) + warp) * G;
   if (w0 >= A.E) return;  // whole warp
   // every lane stays alive (shuffles, __syncwarp): groups beyond the last evaluation shadow it and do not store
@@ -115,7 +109,7 @@ __global__ void __launch_bounds__(kBlkThreads, MINB) loglik_blk_kernel(const Blk
     a0 = i0 >= 0 ? ab[i0] : 0.0;
     a1 = i1 >= 0 ? ab[i1] : 0.0;
   }
-  const double t00 = tb_s[I][0].x, t01 = tb_s[I][0].y, t10 = tb_s[I][1].x, t11 = tb_s[I][1].y;  // zero beyond NB
+  const double t00 = A.Tb[I][0], t01 = A.Tb[I][1], t10 = A.Tb[I][2], t11 = A.Tb[I][3];  // zero beyond NB
   // (R Q R')[i][c] for the own diagonal block (src/LogLikC.cpp:202, hoisted: Q and R are time-invariant here; the
   // host has checked that R Q R' has no entry outside the diagonal blocks)
   double q0, q1, q2, q3;
@@ -167,16 +161,40 @@ __global__ void __launch_bounds__(kBlkThreads, MINB) loglik_blk_kernel(const Blk
     prod = __hiloint2double(hi - (ex << 20), __double2loint(prod));
   };
 
-  // P_IJ <- T_I P_IJ T_J' (+ the own diagonal block of R Q R' when J == I); X[r][c] = sum_k Y[r][k] T_J[c][k]
+  // T_J (and z when p = 1) are the same for every evaluation.  They are kept in VECTOR registers for the whole
+  // kernel (4 NB + 2 NB doubles; the kernel is sized for 2 CTAs per SM, 255 registers), loaded once through an index
+  // that ptxas cannot prove warp-uniform (`lz` is always 0 but derives from the per-lane evaluation number).
+  // What was measured on the way (config 5, one B200):
+  //   constants in shared memory, 16-byte broadcast loads: an LDS.128 costs ~3 LSU wavefronts even when every lane
+  //     reads the same address; LSU pipe 77 % busy, FP64 pipe 58 %, 167 ms per sweep;
+  //   constants through the uniform datapath (LDCU -> uniform-register operand): left loop-invariant, ptxas hoists
+  //     all 42 of a step, runs out of uniform registers and spills them (300 extra instructions per step); made
+  //     loop-variant, it funnels every constant through ONE uniform register pair, LDCU / 2 DFMA / LDCU ..., each
+  //     load's latency exposed (IDC 56 % busy, `short_scoreboard` the top stall), FP64 pipe 60 %, 162 ms.
+  const int lz = (int)(w_id >> 62);
+  double TJ[NB][4], ZJ[NB][2];
+  {
+    const double* tbp = &A.Tb[0][0] + lz;
+    const double* zp = &A.z[0][0] + lz;
+#pragma unroll
+    for (int J = 0; J < NB; J++) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) TJ[J][k] = tbp[J * 4 + k];
+      ZJ[J][0] = P1 ? zp[2 * J] : 0.0;
+      ZJ[J][1] = P1 ? zp[2 * J + 1] : 0.0;
+    }
+  }
+  // P_IJ <- T_I P_IJ T_J' (+ the own diagonal block of R Q R' when J == I); X[r][c] = sum_k Y[r][k] T_J[c][k].
+  // The selected addends (dg ? q : 0) are loop-invariant and hoisted by the compiler: 2 NB doubles when R Q R' is
+  // diagonal (QOFF = false).
   auto time_block = [&](int J, double& p0, double& p1, double& p2, double& p3, bool with_q) {
     const double y00 = fma(t01, p2, t00 * p0), y01 = fma(t01, p3, t00 * p1);
     const double y10 = fma(t11, p2, t10 * p0), y11 = fma(t11, p3, t10 * p1);
     const bool dg = with_q && J == I;
-    const double2 tc0 = tb_s[J][0], tc1 = tb_s[J][1];
-    p0 = fma(y01, tc0.y, fma(y00, tc0.x, dg ? q0 : 0.0));
-    p1 = fma(y01, tc1.y, fma(y00, tc1.x, dg ? q1 : 0.0));
-    p2 = fma(y11, tc0.y, fma(y10, tc0.x, dg ? q2 : 0.0));
-    p3 = fma(y11, tc1.y, fma(y10, tc1.x, dg ? q3 : 0.0));
+    p0 = fma(y01, TJ[J][1], fma(y00, TJ[J][0], dg ? q0 : 0.0));
+    p1 = fma(y01, TJ[J][3], fma(y00, TJ[J][2], (QOFF && dg) ? q1 : 0.0));
+    p2 = fma(y11, TJ[J][1], fma(y10, TJ[J][0], (QOFF && dg) ? q2 : 0.0));
+    p3 = fma(y11, TJ[J][3], fma(y10, TJ[J][2], dg ? q3 : 0.0));
   };
 
   const long long Np = (long long)N * p;
@@ -193,11 +211,11 @@ __global__ void __launch_bounds__(kBlkThreads, MINB) loglik_blk_kernel(const Blk
       for (int j = 0; j < p; j++) {
         const double yv = A.y[((long long)t * p + j) * A.B + b];
         const bool obs = !isnan(yv);  // :88-90
-        const double zi0 = z_s[j][I].x, zi1 = z_s[j][I].y;
+        const double zi0 = A.z[j][2 * I], zi1 = A.z[j][2 * I + 1];
         double ms0 = 0.0, ms1 = 0.0, mi0 = 0.0, mi1 = 0.0;
 #pragma unroll
         for (int J = 0; J < NB; J++) {
-          const double z0 = z_s[j][J].x, z1 = z_s[j][J].y;
+          const double z0 = A.z[j][2 * J], z1 = A.z[j][2 * J + 1];
           ms0 = fma(P[J][1], z1, fma(P[J][0], z0, ms0));
           ms1 = fma(P[J][3], z1, fma(P[J][2], z0, ms1));
           mi0 = fma(pinf[J * 4 + 1][tx], z1, fma(pinf[J * 4 + 0][tx], z0, mi0));
@@ -274,21 +292,90 @@ __global__ void __launch_bounds__(kBlkThreads, MINB) loglik_blk_kernel(const Blk
 
   // ---- regular phase: the hot loop (src/LogLikC.cpp:162-207), branch-free ------------------------------------
   // A missing observation or F < 1e-7 (:88-90, :173-176) makes the update a no-op through 1/F := v := 0.
-  if (t < N) {
+  // loglik terms of one observation; returns 1/F and v of the update (both 0 for a no-op)
+  double F1, vv;
+  auto observe = [&](double yv, double F_star, double za) {
+    const bool obs = !isnan(yv);
+    const bool upd = obs && !(F_star < kEps);
+    F1 = upd ? blk_rcp(F_star) : 0.0;
+    vv = upd ? yv - za : 0.0;
+    acc_log(upd ? F_star : 1.0);
+    n_terms += upd;
+    non_init += obs;
+    F_eq0 += obs && !upd;
+    sumq = fma(vv * vv, F1, sumq);
+  };
+  if constexpr (P1) {
+    // p = 1: the time update does not wait for 1/F.  With M = P z, k = M / F:
+    //     T (P - k M') T' + RQR'  =  (T P T' + RQR')  -  (T M)(T M)' / F,        T (a + k v) = T a + (T M) v / F,
+    // so the 16 NB multiply-adds of T P T' are issued while F = z'M travels through the butterfly and the
+    // reciprocal; lane I publishes T_I M_I instead of M_I and the rank-1 correction comes last.  (At 2 warps per
+    // sub-partition the FP64 pipe otherwise idles through that chain: 148 ms per sweep of config 5 before, see
+    // profiles/README.md.)
+    if (t < N) {
+      const double zi0 = A.z[0][2 * I], zi1 = A.z[0][2 * I + 1];
+      double ynext = A.y[(long long)t * A.B + b];  // observations are fetched one step ahead of their use
+      // M_I = sum_J P_IJ z_J (two chains per row), F = z'M and z'a over the group
+      double m0, m1, F_star, za;
+      auto innovation = [&]() {
+        double m0a = 0.0, m0b = 0.0, m1a = 0.0, m1b = 0.0;
+#pragma unroll
+        for (int J = 0; J < NB; J++) {
+          m0a = fma(P[J][0], ZJ[J][0], m0a);
+          m0b = fma(P[J][1], ZJ[J][1], m0b);
+          m1a = fma(P[J][2], ZJ[J][0], m1a);
+          m1b = fma(P[J][3], ZJ[J][1], m1b);
+        }
+        m0 = m0a + m0b;
+        m1 = m1a + m1b;
+      };
+      for (; t < N - 1; t++) {  // one straight-line block per step: no branch between the butterfly and the products
+        const double yv = ynext;
+        ynext = A.y[(long long)(t + 1) * A.B + b];
+        innovation();
+        const double tm0 = fma(t01, m1, t00 * m0), tm1 = fma(t11, m1, t10 * m0);  // (T M)_I
+        if (own) xch[buf][I][g] = make_double2(tm0, tm1);
+        F_star = group_sum(fma(zi1, m1, zi0 * m0));
+        za = group_sum(fma(zi1, a1, zi0 * a0));
+        __syncwarp();
+#pragma unroll
+        for (int J = 0; J < NB; J++) time_block(J, P[J][0], P[J][1], P[J][2], P[J][3], true);
+        const double ta0 = fma(t01, a1, t00 * a0), ta1 = fma(t11, a1, t10 * a0);
+        observe(yv, F_star, za);
+        const double g0 = tm0 * F1, g1 = tm1 * F1;
+#pragma unroll
+        for (int J = 0; J < NB; J++) {
+          const double2 mJ = xch[buf][J][g];  // (T M)_J
+          P[J][0] = fma(-g0, mJ.x, P[J][0]);
+          P[J][1] = fma(-g0, mJ.y, P[J][1]);
+          P[J][2] = fma(-g1, mJ.x, P[J][2]);
+          P[J][3] = fma(-g1, mJ.y, P[J][3]);
+        }
+        buf ^= 1;
+        a0 = fma(g0, vv, ta0);
+        a1 = fma(g1, vv, ta1);
+      }
+      // the last observation (:200 -- P and a are not needed afterwards)
+      innovation();
+      F_star = group_sum(fma(zi1, m1, zi0 * m0));
+      za = group_sum(fma(zi1, a1, zi0 * a0));
+      observe(ynext, F_star, za);
+    }
+  } else if (t < N) {
     long long idx = (long long)t * p;
     double ynext = A.y[idx * A.B + b];  // observations are fetched one univariate step ahead of their use
     for (; t < N; t++) {
+      const int zo = t >> 30;  // z from the parameter bank; always 0 (N < 2^30), but loop-variant: no hoisting
 #pragma unroll 1
       for (int j = 0; j < p; j++, idx++) {
         const double yv = ynext;
         if (idx + 1 < Np) ynext = A.y[(idx + 1) * A.B + b];
-        const double zi0 = z_s[j][I].x, zi1 = z_s[j][I].y;
-        // M_I = sum_J P_IJ z_J: two chains per row
+        const double* zp = &A.z[0][0] + zo + j * (2 * kBlkMaxNB);
+        const double zi0 = A.z[j][2 * I], zi1 = A.z[j][2 * I + 1];  // own part: a per-lane address, kept apart from zo
         double m0a = 0.0, m0b = 0.0, m1a = 0.0, m1b = 0.0;
 #pragma unroll
         for (int J = 0; J < NB; J++) {
-          const double2 zJ = z_s[j][J];
-          const double z0 = zJ.x, z1 = zJ.y;
+          const double z0 = zp[2 * J], z1 = zp[2 * J + 1];
           m0a = fma(P[J][0], z0, m0a);
           m0b = fma(P[J][1], z1, m0b);
           m1a = fma(P[J][2], z0, m1a);
@@ -299,15 +386,7 @@ __global__ void __launch_bounds__(kBlkThreads, MINB) loglik_blk_kernel(const Blk
         const double F_star = group_sum(fma(zi1, m1, zi0 * m0));
         const double za = group_sum(fma(zi1, a1, zi0 * a0));
         __syncwarp();
-        const bool obs = !isnan(yv);
-        const bool upd = obs && !(F_star < kEps);
-        const double F1 = upd ? blk_rcp(F_star) : 0.0;
-        const double vv = upd ? yv - za : 0.0;
-        acc_log(upd ? F_star : 1.0);
-        n_terms += upd;
-        non_init += obs;
-        F_eq0 += obs && !upd;
-        sumq = fma(vv * vv, F1, sumq);
+        observe(yv, F_star, za);
         const double k0 = m0 * F1, k1 = m1 * F1;
 #pragma unroll
         for (int J = 0; J < NB; J++) {
@@ -353,6 +432,7 @@ bool plan_blocks(const double* Th, int t_diag, const double* Rh, int r_diag, con
     return false;
   };
   std::vector<int> partner(m, -1);
+  bool q_off = false;
   auto couple = [&](int i, int k) {
     if (i == k) return true;
     if (partner[i] == k && partner[k] == i) return true;
@@ -377,6 +457,7 @@ bool plan_blocks(const double* Th, int t_diag, const double* Rh, int r_diag, con
         }
       }
       if (nz && !couple(i, c)) return no("R Q R' couples a state with two others");
+      q_off = q_off || nz;
     }
   int nb = 0;
   std::memset(pl, 0, sizeof *pl);
@@ -402,6 +483,7 @@ bool plan_blocks(const double* Th, int t_diag, const double* Rh, int r_diag, con
   }
   if (pend >= 0 && !put(pend, -1)) return no("more than 8 blocks");
   pl->nb = nb;
+  pl->q_offdiag = q_off ? 1 : 0;
   for (int J = 0; J < nb; J++)
     for (int rr = 0; rr < 2; rr++)
       for (int cc = 0; cc < 2; cc++) {
@@ -424,25 +506,19 @@ bool blk_eligible(const DModel& md, std::string* why) {
   return true;
 }
 
-template <int L, int NB, int MINB>
-static void launch_blk_mb(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
-  if (A.md.p == 1)
-    loglik_blk_kernel<L, NB, true, MINB><<<blocks, kBlkThreads, 0, st>>>(A);
-  else
-    loglik_blk_kernel<L, NB, false, MINB><<<blocks, kBlkThreads, 0, st>>>(A);
-}
-
 template <int L, int NB>
-static void launch_blk_nb(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
-  // resident CTAs per SM the register budget is sized for (tuning knob): 4 = 128 registers, 3 = 168
-  static const int minb = [] {
-    const char* e = getenv("SSGPU_BLK_MINB");
-    return e ? atoi(e) : 4;
-  }();
-  if (L == 8 && minb <= 3)
-    launch_blk_mb<L, NB, (L == 8 ? 3 : 4)>(A, blocks, st);
-  else
-    launch_blk_mb<L, NB, 4>(A, blocks, st);
+static void launch_blk_nb(const BlkArgs& A, bool q_offdiag, unsigned blocks, cudaStream_t st) {
+  if (A.md.p == 1) {
+    if (q_offdiag)
+      loglik_blk_kernel<L, NB, true, true><<<blocks, kBlkThreads, 0, st>>>(A);
+    else
+      loglik_blk_kernel<L, NB, true, false><<<blocks, kBlkThreads, 0, st>>>(A);
+  } else {
+    if (q_offdiag)
+      loglik_blk_kernel<L, NB, false, true><<<blocks, kBlkThreads, 0, st>>>(A);
+    else
+      loglik_blk_kernel<L, NB, false, false><<<blocks, kBlkThreads, 0, st>>>(A);
+  }
 }
 
 int blk_lanes(int nb) { return nb > 4 ? 8 : nb > 2 ? 4 : nb > 1 ? 2 : 1; }
@@ -454,7 +530,8 @@ int blk_flops_per_step(int nb, int p) {
   while ((1 << lg) < L) lg++;
   const int fma_obs = 4 * nb + 2 + 4 + 4 * nb + 2 + 1, mul_obs = 2 + 2 + 3, add_obs = 2 + 2 * lg;
   const int fma_t = 12 * nb + 2, mul_t = 4 * nb + 2;
-  return L * (p * (2 * fma_obs + mul_obs + add_obs) + 2 * fma_t + mul_t);
+  const int tm = p == 1 ? 2 * 2 + 2 : 0;  // p = 1: (T M)_I
+  return L * (p * (2 * fma_obs + mul_obs + add_obs) + 2 * fma_t + mul_t + tm);
 }
 
 int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
@@ -511,14 +588,14 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
   SS_ARG(blocks < (1LL << 31), "block kernel: batch too large for one launch");
   const unsigned nblk = (unsigned)blocks;
   switch (pl.nb) {
-    case 1: launch_blk_nb<1, 1>(A, nblk, st); break;
-    case 2: launch_blk_nb<2, 2>(A, nblk, st); break;
-    case 3: launch_blk_nb<4, 3>(A, nblk, st); break;
-    case 4: launch_blk_nb<4, 4>(A, nblk, st); break;
-    case 5: launch_blk_nb<8, 5>(A, nblk, st); break;
-    case 6: launch_blk_nb<8, 6>(A, nblk, st); break;
-    case 7: launch_blk_nb<8, 7>(A, nblk, st); break;
-    default: launch_blk_nb<8, 8>(A, nblk, st); break;
+    case 1: launch_blk_nb<1, 1>(A, pl.q_offdiag != 0, nblk, st); break;
+    case 2: launch_blk_nb<2, 2>(A, pl.q_offdiag != 0, nblk, st); break;
+    case 3: launch_blk_nb<4, 3>(A, pl.q_offdiag != 0, nblk, st); break;
+    case 4: launch_blk_nb<4, 4>(A, pl.q_offdiag != 0, nblk, st); break;
+    case 5: launch_blk_nb<8, 5>(A, pl.q_offdiag != 0, nblk, st); break;
+    case 6: launch_blk_nb<8, 6>(A, pl.q_offdiag != 0, nblk, st); break;
+    case 7: launch_blk_nb<8, 7>(A, pl.q_offdiag != 0, nblk, st); break;
+    default: launch_blk_nb<8, 8>(A, pl.q_offdiag != 0, nblk, st); break;
   }
   SS_CUDA(cudaGetLastError());
   count_launch();
