@@ -314,7 +314,10 @@ __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel
     // profiles/README.md.)
     if (t < N) {
       const double zi0 = A.z[0][2 * I], zi1 = A.z[0][2 * I + 1];
-      double ynext = A.y[(long long)t * A.B + b];  // observations are fetched one step ahead of their use
+      // observations are fetched two steps ahead of their use (one step, 600 cycles at 2 warps per sub-partition,
+      // does not always cover a DRAM miss: 2.4 % of the stall samples sat on this load)
+      double ynext = A.y[(long long)t * A.B + b];
+      double ynext2 = t + 1 < N ? A.y[(long long)(t + 1) * A.B + b] : 0.0;
       // M_I = sum_J P_IJ z_J (two chains per row), F = z'M and z'a over the group
       double m0, m1, F_star, za;
       auto innovation = [&]() {
@@ -331,7 +334,8 @@ __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel
       };
       for (; t < N - 1; t++) {  // one straight-line block per step: no branch between the butterfly and the products
         const double yv = ynext;
-        ynext = A.y[(long long)(t + 1) * A.B + b];
+        ynext = ynext2;
+        if (t + 2 < N) ynext2 = A.y[(long long)(t + 2) * A.B + b];
         innovation();
         const double tm0 = fma(t01, m1, t00 * m0), tm1 = fma(t11, m1, t10 * m0);  // (T M)_I
         if (own) xch[buf][I][g] = make_double2(tm0, tm1);
