@@ -62,7 +62,9 @@ SCALAR_FLOPS_PER_STEP = (23 * 2 + 11 + 4) * 32
 # dram__bytes_read.sum + dram__bytes_write.sum of one loglik_mma_kernel launch at the default size (125,000 series x 9
 # parameter vectors x 1000 steps), from the `ncu --set full` capture summarised in
 # profiles/ncu_mma_r1_fullsize_summary.csv (1.289 GB + 21.2 MB); algorithmic: y 1.0 GB + variance sets 0.252 GB + out
-NCU_TRAFFIC_BYTES = {("loglik_mma_kernel<TT=2,tiles=0x9,dmma_per_step=14>", 125_000): 1.289423e9 + 21.163008e6}
+NCU_TRAFFIC_BYTES = {("loglik_mma_kernel<TT=2,tiles=0x9,dmma_per_step=14>", 125_000): 1.289423e9 + 21.163008e6,
+                     # profiles/ncu_blk_r1_fullsize_summary.csv
+                     ("loglik_blk_kernel<L=8,NB=7,flop_per_step=2824>", 125_000): 1.269807e9 + 16.314624e6}
 
 
 def executed_flops(kernel_name):

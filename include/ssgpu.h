@@ -223,6 +223,42 @@ int ssgpu_draw_layout_dev(const double* src, double* dst, int N, int K, long lon
  * this process launched; -1 if none yet.  Waits for that kernel. */
 int ssgpu_last_sim_kernel_ms(double* simulate_ms, double* fast_smoother_ms, double* extract_ms);
 
+/* ---- 6d. SimSmoother as one call (new) ---------------------------------------------------------
+ * R/SimSmoother.R:34-769 draws every component of the model unconditionally with SimulateC, adds the draws up to
+ * simulated data, smooths those with FastSmootherC, corrects the draws by the difference to the smoothed estimates of
+ * the observed data and extracts the components -- five .Call round trips per component through N x m x nsim host
+ * arrays.  Here the whole function is one call: only the normal variates go in and only what SimSmoother() returns
+ * comes out; the per-draw arrays never leave the device.
+ *   comps[c]        one SimulateC call of R/SimSmoother.R:65-553 (arguments as for ssgpu_SimulateC; R has
+ *                   r*repeat_Q columns); their states / disturbances are stacked in this order
+ *   H               p x p x nH residual variance (the Q of the eta_only call, :556-573)
+ *   full            the model FastSmootherC runs on (:579-632): residual states first, m = p + sum m_c, r = p + sum r_c
+ *   a_hat N x m, eps_hat N x p, eta_hat N x r   object$smoothed$a / $epsilon / $eta (column-major)
+ *   draws           standard normal variates in the order the reference consumes them: per component
+ *                   [m_c*nsim if draw_initial] then N*r_tot_c*nsim, and N*p*nsim for the residuals last
+ *   epsilon N x p x nsim, a N x m x nsim, eta N x r x nsim   results (any may be NULL)
+ *   Z_extract[e] p x m x nZ_extract[e]  ->  extracted[e] N x p x nsim   (the Z_padded matrices of :645-766)
+ * Arithmetic is that of the three routines (bit-identical to calling them in R's order). */
+typedef struct ssgpu_sim_component {
+  int m, r, repeat_Q, draw_initial;
+  const double *a, *Z, *T, *R, *Q, *P_star;   /* Z p x m x nZ, T m x m x nT, R m x (r*repeat_Q) x nR, Q r x r x nQ, P_star m x m */
+  int nZ, nT, nR, nQ;
+  const double *Q_root, *P_root;              /* optional precomputed symmetric roots (NULL: computed on the host) */
+} ssgpu_sim_component;
+
+typedef struct ssgpu_sim_model {
+  int m, r;
+  const double *a, *P_inf, *P_star, *Z, *T, *R, *Q;
+  int nZ, nT, nR, nQ;
+} ssgpu_sim_model;
+
+int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu_sim_component* comps,
+                      const double* H, int nH, const ssgpu_sim_model* full, int initialisation_steps,
+                      const double* a_hat, const double* eps_hat, const double* eta_hat,
+                      const double* draws, long long n_draws,
+                      double* epsilon, double* a_out, double* eta,
+                      int n_extract, const double* const* Z_extract, const int* nZ_extract, double* const* extracted);
+
 /* Host-only helper (no device needed): the internal state order the tensor kernel would use for a shared
  * m x m transition matrix T (column-major, m <= 23).  perm[i] = caller's index of the state at internal
  * position i; *tile_mask has bit rt*TT + ct set when the 8 x 8 tile (rt, ct) of the re-ordered T holds a

@@ -205,6 +205,66 @@ def ExtractComponentC(a, Z):
     return out
 
 
+def SimSmoother(nsim, N, p, comps, H, full, initialisation_steps, a_hat, eps_hat, eta_hat, draws, extract=(), roots=None):
+    """R/SimSmoother.R:34-769 as one call (include/ssgpu.h section 6d): the unconditional draws of every component,
+    the simulated data, their smoothed states, the mean corrections and the extracted components without the per-draw
+    arrays leaving the device.  Arguments as oracle/sim_smoother.py (comps: dicts a, Z, T, R, Q, P_star, repeat_Q,
+    draw_initial; full: (a, P_inf, P_star, Z, T, R, Q) with the residual states in front; draws in the reference's
+    consumption order).  Returns epsilon (N, p, nsim), a (N, m, nsim), eta (N, r, nsim), components [(N, p, nsim)]."""
+    keep = []
+
+    def hold(x):
+        keep.append(x)
+        return _ptr(x)
+
+    roots = roots or [{} for _ in range(len(comps) + 1)]
+    if roots[len(comps)]:
+        raise ValueError("roots of the residual variance cannot be injected")
+    arr = (native.SimComponent * len(comps))()
+    m = r = 0
+    for i, (c, rt) in enumerate(zip(comps, roots)):
+        a = _f(np.asarray(c["a"], dtype=np.float64).reshape(-1))
+        Z, T, R, Q = _cube(c["Z"], "Z"), _cube(c["T"], "T"), _cube(c["R"], "R"), _cube(c["Q"], "Q")
+        P_star = _f(np.atleast_2d(c["P_star"]))
+        if c["draw_initial"] and P_star.shape[0] != a.shape[0]:
+            raise ValueError("draw_initial needs an m x m P_star")
+        if Z.shape[0] != p or R.shape[1] != Q.shape[0] * c["repeat_Q"]:
+            raise ValueError("component matrices do not match")
+        Q_root = None if rt.get("Q_root") is None else _cube(rt["Q_root"], "Q_root")
+        P_root = None if rt.get("P_root") is None else _f(rt["P_root"])
+        arr[i] = native.SimComponent(a.shape[0], Q.shape[0], int(c["repeat_Q"]), int(bool(c["draw_initial"])), hold(a),
+                                     hold(Z), hold(T), hold(R), hold(Q), hold(P_star), Z.shape[2], T.shape[2],
+                                     R.shape[2], Q.shape[2], hold(Q_root) if Q_root is not None else None,
+                                     hold(P_root) if P_root is not None else None)
+        m += a.shape[0]
+        r += Q.shape[0] * int(c["repeat_Q"])
+    fa, fPi, fPs, fZ, fT, fR, fQ = full
+    fa = _f(np.asarray(fa, dtype=np.float64).reshape(-1))
+    fPi, fPs = _f(fPi), _f(fPs)
+    fZ, fT, fR, fQ = _cube(fZ, "Z"), _cube(fT, "T"), _cube(fR, "R"), _cube(fQ, "Q")
+    fm = native.SimModel(fa.shape[0], fQ.shape[0], hold(fa), hold(fPi), hold(fPs), hold(fZ), hold(fT), hold(fR), hold(fQ),
+                         fZ.shape[2], fT.shape[2], fR.shape[2], fQ.shape[2])
+    H = _cube(H, "H")
+    a_hat, eps_hat, eta_hat = _f(a_hat), _f(eps_hat), _f(eta_hat)
+    if a_hat.shape != (N, m) or eps_hat.shape != (N, p) or eta_hat.shape != (N, r):
+        raise ValueError("smoothed estimates must be N x m, N x p, N x r")
+    draws = np.ascontiguousarray(draws, dtype=np.float64).reshape(-1)
+    eps = np.zeros((N, p, nsim), order="F")
+    a_out = np.zeros((N, m, nsim), order="F")
+    eta = np.zeros((N, r, nsim), order="F")
+    ne = len(extract)
+    Zs = [_cube(Z, "Z_padded") for Z in extract]
+    outs = [np.zeros((N, p, nsim), order="F") for _ in extract]
+    zp = (C.c_void_p * max(ne, 1))(*[_ptr(Z) for Z in Zs])
+    nz = (C.c_int * max(ne, 1))(*[Z.shape[2] for Z in Zs])
+    op = (C.c_void_p * max(ne, 1))(*[_ptr(o) for o in outs])
+    native.check(native.lib().ssgpu_SimSmoother(
+        int(nsim), int(N), int(p), len(comps), arr, _ptr(H), H.shape[2], C.byref(fm), int(initialisation_steps),
+        _ptr(a_hat), _ptr(eps_hat), _ptr(eta_hat), _ptr(draws), draws.shape[0], _ptr(eps), _ptr(a_out), _ptr(eta),
+        ne, zp, nz, op))
+    return {"epsilon": eps, "a": a_out, "eta": eta, "components": outs}
+
+
 # ---- simulation smoother on device-resident draws (torch CUDA float64 tensors, draw-contiguous layout) -----
 def _stream_handle(stream):
     import torch

@@ -247,13 +247,18 @@ static int check_sim(int nsim, int repeat_Q, int N, int p, int m, int rR, int r,
   return SSGPU_OK;
 }
 
+// placement of one component's outputs inside the stacked arrays of the whole model (SimArgs, common.cuh)
+struct SimPlace {
+  int a_ld, a_off, eta_ld, eta_off, y_acc;
+};
+
 // SimulateC on device-resident variates (reference order) writing the draw-contiguous layout; yN / aN / eN may be
 // null.  System matrices are host pointers.
 static int simulate_core(int nsim, int repeat_Q, int N, int p, int m, int rR, int r, const double* a, const double* Z,
                          int nZ, const double* T, int nT, const double* R, int nR, const double* Q, int nQ,
                          const double* P_star, int draw_initial, int eta_only, const double* draws_dev,
                          const double* Q_root, const double* P_root, double* yN, double* aN, double* eN,
-                         cudaStream_t st) {
+                         cudaStream_t st, const SimPlace* place = nullptr) {
   const size_t ns = (size_t)nsim;
   const size_t n_init = draw_initial ? (size_t)m * ns : 0;
   // symmetric roots (host, once) unless supplied
@@ -312,8 +317,14 @@ static int simulate_core(int nsim, int repeat_Q, int N, int p, int m, int rR, in
     A.Re = ep.at(er, elli.as<int>(), ellv.as<double>());
     A.y = yN;
     A.a = aN;
+  } else {
+    A.y = yN;  // residuals: y += eta (R/SimSmoother.R:575-576), null otherwise
   }
   A.eta = eN;
+  if (place) {
+    A.a_ld = place->a_ld; A.a_off = place->a_off; A.eta_ld = place->eta_ld; A.eta_off = place->eta_off;
+    A.y_acc = place->y_acc;
+  }
   SS_TRY(launch_simulate(A, st));
   SS_CUDA(cudaStreamSynchronize(st));  // host staging vectors die with this frame
   return SSGPU_OK;
@@ -378,6 +389,104 @@ extern "C" int ssgpu_SimulateC(int nsim, int repeat_Q, int N, int p, int m, int 
     }
   }
   SS_CUDA(cudaStreamSynchronize(st));
+  return SSGPU_OK;
+}
+
+// ---- SimSmoother as one call (R/SimSmoother.R:34-769) ----------------------------------------------------------
+// Everything between the variates and the returned arrays stays on the device: the component draws land directly in
+// the stacked arrays of the whole model, y is accumulated in place, the smoother runs on it, the mean correction and
+// the component extraction read the same buffers; only epsilon / a / eta / the extracted components cross PCIe.
+extern "C" int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu_sim_component* comps, const double* H,
+                                 int nH, const ssgpu_sim_model* full, int initialisation_steps,
+                                 const double* a_hat, const double* eps_hat, const double* eta_hat, const double* draws,
+                                 long long n_draws, double* epsilon, double* a_out, double* eta, int n_extract,
+                                 const double* const* Z_extract, const int* nZ_extract, double* const* extracted) {
+  SS_ARG(nsim >= 1 && N >= 1 && p >= 1 && n_comp >= 1 && comps && H && full && draws, "SimSmoother: bad arguments");
+  SS_ARG(nH == 1 || nH == N, "SimSmoother: H must have 1 or N slices");
+  SS_ARG(a_hat && eps_hat && eta_hat, "SimSmoother: smoothed estimates of the observed data are required");
+  SS_ARG(n_extract == 0 || (Z_extract && nZ_extract && extracted), "SimSmoother: null extraction arguments");
+  int m = 0, r = 0;
+  long long need = 0;
+  const size_t ns = (size_t)nsim;
+  for (int c = 0; c < n_comp; c++) {
+    const ssgpu_sim_component& C = comps[c];
+    SS_ARG(C.m >= 1 && C.r >= 1 && C.repeat_Q >= 1, "SimSmoother: component dimensions must be positive");
+    m += C.m;
+    r += C.r * C.repeat_Q;
+    need += (long long)(C.draw_initial ? (size_t)C.m * ns : 0) + (long long)N * C.r * C.repeat_Q * (long long)ns;
+  }
+  need += (long long)N * p * (long long)ns;  // residuals
+  if (n_draws != need) {
+    set_error("SimSmoother: n_draws does not match the reference's consumption (components in order, then N*p*nsim)");
+    return SSGPU_E_DRAWS;
+  }
+  SS_ARG(full->m == m + p && full->r == r + p, "SimSmoother: the full model must be the components plus p residual states");
+  SS_TRY(check_fs(draws, N, p, nsim, full->m, full->r, full->a, full->P_inf, full->P_star, full->Z, full->nZ, full->T,
+                  full->nT, full->R, full->nR, full->Q, full->nQ));
+  SS_TRY(ensure_device());
+  cudaStream_t st = lib_stream();
+  DevBuf dr, yN, aN, eN, epsN, afN, efN, hats, outR, zD, cN;
+  SS_TRY(upload(dr, draws, (size_t)n_draws, st));
+  SS_TRY(yN.alloc(sizeof(double) * (size_t)N * p * ns, st));
+  SS_TRY(aN.alloc(sizeof(double) * (size_t)N * m * ns, st));
+  SS_TRY(eN.alloc(sizeof(double) * (size_t)N * r * ns, st));
+  SS_TRY(epsN.alloc(sizeof(double) * (size_t)N * p * ns, st));
+  // unconditional draws, component by component (R/SimSmoother.R:65-553), then the residuals (:556-576)
+  size_t doff = 0;
+  int a_off = 0, e_off = 0;
+  for (int c = 0; c < n_comp; c++) {
+    const ssgpu_sim_component& C = comps[c];
+    const int r_tot = C.r * C.repeat_Q;
+    const size_t cnt = (C.draw_initial ? (size_t)C.m * ns : 0) + (size_t)N * r_tot * ns;
+    SS_TRY(check_sim(nsim, C.repeat_Q, N, p, C.m, r_tot, C.r, C.m, C.a, C.Z, C.nZ, C.T, C.nT, C.R, C.nR, C.Q, C.nQ,
+                     C.P_star, C.draw_initial, 0, draws + doff, (long long)cnt, C.P_root));
+    const SimPlace pl{m, a_off, r, e_off, c > 0};
+    SS_TRY(simulate_core(nsim, C.repeat_Q, N, p, C.m, r_tot, C.r, C.a, C.Z, C.nZ, C.T, C.nT, C.R, C.nR, C.Q, C.nQ,
+                         C.P_star, C.draw_initial, 0, dr.as<double>() + doff, C.Q_root, C.P_root, yN.as<double>(),
+                         aN.as<double>(), eN.as<double>(), st, &pl));
+    doff += cnt;
+    a_off += C.m;
+    e_off += r_tot;
+  }
+  SS_TRY(simulate_core(nsim, 1, N, 1, 1, p, p, nullptr, nullptr, 1, nullptr, 1, nullptr, 1, H, nH, nullptr, 0, 1,
+                       dr.as<double>() + doff, nullptr, nullptr, yN.as<double>(), nullptr, epsN.as<double>(), st));
+  // smoothed state and disturbances of the simulated data (:617-632)
+  SS_TRY(afN.alloc(sizeof(double) * (size_t)N * full->m * ns, st));
+  SS_TRY(efN.alloc(sizeof(double) * (size_t)N * full->r * ns, st));
+  SS_TRY(fast_smoother_core(yN.as<double>(), N, p, nsim, full->m, full->r, full->a, full->P_inf, full->P_star, full->Z,
+                            full->nZ, full->T, full->nT, full->R, full->nR, full->Q, full->nQ, initialisation_steps,
+                            afN.as<double>(), efN.as<double>(), st));
+  // mean corrections (:634-642)
+  HostPack hp;
+  const size_t oa = hp.add(a_hat, (size_t)N * m), oe = hp.add(eps_hat, (size_t)N * p), oh = hp.add(eta_hat, (size_t)N * r);
+  SS_TRY(upload(hats, hp.buf.data(), hp.buf.size(), st));
+  SS_TRY(launch_sim_correct(aN.as<double>(), afN.as<double>(), hats.as<double>() + oa, N, m, full->m, p, nsim, st));
+  SS_TRY(launch_sim_correct(epsN.as<double>(), afN.as<double>(), hats.as<double>() + oe, N, p, full->m, 0, nsim, st));
+  SS_TRY(launch_sim_correct(eN.as<double>(), efN.as<double>(), hats.as<double>() + oh, N, r, full->r, p, nsim, st));
+  // results in R's layouts
+  const int kmax = m > r ? (m > p ? m : p) : (r > p ? r : p);
+  SS_TRY(outR.alloc(sizeof(double) * (size_t)N * kmax * ns, st));
+  struct Out {
+    double* host;
+    const double* dev;
+    int K;
+  } outs[3] = {{epsilon, epsN.as<double>(), p}, {a_out, aN.as<double>(), m}, {eta, eN.as<double>(), r}};
+  for (const Out& o : outs) {
+    if (!o.host) continue;
+    SS_TRY(launch_permute_tks(o.dev, outR.as<double>(), N, o.K, nsim, true, st));
+    SS_CUDA(cudaMemcpyAsync(o.host, outR.get(), sizeof(double) * (size_t)N * o.K * ns, cudaMemcpyDeviceToHost, st));
+  }
+  // components (:645-766): Z_padded a_t per draw, from the corrected states
+  if (n_extract > 0) SS_TRY(cN.alloc(sizeof(double) * (size_t)N * p * ns, st));
+  for (int e = 0; e < n_extract; e++) {
+    SS_ARG(Z_extract[e] && extracted[e] && (nZ_extract[e] == 1 || nZ_extract[e] == N), "SimSmoother: bad extraction matrix");
+    SS_TRY(upload(zD, Z_extract[e], (size_t)p * m * nZ_extract[e], st));
+    SS_TRY(launch_extract(aN.as<double>(), 1, dmat3(zD.as<double>(), p, m, nZ_extract[e]), m, p, nsim, N, cN.as<double>(), st));
+    SS_TRY(launch_permute_tks(cN.as<double>(), outR.as<double>(), N, p, nsim, true, st));
+    SS_CUDA(cudaMemcpyAsync(extracted[e], outR.get(), sizeof(double) * (size_t)N * p * ns, cudaMemcpyDeviceToHost, st));
+  }
+  SS_CUDA(cudaStreamSynchronize(st));
+  (void)hp;
   return SSGPU_OK;
 }
 

@@ -182,6 +182,11 @@ struct SimArgs {
   const double* d0;      // [k + m*s]
   const double* dt;      // [t][kk + r_tot*s]
   double *y, *a, *eta;   // native layouts, may be null
+  // where the outputs land when several components write into the stacked arrays of the whole model
+  // (R/SimSmoother.R:104-110: a[, a_indices, ] <- sim$a, eta[, eta_indices, ] <- sim$eta, y <- y + sim$y):
+  // a[(t*a_ld + a_off + k)*S + s], eta[(t*eta_ld + eta_off + kk)*S + s]; 0 / 0 = the component's own m / r_tot.
+  // y_acc: add to y instead of storing (with eta_only: y += eta, R/SimSmoother.R:575-576)
+  int a_ld, a_off, eta_ld, eta_off, y_acc;
 };
 
 struct FsArgs {
@@ -200,6 +205,9 @@ struct FsArgs {
 };
 
 void last_sim_kernel_ms(double* sim, double* fs, double* ext);
+// x[(t*K + k)*S + s] = (x[..] - sm[(t*K_sm + off_sm + k)*S + s]) + hat[t + N*k]   (R/SimSmoother.R:634-642)
+int launch_sim_correct(double* x, const double* sm, const double* hat, int N, int K, int K_sm, int off_sm, long long S,
+                       cudaStream_t st);
 int launch_simulate(const SimArgs& A, cudaStream_t st);
 int launch_fs_draws(const FsArgs& A, cudaStream_t st);
 int launch_extract(const double* a, int a_native, const DMat& Z, int m, int p, int S, int N, double* out,

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(BT) simulate_kernel(const SimArgs A) {
   const long long s = (long long)blockIdx.x * BT + tid;
   if (s >= A.S) return;
   const int m = A.m, p = A.p, r = A.r, r_tot = A.r * A.repeat_Q, N = A.N;
+  const int a_ld = A.a_ld ? A.a_ld : m, eta_ld = A.eta_ld ? A.eta_ld : r_tot;
   const long long S = A.S;
   ShVec<BT> av{sh + tid}, a2{sh + (size_t)m * BT + tid}, et{sh + (size_t)2 * m * BT + tid};
   if (!A.eta_only) {
@@ -82,17 +83,21 @@ __global__ void __launch_bounds__(BT) simulate_kernel(const SimArgs A) {
         double acc = 0.0;
         for (int l = 0; l < r; l++) acc = fma(Qr[rr + l * r], dd[l + r * q], acc);
         et[rr + r * q] = acc;
-        if (A.eta) A.eta[((long long)t * r_tot + rr + r * q) * S + s] = acc;
+        if (A.eta) A.eta[((long long)t * eta_ld + A.eta_off + rr + r * q) * S + s] = acc;
+        if (A.eta_only && A.y) A.y[((long long)t * r_tot + rr + r * q) * S + s] += acc;
       }
     if (A.eta_only) continue;
     const double* Zt = slice_of(A.Z, t);
     const double* Tt = A.Te.vals(t);
     const double* Rt = A.Re.vals(t);
     if (A.a)
-      for (int k = 0; k < m; k++) A.a[((long long)t * m + k) * S + s] = av[k];
+      for (int k = 0; k < m; k++) A.a[((long long)t * a_ld + A.a_off + k) * S + s] = av[k];
     for (int j = 0; j < p; j++) {
       const double acc = sp_row_dot(A.Zp, j, Zt, p, av);
-      if (A.y) A.y[((long long)t * p + j) * S + s] = acc;
+      if (A.y) {
+        double* yp = A.y + ((long long)t * p + j) * S + s;
+        *yp = A.y_acc ? *yp + acc : acc;
+      }
     }
     if (t < N - 1) {
       for (int i = 0; i < m; i++) a2[i] = ell_row_dot(A.Te, Tt, i, av) + ell_row_dot(A.Re, Rt, i, et);
@@ -302,6 +307,7 @@ __global__ void __launch_bounds__(kRegBT) simulate_reg_kernel(const SimArgs A) {
   const int tid = threadIdx.x;
   const long long s = (long long)blockIdx.x * kRegBT + tid;
   const int m = A.m, p = A.p, r = A.r, r_tot = A.r * A.repeat_Q, N = A.N;
+  const int a_ld = A.a_ld ? A.a_ld : m, eta_ld = A.eta_ld ? A.eta_ld : r_tot;
   const long long S = A.S;
   ShVec<kRegBT> xs{sh + tid}, es{sh + (size_t)MP * kRegBT + tid};
   EllS Te{}, Re{};
@@ -338,14 +344,15 @@ __global__ void __launch_bounds__(kRegBT) simulate_reg_kernel(const SimArgs A) {
         double acc = 0.0;
         for (int l = 0; l < r; l++) acc = fma(Qr[rr + l * r], dd[l + r * q], acc);
         es[rr + r * q] = acc;
-        if (A.eta) A.eta[((long long)t * r_tot + rr + r * q) * S + s] = acc;
+        if (A.eta) A.eta[((long long)t * eta_ld + A.eta_off + rr + r * q) * S + s] = acc;
+        if (A.eta_only && A.y) A.y[((long long)t * r_tot + rr + r * q) * S + s] += acc;
       }
     if (A.eta_only) continue;
     const double* Zt = slice_of(A.Z, t);
     if (A.a) {
 #pragma unroll
       for (int k = 0; k < MP; k++)
-        if (k < m) A.a[((long long)t * m + k) * S + s] = av[k];
+        if (k < m) A.a[((long long)t * a_ld + A.a_off + k) * S + s] = av[k];
     }
     for (int j = 0; j < p; j++) {
       double acc = 0.0;
@@ -355,7 +362,10 @@ __global__ void __launch_bounds__(kRegBT) simulate_reg_kernel(const SimArgs A) {
           const double z = Zt[j + k * p];
           if (z != 0.0) acc = fma(z, av[k], acc);
         }
-      if (A.y) A.y[((long long)t * p + j) * S + s] = acc;
+      if (A.y) {
+        double* yp = A.y + ((long long)t * p + j) * S + s;
+        *yp = A.y_acc ? *yp + acc : acc;
+      }
     }
     if (t < N - 1) {
       double o2[MP];
@@ -575,6 +585,17 @@ __global__ void __launch_bounds__(kSimThreads) extract_kernel(const double* a, i
     }
     out[((long long)t * p + j) * S + s] = acc;
   }
+}
+
+// ---- mean correction of R/SimSmoother.R:634-642 -------------------------------------------------------
+// x <- (x - smoothed(simulated data)) + smoothed(observed data), draw-contiguous layout; hat is R's N x K matrix
+__global__ void __launch_bounds__(kSimThreads) sim_correct_kernel(double* x, const double* sm, const double* hat, int N,
+                                                                   int K, int K_sm, int off_sm, long long S) {
+  const long long s = (long long)blockIdx.x * kSimThreads + threadIdx.x;
+  const int k = blockIdx.y, t = blockIdx.z;
+  if (s >= S) return;
+  const long long i = ((long long)t * K + k) * S + s;
+  x[i] = (x[i] - sm[((long long)t * K_sm + off_sm + k) * S + s]) + hat[t + (long long)N * k];
 }
 
 // ---- layout changes -------------------------------------------------------------------------------
@@ -854,6 +875,15 @@ int launch_extract(const double* a, int a_native, const DMat& Z, int m, int p, i
   g_t_ext.start(st);
   extract_kernel<<<dim3(nblk(S, kSimThreads), N), kSimThreads, 0, st>>>(a, a_native, Z, m, p, S, N, out);
   g_t_ext.stop(st);
+  count_launch();
+  SS_CUDA(cudaGetLastError());
+  return SSGPU_OK;
+}
+
+int launch_sim_correct(double* x, const double* sm, const double* hat, int N, int K, int K_sm, int off_sm, long long S,
+                       cudaStream_t st) {
+  SS_ARG(K <= 65535 && N <= 65535, "SimSmoother: dimension too large");
+  sim_correct_kernel<<<dim3(nblk(S, kSimThreads), K, N), kSimThreads, 0, st>>>(x, sm, hat, N, K, K_sm, off_sm, S);
   count_launch();
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;

@@ -42,13 +42,29 @@ class KalmanOut(C.Structure):
     _fields_ = [("initialisation_steps", ip)] + [(n, dp) for n in KALMAN_FIELDS]
 
 
+class SimComponent(C.Structure):
+    """ssgpu_sim_component"""
+    _fields_ = [("m", C.c_int), ("r", C.c_int), ("repeat_Q", C.c_int), ("draw_initial", C.c_int),
+                ("a", C.c_void_p), ("Z", C.c_void_p), ("T", C.c_void_p), ("R", C.c_void_p), ("Q", C.c_void_p),
+                ("P_star", C.c_void_p), ("nZ", C.c_int), ("nT", C.c_int), ("nR", C.c_int), ("nQ", C.c_int),
+                ("Q_root", C.c_void_p), ("P_root", C.c_void_p)]
+
+
+class SimModel(C.Structure):
+    """ssgpu_sim_model"""
+    _fields_ = [("m", C.c_int), ("r", C.c_int), ("a", C.c_void_p), ("P_inf", C.c_void_p), ("P_star", C.c_void_p),
+                ("Z", C.c_void_p), ("T", C.c_void_p), ("R", C.c_void_p), ("Q", C.c_void_p),
+                ("nZ", C.c_int), ("nT", C.c_int), ("nR", C.c_int), ("nQ", C.c_int)]
+
+
 # every symbol include/ssgpu.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = ["ssgpu_version", "ssgpu_last_error", "ssgpu_set_device", "ssgpu_device_count", "ssgpu_release",
            "ssgpu_launch_count", "ssgpu_LogLikC", "ssgpu_KalmanC", "ssgpu_FastSmootherC", "ssgpu_SimulateC",
            "ssgpu_sym_root", "ssgpu_ExtractComponentC", "ssgpu_loglik_batch", "ssgpu_loglik_batch_dev",
            "ssgpu_last_kernel", "ssgpu_fp64_peak", "ssgpu_plan_state_order", "ssgpu_SimulateC_dev",
            "ssgpu_FastSmootherC_dev", "ssgpu_ExtractComponentC_dev", "ssgpu_draw_layout_dev", "ssgpu_last_sim_kernel_ms",
-           "ssgpu_loglik_grad_batch", "ssgpu_loglik_grad_batch_dev", "ssgpu_loglik_theta_batch_dev"]
+           "ssgpu_loglik_grad_batch", "ssgpu_loglik_grad_batch_dev", "ssgpu_loglik_theta_batch_dev",
+           "ssgpu_SimSmoother"]
 
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS, KERNEL_MMA, KERNEL_MMA_DENSE, KERNEL_WSM, KERNEL_BLK = 0, 1, 2, 3, 4, 5, 6
 
@@ -86,6 +102,8 @@ def lib():
         L.ssgpu_loglik_grad_batch_dev.argtypes = [vp, ll, C.POINTER(Model), vp, i, vp, vp, d, i, vp, vp, vp]
         L.ssgpu_loglik_theta_batch_dev.argtypes = [vp, ll, i, C.POINTER(Model), vp, i, vp, vp, i, vp, vp]
         L.ssgpu_plan_state_order.argtypes = [vp, i, vp, vp, vp]
+        L.ssgpu_SimSmoother.argtypes = [i, i, i, i, C.POINTER(SimComponent), vp, i, C.POINTER(SimModel), i, vp, vp, vp, vp,
+                                        ll, vp, vp, vp, i, vp, vp, vp]
         L.ssgpu_device_count.argtypes = [ip]
         L.ssgpu_set_device.argtypes = [i]
         _lib = L

@@ -653,6 +653,70 @@ def test_fast_smoother_airline_sim_smoother_pipeline():
     assert np.array_equal(sims["gpu"][2], sims["cpu"][2])
 
 
+def _sim_smoother_case(kind, rng):
+    """Inputs of one SimSmoother() call: the components as R/SimSmoother.R would pass them to SimulateC, the full model
+    with the residual states in front and the smoothed estimates of the observed data."""
+    S = sysmat
+    if kind == "airline":
+        air = np.log(load_series("airpassengers.txt"))[:, None]
+        sm = S.airline([0.5 * math.log(0.00135), 0.4, 0.55], H=0.0002)
+        c = S.comp_sarima_univariate((12, 1), (0, 0), (1, 1), (1, 1), [0.5 * math.log(0.00135), 0.4, 0.55])
+        comps = [dict(a=c["a"], Z=c["Z"], T=c["T"], R=c["R"], Q=c["Q"], P_star=c["P_star"], repeat_Q=1, draw_initial=True)]
+        y, p = air, 1
+        extract = [c["Z"]]
+    else:  # level + slope, trigonometric seasonal (repeat_Q = s - 1, R/SimSmoother.R:188) and a cycle, p = 1
+        cl, cs, cc = S.comp_level_slope(0.1, 0.01), S.comp_bsm_trig(4, 0.05), _cycle(0.9, 0.4, 0.3)
+        sm = S._combine(1, [[0.5]], [cl, cs, cc])
+        comps = [dict(a=cl["a"], Z=cl["Z"], T=cl["T"], R=cl["R"], Q=cl["Q"], P_star=np.zeros((1, 1)), repeat_Q=1,
+                      draw_initial=False),
+                 dict(a=cs["a"], Z=cs["Z"], T=cs["T"], R=cs["R"], Q=np.array([[0.05]]), P_star=np.zeros((1, 1)), repeat_Q=3,
+                      draw_initial=False),
+                 dict(a=cc["a"], Z=cc["Z"], T=cc["T"], R=cc["R"], Q=np.array([[0.3]]), P_star=cc["P_star"], repeat_Q=2,
+                      draw_initial=True)]
+        y, p = simulate_y(rng, sm, 60, missing=0.1), 1
+        pad = lambda Zc, lo, k: np.concatenate([np.zeros((1, lo)), Zc, np.zeros((1, sm.m - 1 - lo - k))], axis=1)
+        extract = [pad(cl["Z"], 0, 2), pad(cs["Z"], 2, 3), pad(cc["Z"], 5, 2)]
+    ks = api.KalmanC(y, np.isnan(y), *sm.args(), False)
+    a_hat, eps_hat, eta_hat = ks["a_smooth"][:, p:], ks["a_smooth"][:, :p], ks["eta"][:, p:]
+    H = sm.Q[:p, :p, :]
+    return dict(N=len(y), p=p, comps=comps, H=H, full=tuple(sm.args()), steps=int(ks["initialisation_steps"]),
+                a_hat=a_hat, eps_hat=eps_hat, eta_hat=eta_hat, extract=extract)
+
+
+@pytest.mark.parametrize("kind", ["airline", "structural"])
+def test_sim_smoother_one_call(kind):
+    """ssgpu_SimSmoother (R/SimSmoother.R:34-769 as one call, per-draw arrays resident on the device) against the
+    same function strung together from the C oracle's routines: bit-exact with shared symmetric roots, 1e-9 against
+    the compiled reference with its own SVD roots."""
+    from oracle import sim_smoother
+    rng = np.random.default_rng(12)
+    c = _sim_smoother_case(kind, rng)
+    nsim, N = 37, c["N"]
+    n_draws = sum((np.asarray(k["a"]).size * nsim if k["draw_initial"] else 0)
+                  + N * np.asarray(k["Q"]).shape[0] * k["repeat_Q"] * nsim for k in c["comps"]) + N * c["p"] * nsim
+    draws = rng.normal(size=n_draws)
+    roots = [dict(Q_root=np.stack([cport.sym_root(np.atleast_2d(k["Q"]))], axis=2),
+                  P_root=cport.sym_root(np.atleast_2d(k["P_star"])) if k["draw_initial"] else None) for k in c["comps"]]
+    roots.append({})
+    args = (nsim, N, c["p"], c["comps"], c["H"], c["full"], c["steps"], c["a_hat"], c["eps_hat"], c["eta_hat"], draws)
+    got = api.SimSmoother(*args, extract=c["extract"], roots=roots)
+    want = sim_smoother.SimSmoother(cport, *args, extract=c["extract"], roots=roots)
+    for k in ("epsilon", "a", "eta"):
+        assert np.array_equal(got[k], want[k]), k
+    assert len(got["components"]) == len(c["extract"])
+    for g, w in zip(got["components"], want["components"]):
+        assert np.array_equal(g, w)
+    if ref.available():
+        r0 = sim_smoother.SimSmoother(ref, *args, extract=c["extract"])
+        got2 = api.SimSmoother(*args, extract=c["extract"])                # the library's own Jacobi roots
+        for k in ("epsilon", "a", "eta"):
+            assert rel(got2[k], r0[k]) < 1e-8, k
+        for g, w in zip(got2["components"], r0["components"]):
+            assert rel(g, w) < 1e-8
+    with pytest.raises(RuntimeError, match="n_draws"):
+        api.SimSmoother(*args[:-1], draws[:-1], extract=c["extract"])
+
+
 @pytest.mark.parametrize("nsim", [100, 40000, 80000])
 def test_sim_smoother_device_resident_pipeline(nsim):
     """The *_dev entry points (draws stay on the GPU in the draw-contiguous layout) give the same bits as the
