@@ -186,16 +186,55 @@ def run_reference(args):
 
 # ---- the GPU arm ----------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons sampled DURING the timed region: an NVML polling thread in this process
+    (a resident `nvidia-smi -lms` stalled the driver for tens of milliseconds per query, visible in a 15 ms timed
+    region), `nvidia-smi` only as the fallback when pynvml is missing."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, interval_ms=250):
+    def __init__(self, index, interval_ms=100):
         self.index = index
         self.interval_ms = interval_ms
         self.proc = None
+        self.thread = None
+        self.rows = []
+        self.stop_flag = False
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _poll(self, nv, h):
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        smax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append((float(sm), float(smax), pw, [k for k, b in bits.items() if rs & b]))
+            except Exception:
+                pass
+            time.sleep(self.interval_ms / 1000.0)
 
     def start(self):
+        try:
+            import threading
+
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                           "-lms", str(self.interval_ms), "-i", str(self.index)], stdout=subprocess.PIPE,
@@ -204,6 +243,14 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = [r[0] for r in self.rows]
+            reasons = sorted({k for r in self.rows for k in r[3]})
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(r[1] for r in self.rows) if sm else None,
+                    "power_w_max": max(r[2] for r in self.rows) if sm else None, "samples": len(sm), "reasons": reasons,
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -228,7 +275,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": "nvidia-smi"}
 
 
 def make_shard(torch, dev, B, seed):
@@ -560,11 +608,10 @@ def run_sim_gpu(args):
     for _ in range(args.warmup):
         step()
     sync()
-    # a step is a few ms of kernels between short host-synchronous calls: poll nvidia-smi rarely, its queries
-    # stall the driver for milliseconds
-    sampler = ClockSampler(local, interval_ms=500)
+    # a step is a few ms of kernels between short host-synchronous calls: clocks are polled through NVML in-process
+    sampler = ClockSampler(local, interval_ms=20)
     sampler.start()
-    time.sleep(0.6)
+    time.sleep(0.1)
     l0 = api.launch_count()
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -595,20 +642,43 @@ def run_sim_gpu(args):
         fs = api.FastSmootherC(s1["y"] + s2["eta"], *sm.args(), steps0, True)
         return api.ExtractComponentC(fs["a_t"], sm.Z)
 
-    e2e_step()
-    sync()
-    t0 = time.perf_counter()
-    e2e_step()
-    sync()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = Se * N * world / e2e_s
+    def timed(fn):
+        fn()
+        sync()
+        t0 = time.perf_counter()
+        fn()
+        sync()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt
+
+    legacy_value = Se * N * world / timed(e2e_step)
     m, r, p = sm.m, sm.r, 1
-    h2d = 8 * Se * N * (1 + 1 + p + m)                       # variates x2, y, a_t
-    d2h = 8 * Se * N * ((p + 2 * mc + 1) + 1 + (2 * m + r) + p)
+    legacy_h2d = 8 * Se * N * (1 + 1 + p + m)                # variates x2, y, a_t
+    legacy_d2h = 8 * Se * N * ((p + 2 * mc + 1) + 1 + (2 * m + r) + p)
+
+    # the call a user of the package makes: SimSmoother() (R/SimSmoother.R) as ONE call of the C ABI -- variates in,
+    # epsilon / a / eta / the extracted component out; the per-draw intermediates never leave the device
+    from statespacer_b200 import sysmat
+    ks = api.KalmanC(air, np.isnan(air), *sm.args(), False)
+    import math
+    cs = sysmat.comp_sarima_univariate((12, 1), (0, 1), (1, 1), (1, 1), [0.5 * math.log(0.00135), 0.3, -0.4, -0.55])
+    comps = [dict(a=cs["a"], Z=cs["Z"], T=cs["T"], R=cs["R"], Q=cs["Q"], P_star=cs["P_star"], repeat_Q=1,
+                  draw_initial=True)]
+    n_dr = mc * Se + N * Se + N * Se
+    gh = np.random.default_rng(4 + rank)
+    draws_h = gh.normal(size=n_dr)
+
+    def one_call():
+        return api.SimSmoother(Se, N, 1, comps, sm.Q[:1, :1, :], tuple(sm.args()), steps0, ks["a_smooth"][:, 1:],
+                               ks["a_smooth"][:, :1], ks["eta"][:, 1:], draws_h, extract=[cs["Z"]])
+
+    e2e_value = Se * N * world / timed(one_call)
+    h2d = 8 * n_dr
+    d2h = 8 * Se * N * (p + mc + (r - 1) + p)
 
     if rank == 0:
         b_sim, b_fs, b_ext = sim_bytes(N, p, m, r, mc, 1)
@@ -626,7 +696,13 @@ def run_sim_gpu(args):
                 "config": sim_config(world, S, {"results_finite": finite}),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": SIM_UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": 1, "nsim": Se, "note": "host-pointer C ABI, R array layouts, pageable host memory"},
+                        "steps": 1, "nsim": Se,
+                        "note": "ssgpu_SimSmoother: R's SimSmoother() as one call of the host-pointer C ABI (variates in; "
+                                "epsilon, a, eta and the extracted component out, R array layouts, pageable host memory)",
+                        "legacy_three_call": {"value": legacy_value, "h2d_bytes_per_step": legacy_h2d,
+                                              "d2h_bytes_per_step": legacy_d2h,
+                                              "note": "SimulateC x2 -> FastSmootherC -> ExtractComponentC through the "
+                                                      "five legacy entry points, every array crossing PCIe"}},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "fs_draw_reg_kernel", "achieved": achieved, "peak": hbm_peak,
                              "unit": "GB/s", "frac": achieved / hbm_peak,

@@ -56,3 +56,16 @@ LogLikGradBatchC <- function(Y, theta, q_index, p_star_index, sysmat, h = 1e-3) 
   .Call(`_statespacer_LogLikGradBatchC`, Y, as.matrix(theta), as.integer(q_index) - 1L, as.integer(p_star_index) - 1L,
         as.numeric(h), sysmat$a, sysmat$P_inf, sysmat$P_star, sysmat$Z, sysmat$T, sysmat$R, sysmat$Q)
 }
+
+#' SimSmoother() as one device-resident call (replaces the body of R/SimSmoother.R:53-766).
+#'
+#' `comps` lists, in the order R/SimSmoother.R calls SimulateC, the arguments of each of those calls
+#' (a, Z, T, R, Q, P_star, repeat_Q, draw_initial; 3-D arrays with a trailing dim); `full` is the model of
+#' R/SimSmoother.R:579-615 (residual states in front); `Z_extract` the Z_padded arrays of :645-766.  The normal variates
+#' are drawn inside the shim with norm_rand() in the reference's order, so set.seed() reproduces the CPU package's draws.
+#' @return list(epsilon = N x p x nsim, a = N x m x nsim, eta = N x r x nsim, components = list of N x p x nsim).
+SimSmootherC <- function(nsim, N, p, comps, H, full, initialisation_steps, smoothed, Z_extract = list()) {
+  if (is.matrix(H)) dim(H) <- c(dim(H), 1)
+  .Call(`_statespacer_SimSmootherC`, as.integer(nsim), as.integer(N), as.integer(p), comps, H, full,
+        as.integer(initialisation_steps), smoothed$a, smoothed$epsilon, smoothed$eta, Z_extract)
+}

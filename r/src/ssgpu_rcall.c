@@ -1,5 +1,5 @@
 /* .Call shim: the five registered native routines of statespacer (src/RcppExports.cpp:108-115, same
- * names, same arity) plus `_statespacer_LogLikBatchC` and `_statespacer_LogLikGradBatchC`, implemented on libssgpu (include/ssgpu.h) with
+ * names, same arity) plus `_statespacer_LogLikBatchC`, `_statespacer_LogLikGradBatchC` and `_statespacer_SimSmootherC`, implemented on libssgpu (include/ssgpu.h) with
  * R's plain C API -- no Rcpp, no Armadillo.
  *
  * Build inside the package (src/Makevars):
@@ -287,6 +287,83 @@ SEXP _statespacer_LogLikGradBatchC(SEXP yt, SEXP theta, SEXP q_index, SEXP p_sta
   return out;
 }
 
+/* element `name` of a named R list (R_NilValue if absent) */
+static SEXP list_get(SEXP lst, const char* name) {
+  SEXP names = Rf_getAttrib(lst, R_NamesSymbol);
+  for (int i = 0; i < Rf_length(lst); i++)
+    if (names != R_NilValue && strcmp(CHAR(STRING_ELT(names, i)), name) == 0) return VECTOR_ELT(lst, i);
+  return R_NilValue;
+}
+
+/* New: SimSmoother() as ONE call (ssgpu.h section 6d; replaces the SimulateC / FastSmootherC / ExtractComponentC round
+ * trips of R/SimSmoother.R:65-766).  comps: list of lists(a, Z, T, R, Q, P_star, repeat_Q, draw_initial) in the order
+ * R/SimSmoother.R calls SimulateC; H: p x p x {1|N}; full: list(a, P_inf, P_star, Z, T, R, Q) of :579-615;
+ * a_hat / eps_hat / eta_hat: object$smoothed$a / $epsilon / $eta; Z_extract: list of Z_padded arrays (:645-766).
+ * The normal variates are drawn here with norm_rand() in exactly the order the reference's calls would consume them, so
+ * R's random stream -- and therefore every draw -- is the one the CPU package produces for the same seed. */
+SEXP _statespacer_SimSmootherC(SEXP nsim_, SEXP N_, SEXP p_, SEXP comps, SEXP H, SEXP full, SEXP steps_, SEXP a_hat,
+                               SEXP eps_hat, SEXP eta_hat, SEXP Z_extract) {
+  const int nsim = Rf_asInteger(nsim_), N = Rf_asInteger(N_), p = Rf_asInteger(p_), nc = Rf_length(comps),
+            ne = Rf_length(Z_extract);
+  ssgpu_sim_component* cs = (ssgpu_sim_component*)R_alloc(nc > 0 ? nc : 1, sizeof(ssgpu_sim_component));
+  int m = 0, r = 0, d0, d1, d2;
+  R_xlen_t n_draws = 0;
+  for (int c = 0; c < nc; c++) {
+    SEXP L = VECTOR_ELT(comps, c);
+    SEXP a = list_get(L, "a"), Z = list_get(L, "Z"), T = list_get(L, "T"), R = list_get(L, "R"), Q = list_get(L, "Q"),
+         P = list_get(L, "P_star");
+    memset(&cs[c], 0, sizeof cs[c]);
+    cs[c].m = Rf_length(a);
+    cs[c].repeat_Q = Rf_asInteger(list_get(L, "repeat_Q"));
+    cs[c].draw_initial = Rf_asLogical(list_get(L, "draw_initial"));
+    cs[c].a = REAL(a); cs[c].Z = REAL(Z); cs[c].T = REAL(T); cs[c].R = REAL(R); cs[c].Q = REAL(Q); cs[c].P_star = REAL(P);
+    dims3(Z, &d0, &d1, &cs[c].nZ);
+    dims3(T, &d0, &d1, &cs[c].nT);
+    dims3(R, &d0, &d1, &cs[c].nR);
+    dims3(Q, &cs[c].r, &d1, &cs[c].nQ);
+    m += cs[c].m;
+    r += cs[c].r * cs[c].repeat_Q;
+    n_draws += (cs[c].draw_initial ? (R_xlen_t)cs[c].m * nsim : 0) + (R_xlen_t)N * cs[c].r * cs[c].repeat_Q * nsim;
+  }
+  n_draws += (R_xlen_t)N * p * nsim;
+  ssgpu_sim_model fm;
+  memset(&fm, 0, sizeof fm);
+  fm.a = REAL(list_get(full, "a")); fm.P_inf = REAL(list_get(full, "P_inf")); fm.P_star = REAL(list_get(full, "P_star"));
+  fm.Z = REAL(list_get(full, "Z")); fm.T = REAL(list_get(full, "T")); fm.R = REAL(list_get(full, "R"));
+  fm.Q = REAL(list_get(full, "Q"));
+  dims3(list_get(full, "Z"), &d0, &fm.m, &fm.nZ);
+  dims3(list_get(full, "T"), &d0, &d1, &fm.nT);
+  dims3(list_get(full, "R"), &d0, &fm.r, &fm.nR);
+  dims3(list_get(full, "Q"), &d0, &d1, &fm.nQ);
+  dims3(H, &d0, &d1, &d2);
+  const int nH = d2;
+  double* draws = (double*)R_alloc(n_draws, sizeof(double));
+  GetRNGstate();
+  for (R_xlen_t i = 0; i < n_draws; i++) draws[i] = norm_rand();
+  PutRNGstate();
+  SEXP eps = alloc3(N, p, nsim), a_out = alloc3(N, m, nsim), eta = alloc3(N, r, nsim);
+  SEXP ext = PROTECT(Rf_allocVector(VECSXP, ne));
+  const double** zp = (const double**)R_alloc(ne > 0 ? ne : 1, sizeof(double*));
+  double** op = (double**)R_alloc(ne > 0 ? ne : 1, sizeof(double*));
+  int* nz = (int*)R_alloc(ne > 0 ? ne : 1, sizeof(int));
+  for (int e = 0; e < ne; e++) {
+    SEXP Z = VECTOR_ELT(Z_extract, e);
+    SEXP o = Rf_alloc3DArray(REALSXP, N, p, nsim);
+    SET_VECTOR_ELT(ext, e, o); /* protected through ext */
+    zp[e] = REAL(Z);
+    op[e] = REAL(o);
+    dims3(Z, &d0, &d1, &nz[e]);
+  }
+  int rc = ssgpu_SimSmoother(nsim, N, p, nc, cs, REAL(H), nH, &fm, Rf_asInteger(steps_), REAL(a_hat), REAL(eps_hat),
+                             REAL(eta_hat), draws, (long long)n_draws, REAL(eps), REAL(a_out), REAL(eta), ne, zp, nz, op);
+  if (rc != SSGPU_OK) { UNPROTECT(4); chk(rc); }
+  const char* names[] = {"epsilon", "a", "eta", "components", ""};
+  SEXP res = PROTECT(Rf_mkNamed(VECSXP, names));
+  SET_VECTOR_ELT(res, 0, eps); SET_VECTOR_ELT(res, 1, a_out); SET_VECTOR_ELT(res, 2, eta); SET_VECTOR_ELT(res, 3, ext);
+  UNPROTECT(5);
+  return res;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_statespacer_ExtractComponentC", (DL_FUNC)&_statespacer_ExtractComponentC, 2},
     {"_statespacer_FastSmootherC", (DL_FUNC)&_statespacer_FastSmootherC, 10},
@@ -295,6 +372,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_statespacer_SimulateC", (DL_FUNC)&_statespacer_SimulateC, 12},
     {"_statespacer_LogLikBatchC", (DL_FUNC)&_statespacer_LogLikBatchC, 11},
     {"_statespacer_LogLikGradBatchC", (DL_FUNC)&_statespacer_LogLikGradBatchC, 12},
+    {"_statespacer_SimSmootherC", (DL_FUNC)&_statespacer_SimSmootherC, 11},
     {NULL, NULL, 0}};
 
 void R_init_statespacer(DllInfo* dll) {

@@ -37,5 +37,9 @@ double Rf_asReal(SEXP);
 int Rf_length(SEXP);
 void Rf_error(const char*, ...) __attribute__((noreturn));
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
+SEXP VECTOR_ELT(SEXP, R_xlen_t);
+SEXP STRING_ELT(SEXP, R_xlen_t);
+const char* R_CHAR(SEXP);
+#define CHAR(x) R_CHAR(x)
 void SET_STRING_ELT(SEXP, R_xlen_t, SEXP);
 #endif
