@@ -171,6 +171,20 @@ int ssgpu_loglik_batch_dev(const double* y, long long B, int V, const ssgpu_mode
 /* name of the kernel the last ssgpu_loglik_batch[_dev] call on this thread launched */
 const char* ssgpu_last_kernel(void);
 
+/* ---- 2b. Batched KalmanC (new) ---------------------------------------------------------------
+ * Filter and smoother of B independent series in one call (StateSpaceEval() over a fitted batch, R/StateSpaceEval.R:156-167
+ * once per series in the reference).  y is time-major and batch-contiguous as in section 6, y[(t*p + j)*B + b]; `model`
+ * as in section 6 with V = 1 (per-series a / P_inf / P_star / Q / ... through stride_series; shared matrices with
+ * stride 0).  Every non-NULL member of `out` receives B consecutive blocks, block b holding series b in exactly the
+ * layout of ssgpu_KalmanC (initialisation_steps: B ints).  The diagnostics arrays (v_norm, e, D, Tstat_*) must be NULL.
+ * Only what is asked for crosses to the caller; P_star_pred, P_inf_pred and a_pred are kept as device scratch for
+ * the backward pass when they are not (2 m^2 N + N m doubles per series: size the batch accordingly).
+ * ssgpu_kalman_batch: host pointers everywhere; ssgpu_kalman_batch_dev: device pointers, work enqueued on `stream`,
+ * returns after completion. */
+int ssgpu_kalman_batch(const double* y, long long B, const ssgpu_model* model, const ssgpu_kalman_out* out);
+int ssgpu_kalman_batch_dev(const double* y, long long B, const ssgpu_model* model, const ssgpu_kalman_out* out,
+                           void* stream);
+
 /* ---- 6c. Batched loglikelihood and gradient from parameter vectors (new) ---------------------
  * The objective of the optim loop (R/statespacer.R:917-927) rebuilds the system matrices from theta in R for
  * every call, and stats::optim takes 2k further calls per gradient (R/statespacer.R:977-982).  For models whose

@@ -483,6 +483,47 @@ def loglik_batch_dev(y, model: BatchModel, out, kernel="auto", stream=None):
     return out
 
 
+def kalman_batch(y, sm, want=("loglik", "a_smooth", "V"), **per_series):
+    """Batched KalmanC on host arrays (include/ssgpu.h section 2b).  y: (N, B) or (N, p, B), NaN = missing; per-series
+    overrides as for loglik_batch with leading dimension (B,).  Returns a dict: for every name in `want` an array
+    (B, ...) whose trailing dimensions are the reference's (column-major per series), plus initialisation_steps (B,)."""
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    N, B = _y_dims(y, np.asarray(sm.Z).shape[0])
+    model = BatchModel(sm, N, B, 1, **per_series)
+    p, m, r = model.p, model.m, model.r
+    out = native.KalmanOut()
+    res, flat = {}, {}
+    for name in want:
+        shape = kalman_shapes(N, p, m, r, True)[name]
+        flat[name] = np.zeros((B, int(np.prod(shape))))
+        setattr(out, name, flat[name].ctypes.data_as(native.dp))
+        res[name] = shape
+    steps = np.zeros(B, dtype=np.int32)
+    out.initialisation_steps = steps.ctypes.data_as(native.ip)
+    native.check(native.lib().ssgpu_kalman_batch(y.ctypes.data, B, C.byref(model.c), C.byref(out)))
+    result = {k: flat[k].reshape((B,) + res[k][::-1]).transpose((0,) + tuple(range(len(res[k]), 0, -1))) for k in want}
+    result["initialisation_steps"] = steps
+    return result
+
+
+def kalman_batch_dev(y, model: BatchModel, want=("loglik", "a_smooth", "V"), stream=None):
+    """Batched KalmanC on device-resident data: y a contiguous CUDA tensor (N*p, B); returns CUDA tensors (B, size)
+    -- block b is series b in the reference's column-major layout -- plus initialisation_steps (B,) int32."""
+    import torch
+    N, p, m, r, B = model.N, model.p, model.m, model.r, model.B
+    out = native.KalmanOut()
+    res = {}
+    for name in want:
+        n = int(np.prod(kalman_shapes(N, p, m, r, True)[name]))
+        res[name] = torch.empty(B, n, device=y.device, dtype=torch.float64)
+        setattr(out, name, C.cast(C.c_void_p(res[name].data_ptr()), native.dp))
+    steps = torch.zeros(B, device=y.device, dtype=torch.int32)
+    out.initialisation_steps = C.cast(C.c_void_p(steps.data_ptr()), native.ip)
+    native.check(native.lib().ssgpu_kalman_batch_dev(y.data_ptr(), B, C.byref(model.c), C.byref(out), _stream_handle(stream)))
+    res["initialisation_steps"] = steps
+    return res
+
+
 # ---- theta-driven objective / gradient (include/ssgpu.h section 6c) ---------------------------------------
 def _index_vec(x, n, name):
     v = np.ascontiguousarray(x, dtype=np.int32).reshape(-1)

@@ -385,6 +385,133 @@ int ssgpu_KalmanC(const double* y, const int* y_isna, int N, int p, int m, int r
   return SSGPU_OK;
 }
 
+// ---- batched KalmanC (include/ssgpu.h section 2b) ---------------------------------------------------------------
+namespace {
+
+struct KField {
+  double* ssgpu_kalman_out::*ptr;
+  size_t n;        // doubles per series
+  bool needed;     // read by the backward pass: allocated as scratch when the caller does not ask for it
+  bool diagnostic;
+};
+
+std::vector<KField> kalman_fields(int N, int p, int m, int r) {
+  const size_t Np = (size_t)N * p, mm = (size_t)m * m, Nm = (size_t)N * m;
+  typedef ssgpu_kalman_out K;
+  return {
+      {&K::loglik, Np, false, false},       {&K::a_pred, Nm, true, false},          {&K::a_fil, Nm, false, false},
+      {&K::a_smooth, Nm, false, false},     {&K::P_pred, mm * N, false, false},     {&K::P_fil, mm * N, false, false},
+      {&K::V, mm * N, false, false},        {&K::P_inf_pred, mm * N, true, false},  {&K::P_star_pred, mm * N, true, false},
+      {&K::P_inf_fil, mm * N, false, false}, {&K::P_star_fil, mm * N, false, false}, {&K::yfit, Np, false, false},
+      {&K::v, Np, false, false},            {&K::eta, (size_t)N * r, false, false}, {&K::Fmat, (size_t)p * p * N, false, false},
+      {&K::eta_var, (size_t)r * r * N, false, false}, {&K::a_fc, (size_t)m, false, false}, {&K::P_inf_fc, mm, false, false},
+      {&K::P_star_fc, mm, false, false},    {&K::P_fc, mm, false, false},           {&K::r_vec, (size_t)(N + 1) * m, false, false},
+      {&K::Nmat, mm * (N + 1), false, false}, {&K::v_norm, Np, false, true},        {&K::e, Np, false, true},
+      {&K::D, (size_t)p * p * N, false, true}, {&K::Tstat_observation, Np, false, true},
+      {&K::Tstat_state, (size_t)(N + 1) * m, false, true}};
+}
+
+// `want`: device pointers of the arrays the caller asked for (null = not wanted).  Runs forward + backward for B series.
+int kalman_batch_core(const DModel& md, const double* y_dev, long long B, const ssgpu_kalman_out& want, cudaStream_t st) {
+  const int N = md.N, p = md.p, m = md.m, r = md.r;
+  SS_ARG(B >= 1 && B < (1LL << 31), "kalman_batch: batch size out of range");
+  SS_ARG(!md.a.sv && !md.Q.sv, "kalman_batch: one parameter vector per series");
+  auto pad = [](size_t n) { return (n + 31) / 32 * 32; };
+  const size_t Np = (size_t)N * p, nb = (size_t)B;
+  const bool qtr_tv = md.Q.tv() || md.R.tv();
+  ssgpu_kalman_out d = want;
+  size_t extra = 0;
+  const auto fields = kalman_fields(N, p, m, r);
+  for (const KField& f : fields) {
+    SS_ARG(!(f.diagnostic && want.*(f.ptr)), "kalman_batch: the diagnostics arrays are not available in the batched call");
+    if (f.needed && !(want.*(f.ptr))) extra += pad(f.n * nb);
+  }
+  const size_t per_series = pad(Np) * 3 + pad(Np * m) * 2 + pad((size_t)(qtr_tv ? N : 1) * r * m) + pad(Np);
+  DevBuf blk;
+  SS_TRY(blk.alloc((extra + per_series * nb + pad(nb)) * sizeof(double), st));
+  double* base = blk.as<double>();
+  size_t off = 0;
+  for (const KField& f : fields)
+    if (f.needed && !(want.*(f.ptr))) {
+      d.*(f.ptr) = base + off;
+      off += pad(f.n * nb);
+    }
+  // per-series scratch blocks are contiguous per array (kalman_shift strides by the array's own block size)
+  KalmanScratch s{};
+  s.F1 = base + off; off += Np * nb;
+  s.F2 = base + off; off += Np * nb;
+  s.v = base + off; off += Np * nb;
+  s.K0 = base + off; off += Np * m * nb;
+  s.K1 = base + off; off += Np * m * nb;
+  s.QtR = base + off; off += (size_t)(qtr_tv ? N : 1) * r * m * nb;
+  s.code = reinterpret_cast<int*>(base + off); off += (Np * nb + 1) / 2 + 32;
+  if (!d.initialisation_steps) d.initialisation_steps = reinterpret_cast<int*>(base + off);
+  SS_TRY(launch_fwd_generic(md, y_dev, B, 1, nullptr, &d, &s, st));
+  SS_TRY(launch_bwd_generic(md, &d, &s, st, B));
+  SS_CUDA(cudaStreamSynchronize(st));  // the scratch block is released behind the kernels
+  return SSGPU_OK;
+}
+
+}  // namespace
+
+int ssgpu_kalman_batch_dev(const double* y, long long B, const ssgpu_model* model, const ssgpu_kalman_out* out,
+                           void* stream) {
+  SS_ARG(y && out, "null pointer argument");
+  DModel md{};
+  SS_TRY(to_dmodel(model, &md));
+  SS_TRY(ensure_device());
+  cudaStream_t st = stream ? (cudaStream_t)stream : lib_stream();
+  return kalman_batch_core(md, y, B, *out, st);
+}
+
+int ssgpu_kalman_batch(const double* y, long long B, const ssgpu_model* model, const ssgpu_kalman_out* out) {
+  SS_ARG(y && out && model, "null pointer argument");
+  DModel md{};
+  SS_TRY(to_dmodel(model, &md));
+  SS_ARG(B >= 1, "B must be positive");
+  SS_TRY(ensure_device());
+  cudaStream_t st = lib_stream();
+  const int N = md.N, p = md.p, m = md.m, r = md.r;
+  const ssgpu_matrix* src[7] = {&model->a, &model->P_inf, &model->P_star, &model->Z, &model->T, &model->R, &model->Q};
+  DMat* dst[7] = {&md.a, &md.P_inf, &md.P_star, &md.Z, &md.T, &md.R, &md.Q};
+  auto pad = [](size_t n) { return (n + 31) / 32 * 32; };
+  const size_t n_y = (size_t)N * p * (size_t)B, nb = (size_t)B;
+  size_t total = pad(n_y) + pad(nb), ext[7];
+  for (int i = 0; i < 7; i++) {
+    ext[i] = extent(*src[i], B, 1);
+    total += pad(ext[i]);
+  }
+  const auto fields = kalman_fields(N, p, m, r);
+  for (const KField& f : fields)
+    if (out->*(f.ptr)) total += pad(f.n * nb);
+  DevBuf blk;
+  SS_TRY(blk.alloc(total * sizeof(double), st));
+  double* base = blk.as<double>();
+  size_t off = 0;
+  SS_CUDA(cudaMemcpyAsync(base, y, n_y * sizeof(double), cudaMemcpyHostToDevice, st));
+  off += pad(n_y);
+  for (int i = 0; i < 7; i++) {
+    SS_CUDA(cudaMemcpyAsync(base + off, src[i]->data, ext[i] * sizeof(double), cudaMemcpyHostToDevice, st));
+    dst[i]->p = base + off;
+    off += pad(ext[i]);
+  }
+  ssgpu_kalman_out d{};
+  for (const KField& f : fields)
+    if (out->*(f.ptr)) {
+      d.*(f.ptr) = base + off;
+      off += pad(f.n * nb);
+    }
+  if (out->initialisation_steps) d.initialisation_steps = reinterpret_cast<int*>(base + off);
+  SS_TRY(kalman_batch_core(md, base, B, d, st));
+  for (const KField& f : fields)
+    if (out->*(f.ptr))
+      SS_CUDA(cudaMemcpyAsync(out->*(f.ptr), d.*(f.ptr), f.n * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (out->initialisation_steps)
+    SS_CUDA(cudaMemcpyAsync(out->initialisation_steps, d.initialisation_steps, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SS_CUDA(cudaStreamSynchronize(st));
+  return SSGPU_OK;
+}
+
 int ssgpu_loglik_batch_dev(const double* y, long long B, int V, const ssgpu_model* model, int kernel, double* out,
                            void* stream) {
   SS_ARG(y && out, "null pointer argument");

@@ -54,8 +54,11 @@ __device__ void sandwich_T(double* X, const double* Ts, double* tmp, int m, int 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(512) bwd_generic_kernel(const BwdArgs A) {
+__global__ void __launch_bounds__(512) bwd_generic_kernel(const BwdArgs A_) {
   extern __shared__ double sm[];
+  const long long b = blockIdx.x;  // batched KalmanC: one CTA per series, the b-th block of every array
+  BwdArgs A = A_;
+  kalman_shift(A.k, A.s, b, A.md.N, A.md.p, A.md.m, A.md.r, A.md.Q.tv() || A.md.R.tv());
   const DModel& md = A.md;
   const int m = md.m, p = md.p, r = md.r, N = md.N;
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -88,19 +91,19 @@ __global__ void __launch_bounds__(512) bwd_generic_kernel(const BwdArgs A) {
     Nn[q] = 0.0;
     N1[q] = 0.0;
     N2[q] = 0.0;
-    Ts[q] = mat_get(md.T.block(0, 0, 0), md.T.diag, m, q % m, q / m);
+    Ts[q] = mat_get(md.T.block(b, 0, 0), md.T.diag, m, q % m, q / m);
   }
   for (int q = tid; q < m; q += NT) {
     rv[q] = 0.0;
     r1[q] = 0.0;
   }
-  for (int q = tid; q < p * m; q += NT) Zs[q] = md.Z.block(0, 0, md.Z.tv() ? N - 1 : 0)[q];
+  for (int q = tid; q < p * m; q += NT) Zs[q] = md.Z.block(b, 0, md.Z.tv() ? N - 1 : 0)[q];
   // r_vec row N and Nmat slice N are zero (src/KalmanC.cpp:98-101); eta row N-1 = QtR * 0
   for (int q = tid; q < m; q += NT)
     if (K.r_vec) K.r_vec[N + (long long)(N + 1) * q] = 0.0;
   for (int q = tid; q < mm; q += NT)
     if (K.Nmat) K.Nmat[(long long)N * mm + q] = 0.0;
-  const double* Qlast = md.Q.block(0, 0, md.Q.tv() ? N - 1 : 0);
+  const double* Qlast = md.Q.block(b, 0, md.Q.tv() ? N - 1 : 0);
   for (int q = tid; q < r; q += NT)
     if (K.eta) K.eta[(N - 1) + (long long)N * q] = 0.0;
   for (int q = tid; q < r * r; q += NT)
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(512) bwd_generic_kernel(const BwdArgs A) {
 
   for (int t = N - 1; t >= 0; t--) {
     if (md.Z.tv() && t < N - 1) {
-      for (int q = tid; q < p * m; q += NT) Zs[q] = md.Z.block(0, 0, t)[q];
+      for (int q = tid; q < p * m; q += NT) Zs[q] = md.Z.block(b, 0, t)[q];
       __syncthreads();
     }
     for (int j = p - 1; j >= 0; j--) {
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(512) bwd_generic_kernel(const BwdArgs A) {
       // r and N for the previous time point (:551-558), T of time t-1
       if (md.T.tv()) {
         for (int q = tid; q < mm; q += NT)
-          Ts[q] = mat_get(md.T.block(0, 0, t - 1), md.T.diag, m, q % m, q / m);
+          Ts[q] = mat_get(md.T.block(b, 0, t - 1), md.T.diag, m, q % m, q / m);
         __syncthreads();
       }
       for (int jj = tid; jj < m; jj += NT) {
@@ -305,7 +308,7 @@ static size_t bwd_smem_bytes(const DModel& md) {
 }
 
 int launch_bwd_generic(const DModel& md, const ssgpu_kalman_out* kout, const KalmanScratch* scratch,
-                       cudaStream_t st) {
+                       cudaStream_t st, long long B) {
   BwdArgs A{};
   A.md = md;
   A.k = *kout;
@@ -317,7 +320,7 @@ int launch_bwd_generic(const DModel& md, const ssgpu_kalman_out* kout, const Kal
   if (nt > 512) nt = 512;
   if (nt < 32) nt = 32;
   SS_CUDA(cudaFuncSetAttribute(bwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  bwd_generic_kernel<<<1, nt, smem, st>>>(A);
+  bwd_generic_kernel<<<(unsigned)B, nt, smem, st>>>(A);
   count_launch();
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;

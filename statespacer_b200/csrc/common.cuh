@@ -80,6 +80,29 @@ struct KalmanScratch {
   double* QtR;  // [N*r*m] Q_t R_t' per time point (src/KalmanC.cpp:107-109,139-142), r x m col-major
 };
 
+// Batched KalmanC: series b owns the b-th block of every output / scratch array (each block in the reference's
+// layout for one series).  Null members stay null.
+__host__ __device__ inline void kalman_shift(ssgpu_kalman_out& k, KalmanScratch& s, long long b, int N, int p, int m,
+                                             int r, bool qtr_tv) {
+  const long long Np = (long long)N * p, mm = (long long)m * m, Nm = (long long)N * m;
+  auto sh = [&](double*& x, long long n) {
+    if (x) x += b * n;
+  };
+  if (k.initialisation_steps) k.initialisation_steps += b;
+  sh(k.loglik, Np); sh(k.a_pred, Nm); sh(k.a_fil, Nm); sh(k.a_smooth, Nm);
+  sh(k.P_pred, mm * N); sh(k.P_fil, mm * N); sh(k.V, mm * N); sh(k.P_inf_pred, mm * N); sh(k.P_star_pred, mm * N);
+  sh(k.P_inf_fil, mm * N); sh(k.P_star_fil, mm * N);
+  sh(k.yfit, Np); sh(k.v, Np); sh(k.v_norm, Np); sh(k.e, Np);
+  sh(k.eta, (long long)N * r); sh(k.Fmat, (long long)p * p * N); sh(k.eta_var, (long long)r * r * N);
+  sh(k.D, (long long)p * p * N);
+  sh(k.a_fc, m); sh(k.P_inf_fc, mm); sh(k.P_star_fc, mm); sh(k.P_fc, mm);
+  sh(k.Tstat_observation, Np); sh(k.Tstat_state, (long long)(N + 1) * m);
+  sh(k.r_vec, (long long)(N + 1) * m); sh(k.Nmat, mm * (N + 1));
+  if (s.code) s.code += b * Np;
+  sh(s.F1, Np); sh(s.F2, Np); sh(s.v, Np); sh(s.K0, Np * m); sh(s.K1, Np * m);
+  sh(s.QtR, (long long)(qtr_tv ? N : 1) * r * m);
+}
+
 // ---- device memory: stream-ordered allocations from the default pool (cached by the driver) ---
 cudaStream_t lib_stream();
 int ensure_device();
@@ -111,7 +134,7 @@ int launch_gains_generic(const DModel& md, int init_steps, const KalmanScratch* 
 int launch_kalman_diag(const DModel& md, const ssgpu_kalman_out* kout, const int* code, double* scratch,
                        cudaStream_t st);
 int launch_bwd_generic(const DModel& md, const ssgpu_kalman_out* kout, const KalmanScratch* scratch,
-                       cudaStream_t st);
+                       cudaStream_t st, long long B = 1);
 
 // ---- simulation smoother (sim.cu) --------------------------------------------------------------
 // Non-zero pattern of a (possibly time-varying) matrix, the union over its slices: the entries of row i (or of

@@ -59,14 +59,17 @@ __device__ __forceinline__ void mm_nt(double* C, const double* A, const double* 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A) {
+__global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A_) {
   constexpr bool KALMAN = MODE == MODE_KALMAN, GAINS = MODE == MODE_GAINS;
   extern __shared__ double sm[];
+  const long long e = blockIdx.x;
+  const long long b = e % A_.B, v = e / A_.B;
+  FwdArgs A = A_;
+  // batched KalmanC: this CTA's series owns the b-th block of every output and scratch array
+  if (KALMAN) kalman_shift(A.k, A.s, b, A.md.N, A.md.p, A.md.m, A.md.r, A.md.Q.tv() || A.md.R.tv());
   const DModel& md = A.md;
   const int m = md.m, p = md.p, r = md.r, N = md.N;
   const int tid = threadIdx.x, NT = blockDim.x;
-  const long long e = blockIdx.x;
-  const long long b = e % A.B, v = e / A.B;
   const int mm = m * m;
   int wsz = mm;
   if (m * r > wsz) wsz = m * r;
@@ -383,12 +386,12 @@ int launch_fwd_generic(const DModel& md, const double* y, long long B, int V, do
   SS_ARG(E > 0 && E < (1LL << 31), "generic filter: batch size out of range");
   const int nt = pick_threads(md.m, E > 1);
   if (kout) {
-    SS_ARG(B == 1 && V == 1 && scratch, "KalmanC runs one series per call");
+    SS_ARG(V == 1 && scratch, "KalmanC runs one parameter vector per series");
     A.k = *kout;
     A.s = *scratch;
     SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<MODE_KALMAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
-    fwd_generic_kernel<MODE_KALMAN><<<1, nt, smem, st>>>(A);
+    fwd_generic_kernel<MODE_KALMAN><<<(unsigned)B, nt, smem, st>>>(A);
     set_last_kernel("fwd_generic_kernel<KALMAN>");
   } else {
     SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<MODE_LOGLIK>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -653,6 +653,43 @@ def test_fast_smoother_airline_sim_smoother_pipeline():
     assert np.array_equal(sims["gpu"][2], sims["cpu"][2])
 
 
+@pytest.mark.parametrize("case", ["bsm12", "random_tv"])
+def test_kalman_batch(case):
+    """Batched KalmanC (filter + smoother of B series in one call, only the requested arrays returned) against the
+    single-series entry point and the compiled reference."""
+    rng = np.random.default_rng(8)
+    if case == "bsm12":
+        B, N = 19, 40
+        thetas, Qd, Pd, y = _bsm_batch(rng, B, N, 1, 0.08)
+        sm = sysmat.bsm12(thetas[0, 0])
+        per = dict(Q_diag=Qd[0], P_star_diag=Pd[0])
+        sms = [sysmat.bsm12(thetas[0, b]) for b in range(B)]
+        y3 = y[:, None, :]
+    else:
+        B, N = 7, 30
+        sm = random_model(rng, 6, 2, d=2, tv=("Z", "Q"), N=N)
+        y3 = np.stack([simulate_y(rng, sm, N, missing=0.1) for _ in range(B)], axis=2)
+        ab = rng.normal(size=(B, 6))
+        per = dict(a=ab)
+        sms = [sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=sm.Q, a=ab[b], P_inf=sm.P_inf, P_star=sm.P_star) for b in range(B)]
+    want = ("loglik", "a_smooth", "V", "a_fil", "eta", "eta_var", "r_vec", "Nmat", "P_fc", "a_fc", "v", "Fmat")
+    got = api.kalman_batch(y3, sm, want=want, **per)
+    for b in range(B):
+        yb = y3[:, :, b]
+        one = api.KalmanC(yb, np.isnan(yb), *sms[b].args(), False)
+        assert got["initialisation_steps"][b] == one["initialisation_steps"]
+        for k in want:
+            assert np.array_equal(got[k][b], np.asarray(one[k]).reshape(got[k][b].shape), equal_nan=True), (case, b, k)
+        if ref.available() and b % 3 == 0:
+            r0 = ref.KalmanC(yb, np.isnan(yb), *sms[b].args(), False)
+            for k in ("a_smooth", "V", "eta"):
+                assert rel(got[k][b], np.asarray(r0[k]).reshape(got[k][b].shape)) < 1e-8, (case, b, k)
+    lean = api.kalman_batch(y3, sm, want=("a_smooth",), **per)              # intermediates kept as device scratch
+    assert np.array_equal(lean["a_smooth"], got["a_smooth"])
+    with pytest.raises(RuntimeError, match="diagnostics"):
+        api.kalman_batch(y3, sm, want=("a_smooth", "v_norm"), **per)
+
+
 def _sim_smoother_case(kind, rng):
     """Inputs of one SimSmoother() call: the components as R/SimSmoother.R would pass them to SimulateC, the full model
     with the residual states in front and the smoothed estimates of the observed data."""
