@@ -737,6 +737,132 @@ def run_sim_gpu(args):
         dist.destroy_process_group()
 
 
+# ---- batched KalmanC (--workload kalman): filter + smoother of many series, HBM-bound by its outputs -------------
+KAL_METRIC, KAL_UNIT = "kalman_filter_smoother_series_timesteps_per_s", "series*timesteps/s"
+KAL_SETS = {"lean": ("loglik", "a_smooth", "V"),
+            "full": ("loglik", "a_pred", "a_fil", "a_smooth", "P_pred", "P_fil", "V", "P_inf_pred", "P_star_pred",
+                     "P_inf_fil", "P_star_fil", "yfit", "v", "eta", "Fmat", "eta_var", "r_vec", "Nmat")}
+
+
+def run_kalman_gpu(args):
+    """StateSpaceEval() over a batch (SURVEY.md 8d, row `KalmanC` batched): config-5 model, B series per GPU, the
+    arrays of --kalman-out written to HBM.  Roofline: HBM, algorithmic bytes = requested outputs + y."""
+    import torch
+    import torch.distributed as dist
+    from statespacer_b200 import api
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (statespacer_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    api.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.kalman_series
+    sm, y, theta = make_shard(torch, dev, B, rank)
+    var = torch.exp(2 * theta)
+    Qd = torch.cat([var[:, :3], var[:, 3:4].expand(B, 11)], dim=1).contiguous()
+    Pd = torch.zeros(B, M, device=dev, dtype=torch.float64)
+    Pd[:, 0] = var[:, 0]
+    model = api.BatchModel(sm, T_STEPS, B, 1, Q_diag=Qd, P_star_diag=Pd, device=dev)
+    want = KAL_SETS[args.kalman_out]
+    stream = torch.cuda.current_stream(dev)
+    res = {}
+
+    def step():
+        res["o"] = api.kalman_batch_dev(y, model, want=want, stream=stream)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.1)
+    l0 = api.launch_count()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    sync()
+    launches = api.launch_count() - l0
+    clocks = sampler.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = B * T_STEPS * world * args.steps / (elapsed_ms * 1e-3)
+    shapes = api.kalman_shapes(T_STEPS, 1, M, M, False)
+    out_bytes = 8 * sum(int(np.prod(shapes[k])) for k in want)
+    finite = bool(torch.isfinite(res["o"]["a_smooth"]).all().item())
+    # end to end: host arrays in, the requested arrays out
+    Be = min(B, args.kalman_e2e_series)
+    y_h = y[:, :Be].contiguous().cpu().numpy()
+    Qh, Ph = Qd[:Be].cpu().numpy(), Pd[:Be].cpu().numpy()
+    api.kalman_batch(y_h, sm, want=want, Q_diag=Qh, P_star_diag=Ph)
+    t0 = time.perf_counter()
+    api.kalman_batch(y_h, sm, want=want, Q_diag=Qh, P_star_diag=Ph)
+    e2e_s = time.perf_counter() - t0
+    if rank == 0:
+        hbm_peak, peak_src = 6545.3, "fallback"
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            peak_src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+        alg = (out_bytes + 8 * T_STEPS) * B
+        achieved = alg * args.steps / (elapsed_ms * 1e-3) / 1e9
+        line = {"metric": KAL_METRIC, "value": value, "unit": KAL_UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "KalmanC batched (filter + smoother): config-5 model, m=r=14, d=13 diffuse, T=1000",
+                           "series_per_gpu": B, "outputs": list(want), "bytes_out_per_series_timestep": out_bytes / T_STEPS,
+                           "l2": "outputs larger than L2 (%.1f GB per GPU), no flush" % (out_bytes * B / 1e9),
+                           "results_finite": finite},
+                "clocks": clocks,
+                "e2e": {"value": Be * T_STEPS * world / e2e_s, "unit": KAL_UNIT, "h2d_bytes_per_step": 8 * Be * (T_STEPS + 2 * M),
+                        "d2h_bytes_per_step": out_bytes * Be, "steps": 1, "series": Be,
+                        "note": "ssgpu_kalman_batch, host pointers, pageable memory"},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": "fwd_generic_kernel<KALMAN> + bwd_generic_kernel",
+                             "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                             "traffic": None, "peak_source": peak_src,
+                             "note": "algorithmic bytes = the requested output arrays + y; both kernels of a step together"}}
+        if world == 1 and not args.no_cpu:
+            from concurrent.futures import ThreadPoolExecutor
+            from oracle import cport, ref
+            mod, kind = (ref, "reference") if ref.available() else (cport, "port")
+            cores = host_cores()
+            from statespacer_b200 import sysmat
+            ys = y[:, :cores * 2].cpu().numpy()
+            ths = theta[:cores * 2].cpu().numpy()
+
+            def one(b):
+                smb = sysmat.bsm12(ths[b])
+                yb = ys[:, b:b + 1]
+                return mod.KalmanC(yb, np.isnan(yb), *smb.args(), False)["a_smooth"][0, 0]
+
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(cores) as ex:
+                list(ex.map(one, range(cores * 2)))
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": cores * 2 * T_STEPS / dt, "unit": KAL_UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{cores * 2} series x {T_STEPS} timesteps, one KalmanC call per series, "
+                                              f"{cores} threads ({dt:.1f} s)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -747,14 +873,20 @@ def main():
     ap.add_argument("--missing", type=float, default=0.0, help="fraction of NaN observations (variant B: 0.02)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "blk", "mma", "mma_dense", "cols", "wsm", "generic"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="loglik", choices=["loglik", "sim"],
-                    help="loglik: config 5 (headline, default); sim: config 4 simulation smoother draws")
+    ap.add_argument("--workload", default="loglik", choices=["loglik", "sim", "kalman"],
+                    help="loglik: config 5 (headline, default); sim: config 4 simulation smoother draws; "
+                         "kalman: batched filter + smoother (KalmanC) of config-5 series")
+    ap.add_argument("--kalman-series", type=int, default=2048, help="series per GPU (--workload kalman)")
+    ap.add_argument("--kalman-e2e-series", type=int, default=256, help="series of the end-to-end leg (--workload kalman)")
+    ap.add_argument("--kalman-out", default="lean", choices=list(KAL_SETS), help="output arrays (--workload kalman)")
     ap.add_argument("--nsim", type=int, default=NSIM_PER_GPU, help="draws per GPU (--workload sim)")
     ap.add_argument("--e2e-nsim", type=int, default=NSIM_PER_GPU, help="draws of the end-to-end leg (--workload sim)")
     ap.add_argument("--cpu-draws", type=int, default=128, help="draws per host thread of the CPU arm (--workload sim)")
     args = ap.parse_args()
     if args.workload == "sim":
         run_sim_reference(args) if args.impl == "reference" else run_sim_gpu(args)
+    elif args.workload == "kalman":
+        run_kalman_gpu(args)
     elif args.impl == "reference":
         run_reference(args)
     else:
