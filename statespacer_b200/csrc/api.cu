@@ -277,6 +277,7 @@ int ssgpu_release(void) {
   cudaMemPool_t pool;
   SS_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_device));
   SS_CUDA(cudaMemPoolTrimTo(pool, 0));
+  xfer_release();
   return SSGPU_OK;
 }
 
@@ -488,7 +489,7 @@ int ssgpu_kalman_batch(const double* y, long long B, const ssgpu_model* model, c
   SS_TRY(blk.alloc(total * sizeof(double), st));
   double* base = blk.as<double>();
   size_t off = 0;
-  SS_CUDA(cudaMemcpyAsync(base, y, n_y * sizeof(double), cudaMemcpyHostToDevice, st));
+  SS_TRY(copy_h2d(base, y, n_y * sizeof(double), st));
   off += pad(n_y);
   for (int i = 0; i < 7; i++) {
     SS_CUDA(cudaMemcpyAsync(base + off, src[i]->data, ext[i] * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -505,7 +506,7 @@ int ssgpu_kalman_batch(const double* y, long long B, const ssgpu_model* model, c
   SS_TRY(kalman_batch_core(md, base, B, d, st));
   for (const KField& f : fields)
     if (out->*(f.ptr))
-      SS_CUDA(cudaMemcpyAsync(out->*(f.ptr), d.*(f.ptr), f.n * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+      SS_TRY(copy_d2h(out->*(f.ptr), d.*(f.ptr), f.n * nb * sizeof(double), st));
   if (out->initialisation_steps)
     SS_CUDA(cudaMemcpyAsync(out->initialisation_steps, d.initialisation_steps, nb * sizeof(int), cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));
@@ -542,7 +543,7 @@ int ssgpu_loglik_batch(const double* y, long long B, int V, const ssgpu_model* m
   SS_TRY(blk.alloc(total * sizeof(double), st));
   double* base = blk.as<double>();
   size_t off = 0;
-  SS_CUDA(cudaMemcpyAsync(base, y, n_y * sizeof(double), cudaMemcpyHostToDevice, st));
+  SS_TRY(copy_h2d(base, y, n_y * sizeof(double), st));
   off += pad(n_y);
   for (int i = 0; i < 7; i++) {
     SS_CUDA(cudaMemcpyAsync(base + off, src[i]->data, ext[i] * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -678,7 +679,7 @@ int ssgpu_loglik_grad_batch(const double* y, long long B, const ssgpu_model* mod
   SS_TRY(yd.alloc(n_y * sizeof(double), st));
   SS_TRY(thd.alloc((size_t)B * k * sizeof(double), st));
   SS_TRY(res.alloc((size_t)B * (1 + k) * sizeof(double), st));
-  SS_CUDA(cudaMemcpyAsync(yd.get(), y, n_y * sizeof(double), cudaMemcpyHostToDevice, st));
+  SS_TRY(copy_h2d(yd.get(), y, n_y * sizeof(double), st));
   SS_CUDA(cudaMemcpyAsync(thd.get(), theta, (size_t)B * k * sizeof(double), cudaMemcpyHostToDevice, st));
   ThetaWork W;
   const int V = 1 + 2 * k;

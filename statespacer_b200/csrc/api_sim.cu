@@ -8,7 +8,7 @@ namespace ssgpu {
 
 static int upload(DevBuf& d, const double* src, size_t n, cudaStream_t st) {
   SS_TRY(d.alloc(n * sizeof(double), st));
-  if (n) SS_CUDA(cudaMemcpyAsync(d.get(), src, n * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (n) SS_TRY(copy_h2d(d.get(), src, n * sizeof(double), st));
   return SSGPU_OK;
 }
 
@@ -205,15 +205,15 @@ extern "C" int ssgpu_FastSmootherC(const double* y, int N, int p, int nsim, int 
   SS_TRY(outR.alloc(sizeof(double) * (size_t)N * (m > r ? m : r) * ns, st));
   if (a_smooth) {
     SS_TRY(launch_permute_tks(aN.as<double>(), outR.as<double>(), N, m, nsim, true, st));
-    SS_CUDA(cudaMemcpyAsync(a_smooth, outR.get(), sizeof(double) * (size_t)N * m * ns, cudaMemcpyDeviceToHost, st));
+    SS_TRY(copy_d2h(a_smooth, outR.get(), sizeof(double) * (size_t)N * m * ns, st));
   }
   if (transposed_state && a_t) {
     SS_TRY(launch_permute_at(aN.as<double>(), outR.as<double>(), N, m, nsim, st));
-    SS_CUDA(cudaMemcpyAsync(a_t, outR.get(), sizeof(double) * (size_t)N * m * ns, cudaMemcpyDeviceToHost, st));
+    SS_TRY(copy_d2h(a_t, outR.get(), sizeof(double) * (size_t)N * m * ns, st));
   }
   if (eta) {
     SS_TRY(launch_permute_tks(eN.as<double>(), outR.as<double>(), N, r, nsim, true, st));
-    SS_CUDA(cudaMemcpyAsync(eta, outR.get(), sizeof(double) * (size_t)N * r * ns, cudaMemcpyDeviceToHost, st));
+    SS_TRY(copy_d2h(eta, outR.get(), sizeof(double) * (size_t)N * r * ns, st));
   }
   SS_CUDA(cudaStreamSynchronize(st));
   return SSGPU_OK;
@@ -372,20 +372,20 @@ extern "C" int ssgpu_SimulateC(int nsim, int repeat_Q, int N, int p, int m, int 
   SS_TRY(outR.alloc(sizeof(double) * biggest, st));
   if (eta) {
     SS_TRY(launch_permute_tks(eN.as<double>(), outR.as<double>(), N, r_tot, nsim, true, st));
-    SS_CUDA(cudaMemcpyAsync(eta, outR.get(), sizeof(double) * (size_t)N * r_tot * ns, cudaMemcpyDeviceToHost, st));
+    SS_TRY(copy_d2h(eta, outR.get(), sizeof(double) * (size_t)N * r_tot * ns, st));
   }
   if (!eta_only) {
     if (y) {
       SS_TRY(launch_permute_tks(yN.as<double>(), outR.as<double>(), N, p, nsim, true, st));
-      SS_CUDA(cudaMemcpyAsync(y, outR.get(), sizeof(double) * (size_t)N * p * ns, cudaMemcpyDeviceToHost, st));
+      SS_TRY(copy_d2h(y, outR.get(), sizeof(double) * (size_t)N * p * ns, st));
     }
     if (a_out) {
       SS_TRY(launch_permute_tks(aN.as<double>(), outR.as<double>(), N, m, nsim, true, st));
-      SS_CUDA(cudaMemcpyAsync(a_out, outR.get(), sizeof(double) * (size_t)N * m * ns, cudaMemcpyDeviceToHost, st));
+      SS_TRY(copy_d2h(a_out, outR.get(), sizeof(double) * (size_t)N * m * ns, st));
     }
     if (transposed_state && a_t) {
       SS_TRY(launch_permute_at(aN.as<double>(), outR.as<double>(), N, m, nsim, st));
-      SS_CUDA(cudaMemcpyAsync(a_t, outR.get(), sizeof(double) * (size_t)N * m * ns, cudaMemcpyDeviceToHost, st));
+      SS_TRY(copy_d2h(a_t, outR.get(), sizeof(double) * (size_t)N * m * ns, st));
     }
   }
   SS_CUDA(cudaStreamSynchronize(st));
@@ -474,7 +474,7 @@ extern "C" int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu
   for (const Out& o : outs) {
     if (!o.host) continue;
     SS_TRY(launch_permute_tks(o.dev, outR.as<double>(), N, o.K, nsim, true, st));
-    SS_CUDA(cudaMemcpyAsync(o.host, outR.get(), sizeof(double) * (size_t)N * o.K * ns, cudaMemcpyDeviceToHost, st));
+    SS_TRY(copy_d2h(o.host, outR.get(), sizeof(double) * (size_t)N * o.K * ns, st));
   }
   // components (:645-766): Z_padded a_t per draw, from the corrected states
   if (n_extract > 0) SS_TRY(cN.alloc(sizeof(double) * (size_t)N * p * ns, st));
@@ -483,7 +483,7 @@ extern "C" int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu
     SS_TRY(upload(zD, Z_extract[e], (size_t)p * m * nZ_extract[e], st));
     SS_TRY(launch_extract(aN.as<double>(), 1, dmat3(zD.as<double>(), p, m, nZ_extract[e]), m, p, nsim, N, cN.as<double>(), st));
     SS_TRY(launch_permute_tks(cN.as<double>(), outR.as<double>(), N, p, nsim, true, st));
-    SS_CUDA(cudaMemcpyAsync(extracted[e], outR.get(), sizeof(double) * (size_t)N * p * ns, cudaMemcpyDeviceToHost, st));
+    SS_TRY(copy_d2h(extracted[e], outR.get(), sizeof(double) * (size_t)N * p * ns, st));
   }
   SS_CUDA(cudaStreamSynchronize(st));
   (void)hp;
@@ -529,7 +529,7 @@ extern "C" int ssgpu_ExtractComponentC(const double* a, int m, int nsim, int N, 
   SS_TRY(oR.alloc(sizeof(double) * (size_t)N * p * ns, st));
   SS_TRY(launch_extract(aD.as<double>(), 0, dmat3(zD.as<double>(), p, m, nZ), m, p, nsim, N, oN.as<double>(), st));
   SS_TRY(launch_permute_tks(oN.as<double>(), oR.as<double>(), N, p, nsim, true, st));
-  SS_CUDA(cudaMemcpyAsync(out, oR.get(), sizeof(double) * (size_t)N * p * ns, cudaMemcpyDeviceToHost, st));
+  SS_TRY(copy_d2h(out, oR.get(), sizeof(double) * (size_t)N * p * ns, st));
   SS_CUDA(cudaStreamSynchronize(st));
   return SSGPU_OK;
 }

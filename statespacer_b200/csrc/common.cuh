@@ -124,6 +124,11 @@ class DevBuf {
   cudaStream_t st_ = nullptr;
 };
 
+// ---- large host <-> device copies through pinned staging when the host side is pageable (xfer.cu) ----------
+int copy_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st);   // returns when dst holds the data
+int copy_h2d(void* dst_dev, const void* src, size_t bytes, cudaStream_t st);   // src may be re-used on return
+void xfer_release();
+
 // ---- launchers (implemented in the .cu files) ----------------------------------------------
 // Generic forward filter, one CTA per evaluation (fwd_generic.cu).  kout == nullptr -> loglik only
 // (out_loglik[e]); otherwise B = V = 1 and every non-null member of kout (DEVICE pointers) is filled.
