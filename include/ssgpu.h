@@ -273,6 +273,19 @@ int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu_sim_compon
                       double* epsilon, double* a_out, double* eta,
                       int n_extract, const double* const* Z_extract, const int* nZ_extract, double* const* extracted);
 
+/* ---- 6e. The steps on either side of the path (new) ------------------------------------
+ * ssgpu_collapse: the collapse transform of R/statespacer.R:815-900, done by R inside the optimiser's objective for
+ * every parameter vector of a `collapse = TRUE` model.  y N x p (column-major, NaN = missing, entered as 0 like
+ * :407-409), H p x p x nH, Z p x m2 x nZ (the columns of Z_kal that are collapsed onto), n* in {1, N}, m2 < p <= 16.
+ * y_star N x m2 (NaN where R writes NA: exact zeros), H_star m2 x m2 x max(nH, nZ), *loglik_add as at :823-832.
+ * ssgpu_forecast: the forecast recursion of R/predict.R:205-246 from KalmanC's a_fc / P_fc: y_fc h x p, a_fc h x m,
+ * P_fc m x m x h, Fmat_fc p x p x h; Z p x m, T m x m, R m x r, Q r x r, H p x p with 1 or h slices each. */
+int ssgpu_collapse(const double* y, int N, int p, int m2, const double* H, int nH, const double* Z, int nZ,
+                   double* y_star, double* H_star, double* loglik_add);
+int ssgpu_forecast(int h, int p, int m, int r, const double* a1, const double* P1, const double* Z, int nZ,
+                   const double* T, int nT, const double* R, int nR, const double* Q, int nQ, const double* H, int nH,
+                   double* y_fc, double* a_fc, double* P_fc, double* Fmat_fc);
+
 /* Host-only helper (no device needed): the internal state order the tensor kernel would use for a shared
  * m x m transition matrix T (column-major, m <= 23).  perm[i] = caller's index of the state at internal
  * position i; *tile_mask has bit rt*TT + ct set when the 8 x 8 tile (rt, ct) of the re-ordered T holds a

@@ -69,3 +69,12 @@ SimSmootherC <- function(nsim, N, p, comps, H, full, initialisation_steps, smoot
   .Call(`_statespacer_SimSmootherC`, as.integer(nsim), as.integer(N), as.integer(p), comps, H, full,
         as.integer(initialisation_steps), smoothed$a, smoothed$epsilon, smoothed$eta, Z_extract)
 }
+
+#' Collapse transform of R/statespacer.R:815-900 in one call (replaces the four branches there):
+#' list(y = collapsed observations with NA, H_star, loglik_add).
+CollapseC <- function(y, H, Z) .Call(`_statespacer_CollapseC`, y, H, Z)
+
+#' Forecast recursion of R/predict.R:205-246: list(y_fc, a_fc, P_fc, Fmat_fc) from object$predicted$a_fc / P_fc.
+ForecastC <- function(forecast_period, a_fc, P_fc, Z, T, R, Q, H) {
+  .Call(`_statespacer_ForecastC`, as.integer(forecast_period), a_fc, P_fc, Z, T, R, Q, H)
+}

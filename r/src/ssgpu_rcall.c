@@ -364,6 +364,52 @@ SEXP _statespacer_SimSmootherC(SEXP nsim_, SEXP N_, SEXP p_, SEXP comps, SEXP H,
   return res;
 }
 
+/* New: the collapse transform of R/statespacer.R:815-900 (y N x p with NA, H p x p [x N], Z p x m2 [x N]) ->
+ * list(y = N x m2 with NA, H_star = m2 x m2 x {1|N}, loglik_add). */
+SEXP _statespacer_CollapseC(SEXP y, SEXP H, SEXP Z) {
+  int N, p, one, hr, hc, nH, zr, m2, nZ;
+  dims3(y, &N, &p, &one);
+  dims3(H, &hr, &hc, &nH);
+  dims3(Z, &zr, &m2, &nZ);
+  const int ns = (nH > 1 || nZ > 1) ? N : 1;
+  double* yy = (double*)R_alloc((size_t)N * p, sizeof(double));
+  for (R_xlen_t i = 0; i < (R_xlen_t)N * p; i++) yy[i] = ISNAN(REAL(y)[i]) ? R_NaN : REAL(y)[i];
+  SEXP ys = PROTECT(Rf_allocMatrix(REALSXP, N, m2));
+  SEXP Hs = alloc3(m2, m2, ns);
+  double la = 0.0;
+  int rc = ssgpu_collapse(yy, N, p, m2, REAL(H), nH, REAL(Z), nZ, REAL(ys), REAL(Hs), &la);
+  if (rc != SSGPU_OK) { UNPROTECT(2); chk(rc); }
+  for (R_xlen_t i = 0; i < (R_xlen_t)N * m2; i++)
+    if (ISNAN(REAL(ys)[i])) REAL(ys)[i] = NA_REAL;
+  const char* names[] = {"y", "H_star", "loglik_add", ""};
+  SEXP res = PROTECT(Rf_mkNamed(VECSXP, names));
+  SET_VECTOR_ELT(res, 0, ys); SET_VECTOR_ELT(res, 1, Hs); SET_VECTOR_ELT(res, 2, Rf_ScalarReal(la));
+  UNPROTECT(3);
+  return res;
+}
+
+/* New: the forecast recursion of R/predict.R:205-246 -> list(y_fc, a_fc, P_fc, Fmat_fc). */
+SEXP _statespacer_ForecastC(SEXP h_, SEXP a1, SEXP P1, SEXP Z, SEXP T, SEXP R, SEXP Q, SEXP H) {
+  const int h = Rf_asInteger(h_), m = Rf_length(a1);
+  int p, zc, nZ, tr, tc, nT, rr, r, nR, qr, qc, nQ, hr, hc, nH;
+  dims3(Z, &p, &zc, &nZ);
+  dims3(T, &tr, &tc, &nT);
+  dims3(R, &rr, &r, &nR);
+  dims3(Q, &qr, &qc, &nQ);
+  dims3(H, &hr, &hc, &nH);
+  SEXP y_fc = PROTECT(Rf_allocMatrix(REALSXP, h, p));
+  SEXP a_fc = PROTECT(Rf_allocMatrix(REALSXP, h, m));
+  SEXP P_fc = alloc3(m, m, h), F_fc = alloc3(p, p, h);
+  int rc = ssgpu_forecast(h, p, m, r, REAL(a1), REAL(P1), REAL(Z), nZ, REAL(T), nT, REAL(R), nR, REAL(Q), nQ, REAL(H), nH,
+                          REAL(y_fc), REAL(a_fc), REAL(P_fc), REAL(F_fc));
+  if (rc != SSGPU_OK) { UNPROTECT(4); chk(rc); }
+  const char* names[] = {"y_fc", "a_fc", "P_fc", "Fmat_fc", ""};
+  SEXP res = PROTECT(Rf_mkNamed(VECSXP, names));
+  SET_VECTOR_ELT(res, 0, y_fc); SET_VECTOR_ELT(res, 1, a_fc); SET_VECTOR_ELT(res, 2, P_fc); SET_VECTOR_ELT(res, 3, F_fc);
+  UNPROTECT(5);
+  return res;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_statespacer_ExtractComponentC", (DL_FUNC)&_statespacer_ExtractComponentC, 2},
     {"_statespacer_FastSmootherC", (DL_FUNC)&_statespacer_FastSmootherC, 10},
@@ -373,6 +419,8 @@ static const R_CallMethodDef CallEntries[] = {
     {"_statespacer_LogLikBatchC", (DL_FUNC)&_statespacer_LogLikBatchC, 11},
     {"_statespacer_LogLikGradBatchC", (DL_FUNC)&_statespacer_LogLikGradBatchC, 12},
     {"_statespacer_SimSmootherC", (DL_FUNC)&_statespacer_SimSmootherC, 11},
+    {"_statespacer_CollapseC", (DL_FUNC)&_statespacer_CollapseC, 3},
+    {"_statespacer_ForecastC", (DL_FUNC)&_statespacer_ForecastC, 8},
     {NULL, NULL, 0}};
 
 void R_init_statespacer(DllInfo* dll) {

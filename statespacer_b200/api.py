@@ -205,6 +205,38 @@ def ExtractComponentC(a, Z):
     return out
 
 
+def collapse(y, H, Z):
+    """Collapse transform of R/statespacer.R:815-900 (include/ssgpu.h section 6e).  y N x p (NaN = missing),
+    H p x p x {1|N}, Z p x m2 x {1|N}.  Returns y_star (N x m2, NaN where R writes NA), H_star (m2 x m2 x {1|N}),
+    loglik_add."""
+    y = _f(y)
+    H, Z = _cube(H, "H"), _cube(Z, "Z")
+    N, p = y.shape
+    m2 = Z.shape[1]
+    ns = N if (H.shape[2] > 1 or Z.shape[2] > 1) else 1
+    y_star = np.zeros((N, m2), order="F")
+    H_star = np.zeros((m2, m2, ns), order="F")
+    la = C.c_double()
+    native.check(native.lib().ssgpu_collapse(_ptr(y), N, p, m2, _ptr(H), H.shape[2], _ptr(Z), Z.shape[2], _ptr(y_star),
+                                             _ptr(H_star), C.addressof(la)))
+    return y_star, H_star, la.value
+
+
+def forecast(h, a1, P1, Z, T, R, Q, H):
+    """Forecast recursion of R/predict.R:205-246 from KalmanC's a_fc / P_fc.  Returns y_fc (h x p), a_fc (h x m),
+    P_fc (m x m x h), Fmat_fc (p x p x h)."""
+    a1 = _f(np.asarray(a1, dtype=np.float64).reshape(-1))
+    P1 = _f(P1)
+    Z, T, R, Q, H = _cube(Z, "Z"), _cube(T, "T"), _cube(R, "R"), _cube(Q, "Q"), _cube(H, "H")
+    p, m, r = Z.shape[0], a1.shape[0], Q.shape[0]
+    y_fc, a_fc = np.zeros((h, p), order="F"), np.zeros((h, m), order="F")
+    P_fc, F_fc = np.zeros((m, m, h), order="F"), np.zeros((p, p, h), order="F")
+    native.check(native.lib().ssgpu_forecast(h, p, m, r, _ptr(a1), _ptr(P1), _ptr(Z), Z.shape[2], _ptr(T), T.shape[2],
+                                             _ptr(R), R.shape[2], _ptr(Q), Q.shape[2], _ptr(H), H.shape[2], _ptr(y_fc),
+                                             _ptr(a_fc), _ptr(P_fc), _ptr(F_fc)))
+    return y_fc, a_fc, P_fc, F_fc
+
+
 def SimSmoother(nsim, N, p, comps, H, full, initialisation_steps, a_hat, eps_hat, eta_hat, draws, extract=(), roots=None):
     """R/SimSmoother.R:34-769 as one call (include/ssgpu.h section 6d): the unconditional draws of every component,
     the simulated data, their smoothed states, the mean corrections and the extracted components without the per-draw

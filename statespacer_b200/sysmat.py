@@ -299,6 +299,24 @@ def dns_yield_curve(param):
     return _combine(8, H, [comp]), Phi
 
 
+def dns_collapsed(param, H_star):
+    """Config 3 with collapse = TRUE (R/statespacer.R:380-405,815-832): the 8 yields are collapsed onto the m2 = 3
+    factors, state = [3 residual states of the collapsed observations ; 6 component states], p = 3, m = r = 9.
+    `H_star` (3 x 3) is the variance of the collapsed observation error, A* H A*' from the collapse transform."""
+    sm, _ = dns_yield_curve(param)
+    c = dict(Z=None, T=sm.T[8:, 8:, 0], R=sm.R[8:, 8:, 0], Q=sm.Q[8:, 8:, 0], a=sm.a[8:], P_inf=sm.P_inf[8:, 8:],
+             P_star=sm.P_star[8:, 8:])
+    Hs = np.asarray(H_star, dtype=np.float64).reshape(3, 3)
+    Z = np.concatenate([np.eye(3), np.eye(3), np.zeros((3, 3))], axis=1)               # Z_kal_tf, :399-402
+    T = block_diag(np.zeros((3, 3)), c["T"])
+    R = block_diag(np.eye(3), c["R"])
+    Q = block_diag(Hs, c["Q"])
+    a = np.concatenate([np.zeros(3), c["a"]])
+    P_inf = block_diag(np.zeros((3, 3)), c["P_inf"])
+    P_star = block_diag(Hs, c["P_star"])
+    return SysMat(Z[:, :, None], T[:, :, None], R[:, :, None], Q[:, :, None], a, P_inf, P_star)
+
+
 def bsm_multivariate_regressors(X_list, H, Q_level, Q_slope, Q_seas, s=12):
     """Config 2 shape (Seatbelts-style): p dependent variables with local level + slope
     (R/Components-Unobserved.R:138-184), trigonometric seasonal (:476-536) and explanatory variables with

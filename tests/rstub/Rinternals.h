@@ -10,7 +10,7 @@ typedef unsigned int SEXPTYPE;
 #define VECSXP 19
 typedef enum { FALSE = 0, TRUE } Rboolean;
 extern SEXP R_NilValue, R_DimSymbol, R_NamesSymbol;
-extern double R_NaReal;
+extern double R_NaReal, R_NaN;
 #define NA_REAL R_NaReal
 #define ISNAN(x) ((x) != (x))
 double* REAL(SEXP);

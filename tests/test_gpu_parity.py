@@ -690,6 +690,54 @@ def test_kalman_batch(case):
         api.kalman_batch(y3, sm, want=("a_smooth", "v_norm"), **per)
 
 
+@pytest.mark.parametrize("tv", [(), ("H",), ("Z",), ("H", "Z")])
+def test_collapse_transform(tv):
+    """ssgpu_collapse (R/statespacer.R:815-900) against the NumPy restatement for time-invariant and time-varying H / Z,
+    missing observations and all-zero collapsed values; KAT-3 through the collapsed model on the GPU."""
+    from oracle import collapse_np
+    rng = np.random.default_rng(21)
+    N, p, m2 = 50, 7, 3
+    mk = lambda base, name, f: np.stack([f(base, i) for i in range(N)], axis=2) if name in tv else base[:, :, None]
+    A = rng.normal(size=(p, p))
+    H = mk(A @ A.T / p + np.eye(p), "H", lambda B, i: B * (1.0 + 0.2 * math.sin(i)))
+    Z = mk(rng.normal(size=(p, m2)), "Z", lambda B, i: B + 0.05 * math.cos(i))
+    y = rng.normal(size=(N, p)) * 2
+    y[rng.uniform(size=y.shape) < 0.1] = np.nan
+    y[7] = np.nan                                                       # a time point without observations: y* = 0 -> NA
+    ys, Hs, la = api.collapse(y, H, Z)
+    ys0, Hs0, la0 = collapse_np.collapse(y, H, Z)
+    assert rel(ys, ys0) < RTOL and np.all(np.isnan(ys[7]))
+    assert rel(Hs, Hs0) < RTOL
+    assert abs(la - la0) <= RTOL * max(1, abs(la0))
+    if not tv:
+        fed = load_fed()
+        sm, _ = sysmat.dns_yield_curve(DNS_PARAM)
+        yk, Hk, lk = api.collapse(fed, sm.Q[:8, :8, 0], sm.Z[:, 8:11, 0])
+        smc = sysmat.dns_collapsed(DNS_PARAM, Hk[:, :, 0])
+        ll = api.LogLikC(yk, np.isnan(yk), *smc.args()) + lk / len(fed)
+        assert abs(ll - 7.005830) < 6e-7 * 7                            # docs/articles/selfspec.html:306-307
+    with pytest.raises(RuntimeError, match="m2 < p"):
+        api.collapse(y[:, :3], H[:3, :3], Z[:3])
+
+
+@pytest.mark.parametrize("tv", [False, True])
+def test_forecast_recursion(tv):
+    """ssgpu_forecast (R/predict.R:205-246) started from the GPU KalmanC's a_fc / P_fc, against the NumPy restatement."""
+    from oracle import forecast_np
+    rng = np.random.default_rng(33)
+    h, N = 12, 40
+    sm = random_model(rng, 7, 2, d=2, N=N, tv=())
+    y = simulate_y(rng, sm, N, missing=0.05)
+    ks = api.KalmanC(y, np.isnan(y), *sm.args(), False)
+    rep = (lambda X: np.stack([X[:, :, 0] * (1 + 0.05 * i) for i in range(h)], axis=2)) if tv else (lambda X: X)
+    Z, T, R, Q = rep(sm.Z), rep(sm.T), rep(sm.R), rep(sm.Q)
+    H = rep((np.eye(2) * 0.3)[:, :, None])
+    got = api.forecast(h, ks["a_fc"], ks["P_fc"], Z, T, R, Q, H)
+    want = forecast_np.forecast(h, ks["a_fc"], ks["P_fc"], Z, T, R, Q, H)
+    for g, w in zip(got, want):
+        assert rel(g, w) < RTOL
+
+
 def _sim_smoother_case(kind, rng):
     """Inputs of one SimSmoother() call: the components as R/SimSmoother.R would pass them to SimulateC, the full model
     with the residual states in front and the smoothed estimates of the observed data."""

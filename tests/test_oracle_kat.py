@@ -59,3 +59,28 @@ def test_dns_phi_golden():
     from conftest import DNS_PARAM
     _, Phi = sysmat.dns_yield_curve(DNS_PARAM)
     assert np.all(np.abs(np.linalg.eigvals(Phi)) < 1)
+
+
+def test_collapse_transform_kat3():
+    """The collapse transform (R/statespacer.R:815-900) is likelihood preserving: KAT-3 with collapse = TRUE (p = 3,
+    m = 9, vignettes/selfspec.Rmd:87-90) gives the printed 7.005830 like the uncollapsed model (p = 8, m = 14)."""
+    from conftest import DNS_PARAM, load_fed
+    from oracle import collapse_np
+    fed = load_fed()
+    sm, _ = sysmat.dns_yield_curve(DNS_PARAM)
+    yk, Hs, la = collapse_np.collapse(fed, sm.Q[:8, :8, 0], sm.Z[:, 8:11, 0])
+    smc = sysmat.dns_collapsed(DNS_PARAM, Hs[:, :, 0])
+    assert (smc.p, smc.m) == (3, 9)
+    ll = kalman_np.LogLikC(yk, np.isnan(yk), *smc.args()) + la / len(fed)
+    assert abs(ll - 7.005830) < 6e-7 * 7
+    assert abs(ll - kalman_np.LogLikC(fed, np.isnan(fed), *sm.args())) < 1e-11 * 7
+
+
+def test_forecast_recursion_local_level_closed_form():
+    """R/predict.R:205-246 on a local level model: the forecast is flat and its variance grows by Q per step."""
+    from oracle import forecast_np
+    H, Qv, a, P = 2.0, 0.5, 3.0, 1.25
+    y_fc, a_fc, P_fc, F_fc = forecast_np.forecast(6, [a], [[P]], np.ones((1, 1, 1)), np.ones((1, 1, 1)),
+                                                  np.ones((1, 1, 1)), np.full((1, 1, 1), Qv), np.full((1, 1, 1), H))
+    assert np.allclose(y_fc[:, 0], a) and np.allclose(a_fc[:, 0], a)
+    assert np.allclose(P_fc[0, 0], P + Qv * np.arange(6)) and np.allclose(F_fc[0, 0], P + Qv * np.arange(6) + H)
