@@ -307,6 +307,33 @@ def test_batch_blk_kernel_bivariate_dense_blocks():
         assert abs(got[b] - want) <= RTOL * max(1, abs(want)), (b, got[b], want)
 
 
+@pytest.mark.parametrize("N", [1, 2, 14, 40])
+def test_batch_blk_kernel_degenerate_series(N):
+    """Series of one warp that behave differently: all observations missing (NA, src/LogLikC.cpp:211-213), missing
+    until late (the group leaves the diffuse phase long after its neighbours, or never), zero variances (F = 0 after the
+    initialisation), very short series (N = 1: only a diffuse step)."""
+    rng = np.random.default_rng(50 + N)
+    B = 13
+    thetas, Qd, Pd, y = _bsm_batch(rng, B, N, 1, 0.1)
+    Qd, Pd = Qd[0].copy(), Pd[0].copy()
+    y[:, 1] = np.nan                                  # never observed
+    y[: max(N - 3, 0), 2] = np.nan                    # observed only at the end: still diffuse when the data stop
+    y[: N // 2, 3] = np.nan
+    Qd[4], Pd[4] = 0.0, 0.0                           # no noise at all
+    got = api.loglik_batch(y, sysmat.bsm12(thetas[0, 0]), Q_diag=Qd, P_star_diag=Pd, kernel="blk")
+    gen = api.loglik_batch(y, sysmat.bsm12(thetas[0, 0]), Q_diag=Qd, P_star_diag=Pd, kernel="generic")
+    for b in range(B):
+        sm = sysmat.bsm12(thetas[0, b])
+        smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=np.diag(Qd[b])[:, :, None], a=sm.a, P_inf=sm.P_inf,
+                            P_star=np.diag(Pd[b]))
+        yb = y[:, b:b + 1]
+        want = cport.LogLikC(yb, np.isnan(yb), *smb.args())
+        assert math.isnan(got[b]) == math.isnan(want), (N, b, got[b], want)
+        assert math.isnan(gen[b]) == math.isnan(want), (N, b, gen[b], want)
+        if not math.isnan(want):
+            assert abs(got[b] - want) <= RTOL * max(1, abs(want)), (N, b, got[b], want)
+
+
 def test_batch_blk_kernel_not_eligible():
     """A transition matrix that couples a state with two others (SARIMA companion block, dense T) is refused by
     the explicit selector and passed on by the automatic dispatch."""
