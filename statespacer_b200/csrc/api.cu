@@ -1,4 +1,5 @@
 // C ABI of libssgpu (include/ssgpu.h): argument checks, host<->device staging, kernel dispatch.
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <mutex>
@@ -679,16 +680,65 @@ int ssgpu_loglik_grad_batch(const double* y, long long B, const ssgpu_model* mod
   SS_TRY(yd.alloc(n_y * sizeof(double), st));
   SS_TRY(thd.alloc((size_t)B * k * sizeof(double), st));
   SS_TRY(res.alloc((size_t)B * (1 + k) * sizeof(double), st));
-  SS_TRY(copy_h2d(yd.get(), y, n_y * sizeof(double), st));
-  SS_CUDA(cudaMemcpyAsync(thd.get(), theta, (size_t)B * k * sizeof(double), cudaMemcpyHostToDevice, st));
-  ThetaWork W;
   const int V = 1 + 2 * k;
-  SS_TRY(theta_setup(model, false, B, V, k, thd.as<double>(), q_index, p_star_index, h, 1, W, st));
-  SS_TRY(W.out.alloc((size_t)B * V * sizeof(double), st));
-  SS_TRY(dispatch_batch(W.md, yd.as<double>(), B, V, kernel, W.out.as<double>(), st));
+  const size_t Np = (size_t)model->N * model->p;
   double* ll = res.as<double>();
   double* gr = ll + B;
-  SS_TRY(launch_fd_gradient(W.out.as<double>(), B, k, h, ll, gr, st));
+  ThetaWork W;
+  // Pinned y and a large batch: the upload is pipelined with the kernels over chunks of series (chunk c of y is a
+  // column block of the time-major array: one strided 2-D copy on a second stream; the kernels of chunk c wait for
+  // its event only).  1 GB of y at config 5 otherwise sits in front of the first launch for 18 ms of a 156 ms call.
+  const int nch = (host_is_pinned(y) && B >= 16384) ? 8 : 1;
+  if (getenv("SSGPU_TRACE")) fprintf(stderr, "ssgpu_loglik_grad_batch: B=%lld pinned=%d chunks=%d\n", B, (int)host_is_pinned(y), nch);
+  if (nch == 1) {
+    SS_TRY(copy_h2d(yd.get(), y, n_y * sizeof(double), st));
+    SS_CUDA(cudaMemcpyAsync(thd.get(), theta, (size_t)B * k * sizeof(double), cudaMemcpyHostToDevice, st));
+    SS_TRY(theta_setup(model, false, B, V, k, thd.as<double>(), q_index, p_star_index, h, 1, W, st));
+    SS_TRY(W.out.alloc((size_t)B * V * sizeof(double), st));
+    SS_TRY(dispatch_batch(W.md, yd.as<double>(), B, V, kernel, W.out.as<double>(), st));
+    SS_TRY(launch_fd_gradient(W.out.as<double>(), B, k, h, ll, gr, st));
+  } else {
+    static cudaStream_t cs = nullptr;
+    if (!cs) SS_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    // theta and the small tables first: the one host-to-device copy engine serves both streams in issue order
+    SS_CUDA(cudaMemcpyAsync(thd.get(), theta, (size_t)B * k * sizeof(double), cudaMemcpyHostToDevice, st));
+    SS_TRY(theta_setup(model, false, B, V, k, thd.as<double>(), q_index, p_star_index, h, 1, W, st));
+    SS_TRY(W.out.alloc((size_t)B * V * sizeof(double), st));
+    const long long Bc = ((B + nch - 1) / nch + 31) / 32 * 32;
+    std::vector<cudaEvent_t> ev(nch, nullptr);
+    cudaEvent_t ready = nullptr;
+    SS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    SS_CUDA(cudaEventRecord(ready, st));  // yd exists on the compute stream from here on
+    SS_CUDA(cudaStreamWaitEvent(cs, ready, 0));
+    int used = 0;
+    for (int c = 0; c < nch; c++) {
+      const long long b0 = c * Bc, bn = std::min<long long>(Bc, B - b0);
+      if (bn <= 0) break;
+      SS_CUDA(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
+      SS_CUDA(cudaMemcpy2DAsync(yd.as<double>() + Np * b0, bn * sizeof(double), y + b0, (size_t)B * sizeof(double),
+                                bn * sizeof(double), Np, cudaMemcpyHostToDevice, cs));
+      SS_CUDA(cudaEventRecord(ev[c], cs));
+      used = c + 1;
+    }
+    const HostShared hs{model->T.n_slices == 1 ? model->T.data : nullptr, model->R.n_slices == 1 ? model->R.data : nullptr,
+                        model->Z.n_slices == 1 ? model->Z.data : nullptr, nullptr};
+    int rc = SSGPU_OK;
+    for (int c = 0; c < used && rc == SSGPU_OK; c++) {
+      const long long b0 = c * Bc, bn = std::min<long long>(Bc, B - b0);
+      DModel mdc = W.md;  // per-evaluation variances of the chunk: same strides, shifted base
+      mdc.Q.p += b0 * mdc.Q.sb;
+      mdc.P_star.p += b0 * mdc.P_star.sb;
+      cudaStreamWaitEvent(st, ev[c], 0);
+      double* outc = W.out.as<double>() + (size_t)V * b0;
+      rc = dispatch_batch(mdc, yd.as<double>() + Np * b0, bn, V, kernel, outc, st, &hs);
+      if (rc == SSGPU_OK) rc = launch_fd_gradient(outc, bn, k, h, ll + b0, gr + b0 * k, st);
+    }
+    cudaStreamSynchronize(cs);
+    for (cudaEvent_t e : ev)
+      if (e) cudaEventDestroy(e);
+    cudaEventDestroy(ready);
+    SS_TRY(rc);
+  }
   SS_CUDA(cudaMemcpyAsync(loglik, ll, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaMemcpyAsync(grad, gr, (size_t)B * k * sizeof(double), cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));

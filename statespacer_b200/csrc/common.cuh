@@ -128,6 +128,7 @@ class DevBuf {
 int copy_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st);   // returns when dst holds the data
 int copy_h2d(void* dst_dev, const void* src, size_t bytes, cudaStream_t st);   // src may be re-used on return
 void xfer_release();
+bool host_is_pinned(const void* p);
 
 // ---- launchers (implemented in the .cu files) ----------------------------------------------
 // Generic forward filter, one CTA per evaluation (fwd_generic.cu).  kout == nullptr -> loglik only

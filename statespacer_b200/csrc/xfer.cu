@@ -55,6 +55,8 @@ bool is_pageable(const void* p) {
 }
 }  // namespace
 
+bool host_is_pinned(const void* p) { return !is_pageable(p); }
+
 void xfer_release() {
   std::lock_guard<std::mutex> lk(g_ring.mu);
   g_ring.release();
