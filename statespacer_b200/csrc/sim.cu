@@ -569,6 +569,279 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
     for (int kk = 0; kk < r; kk++) A.eta[((long long)(N - 1) * r + kk) * S + s] = 0.0;  // :81
 }
 
+
+// ---- FastSmootherC per draw, FOUR lanes per draw (m <= 32) -------------------------------------------------------
+// One thread per draw leaves a 12,500-draw shard with 2.6 warps per SM and every warp bound by its own latency
+// (about 600 dependent-ish instructions per time step and pass).  Here a draw is spread over LPD = 4 lanes by ROWS:
+// lane `sub` owns the state rows [sub*RPL, (sub+1)*RPL) (RPL = MP / 4) of a, r and r^(1), so the sparse products
+// T a, T'r, R eta, the gain updates a += K0 v, r += z (.) and the stores are a quarter per lane, and four times as
+// many warps are resident.  The dot products z'a, K0'r, K0'r^(1), K1'r stay ONE fma chain in ascending k -- the pinned
+// order of oracle/kalman_c.c -- that travels through the four lanes (lane q continues the chain of lane q-1; blocks of
+// z that are all zero are skipped, a warp-uniform decision since z is shared by the draws): bit-identical results.
+// MEASURED (config 4, one B200): 1.04 ms at 12,500 draws and 7.6 ms at 100,000 against 0.97 / 4.3 ms for one thread
+// per draw.  Both kernels are bound by the latency of ONE warp (fs_draw_reg_kernel takes 0.89 ms for 64 draws and
+// 0.96 ms for 12,500: 1,041 instructions per warp, time step and pass at 0.24 IPC); spreading a draw over four
+// lanes leaves 539 instructions per warp-step for a quarter of the draws (the chain rounds, the block masks and the
+// table loads are paid per warp, not per draw) and pushes the LSU pipe to 85 % of its wavefront rate.  Kept as an
+// opt-in variant (SSGPU_SIM_LANES=1) because it passes the same bit-exact tests; not the default.
+constexpr int kLPD = 4;
+
+template <int MP>
+__global__ void __launch_bounds__(kRegBT) fs_draw_lanes_kernel(const FsArgs A) {
+  constexpr int RPL = MP / kLPD;     // rows per lane
+  constexpr int DPC = kRegBT / kLPD; // draws per CTA
+  constexpr unsigned FULL = 0xffffffffu;
+  extern __shared__ double sh[];
+  const int tid = threadIdx.x, sub = tid & (kLPD - 1), dl = tid / kLPD;
+  const int m = A.m, p = A.p, r = A.r, N = A.N;
+  const long long S = A.S;
+  const long long s_raw = (long long)blockIdx.x * DPC + dl;
+  const bool live = s_raw < S;
+  const long long s = live ? s_raw : S - 1;  // every lane stays alive; surplus draws shadow the last one
+  const int row0 = sub * RPL, gbase = tid & ~(kLPD - 1);
+  // gather sources of the sparse products, one column per draw: v[k] at [k*DPC + dl]
+  double* xs = sh + dl;
+  double* r1 = sh + (size_t)MP * DPC + dl;
+  double* es = sh + (size_t)2 * MP * DPC + dl;
+  double* dcur = sh + (size_t)3 * MP * DPC;
+  double* kb = dcur;           // [2][MP] gain row K0 of the current / next observation
+  double* zb = dcur + 2 * MP;  // [2][MP] row of Z
+  dcur += 4 * MP;
+  int* icur = reinterpret_cast<int*>(dcur + (A.Te.st ? 0 : A.Te.W * MP) + (A.Tce.st ? 0 : A.Tce.W * MP) +
+                                     (A.Re.st ? 0 : A.Re.W * MP));
+  // ELL tables in shared memory (stage_ell computes byte offsets for a stride of kRegBT doubles: rescale to DPC)
+  EllS Te = stage_ell<MP>(A.Te, dcur, icur, tid);
+  EllS Tce = stage_ell<MP>(A.Tce, dcur, icur, tid);
+  EllS Re = stage_ell<MP>(A.Re, dcur, icur, tid);
+  __syncwarp();
+  const long long Np = (long long)N * p;
+  auto fetch_k = [&](long long index) { return (tid < m && index >= 0 && index < Np) ? A.g.K0[index * m + tid] : 0.0; };
+  auto fetch_z = [&](long long index) {
+    if (!(tid < m && index >= 0 && index < Np)) return 0.0;
+    const int t = (int)(index / p), j = (int)(index % p);
+    return slice_of(A.Z, t)[j + tid * p];
+  };
+  // rows row0 .. row0+RPL-1 of  E x  with x parked at xp (one column per draw)
+  auto apply = [&](const EllS& E, int t, const double* xp, double (&out)[RPL]) {
+#pragma unroll
+    for (int j = 0; j < RPL; j++) out[j] = 0.0;
+    const char* xb = reinterpret_cast<const char*>(xp);
+    const double* vt = E.st ? E.vg + (long long)t * E.st : nullptr;
+    for (int w = 0; w < E.W; w++) {
+#pragma unroll
+      for (int j = 0; j < RPL; j++) {
+        const int i = row0 + j;
+        const int off = E.off[w * MP + i] / (kRegBT / DPC);  // byte offset of x[idx] in a DPC-wide column layout
+        const double val = E.st ? (i < m ? vt[w * E.rows + i] : 0.0) : E.vs[w * MP + i];
+        out[j] = fma(val, *reinterpret_cast<const double*>(xb + off), out[j]);
+      }
+    }
+  };
+  auto park = [&](const double (&x)[RPL], double* dst) {
+#pragma unroll
+    for (int j = 0; j < RPL; j++) dst[(row0 + j) * DPC] = x[j];
+  };
+  // acc + sum_k c[k] x[k], k ascending over all MP rows, x distributed by rows: the chain visits the four lanes in
+  // order.  skip_zero: entries with c[k] == 0 are left out (z'a; the oracle skips them too); nzmask: bit q set when
+  // block q of c has a non-zero (all-zero blocks are skipped altogether, identical for every draw of the warp)
+  auto chain = [&](const double* c, const double (&x)[RPL], bool skip_zero, unsigned nzmask) {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < kLPD; q++) {
+      if (!((nzmask >> q) & 1u)) continue;
+      if (sub == q) {
+#pragma unroll
+        for (int j = 0; j < RPL; j++) {
+          const double cv = c[row0 + j];
+          if (!skip_zero || cv != 0.0) acc = fma(cv, x[j], acc);
+        }
+      }
+      acc = __shfl_sync(FULL, acc, gbase + q);
+    }
+    return acc;
+  };
+  auto block_mask = [&](const double* c) {  // which quarter of c holds a non-zero (c is shared by all draws)
+    bool nz = false;
+#pragma unroll
+    for (int j = 0; j < RPL; j++) nz = nz || (c[row0 + j] != 0.0);
+    const unsigned bal = __ballot_sync(FULL, nz);
+    return bal & ((1u << kLPD) - 1u);  // lanes 0..3 = sub 0..3 of draw 0: c is the same for every draw
+  };
+
+  double av[RPL];
+  // forward: innovations v = y - z'a with the shared gains (src/FastSmootherC.cpp:139-251)
+#pragma unroll
+  for (int j = 0; j < RPL; j++) av[j] = (row0 + j) < m ? A.a0[row0 + j] : 0.0;
+  double y_next = A.y[s];
+  if (tid < MP) {
+    kb[tid] = fetch_k(0);
+    zb[tid] = fetch_z(0);
+  }
+  __syncwarp();
+  int cur = 0;
+  for (int t = 0; t < N; t++) {
+    for (int j = 0; j < p; j++) {
+      const long long index = (long long)t * p + j;
+      const double y_now = y_next;
+      if (index + 1 < Np) y_next = A.y[(index + 1) * S + s];
+      const double k_n = fetch_k(index + 1), z_n = fetch_z(index + 1);
+      const double* kc = kb + cur * MP;
+      const double* zc = zb + cur * MP;
+      if ((A.g.code[index] & 255) != 0) {
+        const double za = chain(zc, av, true, block_mask(zc));
+        const double vv = y_now - za;
+        if (live && sub == 0) A.v[index * S + s] = vv;
+#pragma unroll
+        for (int q = 0; q < RPL; q++) av[q] = fma(kc[row0 + q], vv, av[q]);
+      }
+      __syncwarp();
+      if (tid < MP) {
+        kb[(cur ^ 1) * MP + tid] = k_n;
+        zb[(cur ^ 1) * MP + tid] = z_n;
+      }
+      __syncwarp();
+      cur ^= 1;
+    }
+    if (t < N - 1) {
+      park(av, xs);
+      __syncwarp();
+      apply(Te, t, xs, av);
+      __syncwarp();
+    }
+  }
+
+  // backward: r_t (and r^(1) while diffuse), src/FastSmootherC.cpp:259-334
+  double rr[RPL], rq[RPL];  // r and r^(1), own rows
+#pragma unroll
+  for (int j = 0; j < RPL; j++) rr[j] = rq[j] = 0.0;
+  double v_next = A.v[(Np - 1) * S + s];
+  __syncwarp();
+  if (tid < MP) {
+    kb[tid] = fetch_k(Np - 1);
+    zb[tid] = fetch_z(Np - 1);
+  }
+  __syncwarp();
+  cur = 0;
+  for (int t = N - 1; t >= 0; t--) {
+    for (int j = p - 1; j >= 0; j--) {
+      const long long index = (long long)t * p + j;
+      const double v_now = v_next;
+      if (index > 0) v_next = A.v[(index - 1) * S + s];
+      const double k_n = fetch_k(index - 1), z_n = fetch_z(index - 1);
+      const double* kc = kb + cur * MP;
+      const double* zc = zb + cur * MP;
+      const int c = A.g.code[index] & 255;
+      if (c != 0) {
+        const double c1 = A.g.F1[index] * v_now;
+        const double d0 = chain(kc, rr, false, (1u << kLPD) - 1u);
+        if (c == 1) {
+          const double sc = c1 - d0;
+#pragma unroll
+          for (int q = 0; q < RPL; q++) {
+            const double z = zc[row0 + q];
+            if (z != 0.0) rr[q] = fma(z, sc, rr[q]);
+          }
+        } else {
+          const double* k1 = A.g.K1 + index * m;
+          double k1v[RPL];
+#pragma unroll
+          for (int q = 0; q < RPL; q++) k1v[q] = (row0 + q) < m ? k1[row0 + q] : 0.0;
+          // d1 = K0'r^(1) and d2 = K1'r, each its own ascending chain
+          double d1 = 0.0, d2 = 0.0;
+#pragma unroll
+          for (int qq = 0; qq < kLPD; qq++) {
+            if (sub == qq) {
+#pragma unroll
+              for (int q = 0; q < RPL; q++)
+                if (row0 + q < m) {
+                  d1 = fma(kc[row0 + q], rq[q], d1);
+                  d2 = fma(k1v[q], rr[q], d2);
+                }
+            }
+            d1 = __shfl_sync(FULL, d1, gbase + qq);
+            d2 = __shfl_sync(FULL, d2, gbase + qq);
+          }
+          const double s1 = (c1 - d1) - d2, s0 = -d0;
+#pragma unroll
+          for (int q = 0; q < RPL; q++) {
+            const double z = zc[row0 + q];
+            if (z != 0.0) {
+              rq[q] = fma(z, s1, rq[q]);
+              rr[q] = fma(z, s0, rr[q]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (tid < MP) {
+        kb[(cur ^ 1) * MP + tid] = k_n;
+        zb[(cur ^ 1) * MP + tid] = z_n;
+      }
+      __syncwarp();
+      cur ^= 1;
+    }
+    if (t > 0) {
+      const bool both = ((long long)t * p) < A.init_steps;
+      park(rr, xs);
+      if (both) park(rq, r1);
+      __syncwarp();
+      // eta_{t-1} = Q_{t-1} R_{t-1}' r_t right away (src/FastSmootherC.cpp:345-352): row kk by lane kk % 4
+      const double* Qp = A.g.QtR + (A.qtr_tv ? (long long)(t - 1) * r * m : 0);
+      for (int kk = sub; kk < r; kk += kLPD) {
+        double acc = 0.0;
+        const int e1 = A.Qp.ptr[kk + 1];
+        for (int e = A.Qp.ptr[kk]; e < e1; e++) {
+          const int k = A.Qp.idx[e];
+          acc = fma(Qp[kk + k * r], xs[k * DPC], acc);
+        }
+        if (live) A.eta[((long long)(t - 1) * r + kk) * S + s] = acc;
+      }
+      apply(Tce, t - 1, xs, rr);  // T' r
+      if (both) apply(Tce, t - 1, r1, rq);
+      __syncwarp();
+    }
+  }
+
+  // forward reconstruction (src/FastSmootherC.cpp:338-367); rr holds r_0, rq r^(1)_0
+  park(rr, xs);
+  park(rq, r1);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < RPL; j++) {
+    const int i = row0 + j;
+    av[j] = 0.0;
+    if (i < m) {
+      double acc = 0.0, acc1 = 0.0;
+      for (int k = 0; k < m; k++) {
+        acc = fma(A.P_star[i + k * m], xs[k * DPC], acc);
+        acc1 = fma(A.P_inf[i + k * m], r1[k * DPC], acc1);
+      }
+      av[j] = (A.a0[i] + acc) + acc1;
+    }
+  }
+  __syncwarp();
+  for (int t = 0; t < N; t++) {
+    if (t > 0) {
+      for (int kk = sub; kk < r; kk += kLPD) es[kk * DPC] = A.eta[((long long)(t - 1) * r + kk) * S + s];
+      double o2[RPL];
+      park(av, xs);
+      __syncwarp();
+      apply(Te, t - 1, xs, av);
+      apply(Re, t - 1, es, o2);
+#pragma unroll
+      for (int j = 0; j < RPL; j++) av[j] = av[j] + o2[j];
+      __syncwarp();
+    }
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < RPL; j++)
+        if (row0 + j < m) A.a_smooth[((long long)t * m + row0 + j) * S + s] = av[j];
+    }
+  }
+  if (live)
+    for (int kk = sub; kk < r; kk += kLPD) A.eta[((long long)(N - 1) * r + kk) * S + s] = 0.0;  // :81
+}
+
 // ---- ExtractComponentC ----------------------------------------------------------------------------
 // a: R layout m x nsim x N (a_native == 0) or native [(t*m+k)*S+s]; out native [(t*p+j)*S+s]
 __global__ void __launch_bounds__(kSimThreads) extract_kernel(const double* a, int a_native, DMat Z, int m, int p, int S,
@@ -860,7 +1133,34 @@ static int launch_fs_reg(const FsArgs& A, cudaStream_t st) {
   return SSGPU_OK;
 }
 
+template <int MP>
+static int launch_fs_lanes(const FsArgs& A, cudaStream_t st) {
+  constexpr int DPC = kRegBT / kLPD;
+  auto tab = [](const Ell& E) { return (size_t)E.W * MP * ((E.st ? 0 : sizeof(double)) + sizeof(int)); };
+  const size_t smem = sizeof(double) * (DPC * 3 * MP + 4 * MP) + tab(A.Te) + tab(A.Tce) + tab(A.Re) + 16;
+  SS_ARG(smem <= 200 * 1024, "FastSmootherC: sparse tables too large for shared memory");
+  SS_CUDA(cudaFuncSetAttribute(fs_draw_lanes_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  g_t_fs.start(st);
+  fs_draw_lanes_kernel<MP><<<nblk(A.S, DPC), kRegBT, smem, st>>>(A);
+  g_t_fs.stop(st);
+  count_launch();
+  SS_CUDA(cudaGetLastError());
+  return SSGPU_OK;
+}
+
+static bool lanes_variant_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SSGPU_SIM_LANES");
+    return e ? atoi(e) != 0 : false;  // measured slower than one thread per draw (below): opt-in only
+  }();
+  return on;
+}
+
 int launch_fs_draws(const FsArgs& A, cudaStream_t st) {
+  if (reg_variant_enabled() && lanes_variant_enabled() && A.m <= 32 && A.r <= 32) {
+    const int need = A.m > A.r ? A.m : A.r;
+    return need <= 8 ? launch_fs_lanes<8>(A, st) : need <= 16 ? launch_fs_lanes<16>(A, st) : launch_fs_lanes<32>(A, st);
+  }
   if (reg_variant_enabled() && A.m <= 32 && A.r <= 32) {
     const int need = A.m > A.r ? A.m : A.r;
     return need <= 8 ? launch_fs_reg<8>(A, st) : need <= 16 ? launch_fs_reg<16>(A, st) : launch_fs_reg<32>(A, st);

@@ -3,9 +3,12 @@
 Tolerances: 1e-9 relative on loglikelihoods and on smoothed states / variances (north star);
 simulation smoother draws bit-exact against the pinned-order C oracle given the same variates."""
 import math
+import os
 
 import numpy as np
 import pytest
+
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from conftest import Case, DNS_PARAM, config2_standin, load_fed, load_series, random_model, simulate_y
 from oracle import cport, kalman_np, ref
@@ -892,6 +895,25 @@ def test_sim_smoother_large_state_shared_memory_kernels():
         assert np.array_equal(out["gpu"][0][k], out["cpu"][0][k]), k
     for k in ("a_smooth", "a_t", "eta"):
         assert np.array_equal(out["gpu"][1][k], out["cpu"][1][k]), k
+
+
+def test_fast_smoother_lanes_variant_bit_exact():
+    """The opt-in four-lanes-per-draw smoother kernel (SSGPU_SIM_LANES=1, read once per process: run in a child) gives
+    the same bits as the pinned-order C oracle on the airline pipeline."""
+    import subprocess
+    import sys
+    code = ("import sys, math, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from conftest import load_series\nfrom oracle import cport\nfrom statespacer_b200 import api, sysmat\n"
+            "air = np.log(load_series('airpassengers.txt'))[:, None]\n"
+            "sm = sysmat.airline([0.5 * math.log(0.00135), 0.4, 0.55])\n"
+            "steps = api.KalmanC(air, np.isnan(air), *sm.args(), False)['initialisation_steps']\n"
+            "y = np.random.default_rng(3).normal(size=(len(air), 1, 70)).cumsum(axis=0) * 0.05 + air[:, :, None]\n"
+            "g = api.FastSmootherC(y, *sm.args(), steps, True)\nw = cport.FastSmootherC(y, *sm.args(), steps, True)\n"
+            "assert all(np.array_equal(g[k], w[k]) for k in ('a_smooth', 'a_t', 'eta'))\nprint('lanes ok')\n"
+            % (ROOT_DIR, ROOT_DIR + '/tests'))
+    env = dict(os.environ, SSGPU_SIM_LANES="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "lanes ok" in r.stdout, r.stderr[-2000:]
 
 
 def test_extract_component():
