@@ -54,11 +54,27 @@ __device__ void sandwich_T(double* X, const double* Ts, double* tmp, int m, int 
   __syncthreads();
 }
 
+template <bool SHIFT>
+struct BwdView;
+template <>
+struct BwdView<false> {
+  const BwdArgs& A;
+  __device__ BwdView(const BwdArgs& a, long long) : A(a) {}
+};
+template <>
+struct BwdView<true> {
+  BwdArgs A;
+  __device__ BwdView(const BwdArgs& a, long long b) : A(a) {
+    kalman_shift(A.k, A.s, b, A.md.N, A.md.p, A.md.m, A.md.r, A.md.Q.tv() || A.md.R.tv());
+  }
+};
+
+template <bool SHIFT>
 __global__ void __launch_bounds__(512) bwd_generic_kernel(const BwdArgs A_) {
   extern __shared__ double sm[];
   const long long b = blockIdx.x;  // batched KalmanC: one CTA per series, the b-th block of every array
-  BwdArgs A = A_;
-  kalman_shift(A.k, A.s, b, A.md.N, A.md.p, A.md.m, A.md.r, A.md.Q.tv() || A.md.R.tv());
+  const BwdView<SHIFT> view(A_, b);
+  const BwdArgs& A = view.A;
   const DModel& md = A.md;
   const int m = md.m, p = md.p, r = md.r, N = md.N;
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -319,8 +335,13 @@ int launch_bwd_generic(const DModel& md, const ssgpu_kalman_out* kout, const Kal
   int nt = ((md.m * md.m + 31) / 32) * 32;
   if (nt > 512) nt = 512;
   if (nt < 32) nt = 32;
-  SS_CUDA(cudaFuncSetAttribute(bwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  bwd_generic_kernel<<<(unsigned)B, nt, smem, st>>>(A);
+  if (B > 1) {
+    SS_CUDA(cudaFuncSetAttribute(bwd_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bwd_generic_kernel<true><<<(unsigned)B, nt, smem, st>>>(A);
+  } else {
+    SS_CUDA(cudaFuncSetAttribute(bwd_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bwd_generic_kernel<false><<<1, nt, smem, st>>>(A);
+  }
   count_launch();
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;

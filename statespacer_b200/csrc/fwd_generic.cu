@@ -58,15 +58,32 @@ __device__ __forceinline__ void mm_nt(double* C, const double* A, const double* 
   mm_dmma<false, true>(C, A, Bm, add, m, tid, NT);
 }
 
-template <int MODE>
+// the argument block as the kernel sees it: a private, pointer-shifted copy for the batched KalmanC (SHIFT), the
+// parameter bank itself otherwise (a mutable copy costs the single-series call about 10 %)
+template <bool SHIFT>
+struct ArgsView;
+template <>
+struct ArgsView<false> {
+  const FwdArgs& A;
+  __device__ ArgsView(const FwdArgs& a, long long) : A(a) {}
+};
+template <>
+struct ArgsView<true> {
+  FwdArgs A;
+  __device__ ArgsView(const FwdArgs& a, long long b) : A(a) {
+    kalman_shift(A.k, A.s, b, A.md.N, A.md.p, A.md.m, A.md.r, A.md.Q.tv() || A.md.R.tv());
+  }
+};
+
+template <int MODE, bool SHIFT = false>
 __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A_) {
   constexpr bool KALMAN = MODE == MODE_KALMAN, GAINS = MODE == MODE_GAINS;
   extern __shared__ double sm[];
   const long long e = blockIdx.x;
   const long long b = e % A_.B, v = e / A_.B;
-  FwdArgs A = A_;
   // batched KalmanC: this CTA's series owns the b-th block of every output and scratch array
-  if (KALMAN) kalman_shift(A.k, A.s, b, A.md.N, A.md.p, A.md.m, A.md.r, A.md.Q.tv() || A.md.R.tv());
+  const ArgsView<SHIFT> view(A_, b);
+  const FwdArgs& A = view.A;
   const DModel& md = A.md;
   const int m = md.m, p = md.p, r = md.r, N = md.N;
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -389,9 +406,15 @@ int launch_fwd_generic(const DModel& md, const double* y, long long B, int V, do
     SS_ARG(V == 1 && scratch, "KalmanC runs one parameter vector per series");
     A.k = *kout;
     A.s = *scratch;
-    SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<MODE_KALMAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    fwd_generic_kernel<MODE_KALMAN><<<(unsigned)B, nt, smem, st>>>(A);
+    if (B > 1) {
+      SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<MODE_KALMAN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+      fwd_generic_kernel<MODE_KALMAN, true><<<(unsigned)B, nt, smem, st>>>(A);
+    } else {
+      SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<MODE_KALMAN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+      fwd_generic_kernel<MODE_KALMAN, false><<<1, nt, smem, st>>>(A);
+    }
     set_last_kernel("fwd_generic_kernel<KALMAN>");
   } else {
     SS_CUDA(cudaFuncSetAttribute(fwd_generic_kernel<MODE_LOGLIK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
