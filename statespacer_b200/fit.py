@@ -121,3 +121,59 @@ def hessian_batch(y, model, theta, q_index, p_star_index, h=1e-2, kernel="auto")
             Hm[:, i, j] = v
             Hm[:, j, i] = v
     return Hm
+
+
+def hessian_richardson_batch(y, model, theta, q_index, p_star_index, kernel="auto"):
+    """numDeriv::hessian(method = "Richardson") of loglik / N at theta for every series -- the sweep behind
+    statespacer()'s standard errors (R/statespacer.R:1057-1062; numDeriv's genD with its defaults eps = 1e-4, d = 0.1,
+    r = 4, v = 2) -- with all 1 + 2 k r + k (k - 1) r parameter vectors of a series (81 for k = 4) evaluated in ONE
+    batched launch; the Richardson tables are a few torch operations.  Returns (B, k, k)."""
+    import torch
+
+    B, k = theta.shape
+    dev = theta.device
+    eps, d, r, v = 1e-4, 0.1, 4, 2.0
+    zero_tol = (torch.finfo(torch.float64).eps / 7e-7) ** 0.5
+    h0 = (d * theta).abs() + eps * (theta.abs() < zero_tol).to(torch.float64)        # (B, k)
+    pts, where = [theta], {}
+
+    def add(key, offs):
+        where[key] = len(pts)
+        pts.append(theta + offs)
+
+    eye = torch.eye(k, device=dev, dtype=torch.float64)
+    for i in range(k):
+        for it in range(r):
+            step = eye[i][None] * h0 / v ** it
+            add((i, i, it, 1), step)
+            add((i, i, it, -1), -step)
+    for i in range(k):
+        for j in range(i):
+            for it in range(r):
+                step = (eye[i] + eye[j])[None] * h0 / v ** it
+                add((i, j, it, 1), step)
+                add((i, j, it, -1), -step)
+    f = api.loglik_theta_batch_dev(y, model, torch.stack(pts).contiguous(), q_index, p_star_index, kernel=kernel)
+    f0 = f[0]
+
+    def richardson(tab):                                 # tab: list of r tensors (B,)
+        tab = list(tab)
+        for m_ in range(1, r):
+            for kk in range(r - m_):
+                tab[kk] = (tab[kk + 1] * 4 ** m_ - tab[kk]) / (4 ** m_ - 1)
+        return tab[0]
+
+    Hm = torch.zeros(B, k, k, device=dev, dtype=torch.float64)
+    for i in range(k):
+        hi = [h0[:, i] / v ** it for it in range(r)]
+        Hm[:, i, i] = richardson([(f[where[(i, i, it, 1)]] - 2 * f0 + f[where[(i, i, it, -1)]]) / hi[it] ** 2
+                                  for it in range(r)])
+    for i in range(k):
+        for j in range(i):
+            tab = []
+            for it in range(r):
+                hi, hj = h0[:, i] / v ** it, h0[:, j] / v ** it
+                tab.append((f[where[(i, j, it, 1)]] - 2 * f0 + f[where[(i, j, it, -1)]] - Hm[:, i, i] * hi ** 2
+                            - Hm[:, j, j] * hj ** 2) / (2 * hi * hj))
+            Hm[:, i, j] = Hm[:, j, i] = richardson(tab)
+    return Hm

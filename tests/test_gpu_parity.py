@@ -468,6 +468,28 @@ def _block_diagonal_model(rng, m, p, d, N, scatter=True):
     return sysmat.SysMat(Z=sm.Z, T=T[:, :, None], R=sm.R, Q=sm.Q, a=sm.a, P_inf=sm.P_inf, P_star=sm.P_star)
 
 
+def test_hessian_richardson_batch():
+    """fit.hessian_richardson_batch (the numDeriv::hessian sweep of R/statespacer.R:1057-1062, 81 parameter vectors per
+    series in one launch) against the restated numDeriv algorithm driven by the oracle objective."""
+    import torch
+    from oracle import numderiv_np
+    from statespacer_b200 import fit
+    rng = np.random.default_rng(17)
+    B, N = 6, 120
+    thetas, _, _, y = _bsm_batch(rng, B, N, 1, 0.02)
+    theta = thetas[0]
+    dev = torch.device("cuda", 0)
+    model = api.BatchModel(sysmat.bsm12(theta[0]), N, B, 1, device=dev)
+    Hm = fit.hessian_richardson_batch(torch.tensor(y, device=dev), model, torch.tensor(theta, device=dev), BSM_Q_INDEX,
+                                      BSM_P_INDEX).cpu().numpy()
+    for b in (0, 3, 5):
+        yb = y[:, b:b + 1]
+        f = lambda th: cport.LogLikC(yb, np.isnan(yb), *sysmat.bsm12(th).args())
+        want = numderiv_np.hessian(f, theta[b])
+        assert np.max(np.abs(Hm[b] - want)) <= 1e-6 * max(1.0, np.max(np.abs(want))), (b, Hm[b], want)
+        assert np.allclose(Hm[b], Hm[b].T)
+
+
 @pytest.mark.parametrize("m,p", [(9, 1), (10, 2), (14, 1), (15, 1), (16, 2), (17, 1), (20, 1), (23, 3)])
 def test_batch_tile_sparse_state_order(m, p):
     """Tensor kernel with the states re-ordered internally (block-diagonal T -> all-zero tiles skipped) against

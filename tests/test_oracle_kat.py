@@ -84,3 +84,17 @@ def test_forecast_recursion_local_level_closed_form():
                                                   np.ones((1, 1, 1)), np.full((1, 1, 1), Qv), np.full((1, 1, 1), H))
     assert np.allclose(y_fc[:, 0], a) and np.allclose(a_fc[:, 0], a)
     assert np.allclose(P_fc[0, 0], P + Qv * np.arange(6)) and np.allclose(F_fc[0, 0], P + Qv * np.arange(6) + H)
+
+
+def test_numderiv_richardson_restatement():
+    """oracle/numderiv_np.py (numDeriv::hessian, Richardson, defaults) on a function with a known Hessian."""
+    from oracle import numderiv_np
+    A = np.array([[2.0, 0.3, -0.1], [0.3, 1.5, 0.2], [-0.1, 0.2, 0.7]])
+    f = lambda x: 0.5 * x @ A @ x + 0.25 * np.sum(x ** 4) + np.sin(x[0] * x[1])
+    x = np.array([0.4, -0.8, 1.3])
+    Han = A + np.diag(3 * x ** 2)
+    Han[0, 0] += -np.sin(x[0] * x[1]) * x[1] ** 2
+    Han[1, 1] += -np.sin(x[0] * x[1]) * x[0] ** 2
+    Han[0, 1] += np.cos(x[0] * x[1]) - np.sin(x[0] * x[1]) * x[0] * x[1]
+    Han[1, 0] = Han[0, 1]
+    assert np.max(np.abs(numderiv_np.hessian(f, x) - Han)) < 1e-7
