@@ -510,18 +510,30 @@ bool blk_eligible(const DModel& md, std::string* why) {
   return true;
 }
 
+template <int L, int NB, bool P1, bool QOFF>
+static void launch_blk_one(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
+  // SSGPU_BLK_PAD_SMEM: unused dynamic shared memory per CTA -- an occupancy knob for experiments (e.g. 120000 leaves
+  // one CTA per SM: the step time of a warp that has a sub-partition to itself)
+  static const int pad = [] {
+    const char* e = getenv("SSGPU_BLK_PAD_SMEM");
+    return e ? atoi(e) : 0;
+  }();
+  if (pad > 0) cudaFuncSetAttribute(loglik_blk_kernel<L, NB, P1, QOFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+  loglik_blk_kernel<L, NB, P1, QOFF><<<blocks, kBlkThreads, pad, st>>>(A);
+}
+
 template <int L, int NB>
 static void launch_blk_nb(const BlkArgs& A, bool q_offdiag, unsigned blocks, cudaStream_t st) {
   if (A.md.p == 1) {
     if (q_offdiag)
-      loglik_blk_kernel<L, NB, true, true><<<blocks, kBlkThreads, 0, st>>>(A);
+      launch_blk_one<L, NB, true, true>(A, blocks, st);
     else
-      loglik_blk_kernel<L, NB, true, false><<<blocks, kBlkThreads, 0, st>>>(A);
+      launch_blk_one<L, NB, true, false>(A, blocks, st);
   } else {
     if (q_offdiag)
-      loglik_blk_kernel<L, NB, false, true><<<blocks, kBlkThreads, 0, st>>>(A);
+      launch_blk_one<L, NB, false, true>(A, blocks, st);
     else
-      loglik_blk_kernel<L, NB, false, false><<<blocks, kBlkThreads, 0, st>>>(A);
+      launch_blk_one<L, NB, false, false>(A, blocks, st);
   }
 }
 
