@@ -407,7 +407,8 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
   auto fetch_k = [&](long long index) { return (tid < m && index >= 0 && index < Np) ? A.g.K0[index * m + tid] : 0.0; };
   auto fetch_z = [&](long long index) {
     if (!(tid < m && index >= 0 && index < Np)) return 0.0;
-    const int t = (int)(index / p), j = (int)(index % p);
+    // p = 1 (the usual case) needs no 64-bit division in the look-ahead fetch
+    const int t = p == 1 ? (int)index : (int)(index / p), j = p == 1 ? 0 : (int)(index % p);
     return slice_of(A.Z, t)[j + tid * p];
   };
   double av[MP];
@@ -618,7 +619,8 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_lanes_kernel(const FsArgs A) {
   auto fetch_k = [&](long long index) { return (tid < m && index >= 0 && index < Np) ? A.g.K0[index * m + tid] : 0.0; };
   auto fetch_z = [&](long long index) {
     if (!(tid < m && index >= 0 && index < Np)) return 0.0;
-    const int t = (int)(index / p), j = (int)(index % p);
+    // p = 1 (the usual case) needs no 64-bit division in the look-ahead fetch
+    const int t = p == 1 ? (int)index : (int)(index / p), j = p == 1 ? 0 : (int)(index % p);
     return slice_of(A.Z, t)[j + tid * p];
   };
   // rows row0 .. row0+RPL-1 of  E x  with x parked at xp (one column per draw)
