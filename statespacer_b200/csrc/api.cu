@@ -699,7 +699,10 @@ int ssgpu_loglik_grad_batch(const double* y, long long B, const ssgpu_model* mod
     SS_TRY(launch_fd_gradient(W.out.as<double>(), B, k, h, ll, gr, st));
   } else {
     static cudaStream_t cs = nullptr;
-    if (!cs) SS_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      if (!cs) SS_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    }
     // theta and the small tables first: the one host-to-device copy engine serves both streams in issue order
     SS_CUDA(cudaMemcpyAsync(thd.get(), theta, (size_t)B * k * sizeof(double), cudaMemcpyHostToDevice, st));
     SS_TRY(theta_setup(model, false, B, V, k, thd.as<double>(), q_index, p_star_index, h, 1, W, st));
