@@ -273,6 +273,17 @@ int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu_sim_compon
                       double* epsilon, double* a_out, double* eta,
                       int n_extract, const double* const* Z_extract, const int* nZ_extract, double* const* extracted);
 
+/* The unconditional half of the above as its own call: predict()'s simulations over the forecast period
+ * (R/predict.R:142-856: one SimulateC call per component started from object$predicted$a_fc / P_fc with
+ * draw_initial = TRUE, the residual draws last; y_sim, a_sim, eta_sim stacked exactly like SimSmoother()).  N is the
+ * forecast period.  y N x p x nsim (sum of the components' y and the residuals), epsilon, a, eta as above (no mean
+ * correction); extracted[e] = Z_extract[e] a per draw -- with a component's padded Z this is that component's own
+ * simulated y (sim_list$level, ...). */
+int ssgpu_SimulateModel(int nsim, int N, int p, int n_comp, const ssgpu_sim_component* comps,
+                        const double* H, int nH, const double* draws, long long n_draws,
+                        double* y, double* epsilon, double* a_out, double* eta,
+                        int n_extract, const double* const* Z_extract, const int* nZ_extract, double* const* extracted);
+
 /* ---- 6e. The steps on either side of the path (new) ------------------------------------
  * ssgpu_collapse: the collapse transform of R/statespacer.R:815-900, done by R inside the optimiser's objective for
  * every parameter vector of a `collapse = TRUE` model.  y N x p (column-major, NaN = missing, entered as 0 like

@@ -60,3 +60,43 @@ def SimSmoother(mod, nsim, N, p, comps, H, full, initialisation_steps, a_hat, ep
     a_t = (a_t - a_t_smooth) + np.transpose(np.asarray(a_hat), (1, 0))[:, None, :]
     comps_out = [mod.ExtractComponentC(a_t, Z) for Z in extract]                     # :645-766
     return {"epsilon": epsilon, "a": a, "eta": eta, "components": comps_out}
+
+
+def SimulateModel(mod, nsim, N, p, comps, H, draws, extract=(), roots=None):
+    """The simulations of predict() over the forecast period (R/predict.R:142-856): one SimulateC call per component
+    (started from object$predicted$a_fc / P_fc with draw_initial = TRUE, transposed_state = FALSE), stacked into
+    y_sim / a_sim / eta_sim exactly like SimSmoother(), the residual draws last (:836-862).  extract: padded Z matrices;
+    Z_c a_sim per draw equals the component's own sim$y (sim_list$level, ... at :300-301)."""
+    draws = np.asarray(draws, dtype=np.float64).reshape(-1)
+    m = sum(np.asarray(c["a"]).size for c in comps)
+    r = sum(np.asarray(c["Q"]).shape[0] * c["repeat_Q"] for c in comps)
+    y = np.zeros((N, p, nsim), order="F")                                           # :145-147
+    eta = np.zeros((N, r, nsim), order="F")
+    a = np.zeros((N, m, nsim), order="F")
+    a_t = np.zeros((m, nsim, N), order="F")
+    off = ai = ei = 0
+    roots = roots or [{} for _ in range(len(comps) + 1)]
+    own = []
+    for c, rt in zip(comps, roots):
+        mc = np.asarray(c["a"]).size
+        r_tot = np.asarray(c["Q"]).shape[0] * c["repeat_Q"]
+        cnt = (mc * nsim if c["draw_initial"] else 0) + N * r_tot * nsim
+        sim = mod.SimulateC(nsim, c["repeat_Q"], N, c["a"], c["Z"], c["T"], c["R"], c["Q"], c["P_star"],
+                            c["draw_initial"], False, True, draws[off:off + cnt], **rt)
+        off += cnt
+        own.append(sim["y"])                                                         # sim_list$<component>
+        y = y + sim["y"]
+        eta[:, ei:ei + r_tot, :] = sim["eta"]
+        a[:, ai:ai + mc, :] = sim["a"]
+        a_t[ai:ai + mc, :, :] = sim["a_t"]
+        ai += mc
+        ei += r_tot
+    one = np.zeros((1, 1, 1))
+    cnt = N * p * nsim
+    sim = mod.SimulateC(nsim, 1, N, np.zeros(1), one, one, one, H, np.zeros((1, 1)), False, True, False,
+                        draws[off:off + cnt], **roots[len(comps)])                   # :846-860
+    assert off + cnt == draws.size
+    epsilon = sim["eta"]
+    y = y + epsilon
+    return {"y": y, "epsilon": epsilon, "a": a, "eta": eta, "own_y": own,
+            "components": [mod.ExtractComponentC(a_t, Z) for Z in extract]}

@@ -78,3 +78,12 @@ CollapseC <- function(y, H, Z) .Call(`_statespacer_CollapseC`, y, H, Z)
 ForecastC <- function(forecast_period, a_fc, P_fc, Z, T, R, Q, H) {
   .Call(`_statespacer_ForecastC`, as.integer(forecast_period), a_fc, P_fc, Z, T, R, Q, H)
 }
+
+#' predict()'s simulations over the forecast period (R/predict.R:142-856) as one call: the same shim entry with
+#' full = NULL -- no smoothing, no mean correction; `comps` start from object$predicted$a_fc / P_fc with
+#' draw_initial = TRUE.  Returns list(y, epsilon, a, eta, components).
+SimulateModelC <- function(nsim, forecast_period, p, comps, H, Z_extract = list()) {
+  if (is.matrix(H)) dim(H) <- c(dim(H), 1)
+  .Call(`_statespacer_SimSmootherC`, as.integer(nsim), as.integer(forecast_period), as.integer(p), comps, H, NULL, 0L,
+        NULL, NULL, NULL, Z_extract)
+}

@@ -326,8 +326,10 @@ SEXP _statespacer_SimSmootherC(SEXP nsim_, SEXP N_, SEXP p_, SEXP comps, SEXP H,
     n_draws += (cs[c].draw_initial ? (R_xlen_t)cs[c].m * nsim : 0) + (R_xlen_t)N * cs[c].r * cs[c].repeat_Q * nsim;
   }
   n_draws += (R_xlen_t)N * p * nsim;
+  const int conditional = full != R_NilValue; /* NULL: predict()'s unconditional simulations (ssgpu_SimulateModel) */
   ssgpu_sim_model fm;
   memset(&fm, 0, sizeof fm);
+  if (conditional) {
   fm.a = REAL(list_get(full, "a")); fm.P_inf = REAL(list_get(full, "P_inf")); fm.P_star = REAL(list_get(full, "P_star"));
   fm.Z = REAL(list_get(full, "Z")); fm.T = REAL(list_get(full, "T")); fm.R = REAL(list_get(full, "R"));
   fm.Q = REAL(list_get(full, "Q"));
@@ -335,6 +337,7 @@ SEXP _statespacer_SimSmootherC(SEXP nsim_, SEXP N_, SEXP p_, SEXP comps, SEXP H,
   dims3(list_get(full, "T"), &d0, &d1, &fm.nT);
   dims3(list_get(full, "R"), &d0, &fm.r, &fm.nR);
   dims3(list_get(full, "Q"), &d0, &d1, &fm.nQ);
+  }
   dims3(H, &d0, &d1, &d2);
   const int nH = d2;
   double* draws = (double*)R_alloc(n_draws, sizeof(double));
@@ -342,6 +345,7 @@ SEXP _statespacer_SimSmootherC(SEXP nsim_, SEXP N_, SEXP p_, SEXP comps, SEXP H,
   for (R_xlen_t i = 0; i < n_draws; i++) draws[i] = norm_rand();
   PutRNGstate();
   SEXP eps = alloc3(N, p, nsim), a_out = alloc3(N, m, nsim), eta = alloc3(N, r, nsim);
+  SEXP ysim = alloc3(N, p, conditional ? 0 : nsim);
   SEXP ext = PROTECT(Rf_allocVector(VECSXP, ne));
   const double** zp = (const double**)R_alloc(ne > 0 ? ne : 1, sizeof(double*));
   double** op = (double**)R_alloc(ne > 0 ? ne : 1, sizeof(double*));
@@ -354,13 +358,17 @@ SEXP _statespacer_SimSmootherC(SEXP nsim_, SEXP N_, SEXP p_, SEXP comps, SEXP H,
     op[e] = REAL(o);
     dims3(Z, &d0, &d1, &nz[e]);
   }
-  int rc = ssgpu_SimSmoother(nsim, N, p, nc, cs, REAL(H), nH, &fm, Rf_asInteger(steps_), REAL(a_hat), REAL(eps_hat),
-                             REAL(eta_hat), draws, (long long)n_draws, REAL(eps), REAL(a_out), REAL(eta), ne, zp, nz, op);
-  if (rc != SSGPU_OK) { UNPROTECT(4); chk(rc); }
-  const char* names[] = {"epsilon", "a", "eta", "components", ""};
+  int rc = conditional
+               ? ssgpu_SimSmoother(nsim, N, p, nc, cs, REAL(H), nH, &fm, Rf_asInteger(steps_), REAL(a_hat), REAL(eps_hat),
+                                   REAL(eta_hat), draws, (long long)n_draws, REAL(eps), REAL(a_out), REAL(eta), ne, zp, nz, op)
+               : ssgpu_SimulateModel(nsim, N, p, nc, cs, REAL(H), nH, draws, (long long)n_draws, REAL(ysim), REAL(eps),
+                                     REAL(a_out), REAL(eta), ne, zp, nz, op);
+  if (rc != SSGPU_OK) { UNPROTECT(5); chk(rc); }
+  const char* names[] = {"epsilon", "a", "eta", "components", "y", ""};
   SEXP res = PROTECT(Rf_mkNamed(VECSXP, names));
   SET_VECTOR_ELT(res, 0, eps); SET_VECTOR_ELT(res, 1, a_out); SET_VECTOR_ELT(res, 2, eta); SET_VECTOR_ELT(res, 3, ext);
-  UNPROTECT(5);
+  SET_VECTOR_ELT(res, 4, ysim);
+  UNPROTECT(6);
   return res;
 }
 

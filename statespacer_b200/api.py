@@ -237,18 +237,8 @@ def forecast(h, a1, P1, Z, T, R, Q, H):
     return y_fc, a_fc, P_fc, F_fc
 
 
-def SimSmoother(nsim, N, p, comps, H, full, initialisation_steps, a_hat, eps_hat, eta_hat, draws, extract=(), roots=None):
-    """R/SimSmoother.R:34-769 as one call (include/ssgpu.h section 6d): the unconditional draws of every component,
-    the simulated data, their smoothed states, the mean corrections and the extracted components without the per-draw
-    arrays leaving the device.  Arguments as oracle/sim_smoother.py (comps: dicts a, Z, T, R, Q, P_star, repeat_Q,
-    draw_initial; full: (a, P_inf, P_star, Z, T, R, Q) with the residual states in front; draws in the reference's
-    consumption order).  Returns epsilon (N, p, nsim), a (N, m, nsim), eta (N, r, nsim), components [(N, p, nsim)]."""
-    keep = []
-
-    def hold(x):
-        keep.append(x)
-        return _ptr(x)
-
+def _sim_components(comps, roots, p, hold):
+    """ssgpu_sim_component array of the SimulateC calls of R/SimSmoother.R:65-553 / R/predict.R:262-833."""
     roots = roots or [{} for _ in range(len(comps) + 1)]
     if roots[len(comps)]:
         raise ValueError("roots of the residual variance cannot be injected")
@@ -270,6 +260,51 @@ def SimSmoother(nsim, N, p, comps, H, full, initialisation_steps, a_hat, eps_hat
                                      hold(P_root) if P_root is not None else None)
         m += a.shape[0]
         r += Q.shape[0] * int(c["repeat_Q"])
+    return arr, m, r
+
+
+def SimulateModel(nsim, N, p, comps, H, draws, extract=(), roots=None):
+    """The unconditional half of SimSmoother() as one call -- predict()'s simulations over the forecast period
+    (R/predict.R:142-856; include/ssgpu.h section 6d).  Returns y, epsilon (N, p, nsim), a (N, m, nsim), eta (N, r, nsim)
+    and the extracted components."""
+    keep = []
+
+    def hold(x):
+        keep.append(x)
+        return _ptr(x)
+
+    arr, m, r = _sim_components(comps, roots, p, hold)
+    H = _cube(H, "H")
+    draws = np.ascontiguousarray(draws, dtype=np.float64).reshape(-1)
+    y = np.zeros((N, p, nsim), order="F")
+    eps = np.zeros((N, p, nsim), order="F")
+    a_out = np.zeros((N, m, nsim), order="F")
+    eta = np.zeros((N, r, nsim), order="F")
+    ne = len(extract)
+    Zs = [_cube(Z, "Z_padded") for Z in extract]
+    outs = [np.zeros((N, p, nsim), order="F") for _ in extract]
+    zp = (C.c_void_p * max(ne, 1))(*[_ptr(Z) for Z in Zs])
+    nz = (C.c_int * max(ne, 1))(*[Z.shape[2] for Z in Zs])
+    op = (C.c_void_p * max(ne, 1))(*[_ptr(o) for o in outs])
+    native.check(native.lib().ssgpu_SimulateModel(int(nsim), int(N), int(p), len(comps), arr, _ptr(H), H.shape[2],
+                                                  _ptr(draws), draws.shape[0], _ptr(y), _ptr(eps), _ptr(a_out), _ptr(eta),
+                                                  ne, zp, nz, op))
+    return {"y": y, "epsilon": eps, "a": a_out, "eta": eta, "components": outs}
+
+
+def SimSmoother(nsim, N, p, comps, H, full, initialisation_steps, a_hat, eps_hat, eta_hat, draws, extract=(), roots=None):
+    """R/SimSmoother.R:34-769 as one call (include/ssgpu.h section 6d): the unconditional draws of every component,
+    the simulated data, their smoothed states, the mean corrections and the extracted components without the per-draw
+    arrays leaving the device.  Arguments as oracle/sim_smoother.py (comps: dicts a, Z, T, R, Q, P_star, repeat_Q,
+    draw_initial; full: (a, P_inf, P_star, Z, T, R, Q) with the residual states in front; draws in the reference's
+    consumption order).  Returns epsilon (N, p, nsim), a (N, m, nsim), eta (N, r, nsim), components [(N, p, nsim)]."""
+    keep = []
+
+    def hold(x):
+        keep.append(x)
+        return _ptr(x)
+
+    arr, m, r = _sim_components(comps, roots, p, hold)
     fa, fPi, fPs, fZ, fT, fR, fQ = full
     fa = _f(np.asarray(fa, dtype=np.float64).reshape(-1))
     fPi, fPs = _f(fPi), _f(fPs)

@@ -396,14 +396,16 @@ extern "C" int ssgpu_SimulateC(int nsim, int repeat_Q, int N, int p, int m, int 
 // Everything between the variates and the returned arrays stays on the device: the component draws land directly in
 // the stacked arrays of the whole model, y is accumulated in place, the smoother runs on it, the mean correction and
 // the component extraction read the same buffers; only epsilon / a / eta / the extracted components cross PCIe.
-extern "C" int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu_sim_component* comps, const double* H,
-                                 int nH, const ssgpu_sim_model* full, int initialisation_steps,
-                                 const double* a_hat, const double* eps_hat, const double* eta_hat, const double* draws,
-                                 long long n_draws, double* epsilon, double* a_out, double* eta, int n_extract,
-                                 const double* const* Z_extract, const int* nZ_extract, double* const* extracted) {
-  SS_ARG(nsim >= 1 && N >= 1 && p >= 1 && n_comp >= 1 && comps && H && full && draws, "SimSmoother: bad arguments");
+// full == nullptr: the unconditional half only (predict()'s simulations, R/predict.R:142-856): no smoother, no mean
+// correction; y_out (N x p x nsim) receives the simulated data
+static int sim_smoother_impl(int nsim, int N, int p, int n_comp, const ssgpu_sim_component* comps, const double* H,
+                             int nH, const ssgpu_sim_model* full, int initialisation_steps, const double* a_hat,
+                             const double* eps_hat, const double* eta_hat, const double* draws, long long n_draws,
+                             double* y_out, double* epsilon, double* a_out, double* eta, int n_extract,
+                             const double* const* Z_extract, const int* nZ_extract, double* const* extracted) {
+  SS_ARG(nsim >= 1 && N >= 1 && p >= 1 && n_comp >= 1 && comps && H && draws, "SimSmoother: bad arguments");
   SS_ARG(nH == 1 || nH == N, "SimSmoother: H must have 1 or N slices");
-  SS_ARG(a_hat && eps_hat && eta_hat, "SimSmoother: smoothed estimates of the observed data are required");
+  SS_ARG(!full || (a_hat && eps_hat && eta_hat), "SimSmoother: smoothed estimates of the observed data are required");
   SS_ARG(n_extract == 0 || (Z_extract && nZ_extract && extracted), "SimSmoother: null extraction arguments");
   int m = 0, r = 0;
   long long need = 0;
@@ -420,9 +422,11 @@ extern "C" int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu
     set_error("SimSmoother: n_draws does not match the reference's consumption (components in order, then N*p*nsim)");
     return SSGPU_E_DRAWS;
   }
-  SS_ARG(full->m == m + p && full->r == r + p, "SimSmoother: the full model must be the components plus p residual states");
-  SS_TRY(check_fs(draws, N, p, nsim, full->m, full->r, full->a, full->P_inf, full->P_star, full->Z, full->nZ, full->T,
-                  full->nT, full->R, full->nR, full->Q, full->nQ));
+  if (full) {
+    SS_ARG(full->m == m + p && full->r == r + p, "SimSmoother: the full model must be the components plus p residual states");
+    SS_TRY(check_fs(draws, N, p, nsim, full->m, full->r, full->a, full->P_inf, full->P_star, full->Z, full->nZ, full->T,
+                    full->nT, full->R, full->nR, full->Q, full->nQ));
+  }
   SS_TRY(ensure_device());
   cudaStream_t st = lib_stream();
   DevBuf dr, yN, aN, eN, epsN, afN, efN, hats, outR, zD, cN;
@@ -450,19 +454,21 @@ extern "C" int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu
   }
   SS_TRY(simulate_core(nsim, 1, N, 1, 1, p, p, nullptr, nullptr, 1, nullptr, 1, nullptr, 1, H, nH, nullptr, 0, 1,
                        dr.as<double>() + doff, nullptr, nullptr, yN.as<double>(), nullptr, epsN.as<double>(), st));
-  // smoothed state and disturbances of the simulated data (:617-632)
-  SS_TRY(afN.alloc(sizeof(double) * (size_t)N * full->m * ns, st));
-  SS_TRY(efN.alloc(sizeof(double) * (size_t)N * full->r * ns, st));
-  SS_TRY(fast_smoother_core(yN.as<double>(), N, p, nsim, full->m, full->r, full->a, full->P_inf, full->P_star, full->Z,
-                            full->nZ, full->T, full->nT, full->R, full->nR, full->Q, full->nQ, initialisation_steps,
-                            afN.as<double>(), efN.as<double>(), st));
-  // mean corrections (:634-642)
   HostPack hp;
-  const size_t oa = hp.add(a_hat, (size_t)N * m), oe = hp.add(eps_hat, (size_t)N * p), oh = hp.add(eta_hat, (size_t)N * r);
-  SS_TRY(upload(hats, hp.buf.data(), hp.buf.size(), st));
-  SS_TRY(launch_sim_correct(aN.as<double>(), afN.as<double>(), hats.as<double>() + oa, N, m, full->m, p, nsim, st));
-  SS_TRY(launch_sim_correct(epsN.as<double>(), afN.as<double>(), hats.as<double>() + oe, N, p, full->m, 0, nsim, st));
-  SS_TRY(launch_sim_correct(eN.as<double>(), efN.as<double>(), hats.as<double>() + oh, N, r, full->r, p, nsim, st));
+  if (full) {
+    // smoothed state and disturbances of the simulated data (:617-632)
+    SS_TRY(afN.alloc(sizeof(double) * (size_t)N * full->m * ns, st));
+    SS_TRY(efN.alloc(sizeof(double) * (size_t)N * full->r * ns, st));
+    SS_TRY(fast_smoother_core(yN.as<double>(), N, p, nsim, full->m, full->r, full->a, full->P_inf, full->P_star, full->Z,
+                              full->nZ, full->T, full->nT, full->R, full->nR, full->Q, full->nQ, initialisation_steps,
+                              afN.as<double>(), efN.as<double>(), st));
+    // mean corrections (:634-642)
+    const size_t oa = hp.add(a_hat, (size_t)N * m), oe = hp.add(eps_hat, (size_t)N * p), oh = hp.add(eta_hat, (size_t)N * r);
+    SS_TRY(upload(hats, hp.buf.data(), hp.buf.size(), st));
+    SS_TRY(launch_sim_correct(aN.as<double>(), afN.as<double>(), hats.as<double>() + oa, N, m, full->m, p, nsim, st));
+    SS_TRY(launch_sim_correct(epsN.as<double>(), afN.as<double>(), hats.as<double>() + oe, N, p, full->m, 0, nsim, st));
+    SS_TRY(launch_sim_correct(eN.as<double>(), efN.as<double>(), hats.as<double>() + oh, N, r, full->r, p, nsim, st));
+  }
   // results in R's layouts
   const int kmax = m > r ? (m > p ? m : p) : (r > p ? r : p);
   SS_TRY(outR.alloc(sizeof(double) * (size_t)N * kmax * ns, st));
@@ -470,7 +476,8 @@ extern "C" int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu
     double* host;
     const double* dev;
     int K;
-  } outs[3] = {{epsilon, epsN.as<double>(), p}, {a_out, aN.as<double>(), m}, {eta, eN.as<double>(), r}};
+  } outs[4] = {{epsilon, epsN.as<double>(), p}, {a_out, aN.as<double>(), m}, {eta, eN.as<double>(), r},
+               {y_out, yN.as<double>(), p}};
   for (const Out& o : outs) {
     if (!o.host) continue;
     SS_TRY(launch_permute_tks(o.dev, outR.as<double>(), N, o.K, nsim, true, st));
@@ -486,8 +493,25 @@ extern "C" int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu
     SS_TRY(copy_d2h(extracted[e], outR.get(), sizeof(double) * (size_t)N * p * ns, st));
   }
   SS_CUDA(cudaStreamSynchronize(st));
-  (void)hp;
   return SSGPU_OK;
+}
+
+extern "C" int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu_sim_component* comps, const double* H,
+                                 int nH, const ssgpu_sim_model* full, int initialisation_steps,
+                                 const double* a_hat, const double* eps_hat, const double* eta_hat, const double* draws,
+                                 long long n_draws, double* epsilon, double* a_out, double* eta, int n_extract,
+                                 const double* const* Z_extract, const int* nZ_extract, double* const* extracted) {
+  SS_ARG(full != nullptr, "SimSmoother: the full model is required");
+  return sim_smoother_impl(nsim, N, p, n_comp, comps, H, nH, full, initialisation_steps, a_hat, eps_hat, eta_hat, draws,
+                           n_draws, nullptr, epsilon, a_out, eta, n_extract, Z_extract, nZ_extract, extracted);
+}
+
+extern "C" int ssgpu_SimulateModel(int nsim, int N, int p, int n_comp, const ssgpu_sim_component* comps, const double* H,
+                                   int nH, const double* draws, long long n_draws, double* y, double* epsilon,
+                                   double* a_out, double* eta, int n_extract, const double* const* Z_extract,
+                                   const int* nZ_extract, double* const* extracted) {
+  return sim_smoother_impl(nsim, N, p, n_comp, comps, H, nH, nullptr, 0, nullptr, nullptr, nullptr, draws, n_draws, y,
+                           epsilon, a_out, eta, n_extract, Z_extract, nZ_extract, extracted);
 }
 
 extern "C" int ssgpu_ExtractComponentC_dev(const double* a, int m, int nsim, int N, const double* Z, int p, int nZ,

@@ -882,6 +882,30 @@ def test_sim_smoother_one_call(kind):
         api.SimSmoother(*args[:-1], draws[:-1], extract=c["extract"])
 
 
+def test_simulate_model_predict_simulations():
+    """ssgpu_SimulateModel (predict()'s simulations over the forecast period, R/predict.R:142-856) against the same
+    calls strung together from the C oracle: bit-exact; the component extraction equals each component's own y."""
+    from oracle import sim_smoother
+    rng = np.random.default_rng(23)
+    c = _sim_smoother_case("structural", rng)
+    for k in c["comps"]:                                # predict() starts every component from a_fc / P_fc
+        mc = np.asarray(k["a"]).size
+        A = rng.normal(size=(mc, mc))
+        k["a"], k["P_star"], k["draw_initial"] = rng.normal(size=mc), A @ A.T / mc, True
+    nsim, h = 33, 24
+    n_draws = sum(np.asarray(k["a"]).size * nsim + h * np.asarray(k["Q"]).shape[0] * k["repeat_Q"] * nsim
+                  for k in c["comps"]) + h * c["p"] * nsim
+    draws = rng.normal(size=n_draws)
+    roots = [dict(Q_root=np.stack([cport.sym_root(np.atleast_2d(k["Q"]))], axis=2),
+                  P_root=cport.sym_root(np.atleast_2d(k["P_star"]))) for k in c["comps"]] + [{}]
+    got = api.SimulateModel(nsim, h, c["p"], c["comps"], c["H"], draws, extract=c["extract"], roots=roots)
+    want = sim_smoother.SimulateModel(cport, nsim, h, c["p"], c["comps"], c["H"], draws, extract=c["extract"], roots=roots)
+    for k in ("y", "epsilon", "a", "eta"):
+        assert np.array_equal(got[k], want[k]), k
+    for g, w, own in zip(got["components"], want["components"], want["own_y"]):
+        assert np.array_equal(g, w) and np.array_equal(g, own)
+
+
 @pytest.mark.parametrize("nsim", [100, 40000, 80000])
 def test_sim_smoother_device_resident_pipeline(nsim):
     """The *_dev entry points (draws stay on the GPU in the draw-contiguous layout) give the same bits as the
