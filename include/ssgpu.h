@@ -158,8 +158,9 @@ typedef struct ssgpu_model {
 
 #define SSGPU_KERNEL_BLK 6      /* block-row DFMA kernel: T block diagonal with blocks of at most 2 x 2 after re-ordering
                                    the states (residuals, level, slope, trigonometric seasonals, cycles, regression
-                                   coefficients), at most 8 blocks (m <= 16), p <= 8, R Q R' inside the blocks;
-                                   SSGPU_E_ARG if not eligible.  AUTO tries it first */
+                                   coefficients), at most 8 blocks (m <= 16), p <= 8, R Q R' inside the blocks; Z may be
+                                   time-varying when p = 1 (explanatory variables); SSGPU_E_ARG if not eligible.
+                                   AUTO tries it first */
 
 /* host pointers everywhere (y, the matrices' data, out); copies in, runs, copies out, synchronises */
 int ssgpu_loglik_batch(const double* y, long long B, int V, const ssgpu_model* model, int kernel,

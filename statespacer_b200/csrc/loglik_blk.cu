@@ -2,8 +2,8 @@
 // structure-exploiting DFMA kernel, L lanes per evaluation, the covariance distributed by block rows.
 //
 // Restates the recursion of src/LogLikC.cpp:68-214 (univariate treatment, exact diffuse initialisation,
-// NaN = missing) for models whose Z, T, R are shared by the batch and time-invariant (per-evaluation
-// a, P_inf, P_star, Q allowed) and whose T, after re-ordering the states, is  blkdiag(T_0, ..., T_{NB-1})  with
+// NaN = missing) for models whose Z, T, R are shared by the batch, T and R time-invariant, Z time-invariant or -- with
+// p = 1 -- one row per time point (explanatory variables) (per-evaluation a, P_inf, P_star, Q allowed) and whose T, after re-ordering the states, is  blkdiag(T_0, ..., T_{NB-1})  with
 // 1 x 1 or 2 x 2 blocks, NB <= 8 (m <= 16), and whose R Q R' has no entry outside those blocks.  That is every
 // structural model statespacer builds from residuals, level, slope, trigonometric seasonals, cycles and
 // regression coefficients (R/GetSysMat.R:1388-1426, R/Components-Unobserved.R:143-159,491-519): T couples a state
@@ -45,6 +45,7 @@ struct BlkArgs {
   signed char perm[2 * kBlkMaxNB];     // internal position 2I+e holds state perm[2I+e] of the caller, -1 = padding
   double Tb[kBlkMaxNB][4];             // T_J[row][col] at [2*row + col], internal order
   double z[kBlkMaxP][2 * kBlkMaxNB];   // row j of Z, internal order
+  const double* zt;                    // time-varying Z (p = 1): [t][2 * kBlkMaxNB] in internal order, device memory
 };
 
 __device__ __forceinline__ double blk_rcp(double x) {
@@ -58,7 +59,8 @@ __device__ __forceinline__ double blk_rcp(double x) {
 }
 
 // QOFF: the diagonal blocks of R Q R' have off-diagonal entries (correlated disturbances of a multivariate model)
-template <int L, int NB, bool P1, bool QOFF>
+// ZTV: Z changes with t (explanatory variables, R/Components-Regressors.R:60-78); p = 1 only
+template <int L, int NB, bool P1, bool QOFF, bool ZTV = false>
 __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel(const BlkArgs A) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int G = 32 / L;  // evaluations per warp
@@ -211,11 +213,12 @@ __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel
       for (int j = 0; j < p; j++) {
         const double yv = A.y[((long long)t * p + j) * A.B + b];
         const bool obs = !isnan(yv);  // :88-90
-        const double zi0 = A.z[j][2 * I], zi1 = A.z[j][2 * I + 1];
+        const double* zrow = ZTV ? A.zt + (size_t)t * (2 * kBlkMaxNB) : &A.z[j][0];
+        const double zi0 = zrow[2 * I], zi1 = zrow[2 * I + 1];
         double ms0 = 0.0, ms1 = 0.0, mi0 = 0.0, mi1 = 0.0;
 #pragma unroll
         for (int J = 0; J < NB; J++) {
-          const double z0 = A.z[j][2 * J], z1 = A.z[j][2 * J + 1];
+          const double z0 = zrow[2 * J], z1 = zrow[2 * J + 1];
           ms0 = fma(P[J][1], z1, fma(P[J][0], z0, ms0));
           ms1 = fma(P[J][3], z1, fma(P[J][2], z0, ms1));
           mi0 = fma(pinf[J * 4 + 1][tx], z1, fma(pinf[J * 4 + 0][tx], z0, mi0));
@@ -313,7 +316,22 @@ __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel
     // sub-partition the FP64 pipe otherwise idles through that chain: 148 ms per sweep of config 5 before, see
     // profiles/README.md.)
     if (t < N) {
-      const double zi0 = A.z[0][2 * I], zi1 = A.z[0][2 * I + 1];
+      double zi0 = A.z[0][2 * I], zi1 = A.z[0][2 * I + 1];
+      // time-varying Z: the row of step t in internal order, the same for every evaluation (16-byte broadcast loads)
+      auto load_z = [&](int tt) {
+        if constexpr (ZTV) {
+          const double2* zr = reinterpret_cast<const double2*>(A.zt + (size_t)tt * (2 * kBlkMaxNB));
+#pragma unroll
+          for (int J = 0; J < NB; J++) {
+            const double2 zz = zr[J];
+            ZJ[J][0] = zz.x;
+            ZJ[J][1] = zz.y;
+          }
+          const double2 zo = zr[I];
+          zi0 = zo.x;
+          zi1 = zo.y;
+        }
+      };
       // observations are fetched two steps ahead of their use (one step, 600 cycles at 2 warps per sub-partition,
       // does not always cover a DRAM miss: 2.4 % of the stall samples sat on this load)
       double ynext = A.y[(long long)t * A.B + b];
@@ -336,6 +354,7 @@ __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel
         const double yv = ynext;
         ynext = ynext2;
         if (t + 2 < N) ynext2 = A.y[(long long)(t + 2) * A.B + b];
+        load_z(t);
         innovation();
         const double tm0 = fma(t01, m1, t00 * m0), tm1 = fma(t11, m1, t10 * m0);  // (T M)_I
         if (own) xch[buf][I][g] = make_double2(tm0, tm1);
@@ -360,6 +379,7 @@ __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel
         a1 = fma(g1, vv, ta1);
       }
       // the last observation (:200 -- P and a are not needed afterwards)
+      load_z(N - 1);
       innovation();
       F_star = group_sum(fma(zi1, m1, zi0 * m0));
       za = group_sum(fma(zi1, a1, zi0 * a0));
@@ -505,12 +525,13 @@ bool blk_eligible(const DModel& md, std::string* why) {
   if (md.m > 2 * kBlkMaxNB) return no("m > 16");
   if (md.p > kBlkMaxP) return no("p > 8");
   if (!md.Z.shared() || !md.T.shared() || !md.R.shared()) return no("Z, T, R must be shared by the batch");
-  if (md.Z.tv() || md.T.tv() || md.R.tv() || md.Q.tv()) return no("time-varying system matrices");
+  if (md.T.tv() || md.R.tv() || md.Q.tv()) return no("time-varying T, R or Q");
+  if (md.Z.tv() && md.p != 1) return no("time-varying Z needs p = 1");
   if (!md.Q.diag && !md.Q.shared()) return no("per-evaluation Q must be stored as a diagonal");
   return true;
 }
 
-template <int L, int NB, bool P1, bool QOFF>
+template <int L, int NB, bool P1, bool QOFF, bool ZTV = false>
 static void launch_blk_one(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
   // SSGPU_BLK_PAD_SMEM: unused dynamic shared memory per CTA -- an occupancy knob for experiments (e.g. 120000 leaves
   // one CTA per SM: the step time of a warp that has a sub-partition to itself)
@@ -518,13 +539,19 @@ static void launch_blk_one(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
     const char* e = getenv("SSGPU_BLK_PAD_SMEM");
     return e ? atoi(e) : 0;
   }();
-  if (pad > 0) cudaFuncSetAttribute(loglik_blk_kernel<L, NB, P1, QOFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-  loglik_blk_kernel<L, NB, P1, QOFF><<<blocks, kBlkThreads, pad, st>>>(A);
+  if (pad > 0)
+    cudaFuncSetAttribute(loglik_blk_kernel<L, NB, P1, QOFF, ZTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+  loglik_blk_kernel<L, NB, P1, QOFF, ZTV><<<blocks, kBlkThreads, pad, st>>>(A);
 }
 
 template <int L, int NB>
 static void launch_blk_nb(const BlkArgs& A, bool q_offdiag, unsigned blocks, cudaStream_t st) {
-  if (A.md.p == 1) {
+  if (A.md.p == 1 && A.zt) {
+    if (q_offdiag)
+      launch_blk_one<L, NB, true, true, true>(A, blocks, st);
+    else
+      launch_blk_one<L, NB, true, false, true>(A, blocks, st);
+  } else if (A.md.p == 1) {
     if (q_offdiag)
       launch_blk_one<L, NB, true, true>(A, blocks, st);
     else
@@ -557,7 +584,8 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
   SS_ARG(blk_eligible(md, &why), "block kernel not eligible: " + why);
   const int m = md.m, r = md.r, p = md.p;
   // the shared matrices are a few hundred bytes: fetch what the caller has not passed along (host copies)
-  std::vector<double> Th((size_t)(md.T.diag ? m : m * m)), Rh((size_t)(md.R.diag ? m : m * r)), Zh((size_t)p * m), Qh;
+  const int nZ = md.Z.tv() ? md.N : 1;
+  std::vector<double> Th((size_t)(md.T.diag ? m : m * m)), Rh((size_t)(md.R.diag ? m : m * r)), Zh((size_t)p * m * nZ), Qh;
   std::vector<unsigned char> qpat;
   bool need_sync = false;
   auto fetch = [&](std::vector<double>& dst, const double* host, const double* dev) -> int {
@@ -571,7 +599,7 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
   };
   SS_TRY(fetch(Th, hs ? hs->T : nullptr, md.T.p));
   SS_TRY(fetch(Rh, hs ? hs->R : nullptr, md.R.p));
-  SS_TRY(fetch(Zh, hs ? hs->Z : nullptr, md.Z.p));
+  SS_TRY(fetch(Zh, (hs && nZ == 1) ? hs->Z : nullptr, md.Z.p));
   if (!md.Q.diag) {
     Qh.resize((size_t)r * r);
     SS_TRY(fetch(Qh, hs ? hs->Q : nullptr, md.Q.p));
@@ -599,6 +627,17 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
   std::memcpy(A.Tb, pl.Tb, sizeof A.Tb);
   for (int j = 0; j < p; j++)
     for (int i = 0; i < 2 * kBlkMaxNB; i++) A.z[j][i] = pl.perm[i] >= 0 ? Zh[j + (size_t)pl.perm[i] * p] : 0.0;
+  DevBuf ztd;  // released stream-ordered behind the kernel
+  if (nZ > 1) {
+    std::vector<double> zt((size_t)nZ * 2 * kBlkMaxNB, 0.0);
+    for (int t = 0; t < nZ; t++)
+      for (int i = 0; i < 2 * kBlkMaxNB; i++)
+        if (pl.perm[i] >= 0) zt[(size_t)t * 2 * kBlkMaxNB + i] = Zh[(size_t)t * p * m + (size_t)pl.perm[i] * p];
+    SS_TRY(ztd.alloc(zt.size() * sizeof(double), st));
+    SS_CUDA(cudaMemcpyAsync(ztd.get(), zt.data(), zt.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    SS_CUDA(cudaStreamSynchronize(st));  // the host vector dies with this frame
+    A.zt = ztd.as<double>();
+  }
   const int L = blk_lanes(pl.nb), G = 32 / L, wpb = kBlkThreads / 32;
   const long long blocks = (A.E + (long long)wpb * G - 1) / ((long long)wpb * G);
   SS_ARG(blocks < (1LL << 31), "block kernel: batch too large for one launch");
@@ -616,7 +655,8 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
   SS_CUDA(cudaGetLastError());
   count_launch();
   static thread_local char name[96];
-  snprintf(name, sizeof name, "loglik_blk_kernel<L=%d,NB=%d,flop_per_step=%d>", L, pl.nb, blk_flops_per_step(pl.nb, p));
+  snprintf(name, sizeof name, "loglik_blk_kernel<L=%d,NB=%d,flop_per_step=%d>%s", L, pl.nb, blk_flops_per_step(pl.nb, p),
+           nZ > 1 ? " time-varying Z" : "");
   set_last_kernel(name);
   return SSGPU_OK;
 }

@@ -287,6 +287,42 @@ def test_batch_blk_kernel(name):
         assert abs(gen[b] - want) <= RTOL * max(1, abs(want)), (name, b, gen[b], want)
 
 
+@pytest.mark.parametrize("seasonal", [12, 4])
+def test_batch_blk_kernel_time_varying_z(seasonal):
+    """Univariate structural model with two explanatory variables (R/Components-Regressors.R:60-78: constant, exactly
+    diffuse coefficient states whose row of Z is the regressor value at t): time-varying Z on the block-row kernel,
+    against the oracle and the generic kernel; the automatic dispatch picks it."""
+    rng = np.random.default_rng(60 + seasonal)
+    N, B = 70, 23
+    base = sysmat._combine(1, [[0.8]], [sysmat.comp_level_slope(0.1, 0.01), sysmat.comp_bsm_trig(seasonal, 0.05)])
+    m0 = base.m
+    X = rng.normal(size=(N, 2))
+    m = m0 + 2
+    Z = np.zeros((1, m, N))
+    Z[0, :m0, :] = base.Z[0, :, 0][:, None]
+    Z[0, m0:, :] = X.T
+    T = sysmat.block_diag(base.T[:, :, 0], np.eye(2))
+    R = np.concatenate([np.eye(m0), np.zeros((2, m0))], axis=0)
+    P_inf = sysmat.block_diag(base.P_inf, np.eye(2))
+    P_star = sysmat.block_diag(base.P_star, np.zeros((2, 2)))
+    sm = sysmat.SysMat(Z=Z, T=T[:, :, None], R=R[:, :, None], Q=base.Q, a=np.zeros(m), P_inf=P_inf, P_star=P_star)
+    beta = np.array([1.5, -0.7])
+    y = np.stack([simulate_y(rng, base, N, missing=0.08)[:, 0] + X @ beta for _ in range(B)], axis=1)
+    scale = rng.uniform(0.5, 2.0, size=(B, 1))
+    Qd = np.diag(base.Q[:, :, 0])[None, :] * scale
+    got = api.loglik_batch(y, sm, Q_diag=Qd, kernel="blk")
+    assert "time-varying Z" in api.last_kernel(), api.last_kernel()
+    gen = api.loglik_batch(y, sm, Q_diag=Qd, kernel="generic")
+    auto = api.loglik_batch(y, sm, Q_diag=Qd)
+    assert api.last_kernel().startswith("loglik_blk_kernel<") and np.array_equal(auto, got)
+    for b in range(B):
+        smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=np.diag(Qd[b])[:, :, None], a=sm.a, P_inf=sm.P_inf, P_star=sm.P_star)
+        yb = y[:, b:b + 1]
+        want = cport.LogLikC(yb, np.isnan(yb), *smb.args())
+        assert abs(got[b] - want) <= 1e-8 * max(1, abs(want)), (b, got[b], want)
+        assert abs(gen[b] - want) <= 1e-8 * max(1, abs(want)), (b, gen[b], want)
+
+
 def test_batch_blk_kernel_bivariate_dense_blocks():
     """p = 2: two local levels with correlated disturbances.  T = diag(0, 0, 1, 1); R Q R' = blkdiag(H, Q_level) has
     dense 2 x 2 blocks, which pairs the residuals and the levels; shared dense Q, per-series dense P_star and a."""
