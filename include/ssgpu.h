@@ -304,6 +304,13 @@ int ssgpu_forecast(int h, int p, int m, int r, const double* a1, const double* P
  * non-zero (TT = ceil((m+1)/8)); *dmma_per_step = DMMA instructions one time update then issues.  Any output
  * pointer may be NULL. */
 int ssgpu_plan_state_order(const double* T, int m, int* perm, unsigned* tile_mask, int* dmma_per_step);
+/* The same for the block-row kernel (SSGPU_KERNEL_BLK): T m x m, R m x r, Q r x r or NULL (= diagonal), all
+ * column-major.  *n_blocks = number of 2 x 2 blocks, or 0 when the model does not decompose (a state coupled with two
+ * others through T or R Q R', more than 8 blocks, p > 8); perm[16]: internal position 2I+e -> state index of the
+ * caller, -1 = padding; *lanes = lanes per evaluation; *flop_per_step = FP64 operations the kernel issues per series
+ * and time step (fma = 2, all lanes). */
+int ssgpu_plan_blocks(const double* T, const double* R, const double* Q, int m, int r, int p, int* perm,
+                      int* n_blocks, int* lanes, int* flop_per_step);
 
 /* ---- 7. Measurement helpers ---------------------------------------------------------------
  * FP64 FMA-pipe peak of the current device, measured with a register-resident DFMA chain kernel

@@ -205,6 +205,22 @@ def ExtractComponentC(a, Z):
     return out
 
 
+def plan_blocks(T, R, Q=None, p=1):
+    """Block decomposition of the block-row kernel for shared T (m x m), R (m x r) and the pattern of Q (None =
+    diagonal) -- host-only helper.  Returns None when the model does not decompose, else a dict with n_blocks, lanes,
+    flop_per_step and perm (internal position -> state index, -1 = padding)."""
+    T = _f(np.asarray(T, dtype=np.float64).reshape(np.shape(T)[0], np.shape(T)[1]))
+    R = _f(np.asarray(R, dtype=np.float64).reshape(np.shape(R)[0], np.shape(R)[1]))
+    Qm = None if Q is None else _f(np.asarray(Q, dtype=np.float64).reshape(np.shape(Q)[0], np.shape(Q)[1]))
+    perm = np.full(16, -1, dtype=np.int32)
+    nb, lanes, flops = C.c_int(), C.c_int(), C.c_int()
+    native.check(native.lib().ssgpu_plan_blocks(_ptr(T), _ptr(R), _ptr(Qm), T.shape[0], R.shape[1], int(p), perm.ctypes.data,
+                                                C.addressof(nb), C.addressof(lanes), C.addressof(flops)))
+    if nb.value == 0:
+        return None
+    return {"n_blocks": nb.value, "lanes": lanes.value, "flop_per_step": flops.value, "perm": perm[:2 * nb.value]}
+
+
 def collapse(y, H, Z):
     """Collapse transform of R/statespacer.R:815-900 (include/ssgpu.h section 6e).  y N x p (NaN = missing),
     H p x p x {1|N}, Z p x m2 x {1|N}.  Returns y_star (N x m2, NaN where R writes NA), H_star (m2 x m2 x {1|N}),

@@ -662,3 +662,26 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
 }
 
 }  // namespace ssgpu
+
+// Host-only helper (no device needed): the block decomposition the block-row kernel would use.
+extern "C" int ssgpu_plan_blocks(const double* T, const double* R, const double* Q, int m, int r, int p, int* perm,
+                                 int* n_blocks, int* lanes, int* flop_per_step) {
+  using namespace ssgpu;
+  SS_ARG(T && R && m >= 1 && r >= 1 && p >= 1, "ssgpu_plan_blocks: bad arguments");
+  BlkPlan pl;
+  std::string why;
+  std::vector<unsigned char> qpat;
+  if (Q) {
+    qpat.resize((size_t)r * r);
+    for (size_t i = 0; i < qpat.size(); i++) qpat[i] = Q[i] != 0.0;
+  }
+  const bool ok = m <= 2 * kBlkMaxNB && p <= kBlkMaxP &&
+                  plan_blocks(T, 0, R, 0, Q ? qpat.data() : nullptr, m, r, &pl, &why);
+  if (n_blocks) *n_blocks = ok ? pl.nb : 0;
+  if (!ok) return SSGPU_OK;  // not decomposable: the automatic dispatch uses another kernel
+  if (perm)
+    for (int i = 0; i < 2 * kBlkMaxNB; i++) perm[i] = pl.perm[i];
+  if (lanes) *lanes = blk_lanes(pl.nb);
+  if (flop_per_step) *flop_per_step = blk_flops_per_step(pl.nb, p);
+  return SSGPU_OK;
+}

@@ -4,6 +4,8 @@ import ctypes as C
 import os
 import re
 
+import math
+
 import numpy as np
 import pytest
 
@@ -131,3 +133,28 @@ def test_r_call_shim_type_checks():
     for name, arity in (("ExtractComponentC", 2), ("FastSmootherC", 10), ("KalmanC", 10), ("LogLikC", 9),
                         ("SimulateC", 12)):                       # src/RcppExports.cpp:108-115
         assert f'{{"_statespacer_{name}", (DL_FUNC)&_statespacer_{name}, {arity}}}' in src
+
+
+def test_plan_blocks_host_helper():
+    """ssgpu_plan_blocks (host only): the block decomposition of the block-row kernel.  Config 5 is 7 blocks of coupled
+    pairs (slope pair, five seasonal rotations) plus the paired-up singles; a SARIMA companion matrix, a dense Q that
+    couples three states, or 17 uncoupled states do not decompose."""
+    from statespacer_b200 import api, sysmat
+    sm = sysmat.bsm12(0.5 * np.log([1.0, 0.1, 0.01, 0.05]))
+    T, R, Q = sm.T[:, :, 0], sm.R[:, :, 0], sm.Q[:, :, 0]
+    pl = api.plan_blocks(T, R)
+    assert pl["n_blocks"] == 7 and pl["lanes"] == 8 and pl["flop_per_step"] == 2824
+    perm = pl["perm"].reshape(7, 2)
+    assert sorted(perm.ravel().tolist()) == list(range(14))
+    for a, b in perm:                                   # nothing of T outside the blocks
+        others = [k for k in range(14) if k not in (a, b)]
+        assert not T[np.ix_([a, b], others)].any() and not T[np.ix_(others, [a, b])].any()
+    assert [1, 2] in perm.tolist()                      # level and slope share a block
+    assert api.plan_blocks(T, R, Q)["n_blocks"] == 7    # diagonal Q given explicitly
+    air = sysmat.airline([0.5 * math.log(0.00135), 0.4, 0.55])
+    assert api.plan_blocks(air.T[:, :, 0], air.R[:, :, 0]) is None
+    Qd = Q.copy()
+    Qd[1, 2] = Qd[2, 1] = Qd[1, 3] = Qd[3, 1] = 0.01    # level disturbance correlated with two others
+    assert api.plan_blocks(T, R, Qd) is None
+    assert api.plan_blocks(np.eye(17), np.eye(17)) is None
+    assert api.plan_blocks(np.eye(3), np.eye(3))["n_blocks"] == 2 and api.plan_blocks(np.eye(3), np.eye(3))["lanes"] == 2
