@@ -158,9 +158,10 @@ typedef struct ssgpu_model {
 
 #define SSGPU_KERNEL_BLK 6      /* block-row DFMA kernel: T block diagonal with blocks of at most 2 x 2 after re-ordering
                                    the states (residuals, level, slope, trigonometric seasonals, cycles, regression
-                                   coefficients), at most 8 blocks (m <= 16), p <= 8, R Q R' inside the blocks; Z may be
-                                   time-varying when p = 1 (explanatory variables); SSGPU_E_ARG if not eligible.
-                                   AUTO tries it first */
+                                   coefficients), R Q R' inside the blocks; at most 8 blocks (m <= 16) with p <= 8, or
+                                   up to 16 blocks (m <= 32) with p = 1 and a diagonal R Q R'; Z may be time-varying
+                                   when p = 1 (explanatory variables); SSGPU_E_ARG if not eligible.  AUTO tries it
+                                   first */
 
 /* host pointers everywhere (y, the matrices' data, out); copies in, runs, copies out, synchronises */
 int ssgpu_loglik_batch(const double* y, long long B, int V, const ssgpu_model* model, int kernel,
@@ -306,7 +307,7 @@ int ssgpu_forecast(int h, int p, int m, int r, const double* a1, const double* P
 int ssgpu_plan_state_order(const double* T, int m, int* perm, unsigned* tile_mask, int* dmma_per_step);
 /* The same for the block-row kernel (SSGPU_KERNEL_BLK): T m x m, R m x r, Q r x r or NULL (= diagonal), all
  * column-major.  *n_blocks = number of 2 x 2 blocks, or 0 when the model does not decompose (a state coupled with two
- * others through T or R Q R', more than 8 blocks, p > 8); perm[16]: internal position 2I+e -> state index of the
+ * others through T or R Q R', more than 16 blocks, p > 8); perm[32]: internal position 2I+e -> state index of the
  * caller, -1 = padding; *lanes = lanes per evaluation; *flop_per_step = FP64 operations the kernel issues per series
  * and time step (fma = 2, all lanes). */
 int ssgpu_plan_blocks(const double* T, const double* R, const double* Q, int m, int r, int p, int* perm,

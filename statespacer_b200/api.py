@@ -212,7 +212,7 @@ def plan_blocks(T, R, Q=None, p=1):
     T = _f(np.asarray(T, dtype=np.float64).reshape(np.shape(T)[0], np.shape(T)[1]))
     R = _f(np.asarray(R, dtype=np.float64).reshape(np.shape(R)[0], np.shape(R)[1]))
     Qm = None if Q is None else _f(np.asarray(Q, dtype=np.float64).reshape(np.shape(Q)[0], np.shape(Q)[1]))
-    perm = np.full(16, -1, dtype=np.int32)
+    perm = np.full(32, -1, dtype=np.int32)
     nb, lanes, flops = C.c_int(), C.c_int(), C.c_int()
     native.check(native.lib().ssgpu_plan_blocks(_ptr(T), _ptr(R), _ptr(Qm), T.shape[0], R.shape[1], int(p), perm.ctypes.data,
                                                 C.addressof(nb), C.addressof(lanes), C.addressof(flops)))

@@ -270,8 +270,8 @@ struct HostShared {  // optional host copies of the shared, time-invariant matri
 struct BlkPlan {
   int nb;                // number of 2 x 2 blocks (a lone state is padded with an empty partner)
   int q_offdiag;         // R Q R' has off-diagonal entries inside the blocks
-  signed char perm[16];  // internal position 2I+e holds state perm[2I+e] of the caller, -1 = padding
-  double Tb[8][4];       // T_J[row][col] at [2*row + col]
+  signed char perm[32];  // internal position 2I+e holds state perm[2I+e] of the caller, -1 = padding
+  double Tb[16][4];      // T_J[row][col] at [2*row + col]
 };
 bool plan_blocks(const double* Th, int t_diag, const double* Rh, int r_diag, const unsigned char* qpat, int m, int r,
                  BlkPlan* pl, std::string* why);

@@ -4,7 +4,7 @@
 // Restates the recursion of src/LogLikC.cpp:68-214 (univariate treatment, exact diffuse initialisation,
 // NaN = missing) for models whose Z, T, R are shared by the batch, T and R time-invariant, Z time-invariant or -- with
 // p = 1 -- one row per time point (explanatory variables) (per-evaluation a, P_inf, P_star, Q allowed) and whose T, after re-ordering the states, is  blkdiag(T_0, ..., T_{NB-1})  with
-// 1 x 1 or 2 x 2 blocks, NB <= 8 (m <= 16), and whose R Q R' has no entry outside those blocks.  That is every
+// 1 x 1 or 2 x 2 blocks, NB <= 8 (m <= 16; NB <= 16, m <= 32 when p = 1), and whose R Q R' has no entry outside those blocks.  That is every
 // structural model statespacer builds from residuals, level, slope, trigonometric seasonals, cycles and
 // regression coefficients (R/GetSysMat.R:1388-1426, R/Components-Unobserved.R:143-159,491-519): T couples a state
 // with at most one partner.  BASELINE.json config 5 (m = 14) is 7 such blocks.
@@ -32,8 +32,9 @@ namespace ssgpu {
 #ifndef SSGPU_BLK_MINB
 #define SSGPU_BLK_MINB 2  // resident CTAs per SM the register budget is sized for (2: 255 registers, 3: 168, 4: 128)
 #endif
-constexpr int kBlkThreads = 128;
-constexpr int kBlkMaxNB = 8;
+constexpr int kBlkThreads = 128;   // CTA of the register-constant instantiations (NB <= 8)
+constexpr int kBlkThreadsCS = 64;  // NB > 8: P_inf of a CTA (16 NB doubles per thread) has to fit the static 48 KB
+constexpr int kBlkMaxNB = 16;  // blocks: 1..8 with T_J and z in registers, 9..16 (p = 1) with both in shared memory
 constexpr int kBlkMaxP = 8;
 
 struct BlkArgs {
@@ -61,16 +62,28 @@ __device__ __forceinline__ double blk_rcp(double x) {
 // QOFF: the diagonal blocks of R Q R' have off-diagonal entries (correlated disturbances of a multivariate model)
 // ZTV: Z changes with t (explanatory variables, R/Components-Regressors.R:60-78); p = 1 only
 template <int L, int NB, bool P1, bool QOFF, bool ZTV = false>
-__global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel(const BlkArgs A) {
+__global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, NB > 8 ? 4 : SSGPU_BLK_MINB)
+    loglik_blk_kernel(const BlkArgs A) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int G = 32 / L;  // evaluations per warp
+  // NB > 8 (17 <= m <= 32, p = 1): the block row alone is 8 NB <= 128 registers, so T_J and z live in shared memory
+  // (8-byte broadcast loads) and the R Q R' addends are selected per step instead of hoisted
+  constexpr bool CS = NB > 8;
+  constexpr int BT = CS ? kBlkThreadsCS : kBlkThreads;
+  static_assert(!CS || P1, "more than 8 blocks: p = 1 only");
   const DModel& md = A.md;
   const int N = md.N, p = P1 ? 1 : md.p, M = md.m, r = md.r;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int I = lane % L, g = lane / L;
+  __shared__ double tb_s[CS ? NB * 4 : 1], zs_s[CS ? NB * 2 : 1];
+  if constexpr (CS) {  // before any warp leaves: filled by the whole CTA
+    for (int e = threadIdx.x; e < NB * 4; e += BT) tb_s[e] = (&A.Tb[0][0])[e];
+    for (int e = threadIdx.x; e < NB * 2; e += BT) zs_s[e] = A.z[0][e];
+    __syncthreads();
+  }
   // evaluations are numbered series-major (w = b*V + v) so that the V parameter vectors of a series run side by
   // side and share its y through L1/L2; results keep the public order e = v*B + b
-  const long long w0 = ((long long)blockIdx.x * (kBlkThreads / 32) + warp) * G;
+  const long long w0 = ((long long)blockIdx.x * (BT / 32) + warp) * G;
   if (w0 >= A.E) return;  // whole warp
   // every lane stays alive (shuffles, __syncwarp): groups beyond the last evaluation shadow it and do not store
   const bool live = w0 + g < A.E;
@@ -79,10 +92,10 @@ __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel
   const long long e_id = v * A.B + b;
   const bool own = I < NB;  // L > NB: the surplus lanes carry zero blocks
 
-  __shared__ double2 xch_s[kBlkThreads / 32][2][NB][G];
-  __shared__ double pinf_s[NB * 4][kBlkThreads];
+  __shared__ double2 xch_s[BT / 32][2][NB][G];
+  __shared__ double pinf_s[NB * 4][BT];
   double2(*xch)[NB][G] = xch_s[warp];
-  double(*pinf)[kBlkThreads] = pinf_s;
+  double(*pinf)[BT] = pinf_s;
   const int tx = threadIdx.x;
 
   // ---- own block row of P_star, P_inf, own T block, own part of a and z, own diagonal block of R Q R' ------------
@@ -174,8 +187,8 @@ __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel
   //     loop-variant, it funnels every constant through ONE uniform register pair, LDCU / 2 DFMA / LDCU ..., each
   //     load's latency exposed (IDC 56 % busy, `short_scoreboard` the top stall), FP64 pipe 60 %, 162 ms.
   const int lz = (int)(w_id >> 62);
-  double TJ[NB][4], ZJ[NB][2];
-  {
+  double TJ[CS ? 1 : NB][4], ZJ[CS ? 1 : NB][2];
+  if constexpr (!CS) {
     const double* tbp = &A.Tb[0][0] + lz;
     const double* zp = &A.z[0][0] + lz;
 #pragma unroll
@@ -189,14 +202,18 @@ __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel
   // P_IJ <- T_I P_IJ T_J' (+ the own diagonal block of R Q R' when J == I); X[r][c] = sum_k Y[r][k] T_J[c][k].
   // The selected addends (dg ? q : 0) are loop-invariant and hoisted by the compiler: 2 NB doubles when R Q R' is
   // diagonal (QOFF = false).
+  int zv = 0;  // NB > 8: always 0, but refreshed from a per-lane counter every step so that the selected R Q R' addends
+               // are not hoisted into 4 NB registers
   auto time_block = [&](int J, double& p0, double& p1, double& p2, double& p3, bool with_q) {
     const double y00 = fma(t01, p2, t00 * p0), y01 = fma(t01, p3, t00 * p1);
     const double y10 = fma(t11, p2, t10 * p0), y11 = fma(t11, p3, t10 * p1);
-    const bool dg = with_q && J == I;
-    p0 = fma(y01, TJ[J][1], fma(y00, TJ[J][0], dg ? q0 : 0.0));
-    p1 = fma(y01, TJ[J][3], fma(y00, TJ[J][2], (QOFF && dg) ? q1 : 0.0));
-    p2 = fma(y11, TJ[J][1], fma(y10, TJ[J][0], (QOFF && dg) ? q2 : 0.0));
-    p3 = fma(y11, TJ[J][3], fma(y10, TJ[J][2], dg ? q3 : 0.0));
+    const bool dg = with_q && J == (CS ? I + zv : I);
+    const double tj0 = CS ? tb_s[J * 4 + 0] : TJ[CS ? 0 : J][0], tj1 = CS ? tb_s[J * 4 + 1] : TJ[CS ? 0 : J][1];
+    const double tj2 = CS ? tb_s[J * 4 + 2] : TJ[CS ? 0 : J][2], tj3 = CS ? tb_s[J * 4 + 3] : TJ[CS ? 0 : J][3];
+    p0 = fma(y01, tj1, fma(y00, tj0, dg ? q0 : 0.0));
+    p1 = fma(y01, tj3, fma(y00, tj2, (QOFF && dg) ? q1 : 0.0));
+    p2 = fma(y11, tj1, fma(y10, tj0, (QOFF && dg) ? q2 : 0.0));
+    p3 = fma(y11, tj3, fma(y10, tj2, dg ? q3 : 0.0));
   };
 
   const long long Np = (long long)N * p;
@@ -318,15 +335,20 @@ __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel
     if (t < N) {
       double zi0 = A.z[0][2 * I], zi1 = A.z[0][2 * I + 1];
       // time-varying Z: the row of step t in internal order, the same for every evaluation (16-byte broadcast loads)
+      const double2* zcur = nullptr;  // NB > 8 with time-varying Z: the row of the step, read where it is used
       auto load_z = [&](int tt) {
         if constexpr (ZTV) {
           const double2* zr = reinterpret_cast<const double2*>(A.zt + (size_t)tt * (2 * kBlkMaxNB));
 #pragma unroll
-          for (int J = 0; J < NB; J++) {
-            const double2 zz = zr[J];
-            ZJ[J][0] = zz.x;
-            ZJ[J][1] = zz.y;
+          if constexpr (!CS) {
+#pragma unroll
+            for (int J = 0; J < NB; J++) {
+              const double2 zz = zr[J];
+              ZJ[J][0] = zz.x;
+              ZJ[J][1] = zz.y;
+            }
           }
+          zcur = zr;
           const double2 zo = zr[I];
           zi0 = zo.x;
           zi1 = zo.y;
@@ -342,10 +364,22 @@ __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel
         double m0a = 0.0, m0b = 0.0, m1a = 0.0, m1b = 0.0;
 #pragma unroll
         for (int J = 0; J < NB; J++) {
-          m0a = fma(P[J][0], ZJ[J][0], m0a);
-          m0b = fma(P[J][1], ZJ[J][1], m0b);
-          m1a = fma(P[J][2], ZJ[J][0], m1a);
-          m1b = fma(P[J][3], ZJ[J][1], m1b);
+          double z0, z1;
+          if constexpr (!CS) {
+            z0 = ZJ[J][0];
+            z1 = ZJ[J][1];
+          } else if constexpr (ZTV) {
+            const double2 zz = zcur[J];
+            z0 = zz.x;
+            z1 = zz.y;
+          } else {
+            z0 = zs_s[2 * J];
+            z1 = zs_s[2 * J + 1];
+          }
+          m0a = fma(P[J][0], z0, m0a);
+          m0b = fma(P[J][1], z1, m0b);
+          m1a = fma(P[J][2], z0, m1a);
+          m1b = fma(P[J][3], z1, m1b);
         }
         m0 = m0a + m0b;
         m1 = m1a + m1b;
@@ -354,6 +388,7 @@ __global__ void __launch_bounds__(kBlkThreads, SSGPU_BLK_MINB) loglik_blk_kernel
         const double yv = ynext;
         ynext = ynext2;
         if (t + 2 < N) ynext2 = A.y[(long long)(t + 2) * A.B + b];
+        if constexpr (CS) zv = n_terms >> 30;
         load_z(t);
         innovation();
         const double tm0 = fma(t01, m1, t00 * m0), tm1 = fma(t11, m1, t10 * m0);  // (T M)_I
@@ -522,7 +557,7 @@ bool blk_eligible(const DModel& md, std::string* why) {
     if (why) *why = s;
     return false;
   };
-  if (md.m > 2 * kBlkMaxNB) return no("m > 16");
+  if (md.m > 2 * kBlkMaxNB) return no("m > 32");
   if (md.p > kBlkMaxP) return no("p > 8");
   if (!md.Z.shared() || !md.T.shared() || !md.R.shared()) return no("Z, T, R must be shared by the batch");
   if (md.T.tv() || md.R.tv() || md.Q.tv()) return no("time-varying T, R or Q");
@@ -541,12 +576,18 @@ static void launch_blk_one(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
   }();
   if (pad > 0)
     cudaFuncSetAttribute(loglik_blk_kernel<L, NB, P1, QOFF, ZTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-  loglik_blk_kernel<L, NB, P1, QOFF, ZTV><<<blocks, kBlkThreads, pad, st>>>(A);
+  loglik_blk_kernel<L, NB, P1, QOFF, ZTV><<<blocks, NB > 8 ? kBlkThreadsCS : kBlkThreads, pad, st>>>(A);
 }
 
 template <int L, int NB>
 static void launch_blk_nb(const BlkArgs& A, bool q_offdiag, unsigned blocks, cudaStream_t st) {
-  if (A.md.p == 1 && A.zt) {
+  if constexpr (NB > 8) {  // p = 1, diagonal R Q R' (checked by the caller)
+    if (A.zt)
+      launch_blk_one<L, NB, true, false, true>(A, blocks, st);
+    else
+      launch_blk_one<L, NB, true, false>(A, blocks, st);
+    return;
+  } else if (A.md.p == 1 && A.zt) {
     if (q_offdiag)
       launch_blk_one<L, NB, true, true, true>(A, blocks, st);
     else
@@ -564,7 +605,7 @@ static void launch_blk_nb(const BlkArgs& A, bool q_offdiag, unsigned blocks, cud
   }
 }
 
-int blk_lanes(int nb) { return nb > 4 ? 8 : nb > 2 ? 4 : nb > 1 ? 2 : 1; }
+int blk_lanes(int nb) { return nb > 8 ? 16 : nb > 4 ? 8 : nb > 2 ? 4 : nb > 1 ? 2 : 1; }
 
 // FP64 operations (fma = 2) the kernel issues per series and time step in the regular phase, all L lanes counted
 int blk_flops_per_step(int nb, int p) {
@@ -638,7 +679,15 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     SS_CUDA(cudaStreamSynchronize(st));  // the host vector dies with this frame
     A.zt = ztd.as<double>();
   }
-  const int L = blk_lanes(pl.nb), G = 32 / L, wpb = kBlkThreads / 32;
+  if (pl.nb > 8 && (p != 1 || pl.q_offdiag)) {  // more than 8 blocks: univariate models with a diagonal R Q R' only
+    why = "more than 8 blocks needs p = 1 and a diagonal R Q R'";
+    if (applicable) {
+      *applicable = false;
+      return SSGPU_OK;
+    }
+    SS_ARG(false, "block kernel not eligible: " + why);
+  }
+  const int L = blk_lanes(pl.nb), G = 32 / L, wpb = (pl.nb > 8 ? kBlkThreadsCS : kBlkThreads) / 32;
   const long long blocks = (A.E + (long long)wpb * G - 1) / ((long long)wpb * G);
   SS_ARG(blocks < (1LL << 31), "block kernel: batch too large for one launch");
   const unsigned nblk = (unsigned)blocks;
@@ -650,7 +699,15 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     case 5: launch_blk_nb<8, 5>(A, pl.q_offdiag != 0, nblk, st); break;
     case 6: launch_blk_nb<8, 6>(A, pl.q_offdiag != 0, nblk, st); break;
     case 7: launch_blk_nb<8, 7>(A, pl.q_offdiag != 0, nblk, st); break;
-    default: launch_blk_nb<8, 8>(A, pl.q_offdiag != 0, nblk, st); break;
+    case 8: launch_blk_nb<8, 8>(A, pl.q_offdiag != 0, nblk, st); break;
+    case 9: launch_blk_nb<16, 9>(A, false, nblk, st); break;
+    case 10: launch_blk_nb<16, 10>(A, false, nblk, st); break;
+    case 11: launch_blk_nb<16, 11>(A, false, nblk, st); break;
+    case 12: launch_blk_nb<16, 12>(A, false, nblk, st); break;
+    case 13: launch_blk_nb<16, 13>(A, false, nblk, st); break;
+    case 14: launch_blk_nb<16, 14>(A, false, nblk, st); break;
+    case 15: launch_blk_nb<16, 15>(A, false, nblk, st); break;
+    default: launch_blk_nb<16, 16>(A, false, nblk, st); break;
   }
   SS_CUDA(cudaGetLastError());
   count_launch();

@@ -138,7 +138,7 @@ def test_r_call_shim_type_checks():
 def test_plan_blocks_host_helper():
     """ssgpu_plan_blocks (host only): the block decomposition of the block-row kernel.  Config 5 is 7 blocks of coupled
     pairs (slope pair, five seasonal rotations) plus the paired-up singles; a SARIMA companion matrix, a dense Q that
-    couples three states, or 17 uncoupled states do not decompose."""
+    couples three states, or 33 uncoupled states do not decompose."""
     from statespacer_b200 import api, sysmat
     sm = sysmat.bsm12(0.5 * np.log([1.0, 0.1, 0.01, 0.05]))
     T, R, Q = sm.T[:, :, 0], sm.R[:, :, 0], sm.Q[:, :, 0]
@@ -156,5 +156,6 @@ def test_plan_blocks_host_helper():
     Qd = Q.copy()
     Qd[1, 2] = Qd[2, 1] = Qd[1, 3] = Qd[3, 1] = 0.01    # level disturbance correlated with two others
     assert api.plan_blocks(T, R, Qd) is None
-    assert api.plan_blocks(np.eye(17), np.eye(17)) is None
+    assert api.plan_blocks(np.eye(17), np.eye(17))["n_blocks"] == 9 and api.plan_blocks(np.eye(17), np.eye(17))["lanes"] == 16
+    assert api.plan_blocks(np.eye(33), np.eye(33)) is None
     assert api.plan_blocks(np.eye(3), np.eye(3))["n_blocks"] == 2 and api.plan_blocks(np.eye(3), np.eye(3))["lanes"] == 2

@@ -256,6 +256,12 @@ def _structural_models():
         "slope+seasonal12 (m=14, 7 blocks)": S.bsm12(0.5 * np.log([1.0, 0.1, 0.01, 0.05])),
         "slope+seasonal12+cycle (m=16, 8 blocks)": S._combine(
             1, [[1.0]], [S.comp_level_slope(0.1, 0.01), S.comp_bsm_trig(12, 0.05), _cycle(0.9, 0.4, 0.3)]),
+        "slope+seasonal12+seasonal7 (m=20, 10 blocks)": S._combine(
+            1, [[1.0]], [S.comp_level_slope(0.1, 0.01), S.comp_bsm_trig(12, 0.05), S.comp_bsm_trig(7, 0.03)]),
+        "slope+seasonal24 (m=26, 13 blocks)": S._combine(
+            1, [[1.0]], [S.comp_level_slope(0.1, 0.01), S.comp_bsm_trig(24, 0.05)]),
+        "slope+seasonal24+seasonal7 (m=32, 16 blocks)": S._combine(
+            1, [[1.0]], [S.comp_level_slope(0.1, 0.01), S.comp_bsm_trig(24, 0.05), S.comp_bsm_trig(7, 0.03)]),
     }
 
 
@@ -266,7 +272,8 @@ def test_batch_blk_kernel(name):
     leave the diffuse phase at different time points), against the oracle and the generic kernel."""
     sm = _structural_models()[name]
     rng = np.random.default_rng(len(name))
-    B, N, m = 37, 45, sm.m
+    B, m = 37, sm.m
+    N = 45 if m <= 16 else 3 * m                       # long enough for the d = m - 1 diffuse states to be identified
     y = np.stack([simulate_y(rng, sm, N, missing=0.12)[:, 0] for _ in range(B)], axis=1)      # (N, B)
     y[:3, 5] = np.nan                                                   # a series that starts with missing values
     scale = rng.uniform(0.5, 2.0, size=(B, 1))
@@ -277,7 +284,8 @@ def test_batch_blk_kernel(name):
     assert api.last_kernel().startswith("loglik_blk_kernel<"), api.last_kernel()
     gen = api.loglik_batch(y, sm, Q_diag=Qd, P_star_diag=Pd, a=ab, kernel="generic")
     auto = api.loglik_batch(y, sm, Q_diag=Qd, P_star_diag=Pd, a=ab)
-    assert api.last_kernel().startswith("loglik_blk_kernel<") and np.array_equal(auto, got)
+    assert api.last_kernel().startswith("loglik_blk_kernel<") and np.array_equal(auto, got, equal_nan=True)
+    assert np.all(np.isfinite(got))
     for b in range(B):
         smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=np.diag(Qd[b])[:, :, None], a=ab[b], P_inf=sm.P_inf,
                             P_star=np.diag(Pd[b]))
@@ -287,13 +295,13 @@ def test_batch_blk_kernel(name):
         assert abs(gen[b] - want) <= RTOL * max(1, abs(want)), (name, b, gen[b], want)
 
 
-@pytest.mark.parametrize("seasonal", [12, 4])
+@pytest.mark.parametrize("seasonal", [12, 4, 24])
 def test_batch_blk_kernel_time_varying_z(seasonal):
     """Univariate structural model with two explanatory variables (R/Components-Regressors.R:60-78: constant, exactly
     diffuse coefficient states whose row of Z is the regressor value at t): time-varying Z on the block-row kernel,
     against the oracle and the generic kernel; the automatic dispatch picks it."""
     rng = np.random.default_rng(60 + seasonal)
-    N, B = 70, 23
+    N, B = (70 if seasonal <= 12 else 110), 23
     base = sysmat._combine(1, [[0.8]], [sysmat.comp_level_slope(0.1, 0.01), sysmat.comp_bsm_trig(seasonal, 0.05)])
     m0 = base.m
     X = rng.normal(size=(N, 2))
@@ -314,7 +322,7 @@ def test_batch_blk_kernel_time_varying_z(seasonal):
     assert "time-varying Z" in api.last_kernel(), api.last_kernel()
     gen = api.loglik_batch(y, sm, Q_diag=Qd, kernel="generic")
     auto = api.loglik_batch(y, sm, Q_diag=Qd)
-    assert api.last_kernel().startswith("loglik_blk_kernel<") and np.array_equal(auto, got)
+    assert api.last_kernel().startswith("loglik_blk_kernel<") and np.array_equal(auto, got) and np.all(np.isfinite(got))
     for b in range(B):
         smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=np.diag(Qd[b])[:, :, None], a=sm.a, P_inf=sm.P_inf, P_star=sm.P_star)
         yb = y[:, b:b + 1]
