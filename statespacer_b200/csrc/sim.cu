@@ -248,6 +248,7 @@ struct EllS {
   const double* vs;  // shared memory [W][MP], valid when st == 0
   const double* vg;  // global per-slice blocks [W][rows], used when st != 0
   const int* off;    // shared memory [W][MP]: idx * kRegBT * 8
+  const unsigned* rm;  // shared memory [W]: bit i set when entry w of row i is a stored one (not padding); st == 0 only
   int W, rows;
   long long st;
 };
@@ -266,6 +267,17 @@ __device__ __forceinline__ EllS stage_ell(const Ell& E, double*& dcur, int*& icu
   }
   s.off = icur;
   icur += E.W * MP;
+  // row masks of the sweeps: a padded entry is (index 0, value 0.0) and fma(0.0, x[0], acc) == acc, so leaving it out
+  // changes no bit.  (A stored entry that happens to be an exact 0.0 is left out as well: same argument.)
+  unsigned* rm = reinterpret_cast<unsigned*>(icur);
+  if (E.st == 0 && tid < E.W) {
+    unsigned mk = 0;
+    for (int i = 0; i < E.rows && i < 32; i++)
+      if (E.val[tid * E.rows + i] != 0.0) mk |= 1u << i;
+    rm[tid] = mk;
+  }
+  s.rm = rm;
+  icur += (E.W + 1) & ~1;  // keeps the next table 8-byte aligned
   s.vs = dcur;
   if (E.st == 0) dcur += E.W * MP;
   return s;
@@ -280,8 +292,16 @@ __device__ __forceinline__ void ell_apply_s(const EllS& E, int t, const double* 
     for (int w = 0; w < E.W; w++) {
       const int* of = E.off + w * MP;
       const double* vl = E.vs + w * MP;
+      // groups of four rows without a stored entry in this sweep are branched over (the same decision for every draw):
+      // a SARIMA companion matrix has 28 + 2 + 1 entries in its three sweeps of 32
+      const unsigned mk = E.rm[w];
 #pragma unroll
-      for (int i = 0; i < MP; i++) out[i] = fma(vl[i], *reinterpret_cast<const double*>(xb + of[i]), out[i]);
+      for (int i0 = 0; i0 < MP; i0 += 4) {
+        if (((mk >> i0) & 0xFu) == 0u) continue;
+#pragma unroll
+        for (int i = i0; i < i0 + 4 && i < MP; i++)
+          out[i] = fma(vl[i], *reinterpret_cast<const double*>(xb + of[i]), out[i]);
+      }
     }
   } else {
     const double* vt = E.vg + (long long)t * E.st;
@@ -305,7 +325,10 @@ template <int MP>
 __global__ void __launch_bounds__(kRegBT) simulate_reg_kernel(const SimArgs A) {
   extern __shared__ double sh[];
   const int tid = threadIdx.x;
-  const long long s = (long long)blockIdx.x * kRegBT + tid;
+  // every lane stays alive (warp votes below); lanes beyond the last draw shadow draw S-1 and do not store
+  const long long s_raw = (long long)blockIdx.x * kRegBT + tid;
+  const bool live = s_raw < A.S;
+  const long long s = live ? s_raw : A.S - 1;
   const int m = A.m, p = A.p, r = A.r, r_tot = A.r * A.repeat_Q, N = A.N;
   const int a_ld = A.a_ld ? A.a_ld : m, eta_ld = A.eta_ld ? A.eta_ld : r_tot;
   const long long S = A.S;
@@ -318,7 +341,6 @@ __global__ void __launch_bounds__(kRegBT) simulate_reg_kernel(const SimArgs A) {
     Re = stage_ell<MP>(A.Re, dcur, icur, tid);
   }
   __syncwarp();
-  if (s >= A.S) return;
   double av[MP];
 #pragma unroll
   for (int i = 0; i < MP; i++) av[i] = 0.0;
@@ -344,25 +366,31 @@ __global__ void __launch_bounds__(kRegBT) simulate_reg_kernel(const SimArgs A) {
         double acc = 0.0;
         for (int l = 0; l < r; l++) acc = fma(Qr[rr + l * r], dd[l + r * q], acc);
         es[rr + r * q] = acc;
-        if (A.eta) A.eta[((long long)t * eta_ld + A.eta_off + rr + r * q) * S + s] = acc;
-        if (A.eta_only && A.y) A.y[((long long)t * r_tot + rr + r * q) * S + s] += acc;
+        if (A.eta && live) A.eta[((long long)t * eta_ld + A.eta_off + rr + r * q) * S + s] = acc;
+        if (A.eta_only && A.y && live) A.y[((long long)t * r_tot + rr + r * q) * S + s] += acc;
       }
     if (A.eta_only) continue;
     const double* Zt = slice_of(A.Z, t);
-    if (A.a) {
+    if (A.a && live) {
 #pragma unroll
       for (int k = 0; k < MP; k++)
         if (k < m) A.a[((long long)t * a_ld + A.a_off + k) * S + s] = av[k];
     }
     for (int j = 0; j < p; j++) {
       double acc = 0.0;
+      // non-zero entries of the row of Z (the same for every draw): groups of four zero entries are branched over
+      const unsigned zm = __ballot_sync(0xffffffffu, tid < m && Zt[j + (tid < m ? tid : 0) * p] != 0.0);
 #pragma unroll
-      for (int k = 0; k < MP; k++)
-        if (k < m) {
-          const double z = Zt[j + k * p];
-          if (z != 0.0) acc = fma(z, av[k], acc);
-        }
-      if (A.y) {
+      for (int k0 = 0; k0 < MP; k0 += 4) {
+        if (((zm >> k0) & 0xFu) == 0u) continue;
+#pragma unroll
+        for (int k = k0; k < k0 + 4 && k < MP; k++)
+          if (k < m) {
+            const double z = Zt[j + k * p];
+            if (z != 0.0) acc = fma(z, av[k], acc);
+          }
+      }
+      if (A.y && live) {
         double* yp = A.y + ((long long)t * p + j) * S + s;
         *yp = A.y_acc ? *yp + acc : acc;
       }
@@ -432,11 +460,18 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
       const double* kc = kb + cur * MP;
       const double* zc = zb + cur * MP;
       if ((A.g.code[index] & 255) != 0) {
+        // which entries of the row of Z are non-zero: the same for every draw, so whole groups of four states are
+        // branched over (Z of a structural or SARIMA model has a handful of ones)
+        const unsigned zm = __ballot_sync(0xffffffffu, tid < MP && zc[tid < MP ? tid : 0] != 0.0);
         double za = 0.0;
 #pragma unroll
-        for (int k = 0; k < MP; k++) {
-          const double z = zc[k];
-          if (z != 0.0) za = fma(z, av[k], za);
+        for (int k0 = 0; k0 < MP; k0 += 4) {
+          if (((zm >> k0) & 0xFu) == 0u) continue;
+#pragma unroll
+          for (int k = k0; k < k0 + 4 && k < MP; k++) {
+            const double z = zc[k];
+            if (z != 0.0) za = fma(z, av[k], za);
+          }
         }
         const double vv = y_now - za;
         if (live) A.v[index * S + s] = vv;
@@ -485,10 +520,15 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
         for (int k = 0; k < MP; k++) d0 = fma(kc[k], rr[k], d0);
         if (c == 1) {
           const double sc = c1 - d0;
+          const unsigned zm = __ballot_sync(0xffffffffu, tid < MP && zc[tid < MP ? tid : 0] != 0.0);
 #pragma unroll
-          for (int k = 0; k < MP; k++) {
-            const double z = zc[k];
-            if (z != 0.0) rr[k] = fma(z, sc, rr[k]);
+          for (int k0 = 0; k0 < MP; k0 += 4) {
+            if (((zm >> k0) & 0xFu) == 0u) continue;
+#pragma unroll
+            for (int k = k0; k < k0 + 4 && k < MP; k++) {
+              const double z = zc[k];
+              if (z != 0.0) rr[k] = fma(z, sc, rr[k]);
+            }
           }
         } else {
           const double* k1 = A.g.K1 + index * m;
@@ -550,9 +590,29 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
       av[i] = (A.a0[i] + acc) + acc1;
     }
   }
+  // eta_{t-1} was written by this thread in the backward pass; it is fetched one step ahead of its use (up to four
+  // disturbances in registers -- the load otherwise sits at the head of every step's dependence chain)
+  double en[4] = {0.0, 0.0, 0.0, 0.0};
+  const bool pre = r <= 4;
+  if (pre && N > 1) {
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++)
+      if (kk < r) en[kk] = A.eta[(long long)kk * S + s];
+  }
   for (int t = 0; t < N; t++) {
     if (t > 0) {
-      for (int kk = 0; kk < r; kk++) es[kk] = A.eta[((long long)(t - 1) * r + kk) * S + s];
+      if (pre) {
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++)
+          if (kk < r) es[kk] = en[kk];
+        if (t + 1 < N) {
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++)
+            if (kk < r) en[kk] = A.eta[((long long)t * r + kk) * S + s];
+        }
+      } else {
+        for (int kk = 0; kk < r; kk++) es[kk] = A.eta[((long long)(t - 1) * r + kk) * S + s];
+      }
       double o2[MP];
       park<MP>(av, xs);
       ell_apply_s<MP>(Te, t - 1, &xs[0], m, av);
@@ -1078,7 +1138,9 @@ static int launch_simulate_bt(const SimArgs& A, cudaStream_t st) {
 
 template <int MP>
 static int launch_simulate_reg(const SimArgs& A, cudaStream_t st) {
-  auto tab = [](const Ell& E) { return (size_t)E.W * MP * ((E.st ? 0 : sizeof(double)) + sizeof(int)); };
+  auto tab = [](const Ell& E) {
+    return (size_t)E.W * MP * ((E.st ? 0 : sizeof(double)) + sizeof(int)) + sizeof(unsigned) * ((E.W + 1) & ~1);
+  };
   const size_t smem = sizeof(double) * kRegBT * 2 * MP + (A.eta_only ? 0 : tab(A.Te) + tab(A.Re)) + 16;
   SS_CUDA(cudaFuncSetAttribute(simulate_reg_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_t_sim.start(st);
@@ -1123,7 +1185,9 @@ static int launch_fs_bt(const FsArgs& A, cudaStream_t st) {
 
 template <int MP>
 static int launch_fs_reg(const FsArgs& A, cudaStream_t st) {
-  auto tab = [](const Ell& E) { return (size_t)E.W * MP * ((E.st ? 0 : sizeof(double)) + sizeof(int)); };
+  auto tab = [](const Ell& E) {
+    return (size_t)E.W * MP * ((E.st ? 0 : sizeof(double)) + sizeof(int)) + sizeof(unsigned) * ((E.W + 1) & ~1);
+  };
   const size_t smem = sizeof(double) * (kRegBT * 3 * MP + 4 * MP) + tab(A.Te) + tab(A.Tce) + tab(A.Re) + 16;
   SS_ARG(smem <= 200 * 1024, "FastSmootherC: sparse tables too large for shared memory");
   SS_CUDA(cudaFuncSetAttribute(fs_draw_reg_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1138,7 +1202,9 @@ static int launch_fs_reg(const FsArgs& A, cudaStream_t st) {
 template <int MP>
 static int launch_fs_lanes(const FsArgs& A, cudaStream_t st) {
   constexpr int DPC = kRegBT / kLPD;
-  auto tab = [](const Ell& E) { return (size_t)E.W * MP * ((E.st ? 0 : sizeof(double)) + sizeof(int)); };
+  auto tab = [](const Ell& E) {
+    return (size_t)E.W * MP * ((E.st ? 0 : sizeof(double)) + sizeof(int)) + sizeof(unsigned) * ((E.W + 1) & ~1);
+  };
   const size_t smem = sizeof(double) * (DPC * 3 * MP + 4 * MP) + tab(A.Te) + tab(A.Tce) + tab(A.Re) + 16;
   SS_ARG(smem <= 200 * 1024, "FastSmootherC: sparse tables too large for shared memory");
   SS_CUDA(cudaFuncSetAttribute(fs_draw_lanes_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
