@@ -159,3 +159,20 @@ def test_plan_blocks_host_helper():
     assert api.plan_blocks(np.eye(17), np.eye(17))["n_blocks"] == 9 and api.plan_blocks(np.eye(17), np.eye(17))["lanes"] == 16
     assert api.plan_blocks(np.eye(33), np.eye(33)) is None
     assert api.plan_blocks(np.eye(3), np.eye(3))["n_blocks"] == 2 and api.plan_blocks(np.eye(3), np.eye(3))["lanes"] == 2
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's own LogLikC on the host cores) runs without a GPU and prints one
+    JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "kalman_loglik_series_timesteps_per_s"
+    for k in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
