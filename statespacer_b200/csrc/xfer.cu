@@ -75,6 +75,8 @@ int copy_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st) {
   const size_t n = (bytes + kChunk - 1) / kChunk;
   std::vector<std::future<cudaError_t>> done(n);
   cudaError_t err = cudaSuccess;
+  int dev = 0;
+  cudaGetDevice(&dev);  // helper threads start on device 0: bind them to the caller's device (one process per GPU)
   for (size_t i = 0; i < n; i++) {
     const int slot = (int)(i % kRing);
     if (i >= (size_t)kRing) {
@@ -88,7 +90,8 @@ int copy_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st) {
     void* from = g_ring.buf[slot];
     cudaEvent_t ev = g_ring.ev[slot];
     char* to = static_cast<char*>(dst) + off;
-    done[i] = std::async(std::launch::async, [from, to, len, ev]() {
+    done[i] = std::async(std::launch::async, [from, to, len, ev, dev]() {
+      cudaSetDevice(dev);
       const cudaError_t w = cudaEventSynchronize(ev);
       if (w == cudaSuccess) std::memcpy(to, from, len);
       return w;
