@@ -418,8 +418,10 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
   const bool live = s_raw < S;
   const long long s = live ? s_raw : S - 1;
   // xs: gather source; es: eta_t for R eta; r1: the diffuse-phase vector r^(1) (touched on d of the N steps only)
-  ShVec<kRegBT> xs{sh + tid}, es{sh + (size_t)MP * kRegBT + tid}, r1{sh + (size_t)2 * MP * kRegBT + tid};
-  double* dcur = sh + (size_t)3 * MP * kRegBT;
+  // es holds the r disturbances of a step only (r rows, not MP): 20 instead of 28 KB per CTA at config 4, 11 instead of
+  // 8 resident CTAs per SM -- what bounds the kernel at 100,000 draws
+  ShVec<kRegBT> xs{sh + tid}, r1{sh + (size_t)MP * kRegBT + tid}, es{sh + (size_t)2 * MP * kRegBT + tid};
+  double* dcur = sh + ((size_t)2 * MP + r) * kRegBT;
   // the gain row K0 and the row of Z of an observation are the same for all draws: lane k fetches element k one
   // observation ahead and parks it in shared memory (two buffers), every lane then reads the m values as broadcast
   // loads at immediate offsets -- one global load per lane and step instead of 2 m uniform ones in the chain
@@ -569,9 +571,9 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
         if (live) A.eta[((long long)(t - 1) * r + kk) * S + s] = ev;
       }
       ell_apply_s<MP>(Tce, t - 1, &xs[0], m, rr);  // T' r
-      if (both) {  // T' r^(1): rare (the d diffuse steps), kept out of the registers
-        for (int i = 0; i < m; i++) es[i] = ell_row_dot(A.Tce, Tp, i, r1);
-        for (int i = 0; i < m; i++) r1[i] = es[i];
+      if (both) {  // T' r^(1): rare (the d diffuse steps), kept out of the registers; xs is free again here
+        for (int i = 0; i < m; i++) xs[i] = ell_row_dot(A.Tce, Tp, i, r1);
+        for (int i = 0; i < m; i++) r1[i] = xs[i];
       }
     }
   }
@@ -1188,7 +1190,7 @@ static int launch_fs_reg(const FsArgs& A, cudaStream_t st) {
   auto tab = [](const Ell& E) {
     return (size_t)E.W * MP * ((E.st ? 0 : sizeof(double)) + sizeof(int)) + sizeof(unsigned) * ((E.W + 1) & ~1);
   };
-  const size_t smem = sizeof(double) * (kRegBT * 3 * MP + 4 * MP) + tab(A.Te) + tab(A.Tce) + tab(A.Re) + 16;
+  const size_t smem = sizeof(double) * (kRegBT * (2 * MP + (size_t)A.r) + 4 * MP) + tab(A.Te) + tab(A.Tce) + tab(A.Re) + 16;
   SS_ARG(smem <= 200 * 1024, "FastSmootherC: sparse tables too large for shared memory");
   SS_CUDA(cudaFuncSetAttribute(fs_draw_reg_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_t_fs.start(st);
