@@ -197,7 +197,9 @@ int ssgpu_kalman_batch_dev(const double* y, long long B, const ssgpu_model* mode
  * shared matrices of `model`.
  *   ssgpu_loglik_grad_batch      host pointers; theta [b*k + i]; loglik[b] and the central-difference gradient
  *                                grad[b*k + i] = (l(theta + h e_i) - l(theta - h e_i)) / 2h from ONE launch of
- *                                1 + 2k evaluations per series (h = 1e-3 is stats::optim's ndeps default)
+ *                                1 + 2k evaluations per series (h = 1e-3 is stats::optim's ndeps default); with y in
+ *                                pinned host memory and B >= 16384 the upload is pipelined with the kernels over
+ *                                8 chunks of series, pageable y goes through the library's pinned staging ring
  *   ssgpu_loglik_grad_batch_dev  the same on device pointers (y, theta, loglik, grad), asynchronous on `stream`
  *   ssgpu_loglik_theta_batch_dev V arbitrary parameter vectors per series, theta [(v*B + b)*k + i] -> out[v*B + b]
  *                                (multistart candidates, the points of a numDeriv Hessian sweep) */
