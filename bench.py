@@ -224,6 +224,8 @@ class ClockSampler:
             time.sleep(self.interval_ms / 1000.0)
 
     def start(self):
+        if os.environ.get("SSGPU_BENCH_NO_SAMPLER"):      # diagnostic runs only: no clocks line
+            return
         try:
             import threading
 
