@@ -447,6 +447,7 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
 #pragma unroll
   for (int k = 0; k < MP; k++) av[k] = k < m ? A.a0[k] : 0.0;
   double y_next = A.y[s];  // observations are fetched one univariate step ahead of their use
+  int code_next = A.g.code[0];  // and so is the step's code: the branch on it heads every step's dependence chain
   if (tid < MP) {
     kb[tid] = fetch_k(0);
     zb[tid] = fetch_z(0);
@@ -457,11 +458,15 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
     for (int j = 0; j < p; j++) {
       const long long index = (long long)t * p + j;
       const double y_now = y_next;
-      if (index + 1 < Np) y_next = A.y[(index + 1) * S + s];
+      const int code_now = code_next;
+      if (index + 1 < Np) {
+        y_next = A.y[(index + 1) * S + s];
+        code_next = A.g.code[index + 1];
+      }
       const double k_n = fetch_k(index + 1), z_n = fetch_z(index + 1);  // in flight during this observation
       const double* kc = kb + cur * MP;
       const double* zc = zb + cur * MP;
-      if ((A.g.code[index] & 255) != 0) {
+      if ((code_now & 255) != 0) {
         // which entries of the row of Z are non-zero: the same for every draw, so whole groups of four states are
         // branched over (Z of a structural or SARIMA model has a handful of ones)
         const unsigned zm = __ballot_sync(0xffffffffu, tid < MP && zc[tid < MP ? tid : 0] != 0.0);
@@ -499,6 +504,8 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
   for (int k = 0; k < MP; k++) rr[k] = 0.0;
   for (int k = 0; k < m; k++) r1[k] = 0.0;
   double v_next = A.v[(Np - 1) * S + s];  // innovations, one univariate step ahead (steps without one read junk)
+  code_next = A.g.code[Np - 1];
+  double f1_next = A.g.F1[Np - 1];
   __syncwarp();
   if (tid < MP) {
     kb[tid] = fetch_k(Np - 1);
@@ -509,14 +516,18 @@ __global__ void __launch_bounds__(kRegBT) fs_draw_reg_kernel(const FsArgs A) {
   for (int t = N - 1; t >= 0; t--) {
     for (int j = p - 1; j >= 0; j--) {
       const long long index = (long long)t * p + j;
-      const double v_now = v_next;
-      if (index > 0) v_next = A.v[(index - 1) * S + s];
+      const double v_now = v_next, f1_now = f1_next;
+      const int c = code_next & 255;
+      if (index > 0) {
+        v_next = A.v[(index - 1) * S + s];
+        code_next = A.g.code[index - 1];
+        f1_next = A.g.F1[index - 1];
+      }
       const double k_n = fetch_k(index - 1), z_n = fetch_z(index - 1);
       const double* kc = kb + cur * MP;
       const double* zc = zb + cur * MP;
-      const int c = A.g.code[index] & 255;
       if (c != 0) {
-        const double c1 = A.g.F1[index] * v_now;
+        const double c1 = f1_now * v_now;
         double d0 = 0.0;
 #pragma unroll
         for (int k = 0; k < MP; k++) d0 = fma(kc[k], rr[k], d0);
