@@ -329,6 +329,9 @@ def test_batch_blk_kernel_time_varying_z(seasonal):
         want = cport.LogLikC(yb, np.isnan(yb), *smb.args())
         assert abs(got[b] - want) <= 1e-8 * max(1, abs(want)), (b, got[b], want)
         assert abs(gen[b] - want) <= 1e-8 * max(1, abs(want)), (b, gen[b], want)
+        if b < 3:                                     # the single-series entry point takes the same kernel
+            one = api.LogLikC(yb, np.isnan(yb), *smb.args())
+            assert api.last_kernel().startswith("loglik_blk_kernel<") and abs(one - got[b]) <= 1e-13 * abs(one)
 
 
 def test_batch_blk_kernel_bivariate_dense_blocks():
