@@ -392,10 +392,12 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, NB > 8 ?
         load_z(t);
         innovation();
         const double tm0 = fma(t01, m1, t00 * m0), tm1 = fma(t11, m1, t10 * m0);  // (T M)_I
-        if (own) xch[buf][I][g] = make_double2(tm0, tm1);
+        if constexpr (L > 1) {  // one lane per evaluation owns every block: nothing to exchange
+          if (own) xch[buf][I][g] = make_double2(tm0, tm1);
+        }
         F_star = group_sum(fma(zi1, m1, zi0 * m0));
         za = group_sum(fma(zi1, a1, zi0 * a0));
-        __syncwarp();
+        if constexpr (L > 1) __syncwarp();
 #pragma unroll
         for (int J = 0; J < NB; J++) time_block(J, P[J][0], P[J][1], P[J][2], P[J][3], true);
         const double ta0 = fma(t01, a1, t00 * a0), ta1 = fma(t11, a1, t10 * a0);
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, NB > 8 ?
         const double g0 = tm0 * F1, g1 = tm1 * F1;
 #pragma unroll
         for (int J = 0; J < NB; J++) {
-          const double2 mJ = xch[buf][J][g];  // (T M)_J
+          const double2 mJ = L > 1 ? xch[buf][J][g] : make_double2(tm0, tm1);  // (T M)_J
           P[J][0] = fma(-g0, mJ.x, P[J][0]);
           P[J][1] = fma(-g0, mJ.y, P[J][1]);
           P[J][2] = fma(-g1, mJ.x, P[J][2]);
