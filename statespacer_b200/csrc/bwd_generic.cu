@@ -9,6 +9,8 @@
 // on purpose: N_1 = N_1 L0 only (no r_1 / N_2 update) in the
 // F_inf < eps <= F_star branch (:464-468); N_2 uses the already updated N_1 (:483-487); eta_var uses
 // the Q slice left over from the forward loop (:548); the regime test is index < initialisation_steps.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mm_dmma.cuh"
 
@@ -335,6 +337,16 @@ int launch_bwd_generic(const DModel& md, const ssgpu_kalman_out* kout, const Kal
   int nt = ((md.m * md.m + 31) / 32) * 32;
   if (nt > 512) nt = 512;
   if (nt < 32) nt = 32;
+  if (B > 1) {  // batched: more, smaller CTAs per SM (cheaper barriers, the batch supplies the parallelism)
+    nt = ((md.m * md.m / 4 + 31) / 32) * 32;
+    if (nt > 256) nt = 256;
+    if (nt < 64) nt = 64;
+    static const int forced = [] {
+      const char* e = getenv("SSGPU_GENERIC_NT");
+      return e ? atoi(e) : 0;
+    }();
+    if (forced > 0) nt = forced;
+  }
   if (B > 1) {
     SS_CUDA(cudaFuncSetAttribute(bwd_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bwd_generic_kernel<true><<<(unsigned)B, nt, smem, st>>>(A);
