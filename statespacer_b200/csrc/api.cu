@@ -708,8 +708,19 @@ int ssgpu_loglik_grad_batch(const double* y, long long B, const ssgpu_model* mod
     SS_TRY(theta_setup(model, false, B, V, k, thd.as<double>(), q_index, p_star_index, h, 1, W, st));
     SS_TRY(W.out.alloc((size_t)B * V * sizeof(double), st));
     const long long Bc = ((B + nch - 1) / nch + 31) / 32 * 32;
-    std::vector<cudaEvent_t> ev(nch, nullptr);
-    cudaEvent_t ready = nullptr;
+    // events die with the frame on every return path; the copy stream is drained first so that no queued copy
+    // still refers to them (or to the caller's y)
+    struct Events {
+      std::vector<cudaEvent_t> v;
+      cudaStream_t drain;
+      ~Events() {
+        cudaStreamSynchronize(drain);
+        for (cudaEvent_t e : v)
+          if (e) cudaEventDestroy(e);
+      }
+    } evs{std::vector<cudaEvent_t>(nch + 1, nullptr), cs};
+    cudaEvent_t* ev = evs.v.data();
+    cudaEvent_t& ready = evs.v[nch];
     SS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     SS_CUDA(cudaEventRecord(ready, st));  // yd exists on the compute stream from here on
     SS_CUDA(cudaStreamWaitEvent(cs, ready, 0));
@@ -736,10 +747,6 @@ int ssgpu_loglik_grad_batch(const double* y, long long B, const ssgpu_model* mod
       rc = dispatch_batch(mdc, yd.as<double>() + Np * b0, bn, V, kernel, outc, st, &hs);
       if (rc == SSGPU_OK) rc = launch_fd_gradient(outc, bn, k, h, ll + b0, gr + b0 * k, st);
     }
-    cudaStreamSynchronize(cs);
-    for (cudaEvent_t e : ev)
-      if (e) cudaEventDestroy(e);
-    cudaEventDestroy(ready);
     SS_TRY(rc);
   }
   SS_CUDA(cudaMemcpyAsync(loglik, ll, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
