@@ -36,7 +36,10 @@ __device__ void sandwich_L0(double* X, const double* k0, const double* z, double
     u[i] = acc;
   }
   __syncthreads();
-  for (int q = tid; q < m * m; q += NT) X[q] -= u[q % m] * z[q / m];
+  for (int q = tid; q < m * m; q += NT) {
+    const int c = div_small(q, m);
+    X[q] -= u[q - c * m] * z[c];
+  }
   __syncthreads();
   for (int j = tid; j < m; j += NT) {
     double acc = 0.0;
@@ -44,7 +47,10 @@ __device__ void sandwich_L0(double* X, const double* k0, const double* z, double
     w[j] = acc;
   }
   __syncthreads();
-  for (int q = tid; q < m * m; q += NT) X[q] -= z[q % m] * w[q / m];
+  for (int q = tid; q < m * m; q += NT) {
+    const int c = div_small(q, m);
+    X[q] -= z[q - c * m] * w[c];
+  }
   __syncthreads();
 }
 
@@ -151,7 +157,10 @@ __global__ void __launch_bounds__(512) bwd_generic_kernel(const BwdArgs A_) {
         __syncthreads();
         for (int q = tid; q < m; q += NT) rv[q] = zr[q] * F1 * vv + (rv[q] - rk * zr[q]);
         sandwich_L0(Nn, k0, zr, u, w, m, tid, NT);
-        for (int q = tid; q < mm; q += NT) Nn[q] = zr[q % m] * zr[q / m] * F1 + Nn[q];
+        for (int q = tid; q < mm; q += NT) {
+          const int c = div_small(q, m);
+          Nn[q] = zr[q - c * m] * zr[c] * F1 + Nn[q];
+        }
         if (diffuse) {  // N_1 = N_1 L0   (:468)
           for (int i = tid; i < m; i += NT) {
             double acc = 0.0;
@@ -235,9 +244,18 @@ __global__ void __launch_bounds__(512) bwd_generic_kernel(const BwdArgs A_) {
       }
       if (K.a_smooth) K.a_smooth[t + (long long)N * jj] = K.a_pred[t + (long long)N * jj] + acc;
     }
-    if (K.V) {
+    if (K.V && !diffuse_t) {
+      // V = P* - P* (N P*): P*_pred of this time point staged once (the scalar loops below read it m-fold from
+      // global memory), two DMMA products -- the same k-ascending fma chains, bit for bit
+      for (int q = tid; q < mm; q += NT) tB[q] = Pst[q];
+      __syncthreads();
+      mm_dmma<false, false>(tA, Nn, tB, nullptr, m, tid, NT);
+      __syncthreads();
+      mm_dmma<false, false, true>(K.V + (long long)t * mm, tB, tA, tB, m, tid, NT);
+      __syncthreads();
+    } else if (K.V) {
       for (int q = tid; q < mm; q += NT) {
-        const int kk = q % m, jj = q / m;
+        const int jj = div_small(q, m), kk = q - jj * m;
         double a1 = 0.0, a2 = 0.0;
         for (int l = 0; l < m; l++) {
           a1 = fma(Nn[kk + l * m], Pst[l + jj * m], a1);
@@ -252,7 +270,7 @@ __global__ void __launch_bounds__(512) bwd_generic_kernel(const BwdArgs A_) {
       }
       __syncthreads();
       for (int q = tid; q < mm; q += NT) {
-        const int i = q % m, jj = q / m;
+        const int jj = div_small(q, m), i = q - jj * m;
         double acc = 0.0;
         for (int kk = 0; kk < m; kk++) {
           acc = fma(Pst[i + kk * m], tA[kk + jj * m], acc);

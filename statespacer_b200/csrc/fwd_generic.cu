@@ -58,32 +58,26 @@ __device__ __forceinline__ void mm_nt(double* C, const double* A, const double* 
   mm_dmma<false, true>(C, A, Bm, add, m, tid, NT);
 }
 
-// the argument block as the kernel sees it: a private, pointer-shifted copy for the batched KalmanC (SHIFT), the
-// parameter bank itself otherwise (a mutable copy costs the single-series call about 10 %)
-template <bool SHIFT>
-struct ArgsView;
-template <>
-struct ArgsView<false> {
-  const FwdArgs& A;
-  __device__ ArgsView(const FwdArgs& a, long long) : A(a) {}
-};
-template <>
-struct ArgsView<true> {
-  FwdArgs A;
-  __device__ ArgsView(const FwdArgs& a, long long b) : A(a) {
-    kalman_shift(A.k, A.s, b, A.md.N, A.md.p, A.md.m, A.md.r, A.md.Q.tv() || A.md.R.tv());
-  }
-};
-
 template <int MODE, bool SHIFT = false>
 __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A_) {
   constexpr bool KALMAN = MODE == MODE_KALMAN, GAINS = MODE == MODE_GAINS;
   extern __shared__ double sm[];
   const long long e = blockIdx.x;
   const long long b = e % A_.B, v = e / A_.B;
-  // batched KalmanC: this CTA's series owns the b-th block of every output and scratch array
-  const ArgsView<SHIFT> view(A_, b);
-  const FwdArgs& A = view.A;
+  // batched KalmanC (SHIFT): this CTA's series owns the b-th block of every output and scratch array.  The shifted
+  // argument block lives in shared memory: as a thread-private copy ptxas rematerialised every pointer (base +
+  // b * block) at each use, 10 % of the instructions of an issue-bound kernel.  Single-series calls read the
+  // parameter bank itself.
+  __shared__ __align__(16) unsigned char shifted_args[SHIFT ? sizeof(FwdArgs) : 16];
+  if constexpr (SHIFT) {
+    if (threadIdx.x == 0) {
+      FwdArgs* S = reinterpret_cast<FwdArgs*>(shifted_args);
+      *S = A_;
+      kalman_shift(S->k, S->s, b, A_.md.N, A_.md.p, A_.md.m, A_.md.r, A_.md.Q.tv() || A_.md.R.tv());
+    }
+    __syncthreads();
+  }
+  const FwdArgs& A = SHIFT ? *reinterpret_cast<const FwdArgs*>(shifted_args) : A_;
   const DModel& md = A.md;
   const int m = md.m, p = md.p, r = md.r, N = md.N;
   const int tid = threadIdx.x, NT = blockDim.x;
@@ -256,17 +250,23 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A_) {
         else
           code = 1;
       }
+      // the likelihood term is thread 0's alone (it owns loglik and the stores): the logarithm is ~40 instructions
+      // that every other warp of an issue-bound kernel can skip
       if (code == 1) {
         F1 = 1.0 / F_star;
         vv = yv - za;
-        ll = kLogConst - (log(F_star) + vv * vv * F1) / 2;
-        loglik += ll;
+        if (tid == 0) {
+          ll = kLogConst - (log(F_star) + vv * vv * F1) / 2;
+          loglik += ll;
+        }
       } else if (code == 2) {
         F1 = 1.0 / F_inf;
         F2 = -(F1 * F1) * F_star;
         vv = yv - za;
-        ll = kLogConst - log(F_inf) / 2;
-        loglik += ll;
+        if (tid == 0) {
+          ll = kLogConst - log(F_inf) / 2;
+          loglik += ll;
+        }
       }
       if ((KALMAN || GAINS) && tid == 0) {
         if (KALMAN && A.k.loglik) A.k.loglik[index] = ll;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(512) fwd_generic_kernel(const FwdArgs A_) {
       __syncthreads();
       if (code == 0) continue;  // block-uniform
       for (int q = tid; q < mm; q += NT) {
-        const int i = q % m, c = q / m;
+        const int c = div_small(q, m), i = q - c * m;
         if (code == 1) {
           Ps[q] = Ps[q] - Ms[i] * k0v[c];
         } else {

@@ -16,14 +16,20 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
                : "d"(a), "d"(b));
 }
 
+// q / d for 0 <= q < 4096, 1 <= d <= 64 without the ~20-instruction integer division (the generic kernels are
+// issue-bound: profiles/README.md): (q + 0.5) / d stays 1 / 128 away from every integer, far more than the error of
+// the approximate single-precision quotient
+__device__ __forceinline__ int div_small(int q, int d) { return __float2int_rz(__fdividef((float)q + 0.5f, (float)d)); }
+
 // TA / TB: use the transpose of A / B.  All threads of the CTA must call (NT a multiple of 32); no barrier inside.
-template <bool TA, bool TB>
+// SUB: C = add - A B (add required) instead of C = A B + add.
+template <bool TA, bool TB, bool SUB = false>
 __device__ __forceinline__ void mm_dmma(double* C, const double* A, const double* Bm, const double* add, int m, int tid,
                                         int NT) {
   const int warp = tid >> 5, nw = NT >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
   const int TT = (m + 7) >> 3;
   for (int tile = warp; tile < TT * TT; tile += nw) {
-    const int rt = tile % TT, nt = tile / TT;
+    const int nt = div_small(tile, TT), rt = tile - nt * TT;
     const int i = 8 * rt + g, n = 8 * nt + g;
     double c0 = 0.0, c1 = 0.0;
     for (int k0 = 0; k0 < m; k0 += 4) {
@@ -35,8 +41,13 @@ __device__ __forceinline__ void mm_dmma(double* C, const double* A, const double
     }
     const int j0 = 8 * nt + 2 * q;
     if (i < m) {
-      if (j0 < m) C[i + j0 * m] = add ? c0 + add[i + j0 * m] : c0;
-      if (j0 + 1 < m) C[i + (j0 + 1) * m] = add ? c1 + add[i + (j0 + 1) * m] : c1;
+      if constexpr (SUB) {
+        if (j0 < m) C[i + j0 * m] = add[i + j0 * m] - c0;
+        if (j0 + 1 < m) C[i + (j0 + 1) * m] = add[i + (j0 + 1) * m] - c1;
+      } else {
+        if (j0 < m) C[i + j0 * m] = add ? c0 + add[i + j0 * m] : c0;
+        if (j0 + 1 < m) C[i + (j0 + 1) * m] = add ? c1 + add[i + (j0 + 1) * m] : c1;
+      }
     }
   }
 }
