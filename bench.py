@@ -14,11 +14,13 @@ metric   series*timesteps / s, FP64, whole job, inputs resident in HBM (CUDA eve
          gradient out, the 9 variance sets per series built on the device
 e2e      the same through the host-pointer C ABI (ssgpu_loglik_grad_batch): pinned host y / theta are copied in
          and loglik + gradient copied out inside the timed region
-roofline dominant kernel loglik_mma_kernel against the FP64 peak measured in this run by ssgpu_fp64_peak
-         (MEASURED_PEAKS.json carries no FP64 figure): algorithmic flops of SURVEY.md 8d (frac) and the flops
-         the tile-sparse kernel issues (executed_frac)
+roofline dominant kernel (loglik_blk_kernel for this model) against the FP64 peak measured in this run by
+         ssgpu_fp64_peak (MEASURED_PEAKS.json carries no FP64 figure): achieved / frac count the FP64 operations the
+         structure-exploiting kernel issues (the kernel reports flop_per_step in its name); the dense algorithm's
+         count of SURVEY.md 8d is reported beside it (dense_algorithm_*)
 cpu_baseline  the reference's own LogLikC.cpp (oracle/_ref, compiled unmodified) on all host cores over a
-         bounded sample of the same workload; --impl reference runs only that and prints its own line.
+         bounded sample of the same workload (value_1core: one thread, port_value: the allocation-free C
+         restatement on all cores); --impl reference runs only the all-core leg and prints its own line.
 
 --workload sim runs BASELINE.json config 4 instead (simulation smoother draws, see the section below).
 """
@@ -467,7 +469,9 @@ def run_gpu(args):
             smc, yy, Pfull, Qfull = cpu_sample(n_series)
             v_ref, dt, o_ref = time_cpu(mod, smc, yy, Pfull, Qfull, cores)
             v_port, _, o_port = time_cpu(cport, smc, yy, Pfull, Qfull, cores)
-            line["cpu_baseline"] = {"value": v_ref, "unit": UNIT, "cores": cores, "kind": kind,
+            n1 = 64 * V                                      # the 1-core rate next to the all-core one
+            v_one, _, _ = time_cpu(mod, smc, yy[:n1], Pfull[:n1], Qfull[:n1], 1)
+            line["cpu_baseline"] = {"value": v_ref, "unit": UNIT, "cores": cores, "kind": kind, "value_1core": v_one,
                                     "sample": f"{n_series} series x {V} parameter vectors x {T_STEPS} timesteps "
                                               f"({dt:.1f} s)",
                                     "port_value": v_port,
