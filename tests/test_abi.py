@@ -161,6 +161,44 @@ def test_plan_blocks_host_helper():
     assert api.plan_blocks(np.eye(3), np.eye(3))["n_blocks"] == 2 and api.plan_blocks(np.eye(3), np.eye(3))["lanes"] == 2
 
 
+def test_plan_blocks_random_models():
+    """Property check of the host planner over random models: a T made of 1x1 and 2x2 blocks, states shuffled, R = I
+    and a diagonal Q must decompose into closed blocks covering every state once; one extra coupling that chains three
+    states must be refused."""
+    from statespacer_b200 import api
+    rng = np.random.default_rng(11)
+    for trial in range(60):
+        sizes = rng.integers(1, 3, size=rng.integers(1, 12)).tolist()
+        m = int(sum(sizes))
+        T = np.zeros((m, m))
+        o = 0
+        for sz in sizes:
+            blk = rng.normal(size=(sz, sz))
+            if sz == 2 and rng.random() < 0.3:
+                blk[1, 0] = 0.0                             # level/slope-like: coupled one way only
+            T[o:o + sz, o:o + sz] = blk
+            o += sz
+        shuffle = rng.permutation(m)
+        Ts = T[np.ix_(shuffle, shuffle)]
+        pl = api.plan_blocks(Ts, np.eye(m))
+        assert pl is not None, (trial, sizes)
+        perm = pl["perm"].reshape(-1, 2)
+        real = [k for k in perm.ravel().tolist() if k >= 0]
+        assert sorted(real) == list(range(m)), (trial, perm)
+        assert pl["n_blocks"] <= 16 and pl["lanes"] in (1, 2, 4, 8, 16) and pl["lanes"] >= min(pl["n_blocks"], 16) / 2
+        for a, b in perm:
+            inside = [k for k in (a, b) if k >= 0]
+            others = [k for k in range(m) if k not in inside]
+            assert not Ts[np.ix_(inside, others)].any() and not Ts[np.ix_(others, inside)].any(), (trial, perm)
+        pairs = [i for i, sz in enumerate(sizes) if sz == 2]
+        if pairs and m >= 3:                                # chain a third state onto a coupled pair
+            o = int(sum(sizes[:pairs[0]]))
+            third = (o + 2) % m
+            Tc = T.copy()
+            Tc[o, third] = 0.5
+            assert api.plan_blocks(Tc[np.ix_(shuffle, shuffle)], np.eye(m)) is None, (trial, sizes)
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the reference's own LogLikC on the host cores) runs without a GPU and prints one
     JSON line with the contract's keys."""
