@@ -199,6 +199,19 @@ def test_plan_blocks_random_models():
             assert api.plan_blocks(Tc[np.ix_(shuffle, shuffle)], np.eye(m)) is None, (trial, sizes)
 
 
+def test_div_small_margin():
+    """mm_dmma.cuh div_small(q, d) = trunc(__fdividef(q + 0.5f, d)) replaces q / d in the generic kernels for
+    0 <= q < 4096, 1 <= d <= 64.  __fdividef is within 2 ulp of the quotient; the truncation is exact as long as
+    (q + 0.5) / d stays further from every integer than that error -- checked here over the whole range with a
+    64-ulp allowance."""
+    q = np.arange(4096, dtype=np.float64)[:, None]
+    d = np.arange(1, 65, dtype=np.float64)[None, :]
+    x = (q + 0.5) / d
+    err = 64 * np.spacing(x.astype(np.float32)).astype(np.float64)
+    assert np.all(np.floor(x - err) == np.floor(q / d)) and np.all(np.floor(x + err) == np.floor(q / d))
+    assert np.all(np.trunc(((q + 0.5).astype(np.float32) / d.astype(np.float32))) == np.floor(q / d))
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the reference's own LogLikC on the host cores) runs without a GPU and prints one
     JSON line with the contract's keys."""
