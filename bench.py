@@ -877,7 +877,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--series", type=int, default=B_PER_GPU, help="series per GPU")
     ap.add_argument("--missing", type=float, default=0.0, help="fraction of NaN observations (variant B: 0.02)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "blk", "mma", "mma_dense", "cols", "wsm", "generic"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "blk", "blk_lanes", "mma", "mma_dense", "cols", "wsm", "generic"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="loglik", choices=["loglik", "sim", "kalman"],
                     help="loglik: config 5 (headline, default); sim: config 4 simulation smoother draws; "

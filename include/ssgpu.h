@@ -161,7 +161,11 @@ typedef struct ssgpu_model {
                                    coefficients), R Q R' inside the blocks; at most 8 blocks (m <= 16) with p <= 8, or
                                    up to 16 blocks (m <= 32) with p = 1 and a diagonal R Q R'; Z may be time-varying
                                    when p = 1 (explanatory variables); SSGPU_E_ARG if not eligible.  AUTO tries it
-                                   first */
+                                   first.  With 5 to 8 blocks, p = 1 and a time-invariant Z (BASELINE.json config 5)
+                                   the lanes run the exact diffuse phase only and a second kernel, one thread per
+                                   evaluation, runs the regular phase */
+#define SSGPU_KERNEL_BLK_LANES 7 /* the same model class on the lane kernel alone (second implementation the tests
+                                   cross-check; A/B runs) */
 
 /* host pointers everywhere (y, the matrices' data, out); copies in, runs, copies out, synchronises */
 int ssgpu_loglik_batch(const double* y, long long B, int V, const ssgpu_model* model, int kernel,

@@ -16,11 +16,11 @@ import ctypes as C
 import numpy as np
 
 from . import native
-from .native import (KERNEL_AUTO, KERNEL_BLK, KERNEL_COLS, KERNEL_GENERIC, KERNEL_MMA, KERNEL_MMA_DENSE,  # noqa: F401
+from .native import (KERNEL_AUTO, KERNEL_BLK, KERNEL_BLK_LANES, KERNEL_COLS, KERNEL_GENERIC, KERNEL_MMA, KERNEL_MMA_DENSE,  # noqa: F401
                      KERNEL_WSM)
 
 _KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "cols": KERNEL_COLS, "mma": KERNEL_MMA,
-            "mma_dense": KERNEL_MMA_DENSE, "wsm": KERNEL_WSM, "blk": KERNEL_BLK}
+            "mma_dense": KERNEL_MMA_DENSE, "wsm": KERNEL_WSM, "blk": KERNEL_BLK, "blk_lanes": KERNEL_BLK_LANES}
 
 
 def _f(x):

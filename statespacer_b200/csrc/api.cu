@@ -216,6 +216,7 @@ static int dispatch_batch(const DModel& md, const double* y_dev, long long B, in
   // block-diagonal T with blocks of at most 2 x 2 (structural models): the block-row kernel issues 4 m^2 instead of
   // 4 m^3 multiply-adds per time update
   if (kernel == SSGPU_KERNEL_BLK) return launch_loglik_blk(md, y_dev, B, V, out_dev, st, hs);
+  if (kernel == SSGPU_KERNEL_BLK_LANES) return launch_loglik_blk(md, y_dev, B, V, out_dev, st, hs, nullptr, true);
   if (kernel == SSGPU_KERNEL_AUTO && auto_blk_enabled() && blk_eligible(md, &why)) {
     bool ran = true;
     SS_TRY(launch_loglik_blk(md, y_dev, B, V, out_dev, st, hs, &ran));

@@ -280,7 +280,16 @@ int blk_lanes(int nb);
 int blk_flops_per_step(int nb, int p);
 // applicable != null: a model whose T / R Q R' does not decompose is not an error; *applicable = false, nothing runs
 int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
-                      const HostShared* hs = nullptr, bool* applicable = nullptr);
+                      const HostShared* hs = nullptr, bool* applicable = nullptr, bool lanes_only = false);
+
+// Thread-per-evaluation kernel for the regular phase of the same model class (loglik_thr.cu); the lane kernel
+// above runs the diffuse phase first and hands the state over (blk_handoff.cuh)
+bool thr_supported(int nb, int p, bool ztv);
+size_t thr_handoff_bytes(int nb, bool qoff, long long E);
+int thr_flops_per_step(int nb, bool qoff);
+int thr_smem_blocks_host(int nb);
+int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* y, long long B, long long E,
+                      long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st);
 
 // Column-per-thread register kernel (loglik_cols.cu)
 bool cols_eligible(const DModel& md, std::string* why);

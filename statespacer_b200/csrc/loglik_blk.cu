@@ -1,48 +1,61 @@
 // Batched loglikelihood for models whose transition matrix is block diagonal with blocks of at most 2 x 2:
-// structure-exploiting DFMA kernel, L lanes per evaluation, the covariance distributed by block rows.
+// structure-exploiting DFMA kernel, L lanes per evaluation, the SYMMETRIC covariance distributed over the lanes in
+// circulant block ownership.
 //
 // Restates the recursion of src/LogLikC.cpp:68-214 (univariate treatment, exact diffuse initialisation,
 // NaN = missing) for models whose Z, T, R are shared by the batch, T and R time-invariant, Z time-invariant or -- with
-// p = 1 -- one row per time point (explanatory variables) (per-evaluation a, P_inf, P_star, Q allowed) and whose T, after re-ordering the states, is  blkdiag(T_0, ..., T_{NB-1})  with
-// 1 x 1 or 2 x 2 blocks, NB <= 8 (m <= 16; NB <= 16, m <= 32 when p = 1), and whose R Q R' has no entry outside those blocks.  That is every
-// structural model statespacer builds from residuals, level, slope, trigonometric seasonals, cycles and
-// regression coefficients (R/GetSysMat.R:1388-1426, R/Components-Unobserved.R:143-159,491-519): T couples a state
-// with at most one partner.  BASELINE.json config 5 (m = 14) is 7 such blocks.
+// p = 1 -- one row per time point (explanatory variables) (per-evaluation a, P_inf, P_star, Q allowed) and whose T,
+// after re-ordering the states, is  blkdiag(T_0, ..., T_{NB-1})  with 1 x 1 or 2 x 2 blocks, NB <= 8 (m <= 16;
+// NB <= 16, m <= 32 when p = 1), and whose R Q R' has no entry outside those blocks.  That is every structural model
+// statespacer builds from residuals, level, slope, trigonometric seasonals, cycles and regression coefficients
+// (R/GetSysMat.R:1388-1426, R/Components-Unobserved.R:143-159,491-519): T couples a state with at most one partner.
+// BASELINE.json config 5 (m = 14) is 7 such blocks.
 //
 // Why this shape.  With P cut into 2 x 2 blocks P_IJ the time update  P <- T P T' + R Q R'  (src/LogLikC.cpp:202)
 // is  P_IJ <- T_I P_IJ T_J' (+ (RQR')_II)  block by block: 16 multiply-adds per block, 4 m^2 per step instead of the
-// 4 m^3 of the dense product (the FP64 tensor kernel of loglik_mma.cu multiplies whole 8 x 8 tiles: 7,168 flop per
-// step at m = 14 where this kernel issues about 1,800), and it needs NO data from any other block.  Lane I of a
-// group of L lanes therefore owns block row I (NB blocks, 8 NB registers) and runs the whole time update from its
-// own registers; T_J and z are the same for every evaluation and come from the kernel parameters (constant bank).
-// Only the measurement update couples the block rows:  M = P z  is computed row-wise in place, all-gathered through
-// a few hundred bytes of shared memory (one 16-byte store and NB broadcast 16-byte loads per lane), F = z'M and z'a
-// are xor-butterfly sums over the group (bit-identical in every lane), and  P_IJ -= (M_I / F) M_J'  is local again.
-// 32 / L evaluations share a warp; the exact diffuse phase (about d of the N steps) runs in a select-based
-// loop that all groups of the warp execute until the last of them has left it, with P_inf parked in shared memory
-// so that the registers are sized for the regular phase.
+// 4 m^3 of the dense product, and it needs NO data from any other block.  P is symmetric, so only the blocks on and
+// above the diagonal are kept: lane I of a group of L lanes owns  P_{I,(I+k) mod NB},  k = 0 .. H = NB / 2  -- the
+// diagonal block and the next H blocks of block row I, wrapping around.  Every unordered pair {I, J} has exactly one
+// owner (NB even: the pairs at distance NB / 2 would have two; the lanes I >= NB / 2 keep theirs at zero).  That is
+// H + 1 blocks (4 of the 7 x 7 at config 5: 32 registers instead of 56) and 16 (H + 1) multiply-adds of time update
+// per lane, all from the lane's own registers; T_I, T_{I+k} and z_{I+k} are per-lane constants in registers.
+// Only the measurement update couples the lanes:  M = P z  needs, for row I, the own blocks times z_{I+k} (local) and
+// the transposed blocks of the H lanes behind times THEIR z (H shuffled 2-vectors);  F = z'M = sum_I z_I'(2 m_I - u_I)
+// (m_I the local part of M_I, u_I = P_II z_I) is formed from local data, so its xor-butterfly over the group starts
+// before the exchange of M;  P_IJ -= (M_I / F) M_J'  needs M_{I+k} from the H lanes ahead (H shuffled 2-vectors).
+// 32 / L evaluations share a warp; the exact diffuse phase (about d of the N steps) runs in a select-based loop that
+// all groups of the warp execute until the last of them has left it, with P_inf parked in shared memory so that the
+// registers are sized for the regular phase.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
+#include "blk_handoff.cuh"
 #include "common.cuh"
 
 namespace ssgpu {
 
-#ifndef SSGPU_BLK_MINB
-#define SSGPU_BLK_MINB 2  // resident CTAs per SM the register budget is sized for (2: 255 registers, 3: 168, 4: 128)
-#endif
 constexpr int kBlkThreads = 128;   // CTA of the register-constant instantiations (NB <= 8)
-constexpr int kBlkThreadsCS = 64;  // NB > 8: P_inf of a CTA (16 NB doubles per thread) has to fit the static 48 KB
+constexpr int kBlkThreadsCS = 64;  // NB > 8
 constexpr int kBlkMaxNB = 16;  // blocks: 1..8 with T_J and z in registers, 9..16 (p = 1) with both in shared memory
 constexpr int kBlkMaxP = 8;
 
+// resident CTAs per SM the register budget is sized for: 7 and 8 blocks (5 own blocks at most) 3 x 128 threads at
+// 168 registers, fewer blocks 4 x 128 at 128 registers, more than 8 blocks 4 x 64 at 255
+#ifndef SSGPU_BLK_MINB
+#define SSGPU_BLK_MINB 3
+#endif
+constexpr int blk_minb(int nb) { return nb > 8 ? 4 : nb > 4 ? SSGPU_BLK_MINB : 4; }
+
 struct BlkArgs {
   DModel md;
-  const double* y;  // [(t*p + j) * B + b]
-  long long B;
-  long long E;  // B * V
-  double* out;
+  const double* y;  // [(t*p + j) * ldy + b]
+  long long B;      // series of this launch
+  long long E;      // B * V
+  long long ldy;    // series of the whole batch (a launch may cover a range of them)
+  double* out;      // [v * ldy + b]
+  double* hd;       // hand-over to the thread kernel (blk_handoff.cuh), null = run to the end
+  int* hi;
   signed char perm[2 * kBlkMaxNB];     // internal position 2I+e holds state perm[2I+e] of the caller, -1 = padding
   double Tb[kBlkMaxNB][4];             // T_J[row][col] at [2*row + col], internal order
   double z[kBlkMaxP][2 * kBlkMaxNB];   // row j of Z, internal order
@@ -59,63 +72,88 @@ __device__ __forceinline__ double blk_rcp(double x) {
   return fma(r, e, r);
 }
 
+__device__ __forceinline__ double2 blk_shfl(double2 x, int src) {
+  return make_double2(__shfl_sync(0xffffffffu, x.x, src), __shfl_sync(0xffffffffu, x.y, src));
+}
+
 // QOFF: the diagonal blocks of R Q R' have off-diagonal entries (correlated disturbances of a multivariate model)
 // ZTV: Z changes with t (explanatory variables, R/Components-Regressors.R:60-78); p = 1 only
-template <int L, int NB, bool P1, bool QOFF, bool ZTV = false>
-__global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, NB > 8 ? 4 : SSGPU_BLK_MINB)
-    loglik_blk_kernel(const BlkArgs A) {
+// HO: leave after the diffuse phase and hand the state over (A.hd, A.hi) to the thread kernel
+template <int L, int NB, bool P1, bool QOFF, bool ZTV = false, bool HO = false>
+__global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb(NB)) loglik_blk_kernel(const BlkArgs A) {
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int G = 32 / L;  // evaluations per warp
-  // NB > 8 (17 <= m <= 32, p = 1): the block row alone is 8 NB <= 128 registers, so T_J and z live in shared memory
-  // (8-byte broadcast loads) and the R Q R' addends are selected per step instead of hoisted
+  constexpr int G = 32 / L;       // evaluations per warp
+  constexpr int H = NB / 2;       // own blocks: (I, I + k mod NB), k = 0 .. H
+  constexpr int K = H + 1;
+  constexpr bool EVEN = NB > 1 && NB % 2 == 0;  // the pairs at distance H have two candidate owners: lanes I < H keep them
+  // NB > 8 (17 <= m <= 32, p = 1): T_J comes from shared memory (per-lane 8-byte loads) instead of 4 H registers pairs
   constexpr bool CS = NB > 8;
+  constexpr bool ZREG = P1 && !ZTV && !CS;  // z_{I+k} in registers for the whole kernel
   constexpr int BT = CS ? kBlkThreadsCS : kBlkThreads;
   static_assert(!CS || P1, "more than 8 blocks: p = 1 only");
+  static_assert(NB <= L, "one lane per block row");
   const DModel& md = A.md;
   const int N = md.N, p = P1 ? 1 : md.p, M = md.m, r = md.r;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int I = lane % L, g = lane / L;
-  __shared__ double tb_s[CS ? NB * 4 : 1], zs_s[CS ? NB * 2 : 1];
-  if constexpr (CS) {  // before any warp leaves: filled by the whole CTA
+  __shared__ double tb_s[CS ? NB * 4 : 1];
+  __shared__ double2 zs_s[ZREG || ZTV ? 1 : kBlkMaxP * NB];  // rows of Z, internal order, as block pairs
+  if constexpr (CS) {
     for (int e = threadIdx.x; e < NB * 4; e += BT) tb_s[e] = (&A.Tb[0][0])[e];
-    for (int e = threadIdx.x; e < NB * 2; e += BT) zs_s[e] = A.z[0][e];
-    __syncthreads();
   }
+  if constexpr (!(ZREG || ZTV)) {
+    for (int e = threadIdx.x; e < p * NB; e += BT) {
+      const int j = e / NB, J = e % NB;
+      zs_s[e] = make_double2(A.z[j][2 * J], A.z[j][2 * J + 1]);
+    }
+  }
+  if constexpr (CS || !(ZREG || ZTV)) __syncthreads();  // before any warp leaves
   // evaluations are numbered series-major (w = b*V + v) so that the V parameter vectors of a series run side by
   // side and share its y through L1/L2; results keep the public order e = v*B + b
   const long long w0 = ((long long)blockIdx.x * (BT / 32) + warp) * G;
   if (w0 >= A.E) return;  // whole warp
-  // every lane stays alive (shuffles, __syncwarp): groups beyond the last evaluation shadow it and do not store
+  // every lane stays alive (shuffles): groups beyond the last evaluation shadow it and do not store
   const bool live = w0 + g < A.E;
   const long long w_id = live ? w0 + g : A.E - 1;
   const long long V = A.E / A.B, b = w_id / V, v = w_id % V;
-  const long long e_id = v * A.B + b;
+  const long long e_id = v * A.ldy + b;
   const bool own = I < NB;  // L > NB: the surplus lanes carry zero blocks
+  // block column of the k-th own block; the lane it is shared with; the lane that shares ITS k-th block with this one
+  int Jk[K], srcF[K], srcB[K];
+  bool keep[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const int jf = I + k < NB ? I + k : I + k - NB, jb = I - k >= 0 ? I - k : I - k + NB;
+    Jk[k] = own ? jf : 0;
+    srcF[k] = own ? lane - I + jf : lane;
+    srcB[k] = own ? lane - I + jb : lane;
+    keep[k] = own && !(EVEN && k == H && I >= H);
+    // opaque to the optimiser: otherwise ptxas recomputes the wrapped lane numbers inside the hot loop
+    asm volatile("" : "+r"(srcF[k]), "+r"(srcB[k]));
+  }
 
-  __shared__ double2 xch_s[BT / 32][2][NB][G];
-  __shared__ double pinf_s[NB * 4][BT];
-  double2(*xch)[NB][G] = xch_s[warp];
+  __shared__ double pinf_s[K * 4][BT];
   double(*pinf)[BT] = pinf_s;
   const int tx = threadIdx.x;
 
-  // ---- own block row of P_star, P_inf, own T block, own part of a and z, own diagonal block of R Q R' ------------
+  // ---- own blocks of P_star, P_inf, own T blocks, own part of a, own diagonal block of R Q R' ---------------------
   const int i0 = own ? (int)A.perm[2 * I] : -1, i1 = own ? (int)A.perm[2 * I + 1] : -1;
   auto elem = [&](const double* blk, int diag, int i, int k) { return (i >= 0 && k >= 0) ? mat_get(blk, diag, M, i, k) : 0.0; };
-  double P[NB][4];
+  double P[K][4];
   {
     const double* Ps = md.P_star.block(b, v, 0);
     const double* Pi = md.P_inf.block(b, v, 0);
 #pragma unroll
-    for (int J = 0; J < NB; J++) {
-      const int k0 = A.perm[2 * J], k1 = A.perm[2 * J + 1];
-      P[J][0] = elem(Ps, md.P_star.diag, i0, k0);
-      P[J][1] = elem(Ps, md.P_star.diag, i0, k1);
-      P[J][2] = elem(Ps, md.P_star.diag, i1, k0);
-      P[J][3] = elem(Ps, md.P_star.diag, i1, k1);
-      pinf[J * 4 + 0][tx] = elem(Pi, md.P_inf.diag, i0, k0);
-      pinf[J * 4 + 1][tx] = elem(Pi, md.P_inf.diag, i0, k1);
-      pinf[J * 4 + 2][tx] = elem(Pi, md.P_inf.diag, i1, k0);
-      pinf[J * 4 + 3][tx] = elem(Pi, md.P_inf.diag, i1, k1);
+    for (int k = 0; k < K; k++) {
+      const int k0 = keep[k] ? (int)A.perm[2 * Jk[k]] : -1, k1 = keep[k] ? (int)A.perm[2 * Jk[k] + 1] : -1;
+      P[k][0] = elem(Ps, md.P_star.diag, i0, k0);
+      P[k][1] = elem(Ps, md.P_star.diag, i0, k1);
+      P[k][2] = elem(Ps, md.P_star.diag, i1, k0);
+      P[k][3] = elem(Ps, md.P_star.diag, i1, k1);
+      pinf[k * 4 + 0][tx] = elem(Pi, md.P_inf.diag, i0, k0);
+      pinf[k * 4 + 1][tx] = elem(Pi, md.P_inf.diag, i0, k1);
+      pinf[k * 4 + 2][tx] = elem(Pi, md.P_inf.diag, i1, k0);
+      pinf[k * 4 + 3][tx] = elem(Pi, md.P_inf.diag, i1, k1);
     }
   }
   double a0, a1;
@@ -124,7 +162,18 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, NB > 8 ?
     a0 = i0 >= 0 ? ab[i0] : 0.0;
     a1 = i1 >= 0 ? ab[i1] : 0.0;
   }
-  const double t00 = A.Tb[I][0], t01 = A.Tb[I][1], t10 = A.Tb[I][2], t11 = A.Tb[I][3];  // zero beyond NB
+  const int Iz = own ? I : 0;
+  const double t00 = own ? A.Tb[Iz][0] : 0.0, t01 = own ? A.Tb[Iz][1] : 0.0, t10 = own ? A.Tb[Iz][2] : 0.0,
+               t11 = own ? A.Tb[Iz][3] : 0.0;
+  // T_{I+k}, k = 1 .. H: per-lane constants in vector registers for the whole kernel (NB <= 8)
+  double TJ[CS ? 1 : K][4];
+  if constexpr (!CS) {
+#pragma unroll
+    for (int k = 1; k < K; k++) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) TJ[k][e] = A.Tb[Jk[k]][e];
+    }
+  }
   // (R Q R')[i][c] for the own diagonal block (src/LogLikC.cpp:202, hoisted: Q and R are time-invariant here; the
   // host has checked that R Q R' has no entry outside the diagonal blocks)
   double q0, q1, q2, q3;
@@ -149,8 +198,8 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, NB > 8 ?
       return acc;
     };
     q0 = rqr(i0, i0);
-    q1 = rqr(i0, i1);
-    q2 = rqr(i1, i0);
+    q1 = QOFF ? rqr(i0, i1) : 0.0;
+    q2 = QOFF ? rqr(i1, i0) : 0.0;
     q3 = rqr(i1, i1);
   }
 
@@ -176,74 +225,117 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, NB > 8 ?
     prod = __hiloint2double(hi - (ex << 20), __double2loint(prod));
   };
 
-  // T_J (and z when p = 1) are the same for every evaluation.  They are kept in VECTOR registers for the whole
-  // kernel (4 NB + 2 NB doubles; the kernel is sized for 2 CTAs per SM, 255 registers), loaded once through an index
-  // that ptxas cannot prove warp-uniform (`lz` is always 0 but derives from the per-lane evaluation number).
-  // What was measured on the way (config 5, one B200):
-  //   constants in shared memory, 16-byte broadcast loads: an LDS.128 costs ~3 LSU wavefronts even when every lane
-  //     reads the same address; LSU pipe 77 % busy, FP64 pipe 58 %, 167 ms per sweep;
-  //   constants through the uniform datapath (LDCU -> uniform-register operand): left loop-invariant, ptxas hoists
-  //     all 42 of a step, runs out of uniform registers and spills them (300 extra instructions per step); made
-  //     loop-variant, it funnels every constant through ONE uniform register pair, LDCU / 2 DFMA / LDCU ..., each
-  //     load's latency exposed (IDC 56 % busy, `short_scoreboard` the top stall), FP64 pipe 60 %, 162 ms.
-  const int lz = (int)(w_id >> 62);
-  double TJ[CS ? 1 : NB][4], ZJ[CS ? 1 : NB][2];
-  if constexpr (!CS) {
-    const double* tbp = &A.Tb[0][0] + lz;
-    const double* zp = &A.z[0][0] + lz;
+  // z_{I+k} of observation j at time t: registers (p = 1, time-invariant), the row of the step in device memory
+  // (time-varying, L1-resident: the same few hundred bytes for every evaluation) or shared memory (p > 1, NB > 8)
+  double2 ZK[K];
+  if constexpr (ZREG) {
 #pragma unroll
-    for (int J = 0; J < NB; J++) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) TJ[J][k] = tbp[J * 4 + k];
-      ZJ[J][0] = P1 ? zp[2 * J] : 0.0;
-      ZJ[J][1] = P1 ? zp[2 * J + 1] : 0.0;
-    }
+    for (int k = 0; k < K; k++) ZK[k] = own ? make_double2(A.z[0][2 * Jk[k]], A.z[0][2 * Jk[k] + 1]) : make_double2(0.0, 0.0);
   }
-  // P_IJ <- T_I P_IJ T_J' (+ the own diagonal block of R Q R' when J == I); X[r][c] = sum_k Y[r][k] T_J[c][k].
-  // The selected addends (dg ? q : 0) are loop-invariant and hoisted by the compiler: 2 NB doubles when R Q R' is
-  // diagonal (QOFF = false).
-  int zv = 0;  // NB > 8: always 0, but refreshed from a per-lane counter every step so that the selected R Q R' addends
-               // are not hoisted into 4 NB registers
-  auto time_block = [&](int J, double& p0, double& p1, double& p2, double& p3, bool with_q) {
+  auto load_z = [&](int t, int j) {
+    if constexpr (ZTV) {
+      const double2* zr = reinterpret_cast<const double2*>(A.zt + (size_t)t * (2 * kBlkMaxNB));
+#pragma unroll
+      for (int k = 0; k < K; k++) ZK[k] = own ? zr[Jk[k]] : make_double2(0.0, 0.0);
+    } else if constexpr (!ZREG) {
+#pragma unroll
+      for (int k = 0; k < K; k++) ZK[k] = own ? zs_s[j * NB + Jk[k]] : make_double2(0.0, 0.0);
+    }
+  };
+
+  // local part of M = X z for a symmetric X held like P (X[k][e] = element e of the k-th own block):
+  //   ml = sum_k X_{I,I+k} z_{I+k}  (stays in row I),   u0 = X_II z_I,   c[k] = X_{I,I+k}' z_I  (belongs to row I+k)
+  auto products = [&](const double (&X)[K][4], double2& ml, double2& u0, double2 (&c)[K]) {
+    const double2 zi = ZK[0];
+    u0.x = fma(X[0][1], zi.y, X[0][0] * zi.x);
+    u0.y = fma(X[0][3], zi.y, X[0][2] * zi.x);
+    ml = u0;
+#pragma unroll
+    for (int k = 1; k < K; k++) {
+      const double2 zk = ZK[k];
+      ml.x = fma(X[k][1], zk.y, fma(X[k][0], zk.x, ml.x));
+      ml.y = fma(X[k][3], zk.y, fma(X[k][2], zk.x, ml.y));
+      c[k].x = fma(X[k][2], zi.y, X[k][0] * zi.x);
+      c[k].y = fma(X[k][3], zi.y, X[k][1] * zi.x);
+    }
+  };
+  // M_I = ml + the parts the H lanes behind hold for row I
+  auto complete = [&](double2 ml, const double2 (&c)[K]) {
+#pragma unroll
+    for (int k = 1; k < K; k++) {
+      const double2 ci = blk_shfl(c[k], srcB[k]);
+      ml.x += ci.x;
+      ml.y += ci.y;
+    }
+    return ml;
+  };
+  // x_{I+k}, k = 0 .. H, of a 2-vector per block row (zero where the k-th block is not kept)
+  auto ahead = [&](double2 x, double2 (&xk)[K]) {
+    xk[0] = x;
+#pragma unroll
+    for (int k = 1; k < K; k++) {
+      const double2 f = blk_shfl(x, srcF[k]);
+      xk[k] = (EVEN && k == H && !keep[k]) ? make_double2(0.0, 0.0) : f;
+    }
+  };
+
+  // P_{I,I+k} <- T_I P_{I,I+k} T_{I+k}' (+ the own diagonal block of R Q R' when k == 0); X[r][c] = sum_l Y[r][l] T_J[c][l]
+  auto time_block = [&](int k, double& p0, double& p1, double& p2, double& p3, bool with_q) {
     const double y00 = fma(t01, p2, t00 * p0), y01 = fma(t01, p3, t00 * p1);
     const double y10 = fma(t11, p2, t10 * p0), y11 = fma(t11, p3, t10 * p1);
-    const bool dg = with_q && J == (CS ? I + zv : I);
-    const double tj0 = CS ? tb_s[J * 4 + 0] : TJ[CS ? 0 : J][0], tj1 = CS ? tb_s[J * 4 + 1] : TJ[CS ? 0 : J][1];
-    const double tj2 = CS ? tb_s[J * 4 + 2] : TJ[CS ? 0 : J][2], tj3 = CS ? tb_s[J * 4 + 3] : TJ[CS ? 0 : J][3];
-    p0 = fma(y01, tj1, fma(y00, tj0, dg ? q0 : 0.0));
-    p1 = fma(y01, tj3, fma(y00, tj2, (QOFF && dg) ? q1 : 0.0));
-    p2 = fma(y11, tj1, fma(y10, tj0, (QOFF && dg) ? q2 : 0.0));
-    p3 = fma(y11, tj3, fma(y10, tj2, dg ? q3 : 0.0));
+    if (k == 0) {
+      if (with_q) {
+        p0 = fma(y01, t01, fma(y00, t00, q0));
+        p1 = QOFF ? fma(y01, t11, fma(y00, t10, q1)) : fma(y01, t11, y00 * t10);
+        p2 = QOFF ? fma(y11, t01, fma(y10, t00, q2)) : fma(y11, t01, y10 * t00);
+        p3 = fma(y11, t11, fma(y10, t10, q3));
+      } else {
+        p0 = fma(y01, t01, y00 * t00);
+        p1 = fma(y01, t11, y00 * t10);
+        p2 = fma(y11, t01, y10 * t00);
+        p3 = fma(y11, t11, y10 * t10);
+      }
+    } else {
+      double tj0, tj1, tj2, tj3;
+      if constexpr (CS) {
+        const double* tp = tb_s + Jk[k] * 4;
+        tj0 = tp[0], tj1 = tp[1], tj2 = tp[2], tj3 = tp[3];
+      } else {
+        tj0 = TJ[CS ? 0 : k][0], tj1 = TJ[CS ? 0 : k][1], tj2 = TJ[CS ? 0 : k][2], tj3 = TJ[CS ? 0 : k][3];
+      }
+      p0 = fma(y01, tj1, y00 * tj0);
+      p1 = fma(y01, tj3, y00 * tj2);
+      p2 = fma(y11, tj1, y10 * tj0);
+      p3 = fma(y11, tj3, y10 * tj2);
+    }
   };
 
   const long long Np = (long long)N * p;
-  int buf = 0;
   int t = 0;
   {
     // ---- exact diffuse phase (src/LogLikC.cpp:98-159), select-based: the groups of a warp may leave it at
     // different time points (missing observations), so every group runs this loop until the last one is done ----
     bool small = true;
 #pragma unroll
-    for (int e = 0; e < NB * 4; e++) small = small && (fabs(pinf[e][tx]) < kEps);
+    for (int e = 0; e < K * 4; e++) small = small && (fabs(pinf[e][tx]) < kEps);
     bool init = !group_all(small);  // :49
     while (t < N && __any_sync(FULL, init)) {
       for (int j = 0; j < p; j++) {
-        const double yv = A.y[((long long)t * p + j) * A.B + b];
+        const double yv = A.y[((long long)t * p + j) * A.ldy + b];
         const bool obs = !isnan(yv);  // :88-90
-        const double* zrow = ZTV ? A.zt + (size_t)t * (2 * kBlkMaxNB) : &A.z[j][0];
-        const double zi0 = zrow[2 * I], zi1 = zrow[2 * I + 1];
-        double ms0 = 0.0, ms1 = 0.0, mi0 = 0.0, mi1 = 0.0;
+        load_z(t, j);
+        const double2 zi = ZK[0];
+        double2 ml, u0, cs[K], ci[K];
+        products(P, ml, u0, cs);
+        const double2 ms = complete(ml, cs);
+        double Pi[K][4];
 #pragma unroll
-        for (int J = 0; J < NB; J++) {
-          const double z0 = zrow[2 * J], z1 = zrow[2 * J + 1];
-          ms0 = fma(P[J][1], z1, fma(P[J][0], z0, ms0));
-          ms1 = fma(P[J][3], z1, fma(P[J][2], z0, ms1));
-          mi0 = fma(pinf[J * 4 + 1][tx], z1, fma(pinf[J * 4 + 0][tx], z0, mi0));
-          mi1 = fma(pinf[J * 4 + 3][tx], z1, fma(pinf[J * 4 + 2][tx], z0, mi1));
-        }
-        const double F_star = group_sum(fma(zi1, ms1, zi0 * ms0));
-        const double F_inf = group_sum(fma(zi1, mi1, zi0 * mi0));
-        const double za = group_sum(fma(zi1, a1, zi0 * a0));
+        for (int e = 0; e < K * 4; e++) Pi[e / 4][e % 4] = pinf[e][tx];
+        products(Pi, ml, u0, ci);
+        const double2 mi = complete(ml, ci);
+        const double F_star = group_sum(fma(zi.y, ms.y, zi.x * ms.x));
+        const double F_inf = group_sum(fma(zi.y, mi.y, zi.x * mi.x));
+        const double za = group_sum(fma(zi.y, a1, zi.x * a0));
         // the three outcomes of :109-153 and the regular step of :162-195 (a group whose P_inf has vanished)
         const bool dif = init && obs && !(F_inf < kEps);
         const bool star = obs && !dif && !(F_star < kEps);
@@ -258,31 +350,30 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, NB > 8 ?
         sumq = fma(vv * vv, F1s, sumq);
         // K0 = M_inf F1 (diffuse) or M_star F1 (star); K1 = M_star F1 + M_inf F2 (diffuse only)
         // P*_IJ -= M*_I K0_J' + M_inf,I K1_J';  P_inf,IJ -= M_inf,I K0_J' (diffuse only)
-        if (own) xch[buf][I][g] = make_double2(ms0, ms1);
-        if (own) xch[buf ^ 1][I][g] = make_double2(mi0, mi1);
-        __syncwarp();
+        double2 msk[K], mik[K];
+        ahead(ms, msk);
+        ahead(mi, mik);
 #pragma unroll
-        for (int J = 0; J < NB; J++) {
-          const double2 sJ = xch[buf][J][g], iJ = xch[buf ^ 1][J][g];
+        for (int k = 0; k < K; k++) {
+          const double2 sJ = msk[k], iJ = mik[k];
           const double k00 = fma(F1s, sJ.x, F1i * iJ.x), k01 = fma(F1s, sJ.y, F1i * iJ.y);    // K0_J
           const double k10 = fma(F2, iJ.x, F1i * sJ.x), k11 = fma(F2, iJ.y, F1i * sJ.y);      // K1_J
-          P[J][0] = fma(-mi0, k10, fma(-ms0, k00, P[J][0]));
-          P[J][1] = fma(-mi0, k11, fma(-ms0, k01, P[J][1]));
-          P[J][2] = fma(-mi1, k10, fma(-ms1, k00, P[J][2]));
-          P[J][3] = fma(-mi1, k11, fma(-ms1, k01, P[J][3]));
+          P[k][0] = fma(-mi.x, k10, fma(-ms.x, k00, P[k][0]));
+          P[k][1] = fma(-mi.x, k11, fma(-ms.x, k01, P[k][1]));
+          P[k][2] = fma(-mi.y, k10, fma(-ms.y, k00, P[k][2]));
+          P[k][3] = fma(-mi.y, k11, fma(-ms.y, k01, P[k][3]));
           const double c0 = F1i * iJ.x, c1 = F1i * iJ.y;
-          pinf[J * 4 + 0][tx] = fma(-mi0, c0, pinf[J * 4 + 0][tx]);
-          pinf[J * 4 + 1][tx] = fma(-mi0, c1, pinf[J * 4 + 1][tx]);
-          pinf[J * 4 + 2][tx] = fma(-mi1, c0, pinf[J * 4 + 2][tx]);
-          pinf[J * 4 + 3][tx] = fma(-mi1, c1, pinf[J * 4 + 3][tx]);
+          pinf[k * 4 + 0][tx] = fma(-mi.x, c0, pinf[k * 4 + 0][tx]);
+          pinf[k * 4 + 1][tx] = fma(-mi.x, c1, pinf[k * 4 + 1][tx]);
+          pinf[k * 4 + 2][tx] = fma(-mi.y, c0, pinf[k * 4 + 2][tx]);
+          pinf[k * 4 + 3][tx] = fma(-mi.y, c1, pinf[k * 4 + 3][tx]);
         }
-        __syncwarp();  // both buffers are rewritten by the next observation
-        a0 = fma(fma(F1s, ms0, F1i * mi0), vv, a0);
-        a1 = fma(fma(F1s, ms1, F1i * mi1), vv, a1);
+        a0 = fma(fma(F1s, ms.x, F1i * mi.x), vv, a0);
+        a1 = fma(fma(F1s, ms.y, F1i * mi.y), vv, a1);
         if (j < p - 1) {  // :157-159 (only after a diffuse update)
           small = true;
 #pragma unroll
-          for (int e = 0; e < NB * 4; e++) small = small && (fabs(pinf[e][tx]) < kEps);
+          for (int e = 0; e < K * 4; e++) small = small && (fabs(pinf[e][tx]) < kEps);
           const bool gone = group_all(small);
           if (dif && gone) init = false;
         }
@@ -290,14 +381,14 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, NB > 8 ?
       if (t < N - 1) {  // :200-207
         small = true;
 #pragma unroll
-        for (int J = 0; J < NB; J++) {
-          time_block(J, P[J][0], P[J][1], P[J][2], P[J][3], true);
-          double i0v = pinf[J * 4 + 0][tx], i1v = pinf[J * 4 + 1][tx], i2v = pinf[J * 4 + 2][tx], i3v = pinf[J * 4 + 3][tx];
-          time_block(J, i0v, i1v, i2v, i3v, false);
-          pinf[J * 4 + 0][tx] = i0v;
-          pinf[J * 4 + 1][tx] = i1v;
-          pinf[J * 4 + 2][tx] = i2v;
-          pinf[J * 4 + 3][tx] = i3v;
+        for (int k = 0; k < K; k++) {
+          time_block(k, P[k][0], P[k][1], P[k][2], P[k][3], true);
+          double i0v = pinf[k * 4 + 0][tx], i1v = pinf[k * 4 + 1][tx], i2v = pinf[k * 4 + 2][tx], i3v = pinf[k * 4 + 3][tx];
+          time_block(k, i0v, i1v, i2v, i3v, false);
+          pinf[k * 4 + 0][tx] = i0v;
+          pinf[k * 4 + 1][tx] = i1v;
+          pinf[k * 4 + 2][tx] = i2v;
+          pinf[k * 4 + 3][tx] = i3v;
           small = small && (fabs(i0v) < kEps) && (fabs(i1v) < kEps) && (fabs(i2v) < kEps) && (fabs(i3v) < kEps);
         }
         const double na0 = fma(t01, a1, t00 * a0), na1 = fma(t11, a1, t10 * a0);
@@ -308,6 +399,48 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, NB > 8 ?
       }
       t++;
     }
+  }
+
+  if constexpr (HO) {
+    // ---- hand-over: every group of the warp is through the diffuse phase (or at t == N).  The state at the start of
+    // time point t goes to the record of blk_handoff.cuh; an evaluation that is already complete (t == N) writes its
+    // result below as usual and the thread kernel skips it.
+    constexpr BlkHandoff HL(NB, QOFF);
+    if (live && own) {
+      double* const hd = A.hd + w_id;
+      const long long E = A.E;
+      hd[(HL.a() + 2 * I) * E] = a0;
+      hd[(HL.a() + 2 * I + 1) * E] = a1;
+      hd[(HL.q() + HL.qw * I) * E] = q0;
+      if constexpr (QOFF) hd[(HL.q() + HL.qw * I + 1) * E] = q1;
+      hd[(HL.q() + HL.qw * I + HL.qw - 1) * E] = q3;
+      hd[(HL.d() + 3 * I) * E] = P[0][0];
+      hd[(HL.d() + 3 * I + 1) * E] = P[0][1];
+      hd[(HL.d() + 3 * I + 2) * E] = P[0][3];
+#pragma unroll
+      for (int k = 1; k < K; k++) {
+        if (!keep[k]) continue;
+        const int J = Jk[k];
+        const bool up = J > I;  // held as (I, J): as is; as (I, J) with J < I: the transpose of block (J, I)
+        const int oi = up ? HL.off_index(I, J) : HL.off_index(J, I);
+        double* const ho = hd + (long long)(HL.o() + 4 * oi) * E;
+        ho[0] = P[k][0];
+        ho[E] = up ? P[k][1] : P[k][2];
+        ho[2 * E] = up ? P[k][2] : P[k][1];
+        ho[3 * E] = P[k][3];
+      }
+      if (I == 0) {
+        hd[HL.s() * E] = prod;
+        hd[(HL.s() + 1) * E] = sumq;
+        int* const hi = A.hi + w_id;
+        hi[0] = t;
+        hi[E] = esum;
+        hi[2 * E] = n_terms;
+        hi[3 * E] = non_init;
+        hi[4 * E] = F_eq0;
+      }
+    }
+    if (t < N) return;
   }
 
   // ---- regular phase: the hot loop (src/LogLikC.cpp:162-207), branch-free ------------------------------------
@@ -325,145 +458,86 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, NB > 8 ?
     F_eq0 += obs && !upd;
     sumq = fma(vv * vv, F1, sumq);
   };
+  // F = z'Pz = sum_I z_I'(2 ml_I - u0_I) and z'a over the group: needs no data of another lane
+  auto innovation_sums = [&](double2 ml, double2 u0, double& F_star, double& za) {
+    const double2 zi = ZK[0];
+    const double w0 = fma(2.0, ml.x, -u0.x), w1 = fma(2.0, ml.y, -u0.y);
+    F_star = group_sum(fma(zi.y, w1, zi.x * w0));
+    za = group_sum(fma(zi.y, a1, zi.x * a0));
+  };
   if constexpr (P1) {
     // p = 1: the time update does not wait for 1/F.  With M = P z, k = M / F:
     //     T (P - k M') T' + RQR'  =  (T P T' + RQR')  -  (T M)(T M)' / F,        T (a + k v) = T a + (T M) v / F,
-    // so the 16 NB multiply-adds of T P T' are issued while F = z'M travels through the butterfly and the
-    // reciprocal; lane I publishes T_I M_I instead of M_I and the rank-1 correction comes last.  (At 2 warps per
-    // sub-partition the FP64 pipe otherwise idles through that chain: 148 ms per sweep of config 5 before, see
-    // profiles/README.md.)
+    // so the multiply-adds of T P T' are issued while F travels through the butterfly and the reciprocal;
+    // (T M)_{I+k} is what the lanes ahead hand over and the rank-1 correction comes last.
     if (t < N) {
-      double zi0 = A.z[0][2 * I], zi1 = A.z[0][2 * I + 1];
-      // time-varying Z: the row of step t in internal order, the same for every evaluation (16-byte broadcast loads)
-      const double2* zcur = nullptr;  // NB > 8 with time-varying Z: the row of the step, read where it is used
-      auto load_z = [&](int tt) {
-        if constexpr (ZTV) {
-          const double2* zr = reinterpret_cast<const double2*>(A.zt + (size_t)tt * (2 * kBlkMaxNB));
-#pragma unroll
-          if constexpr (!CS) {
-#pragma unroll
-            for (int J = 0; J < NB; J++) {
-              const double2 zz = zr[J];
-              ZJ[J][0] = zz.x;
-              ZJ[J][1] = zz.y;
-            }
-          }
-          zcur = zr;
-          const double2 zo = zr[I];
-          zi0 = zo.x;
-          zi1 = zo.y;
-        }
-      };
-      // observations are fetched two steps ahead of their use (one step, 600 cycles at 2 warps per sub-partition,
-      // does not always cover a DRAM miss: 2.4 % of the stall samples sat on this load)
-      double ynext = A.y[(long long)t * A.B + b];
-      double ynext2 = t + 1 < N ? A.y[(long long)(t + 1) * A.B + b] : 0.0;
-      // M_I = sum_J P_IJ z_J (two chains per row), F = z'M and z'a over the group
-      double m0, m1, F_star, za;
-      auto innovation = [&]() {
-        double m0a = 0.0, m0b = 0.0, m1a = 0.0, m1b = 0.0;
-#pragma unroll
-        for (int J = 0; J < NB; J++) {
-          double z0, z1;
-          if constexpr (!CS) {
-            z0 = ZJ[J][0];
-            z1 = ZJ[J][1];
-          } else if constexpr (ZTV) {
-            const double2 zz = zcur[J];
-            z0 = zz.x;
-            z1 = zz.y;
-          } else {
-            z0 = zs_s[2 * J];
-            z1 = zs_s[2 * J + 1];
-          }
-          m0a = fma(P[J][0], z0, m0a);
-          m0b = fma(P[J][1], z1, m0b);
-          m1a = fma(P[J][2], z0, m1a);
-          m1b = fma(P[J][3], z1, m1b);
-        }
-        m0 = m0a + m0b;
-        m1 = m1a + m1b;
-      };
-      for (; t < N - 1; t++) {  // one straight-line block per step: no branch between the butterfly and the products
+      // observations are fetched two steps ahead of their use
+      double ynext = A.y[(long long)t * A.ldy + b];
+      double ynext2 = t + 1 < N ? A.y[(long long)(t + 1) * A.ldy + b] : 0.0;
+      double2 ml, u0, c[K];
+      double F_star, za;
+      for (; t < N - 1; t++) {  // one straight-line block per step
         const double yv = ynext;
         ynext = ynext2;
-        if (t + 2 < N) ynext2 = A.y[(long long)(t + 2) * A.B + b];
-        if constexpr (CS) zv = n_terms >> 30;
-        load_z(t);
-        innovation();
-        const double tm0 = fma(t01, m1, t00 * m0), tm1 = fma(t11, m1, t10 * m0);  // (T M)_I
-        if constexpr (L > 1) {  // one lane per evaluation owns every block: nothing to exchange
-          if (own) xch[buf][I][g] = make_double2(tm0, tm1);
-        }
-        F_star = group_sum(fma(zi1, m1, zi0 * m0));
-        za = group_sum(fma(zi1, a1, zi0 * a0));
-        if constexpr (L > 1) __syncwarp();
+        if (t + 2 < N) ynext2 = A.y[(long long)(t + 2) * A.ldy + b];
+        load_z(t, 0);
+        products(P, ml, u0, c);
+        innovation_sums(ml, u0, F_star, za);
+        const double2 m = complete(ml, c);
+        const double2 tm = make_double2(fma(t01, m.y, t00 * m.x), fma(t11, m.y, t10 * m.x));  // (T M)_I
+        double2 tmk[K];
+        ahead(tm, tmk);
 #pragma unroll
-        for (int J = 0; J < NB; J++) time_block(J, P[J][0], P[J][1], P[J][2], P[J][3], true);
+        for (int k = 0; k < K; k++) time_block(k, P[k][0], P[k][1], P[k][2], P[k][3], true);
         const double ta0 = fma(t01, a1, t00 * a0), ta1 = fma(t11, a1, t10 * a0);
         observe(yv, F_star, za);
-        const double g0 = tm0 * F1, g1 = tm1 * F1;
+        const double g0 = tm.x * F1, g1 = tm.y * F1;
 #pragma unroll
-        for (int J = 0; J < NB; J++) {
-          const double2 mJ = L > 1 ? xch[buf][J][g] : make_double2(tm0, tm1);  // (T M)_J
-          P[J][0] = fma(-g0, mJ.x, P[J][0]);
-          P[J][1] = fma(-g0, mJ.y, P[J][1]);
-          P[J][2] = fma(-g1, mJ.x, P[J][2]);
-          P[J][3] = fma(-g1, mJ.y, P[J][3]);
+        for (int k = 0; k < K; k++) {
+          P[k][0] = fma(-g0, tmk[k].x, P[k][0]);
+          P[k][1] = fma(-g0, tmk[k].y, P[k][1]);
+          P[k][2] = fma(-g1, tmk[k].x, P[k][2]);
+          P[k][3] = fma(-g1, tmk[k].y, P[k][3]);
         }
-        buf ^= 1;
         a0 = fma(g0, vv, ta0);
         a1 = fma(g1, vv, ta1);
       }
       // the last observation (:200 -- P and a are not needed afterwards)
-      load_z(N - 1);
-      innovation();
-      F_star = group_sum(fma(zi1, m1, zi0 * m0));
-      za = group_sum(fma(zi1, a1, zi0 * a0));
+      load_z(N - 1, 0);
+      products(P, ml, u0, c);
+      innovation_sums(ml, u0, F_star, za);
       observe(ynext, F_star, za);
     }
   } else if (t < N) {
     long long idx = (long long)t * p;
-    double ynext = A.y[idx * A.B + b];  // observations are fetched one univariate step ahead of their use
+    double ynext = A.y[idx * A.ldy + b];  // observations are fetched one univariate step ahead of their use
     for (; t < N; t++) {
-      const int zo = t >> 30;  // z from the parameter bank; always 0 (N < 2^30), but loop-variant: no hoisting
 #pragma unroll 1
       for (int j = 0; j < p; j++, idx++) {
         const double yv = ynext;
-        if (idx + 1 < Np) ynext = A.y[(idx + 1) * A.B + b];
-        const double* zp = &A.z[0][0] + zo + j * (2 * kBlkMaxNB);
-        const double zi0 = A.z[j][2 * I], zi1 = A.z[j][2 * I + 1];  // own part: a per-lane address, kept apart from zo
-        double m0a = 0.0, m0b = 0.0, m1a = 0.0, m1b = 0.0;
-#pragma unroll
-        for (int J = 0; J < NB; J++) {
-          const double z0 = zp[2 * J], z1 = zp[2 * J + 1];
-          m0a = fma(P[J][0], z0, m0a);
-          m0b = fma(P[J][1], z1, m0b);
-          m1a = fma(P[J][2], z0, m1a);
-          m1b = fma(P[J][3], z1, m1b);
-        }
-        const double m0 = m0a + m0b, m1 = m1a + m1b;
-        if (own) xch[buf][I][g] = make_double2(m0, m1);
-        const double F_star = group_sum(fma(zi1, m1, zi0 * m0));
-        const double za = group_sum(fma(zi1, a1, zi0 * a0));
-        __syncwarp();
+        if (idx + 1 < Np) ynext = A.y[(idx + 1) * A.ldy + b];
+        load_z(t, j);
+        double2 ml, u0, c[K], mk[K];
+        double F_star, za;
+        products(P, ml, u0, c);
+        innovation_sums(ml, u0, F_star, za);
+        const double2 m = complete(ml, c);
+        ahead(m, mk);
         observe(yv, F_star, za);
-        const double k0 = m0 * F1, k1 = m1 * F1;
+        const double k0 = m.x * F1, k1 = m.y * F1;
 #pragma unroll
-        for (int J = 0; J < NB; J++) {
-          const double2 mJ = xch[buf][J][g];
-          P[J][0] = fma(-k0, mJ.x, P[J][0]);
-          P[J][1] = fma(-k0, mJ.y, P[J][1]);
-          P[J][2] = fma(-k1, mJ.x, P[J][2]);
-          P[J][3] = fma(-k1, mJ.y, P[J][3]);
+        for (int k = 0; k < K; k++) {
+          P[k][0] = fma(-k0, mk[k].x, P[k][0]);
+          P[k][1] = fma(-k0, mk[k].y, P[k][1]);
+          P[k][2] = fma(-k1, mk[k].x, P[k][2]);
+          P[k][3] = fma(-k1, mk[k].y, P[k][3]);
         }
-        buf ^= 1;
         a0 = fma(k0, vv, a0);
         a1 = fma(k1, vv, a1);
       }
       if (t < N - 1) {  // :200-204 (after the last observation P and a are not needed any more)
 #pragma unroll
-        for (int J = 0; J < NB; J++) time_block(J, P[J][0], P[J][1], P[J][2], P[J][3], true);
+        for (int k = 0; k < K; k++) time_block(k, P[k][0], P[k][1], P[k][2], P[k][3], true);
         const double na0 = fma(t01, a1, t00 * a0), na1 = fma(t11, a1, t10 * a0);
         a0 = na0;
         a1 = na1;
@@ -568,7 +642,7 @@ bool blk_eligible(const DModel& md, std::string* why) {
   return true;
 }
 
-template <int L, int NB, bool P1, bool QOFF, bool ZTV = false>
+template <int L, int NB, bool P1, bool QOFF, bool ZTV = false, bool HO = false>
 static void launch_blk_one(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
   // SSGPU_BLK_PAD_SMEM: unused dynamic shared memory per CTA -- an occupancy knob for experiments (e.g. 120000 leaves
   // one CTA per SM: the step time of a warp that has a sub-partition to itself)
@@ -577,8 +651,8 @@ static void launch_blk_one(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
     return e ? atoi(e) : 0;
   }();
   if (pad > 0)
-    cudaFuncSetAttribute(loglik_blk_kernel<L, NB, P1, QOFF, ZTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-  loglik_blk_kernel<L, NB, P1, QOFF, ZTV><<<blocks, NB > 8 ? kBlkThreadsCS : kBlkThreads, pad, st>>>(A);
+    cudaFuncSetAttribute(loglik_blk_kernel<L, NB, P1, QOFF, ZTV, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+  loglik_blk_kernel<L, NB, P1, QOFF, ZTV, HO><<<blocks, NB > 8 ? kBlkThreadsCS : kBlkThreads, pad, st>>>(A);
 }
 
 template <int L, int NB>
@@ -589,6 +663,13 @@ static void launch_blk_nb(const BlkArgs& A, bool q_offdiag, unsigned blocks, cud
     else
       launch_blk_one<L, NB, true, false>(A, blocks, st);
     return;
+  } else if (A.hd) {  // diffuse prologue of the thread kernel (5 to 8 blocks, p = 1, time-invariant Z)
+    if constexpr (NB >= 5) {
+      if (q_offdiag)
+        launch_blk_one<L, NB, true, true, false, true>(A, blocks, st);
+      else
+        launch_blk_one<L, NB, true, false, false, true>(A, blocks, st);
+    }
   } else if (A.md.p == 1 && A.zt) {
     if (q_offdiag)
       launch_blk_one<L, NB, true, true, true>(A, blocks, st);
@@ -610,18 +691,28 @@ static void launch_blk_nb(const BlkArgs& A, bool q_offdiag, unsigned blocks, cud
 int blk_lanes(int nb) { return nb > 8 ? 16 : nb > 4 ? 8 : nb > 2 ? 4 : nb > 1 ? 2 : 1; }
 
 // FP64 operations (fma = 2) the kernel issues per series and time step in the regular phase, all L lanes counted
+// (H = nb / 2 blocks beside the diagonal one per lane; the counts are those of the SASS of the hot loop)
 int blk_flops_per_step(int nb, int p) {
-  const int L = blk_lanes(nb);
+  const int L = blk_lanes(nb), H = nb / 2, K = H + 1;
   int lg = 0;
   while ((1 << lg) < L) lg++;
-  const int fma_obs = 4 * nb + 2 + 4 + 4 * nb + 2 + 1, mul_obs = 2 + 2 + 3, add_obs = 2 + 2 * lg;
-  const int fma_t = 12 * nb + 2, mul_t = 4 * nb + 2;
-  const int tm = p == 1 ? 2 * 2 + 2 : 0;  // p = 1: (T M)_I
-  return L * (p * (2 * fma_obs + mul_obs + add_obs) + 2 * fma_t + mul_t + tm);
+  // per observation: local products (u0, ml, c), F partial 2 ml - u0, z'a, completion of M, 1/F, loglik terms, rank-1
+  const int fma_obs = (2 + 4 * H + 2 * H) + 2 + 1 + 1 + 4 + 1 + 4 * K + 2, mul_obs = 2 + 2 * H + 1 + 1 + 1 + 1 + 2,
+            add_obs = 2 * lg + 2 * H + 1;
+  // per time step: T_I P_IJ T_J' for the K own blocks (R Q R' added on the diagonal one), T a
+  const int fma_t = 4 + 6 + 8 * H + 2, mul_t = 4 + 2 + 8 * H + 2;
+  const int tm_fma = p == 1 ? 2 : 0, tm_mul = p == 1 ? 2 : 0;  // p = 1: (T M)_I
+  return L * (p * (2 * fma_obs + mul_obs + add_obs) + 2 * (fma_t + tm_fma) + mul_t + tm_mul);
+}
+// the same without the lanes and blocks that only pad (L > nb: surplus lanes; nb even: the unowned half of the
+// blocks at distance nb / 2)
+int blk_useful_flops_per_step(int nb, int p) {
+  const int L = blk_lanes(nb);
+  return (int)((long long)blk_flops_per_step(nb, p) * nb / L);
 }
 
 int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
-                      const HostShared* hs, bool* applicable) {
+                      const HostShared* hs, bool* applicable, bool lanes_only) {
   std::string why;
   if (applicable) *applicable = true;
   SS_ARG(blk_eligible(md, &why), "block kernel not eligible: " + why);
@@ -689,31 +780,74 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     }
     SS_ARG(false, "block kernel not eligible: " + why);
   }
+  A.ldy = B;
   const int L = blk_lanes(pl.nb), G = 32 / L, wpb = (pl.nb > 8 ? kBlkThreadsCS : kBlkThreads) / 32;
-  const long long blocks = (A.E + (long long)wpb * G - 1) / ((long long)wpb * G);
-  SS_ARG(blocks < (1LL << 31), "block kernel: batch too large for one launch");
-  const unsigned nblk = (unsigned)blocks;
-  switch (pl.nb) {
-    case 1: launch_blk_nb<1, 1>(A, pl.q_offdiag != 0, nblk, st); break;
-    case 2: launch_blk_nb<2, 2>(A, pl.q_offdiag != 0, nblk, st); break;
-    case 3: launch_blk_nb<4, 3>(A, pl.q_offdiag != 0, nblk, st); break;
-    case 4: launch_blk_nb<4, 4>(A, pl.q_offdiag != 0, nblk, st); break;
-    case 5: launch_blk_nb<8, 5>(A, pl.q_offdiag != 0, nblk, st); break;
-    case 6: launch_blk_nb<8, 6>(A, pl.q_offdiag != 0, nblk, st); break;
-    case 7: launch_blk_nb<8, 7>(A, pl.q_offdiag != 0, nblk, st); break;
-    case 8: launch_blk_nb<8, 8>(A, pl.q_offdiag != 0, nblk, st); break;
-    case 9: launch_blk_nb<16, 9>(A, false, nblk, st); break;
-    case 10: launch_blk_nb<16, 10>(A, false, nblk, st); break;
-    case 11: launch_blk_nb<16, 11>(A, false, nblk, st); break;
-    case 12: launch_blk_nb<16, 12>(A, false, nblk, st); break;
-    case 13: launch_blk_nb<16, 13>(A, false, nblk, st); break;
-    case 14: launch_blk_nb<16, 14>(A, false, nblk, st); break;
-    case 15: launch_blk_nb<16, 15>(A, false, nblk, st); break;
-    default: launch_blk_nb<16, 16>(A, false, nblk, st); break;
+  auto launch_lanes = [&](const BlkArgs& Ax) -> int {
+    const long long blocks = (Ax.E + (long long)wpb * G - 1) / ((long long)wpb * G);
+    SS_ARG(blocks < (1LL << 31), "block kernel: batch too large for one launch");
+    const unsigned nblk = (unsigned)blocks;
+    switch (pl.nb) {
+      case 1: launch_blk_nb<1, 1>(Ax, pl.q_offdiag != 0, nblk, st); break;
+      case 2: launch_blk_nb<2, 2>(Ax, pl.q_offdiag != 0, nblk, st); break;
+      case 3: launch_blk_nb<4, 3>(Ax, pl.q_offdiag != 0, nblk, st); break;
+      case 4: launch_blk_nb<4, 4>(Ax, pl.q_offdiag != 0, nblk, st); break;
+      case 5: launch_blk_nb<8, 5>(Ax, pl.q_offdiag != 0, nblk, st); break;
+      case 6: launch_blk_nb<8, 6>(Ax, pl.q_offdiag != 0, nblk, st); break;
+      case 7: launch_blk_nb<8, 7>(Ax, pl.q_offdiag != 0, nblk, st); break;
+      case 8: launch_blk_nb<8, 8>(Ax, pl.q_offdiag != 0, nblk, st); break;
+      case 9: launch_blk_nb<16, 9>(Ax, false, nblk, st); break;
+      case 10: launch_blk_nb<16, 10>(Ax, false, nblk, st); break;
+      case 11: launch_blk_nb<16, 11>(Ax, false, nblk, st); break;
+      case 12: launch_blk_nb<16, 12>(Ax, false, nblk, st); break;
+      case 13: launch_blk_nb<16, 13>(Ax, false, nblk, st); break;
+      case 14: launch_blk_nb<16, 14>(Ax, false, nblk, st); break;
+      case 15: launch_blk_nb<16, 15>(Ax, false, nblk, st); break;
+      default: launch_blk_nb<16, 16>(Ax, false, nblk, st); break;
+    }
+    SS_CUDA(cudaGetLastError());
+    count_launch();
+    return SSGPU_OK;
+  };
+  static thread_local char name[160];
+  // SSGPU_BLK_THREAD=0: the lane kernel alone (experiments, A/B runs)
+  static const bool thr_on = [] {
+    const char* e = getenv("SSGPU_BLK_THREAD");
+    return !(e && e[0] == '0');
+  }();
+  if (thr_on && !lanes_only && thr_supported(pl.nb, p, nZ > 1)) {
+    // Two launches per range of series: the lane kernel runs the exact diffuse phase and leaves the state behind, the
+    // thread kernel (loglik_thr.cu) runs the regular phase.  The state record is ~1.1 KB per evaluation at 7 blocks:
+    // ranges of series are sized for SSGPU_THR_SCRATCH_MB (default 2048) of scratch.
+    static const long long cap = [] {
+      const char* e = getenv("SSGPU_THR_SCRATCH_MB");
+      return (long long)(e ? std::max(1, atoi(e)) : 2048) << 20;
+    }();
+    const size_t per_eval = thr_handoff_bytes(pl.nb, pl.q_offdiag != 0, 1);
+    const long long Bc_max = std::min<long long>(B, std::max<long long>(1, cap / (long long)(per_eval * V)));
+    const BlkHandoff hl(pl.nb, pl.q_offdiag != 0);
+    DevBuf scratch;  // released stream-ordered behind the last kernel
+    SS_TRY(scratch.alloc((size_t)Bc_max * V * per_eval, st));
+    for (long long b0 = 0; b0 < B; b0 += Bc_max) {
+      const long long Bc = std::min(Bc_max, B - b0), Ec = Bc * V;
+      BlkArgs Ac = A;
+      for (DMat* dm : {&Ac.md.a, &Ac.md.P_inf, &Ac.md.P_star, &Ac.md.Q}) dm->p += b0 * dm->sb;
+      Ac.y = y + b0;
+      Ac.out = out + b0;
+      Ac.B = Bc;
+      Ac.E = Ec;
+      Ac.hd = scratch.as<double>();
+      Ac.hi = reinterpret_cast<int*>(Ac.hd + (size_t)hl.doubles() * Ec);
+      SS_TRY(launch_lanes(Ac));
+      SS_TRY(launch_loglik_thr(pl, &A.z[0][0], Ac.y, Bc, Ec, B, md.N, Ac.hd, Ac.hi, Ac.out, st));
+      count_launch();
+    }
+    snprintf(name, sizeof name, "loglik_thr_kernel<NB=%d,S=%d,flop_per_step=%d> after loglik_blk_kernel<L=%d,NB=%d> (diffuse phase)",
+             pl.nb, thr_smem_blocks_host(pl.nb), thr_flops_per_step(pl.nb, pl.q_offdiag != 0), L, pl.nb);
+    set_last_kernel(name);
+    return SSGPU_OK;
   }
-  SS_CUDA(cudaGetLastError());
-  count_launch();
-  static thread_local char name[96];
+  A.B = B;
+  SS_TRY(launch_lanes(A));
   snprintf(name, sizeof name, "loglik_blk_kernel<L=%d,NB=%d,flop_per_step=%d>%s", L, pl.nb, blk_flops_per_step(pl.nb, p),
            nZ > 1 ? " time-varying Z" : "");
   set_last_kernel(name);

@@ -1,0 +1,341 @@
+// Regular phase of the batched loglikelihood for block-diagonal T (blocks of at most 2 x 2), ONE THREAD PER
+// EVALUATION, the symmetric covariance held once (blocks on and above the diagonal) in registers and, for what does
+// not fit, in shared memory.
+//
+// Same recursion and model class as loglik_blk.cu (src/LogLikC.cpp:162-207; p = 1, Z / T / R shared by the batch and
+// time-invariant, 5 to 8 blocks: 9 <= m <= 16 -- BASELINE.json config 5 is 7 blocks).  The lane kernel of
+// loglik_blk.cu runs the exact diffuse phase (about d of the N time points, src/LogLikC.cpp:98-159) and leaves the
+// state behind (blk_handoff.cuh); this kernel runs the remaining time points.
+//
+// Why one thread per evaluation.  Spread over 8 lanes, an evaluation pays for the exchange of M = P z between the
+// lanes (36 shuffles per step), for 8 copies of the scalar part of a step (1/F, the loglikelihood terms), for one
+// idle lane in 8 at 7 blocks, and every lane needs its own copies of T_J and z in vector registers: 1,168
+// FP64 instructions per series and time step.  Here T and z are the same for all 32 lanes at every instruction, so ptxas
+// keeps them in UNIFORM registers (DFMA takes a uniform-register operand) and the vector registers hold P alone;
+// nothing is exchanged, nothing is padded, nothing is computed twice: 861 FP64 instructions per series and time step,
+// 80 % of all instructions of the loop.
+//
+// One sweep per time step (p = 1): with M = P z known from the previous sweep,
+//     tm = T M,  F = z'M,  v = y - z'a,  s = tm / sqrt(F),  a <- T a + s (v / sqrt(F)),
+// then block by block  P_IJ <- T_I P_IJ T_J' (+ R Q R' on the diagonal) - s_I s_J'   [= T (P - M M'/F) T' + R Q R']
+// and at once the block's share of the NEXT step's M:  M_I += P_IJ z_J,  M_J += P_IJ' z_I.  Every block is read once
+// and written once per step; the blocks are independent, so the FP64 pipe never waits for the reciprocal square root.
+// A missing observation or F < 1e-7 (src/LogLikC.cpp:88-90,173-176) is a no-op through 1/sqrt(F) := 0.
+//
+// Storage (7 blocks): 7 diagonal blocks x 3 + 21 blocks above the diagonal x 4 = 105 doubles.  255 registers hold
+// the diagonal blocks, the first NOFF - S blocks above the diagonal, s and the M being accumulated; the last S blocks,
+// a and the diagonal of R Q R' live in shared memory as [slot][thread] (conflict-free, one read and one write per
+// step).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "blk_handoff.cuh"
+#include "common.cuh"
+
+namespace ssgpu {
+
+constexpr int kThrThreads = 128;
+constexpr int kThrMaxNB = 8;
+
+struct ThrArgs {
+  const double* y;  // [t * ldy + b]
+  long long B, E, ldy;
+  int N;
+  const double* hd;
+  const int* hi;
+  double* out;  // [v * ldy + b]
+  double cst[kThrMaxNB][6];  // T_I row-major (4), z_I (2): internal order of the block plan
+};
+
+__device__ __forceinline__ double thr_rsqrt(double x) {
+  // MUFU.RSQ64H seed and three coupled Newton steps (x is finite, normal and >= 1e-7 here); relative error of the
+  // seed <= 2^-20, after the steps below the rounding of the last fma
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * r, r, 0.5);
+  r = fma(r, e, r);
+  e = fma(-h * r, r, 0.5);
+  r = fma(r, e, r);
+  e = fma(-h * r, r, 0.5);
+  return fma(r, e, r);
+}
+
+// An offset of zero the optimiser cannot see through.  T and z are read from the kernel parameters through it inside
+// the time loop: ptxas then serves them from uniform registers / the constant bank at the instruction that uses
+// them.  Read at fixed parameter offsets they are hoisted out of the loop into 84 VECTOR registers and the
+// covariance spills.
+__device__ __forceinline__ int thr_opaque0() {
+  int o;
+  asm volatile("mov.u32 %0, 0;" : "=r"(o));
+  return o;
+}
+
+// S: blocks above the diagonal kept in shared memory (the last S in row-major order)
+template <int NB, int S, bool QOFF>
+__global__ void __launch_bounds__(kThrThreads, 2) loglik_thr_kernel(const ThrArgs A) {
+  constexpr BlkHandoff HL(NB, QOFF);
+  constexpr int NOFF = HL.noff();
+  constexpr int RO = NOFF - S;  // blocks above the diagonal in registers
+  constexpr int QW = HL.qw;
+  static_assert(S >= 0 && S <= NOFF, "shared-memory blocks");
+  const long long w = (long long)blockIdx.x * kThrThreads + threadIdx.x;
+  if (w >= A.E) return;
+  const long long E = A.E;
+  int t = A.hi[w];
+  const int N = A.N;
+  if (t >= N) return;  // finished by the lane kernel
+  const long long V = E / A.B, b = w / V, v = w % V;
+  extern __shared__ double thr_sm[];  // [slot][thread]: a (2 NB), R Q R' (QW NB), S blocks (4 each)
+  double* const smt = thr_sm + threadIdx.x;
+  auto SA = [&](int i) -> double& { return smt[i * kThrThreads]; };
+  auto SQ = [&](int i) -> double& { return smt[(2 * NB + i) * kThrThreads]; };
+  auto SP = [&](int i) -> double& { return smt[((2 + QW) * NB + i) * kThrThreads]; };
+  const double* const hd = A.hd + w;
+  double D[NB][3], O[RO > 0 ? RO : 1][4], M[NB][2];
+#pragma unroll
+  for (int i = 0; i < 2 * NB; i++) SA(i) = hd[(long long)(HL.a() + i) * E];
+#pragma unroll
+  for (int i = 0; i < QW * NB; i++) SQ(i) = hd[(long long)(HL.q() + i) * E];
+#pragma unroll
+  for (int I = 0; I < NB; I++) {
+#pragma unroll
+    for (int e = 0; e < 3; e++) D[I][e] = hd[(long long)(HL.d() + 3 * I + e) * E];
+  }
+#pragma unroll
+  for (int i = 0; i < NOFF; i++) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const double x = hd[(long long)(HL.o() + 4 * i + e) * E];
+      if (i < RO)
+        O[i][e] = x;
+      else
+        SP((i - RO) * 4 + e) = x;
+    }
+  }
+  double prod = hd[(long long)HL.s() * E], sumq = hd[(long long)(HL.s() + 1) * E];
+  int esum = A.hi[E + w], n_upd = 0, n_obs = 0;
+
+  // M = P z of the first time point (afterwards every sweep leaves the next step's M behind)
+  {
+    int oi = 0;
+#pragma unroll
+    for (int I = 0; I < NB; I++) M[I][0] = M[I][1] = 0.0;
+#pragma unroll
+    for (int I = 0; I < NB; I++) {
+      const double zi0 = A.cst[I][4], zi1 = A.cst[I][5];
+      M[I][0] = fma(D[I][1], zi1, fma(D[I][0], zi0, M[I][0]));
+      M[I][1] = fma(D[I][2], zi1, fma(D[I][1], zi0, M[I][1]));
+#pragma unroll
+      for (int J = I + 1; J < NB; J++, oi++) {
+        const double zj0 = A.cst[J][4], zj1 = A.cst[J][5];
+        double p0, p1, p2, p3;
+        if (oi < RO) {
+          p0 = O[oi < RO ? oi : 0][0], p1 = O[oi < RO ? oi : 0][1], p2 = O[oi < RO ? oi : 0][2], p3 = O[oi < RO ? oi : 0][3];
+        } else {
+          const int o = (oi - RO) * 4;
+          p0 = SP(o), p1 = SP(o + 1), p2 = SP(o + 2), p3 = SP(o + 3);
+        }
+        M[I][0] = fma(p1, zj1, fma(p0, zj0, M[I][0]));
+        M[I][1] = fma(p3, zj1, fma(p2, zj0, M[I][1]));
+        M[J][0] = fma(p2, zi1, fma(p0, zi0, M[J][0]));
+        M[J][1] = fma(p3, zi1, fma(p1, zi0, M[J][1]));
+      }
+    }
+  }
+
+  // loglik terms of one observation (src/LogLikC.cpp:173-195): r = 1/sqrt(F) or 0, cv = v / sqrt(F)
+  double r, cv;
+  auto observe = [&](double yv, double F, double za) {
+    const bool obs = !isnan(yv);  // :88-90
+    const bool upd = obs && !(F < kEps);
+    r = thr_rsqrt(upd ? F : 1.0);
+    r = upd ? r : 0.0;
+    cv = r * (upd ? yv - za : 0.0);
+    prod *= upd ? F : 1.0;
+    const int hi = __double2hiint(prod);
+    const int ex = ((hi >> 20) & 0x7ff) - 1023;
+    esum += ex;
+    prod = __hiloint2double(hi - (ex << 20), __double2loint(prod));
+    n_upd += upd;
+    n_obs += obs;
+    sumq = fma(cv, cv, sumq);
+  };
+
+  const double* yp = A.y + b + (long long)t * A.ldy;
+  double ynext = *yp;
+  for (; t < N - 1; t++) {
+    const double yv = ynext;
+    yp += A.ldy;
+    ynext = *yp;
+    // ---- the vectors: tm = T M (in place), F = z'M, z'a, T a
+    double F = 0.0, za = 0.0, ta[NB][2];
+    const double* const cv0 = &A.cst[0][0] + thr_opaque0();
+#pragma unroll
+    for (int I = 0; I < NB; I++) {
+      const double t00 = cv0[I * 6], t01 = cv0[I * 6 + 1], t10 = cv0[I * 6 + 2], t11 = cv0[I * 6 + 3], z0 = cv0[I * 6 + 4], z1 = cv0[I * 6 + 5];
+      const double m0 = M[I][0], m1 = M[I][1], a0 = SA(2 * I), a1 = SA(2 * I + 1);
+      F = fma(z1, m1, fma(z0, m0, F));
+      za = fma(z1, a1, fma(z0, a0, za));
+      M[I][0] = fma(t01, m1, t00 * m0);
+      M[I][1] = fma(t11, m1, t10 * m0);
+      ta[I][0] = fma(t01, a1, t00 * a0);
+      ta[I][1] = fma(t11, a1, t10 * a0);
+    }
+    observe(yv, F, za);
+    double s[NB][2];
+#pragma unroll
+    for (int I = 0; I < NB; I++) {
+      s[I][0] = M[I][0] * r;
+      s[I][1] = M[I][1] * r;
+      SA(2 * I) = fma(s[I][0], cv, ta[I][0]);
+      SA(2 * I + 1) = fma(s[I][1], cv, ta[I][1]);
+      M[I][0] = 0.0;
+      M[I][1] = 0.0;
+    }
+    // ---- one sweep over the blocks on and above the diagonal
+    int oi = 0;
+#pragma unroll
+    for (int I = 0; I < NB; I++) {
+      const double* const ci = &A.cst[0][0] + thr_opaque0();
+      const double t00 = ci[I * 6], t01 = ci[I * 6 + 1], t10 = ci[I * 6 + 2], t11 = ci[I * 6 + 3], zi0 = ci[I * 6 + 4], zi1 = ci[I * 6 + 5];
+      {
+        double p0 = D[I][0], p1 = D[I][1], p3 = D[I][2];
+        const double y00 = fma(t01, p1, t00 * p0), y01 = fma(t01, p3, t00 * p1);
+        const double y10 = fma(t11, p1, t10 * p0), y11 = fma(t11, p3, t10 * p1);
+        p0 = fma(y01, t01, fma(y00, t00, SQ(QW * I)));
+        p1 = QOFF ? fma(y01, t11, fma(y00, t10, SQ(QW * I + 1))) : fma(y01, t11, y00 * t10);
+        p3 = fma(y11, t11, fma(y10, t10, SQ(QW * I + QW - 1)));
+        p0 = fma(-s[I][0], s[I][0], p0);
+        p1 = fma(-s[I][0], s[I][1], p1);
+        p3 = fma(-s[I][1], s[I][1], p3);
+        D[I][0] = p0;
+        D[I][1] = p1;
+        D[I][2] = p3;
+        M[I][0] = fma(p1, zi1, fma(p0, zi0, M[I][0]));
+        M[I][1] = fma(p3, zi1, fma(p1, zi0, M[I][1]));
+      }
+#pragma unroll
+      for (int J = I + 1; J < NB; J++, oi++) {
+        const double* const cj = &A.cst[0][0] + thr_opaque0();
+        const double u00 = cj[J * 6], u01 = cj[J * 6 + 1], u10 = cj[J * 6 + 2], u11 = cj[J * 6 + 3], zj0 = cj[J * 6 + 4], zj1 = cj[J * 6 + 5];
+        double p0, p1, p2, p3;
+        if (oi < RO) {
+          p0 = O[oi < RO ? oi : 0][0], p1 = O[oi < RO ? oi : 0][1], p2 = O[oi < RO ? oi : 0][2], p3 = O[oi < RO ? oi : 0][3];
+        } else {
+          const int o = (oi - RO) * 4;
+          p0 = SP(o), p1 = SP(o + 1), p2 = SP(o + 2), p3 = SP(o + 3);
+        }
+        const double y00 = fma(t01, p2, t00 * p0), y01 = fma(t01, p3, t00 * p1);
+        const double y10 = fma(t11, p2, t10 * p0), y11 = fma(t11, p3, t10 * p1);
+        p0 = fma(-s[I][0], s[J][0], fma(y01, u01, y00 * u00));
+        p1 = fma(-s[I][0], s[J][1], fma(y01, u11, y00 * u10));
+        p2 = fma(-s[I][1], s[J][0], fma(y11, u01, y10 * u00));
+        p3 = fma(-s[I][1], s[J][1], fma(y11, u11, y10 * u10));
+        if (oi < RO) {
+          O[oi < RO ? oi : 0][0] = p0, O[oi < RO ? oi : 0][1] = p1, O[oi < RO ? oi : 0][2] = p2, O[oi < RO ? oi : 0][3] = p3;
+        } else {
+          const int o = (oi - RO) * 4;
+          SP(o) = p0, SP(o + 1) = p1, SP(o + 2) = p2, SP(o + 3) = p3;
+        }
+        M[I][0] = fma(p1, zj1, fma(p0, zj0, M[I][0]));
+        M[I][1] = fma(p3, zj1, fma(p2, zj0, M[I][1]));
+        M[J][0] = fma(p2, zi1, fma(p0, zi0, M[J][0]));
+        M[J][1] = fma(p3, zi1, fma(p1, zi0, M[J][1]));
+      }
+    }
+  }
+  {  // the last observation (src/LogLikC.cpp:200 -- P and a are not needed afterwards)
+    double F = 0.0, za = 0.0;
+#pragma unroll
+    for (int I = 0; I < NB; I++) {
+      F = fma(A.cst[I][5], M[I][1], fma(A.cst[I][4], M[I][0], F));
+      za = fma(A.cst[I][5], SA(2 * I + 1), fma(A.cst[I][4], SA(2 * I), za));
+    }
+    observe(ynext, F, za);
+  }
+  const int n_terms = A.hi[2 * E + w] + n_upd, non_init = A.hi[3 * E + w] + n_obs, F_eq0 = A.hi[4 * E + w] + (n_obs - n_upd);
+  double res;
+  if (non_init == F_eq0) {
+    res = nan("");  // src/LogLikC.cpp:211-213
+  } else {
+    const double sumlog = (double)esum * 0.69314718055994530942 + log(prod);
+    res = ((double)n_terms * kLogConst - 0.5 * (sumlog + sumq)) / (double)N;
+  }
+  A.out[v * A.ldy + b] = res;
+}
+
+// blocks above the diagonal that go to shared memory: what 255 registers do not hold next to s, the M being
+// accumulated and the temporaries of a block (sized with ptxas -v: no spill at these values)
+constexpr int thr_smem_blocks(int nb) { return nb == 8 ? 17 : nb == 7 ? 10 : nb == 6 ? 3 : 0; }
+
+int thr_smem_blocks_host(int nb) { return thr_smem_blocks(nb); }
+
+size_t thr_handoff_bytes(int nb, bool qoff, long long E) {
+  const BlkHandoff hl(nb, qoff);
+  return (size_t)E * (hl.doubles() * sizeof(double) + kBlkHandoffInts * sizeof(int));
+}
+
+// FP64 operations (fma = 2) per series and time step: the counts of the SASS of the loop
+int thr_flops_per_step(int nb, bool qoff) {
+  const int noff = nb * (nb - 1) / 2;
+  // vectors: F, z'a 4 fma; tm, T a 2 mul + 2 fma each; s 2 mul; a 2 fma    (per block row)
+  const int fma_v = 4 + 4 + 2, mul_v = 4 + 2;
+  // 1/sqrt(F): 3 x (1 mul + 2 fma) + 1 mul; cv 1 mul + 1 add; prod 1 mul; sumq 1 fma
+  const int fma_s = 7, mul_s = 6, add_s = 1;
+  // diagonal block: 4 mul + 4 fma, 3 outputs (5 fma + 1 mul, all fma with correlated R Q R'), rank-1 3 fma, M 4 fma
+  const int fma_d = 4 + (qoff ? 6 : 5) + 3 + 4, mul_d = 4 + (qoff ? 0 : 1);
+  // block above the diagonal: 4 mul + 4 fma, 4 mul + 4 fma, rank-1 4 fma, M 8 fma
+  const int fma_o = 4 + 4 + 4 + 8, mul_o = 8;
+  const int fma = nb * fma_v + fma_s + nb * fma_d + noff * fma_o, mul = nb * mul_v + mul_s + nb * mul_d + noff * mul_o;
+  return 2 * fma + mul + add_s;
+}
+
+template <int NB, bool QOFF>
+static int launch_thr_one(const ThrArgs& A, cudaStream_t st) {
+  constexpr int S = thr_smem_blocks(NB);
+  constexpr BlkHandoff HL(NB, QOFF);
+  const size_t smem = (size_t)((2 + HL.qw) * NB + 4 * S) * kThrThreads * sizeof(double);
+  static bool attr_done = false;  // per instantiation; a repeated call is harmless
+  if (!attr_done) {
+    SS_CUDA(cudaFuncSetAttribute(loglik_thr_kernel<NB, S, QOFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const long long blocks = (A.E + kThrThreads - 1) / kThrThreads;
+  SS_ARG(blocks < (1LL << 31), "thread kernel: batch too large for one launch");
+  loglik_thr_kernel<NB, S, QOFF><<<(unsigned)blocks, kThrThreads, smem, st>>>(A);
+  SS_CUDA(cudaGetLastError());
+  return SSGPU_OK;
+}
+
+bool thr_supported(int nb, int p, bool ztv) { return p == 1 && !ztv && nb >= 5 && nb <= kThrMaxNB; }
+
+// y, out: of the first series of the launch; hd / hi: filled by the lane kernel for the same E evaluations
+int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* y, long long B, long long E,
+                      long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st) {
+  ThrArgs A{};
+  A.y = y;
+  A.B = B;
+  A.E = E;
+  A.ldy = ldy;
+  A.N = N;
+  A.hd = hd;
+  A.hi = hi;
+  A.out = out;
+  for (int I = 0; I < pl.nb; I++) {
+    for (int k = 0; k < 4; k++) A.cst[I][k] = pl.Tb[I][k];
+    A.cst[I][4] = z_internal[2 * I];
+    A.cst[I][5] = z_internal[2 * I + 1];
+  }
+  const bool qoff = pl.q_offdiag != 0;
+  switch (pl.nb) {
+    case 5: return qoff ? launch_thr_one<5, true>(A, st) : launch_thr_one<5, false>(A, st);
+    case 6: return qoff ? launch_thr_one<6, true>(A, st) : launch_thr_one<6, false>(A, st);
+    case 7: return qoff ? launch_thr_one<7, true>(A, st) : launch_thr_one<7, false>(A, st);
+    case 8: return qoff ? launch_thr_one<8, true>(A, st) : launch_thr_one<8, false>(A, st);
+  }
+  SS_ARG(false, "thread kernel: 5 to 8 blocks");
+}
+
+}  // namespace ssgpu

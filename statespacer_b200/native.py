@@ -66,7 +66,7 @@ SYMBOLS = ["ssgpu_version", "ssgpu_last_error", "ssgpu_set_device", "ssgpu_devic
            "ssgpu_loglik_grad_batch", "ssgpu_loglik_grad_batch_dev", "ssgpu_loglik_theta_batch_dev",
            "ssgpu_SimSmoother", "ssgpu_kalman_batch", "ssgpu_kalman_batch_dev", "ssgpu_collapse", "ssgpu_forecast", "ssgpu_SimulateModel", "ssgpu_plan_blocks"]
 
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS, KERNEL_MMA, KERNEL_MMA_DENSE, KERNEL_WSM, KERNEL_BLK = 0, 1, 2, 3, 4, 5, 6
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS, KERNEL_MMA, KERNEL_MMA_DENSE, KERNEL_WSM, KERNEL_BLK, KERNEL_BLK_LANES = 0, 1, 2, 3, 4, 5, 6, 7
 
 
 def lib():

@@ -193,11 +193,11 @@ def _bsm_batch(rng, B, N, V, missing):
 
 
 KERNEL_NAMES = {"mma": "loglik_mma_kernel<TT=2,tiles=0x9,", "mma_dense": "loglik_mma_kernel<TT=2,tiles=0xf,",
-                "cols": "loglik_cols", "generic": "fwd_generic", "blk": "loglik_blk_kernel<L=8,NB=7,",
-                "auto": "loglik_blk_kernel<L=8,NB=7,"}
+                "cols": "loglik_cols", "generic": "fwd_generic", "blk": "loglik_thr_kernel<NB=7,",
+                "auto": "loglik_thr_kernel<NB=7,", "blk_lanes": "loglik_blk_kernel<L=8,NB=7,"}
 
 
-@pytest.mark.parametrize("kernel", ["mma", "mma_dense", "cols", "generic", "blk", "auto"])
+@pytest.mark.parametrize("kernel", ["mma", "mma_dense", "cols", "generic", "blk", "blk_lanes", "auto"])
 def test_batch_config5_shape(kernel):
     rng = np.random.default_rng(5)
     B, N, V = 70, 60, 3
@@ -281,17 +281,22 @@ def test_batch_blk_kernel(name):
     Pd = np.diag(sm.P_star)[None, :] * scale
     ab = rng.normal(size=(B, m)) * 0.1
     got = api.loglik_batch(y, sm, Q_diag=Qd, P_star_diag=Pd, a=ab, kernel="blk")
-    assert api.last_kernel().startswith("loglik_blk_kernel<"), api.last_kernel()
+    # 5 to 8 blocks: the lanes run the diffuse phase and hand over to the thread-per-evaluation kernel
+    first = "loglik_thr_kernel<" if 9 <= m <= 16 else "loglik_blk_kernel<"
+    assert api.last_kernel().startswith(first), api.last_kernel()
     gen = api.loglik_batch(y, sm, Q_diag=Qd, P_star_diag=Pd, a=ab, kernel="generic")
     auto = api.loglik_batch(y, sm, Q_diag=Qd, P_star_diag=Pd, a=ab)
-    assert api.last_kernel().startswith("loglik_blk_kernel<") and np.array_equal(auto, got, equal_nan=True)
-    assert np.all(np.isfinite(got))
+    assert api.last_kernel().startswith(first) and np.array_equal(auto, got, equal_nan=True)
+    lanes = api.loglik_batch(y, sm, Q_diag=Qd, P_star_diag=Pd, a=ab, kernel="blk_lanes")
+    assert api.last_kernel().startswith("loglik_blk_kernel<"), api.last_kernel()
+    assert np.all(np.isfinite(got)) and np.all(np.isfinite(lanes))
     for b in range(B):
         smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=np.diag(Qd[b])[:, :, None], a=ab[b], P_inf=sm.P_inf,
                             P_star=np.diag(Pd[b]))
         yb = y[:, b:b + 1]
         want = cport.LogLikC(yb, np.isnan(yb), *smb.args())
         assert abs(got[b] - want) <= RTOL * max(1, abs(want)), (name, b, got[b], want)
+        assert abs(lanes[b] - want) <= RTOL * max(1, abs(want)), (name, b, lanes[b], want)
         assert abs(gen[b] - want) <= RTOL * max(1, abs(want)), (name, b, gen[b], want)
 
 
@@ -371,6 +376,9 @@ def test_batch_blk_kernel_degenerate_series(N):
     y[: N // 2, 3] = np.nan
     Qd[4], Pd[4] = 0.0, 0.0                           # no noise at all
     got = api.loglik_batch(y, sysmat.bsm12(thetas[0, 0]), Q_diag=Qd, P_star_diag=Pd, kernel="blk")
+    assert api.last_kernel().startswith("loglik_thr_kernel<NB=7,"), api.last_kernel()
+    lanes = api.loglik_batch(y, sysmat.bsm12(thetas[0, 0]), Q_diag=Qd, P_star_diag=Pd, kernel="blk_lanes")
+    assert np.allclose(got, lanes, rtol=RTOL, atol=RTOL, equal_nan=True)
     gen = api.loglik_batch(y, sysmat.bsm12(thetas[0, 0]), Q_diag=Qd, P_star_diag=Pd, kernel="generic")
     for b in range(B):
         sm = sysmat.bsm12(thetas[0, b])
@@ -411,7 +419,7 @@ def test_loglik_grad_batch_from_theta():
     theta = thetas[0]                                                   # (B, 4)
     sm0 = sysmat.bsm12(theta[0])
     ll, gr = api.loglik_grad_batch(y, sm0, theta, BSM_Q_INDEX, BSM_P_INDEX, h=h)
-    assert api.last_kernel().startswith("loglik_blk")
+    assert api.last_kernel().startswith("loglik_thr_kernel<NB=7,")
     for b in range(0, B, 5):
         yb = y[:, b:b + 1]
         f = lambda th: cport.LogLikC(yb, np.isnan(yb), *sysmat.bsm12(th).args())
@@ -655,7 +663,7 @@ def test_batch_properties_large():
 
 def test_full_size_block_row_vs_tensor_kernel():
     """BASELINE.json config 5 at its full per-GPU size (125,000 series x 9 parameter vectors x T = 1000, the bench's
-    own synthetic shard): the block-row kernel and the tensor kernel -- two independent implementations of the
+    own synthetic shard): the thread-per-evaluation kernel (default), the lane kernel and the tensor kernel -- three independent implementations of the
     recursion -- agree to 1e-9 on every loglikelihood and on the central-difference gradients, and a sample of series
     agrees with the oracle."""
     import torch
@@ -666,12 +674,15 @@ def test_full_size_block_row_vs_tensor_kernel():
     y[torch.rand(y.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(1)) < 0.01] = float("nan")
     model = api.BatchModel(sm, bench.T_STEPS, B, 1, device=dev)
     out = {}
-    for kernel in ("blk", "mma"):
+    for kernel in ("blk", "blk_lanes", "mma"):
         out[kernel] = api.loglik_grad_batch_dev(y, model, theta, bench.Q_INDEX, bench.P_INDEX, h=bench.H_FD, kernel=kernel)
     ll_b, gr_b = out["blk"]
+    ll_l, gr_l = out["blk_lanes"]
     ll_m, gr_m = out["mma"]
     assert bool(torch.isfinite(ll_b).all()) and bool(torch.isfinite(gr_b).all())
     assert float(((ll_b - ll_m).abs() / ll_m.abs().clamp(min=1.0)).max()) < RTOL
+    assert float(((ll_l - ll_m).abs() / ll_m.abs().clamp(min=1.0)).max()) < RTOL
+    assert float((gr_l - gr_m).abs().max()) < 1e-6
     # gradients are differences of loglik / N at h = 1e-3: 1e-9 on the values is 1e-6 on the quotient
     assert float((gr_b - gr_m).abs().max()) < 1e-6
     yh, th = y[:, :4].cpu().numpy(), theta[:4].cpu().numpy()
