@@ -61,13 +61,6 @@ def f_alg(m, p):
 # Scalar FP64 instructions per warp and time step in the p = 1 hot loop of loglik_mma_kernel (cuobjdump -sass and
 # ncu smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul}_pred_on, profiles/README.md): 23 DFMA, 11 DADD, 4 DMUL
 SCALAR_FLOPS_PER_STEP = (23 * 2 + 11 + 4) * 32
-# dram__bytes_read.sum + dram__bytes_write.sum of one loglik_mma_kernel launch at the default size (125,000 series x 9
-# parameter vectors x 1000 steps), from the `ncu --set full` capture summarised in
-# profiles/ncu_mma_r1_fullsize_summary.csv (1.289 GB + 21.2 MB); algorithmic: y 1.0 GB + variance sets 0.252 GB + out
-NCU_TRAFFIC_BYTES = {("loglik_mma_kernel<TT=2,tiles=0x9,dmma_per_step=14>", 125_000): 1.289423e9 + 21.163008e6,
-                     # profiles/ncu_blk_r1_fullsize_summary.csv
-                     ("loglik_blk_kernel<L=8,NB=7,flop_per_step=2824>", 125_000): 1.269807e9 + 16.314624e6}
-
 
 def executed_flops(kernel_name):
     """Flops the tensor kernel issues per series*timestep: DMMAs (8x8x4: 512 flops each, padding included) + scalar
@@ -76,8 +69,15 @@ def executed_flops(kernel_name):
     m = re.search(r"dmma_per_step=(\d+)", kernel_name or "")
     if m:
         return int(m.group(1)) * 512 + SCALAR_FLOPS_PER_STEP
-    m = re.search(r"flop_per_step=(\d+)", kernel_name or "")     # block-row kernel: counted by the library itself
+    m = re.search(r"flop_per_step=(\d+)", kernel_name or "")     # block kernels: counted by the library itself
     return int(m.group(1)) if m else None
+
+
+def executed_fp64_instructions(kernel_name):
+    """FP64 instructions (DFMA + DMUL + DADD) per series*timestep of the thread-per-evaluation kernel at 7 blocks
+    (loglik_thr.cu thr_flops_per_step: 609 DFMA + 251 DMUL + 1 DADD, the counts of the SASS of its loop and of ncu's
+    smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on); None for the other kernels."""
+    return 861 if (kernel_name or "").startswith("loglik_thr_kernel<NB=7,") else None
 
 
 def variants(theta):
@@ -163,9 +163,13 @@ def run_reference(args):
     from oracle import cport, ref
     mod, kind = (ref, "reference") if ref.available() else (cport, "port")
     cores = host_cores()
-    n_series = max(16, 32 * cores)
+    # BASELINE.md 3.4 asks for >= 8192 series per sample; the whole `--steps K --warmup W` run has to end within a few
+    # minutes, so the sample is sized from a probe: 8192 series when K + W steps of it fit ~150 s, fewer otherwise
+    smp, yyp, Pp, Qp = cpu_sample(64 * max(1, cores // 4))
+    rate, _, _ = time_cpu(mod, smp, yyp, Pp, Qp, cores)
+    n_series = args.cpu_series or int(min(8192, max(32 * cores, rate * 150.0 / ((args.steps + min(args.warmup, 1)) * V * T_STEPS))))
     sm, yy, Pfull, Qfull = cpu_sample(n_series)
-    for _ in range(args.warmup):
+    for _ in range(min(args.warmup, 1)):
         time_cpu(mod, sm, yy, Pfull, Qfull, cores)
     times = []
     for _ in range(args.steps):
@@ -305,11 +309,11 @@ def make_shard(torch, dev, B, seed):
     return sm, y, theta
 
 
-def run_gpu(args):
+def gpu_setup():
+    """One process per GPU (RANK / LOCAL_RANK / WORLD_SIZE from torchrun); the NCCL group is created once per process."""
     import torch
     import torch.distributed as dist
     from statespacer_b200 import api
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -318,8 +322,46 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     api.set_device(local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
+    return world, rank, local, dev
+
+
+def committed_traffic(kernel_prefix, grid):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel from the `ncu --set full` summaries
+    committed under profiles/ (scripts/ncu_summary.py), matched by kernel name and grid size; None when no capture of
+    this kernel at this size is committed.  DRAM bytes cannot be counted in-run without a profiler."""
+    import csv
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_*_summary.csv"))):
+        try:
+            rows = list(csv.reader(open(path)))
+        except OSError:
+            continue
+        cur = None
+        for r in rows + [["kernel", "", ""]]:
+            if r and r[0] == "kernel":
+                if cur and kernel_prefix in cur.get("name", "") and cur.get("grid") == grid and "rd" in cur and "wr" in cur:
+                    best = {"bytes": cur["rd"] + cur["wr"], "source": os.path.relpath(path, ROOT)}
+                cur = {"name": r[2] if len(r) > 2 else ""}
+            elif cur is not None and len(r) >= 3:
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[1])
+                if r[0] == "dram__bytes_read.sum" and scale:
+                    cur["rd"] = float(r[2]) * scale
+                elif r[0] == "dram__bytes_write.sum" and scale:
+                    cur["wr"] = float(r[2]) * scale
+                elif r[0] == "launch__grid_size":
+                    cur["grid"] = int(float(r[2]))
+    return best
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from statespacer_b200 import api
+
+    world, rank, local, dev = gpu_setup()
     B = args.series
     sm, y, theta = make_shard(torch, dev, B, rank)
     if args.missing > 0:
@@ -421,6 +463,28 @@ def run_gpu(args):
                      and np.array_equal(gr_h.numpy(), res["gr"].cpu().numpy()))
     h2d = y_h.numel() * 8 + th_h.numel() * 8 + 8 * (M * M * 3 + M * 3)
     d2h = (ll_h.numel() + gr_h.numel()) * 8
+    # the same call on PAGEABLE host arrays (what R hands over): the library stages them through its pinned ring
+    y_p, th_p = y_h.numpy().copy(), th_h.numpy().copy()
+    ll_p, gr_p = np.empty(B), np.empty((B, K_PAR))
+
+    def e2e_pageable_step():
+        native.check(native.lib().ssgpu_loglik_grad_batch(y_p.ctypes.data, B, C.byref(hmodel.c), th_p.ctypes.data, K_PAR,
+                                                          qi.ctypes.data, pi.ctypes.data, H_FD,
+                                                          api._KERNELS[args.kernel], ll_p.ctypes.data, gr_p.ctypes.data))
+
+    e2e_pageable_step()
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_pageable_step()
+    sync()
+    e2e_p_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_p_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_p_s = float(t.item())
+    e2e_pageable_value = units_per_step * e2e_steps / e2e_p_s
+    e2e_pageable_match = bool(np.array_equal(ll_p, ll_h.numpy()) and np.array_equal(gr_p, gr_h.numpy()))
 
     if rank == 0:
         flops = f_alg(M, 1) * B * V * T_STEPS
@@ -432,6 +496,21 @@ def run_gpu(args):
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             pass
+        thr = kernel_name.startswith("loglik_thr_kernel")
+        # every lane of the thread kernel works on its own evaluation; the lane kernel at 7 blocks idles 1 lane in 8
+        useful = 1.0 if thr else 7.0 / 8.0 if kernel_name.startswith("loglik_blk_kernel<L=8,NB=7") else 1.0
+        n_inst = executed_fp64_instructions(kernel_name)
+        # share of the FP64 pipe's issue slots the kernel fills: one FP64 instruction of a warp occupies a
+        # sub-partition's pipe for 2 cycles, whether it is a DFMA (2 flop) or a DMUL / DADD (1 flop)
+        pipe_frac = None
+        if n_inst:
+            props = torch.cuda.get_device_properties(dev)
+            sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            pipe_frac = n_inst * 2.0 * B * V * T_STEPS / 32.0 / (props.multi_processor_count * 4 * sm_hz * kernel_ms * 1e-3)
+        # state record of blk_handoff.cuh: 135 doubles + 5 ints per evaluation at 7 blocks, written once, read once
+        handoff = 2.0 * (135 * 8 + 5 * 4) * B * V if thr else 0.0
+        grid = (B * V + 127) // 128 if thr else None
+        traffic = committed_traffic("loglik_thr_kernel" if thr else kernel_name.split("<")[0], grid) if grid else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -439,22 +518,35 @@ def run_gpu(args):
                                             "results_finite": finite}),
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "bit_identical_to_resident_path": e2e_match},
+                        "steps": e2e_steps, "bit_identical_to_resident_path": e2e_match, "host_memory": "pinned",
+                        "pageable": {"value": e2e_pageable_value, "unit": UNIT, "steps": e2e_steps,
+                                     "bit_identical_to_pinned": e2e_pageable_match,
+                                     "note": "the same call on pageable host arrays (what R passes): staged through "
+                                             "the library's ring of pinned buffers"}},
                 "gpu_launches": launches,
                 "roofline": {"bound": "fp64", "kernel": kernel_name,
                              "achieved": executed if executed else achieved, "peak": peak_tf, "unit": "TFLOP/s",
                              "frac": (executed if executed else achieved) / peak_tf,
-                             "traffic": NCU_TRAFFIC_BYTES.get((kernel_name, B)),
-                             "traffic_algorithmic": 8.0 * B * T_STEPS + 8.0 * B * V * 2 * M + 8.0 * B * V,
+                             "traffic": traffic["bytes"] if traffic else None,
+                             "traffic_source": traffic["source"] if traffic else
+                             "no ncu capture of this kernel at this size under profiles/",
+                             "traffic_algorithmic": 8.0 * B * T_STEPS + 8.0 * B * V * 2 * M + 8.0 * B * V + handoff,
+                             "traffic_algorithmic_note": "y once + the variance sets + results"
+                             + (" + the state the lane kernel hands to the thread kernel after the diffuse phase, "
+                                "written and read once (%d B per evaluation)" % (handoff / (B * V)) if handoff else ""),
+                             "useful_frac": (executed if executed else achieved) / peak_tf * useful,
+                             "fp64_pipe_frac": pipe_frac,
                              "kernel_ms": kernel_ms,
                              "flops_executed_per_series_timestep": f_exec,
                              "dense_algorithm_flops_per_series_timestep": f_alg(M, 1),
                              "dense_algorithm_equivalent_tflops": achieved,
                              "dense_algorithm_equivalent_frac": achieved / peak_tf,
-                             "note": "achieved/frac count the FP64 operations the kernel ISSUES (fma = 2; every lane, "
-                                     "padding included): the kernels exploit the block-diagonal T of the model (SURVEY.md "
-                                     "8d: a structure-exploiting kernel reports its own executed-flop count), so frac is "
-                                     "the FP64 datapath utilisation.  dense_algorithm_*: the same run priced at the dense "
+                             "note": "achieved/frac count the FP64 operations the kernel ISSUES (fma = 2, mul = add = 1; every "
+                                     "lane): the kernels exploit the block-diagonal T and the symmetry of P (SURVEY.md "
+                                     "8d: a structure-exploiting kernel reports its own executed-flop count).  "
+                                     "fp64_pipe_frac is the share of FP64 issue slots filled (30 % of the kernel's FP64 "
+                                     "instructions are DMUL / DADD: one flop, same slot); useful_frac discounts lanes "
+                                     "that only pad.  dense_algorithm_*: the same run priced at the dense "
                                      "algorithm's 4m^3 + 7m^2 + 7m flops per series*timestep, for comparison with a "
                                      "dense kernel only -- it exceeds the peak when the structure is exploited",
                              "peak_source": "ssgpu_fp64_peak DFMA chains, measured in this run (MEASURED_PEAKS.json "
@@ -465,7 +557,7 @@ def run_gpu(args):
             from oracle import cport, ref
             mod, kind = (ref, "reference") if ref.available() else (cport, "port")
             cores = host_cores()
-            n_series = 256 * cores
+            n_series = max(8192, 256 * cores) if not args.cpu_series else args.cpu_series   # >= 8192 series
             smc, yy, Pfull, Qfull = cpu_sample(n_series)
             v_ref, dt, o_ref = time_cpu(mod, smc, yy, Pfull, Qfull, cores)
             v_port, _, o_port = time_cpu(cport, smc, yy, Pfull, Qfull, cores)
@@ -476,9 +568,8 @@ def run_gpu(args):
                                               f"({dt:.1f} s)",
                                     "port_value": v_port,
                                     "port_vs_reference_max_abs_diff": float(np.max(np.abs(o_ref - o_port)))}
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 # ---- config 4: simulation smoother draws (--workload sim) ---------------------------------------------
@@ -567,16 +658,7 @@ def run_sim_gpu(args):
     import torch.distributed as dist
     from statespacer_b200 import api
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (statespacer_b200 has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    api.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, local, dev = gpu_setup()
     air, sm = sim_model()
     N, S = len(air), args.nsim
     steps0 = int(api.KalmanC(air, np.isnan(air), *sm.args(), False)["initialisation_steps"])
@@ -696,6 +778,7 @@ def run_sim_gpu(args):
             pass
         fs_ms = statistics.mean(kt["smoother"])
         achieved = b_fs * S * N / (fs_ms * 1e-3) / 1e9
+        fs_traffic = committed_traffic("fs_draw_reg_kernel", (S + 31) // 32)
         line = {"metric": SIM_METRIC, "value": value, "unit": SIM_UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -712,9 +795,9 @@ def run_sim_gpu(args):
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "fs_draw_reg_kernel", "achieved": achieved, "peak": hbm_peak,
                              "unit": "GB/s", "frac": achieved / hbm_peak,
-                             # ncu --set full at 100,000 draws: 0.382 GB read + 3.514 GB written
-                             # (profiles/ncu_sim_r1_summary.csv) against 3.571 GB algorithmic
-                             "traffic": 0.381991936e9 + 3.513818e9 if S == 100_000 else None,
+                             "traffic": fs_traffic["bytes"] if fs_traffic else None,
+                             "traffic_source": fs_traffic["source"] if fs_traffic else
+                             "no ncu capture of this kernel at this size under profiles/",
                              "peak_source": peak_src,
                              "bytes_per_draw_timestep": b_fs, "kernel_ms": fs_ms,
                              "other_kernels": {
@@ -738,9 +821,8 @@ def run_sim_gpu(args):
             with contextlib.redirect_stdout(buf):
                 run_sim_reference(a2)
             line["cpu_baseline"] = json.loads(buf.getvalue())["cpu_baseline"]
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 # ---- batched KalmanC (--workload kalman): filter + smoother of many series, HBM-bound by its outputs -------------
@@ -756,16 +838,7 @@ def run_kalman_gpu(args):
     import torch
     import torch.distributed as dist
     from statespacer_b200 import api
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (statespacer_b200 has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    api.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    world, rank, local, dev = gpu_setup()
     B = args.kalman_series
     sm, y, theta = make_shard(torch, dev, B, rank)
     var = torch.exp(2 * theta)
@@ -864,9 +937,8 @@ def run_kalman_gpu(args):
             line["cpu_baseline"] = {"value": cores * 2 * T_STEPS / dt, "unit": KAL_UNIT, "cores": cores, "kind": kind,
                                     "sample": f"{cores * 2} series x {T_STEPS} timesteps, one KalmanC call per series, "
                                               f"{cores} threads ({dt:.1f} s)"}
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 def main():
@@ -879,8 +951,9 @@ def main():
     ap.add_argument("--missing", type=float, default=0.0, help="fraction of NaN observations (variant B: 0.02)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "blk", "blk_lanes", "mma", "mma_dense", "cols", "wsm", "generic"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="loglik", choices=["loglik", "sim", "kalman"],
-                    help="loglik: config 5 (headline, default); sim: config 4 simulation smoother draws; "
+    ap.add_argument("--workload", default="all", choices=["all", "loglik", "sim", "kalman"],
+                    help="all (default): the config-5 loglik line (headline fields) with the sim and kalman lines attached "
+                         "under `workloads`; loglik: config 5 alone; sim: config 4 simulation smoother draws; "
                          "kalman: batched filter + smoother (KalmanC) of config-5 series")
     ap.add_argument("--kalman-series", type=int, default=2048, help="series per GPU (--workload kalman)")
     ap.add_argument("--kalman-e2e-series", type=int, default=256, help="series of the end-to-end leg (--workload kalman)")
@@ -888,15 +961,32 @@ def main():
     ap.add_argument("--nsim", type=int, default=NSIM_PER_GPU, help="draws per GPU (--workload sim)")
     ap.add_argument("--e2e-nsim", type=int, default=NSIM_PER_GPU, help="draws of the end-to-end leg (--workload sim)")
     ap.add_argument("--cpu-draws", type=int, default=128, help="draws per host thread of the CPU arm (--workload sim)")
+    ap.add_argument("--cpu-series", type=int, default=0, help="series of the CPU sample (0 = sized automatically)")
     args = ap.parse_args()
+    if args.impl == "reference":
+        run_sim_reference(args) if args.workload == "sim" else run_reference(args)
+        return
+    import torch.distributed as dist
     if args.workload == "sim":
-        run_sim_reference(args) if args.impl == "reference" else run_sim_gpu(args)
+        line = run_sim_gpu(args)
     elif args.workload == "kalman":
-        run_kalman_gpu(args)
-    elif args.impl == "reference":
-        run_reference(args)
+        line = run_kalman_gpu(args)
+    elif args.workload == "loglik":
+        line = run_gpu(args)
     else:
-        run_gpu(args)
+        # the headline line (config 5) carries the other two workloads of the path as sub-results, each with its own
+        # roofline, cpu_baseline and e2e; their step counts are bounded so that the default run stays within minutes
+        line = run_gpu(args)
+        sub = argparse.Namespace(**vars(args))
+        sub.steps, sub.warmup = min(args.steps, 5), min(args.warmup, 3)
+        sim = run_sim_gpu(sub)
+        kal = run_kalman_gpu(sub)
+        if line is not None:
+            line["workloads"] = {"sim": sim, "kalman": kal}
+    if line is not None:
+        print(json.dumps(line))
+    if dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -314,7 +314,7 @@ int ssgpu_plan_state_order(const double* T, int m, int* perm, unsigned* tile_mas
 /* The same for the block-row kernel (SSGPU_KERNEL_BLK): T m x m, R m x r, Q r x r or NULL (= diagonal), all
  * column-major.  *n_blocks = number of 2 x 2 blocks, or 0 when the model does not decompose (a state coupled with two
  * others through T or R Q R', more than 16 blocks, p > 8); perm[32]: internal position 2I+e -> state index of the
- * caller, -1 = padding; *lanes = lanes per evaluation; *flop_per_step = FP64 operations the kernel issues per series
+ * caller, -1 = padding; *lanes = lanes per evaluation of the lane kernel (the diffuse phase; with 5 to 8 blocks and p = 1 the regular phase runs one thread per evaluation); *flop_per_step = FP64 operations the kernel of the regular phase issues per series
  * and time step (fma = 2, all lanes). */
 int ssgpu_plan_blocks(const double* T, const double* R, const double* Q, int m, int r, int p, int* perm,
                       int* n_blocks, int* lanes, int* flop_per_step);

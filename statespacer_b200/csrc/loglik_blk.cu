@@ -875,6 +875,9 @@ extern "C" int ssgpu_plan_blocks(const double* T, const double* R, const double*
   if (perm)
     for (int i = 0; i < 2 * kBlkMaxNB; i++) perm[i] = pl.perm[i];
   if (lanes) *lanes = blk_lanes(pl.nb);
-  if (flop_per_step) *flop_per_step = blk_flops_per_step(pl.nb, p);
+  // what the automatic dispatch runs: 5 to 8 blocks with p = 1 go to the thread-per-evaluation kernel after the diffuse
+  // phase (time-invariant Z assumed here: the planner does not see Z)
+  if (flop_per_step)
+    *flop_per_step = thr_supported(pl.nb, p, false) ? thr_flops_per_step(pl.nb, pl.q_offdiag != 0) : blk_flops_per_step(pl.nb, p);
   return SSGPU_OK;
 }

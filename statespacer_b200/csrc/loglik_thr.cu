@@ -268,7 +268,13 @@ __global__ void __launch_bounds__(kThrThreads, 2) loglik_thr_kernel(const ThrArg
 
 // blocks above the diagonal that go to shared memory: what 255 registers do not hold next to s, the M being
 // accumulated and the temporaries of a block (sized with ptxas -v: no spill at these values)
-constexpr int thr_smem_blocks(int nb) { return nb == 8 ? 17 : nb == 7 ? 10 : nb == 6 ? 3 : 0; }
+#ifndef SSGPU_THR_S7
+#define SSGPU_THR_S7 10
+#endif
+#ifndef SSGPU_THR_S8
+#define SSGPU_THR_S8 17
+#endif
+constexpr int thr_smem_blocks(int nb) { return nb == 8 ? SSGPU_THR_S8 : nb == 7 ? SSGPU_THR_S7 : nb == 6 ? 3 : 0; }
 
 int thr_smem_blocks_host(int nb) { return thr_smem_blocks(nb); }
 

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libssgpu.so")
+# SSGPU_LIB: another build of the same library (A/B runs of kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("SSGPU_LIB") or os.path.join(_HERE, "libssgpu.so")
 _lib = None
 
 dp = C.POINTER(C.c_double)
