@@ -1,21 +1,29 @@
 # R-side glue for the GPU shim (replaces R/RcppExports.R of statespacer; same five stubs, same arguments --
 # R/RcppExports.R:11-99 -- plus the batched objective).  Not run in this repository's image (no R there).
 
+# The Rcpp signatures of the reference (NumericMatrix, arma::cube, LogicalMatrix: src/RcppExports.cpp:17-105) coerce
+# integer-typed arguments -- statespacer() never coerces y, and count data arrive as an integer matrix.  The C shim reads
+# REAL() / LOGICAL() directly, so the stubs do the coercion (dim and dimnames are kept by storage.mode<-).
+.d <- function(x) { if (!is.null(x) && !is.double(x)) storage.mode(x) <- "double"; x }
+.l <- function(x) { if (!is.logical(x)) storage.mode(x) <- "logical"; x }
+
 LogLikC <- function(y, y_isna, a, P_inf, P_star, Z, T, R, Q) {
-  .Call(`_statespacer_LogLikC`, y, y_isna, a, P_inf, P_star, Z, T, R, Q)
+  .Call(`_statespacer_LogLikC`, .d(y), .l(y_isna), .d(a), .d(P_inf), .d(P_star), .d(Z), .d(T), .d(R), .d(Q))
 }
 KalmanC <- function(y, y_isna, a, P_inf, P_star, Z, T, R, Q, diagnostics) {
-  .Call(`_statespacer_KalmanC`, y, y_isna, a, P_inf, P_star, Z, T, R, Q, diagnostics)
+  .Call(`_statespacer_KalmanC`, .d(y), .l(y_isna), .d(a), .d(P_inf), .d(P_star), .d(Z), .d(T), .d(R), .d(Q),
+        as.logical(diagnostics))
 }
 FastSmootherC <- function(y, a, P_inf, P_star, Z, T, R, Q, initialisation_steps, transposed_state) {
-  .Call(`_statespacer_FastSmootherC`, y, a, P_inf, P_star, Z, T, R, Q, initialisation_steps, transposed_state)
+  .Call(`_statespacer_FastSmootherC`, .d(y), .d(a), .d(P_inf), .d(P_star), .d(Z), .d(T), .d(R), .d(Q),
+        as.integer(initialisation_steps), as.logical(transposed_state))
 }
 SimulateC <- function(nsim, repeat_Q, N, a, Z, T, R, Q, P_star, draw_initial, eta_only, transposed_state) {
-  .Call(`_statespacer_SimulateC`, nsim, repeat_Q, N, a, Z, T, R, Q, P_star, draw_initial, eta_only,
-        transposed_state)
+  .Call(`_statespacer_SimulateC`, as.integer(nsim), as.integer(repeat_Q), as.integer(N), .d(a), .d(Z), .d(T), .d(R),
+        .d(Q), .d(P_star), as.logical(draw_initial), as.logical(eta_only), as.logical(transposed_state))
 }
 ExtractComponentC <- function(a, Z) {
-  .Call(`_statespacer_ExtractComponentC`, a, Z)
+  .Call(`_statespacer_ExtractComponentC`, .d(a), .d(Z))
 }
 
 #' Batched loglikelihood: B series x V parameter vectors in one launch.
@@ -27,8 +35,10 @@ ExtractComponentC <- function(a, Z) {
 #'   (column e = (v-1)*B + b), or NULL for the shared Q / P_star of the system matrices.
 #' @return B x V matrix of loglik / N (NA where LogLikC would return NA).
 LogLikBatchC <- function(Y, V, a, P_inf, P_star, Z, T, R, Q, Q_diag = NULL, P_star_diag = NULL) {
+  Y <- .d(Y)
   Y[is.na(Y)] <- NaN
-  .Call(`_statespacer_LogLikBatchC`, Y, as.integer(V), a, P_inf, P_star, Z, T, R, Q, Q_diag, P_star_diag)
+  .Call(`_statespacer_LogLikBatchC`, Y, as.integer(V), .d(a), .d(P_inf), .d(P_star), .d(Z), .d(T), .d(R), .d(Q),
+        .d(Q_diag), .d(P_star_diag))
 }
 
 #' Objective + central-difference gradient for optim(gr = ...) from ONE launch (replaces the 2k sequential
@@ -39,7 +49,9 @@ loglik_and_gradient <- function(theta, y, sysmat, sysmat_diag, h = 1e-3) {
   thetas <- cbind(theta, do.call(cbind, lapply(seq_len(k), function(i) {
     e <- replace(numeric(k), i, h); cbind(theta + e, theta - e) })))
   d <- lapply(seq_len(ncol(thetas)), function(j) sysmat_diag(thetas[, j]))
-  ll <- LogLikBatchC(matrix(y, nrow = 1), ncol(thetas), sysmat$a, sysmat$P_inf, sysmat$P_star, sysmat$Z, sysmat$T,
+  # one row per series with the p observations of a time point ADJACENT (index t * p + j): y is N x p, stored
+  # column-major (t + N * j), so the row is t(y) flattened -- matrix(y, nrow = 1) would scramble a multivariate y
+  ll <- LogLikBatchC(matrix(t(as.matrix(y)), nrow = 1), ncol(thetas), sysmat$a, sysmat$P_inf, sysmat$P_star, sysmat$Z, sysmat$T,
                      sysmat$R, sysmat$Q, Q_diag = sapply(d, `[[`, "Q"), P_star_diag = sapply(d, `[[`, "P_star"))
   list(value = ll[1, 1], gradient = (ll[1, seq(2, 2 * k, 2)] - ll[1, seq(3, 2 * k + 1, 2)]) / (2 * h))
 }
@@ -52,9 +64,11 @@ loglik_and_gradient <- function(theta, y, sysmat, sysmat_diag, h = 1e-3) {
 #' @param Y B x (N*p) matrix as for LogLikBatchC; @param theta k x B matrix.
 #' @return list(value = numeric(B), gradient = k x B matrix), both of loglik / N.
 LogLikGradBatchC <- function(Y, theta, q_index, p_star_index, sysmat, h = 1e-3) {
+  Y <- .d(Y)
   Y[is.na(Y)] <- NaN
-  .Call(`_statespacer_LogLikGradBatchC`, Y, as.matrix(theta), as.integer(q_index) - 1L, as.integer(p_star_index) - 1L,
-        as.numeric(h), sysmat$a, sysmat$P_inf, sysmat$P_star, sysmat$Z, sysmat$T, sysmat$R, sysmat$Q)
+  .Call(`_statespacer_LogLikGradBatchC`, Y, .d(as.matrix(theta)), as.integer(q_index) - 1L,
+        as.integer(p_star_index) - 1L, as.numeric(h), .d(sysmat$a), .d(sysmat$P_inf), .d(sysmat$P_star), .d(sysmat$Z),
+        .d(sysmat$T), .d(sysmat$R), .d(sysmat$Q))
 }
 
 #' SimSmoother() as one device-resident call (replaces the body of R/SimSmoother.R:53-766).

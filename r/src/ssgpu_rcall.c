@@ -39,12 +39,33 @@ static void dims3(SEXP x, int* r, int* c, int* s) {
   }
 }
 
+/* The reference's Rcpp signatures (NumericMatrix, arma::cube, LogicalMatrix) coerce what they are handed; REAL() /
+ * LOGICAL() / INTEGER() on a vector of another type is undefined behaviour.  The R stubs (r/R/ssgpu_glue.R) coerce
+ * with storage.mode<-; a caller that reaches .Call directly with an integer matrix gets an R error here instead. */
+static void need(SEXP x, SEXPTYPE type, const char* what) {
+  if (x != R_NilValue && TYPEOF(x) != type)
+    Rf_error("libssgpu shim: argument `%s` must be of type %s (the stubs of ssgpu_glue.R coerce it)", what,
+             type == REALSXP ? "double" : type == LGLSXP ? "logical" : "integer");
+}
+static void need_model(SEXP a, SEXP P_inf, SEXP P_star, SEXP Z, SEXP T, SEXP R, SEXP Q) {
+  need(a, REALSXP, "a"); need(P_inf, REALSXP, "P_inf"); need(P_star, REALSXP, "P_star"); need(Z, REALSXP, "Z");
+  need(T, REALSXP, "T"); need(R, REALSXP, "R"); need(Q, REALSXP, "Q");
+  int m, mc, ms, im, imc, ims, zr, zc, nZ, tr, tc, nT, rr, r, nR, qr, qc, nQ;
+  dims3(P_star, &m, &mc, &ms); dims3(P_inf, &im, &imc, &ims); dims3(Z, &zr, &zc, &nZ); dims3(T, &tr, &tc, &nT);
+  dims3(R, &rr, &r, &nR); dims3(Q, &qr, &qc, &nQ);
+  /* Armadillo throws on these in the reference (src/LogLikC.cpp:101,202); here they would be out-of-bounds reads */
+  if (mc != m || im != m || imc != m || Rf_length(a) != m || zc != m || tr != m || tc != m || rr != m || qr != r || qc != r)
+    Rf_error("libssgpu shim: non-conformable system matrices (m = %d: a %d, P_inf %d x %d, Z . x %d, T %d x %d, R %d x %d, Q %d x %d)",
+             m, Rf_length(a), im, imc, zc, tr, tc, rr, r, qr, qc);
+}
+
 static SEXP alloc3(int a, int b, int c) {
   SEXP x = PROTECT(Rf_alloc3DArray(REALSXP, a, b, c));
   return x;
 }
 
 SEXP _statespacer_LogLikC(SEXP y, SEXP y_isna, SEXP a, SEXP P_inf, SEXP P_star, SEXP Z, SEXP T, SEXP R, SEXP Q) {
+  need(y, REALSXP, "y"); need(y_isna, LGLSXP, "y_isna"); need_model(a, P_inf, P_star, Z, T, R, Q);
   int N, p, one, m, mc, ms, zr, zc, nZ, tr, tc, nT, rr, r, nR, qr, qc, nQ;
   dims3(y, &N, &p, &one);
   dims3(P_star, &m, &mc, &ms);
@@ -60,6 +81,7 @@ SEXP _statespacer_LogLikC(SEXP y, SEXP y_isna, SEXP a, SEXP P_inf, SEXP P_star, 
 
 SEXP _statespacer_KalmanC(SEXP y, SEXP y_isna, SEXP a, SEXP P_inf, SEXP P_star, SEXP Z, SEXP T, SEXP R, SEXP Q,
                           SEXP diagnostics) {
+  need(y, REALSXP, "y"); need(y_isna, LGLSXP, "y_isna"); need_model(a, P_inf, P_star, Z, T, R, Q);
   int N, p, one, m, mc, ms, zr, zc, nZ, tr, tc, nT, rr, r, nR, qr, qc, nQ, np = 0;
   dims3(y, &N, &p, &one);
   dims3(P_star, &m, &mc, &ms);
@@ -143,6 +165,7 @@ SEXP _statespacer_KalmanC(SEXP y, SEXP y_isna, SEXP a, SEXP P_inf, SEXP P_star, 
 
 SEXP _statespacer_FastSmootherC(SEXP y, SEXP a, SEXP P_inf, SEXP P_star, SEXP Z, SEXP T, SEXP R, SEXP Q,
                                 SEXP initialisation_steps, SEXP transposed_state) {
+  need(y, REALSXP, "y"); need_model(a, P_inf, P_star, Z, T, R, Q);
   int N, p, nsim, m, mc, ms, zr, zc, nZ, tr, tc, nT, rr, r, nR, qr, qc, nQ;
   dims3(y, &N, &p, &nsim);
   dims3(P_star, &m, &mc, &ms);
@@ -166,6 +189,8 @@ SEXP _statespacer_FastSmootherC(SEXP y, SEXP a, SEXP P_inf, SEXP P_star, SEXP Z,
 
 SEXP _statespacer_SimulateC(SEXP nsim_, SEXP repeat_Q_, SEXP N_, SEXP a, SEXP Z, SEXP T, SEXP R, SEXP Q, SEXP P_star,
                             SEXP draw_initial_, SEXP eta_only_, SEXP transposed_state_) {
+  need(a, REALSXP, "a"); need(Z, REALSXP, "Z"); need(T, REALSXP, "T"); need(R, REALSXP, "R"); need(Q, REALSXP, "Q");
+  need(P_star, REALSXP, "P_star");
   const int nsim = Rf_asInteger(nsim_), repeat_Q = Rf_asInteger(repeat_Q_), N = Rf_asInteger(N_);
   const int draw_initial = Rf_asLogical(draw_initial_), eta_only = Rf_asLogical(eta_only_),
             tst = Rf_asLogical(transposed_state_);
@@ -201,6 +226,7 @@ SEXP _statespacer_SimulateC(SEXP nsim_, SEXP repeat_Q_, SEXP N_, SEXP a, SEXP Z,
 }
 
 SEXP _statespacer_ExtractComponentC(SEXP a, SEXP Z) {
+  need(a, REALSXP, "a"); need(Z, REALSXP, "Z");
   int m, nsim, N, p, zc, nZ;
   dims3(a, &m, &nsim, &N);
   dims3(Z, &p, &zc, &nZ);
@@ -217,6 +243,8 @@ SEXP _statespacer_ExtractComponentC(SEXP a, SEXP Z) {
  * per-evaluation diagonals (evaluation e = v*B + b), or NULL to use the shared Q / P_star. */
 SEXP _statespacer_LogLikBatchC(SEXP yt, SEXP V_, SEXP a, SEXP P_inf, SEXP P_star, SEXP Z, SEXP T, SEXP R, SEXP Q,
                                SEXP Q_diag, SEXP P_star_diag) {
+  need(yt, REALSXP, "Y"); need_model(a, P_inf, P_star, Z, T, R, Q); need(Q_diag, REALSXP, "Q_diag");
+  need(P_star_diag, REALSXP, "P_star_diag");
   int B, Np, one, m, mc, ms, p, zc, nZ, tr, tc, nT, rr, r, nR, qr, qc, nQ;
   const int V = Rf_asInteger(V_);
   dims3(yt, &B, &Np, &one); /* B x (N*p): element [b + B*q] = y_b[q]  == y[q*B + b] */
@@ -252,6 +280,8 @@ SEXP _statespacer_LogLikBatchC(SEXP yt, SEXP V_, SEXP a, SEXP P_inf, SEXP P_star
  * the entry of the shared matrix).  Returns list(value = numeric(B), gradient = k x B matrix). */
 SEXP _statespacer_LogLikGradBatchC(SEXP yt, SEXP theta, SEXP q_index, SEXP p_star_index, SEXP h_, SEXP a, SEXP P_inf,
                                    SEXP P_star, SEXP Z, SEXP T, SEXP R, SEXP Q) {
+  need(yt, REALSXP, "Y"); need(theta, REALSXP, "theta"); need(q_index, INTSXP, "q_index");
+  need(p_star_index, INTSXP, "p_star_index"); need_model(a, P_inf, P_star, Z, T, R, Q);
   int B, Np, one, m, mc, ms, p, zc, nZ, tr, tc, nT, rr, r, nR, qr, qc, nQ, k, Bt, one2;
   dims3(yt, &B, &Np, &one);
   dims3(theta, &k, &Bt, &one2);

@@ -126,7 +126,7 @@ class DevBuf {
 
 // ---- large host <-> device copies through pinned staging when the host side is pageable (xfer.cu) ----------
 int copy_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st);   // returns when dst holds the data
-int copy_h2d(void* dst_dev, const void* src, size_t bytes, cudaStream_t st);   // src may be re-used on return
+int copy_h2d(void* dst_dev, const void* src, size_t bytes, cudaStream_t st);   // pinned src: valid until st is synchronised
 void xfer_release();
 bool host_is_pinned(const void* p);
 

@@ -105,7 +105,9 @@ int copy_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st) {
   return SSGPU_OK;
 }
 
-// dst (device) <- src (host); the copy is enqueued on st and src may be re-used when the call returns
+// dst (device) <- src (host), enqueued on st.  Pageable src: staged through the pinned ring, src may be re-used when the
+// call returns.  Pinned / registered src (and small copies): a plain cudaMemcpyAsync -- src must stay valid and unchanged
+// until st is synchronised (every entry point of the library synchronises before it returns to its caller).
 int copy_h2d(void* dst_dev, const void* src, size_t bytes, cudaStream_t st) {
   if (bytes == 0) return SSGPU_OK;
   if (bytes < kMinStaged || !is_pageable(src)) {

@@ -16,14 +16,23 @@ from dataclasses import dataclass
 from . import api
 
 
+# per-series outcome of fit_batch (stats::optim reports a convergence code as well; R/statespacer.R:984-997 prints it)
+CONVERGED, ITERATION_LIMIT, LINE_SEARCH_FAILED, NON_FINITE = 0, 1, 2, 3
+
+
 @dataclass
 class FitResult:
-    theta: "torch.Tensor"       # (B, k) parameters at the optimum
+    theta: "torch.Tensor"       # (B, k) parameters at the optimum (multistart: of the best start)
     loglik: "torch.Tensor"      # (B,)  loglik / N there (what LogLikC returns)
     grad: "torch.Tensor"        # (B, k) central-difference gradient there
     iterations: int
-    converged: "torch.Tensor"   # (B,) bool: max |grad| < gtol or no candidate improved
+    converged: "torch.Tensor"   # (B,) bool: status == CONVERGED (max |grad| < gtol)
     evaluations: int            # filter runs per series (for the series*timesteps bookkeeping)
+    status: "torch.Tensor" = None   # (B,) int: CONVERGED, ITERATION_LIMIT, LINE_SEARCH_FAILED (no candidate improved,
+                                    # also after the inverse Hessian was reset to the identity), NON_FINITE (objective
+                                    # not finite at the start values)
+    start: "torch.Tensor" = None    # (B,) multistart: index of the start that won; None for a single start
+    loglik_starts: "torch.Tensor" = None  # (S, B) multistart: loglik / N reached from every start
 
 
 def fit_batch(y, model, theta0, q_index, p_star_index, max_iter=60, h=1e-3, gtol=1e-5, kernel="auto",
@@ -31,20 +40,46 @@ def fit_batch(y, model, theta0, q_index, p_star_index, max_iter=60, h=1e-3, gtol
     """Maximise loglik / N over theta for every series of the batch (BFGS, backtracking line search).
 
     y (N, B) or (N, p, B) CUDA float64 tensor, `model` an api.BatchModel built with device=... (shared matrices),
-    theta0 (B, k) CUDA tensor of start values, q_index / p_star_index as for api.loglik_grad_batch_dev."""
+    theta0 (B, k) CUDA tensor of start values, q_index / p_star_index as for api.loglik_grad_batch_dev.
+    theta0 of shape (S, B, k): MULTISTART -- S start vectors per series, all S x B optimisations advance in lock-step
+    and share the launches (the S (1 + 2k) gradient points and the S line searches of a series are parameter vectors of
+    that series: y is read once for all of them), the best start per series is returned."""
     import torch
 
-    B, k = theta0.shape
+    multi = theta0.dim() == 3
+    S = theta0.shape[0] if multi else 1
+    B, k = theta0.shape[-2:]
     dev = theta0.device
-    theta = theta0.clone()
-    eye = torch.eye(k, device=dev, dtype=torch.float64).expand(B, k, k)
+    theta = theta0.reshape(S * B, k).clone()                     # row s * B + b
+    n_rows = S * B
+    eye = torch.eye(k, device=dev, dtype=torch.float64).expand(n_rows, k, k)
     H = eye.clone()                                               # inverse-Hessian approximation of -loglik
     alphas = torch.tensor(steps, device=dev, dtype=torch.float64)
     L = alphas.numel()
-    ll, gr = api.loglik_grad_batch_dev(y, model, theta, q_index, p_star_index, h=h, kernel=kernel)
+    offs = torch.zeros(1 + 2 * k, k, device=dev, dtype=torch.float64)
+    for i in range(k):
+        offs[1 + 2 * i, i], offs[2 + 2 * i, i] = h, -h
+
+    def theta_batch(pts):                                         # pts (V, S * B, k) -> (V, S * B): one launch
+        V = pts.shape[0]
+        if not multi:
+            return api.loglik_theta_batch_dev(y, model, pts.contiguous(), q_index, p_star_index, kernel=kernel)
+        arranged = pts.reshape(V, S, B, k).reshape(V * S, B, k).contiguous()
+        return api.loglik_theta_batch_dev(y, model, arranged, q_index, p_star_index, kernel=kernel).reshape(V, S * B)
+
+    def value_grad(th):
+        if not multi:                                             # variance sets and differences formed on the device
+            return api.loglik_grad_batch_dev(y, model, th, q_index, p_star_index, h=h, kernel=kernel)
+        fv = theta_batch(th[None] + offs[:, None, :])
+        return fv[0], ((fv[1::2] - fv[2::2]) / (2.0 * h)).transpose(0, 1).contiguous()
+
+    ll, gr = value_grad(theta)
     f, g = -ll, -gr
     n_eval = 1 + 2 * k
+    status = torch.full((n_rows,), ITERATION_LIMIT, device=dev, dtype=torch.int64)
+    status[~torch.isfinite(f)] = NON_FINITE
     done = ~torch.isfinite(f)
+    reset = torch.zeros(n_rows, device=dev, dtype=torch.bool)     # H already reset to the identity after a failed search
     it = 0
     for it in range(1, max_iter + 1):
         d = -torch.bmm(H, g.unsqueeze(2)).squeeze(2)
@@ -57,8 +92,8 @@ def fit_batch(y, model, theta0, q_index, p_star_index, max_iter=60, h=1e-3, gtol
         scale = torch.clamp(max_step / d.abs().amax(1).clamp_min(1e-300), max=1.0)   # variances are exp(2 theta)
         d = d * scale[:, None]
         slope = slope * scale
-        cand = theta[None] + alphas[:, None, None] * d[None]      # (L, B, k)
-        fc = -api.loglik_theta_batch_dev(y, model, cand.contiguous(), q_index, p_star_index, kernel=kernel)
+        cand = theta[None] + alphas[:, None, None] * d[None]      # (L, rows, k)
+        fc = -theta_batch(cand)
         n_eval += L
         fc = torch.where(torch.isfinite(fc), fc, torch.full_like(fc, float("inf")))
         armijo = fc <= f[None] + c1 * alphas[:, None] * slope[None]
@@ -67,7 +102,7 @@ def fit_batch(y, model, theta0, q_index, p_star_index, max_iter=60, h=1e-3, gtol
         improved = (f_new < f) & ~done
         a_sel = alphas[first]
         theta_new = torch.where(improved[:, None], theta + a_sel[:, None] * d, theta)
-        ll_new, gr_new = api.loglik_grad_batch_dev(y, model, theta_new, q_index, p_star_index, h=h, kernel=kernel)
+        ll_new, gr_new = value_grad(theta_new)
         n_eval += 1 + 2 * k
         g_new = -gr_new
         s = theta_new - theta
@@ -79,10 +114,29 @@ def fit_batch(y, model, theta0, q_index, p_star_index, max_iter=60, h=1e-3, gtol
         H_new = torch.bmm(torch.bmm(I_rsy, H), I_rsy.transpose(1, 2)) + rho[:, None, None] * s.unsqueeze(2) * s.unsqueeze(1)
         H = torch.where(upd[:, None, None], H_new, H)
         theta, f, g = theta_new, torch.where(improved, -ll_new, f), torch.where(improved[:, None], g_new, g)
-        done = done | ~improved | (g.abs().amax(1) < gtol)
+        small = g.abs().amax(1) < gtol
+        failed = ~improved & ~done & ~small
+        # a search that found nothing along the BFGS direction gets one more along the gradient (H := I) before the
+        # series is given up; a second failure in a row is final
+        give_up = failed & reset
+        retry = failed & ~reset
+        H = torch.where(retry[:, None, None], eye, H)
+        reset = (reset | retry) & ~improved
+        status = torch.where(small & ~done, torch.full_like(status, CONVERGED), status)
+        status = torch.where(give_up, torch.full_like(status, LINE_SEARCH_FAILED), status)
+        done = done | small | give_up
         if bool(done.all()):
             break
-    return FitResult(theta=theta, loglik=-f, grad=-g, iterations=it, converged=done, evaluations=n_eval)
+    if not multi:
+        return FitResult(theta=theta, loglik=-f, grad=-g, iterations=it, converged=status == CONVERGED,
+                         evaluations=n_eval, status=status)
+    fs = torch.where(torch.isfinite(f), f, torch.full_like(f, float("inf"))).reshape(S, B)
+    best = fs.argmin(0)
+    pick = lambda x: x.reshape((S, B) + x.shape[1:]).gather(
+        0, best.reshape((1, B) + (1,) * (x.dim() - 1)).expand((1, B) + x.shape[1:])).squeeze(0)
+    st = pick(status)
+    return FitResult(theta=pick(theta), loglik=-pick(f), grad=-pick(g), iterations=it, converged=st == CONVERGED,
+                     evaluations=S * n_eval, status=st, start=best, loglik_starts=-fs)
 
 
 def hessian_batch(y, model, theta, q_index, p_star_index, h=1e-2, kernel="auto"):

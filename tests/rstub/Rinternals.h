@@ -13,6 +13,7 @@ extern SEXP R_NilValue, R_DimSymbol, R_NamesSymbol;
 extern double R_NaReal, R_NaN;
 #define NA_REAL R_NaReal
 #define ISNAN(x) ((x) != (x))
+int TYPEOF(SEXP);
 double* REAL(SEXP);
 int* INTEGER(SEXP);
 int* LOGICAL(SEXP);

@@ -557,6 +557,26 @@ def test_fit_batch_bfgs():
         ref_opt = minimize(obj, start[b].cpu().numpy(), method="BFGS", options={"gtol": 1e-6, "eps": 1e-3})
         assert ll[b] >= -ref_opt.fun - 5e-5 * max(1.0, abs(ref_opt.fun)), (b, ll[b], -ref_opt.fun)
     assert res.evaluations == (1 + 2 * k) * (res.iterations + 1) + 7 * res.iterations
+    # every series carries an outcome code; `converged` means the gradient test was met, nothing else
+    st = res.status.cpu().numpy()
+    assert set(st.tolist()) <= {fit.CONVERGED, fit.ITERATION_LIMIT, fit.LINE_SEARCH_FAILED}
+    assert np.array_equal(res.converged.cpu().numpy(), st == fit.CONVERGED)
+    gmax = res.grad.abs().amax(1).cpu().numpy()
+    assert np.all(gmax[st == fit.CONVERGED] < 1e-5)
+    # multistart: three start vectors per series advance in lock-step in the same launches; the winner per series is at
+    # least as good as the single start from above (which is one of the three), and every start's value is reported
+    starts = torch.stack([start, start + 0.7, torch.from_numpy(truth).to(dev)])
+    ms = fit.fit_batch(y_d, model, starts, BSM_Q_INDEX, BSM_P_INDEX, max_iter=80)
+    assert ms.loglik_starts.shape == (3, B) and ms.start.shape == (B,)
+    best = ms.loglik.cpu().numpy()
+    assert np.allclose(best, ms.loglik_starts.max(0).values.cpu().numpy(), rtol=0, atol=0)
+    assert np.all(best >= ll - 2e-5 * np.maximum(1.0, np.abs(ll)))
+    chk, _ = api.loglik_grad_batch_dev(y_d, model, ms.theta, BSM_Q_INDEX, BSM_P_INDEX)    # theta and value belong together
+    assert np.allclose(chk.cpu().numpy(), best, rtol=1e-12, atol=1e-12)
+    bad = start.clone()
+    bad[3] = float("nan")                                        # a start the objective cannot be evaluated at
+    rb = fit.fit_batch(y_d, model, bad, BSM_Q_INDEX, BSM_P_INDEX, max_iter=5)
+    assert int(rb.status[3]) == fit.NON_FINITE and not bool(rb.converged[3])
 
 
 def test_hessian_batch():
@@ -1292,3 +1312,22 @@ def test_config4_shards_concatenate_to_one_call():
     o1 = cport.SimulateC(k0, 1, N, np.zeros(mc), c["Z"], c["T"], c["R"], c["Q"], np.zeros((mc, mc)), False, False, True,
                          e1[:, :k0].contiguous().view(-1).cpu().numpy())
     assert np.array_equal(o1["a"], whole[0][:, :, :k0].cpu().numpy())
+
+
+def test_r_glue_row_layout_multivariate():
+    """r/R/ssgpu_glue.R loglik_and_gradient() hands LogLikBatchC one row per series, matrix(t(y), nrow = 1): R stores the
+    N x p matrix y column-major (t + N j), so t(y) flattened has observation (t, j) at t p + j -- the time-major layout
+    the batched kernels read.  Emulated here for p = 2 (a plain matrix(y, nrow = 1) puts (t, j) at t + N j and gives a
+    different, wrong, value)."""
+    rng = np.random.default_rng(17)
+    N, p, m = 30, 2, 5
+    sm = random_model(rng, m, p, d=1, N=N)
+    y = simulate_y(rng, sm, N, missing=0.1)                       # (N, p)
+    r_storage = np.asfortranarray(y).ravel(order="F")            # what R holds for y
+    row_t = np.asfortranarray(y.T).ravel(order="F")              # matrix(t(y), nrow = 1)
+    assert np.array_equal(row_t, y.reshape(-1), equal_nan=True)  # index t * p + j
+    want, tol = loglik_want(y, np.isnan(y), *sm.args())
+    got = api.loglik_batch(row_t.reshape(N, p, 1), sm)[0]
+    assert abs(got - want) <= tol
+    wrong = api.loglik_batch(r_storage.reshape(N, p, 1), sm)[0]   # matrix(y, nrow = 1): observations scrambled
+    assert not abs(wrong - want) <= 1e-6 * abs(want)
