@@ -363,6 +363,8 @@ def run_gpu(args):
 
     world, rank, local, dev = gpu_setup()
     B = args.series
+    if args.scaling == "strong":           # a fixed job (--series-total, default 1M series = config 5) cut into world shards
+        B = args.series_total // world
     sm, y, theta = make_shard(torch, dev, B, rank)
     if args.missing > 0:
         g = torch.Generator(device=dev)
@@ -486,6 +488,41 @@ def run_gpu(args):
     e2e_pageable_value = units_per_step * e2e_steps / e2e_p_s
     e2e_pageable_match = bool(np.array_equal(ll_p, ll_h.numpy()) and np.array_equal(gr_p, gr_h.numpy()))
 
+    # ONE process driving several GPUs through the C ABI (ssgpu_use_devices): what an R session can do.  Weak scaling:
+    # args.single_process devices x B series, host arrays pinned, results written straight into the caller's arrays.
+    sp = None
+    if world == 1 and args.single_process > 1:
+        nd = api.use_devices(args.single_process)
+        Bt = B * nd
+        y_all = torch.empty(T_STEPS, Bt, dtype=torch.float64, pin_memory=True)
+        th_all = torch.empty(Bt, K_PAR, dtype=torch.float64, pin_memory=True)
+        for d in range(nd):                    # the same shard on every device: results must repeat bit for bit
+            y_all[:, d * B:(d + 1) * B].copy_(y_h)
+            th_all[d * B:(d + 1) * B].copy_(th_h)
+        ll_all = torch.empty(Bt, dtype=torch.float64, pin_memory=True)
+        gr_all = torch.empty(Bt, K_PAR, dtype=torch.float64, pin_memory=True)
+        big = api.BatchModel(sm, T_STEPS, Bt, 1)
+
+        def sp_step():
+            native.check(native.lib().ssgpu_loglik_grad_batch(y_all.data_ptr(), Bt, C.byref(big.c), th_all.data_ptr(), K_PAR,
+                                                              qi.ctypes.data, pi.ctypes.data, H_FD,
+                                                              api._KERNELS[args.kernel], ll_all.data_ptr(), gr_all.data_ptr()))
+
+        sp_step()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            sp_step()
+        sp_s = time.perf_counter() - t0
+        same = all(bool(torch.equal(ll_all[d * B:(d + 1) * B], ll_h)) and bool(torch.equal(gr_all[d * B:(d + 1) * B], gr_h))
+                   for d in range(nd))
+        sp = {"n_devices": nd, "value": Bt * V * T_STEPS * e2e_steps / sp_s, "unit": UNIT, "steps": e2e_steps,
+              "series_total": Bt, "every_device_bit_identical_to_single_device": same,
+              "h2d_bytes_per_step": y_all.numel() * 8 + th_all.numel() * 8, "d2h_bytes_per_step": (Bt + Bt * K_PAR) * 8,
+              "note": "ssgpu_use_devices + ssgpu_loglik_grad_batch from one process: one worker thread, stream and staging "
+                      "ring per device, no collective"}
+        api.use_devices(1)
+        del y_all, th_all
+
     if rank == 0:
         flops = f_alg(M, 1) * B * V * T_STEPS
         achieved = flops / (kernel_ms * 1e-3) / 1e12
@@ -513,7 +550,7 @@ def run_gpu(args):
         traffic = committed_traffic("loglik_thr_kernel" if thr else kernel_name.split("<")[0], grid) if grid else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config(world, B, {"kernel": kernel_name, "missing_fraction": args.missing,
                                             "results_finite": finite}),
                 "clocks": clocks,
@@ -522,7 +559,8 @@ def run_gpu(args):
                         "pageable": {"value": e2e_pageable_value, "unit": UNIT, "steps": e2e_steps,
                                      "bit_identical_to_pinned": e2e_pageable_match,
                                      "note": "the same call on pageable host arrays (what R passes): staged through "
-                                             "the library's ring of pinned buffers"}},
+                                             "the library's ring of pinned buffers"},
+                        "single_process_multi_gpu": sp},
                 "gpu_launches": launches,
                 "roofline": {"bound": "fp64", "kernel": kernel_name,
                              "achieved": executed if executed else achieved, "peak": peak_tf, "unit": "TFLOP/s",
@@ -961,6 +999,11 @@ def main():
     ap.add_argument("--nsim", type=int, default=NSIM_PER_GPU, help="draws per GPU (--workload sim)")
     ap.add_argument("--e2e-nsim", type=int, default=NSIM_PER_GPU, help="draws of the end-to-end leg (--workload sim)")
     ap.add_argument("--cpu-draws", type=int, default=128, help="draws per host thread of the CPU arm (--workload sim)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): --series per GPU; strong: --series-total series cut into one shard per GPU")
+    ap.add_argument("--series-total", type=int, default=1_000_000, help="series of the whole job (--scaling strong)")
+    ap.add_argument("--single-process", type=int, default=0,
+                    help="also time the end-to-end call from ONE process on this many GPUs (ssgpu_use_devices; --gpus 1 only)")
     ap.add_argument("--cpu-series", type=int, default=0, help="series of the CPU sample (0 = sized automatically)")
     args = ap.parse_args()
     if args.impl == "reference":

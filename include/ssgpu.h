@@ -42,6 +42,14 @@ int ssgpu_version(void);                     /* 100*major + minor */
 const char* ssgpu_last_error(void);          /* thread-local, never NULL */
 int ssgpu_set_device(int device);            /* device used by subsequent calls of this process */
 int ssgpu_device_count(int* count);
+/* Multi-GPU from ONE process (R is one process: R/statespacer.R:977-982 calls the objective from the main R thread).
+ * n devices starting at the one of ssgpu_set_device (n <= 0: all visible).  The host-pointer batch entry point
+ * ssgpu_loglik_grad_batch then shards its series over them in contiguous ranges -- one worker thread, stream and pinned
+ * staging ring per device; every device writes its series' results straight into the caller's arrays (the recursion has
+ * no exchange step: nothing is gathered, no collective is needed).  Results are bit-identical to the single-device call.
+ * The `_dev` entry points stay on the device of ssgpu_set_device. */
+int ssgpu_use_devices(int n);
+int ssgpu_devices_in_use(int* n);
 int ssgpu_release(void);                     /* free cached device workspaces and pinned staging */
 /* number of kernels this library launched since process start (bench.py's gpu_launches) */
 long long ssgpu_launch_count(void);

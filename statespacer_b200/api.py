@@ -58,6 +58,14 @@ def _prep(a, P_inf, P_star, Z, T, R, Q):
     return a, _f(P_inf), _f(P_star), _cube(Z, "Z"), _cube(T, "T"), _cube(R, "R"), _cube(Q, "Q")
 
 
+def use_devices(n=0):
+    """Shard the host-pointer batch entry points over n devices of this process (0 = all visible); returns the count."""
+    native.check(native.lib().ssgpu_use_devices(int(n)))
+    out = C.c_int(0)
+    native.check(native.lib().ssgpu_devices_in_use(C.byref(out)))
+    return out.value
+
+
 def last_kernel() -> str:
     return native.lib().ssgpu_last_kernel().decode()
 

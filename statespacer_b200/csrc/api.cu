@@ -2,7 +2,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <functional>
 #include <mutex>
+#include <thread>
 
 #include "common.cuh"
 
@@ -13,9 +15,20 @@ static thread_local std::string g_err;
 static thread_local const char* g_last_kernel = "";
 static std::atomic<long long> g_launches{0};
 static std::mutex g_mu;
-static cudaStream_t g_stream = nullptr;
-static int g_device = 0;
+// One context per device the process uses.  Slot 0 is the device of ssgpu_set_device (the only one unless
+// ssgpu_use_devices asks for more); the host-pointer batch entry points then shard their series / draws over the slots
+// with one worker thread per device.  A thread works on the slot named by t_slot (0 for every caller thread).
+constexpr int kMaxDev = 16;
+struct DevCtx {
+  int device = -1;
+  cudaStream_t stream = nullptr, copy = nullptr;
+  bool ready = false;
+};
+static DevCtx g_ctx[kMaxDev];
+static int g_device = 0;    // device of slot 0
+static int g_n_use = 1;     // slots the sharded entry points use
 static bool g_ready = false;
+static thread_local int t_slot = 0;
 
 void set_error(const std::string& msg) { g_err = msg; }
 void count_launch(int n) { g_launches += n; }
@@ -29,10 +42,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return SSGPU_E_CUDA;
 }
 
+int dev_slot() { return t_slot; }
+
 int ensure_device() {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_ready) {
-    SS_CUDA(cudaSetDevice(g_device));
+  DevCtx& c = g_ctx[t_slot];
+  if (c.ready) {
+    SS_CUDA(cudaSetDevice(c.device));
     return SSGPU_OK;
   }
   int n = 0;
@@ -42,17 +58,59 @@ int ensure_device() {
     g_err = "no CUDA device available (libssgpu has no CPU fallback)";
     return SSGPU_E_CUDA;
   }
-  SS_CUDA(cudaSetDevice(g_device));
-  SS_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  c.device = (g_device + t_slot) % n;
+  SS_CUDA(cudaSetDevice(c.device));
+  SS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  SS_CUDA(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
   cudaMemPool_t pool;
-  SS_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_device));
+  SS_CUDA(cudaDeviceGetDefaultMemPool(&pool, c.device));
   unsigned long long thr = ~0ULL;  // keep freed blocks cached in the pool
   SS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-  g_ready = true;
+  c.ready = true;
+  if (t_slot == 0) g_ready = true;
   return SSGPU_OK;
 }
 
-cudaStream_t lib_stream() { return g_stream; }
+cudaStream_t lib_stream() { return g_ctx[t_slot].stream; }
+cudaStream_t lib_copy_stream() { return g_ctx[t_slot].copy; }
+
+// Runs fn(slot, lo, hi) for the contiguous ranges [lo, hi) of 0 .. n that the slots in use own (multiples of `align`),
+// one worker thread per slot; returns the first failure with its message.
+int for_each_device(long long n, long long align, const std::function<int(int, long long, long long)>& fn) {
+  int use;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    use = g_n_use;
+  }
+  const long long per = ((n + use - 1) / use + align - 1) / align * align;
+  std::vector<std::thread> th;
+  std::vector<int> rc(use, SSGPU_OK);
+  std::vector<std::string> msg(use);
+  const char* kname[kMaxDev] = {nullptr};
+  for (int s = 0; s < use; s++) {
+    const long long lo = s * per, hi = std::min(n, lo + per);
+    if (lo >= hi) break;
+    th.emplace_back([&, s, lo, hi]() {
+      t_slot = s;
+      rc[s] = ensure_device();
+      if (rc[s] == SSGPU_OK) rc[s] = fn(s, lo, hi);
+      if (rc[s] != SSGPU_OK) msg[s] = g_err;
+      kname[s] = g_last_kernel;
+    });
+  }
+  for (auto& t : th) t.join();
+  if (kname[0]) g_last_kernel = kname[0];
+  for (int s = 0; s < use; s++)
+    if (rc[s] != SSGPU_OK) {
+      g_err = "device slot " + std::to_string(s) + ": " + msg[s];
+      return rc[s];
+    }
+  return SSGPU_OK;
+}
+int devices_in_use() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_n_use;
+}
 
 int DevBuf::alloc(size_t bytes, cudaStream_t st) {
   free();
@@ -275,11 +333,42 @@ int ssgpu_device_count(int* count) {
 
 int ssgpu_release(void) {
   if (!g_ready) return SSGPU_OK;
-  SS_CUDA(cudaStreamSynchronize(g_stream));
-  cudaMemPool_t pool;
-  SS_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_device));
-  SS_CUDA(cudaMemPoolTrimTo(pool, 0));
+  for (int s = 0; s < kMaxDev; s++) {
+    DevCtx& c = g_ctx[s];
+    if (!c.ready) continue;
+    SS_CUDA(cudaSetDevice(c.device));
+    SS_CUDA(cudaStreamSynchronize(c.stream));
+    SS_CUDA(cudaStreamSynchronize(c.copy));
+    cudaMemPool_t pool;
+    SS_CUDA(cudaDeviceGetDefaultMemPool(&pool, c.device));
+    SS_CUDA(cudaMemPoolTrimTo(pool, 0));
+  }
+  SS_CUDA(cudaSetDevice(g_ctx[0].device));
   xfer_release();
+  return SSGPU_OK;
+}
+
+int ssgpu_use_devices(int n) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    count = 0;
+  }
+  SS_ARG(count >= 1, "no CUDA device available (libssgpu has no CPU fallback)");
+  if (n <= 0) n = count;
+  // SSGPU_ALLOW_SHARED_DEVICE=1 (tests on a one-GPU box): slots beyond the visible devices wrap around and share them
+  const char* share = getenv("SSGPU_ALLOW_SHARED_DEVICE");
+  SS_ARG(n <= kMaxDev && (n <= count || (share && share[0] == '1')), "ssgpu_use_devices: more devices than are visible");
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_n_use = n;
+  }
+  return ensure_device();
+}
+
+int ssgpu_devices_in_use(int* n) {
+  SS_ARG(n != nullptr, "null pointer");
+  *n = devices_in_use();
   return SSGPU_OK;
 }
 
@@ -670,40 +759,42 @@ int ssgpu_loglik_grad_batch_dev(const double* y, long long B, const ssgpu_model*
   return launch_fd_gradient(W.out.as<double>(), B, k, h, loglik, grad, st);
 }
 
-int ssgpu_loglik_grad_batch(const double* y, long long B, const ssgpu_model* model, const double* theta, int k,
-                            const int* q_index, const int* p_star_index, double h, int kernel, double* loglik,
+}  // extern "C"
+
+namespace ssgpu {
+// ssgpu_loglik_grad_batch for the series [b0, b0 + B) of a batch of ldy series, on the device of the calling thread's
+// slot: y points at series b0 of the time-major array (row pitch ldy), theta / loglik / grad at that series' entries.
+static int grad_batch_slice(const double* y, long long ldy, long long B, const ssgpu_model* model, const double* theta,
+                            int k, const int* q_index, const int* p_star_index, double h, int kernel, double* loglik,
                             double* grad) {
-  SS_ARG(y && theta && loglik && grad && B >= 1 && h > 0.0 && model, "bad arguments");
-  SS_TRY(ensure_device());
   cudaStream_t st = lib_stream();
-  const size_t n_y = (size_t)model->N * model->p * (size_t)B;
+  const size_t Np = (size_t)model->N * model->p;
+  const size_t n_y = Np * (size_t)B;
   DevBuf yd, thd, res;
   SS_TRY(yd.alloc(n_y * sizeof(double), st));
   SS_TRY(thd.alloc((size_t)B * k * sizeof(double), st));
   SS_TRY(res.alloc((size_t)B * (1 + k) * sizeof(double), st));
   const int V = 1 + 2 * k;
-  const size_t Np = (size_t)model->N * model->p;
   double* ll = res.as<double>();
   double* gr = ll + B;
   ThetaWork W;
   // Pinned y and a large batch: the upload is pipelined with the kernels over chunks of series (chunk c of y is a
   // column block of the time-major array: one strided 2-D copy on a second stream; the kernels of chunk c wait for
-  // its event only).  1 GB of y at config 5 otherwise sits in front of the first launch for 18 ms of a 156 ms call.
-  const int nch = (host_is_pinned(y) && B >= 16384) ? 8 : 1;
-  if (getenv("SSGPU_TRACE")) fprintf(stderr, "ssgpu_loglik_grad_batch: B=%lld pinned=%d chunks=%d\n", B, (int)host_is_pinned(y), nch);
+  // its event only).  1 GB of y at config 5 otherwise sits in front of the first launch for 18 ms of the call.
+  const bool pinned = host_is_pinned(y);
+  const int nch = (pinned && B >= 16384) ? 8 : 1;
+  if (getenv("SSGPU_TRACE"))
+    fprintf(stderr, "ssgpu_loglik_grad_batch: slot=%d B=%lld of %lld pinned=%d chunks=%d\n", dev_slot(), B, ldy, (int)pinned, nch);
   if (nch == 1) {
-    SS_TRY(copy_h2d(yd.get(), y, n_y * sizeof(double), st));
+    // pageable y: rows of the column block travel through the slot's ring of pinned buffers (xfer.cu)
+    SS_TRY(copy_h2d_2d(yd.get(), y, (size_t)ldy * sizeof(double), (size_t)B * sizeof(double), Np, st));
     SS_CUDA(cudaMemcpyAsync(thd.get(), theta, (size_t)B * k * sizeof(double), cudaMemcpyHostToDevice, st));
     SS_TRY(theta_setup(model, false, B, V, k, thd.as<double>(), q_index, p_star_index, h, 1, W, st));
     SS_TRY(W.out.alloc((size_t)B * V * sizeof(double), st));
     SS_TRY(dispatch_batch(W.md, yd.as<double>(), B, V, kernel, W.out.as<double>(), st));
     SS_TRY(launch_fd_gradient(W.out.as<double>(), B, k, h, ll, gr, st));
   } else {
-    static cudaStream_t cs = nullptr;
-    {
-      std::lock_guard<std::mutex> lk(g_mu);
-      if (!cs) SS_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    }
+    cudaStream_t cs = lib_copy_stream();
     // theta and the small tables first: the one host-to-device copy engine serves both streams in issue order
     SS_CUDA(cudaMemcpyAsync(thd.get(), theta, (size_t)B * k * sizeof(double), cudaMemcpyHostToDevice, st));
     SS_TRY(theta_setup(model, false, B, V, k, thd.as<double>(), q_index, p_star_index, h, 1, W, st));
@@ -730,7 +821,7 @@ int ssgpu_loglik_grad_batch(const double* y, long long B, const ssgpu_model* mod
       const long long b0 = c * Bc, bn = std::min<long long>(Bc, B - b0);
       if (bn <= 0) break;
       SS_CUDA(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
-      SS_CUDA(cudaMemcpy2DAsync(yd.as<double>() + Np * b0, bn * sizeof(double), y + b0, (size_t)B * sizeof(double),
+      SS_CUDA(cudaMemcpy2DAsync(yd.as<double>() + Np * b0, bn * sizeof(double), y + b0, (size_t)ldy * sizeof(double),
                                 bn * sizeof(double), Np, cudaMemcpyHostToDevice, cs));
       SS_CUDA(cudaEventRecord(ev[c], cs));
       used = c + 1;
@@ -754,6 +845,25 @@ int ssgpu_loglik_grad_batch(const double* y, long long B, const ssgpu_model* mod
   SS_CUDA(cudaMemcpyAsync(grad, gr, (size_t)B * k * sizeof(double), cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));
   return SSGPU_OK;
+}
+}  // namespace ssgpu
+
+extern "C" {
+
+int ssgpu_loglik_grad_batch(const double* y, long long B, const ssgpu_model* model, const double* theta, int k,
+                            const int* q_index, const int* p_star_index, double h, int kernel, double* loglik,
+                            double* grad) {
+  SS_ARG(y && theta && loglik && grad && B >= 1 && h > 0.0 && model, "bad arguments");
+  SS_TRY(ensure_device());
+  // Several devices in use (ssgpu_use_devices): contiguous ranges of series, one worker thread, stream and staging ring
+  // per device, every device writes its series' results straight into the caller's arrays -- the recursion has no
+  // exchange step, so there is nothing to gather.
+  if (devices_in_use() > 1 && B >= 64 * devices_in_use())
+    return for_each_device(B, 32, [&](int, long long lo, long long hi) {
+      return grad_batch_slice(y + lo, B, hi - lo, model, theta + lo * k, k, q_index, p_star_index, h, kernel, loglik + lo,
+                              grad + lo * k);
+    });
+  return grad_batch_slice(y, B, B, model, theta, k, q_index, p_star_index, h, kernel, loglik, grad);
 }
 
 }  // extern "C"

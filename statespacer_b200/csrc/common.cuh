@@ -104,8 +104,11 @@ __host__ __device__ inline void kalman_shift(ssgpu_kalman_out& k, KalmanScratch&
 }
 
 // ---- device memory: stream-ordered allocations from the default pool (cached by the driver) ---
-cudaStream_t lib_stream();
+cudaStream_t lib_stream();       // compute stream of the calling thread's device slot
+cudaStream_t lib_copy_stream();  // second stream of the slot (uploads that overlap kernels)
 int ensure_device();
+int dev_slot();                  // device slot of the calling thread (0 unless a worker of for_each_device)
+int devices_in_use();
 
 class DevBuf {
  public:
@@ -127,6 +130,8 @@ class DevBuf {
 // ---- large host <-> device copies through pinned staging when the host side is pageable (xfer.cu) ----------
 int copy_d2h(void* dst, const void* src_dev, size_t bytes, cudaStream_t st);   // returns when dst holds the data
 int copy_h2d(void* dst_dev, const void* src, size_t bytes, cudaStream_t st);   // pinned src: valid until st is synchronised
+// the same for `rows` rows of `width` bytes each, `spitch` bytes apart in the caller's memory, dense on the device
+int copy_h2d_2d(void* dst_dev, const void* src, size_t spitch, size_t width, size_t rows, cudaStream_t st);
 void xfer_release();
 bool host_is_pinned(const void* p);
 

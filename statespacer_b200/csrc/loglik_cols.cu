@@ -21,6 +21,8 @@
 // real arithmetic, O(eps) apart in FP64.
 #include <type_traits>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace ssgpu {
@@ -374,12 +376,24 @@ static int launch_cols_m(const ColsArgs& A, cudaStream_t st) {
   return launch_cols_inst<M, G, false>(A, st);
 }
 
-static double* g_pack = nullptr;
+// T, Z, R travel through ONE __constant__ block per device.  Two launches on different streams of one device would
+// race on it, so they are chained: a launch waits (on its own stream) for the event its predecessor recorded behind
+// its kernel before it overwrites the block.  Host side: one mutex per device slot around the enqueue.
+static double* g_packs[16] = {nullptr};
+static cudaEvent_t g_cols_done[16] = {nullptr};
+static std::mutex g_cols_mu[16];
 
 int launch_loglik_cols(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st) {
   std::string why;
   SS_ARG(cols_eligible(md, &why), "column kernel not eligible: " + why);
+  const int slot = dev_slot();
+  std::lock_guard<std::mutex> lk(g_cols_mu[slot]);
+  double*& g_pack = g_packs[slot];
   if (!g_pack) SS_CUDA(cudaMalloc(&g_pack, sizeof(double) * kConstDoubles));
+  if (!g_cols_done[slot])
+    SS_CUDA(cudaEventCreateWithFlags(&g_cols_done[slot], cudaEventDisableTiming));
+  else
+    SS_CUDA(cudaStreamWaitEvent(st, g_cols_done[slot], 0));  // the previous launch has finished reading the block
   cols_pack_kernel<<<1, 256, 0, st>>>(md, g_pack);
   SS_CUDA(cudaGetLastError());
   SS_CUDA(cudaMemcpyToSymbolAsync(cMat, g_pack, sizeof(double) * kConstDoubles, 0, cudaMemcpyDeviceToDevice, st));
@@ -409,6 +423,7 @@ int launch_loglik_cols(const DModel& md, const double* y, long long B, int V, do
   }
   SS_TRY(rc);
   SS_CUDA(cudaGetLastError());
+  SS_CUDA(cudaEventRecord(g_cols_done[slot], st));  // the next launch on this device overwrites cMat behind it
   count_launch(2);
   set_last_kernel("loglik_cols_kernel");
   return SSGPU_OK;

@@ -303,11 +303,8 @@ static int launch_thr_one(const ThrArgs& A, cudaStream_t st) {
   constexpr int S = thr_smem_blocks(NB);
   constexpr BlkHandoff HL(NB, QOFF);
   const size_t smem = (size_t)((2 + HL.qw) * NB + 4 * S) * kThrThreads * sizeof(double);
-  static bool attr_done = false;  // per instantiation; a repeated call is harmless
-  if (!attr_done) {
-    SS_CUDA(cudaFuncSetAttribute(loglik_thr_kernel<NB, S, QOFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  // a function attribute belongs to the device it was set on (one slot per device: api.cu)
+  SS_CUDA(cudaFuncSetAttribute(loglik_thr_kernel<NB, S, QOFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (A.E + kThrThreads - 1) / kThrThreads;
   SS_ARG(blocks < (1LL << 31), "thread kernel: batch too large for one launch");
   loglik_thr_kernel<NB, S, QOFF><<<(unsigned)blocks, kThrThreads, smem, st>>>(A);

@@ -43,7 +43,9 @@ struct Ring {
     ready = false;
   }
 };
-Ring g_ring;
+// one ring per device slot: the worker threads of a sharded call stage their slices side by side
+Ring g_rings[16];
+#define g_ring g_rings[dev_slot()]
 
 bool is_pageable(const void* p) {
   cudaPointerAttributes a{};
@@ -58,8 +60,10 @@ bool is_pageable(const void* p) {
 bool host_is_pinned(const void* p) { return !is_pageable(p); }
 
 void xfer_release() {
-  std::lock_guard<std::mutex> lk(g_ring.mu);
-  g_ring.release();
+  for (Ring& r : g_rings) {
+    std::lock_guard<std::mutex> lk(r.mu);
+    r.release();
+  }
 }
 
 // dst (host) <- src (device); returns when dst holds the data
@@ -138,6 +142,46 @@ int copy_h2d(void* dst_dev, const void* src, size_t bytes, cudaStream_t st) {
     }
   }
   SS_CUDA(cudaStreamSynchronize(st));  // the ring is shared: the next transfer must not overwrite slots in flight
+  return SSGPU_OK;
+}
+
+// dst (device, dense rows of `width` bytes) <- `rows` rows of the caller's array, `spitch` bytes apart.  Pinned source:
+// one strided DMA.  Pageable source: the rows are packed into the ring's pinned slots by helper threads (a slot holds
+// as many whole rows as fit) and leave it as contiguous copies.
+int copy_h2d_2d(void* dst_dev, const void* src, size_t spitch, size_t width, size_t rows, cudaStream_t st) {
+  if (rows == 0 || width == 0) return SSGPU_OK;
+  if (spitch == width) return copy_h2d(dst_dev, src, width * rows, st);
+  if (!is_pageable(src) || width > kChunk) {
+    SS_CUDA(cudaMemcpy2DAsync(dst_dev, width, src, spitch, width, rows, cudaMemcpyHostToDevice, st));
+    return SSGPU_OK;
+  }
+  Ring& ring = g_ring;
+  std::lock_guard<std::mutex> lk(ring.mu);
+  SS_TRY(ring.init());
+  const size_t rpc = kChunk / width;  // rows per chunk
+  const size_t n = (rows + rpc - 1) / rpc;
+  std::vector<std::future<void>> filled(n);
+  auto fill = [&](size_t i) {
+    const size_t r0 = i * rpc, nr = rows - r0 < rpc ? rows - r0 : rpc;
+    char* to = static_cast<char*>(ring.buf[i % kRing]);
+    const char* from = static_cast<const char*>(src) + r0 * spitch;
+    filled[i] = std::async(std::launch::async, [to, from, nr, width, spitch]() {
+      for (size_t r = 0; r < nr; r++) std::memcpy(to + r * width, from + r * spitch, width);
+    });
+  };
+  for (size_t i = 0; i < n && i < (size_t)kRing; i++) fill(i);
+  for (size_t i = 0; i < n; i++) {
+    const int slot = (int)(i % kRing);
+    const size_t r0 = i * rpc, nr = rows - r0 < rpc ? rows - r0 : rpc;
+    filled[i].get();
+    SS_CUDA(cudaMemcpyAsync(static_cast<char*>(dst_dev) + r0 * width, ring.buf[slot], nr * width, cudaMemcpyHostToDevice, st));
+    SS_CUDA(cudaEventRecord(ring.ev[slot], st));
+    if (i + kRing < n) {
+      SS_CUDA(cudaEventSynchronize(ring.ev[slot]));
+      fill(i + kRing);
+    }
+  }
+  SS_CUDA(cudaStreamSynchronize(st));
   return SSGPU_OK;
 }
 

@@ -1331,3 +1331,41 @@ def test_r_glue_row_layout_multivariate():
     assert abs(got - want) <= tol
     wrong = api.loglik_batch(r_storage.reshape(N, p, 1), sm)[0]   # matrix(y, nrow = 1): observations scrambled
     assert not abs(wrong - want) <= 1e-6 * abs(want)
+
+
+def test_single_process_device_sharding():
+    """ssgpu_use_devices: the host-pointer objective + gradient call shards its series over device slots with one worker
+    thread, stream and staging ring per slot and writes each range straight into the caller's arrays.  On a one-GPU box
+    the slots share the device (SSGPU_ALLOW_SHARED_DEVICE): same code path, and the results must be the bits of the
+    unsharded call -- pinned and pageable host memory, a batch that does not divide evenly."""
+    import ctypes as C
+    import torch
+    rng = np.random.default_rng(91)
+    B, N, k = 1000, 60, 4
+    thetas, _, _, y = _bsm_batch(rng, B, N, 1, 0.03)
+    theta = np.ascontiguousarray(thetas[0])
+    sm0 = sysmat.bsm12(theta[0])
+    hmodel = api.BatchModel(sm0, N, B, 1)
+    qi, pi = np.asarray(BSM_Q_INDEX, dtype=np.int32), np.asarray(BSM_P_INDEX, dtype=np.int32)
+
+    def call(yh, th):
+        ll, gr = np.empty(B), np.empty((B, k))
+        native.check(native.lib().ssgpu_loglik_grad_batch(C.c_void_p(yh), B, C.byref(hmodel.c), C.c_void_p(th), k,
+                                                          qi.ctypes.data, pi.ctypes.data, C.c_double(1e-3), 0,
+                                                          ll.ctypes.data, gr.ctypes.data))
+        return ll, gr
+
+    y_pin = torch.from_numpy(y).pin_memory()
+    ll1, gr1 = call(y.ctypes.data, theta.ctypes.data)
+    os.environ["SSGPU_ALLOW_SHARED_DEVICE"] = "1"
+    try:
+        assert api.use_devices(3) == 3
+        ll3, gr3 = call(y.ctypes.data, theta.ctypes.data)                   # pageable: rows through the slots' rings
+        ll3p, gr3p = call(y_pin.data_ptr(), theta.ctypes.data)              # pinned: strided DMA per slot
+    finally:
+        api.use_devices(1)
+        del os.environ["SSGPU_ALLOW_SHARED_DEVICE"]
+    assert np.array_equal(ll1, ll3) and np.array_equal(gr1, gr3)
+    assert np.array_equal(ll1, ll3p) and np.array_equal(gr1, gr3p)
+    want = cport.LogLikC(y[:, 700:701], np.isnan(y[:, 700:701]), *sysmat.bsm12(theta[700]).args())
+    assert abs(ll3[700] - want) <= RTOL * max(1, abs(want))
