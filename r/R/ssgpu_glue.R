@@ -101,3 +101,7 @@ SimulateModelC <- function(nsim, forecast_period, p, comps, H, Z_extract = list(
   .Call(`_statespacer_SimSmootherC`, as.integer(nsim), as.integer(forecast_period), as.integer(p), comps, H, NULL, 0L,
         NULL, NULL, NULL, Z_extract)
 }
+
+#' Use n GPUs (0 = all visible) for the batched objective from this R session: LogLikGradBatchC() then shards its series
+#' over them inside the call (one worker thread and stream per device, no collective).  Returns the number in use.
+UseDevices <- function(n = 0L) .Call(`_statespacer_UseDevices`, as.integer(n))

@@ -448,6 +448,14 @@ SEXP _statespacer_ForecastC(SEXP h_, SEXP a1, SEXP P1, SEXP Z, SEXP T, SEXP R, S
   return res;
 }
 
+/* New: shard the batched objective over n GPUs of this R process (n <= 0: all visible); returns the count in use. */
+SEXP _statespacer_UseDevices(SEXP n_) {
+  int n = 0;
+  chk(ssgpu_use_devices(Rf_asInteger(n_)));
+  chk(ssgpu_devices_in_use(&n));
+  return Rf_ScalarInteger(n);
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_statespacer_ExtractComponentC", (DL_FUNC)&_statespacer_ExtractComponentC, 2},
     {"_statespacer_FastSmootherC", (DL_FUNC)&_statespacer_FastSmootherC, 10},
@@ -459,6 +467,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_statespacer_SimSmootherC", (DL_FUNC)&_statespacer_SimSmootherC, 11},
     {"_statespacer_CollapseC", (DL_FUNC)&_statespacer_CollapseC, 3},
     {"_statespacer_ForecastC", (DL_FUNC)&_statespacer_ForecastC, 8},
+    {"_statespacer_UseDevices", (DL_FUNC)&_statespacer_UseDevices, 1},
     {NULL, NULL, 0}};
 
 void R_init_statespacer(DllInfo* dll) {
