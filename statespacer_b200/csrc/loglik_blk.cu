@@ -72,6 +72,43 @@ __device__ __forceinline__ double blk_rcp(double x) {
   return fma(r, e, r);
 }
 
+// ---- bulk-asynchronous (TMA) staging of per-step parameter rows: cp.async.bulk + mbarrier ------------------------------
+// Time-varying Z (explanatory variables, R/Components-Regressors.R:60-78) is one 256-byte row per time point, the same
+// for every evaluation.  Each warp keeps a ring of kBlkZStages rows in shared memory; lane 0 arms the stage's mbarrier
+// with the byte count and issues ONE bulk copy for the row kBlkZStages steps ahead (the copy engine, not the LSU, moves
+// it and signals the barrier), the lanes wait on the barrier's phase parity and read their z_{I+k} from shared memory.
+// One copy per row costs more than it saves (arm + issue + wait every step: measured 4.3e9 against 7.5e9
+// series*timesteps/s with plain loads on the m = 16 regression model), so a stage is a block of kBlkZRows rows: one copy,
+// one wait and one refill per kBlkZRows steps.
+constexpr int kBlkZStages = 2;
+constexpr int kBlkZRows = 8;
+constexpr int kBlkZRowBytes = 2 * kBlkMaxNB * (int)sizeof(double);
+__device__ __forceinline__ unsigned blk_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void blk_bar_init(unsigned long long* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(blk_smem_u32(bar)));
+}
+__device__ __forceinline__ void blk_bar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void blk_bulk_rows(double* dst, const double* src, int bytes, unsigned long long* bar) {
+  const unsigned b = blk_smem_u32(bar), d = blk_smem_u32(dst);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src),
+               "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void blk_bar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned b = blk_smem_u32(bar);
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(b), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
 __device__ __forceinline__ double2 blk_shfl(double2 x, int src) {
   return make_double2(__shfl_sync(0xffffffffu, x.x, src), __shfl_sync(0xffffffffu, x.y, src));
 }
@@ -79,7 +116,8 @@ __device__ __forceinline__ double2 blk_shfl(double2 x, int src) {
 // QOFF: the diagonal blocks of R Q R' have off-diagonal entries (correlated disturbances of a multivariate model)
 // ZTV: Z changes with t (explanatory variables, R/Components-Regressors.R:60-78); p = 1 only
 // HO: leave after the diffuse phase and hand the state over (A.hd, A.hi) to the thread kernel
-template <int L, int NB, bool P1, bool QOFF, bool ZTV = false, bool HO = false>
+// ZTMA: the rows of a time-varying Z arrive through the cp.async.bulk ring instead of per-lane loads (SSGPU_BLK_ZTMA=1)
+template <int L, int NB, bool P1, bool QOFF, bool ZTV = false, bool HO = false, bool ZTMA = false>
 __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb(NB)) loglik_blk_kernel(const BlkArgs A) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int G = 32 / L;       // evaluations per warp
@@ -135,7 +173,35 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
   __shared__ double pinf_s[K * 4][BT];
   double(*pinf)[BT] = pinf_s;
   const int tx = threadIdx.x;
-
+  // ring of blocks of rows of the time-varying Z, one ring per warp (see blk_bulk_rows above)
+  __shared__ __align__(128) double zring_s[ZTMA ? BT / 32 : 1][ZTMA ? kBlkZStages : 1][ZTMA ? kBlkZRows : 1][2 * kBlkMaxNB];
+  __shared__ __align__(8) unsigned long long zbar_s[ZTMA ? BT / 32 : 1][ZTMA ? kBlkZStages : 1];
+  int zblk = -1;  // block of rows the lanes have waited for
+  auto z_issue = [&](int blk) {  // lane 0: rows blk * kBlkZRows ... into stage blk % kBlkZStages
+    const int row0 = blk * kBlkZRows, nr = min(kBlkZRows, N - row0);
+    if (nr > 0)
+      blk_bulk_rows(&zring_s[warp][blk % kBlkZStages][0][0], A.zt + (size_t)row0 * (2 * kBlkMaxNB), nr * kBlkZRowBytes,
+                    &zbar_s[warp][blk % kBlkZStages]);
+  };
+  if constexpr (ZTMA) {
+    if (lane == 0) {
+#pragma unroll
+      for (int sg = 0; sg < kBlkZStages; sg++) blk_bar_init(&zbar_s[warp][sg]);
+      blk_bar_fence_init();
+#pragma unroll
+      for (int sg = 0; sg < kBlkZStages; sg++) z_issue(sg);
+    }
+    __syncwarp();
+  }
+  // block b + kBlkZStages takes the place of block b once every lane has used the last row of b (call at the end of step t)
+  auto z_refill = [&](int t) {
+    if constexpr (ZTMA) {
+      if ((t & (kBlkZRows - 1)) == kBlkZRows - 1) {
+        __syncwarp();
+        if (lane == 0) z_issue(t / kBlkZRows + kBlkZStages);
+      }
+    }
+  };
   // ---- own blocks of P_star, P_inf, own T blocks, own part of a, own diagonal block of R Q R' ---------------------
   const int i0 = own ? (int)A.perm[2 * I] : -1, i1 = own ? (int)A.perm[2 * I + 1] : -1;
   auto elem = [&](const double* blk, int diag, int i, int k) { return (i >= 0 && k >= 0) ? mat_get(blk, diag, M, i, k) : 0.0; };
@@ -233,8 +299,17 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
     for (int k = 0; k < K; k++) ZK[k] = own ? make_double2(A.z[0][2 * Jk[k]], A.z[0][2 * Jk[k] + 1]) : make_double2(0.0, 0.0);
   }
   auto load_z = [&](int t, int j) {
-    if constexpr (ZTV) {
+    if constexpr (ZTV && !ZTMA) {  // default: the row of the step from device memory (L1-resident, per-lane 16-byte loads)
       const double2* zr = reinterpret_cast<const double2*>(A.zt + (size_t)t * (2 * kBlkMaxNB));
+#pragma unroll
+      for (int k = 0; k < K; k++) ZK[k] = own ? zr[Jk[k]] : make_double2(0.0, 0.0);
+    } else if constexpr (ZTV) {
+      const int blk = t / kBlkZRows, sg = blk % kBlkZStages;
+      if (blk != zblk) {  // first row of a block: its copy has landed when the stage's barrier has flipped
+        blk_bar_wait(&zbar_s[warp][sg], (unsigned)(blk / kBlkZStages) & 1u);
+        zblk = blk;
+      }
+      const double2* zr = reinterpret_cast<const double2*>(zring_s[warp][sg][t & (kBlkZRows - 1)]);
 #pragma unroll
       for (int k = 0; k < K; k++) ZK[k] = own ? zr[Jk[k]] : make_double2(0.0, 0.0);
     } else if constexpr (!ZREG) {
@@ -397,6 +472,7 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
         const bool gone = group_all(small);
         if (init && gone) init = false;
       }
+      z_refill(t);
       t++;
     }
   }
@@ -501,6 +577,7 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
         }
         a0 = fma(g0, vv, ta0);
         a1 = fma(g1, vv, ta1);
+        z_refill(t);
       }
       // the last observation (:200 -- P and a are not needed afterwards)
       load_z(N - 1, 0);
@@ -642,8 +719,16 @@ bool blk_eligible(const DModel& md, std::string* why) {
   return true;
 }
 
-template <int L, int NB, bool P1, bool QOFF, bool ZTV = false, bool HO = false>
+template <int L, int NB, bool P1, bool QOFF, bool ZTV = false, bool HO = false, bool ZTMA = false>
 static void launch_blk_one(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
+  if constexpr (ZTV && !ZTMA && NB <= 8) {
+    // SSGPU_BLK_ZTMA=1: time-varying Z through the bulk-copy ring (measured slower than the per-lane loads: DESIGN.md)
+    static const bool ztma = [] {
+      const char* e = getenv("SSGPU_BLK_ZTMA");
+      return e && e[0] == '1';
+    }();
+    if (ztma) return launch_blk_one<L, NB, P1, QOFF, ZTV, HO, true>(A, blocks, st);
+  }
   // SSGPU_BLK_PAD_SMEM: unused dynamic shared memory per CTA -- an occupancy knob for experiments (e.g. 120000 leaves
   // one CTA per SM: the step time of a warp that has a sub-partition to itself)
   static const int pad = [] {
@@ -651,8 +736,8 @@ static void launch_blk_one(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
     return e ? atoi(e) : 0;
   }();
   if (pad > 0)
-    cudaFuncSetAttribute(loglik_blk_kernel<L, NB, P1, QOFF, ZTV, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-  loglik_blk_kernel<L, NB, P1, QOFF, ZTV, HO><<<blocks, NB > 8 ? kBlkThreadsCS : kBlkThreads, pad, st>>>(A);
+    cudaFuncSetAttribute(loglik_blk_kernel<L, NB, P1, QOFF, ZTV, HO, ZTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+  loglik_blk_kernel<L, NB, P1, QOFF, ZTV, HO, ZTMA><<<blocks, NB > 8 ? kBlkThreadsCS : kBlkThreads, pad, st>>>(A);
 }
 
 template <int L, int NB>

@@ -1369,3 +1369,41 @@ def test_single_process_device_sharding():
     assert np.array_equal(ll1, ll3p) and np.array_equal(gr1, gr3p)
     want = cport.LogLikC(y[:, 700:701], np.isnan(y[:, 700:701]), *sysmat.bsm12(theta[700]).args())
     assert abs(ll3[700] - want) <= RTOL * max(1, abs(want))
+
+
+def test_time_varying_z_bulk_copy_ring():
+    """SSGPU_BLK_ZTMA=1: the rows of a time-varying Z reach the lane kernel through a per-warp ring of shared-memory stages
+    filled by cp.async.bulk (TMA) with mbarrier completion instead of per-lane loads.  Opt-in (measured slower for 256-byte
+    rows); the environment switch is read once per process, hence the subprocess.  Same bits as the default
+    path, for a series length that is not a multiple of the 8-row stage and one shorter than a stage."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
+from conftest import simulate_y
+from statespacer_b200 import api, sysmat
+rng = np.random.default_rng(3)
+for N in (61, 5):
+    base = sysmat.bsm12(0.5 * np.log([1.0, 0.1, 0.01, 0.05])); m0 = base.m; m = m0 + 2
+    X = rng.normal(size=(N, 2))
+    Z = np.zeros((1, m, N)); Z[0, :m0, :] = base.Z[0, :, 0][:, None]; Z[0, m0:, :] = X.T
+    sm = sysmat.SysMat(Z=Z, T=sysmat.block_diag(base.T[:, :, 0], np.eye(2))[:, :, None],
+                       R=np.concatenate([np.eye(m0), np.zeros((2, m0))], axis=0)[:, :, None], Q=base.Q, a=np.zeros(m),
+                       P_inf=sysmat.block_diag(base.P_inf, np.eye(2)), P_star=sysmat.block_diag(base.P_star, np.zeros((2, 2))))
+    y = np.stack([simulate_y(rng, base, N, missing=0.08)[:, 0] + X @ np.array([1.5, -0.7]) for _ in range(45)], axis=1)
+    got = api.loglik_batch(y, sm, kernel="blk")
+    assert "time-varying Z" in api.last_kernel()
+    np.save(sys.argv[1] + "_%%d.npy" %% N, got)
+''' % (ROOT_DIR, ROOT_DIR)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        outs = {}
+        for tag, env in (("plain", {}), ("ring", {"SSGPU_BLK_ZTMA": "1"})):
+            r = subprocess.run([sys.executable, "-c", code, os.path.join(d, tag)], env={**os.environ, **env},
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs[tag] = [np.load(os.path.join(d, f"{tag}_{N}.npy")) for N in (61, 5)]
+        for a, b in zip(outs["plain"], outs["ring"]):
+            assert np.array_equal(a, b, equal_nan=True) and np.all(np.isfinite(a[~np.isnan(a)]))
+        assert np.all(np.isfinite(outs["plain"][0]))
