@@ -225,6 +225,26 @@ int ssgpu_loglik_theta_batch_dev(const double* y, long long B, int V, const ssgp
                                  int k, const int* q_index, const int* p_star_index, int kernel, double* out,
                                  void* stream);
 
+/* ---- 6d. ... with full covariance blocks: the LDL' parameterisation on the device (new) ------------------------------
+ * Multivariate models parameterise every variance matrix as L D L' (R/Cholesky.R:148-167): D = diag(exp(2 theta_i)), L
+ * unit lower triangular with its strict lower triangle filled column by column from the following parameters.  A block
+ * descriptor places such an n x n matrix (n <= 8) on the diagonal of Q (target 0) or P_star (target 1) at row = column
+ * `offset`, built from theta[theta_offset ...] (n + n(n-1)/2 parameters); n = 1 is the plain exp(2 theta) of section 6c.
+ * Entries of the model's (shared, dense) Q / P_star outside the blocks are kept.  A parameter vector with a diagonal of
+ * D <= 1e-7 is not admissible: the reference returns NA (R/Cholesky.R:159-161), this entry point NaN.
+ *   fd != 0: theta [b*k + i]; out[b] = loglik / N, grad[b*k + i] central differences with step h (V is ignored)
+ *   fd == 0: theta [(v*B + b)*k + i] -> out[v*B + b]; grad is not touched
+ * Device pointers (y, theta, out, grad), asynchronous on `stream`; a, P_inf, Z, T, R, Q, P_star of `model` shared. */
+typedef struct {
+  int target;       /* 0 = Q, 1 = P_star */
+  int offset;       /* first row = first column of the block */
+  int n;            /* 1 .. 8 */
+  int theta_offset; /* first of its n + n(n-1)/2 parameters */
+} ssgpu_cov_block;
+int ssgpu_loglik_cov_batch_dev(const double* y, long long B, int V, const ssgpu_model* model, const double* theta, int k,
+                               const ssgpu_cov_block* blocks, int n_blocks, double h, int fd, int kernel, double* out,
+                               double* grad, void* stream);
+
 /* ---- 6b. Simulation smoother on device-resident draws (new) ---------------------------------
  * The three per-draw routines again, for callers that keep the draws on the GPU between the steps of
  * R/SimSmoother.R:91-769 (simulate every component -> add -> smooth -> extract) instead of round-tripping

@@ -664,3 +664,30 @@ def loglik_theta_batch_dev(y, model: BatchModel, theta, q_index, p_star_index, k
         C.c_void_p(y.data_ptr()), B, V, C.byref(model.c), C.c_void_p(theta.contiguous().data_ptr()), k,
         qi.ctypes.data, pi.ctypes.data, _KERNELS[kernel], C.c_void_p(out.data_ptr()), _stream_handle(stream)))
     return out
+
+
+def loglik_cov_batch_dev(y, model: BatchModel, theta, blocks, h=1e-3, grad=True, kernel="auto", stream=None):
+    """Objective (and central-difference gradient) from parameter vectors with full covariance blocks: every block
+    (target, offset, n, theta_offset) -- target "Q" or "P_star" -- is L D L' built on the device from
+    theta[theta_offset : theta_offset + n + n (n - 1) / 2] (R/Cholesky.R:148-167; include/ssgpu.h section 6d).
+    grad=True: theta (B, k) -> (loglik (B,), gradient (B, k)); grad=False: theta (V, B, k) -> (V, B).
+    NaN where the reference's Cholesky() returns NA (a variance <= 1e-7)."""
+    import torch
+    arr = (native.CovBlock * len(blocks))()
+    for i, (target, offset, n, t0) in enumerate(blocks):
+        arr[i] = native.CovBlock({"Q": 0, "P_star": 1}[target], int(offset), int(n), int(t0))
+    theta = theta.contiguous()
+    if grad:
+        B, k = theta.shape
+        ll = torch.empty(B, device=y.device, dtype=torch.float64)
+        gr = torch.empty(B, k, device=y.device, dtype=torch.float64)
+        native.check(native.lib().ssgpu_loglik_cov_batch_dev(
+            C.c_void_p(y.data_ptr()), B, 0, C.byref(model.c), C.c_void_p(theta.data_ptr()), k, arr, len(blocks),
+            C.c_double(h), 1, _KERNELS[kernel], C.c_void_p(ll.data_ptr()), C.c_void_p(gr.data_ptr()), _stream_handle(stream)))
+        return ll, gr
+    V, B, k = theta.shape
+    out = torch.empty(V, B, device=y.device, dtype=torch.float64)
+    native.check(native.lib().ssgpu_loglik_cov_batch_dev(
+        C.c_void_p(y.data_ptr()), B, V, C.byref(model.c), C.c_void_p(theta.data_ptr()), k, arr, len(blocks),
+        C.c_double(0.0), 0, _KERNELS[kernel], C.c_void_p(out.data_ptr()), None, _stream_handle(stream)))
+    return out

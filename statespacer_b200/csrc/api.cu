@@ -745,6 +745,54 @@ int ssgpu_loglik_theta_batch_dev(const double* y, long long B, int V, const ssgp
   return dispatch_batch(W.md, y, B, V, kernel, out, st);
 }
 
+int ssgpu_loglik_cov_batch_dev(const double* y, long long B, int V, const ssgpu_model* model, const double* theta, int k,
+                               const ssgpu_cov_block* blocks, int n_blocks, double h, int fd, int kernel, double* out,
+                               double* grad, void* stream) {
+  SS_ARG(y && theta && out && model && blocks && B >= 1 && k >= 1 && n_blocks >= 1, "bad arguments");
+  SS_ARG(!fd || (grad && h > 0.0), "fd: grad and a positive step are needed");
+  SS_TRY(ensure_device());
+  cudaStream_t st = stream ? (cudaStream_t)stream : lib_stream();
+  if (fd) V = 1 + 2 * k;
+  SS_ARG(V >= 1, "V must be positive");
+  DModel md;
+  SS_TRY(to_dmodel(model, &md));
+  const int m = md.m, r = md.r;
+  SS_ARG(md.Q.shared() && md.P_star.shared() && !md.Q.tv() && !md.Q.diag && !md.P_star.diag,
+         "Q / P_star of the model must be the shared dense templates");
+  SS_ARG(md.a.shared() && md.P_inf.shared() && md.Z.shared() && md.T.shared() && md.R.shared(),
+         "theta-driven entry points take shared a, P_inf, Z, T, R");
+  bool p_blocks = false;
+  for (int i = 0; i < n_blocks; i++) {
+    const ssgpu_cov_block& bl = blocks[i];
+    SS_ARG(bl.target == 0 || bl.target == 1, "covariance block: target must be 0 (Q) or 1 (P_star)");
+    SS_ARG(bl.n >= 1 && bl.n <= 8 && bl.offset >= 0 && bl.offset + bl.n <= (bl.target == 0 ? r : m),
+           "covariance block outside its matrix (1 <= n <= 8)");
+    SS_ARG(bl.theta_offset >= 0 && bl.theta_offset + bl.n + bl.n * (bl.n - 1) / 2 <= k, "covariance block: parameters out of range");
+    p_blocks = p_blocks || bl.target == 1;
+  }
+  const size_t E = (size_t)B * V;
+  DevBuf bd, Qe, Pe, valid, work;
+  SS_TRY(bd.alloc(sizeof(ssgpu_cov_block) * n_blocks, st));
+  SS_CUDA(cudaMemcpyAsync(bd.get(), blocks, sizeof(ssgpu_cov_block) * n_blocks, cudaMemcpyHostToDevice, st));
+  SS_CUDA(cudaStreamSynchronize(st));  // `blocks` is the caller's
+  SS_TRY(Qe.alloc(E * r * r * sizeof(double), st));
+  if (p_blocks) SS_TRY(Pe.alloc(E * m * m * sizeof(double), st));
+  SS_TRY(valid.alloc(E * sizeof(int), st));
+  SS_TRY(launch_expand_cov(theta, B, V, k, r, m, bd.as<ssgpu_cov_block>(), n_blocks, md.Q.p, md.P_star.p, h, fd,
+                           Qe.as<double>(), p_blocks ? Pe.as<double>() : nullptr, valid.as<int>(), st));
+  md.Q = DMat{Qe.as<double>(), (long long)r * r, (long long)B * r * r, 0, r, r, 0};
+  if (p_blocks) md.P_star = DMat{Pe.as<double>(), (long long)m * m, (long long)B * m * m, 0, m, m, 0};
+  double* res = out;
+  if (fd) {
+    SS_TRY(work.alloc(E * sizeof(double), st));
+    res = work.as<double>();
+  }
+  SS_TRY(dispatch_batch(md, y, B, V, kernel, res, st));
+  SS_TRY(launch_mask_invalid(res, valid.as<int>(), (long long)E, st));
+  if (fd) SS_TRY(launch_fd_gradient(res, B, k, h, out, grad, st));
+  return SSGPU_OK;
+}
+
 int ssgpu_loglik_grad_batch_dev(const double* y, long long B, const ssgpu_model* model, const double* theta, int k,
                                 const int* q_index, const int* p_star_index, double h, int kernel, double* loglik,
                                 double* grad, void* stream) {

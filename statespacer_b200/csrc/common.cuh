@@ -266,6 +266,10 @@ int launch_loglik_wsm(const DModel& md, const double* y, long long B, int V, dou
 int launch_expand_theta(const double* theta, long long B, int V, int k, int r, int m, const int* q_index,
                         const int* p_index, const double* q_fixed, const double* p_fixed, double h, int fd, double* Qd,
                         double* Pd, cudaStream_t st);
+int launch_expand_cov(const double* theta, long long B, int V, int k, int r, int m, const ssgpu_cov_block* blocks,
+                      int n_blocks, const double* q_tpl, const double* p_tpl, double h, int fd, double* Qe, double* Pe,
+                      int* valid, cudaStream_t st);
+int launch_mask_invalid(double* out, const int* valid, long long E, cudaStream_t st);
 int launch_fd_gradient(const double* out, long long B, int k, double h, double* loglik, double* grad, cudaStream_t st);
 
 // Block-row DFMA kernel for transition matrices that are block diagonal with blocks of at most 2 x 2 (loglik_blk.cu)

@@ -43,6 +43,11 @@ class KalmanOut(C.Structure):
     _fields_ = [("initialisation_steps", ip)] + [(n, dp) for n in KALMAN_FIELDS]
 
 
+class CovBlock(C.Structure):
+    """ssgpu_cov_block"""
+    _fields_ = [("target", C.c_int), ("offset", C.c_int), ("n", C.c_int), ("theta_offset", C.c_int)]
+
+
 class SimComponent(C.Structure):
     """ssgpu_sim_component"""
     _fields_ = [("m", C.c_int), ("r", C.c_int), ("repeat_Q", C.c_int), ("draw_initial", C.c_int),
@@ -66,7 +71,7 @@ SYMBOLS = ["ssgpu_version", "ssgpu_last_error", "ssgpu_set_device", "ssgpu_devic
            "ssgpu_FastSmootherC_dev", "ssgpu_ExtractComponentC_dev", "ssgpu_draw_layout_dev", "ssgpu_last_sim_kernel_ms",
            "ssgpu_loglik_grad_batch", "ssgpu_loglik_grad_batch_dev", "ssgpu_loglik_theta_batch_dev",
            "ssgpu_SimSmoother", "ssgpu_kalman_batch", "ssgpu_kalman_batch_dev", "ssgpu_collapse", "ssgpu_forecast", "ssgpu_SimulateModel", "ssgpu_plan_blocks",
-           "ssgpu_use_devices", "ssgpu_devices_in_use"]
+           "ssgpu_use_devices", "ssgpu_devices_in_use", "ssgpu_loglik_cov_batch_dev"]
 
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS, KERNEL_MMA, KERNEL_MMA_DENSE, KERNEL_WSM, KERNEL_BLK, KERNEL_BLK_LANES = 0, 1, 2, 3, 4, 5, 6, 7
 

@@ -1407,3 +1407,58 @@ for N in (61, 5):
         for a, b in zip(outs["plain"], outs["ring"]):
             assert np.array_equal(a, b, equal_nan=True) and np.all(np.isfinite(a[~np.isnan(a)]))
         assert np.all(np.isfinite(outs["plain"][0]))
+
+
+def test_loglik_from_theta_with_ldl_covariance_blocks():
+    """SURVEY.md 8f row 1 for multivariate models: the variance matrices are L D L' built ON THE DEVICE from theta
+    (R/Cholesky.R:148-167) -- a bivariate local level with correlated observation errors and correlated level
+    disturbances (p = 2, m = 4; Q = blkdiag(H, Q_level), P_star = blkdiag(H, 0): three blocks, k = 6) and a trivariate
+    one (3 x 3 blocks, k = 12) -- against the oracle on matrices built by sysmat.cholesky_cov; the central-difference
+    gradient against differences of the oracle; the <= 1e-7 -> NA rule (:159-161)."""
+    import torch
+    dev = torch.device("cuda")
+    rng = np.random.default_rng(23)
+    for p in (2, 3):
+        npar = p + p * (p - 1) // 2
+        k, N, B, m = 2 * npar, 40, 9, 2 * p
+        Z = np.concatenate([np.eye(p), np.eye(p)], axis=1)
+        T = sysmat.block_diag(np.zeros((p, p)), np.eye(p))
+
+        def build(th):
+            H, Ql = sysmat.cholesky_cov(th[:npar], p), sysmat.cholesky_cov(th[npar:], p)
+            if H is None or Ql is None:
+                return None
+            return sysmat.SysMat(Z=Z[:, :, None], T=T[:, :, None], R=np.eye(m)[:, :, None], Q=sysmat.block_diag(H, Ql)[:, :, None],
+                                 a=np.zeros(m), P_inf=sysmat.block_diag(np.zeros((p, p)), np.eye(p)),
+                                 P_star=sysmat.block_diag(H, np.zeros((p, p))))
+
+        theta = np.concatenate([0.5 * np.log(rng.uniform(0.3, 2.0, size=(B, p))), 0.4 * rng.normal(size=(B, npar - p)),
+                                0.5 * np.log(rng.uniform(0.05, 0.5, size=(B, p))), 0.4 * rng.normal(size=(B, npar - p))], axis=1)
+        theta[4, 0] = 0.5 * math.log(5e-8)                       # a variance below 1e-7: NA
+        tpl = build(theta[0])
+        y = np.stack([simulate_y(rng, tpl, N, missing=0.1) for _ in range(B)], axis=2)       # (N, p, B)
+        model = api.BatchModel(tpl, N, B, 1, device=dev)
+        blocks = [("Q", 0, p, 0), ("Q", p, p, npar), ("P_star", 0, p, 0)]
+        y_d, th_d = torch.from_numpy(y).to(dev), torch.from_numpy(theta).to(dev)
+        ll, gr = api.loglik_cov_batch_dev(y_d, model, th_d, blocks, h=1e-3)
+        ll, gr = ll.cpu().numpy(), gr.cpu().numpy()
+        assert math.isnan(ll[4]) and np.all(np.isnan(gr[4]))
+        for b in range(B):
+            if b == 4:
+                assert build(theta[b]) is None
+                continue
+            yb = y[:, :, b]
+            f = lambda th: cport.LogLikC(yb, np.isnan(yb), *build(th).args())
+            want = f(theta[b])
+            assert abs(ll[b] - want) <= RTOL * max(1, abs(want)), (p, b, ll[b], want)
+            for i in range(0, k, 3):
+                e = np.zeros(k)
+                e[i] = 1e-3
+                g = (f(theta[b] + e) - f(theta[b] - e)) / 2e-3
+                assert abs(gr[b, i] - g) <= 1e-6 * max(1, abs(g)), (p, b, i, gr[b, i], g)
+        # V arbitrary vectors per series, no gradient
+        pts = np.stack([theta, theta + 0.05, theta - 0.07])
+        out = api.loglik_cov_batch_dev(y_d, model, torch.from_numpy(pts).to(dev), blocks, grad=False).cpu().numpy()
+        assert out.shape == (3, B) and np.array_equal(out[0], ll, equal_nan=True)
+        want = cport.LogLikC(y[:, :, 2], np.isnan(y[:, :, 2]), *build(pts[1, 2]).args())
+        assert abs(out[1, 2] - want) <= RTOL * max(1, abs(want))
