@@ -979,6 +979,98 @@ def run_kalman_gpu(args):
     return None
 
 
+# ---- configs 2, 3 and 4 as batched loglikelihoods (--workload models) ------------------------------------------------
+def model_cases():
+    """BASELINE.json configs 2 (synthetic stand-in: bivariate BSM + regressors), 3 (dynamic Nelson-Siegel on
+    FedYieldCurve) and 4's model (SARIMA(1,1,1)(0,1,1)12 on log AirPassengers) as concrete inputs."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import DNS_PARAM, config2_standin, load_fed
+    from statespacer_b200 import sysmat
+    c2 = config2_standin()
+    air, sm4 = sim_model()
+    sm3, _ = sysmat.dns_yield_curve(DNS_PARAM)
+    return [("config2", "bivariate BSM + 3 shared regressors (stand-in), p=2, N=192, m=34, time-varying Z, 5% missing", c2.sm, c2.y, 16384),
+            ("config3", "dynamic Nelson-Siegel, FedYieldCurve 1985-2000, p=8, N=192, m=14", sm3, load_fed(), 32768),
+            ("config4_loglik", "SARIMA(1,1,1)(0,1,1)12 on log AirPassengers, p=1, N=144, m=28 (companion-form T)", sm4, air, 16384)]
+
+
+def run_models_gpu(args):
+    """Batched LogLikC of configs 2, 3 and 4's model: the data of the config replicated B times with 1 % noise on the
+    values, all matrices shared.  Roofline: FP64, algorithmic flops of the dense recursion (SURVEY.md 8d F_alg) -- these T
+    are not block diagonal with 2 x 2 blocks, so the dense algorithm is what the kernels run."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from statespacer_b200 import api
+    world, rank, local, dev = gpu_setup()
+    peak_tf, _ = api.fp64_peak(0, 4000, 5)
+    stream = torch.cuda.current_stream(dev)
+    lines = {}
+    for name, what, sm, y1, B in model_cases():
+        N, p = y1.shape
+        g = torch.Generator(device=dev)
+        g.manual_seed(11 + rank)
+        yd = torch.from_numpy(np.ascontiguousarray(y1)).to(dev)[:, :, None] * (
+            1.0 + 0.01 * torch.randn(1, 1, B, generator=g, device=dev, dtype=torch.float64))
+        yd = yd.contiguous()
+        model = api.BatchModel(sm, N, B, 1, device=dev)
+        out = torch.empty(1, B, device=dev, dtype=torch.float64)
+        for _ in range(max(1, args.warmup)):
+            api.loglik_batch_dev(yd, model, out, stream=stream)
+        torch.cuda.synchronize(dev)
+        l0 = api.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            api.loglik_batch_dev(yd, model, out, stream=stream)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / args.steps
+        launches = api.launch_count() - l0
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        value = B * N * world / (ms * 1e-3)
+        falg = f_alg(sm.m, p)
+        # end to end: host arrays in, loglik out (pageable memory)
+        Be = min(B, 4096)
+        yh = yd[:, :, :Be].contiguous().cpu().numpy()
+        api.loglik_batch(yh, sm)
+        t0 = time.perf_counter()
+        got = api.loglik_batch(yh, sm)
+        e2e_s = time.perf_counter() - t0
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": f"{name}: {what}", "series_per_gpu": B, "timesteps": N,
+                                                 "kernel": api.last_kernel(),
+                                                 "results_finite": bool(np.all(np.isfinite(got)))},
+                "e2e": {"value": Be * N * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": yh.nbytes,
+                        "d2h_bytes_per_step": 8 * Be, "steps": 1, "series": Be, "note": "ssgpu_loglik_batch, pageable host arrays"},
+                "gpu_launches": launches,
+                "roofline": {"bound": "fp64", "kernel": api.last_kernel(), "achieved": value / world * falg / 1e12,
+                             "peak": peak_tf, "unit": "TFLOP/s", "frac": value / world * falg / 1e12 / peak_tf, "traffic": None,
+                             "flops_per_series_timestep": falg,
+                             "note": "dense-algorithm flops 4m^3 + (4p+3)m^2 + 7pm per series*timestep (SURVEY.md 8d); the "
+                                     "tensor / warp kernels skip the all-zero 8 x 8 tiles of T, so the executed count is lower",
+                             "peak_source": "ssgpu_fp64_peak DFMA chains, measured in this run"}}
+        if world == 1 and not args.no_cpu and rank == 0:
+            from oracle import cport, ref
+            mod, kind = (ref, "reference") if ref.available() else (cport, "port")
+            cores = host_cores()
+            n = 2 * cores
+            ys = yd[:, :, :n].cpu().numpy()
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(cores) as ex:
+                list(ex.map(lambda b: mod.LogLikC(ys[:, :, b], np.isnan(ys[:, :, b]), *sm.args()), range(n)))
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n * N / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{n} series x {N} timesteps, one LogLikC call per series on {cores} threads ({dt:.2f} s)"}
+        lines[name] = line
+        del yd, out, model
+    return lines if rank == 0 else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -989,7 +1081,7 @@ def main():
     ap.add_argument("--missing", type=float, default=0.0, help="fraction of NaN observations (variant B: 0.02)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "blk", "blk_lanes", "mma", "mma_dense", "cols", "wsm", "generic"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--workload", default="all", choices=["all", "loglik", "sim", "kalman"],
+    ap.add_argument("--workload", default="all", choices=["all", "loglik", "sim", "kalman", "models"],
                     help="all (default): the config-5 loglik line (headline fields) with the sim and kalman lines attached "
                          "under `workloads`; loglik: config 5 alone; sim: config 4 simulation smoother draws; "
                          "kalman: batched filter + smoother (KalmanC) of config-5 series")
@@ -1014,6 +1106,8 @@ def main():
         line = run_sim_gpu(args)
     elif args.workload == "kalman":
         line = run_kalman_gpu(args)
+    elif args.workload == "models":
+        line = run_models_gpu(args)
     elif args.workload == "loglik":
         line = run_gpu(args)
     else:
@@ -1024,8 +1118,9 @@ def main():
         sub.steps, sub.warmup = min(args.steps, 5), min(args.warmup, 3)
         sim = run_sim_gpu(sub)
         kal = run_kalman_gpu(sub)
+        mods = run_models_gpu(sub)
         if line is not None:
-            line["workloads"] = {"sim": sim, "kalman": kal}
+            line["workloads"] = {"sim": sim, "kalman": kal, **(mods or {})}
     if line is not None:
         print(json.dumps(line))
     if dist.is_initialized():

@@ -120,9 +120,49 @@ int DevBuf::alloc(size_t bytes, cudaStream_t st) {
   return SSGPU_OK;
 }
 void DevBuf::free() {
-  if (p_) cudaFreeAsync(p_, st_);
+  if (p_ && !borrowed_) cudaFreeAsync(p_, st_);
   p_ = nullptr;
+  borrowed_ = false;
 }
+
+// ---- call arena: what a single small call needs without touching the allocator -----------------------------------
+// One per device slot: a pinned host block the arguments are packed into, a device block of the same size they are
+// copied to with ONE asynchronous copy, and a pinned word the scalar result comes back into.  ssgpu_LogLikC on a
+// 100-point series otherwise spends more time in cudaMallocAsync / cudaFreeAsync and in the driver's staging of two
+// pageable copies than in its kernel.  A call takes the arena only if it is free (try_lock) and large enough.
+constexpr size_t kArenaBytes = 1u << 20;
+struct CallArena {
+  std::mutex mu;
+  void* host = nullptr;
+  void* dev = nullptr;
+  double* res_host = nullptr;
+  bool ready = false;
+  int init() {
+    if (ready) return SSGPU_OK;
+    SS_CUDA(cudaHostAlloc(&host, kArenaBytes, cudaHostAllocDefault));
+    SS_CUDA(cudaMalloc(&dev, kArenaBytes + 256));
+    SS_CUDA(cudaHostAlloc((void**)&res_host, 256, cudaHostAllocDefault));
+    ready = true;
+    return SSGPU_OK;
+  }
+  double* res_dev() const { return reinterpret_cast<double*>(static_cast<char*>(dev) + kArenaBytes); }
+};
+static CallArena g_arena[kMaxDev];
+struct ArenaLease {
+  CallArena* a = nullptr;
+  ArenaLease() {
+    CallArena& c = g_arena[t_slot];
+    if (c.mu.try_lock()) {
+      if (c.init() == SSGPU_OK)
+        a = &c;
+      else
+        c.mu.unlock();
+    }
+  }
+  ~ArenaLease() {
+    if (a) a->mu.unlock();
+  }
+};
 
 // ---- host-side packing of many small arrays into one H2D copy ------------------------------
 class Packer {
@@ -142,9 +182,16 @@ class Packer {
   }
   double* host(size_t off) { return buf_.data() + off; }
   size_t size() const { return buf_.size(); }
-  int upload(DevBuf& d, cudaStream_t st) {
-    SS_TRY(d.alloc(buf_.size() * sizeof(double), st));
-    SS_CUDA(cudaMemcpyAsync(d.get(), buf_.data(), buf_.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  int upload(DevBuf& d, cudaStream_t st, CallArena* arena = nullptr) {
+    const size_t bytes = buf_.size() * sizeof(double);
+    if (arena && bytes <= kArenaBytes) {  // pinned staging, persistent device block: one truly asynchronous copy
+      std::memcpy(arena->host, buf_.data(), bytes);
+      d.borrow(arena->dev);
+      SS_CUDA(cudaMemcpyAsync(arena->dev, arena->host, bytes, cudaMemcpyHostToDevice, st));
+      return SSGPU_OK;
+    }
+    SS_TRY(d.alloc(bytes, st));
+    SS_CUDA(cudaMemcpyAsync(d.get(), buf_.data(), bytes, cudaMemcpyHostToDevice, st));
     return SSGPU_OK;
   }
 
@@ -190,14 +237,14 @@ struct SingleModel {
 // uploads y + the 7 matrices of one model, fills md with device pointers
 static int stage_single(SingleModel& S, const double* y, const int* y_isna, int N, int p, int m, int r, const double* a,
                         const double* P_inf, const double* P_star, const double* Z, int nZ, const double* T, int nT,
-                        const double* R, int nR, const double* Q, int nQ, cudaStream_t st) {
+                        const double* R, int nR, const double* Q, int nQ, cudaStream_t st, CallArena* arena = nullptr) {
   Packer& pk = S.pk;
   S.oy = pk.reserve((size_t)N * p);
   pack_y_single(y, y_isna, N, p, pk.host(S.oy));
   const size_t oa = pk.add(a, m), opi = pk.add(P_inf, (size_t)m * m), ops = pk.add(P_star, (size_t)m * m);
   const size_t oz = pk.add(Z, (size_t)p * m * nZ), ot = pk.add(T, (size_t)m * m * nT);
   const size_t orr = pk.add(R, (size_t)m * r * nR), oq = pk.add(Q, (size_t)r * r * nQ);
-  SS_TRY(pk.upload(S.dev, st));
+  SS_TRY(pk.upload(S.dev, st, arena));
   const double* d = S.dev.as<double>();
   DModel& md = S.md;
   md.N = N;
@@ -379,16 +426,22 @@ int ssgpu_LogLikC(const double* y, const int* y_isna, int N, int p, int m, int r
   SS_TRY(check_single(N, p, m, r, nZ, nT, nR, nQ));
   SS_TRY(ensure_device());
   cudaStream_t st = lib_stream();
+  ArenaLease lease;  // no allocator call, no pageable copy when the per-device call arena is free
   SingleModel S;
-  SS_TRY(stage_single(S, y, y_isna, N, p, m, r, a, P_inf, P_star, Z, nZ, T, nT, R, nR, Q, nQ, st));
+  SS_TRY(stage_single(S, y, y_isna, N, p, m, r, a, P_inf, P_star, Z, nZ, T, nT, R, nR, Q, nQ, st, lease.a));
   DevBuf out;
-  SS_TRY(out.alloc(sizeof(double), st));
+  if (lease.a)
+    out.borrow(lease.a->res_dev());
+  else
+    SS_TRY(out.alloc(sizeof(double), st));
   // one series is a batch of one: the warp-level kernels serve it when the model qualifies (a few hundred cycles
   // per observation instead of the CTA kernel's barriers), the generic kernel otherwise
   const HostShared hs{nT == 1 ? T : nullptr, nR == 1 ? R : nullptr, nZ == 1 ? Z : nullptr, nQ == 1 ? Q : nullptr};
   SS_TRY(dispatch_batch(S.md, S.dev.as<double>() + S.oy, 1, 1, SSGPU_KERNEL_AUTO, out.as<double>(), st, &hs));
-  SS_CUDA(cudaMemcpyAsync(loglik, out.get(), sizeof(double), cudaMemcpyDeviceToHost, st));
+  double* back = lease.a ? lease.a->res_host : loglik;
+  SS_CUDA(cudaMemcpyAsync(back, out.get(), sizeof(double), cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));
+  if (lease.a) *loglik = *back;
   return SSGPU_OK;
 }
 

@@ -118,6 +118,11 @@ class DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   int alloc(size_t bytes, cudaStream_t st);
   void free();
+  void borrow(void* p) {  // memory owned by someone else (the per-device call arena): never freed here
+    free();
+    p_ = p;
+    borrowed_ = true;
+  }
   template <class T>
   T* as() const { return reinterpret_cast<T*>(p_); }
   void* get() const { return p_; }
@@ -125,6 +130,7 @@ class DevBuf {
  private:
   void* p_ = nullptr;
   cudaStream_t st_ = nullptr;
+  bool borrowed_ = false;
 };
 
 // ---- large host <-> device copies through pinned staging when the host side is pageable (xfer.cu) ----------
