@@ -731,8 +731,11 @@ def run_sim_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        step()
+    out = None
+    for _ in range(args.warmup + 1):
+        # the same ownership pattern as the timed loop (the previous step's results are alive while the next step runs):
+        # otherwise torch's caching allocator meets a new peak inside the timed region and stalls it with cudaMalloc calls
+        out = step()
     sync()
     # a step is a few ms of kernels between short host-synchronous calls: clocks are polled through NVML in-process
     sampler = ClockSampler(local, interval_ms=20)

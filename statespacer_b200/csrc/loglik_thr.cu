@@ -35,7 +35,10 @@
 
 namespace ssgpu {
 
-constexpr int kThrThreads = 128;
+#ifndef SSGPU_THR_THREADS
+#define SSGPU_THR_THREADS 128
+#endif
+constexpr int kThrThreads = SSGPU_THR_THREADS;  // 2 x 128 or 4 x 64 threads per SM: 255 registers either way
 constexpr int kThrMaxNB = 8;
 
 struct ThrArgs {
@@ -74,7 +77,7 @@ __device__ __forceinline__ int thr_opaque0() {
 
 // S: blocks above the diagonal kept in shared memory (the last S in row-major order)
 template <int NB, int S, bool QOFF>
-__global__ void __launch_bounds__(kThrThreads, 2) loglik_thr_kernel(const ThrArgs A) {
+__global__ void __launch_bounds__(kThrThreads, 256 / kThrThreads) loglik_thr_kernel(const ThrArgs A) {
   constexpr BlkHandoff HL(NB, QOFF);
   constexpr int NOFF = HL.noff();
   constexpr int RO = NOFF - S;  // blocks above the diagonal in registers
