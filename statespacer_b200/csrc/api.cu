@@ -883,7 +883,7 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
   // column block of the time-major array: one strided 2-D copy on a second stream; the kernels of chunk c wait for
   // its event only).  1 GB of y at config 5 otherwise sits in front of the first launch for 18 ms of the call.
   const bool pinned = host_is_pinned(y);
-  const int nch = (pinned && B >= 16384) ? 8 : 1;
+  const int nch = B >= 16384 ? 8 : 1;
   if (getenv("SSGPU_TRACE"))
     fprintf(stderr, "ssgpu_loglik_grad_batch: slot=%d B=%lld of %lld pinned=%d chunks=%d\n", dev_slot(), B, ldy, (int)pinned, nch);
   if (nch == 1) {
@@ -895,6 +895,12 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
     SS_TRY(dispatch_batch(W.md, yd.as<double>(), B, V, kernel, W.out.as<double>(), st));
     SS_TRY(launch_fd_gradient(W.out.as<double>(), B, k, h, ll, gr, st));
   } else {
+    // A large batch is cut into chunks of series and the upload of chunk c + 1 overlaps the kernels of chunk c (chunk c of
+    // y is a column block of the time-major array).  Pinned y: one strided 2-D copy per chunk on the slot's copy stream,
+    // the kernels of the chunk wait for its event only.  Pageable y (what R passes): the chunk's rows are packed into the
+    // slot's ring of pinned buffers by helper threads and leave it as contiguous copies (copy_h2d_2d); that call returns
+    // when the chunk is on the device, the kernels are enqueued asynchronously, and the host goes on staging the next chunk
+    // while they run.  1 GB of y at config 5 otherwise sits in front of the first launch.
     cudaStream_t cs = lib_copy_stream();
     // theta and the small tables first: the one host-to-device copy engine serves both streams in issue order
     SS_CUDA(cudaMemcpyAsync(thd.get(), theta, (size_t)B * k * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -917,30 +923,34 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
     SS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     SS_CUDA(cudaEventRecord(ready, st));  // yd exists on the compute stream from here on
     SS_CUDA(cudaStreamWaitEvent(cs, ready, 0));
-    int used = 0;
-    for (int c = 0; c < nch; c++) {
-      const long long b0 = c * Bc, bn = std::min<long long>(Bc, B - b0);
-      if (bn <= 0) break;
-      SS_CUDA(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
-      SS_CUDA(cudaMemcpy2DAsync(yd.as<double>() + Np * b0, bn * sizeof(double), y + b0, (size_t)ldy * sizeof(double),
-                                bn * sizeof(double), Np, cudaMemcpyHostToDevice, cs));
-      SS_CUDA(cudaEventRecord(ev[c], cs));
-      used = c + 1;
-    }
     const HostShared hs{model->T.n_slices == 1 ? model->T.data : nullptr, model->R.n_slices == 1 ? model->R.data : nullptr,
                         model->Z.n_slices == 1 ? model->Z.data : nullptr, nullptr};
-    int rc = SSGPU_OK;
-    for (int c = 0; c < used && rc == SSGPU_OK; c++) {
+    auto upload = [&](int c) -> int {
       const long long b0 = c * Bc, bn = std::min<long long>(Bc, B - b0);
+      SS_CUDA(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
+      if (pinned)
+        SS_CUDA(cudaMemcpy2DAsync(yd.as<double>() + Np * b0, bn * sizeof(double), y + b0, (size_t)ldy * sizeof(double),
+                                  bn * sizeof(double), Np, cudaMemcpyHostToDevice, cs));
+      else
+        SS_TRY(copy_h2d_2d(yd.as<double>() + Np * b0, y + b0, (size_t)ldy * sizeof(double), bn * sizeof(double), Np, cs));
+      SS_CUDA(cudaEventRecord(ev[c], cs));
+      return SSGPU_OK;
+    };
+    int used = 0;
+    for (int c = 0; c < nch && c * Bc < B; c++) used = c + 1;
+    if (pinned)  // all copies queued up front: the copy engine never waits for the host
+      for (int c = 0; c < used; c++) SS_TRY(upload(c));
+    for (int c = 0; c < used; c++) {
+      const long long b0 = c * Bc, bn = std::min<long long>(Bc, B - b0);
+      if (!pinned) SS_TRY(upload(c));
       DModel mdc = W.md;  // per-evaluation variances of the chunk: same strides, shifted base
       mdc.Q.p += b0 * mdc.Q.sb;
       mdc.P_star.p += b0 * mdc.P_star.sb;
-      cudaStreamWaitEvent(st, ev[c], 0);
+      SS_CUDA(cudaStreamWaitEvent(st, ev[c], 0));
       double* outc = W.out.as<double>() + (size_t)V * b0;
-      rc = dispatch_batch(mdc, yd.as<double>() + Np * b0, bn, V, kernel, outc, st, &hs);
-      if (rc == SSGPU_OK) rc = launch_fd_gradient(outc, bn, k, h, ll + b0, gr + b0 * k, st);
+      SS_TRY(dispatch_batch(mdc, yd.as<double>() + Np * b0, bn, V, kernel, outc, st, &hs));
+      SS_TRY(launch_fd_gradient(outc, bn, k, h, ll + b0, gr + b0 * k, st));
     }
-    SS_TRY(rc);
   }
   SS_CUDA(cudaMemcpyAsync(loglik, ll, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaMemcpyAsync(grad, gr, (size_t)B * k * sizeof(double), cudaMemcpyDeviceToHost, st));
