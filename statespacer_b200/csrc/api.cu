@@ -906,7 +906,15 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
     SS_CUDA(cudaMemcpyAsync(thd.get(), theta, (size_t)B * k * sizeof(double), cudaMemcpyHostToDevice, st));
     SS_TRY(theta_setup(model, false, B, V, k, thd.as<double>(), q_index, p_star_index, h, 1, W, st));
     SS_TRY(W.out.alloc((size_t)B * V * sizeof(double), st));
-    const long long Bc = ((B + nch - 1) / nch + 31) / 32 * 32;
+    // chunk sizes 1/16, 1/16, 1/8, 1/4, 1/2 of the batch: the first kernels start after 1/16 of the upload, every later
+    // upload is shorter than the kernels it hides behind, and most of the work runs in large launches (few partial waves)
+    long long cb[9] = {0};  // chunk c covers the series [cb[c], cb[c + 1])
+    {
+      const long long u = (B / 16 + 31) / 32 * 32;
+      const long long cut[5] = {u, 2 * u, 4 * u, 8 * u, B};
+      for (int c = 0; c < 5; c++) cb[c + 1] = std::min<long long>(B, cut[c]);
+      for (int c = 5; c < 8; c++) cb[c + 1] = B;
+    }
     // events die with the frame on every return path; the copy stream is drained first so that no queued copy
     // still refers to them (or to the caller's y)
     struct Events {
@@ -926,7 +934,7 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
     const HostShared hs{model->T.n_slices == 1 ? model->T.data : nullptr, model->R.n_slices == 1 ? model->R.data : nullptr,
                         model->Z.n_slices == 1 ? model->Z.data : nullptr, nullptr};
     auto upload = [&](int c) -> int {
-      const long long b0 = c * Bc, bn = std::min<long long>(Bc, B - b0);
+      const long long b0 = cb[c], bn = cb[c + 1] - cb[c];
       SS_CUDA(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
       if (pinned)
         SS_CUDA(cudaMemcpy2DAsync(yd.as<double>() + Np * b0, bn * sizeof(double), y + b0, (size_t)ldy * sizeof(double),
@@ -937,11 +945,11 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
       return SSGPU_OK;
     };
     int used = 0;
-    for (int c = 0; c < nch && c * Bc < B; c++) used = c + 1;
+    for (int c = 0; c < nch && cb[c] < B; c++) used = c + 1;
     if (pinned)  // all copies queued up front: the copy engine never waits for the host
       for (int c = 0; c < used; c++) SS_TRY(upload(c));
     for (int c = 0; c < used; c++) {
-      const long long b0 = c * Bc, bn = std::min<long long>(Bc, B - b0);
+      const long long b0 = cb[c], bn = cb[c + 1] - cb[c];
       if (!pinned) SS_TRY(upload(c));
       DModel mdc = W.md;  // per-evaluation variances of the chunk: same strides, shifted base
       mdc.Q.p += b0 * mdc.Q.sb;
