@@ -544,8 +544,8 @@ def run_gpu(args):
             props = torch.cuda.get_device_properties(dev)
             sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
             pipe_frac = n_inst * 2.0 * B * V * T_STEPS / 32.0 / (props.multi_processor_count * 4 * sm_hz * kernel_ms * 1e-3)
-        # state record of blk_handoff.cuh: 135 doubles + 5 ints per evaluation at 7 blocks, written once, read once
-        handoff = 2.0 * (135 * 8 + 5 * 4) * B * V if thr else 0.0
+        # state record of blk_handoff.cuh: 135 doubles + 5 ints per evaluation at 7 blocks (written by the lane kernel, read here)
+        handoff = 1.0 * (135 * 8 + 5 * 4) * B * V if thr else 0.0
         grid = (B * V + 127) // 128 if thr else None
         traffic = committed_traffic("loglik_thr_kernel" if thr else kernel_name.split("<")[0], grid) if grid else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -568,10 +568,12 @@ def run_gpu(args):
                              "traffic": traffic["bytes"] if traffic else None,
                              "traffic_source": traffic["source"] if traffic else
                              "no ncu capture of this kernel at this size under profiles/",
-                             "traffic_algorithmic": 8.0 * B * T_STEPS + 8.0 * B * V * 2 * M + 8.0 * B * V + handoff,
-                             "traffic_algorithmic_note": "y once + the variance sets + results"
-                             + (" + the state the lane kernel hands to the thread kernel after the diffuse phase, "
-                                "written and read once (%d B per evaluation)" % (handoff / (B * V)) if handoff else ""),
+                             "traffic_algorithmic": 8.0 * B * T_STEPS + 8.0 * B * V + (handoff if thr else 8.0 * B * V * 2 * M),
+                             "traffic_algorithmic_note": "of the dominant kernel's launch: y once + results + "
+                             + ("the state record the lane kernel leaves behind after the diffuse phase, read once (%d B per "
+                                "evaluation; the lane kernel's own launch writes it and reads the variance sets: %.2f GB)"
+                                % (handoff / (B * V), (handoff + 8.0 * B * V * 2 * M + 8.0 * B * 13) / 1e9) if thr
+                                else "the variance sets"),
                              "useful_frac": (executed if executed else achieved) / peak_tf * useful,
                              "fp64_pipe_frac": pipe_frac,
                              "kernel_ms": kernel_ms,
