@@ -170,9 +170,13 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
     asm volatile("" : "+r"(srcF[k]), "+r"(srcB[k]));
   }
 
-  __shared__ double pinf_s[K * 4][BT];
-  double(*pinf)[BT] = pinf_s;
+  // P_inf: parked in shared memory [element][thread] so that the registers are sized for the regular phase -- except in
+  // the hand-over instantiation, which ends with the diffuse phase and keeps it in registers (its launch was LSU-bound
+  // on this traffic: 72 % of the wavefront rate, FP64 pipe 47 %)
+  __shared__ double pinf_s[HO ? 1 : K * 4][HO ? 1 : BT];
+  double pinf_r[HO ? K * 4 : 1];
   const int tx = threadIdx.x;
+#define PINF(e) (*(HO ? &pinf_r[HO ? (e) : 0] : &pinf_s[HO ? 0 : (e)][HO ? 0 : tx]))
   // ring of blocks of rows of the time-varying Z, one ring per warp (see blk_bulk_rows above)
   __shared__ __align__(128) double zring_s[ZTMA ? BT / 32 : 1][ZTMA ? kBlkZStages : 1][ZTMA ? kBlkZRows : 1][2 * kBlkMaxNB];
   __shared__ __align__(8) unsigned long long zbar_s[ZTMA ? BT / 32 : 1][ZTMA ? kBlkZStages : 1];
@@ -216,10 +220,10 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
       P[k][1] = elem(Ps, md.P_star.diag, i0, k1);
       P[k][2] = elem(Ps, md.P_star.diag, i1, k0);
       P[k][3] = elem(Ps, md.P_star.diag, i1, k1);
-      pinf[k * 4 + 0][tx] = elem(Pi, md.P_inf.diag, i0, k0);
-      pinf[k * 4 + 1][tx] = elem(Pi, md.P_inf.diag, i0, k1);
-      pinf[k * 4 + 2][tx] = elem(Pi, md.P_inf.diag, i1, k0);
-      pinf[k * 4 + 3][tx] = elem(Pi, md.P_inf.diag, i1, k1);
+      PINF(k * 4 + 0) = elem(Pi, md.P_inf.diag, i0, k0);
+      PINF(k * 4 + 1) = elem(Pi, md.P_inf.diag, i0, k1);
+      PINF(k * 4 + 2) = elem(Pi, md.P_inf.diag, i1, k0);
+      PINF(k * 4 + 3) = elem(Pi, md.P_inf.diag, i1, k1);
     }
   }
   double a0, a1;
@@ -392,7 +396,7 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
     // different time points (missing observations), so every group runs this loop until the last one is done ----
     bool small = true;
 #pragma unroll
-    for (int e = 0; e < K * 4; e++) small = small && (fabs(pinf[e][tx]) < kEps);
+    for (int e = 0; e < K * 4; e++) small = small && (fabs(PINF(e)) < kEps);
     bool init = !group_all(small);  // :49
     while (t < N && __any_sync(FULL, init)) {
       for (int j = 0; j < p; j++) {
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
         const double2 ms = complete(ml, cs);
         double Pi[K][4];
 #pragma unroll
-        for (int e = 0; e < K * 4; e++) Pi[e / 4][e % 4] = pinf[e][tx];
+        for (int e = 0; e < K * 4; e++) Pi[e / 4][e % 4] = PINF(e);
         products(Pi, ml, u0, ci);
         const double2 mi = complete(ml, ci);
         const double F_star = group_sum(fma(zi.y, ms.y, zi.x * ms.x));
@@ -438,17 +442,17 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
           P[k][2] = fma(-mi.y, k10, fma(-ms.y, k00, P[k][2]));
           P[k][3] = fma(-mi.y, k11, fma(-ms.y, k01, P[k][3]));
           const double c0 = F1i * iJ.x, c1 = F1i * iJ.y;
-          pinf[k * 4 + 0][tx] = fma(-mi.x, c0, pinf[k * 4 + 0][tx]);
-          pinf[k * 4 + 1][tx] = fma(-mi.x, c1, pinf[k * 4 + 1][tx]);
-          pinf[k * 4 + 2][tx] = fma(-mi.y, c0, pinf[k * 4 + 2][tx]);
-          pinf[k * 4 + 3][tx] = fma(-mi.y, c1, pinf[k * 4 + 3][tx]);
+          PINF(k * 4 + 0) = fma(-mi.x, c0, PINF(k * 4 + 0));
+          PINF(k * 4 + 1) = fma(-mi.x, c1, PINF(k * 4 + 1));
+          PINF(k * 4 + 2) = fma(-mi.y, c0, PINF(k * 4 + 2));
+          PINF(k * 4 + 3) = fma(-mi.y, c1, PINF(k * 4 + 3));
         }
         a0 = fma(fma(F1s, ms.x, F1i * mi.x), vv, a0);
         a1 = fma(fma(F1s, ms.y, F1i * mi.y), vv, a1);
         if (j < p - 1) {  // :157-159 (only after a diffuse update)
           small = true;
 #pragma unroll
-          for (int e = 0; e < K * 4; e++) small = small && (fabs(pinf[e][tx]) < kEps);
+          for (int e = 0; e < K * 4; e++) small = small && (fabs(PINF(e)) < kEps);
           const bool gone = group_all(small);
           if (dif && gone) init = false;
         }
@@ -458,12 +462,12 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
 #pragma unroll
         for (int k = 0; k < K; k++) {
           time_block(k, P[k][0], P[k][1], P[k][2], P[k][3], true);
-          double i0v = pinf[k * 4 + 0][tx], i1v = pinf[k * 4 + 1][tx], i2v = pinf[k * 4 + 2][tx], i3v = pinf[k * 4 + 3][tx];
+          double i0v = PINF(k * 4 + 0), i1v = PINF(k * 4 + 1), i2v = PINF(k * 4 + 2), i3v = PINF(k * 4 + 3);
           time_block(k, i0v, i1v, i2v, i3v, false);
-          pinf[k * 4 + 0][tx] = i0v;
-          pinf[k * 4 + 1][tx] = i1v;
-          pinf[k * 4 + 2][tx] = i2v;
-          pinf[k * 4 + 3][tx] = i3v;
+          PINF(k * 4 + 0) = i0v;
+          PINF(k * 4 + 1) = i1v;
+          PINF(k * 4 + 2) = i2v;
+          PINF(k * 4 + 3) = i3v;
           small = small && (fabs(i0v) < kEps) && (fabs(i1v) < kEps) && (fabs(i2v) < kEps) && (fabs(i3v) < kEps);
         }
         const double na0 = fma(t01, a1, t00 * a0), na1 = fma(t11, a1, t10 * a0);
@@ -541,7 +545,9 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
     F_star = group_sum(fma(zi.y, w1, zi.x * w0));
     za = group_sum(fma(zi.y, a1, zi.x * a0));
   };
-  if constexpr (P1) {
+  if constexpr (HO) {
+    // nothing left: the thread kernel runs the regular phase (an evaluation that reaches this point has t == N)
+  } else if constexpr (P1) {
     // p = 1: the time update does not wait for 1/F.  With M = P z, k = M / F:
     //     T (P - k M') T' + RQR'  =  (T P T' + RQR')  -  (T M)(T M)' / F,        T (a + k v) = T a + (T M) v / F,
     // so the multiply-adds of T P T' are issued while F travels through the butterfly and the reciprocal;
@@ -633,6 +639,8 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
     A.out[e_id] = res;
   }
 }
+
+#undef PINF
 
 // ---- host side -----------------------------------------------------------------------------------
 // States i, k share a block when T or R Q R' couples them.  `Rh` m x r, `qpat` r x r (non-zero pattern of Q as 0/1,
