@@ -47,7 +47,9 @@ int ssgpu_device_count(int* count);
  * ssgpu_loglik_grad_batch then shards its series over them in contiguous ranges -- one worker thread, stream and pinned
  * staging ring per device; every device writes its series' results straight into the caller's arrays (the recursion has
  * no exchange step: nothing is gathered, no collective is needed).  Results are bit-identical to the single-device call.
- * The `_dev` entry points stay on the device of ssgpu_set_device. */
+ * ssgpu_SimSmoother / ssgpu_SimulateModel shard their draws the same way (the variates of a range are gathered on the
+ * host, the outputs of a range are a contiguous block of R's arrays).  The `_dev` entry points stay on the device of
+ * ssgpu_set_device. */
 int ssgpu_use_devices(int n);
 int ssgpu_devices_in_use(int* n);
 int ssgpu_release(void);                     /* free cached device workspaces and pinned staging */

@@ -2,6 +2,8 @@
 // ssgpu_ExtractComponentC (include/ssgpu.h sections 3-5) -- host staging around the kernels of sim.cu.
 #include <cstring>
 
+#include <functional>
+
 #include "common.cuh"
 
 namespace ssgpu {
@@ -496,22 +498,78 @@ static int sim_smoother_impl(int nsim, int N, int p, int n_comp, const ssgpu_sim
   return SSGPU_OK;
 }
 
+// Draws [lo, hi) of a call as their own call: the variates of the reference's consumption order (per component
+// [m x nsim initial draws] then per time point [r_tot x nsim], draws slowest inside each block; the residuals last) are
+// gathered for the range, the outputs are R arrays with the draw index slowest, so the range is a contiguous tail block.
+static int sim_smoother_range(long long lo, long long hi, int nsim, int N, int p, int n_comp, const ssgpu_sim_component* comps,
+                              const double* H, int nH, const ssgpu_sim_model* full, int initialisation_steps,
+                              const double* a_hat, const double* eps_hat, const double* eta_hat, const double* draws,
+                              double* y_out, double* epsilon, double* a_out, double* eta, int n_extract,
+                              const double* const* Z_extract, const int* nZ_extract, double* const* extracted) {
+  const size_t ns = (size_t)nsim, n = (size_t)(hi - lo);
+  std::vector<double> sub;
+  size_t off = 0;
+  int m = 0, r = 0;
+  auto take = [&](size_t width, size_t blocks) {  // `blocks` blocks of width x nsim doubles each
+    for (size_t t = 0; t < blocks; t++) {
+      const double* src = draws + off + t * width * ns + width * (size_t)lo;
+      sub.insert(sub.end(), src, src + width * n);
+    }
+    off += blocks * width * ns;
+  };
+  for (int c = 0; c < n_comp; c++) {
+    const ssgpu_sim_component& C = comps[c];
+    if (C.draw_initial) take((size_t)C.m, 1);
+    take((size_t)C.r * C.repeat_Q, (size_t)N);
+    m += C.m;
+    r += C.r * C.repeat_Q;
+  }
+  take((size_t)p, (size_t)N);
+  std::vector<double*> ext(n_extract > 0 ? n_extract : 0);
+  for (int i = 0; i < n_extract; i++) ext[i] = extracted[i] + (size_t)N * p * (size_t)lo;
+  auto at = [&](double* x, size_t K) { return x ? x + (size_t)N * K * (size_t)lo : nullptr; };
+  return sim_smoother_impl((int)n, N, p, n_comp, comps, H, nH, full, initialisation_steps, a_hat, eps_hat, eta_hat,
+                           sub.data(), (long long)sub.size(), at(y_out, p), at(epsilon, p), at(a_out, m), at(eta, r), n_extract,
+                           Z_extract, nZ_extract, n_extract > 0 ? ext.data() : nullptr);
+}
+
+// Several devices in use (ssgpu_use_devices): the draws are cut into contiguous ranges, one worker thread per device.
+static int sim_smoother_sharded(int nsim, int N, int p, int n_comp, const ssgpu_sim_component* comps, const double* H,
+                                int nH, const ssgpu_sim_model* full, int initialisation_steps, const double* a_hat,
+                                const double* eps_hat, const double* eta_hat, const double* draws, long long n_draws,
+                                double* y_out, double* epsilon, double* a_out, double* eta, int n_extract,
+                                const double* const* Z_extract, const int* nZ_extract, double* const* extracted) {
+  if (devices_in_use() > 1 && nsim >= 64 * devices_in_use() && n_comp >= 1 && comps && draws) {
+    long long need = (long long)N * p * nsim;
+    for (int c = 0; c < n_comp; c++)
+      need += (long long)(comps[c].draw_initial ? (long long)comps[c].m * nsim : 0) +
+              (long long)N * comps[c].r * comps[c].repeat_Q * (long long)nsim;
+    if (need == n_draws)  // a wrong count is reported by the unsharded path below
+      return for_each_device(nsim, 32, [&](int, long long lo, long long hi) {
+        return sim_smoother_range(lo, hi, nsim, N, p, n_comp, comps, H, nH, full, initialisation_steps, a_hat, eps_hat, eta_hat,
+                                  draws, y_out, epsilon, a_out, eta, n_extract, Z_extract, nZ_extract, extracted);
+      });
+  }
+  return sim_smoother_impl(nsim, N, p, n_comp, comps, H, nH, full, initialisation_steps, a_hat, eps_hat, eta_hat, draws,
+                           n_draws, y_out, epsilon, a_out, eta, n_extract, Z_extract, nZ_extract, extracted);
+}
+
 extern "C" int ssgpu_SimSmoother(int nsim, int N, int p, int n_comp, const ssgpu_sim_component* comps, const double* H,
                                  int nH, const ssgpu_sim_model* full, int initialisation_steps,
                                  const double* a_hat, const double* eps_hat, const double* eta_hat, const double* draws,
                                  long long n_draws, double* epsilon, double* a_out, double* eta, int n_extract,
                                  const double* const* Z_extract, const int* nZ_extract, double* const* extracted) {
   SS_ARG(full != nullptr, "SimSmoother: the full model is required");
-  return sim_smoother_impl(nsim, N, p, n_comp, comps, H, nH, full, initialisation_steps, a_hat, eps_hat, eta_hat, draws,
-                           n_draws, nullptr, epsilon, a_out, eta, n_extract, Z_extract, nZ_extract, extracted);
+  return sim_smoother_sharded(nsim, N, p, n_comp, comps, H, nH, full, initialisation_steps, a_hat, eps_hat, eta_hat, draws,
+                              n_draws, nullptr, epsilon, a_out, eta, n_extract, Z_extract, nZ_extract, extracted);
 }
 
 extern "C" int ssgpu_SimulateModel(int nsim, int N, int p, int n_comp, const ssgpu_sim_component* comps, const double* H,
                                    int nH, const double* draws, long long n_draws, double* y, double* epsilon,
                                    double* a_out, double* eta, int n_extract, const double* const* Z_extract,
                                    const int* nZ_extract, double* const* extracted) {
-  return sim_smoother_impl(nsim, N, p, n_comp, comps, H, nH, nullptr, 0, nullptr, nullptr, nullptr, draws, n_draws, y,
-                           epsilon, a_out, eta, n_extract, Z_extract, nZ_extract, extracted);
+  return sim_smoother_sharded(nsim, N, p, n_comp, comps, H, nH, nullptr, 0, nullptr, nullptr, nullptr, draws, n_draws, y,
+                              epsilon, a_out, eta, n_extract, Z_extract, nZ_extract, extracted);
 }
 
 extern "C" int ssgpu_ExtractComponentC_dev(const double* a, int m, int nsim, int N, const double* Z, int p, int nZ,

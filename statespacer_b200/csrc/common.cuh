@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -109,6 +110,8 @@ cudaStream_t lib_copy_stream();  // second stream of the slot (uploads that over
 int ensure_device();
 int dev_slot();                  // device slot of the calling thread (0 unless a worker of for_each_device)
 int devices_in_use();
+// fn(slot, lo, hi) on one worker thread per device slot in use, for the contiguous ranges of 0 .. n (multiples of align)
+int for_each_device(long long n, long long align, const std::function<int(int, long long, long long)>& fn);
 
 class DevBuf {
  public:

@@ -1462,3 +1462,31 @@ def test_loglik_from_theta_with_ldl_covariance_blocks():
         assert out.shape == (3, B) and np.array_equal(out[0], ll, equal_nan=True)
         want = cport.LogLikC(y[:, :, 2], np.isnan(y[:, :, 2]), *build(pts[1, 2]).args())
         assert abs(out[1, 2] - want) <= RTOL * max(1, abs(want))
+
+
+def test_sim_smoother_sharded_over_device_slots():
+    """ssgpu_use_devices + ssgpu_SimSmoother: the draws are cut into contiguous ranges (one worker thread per device slot;
+    on a one-GPU box the slots share the device), each range's variates gathered from the reference's consumption order and
+    its results written into its block of R's arrays: the bits of the unsharded call, for a model whose components draw
+    initial states and repeat Q (structural) and for config 4's SARIMA."""
+    from oracle import sim_smoother  # noqa: F401
+    rng = np.random.default_rng(12)
+    for kind in ("structural", "airline"):
+        c = _sim_smoother_case(kind, rng)
+        nsim, N = 333, c["N"]
+        n_draws = sum((np.asarray(k["a"]).size * nsim if k["draw_initial"] else 0)
+                      + N * np.asarray(k["Q"]).shape[0] * k["repeat_Q"] * nsim for k in c["comps"]) + N * c["p"] * nsim
+        draws = rng.normal(size=n_draws)
+        args = (nsim, N, c["p"], c["comps"], c["H"], c["full"], c["steps"], c["a_hat"], c["eps_hat"], c["eta_hat"], draws)
+        one = api.SimSmoother(*args, extract=c["extract"])
+        os.environ["SSGPU_ALLOW_SHARED_DEVICE"] = "1"
+        try:
+            assert api.use_devices(3) == 3
+            three = api.SimSmoother(*args, extract=c["extract"])
+        finally:
+            api.use_devices(1)
+            del os.environ["SSGPU_ALLOW_SHARED_DEVICE"]
+        for k in ("epsilon", "a", "eta"):
+            assert np.array_equal(one[k], three[k]), (kind, k)
+        for g, w in zip(three["components"], one["components"]):
+            assert np.array_equal(g, w), kind
