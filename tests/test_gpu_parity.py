@@ -1490,3 +1490,63 @@ def test_sim_smoother_sharded_over_device_slots():
             assert np.array_equal(one[k], three[k]), (kind, k)
         for g, w in zip(three["components"], one["components"]):
             assert np.array_equal(g, w), kind
+
+
+def test_thread_kernel_correlated_block_and_scratch_ranges():
+    """The thread-per-evaluation kernel with (i) correlated disturbances INSIDE a 2 x 2 block (level and slope
+    disturbances correlated: R Q R' has off-diagonal entries in the block, the QOFF instantiation) and (ii) a hand-over
+    scratch so small that the batch is cut into many ranges of series (SSGPU_THR_SCRATCH_MB, read once per process: hence
+    the subprocess) -- same values as one range, and as the oracle."""
+    import subprocess
+    import sys
+    import tempfile
+    rng = np.random.default_rng(71)
+    B, N = 41, 50
+    sm = sysmat.bsm12(0.5 * np.log([1.0, 0.1, 0.01, 0.05]))
+    Q = sm.Q[:, :, 0].copy()
+    Q[1, 2] = Q[2, 1] = 0.6 * math.sqrt(Q[1, 1] * Q[2, 2])
+    smq = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=Q[:, :, None], a=sm.a, P_inf=sm.P_inf, P_star=sm.P_star)
+    y = np.stack([simulate_y(rng, smq, N, missing=0.1)[:, 0] for _ in range(B)], axis=1)
+    ab = rng.normal(size=(B, 14)) * 0.1
+    got = api.loglik_batch(y, smq, a=ab, kernel="blk")
+    assert api.last_kernel().startswith("loglik_thr_kernel<NB=7,"), api.last_kernel()
+    lanes = api.loglik_batch(y, smq, a=ab, kernel="blk_lanes")
+    for b in range(B):
+        smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=Q[:, :, None], a=ab[b], P_inf=sm.P_inf, P_star=sm.P_star)
+        want = cport.LogLikC(y[:, b:b + 1], np.isnan(y[:, b:b + 1]), *smb.args())
+        assert abs(got[b] - want) <= RTOL * max(1, abs(want)), (b, got[b], want)
+        assert abs(lanes[b] - want) <= RTOL * max(1, abs(want)), (b, lanes[b], want)
+    # ranges of series: 1 MB of scratch holds ~100 evaluations of 9 parameter vectors
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+from statespacer_b200 import api, sysmat
+rng = np.random.default_rng(5)
+B, N, V = 700, 30, 9
+thetas = 0.5 * np.log([1.0, 0.1, 0.01, 0.05]) + 0.25 * rng.normal(size=(V, B, 4))
+var = np.exp(2 * thetas)
+Qd = np.concatenate([var[..., :3], np.repeat(var[..., 3:4], 11, axis=-1)], axis=-1)
+Pd = np.zeros((V, B, 14)); Pd[..., 0] = var[..., 0]
+y = np.cumsum(rng.normal(size=(N, B)), axis=0)
+y[rng.uniform(size=y.shape) < 0.05] = np.nan
+got = api.loglik_batch(y, sysmat.bsm12(thetas[0, 0]), V=V, Q_diag=Qd, P_star_diag=Pd, kernel="blk")
+assert api.last_kernel().startswith("loglik_thr_kernel<NB=7,")
+from oracle import cport
+for v, b in ((0, 0), (3, 350), (8, 698), (0, 699)):
+    yb = y[:, b:b + 1]
+    want = cport.LogLikC(yb, np.isnan(yb), *sysmat.bsm12(thetas[v, b]).args())
+    assert (np.isnan(want) and np.isnan(got[v, b])) or abs(got[v, b] - want) <= 1e-9 * max(1, abs(want)), (v, b, got[v, b], want)
+np.save(sys.argv[1], got)
+''' % ROOT_DIR
+    with tempfile.TemporaryDirectory() as d:
+        outs = []
+        for tag, env in (("one", {}), ("many", {"SSGPU_THR_SCRATCH_MB": "1"})):
+            r = subprocess.run([sys.executable, "-c", code, os.path.join(d, tag + ".npy")], env={**os.environ, **env},
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(np.load(os.path.join(d, tag + ".npy")))
+        # a range boundary changes which evaluations share a warp of the lane kernel, i.e. the time point at which an
+        # evaluation is handed over (the warp's last group to leave the diffuse phase decides): same arithmetic, a few steps
+        # computed by the other kernel -- equal to rounding, not to the bit
+        assert outs[0].shape == (9, 700) and np.allclose(outs[0], outs[1], rtol=1e-12, atol=0, equal_nan=True)
+        assert np.isnan(outs[0][:, 699]).all() and np.mean(np.isfinite(outs[0])) > 0.9    # series 699: NA in the reference too
