@@ -171,7 +171,7 @@ typedef struct ssgpu_model {
                                    coefficients), R Q R' inside the blocks; at most 8 blocks (m <= 16) with p <= 8, or
                                    up to 16 blocks (m <= 32) with p = 1 and a diagonal R Q R'; Z may be time-varying
                                    when p = 1 (explanatory variables); SSGPU_E_ARG if not eligible.  AUTO tries it
-                                   first.  With 5 to 8 blocks, p = 1 and a time-invariant Z (BASELINE.json config 5)
+                                   first.  With 2 to 8 blocks, p = 1 and a time-invariant Z (BASELINE.json config 5)
                                    the lanes run the exact diffuse phase only and a second kernel, one thread per
                                    evaluation, runs the regular phase */
 #define SSGPU_KERNEL_BLK_LANES 7 /* the same model class on the lane kernel alone (second implementation the tests
@@ -344,7 +344,7 @@ int ssgpu_plan_state_order(const double* T, int m, int* perm, unsigned* tile_mas
 /* The same for the block-row kernel (SSGPU_KERNEL_BLK): T m x m, R m x r, Q r x r or NULL (= diagonal), all
  * column-major.  *n_blocks = number of 2 x 2 blocks, or 0 when the model does not decompose (a state coupled with two
  * others through T or R Q R', more than 16 blocks, p > 8); perm[32]: internal position 2I+e -> state index of the
- * caller, -1 = padding; *lanes = lanes per evaluation of the lane kernel (the diffuse phase; with 5 to 8 blocks and p = 1 the regular phase runs one thread per evaluation); *flop_per_step = FP64 operations the kernel of the regular phase issues per series
+ * caller, -1 = padding; *lanes = lanes per evaluation of the lane kernel (the diffuse phase; with 2 to 8 blocks and p = 1 the regular phase runs one thread per evaluation); *flop_per_step = FP64 operations the kernel of the regular phase issues per series
  * and time step (fma = 2, all lanes). */
 int ssgpu_plan_blocks(const double* T, const double* R, const double* Q, int m, int r, int p, int* perm,
                       int* n_blocks, int* lanes, int* flop_per_step);

@@ -756,8 +756,8 @@ static void launch_blk_nb(const BlkArgs& A, bool q_offdiag, unsigned blocks, cud
     else
       launch_blk_one<L, NB, true, false>(A, blocks, st);
     return;
-  } else if (A.hd) {  // diffuse prologue of the thread kernel (5 to 8 blocks, p = 1, time-invariant Z)
-    if constexpr (NB >= 5) {
+  } else if (A.hd) {  // diffuse prologue of the thread kernel (2 to 8 blocks, p = 1, time-invariant Z)
+    if constexpr (NB >= 2) {
       if (q_offdiag)
         launch_blk_one<L, NB, true, true, false, true>(A, blocks, st);
       else
@@ -968,7 +968,7 @@ extern "C" int ssgpu_plan_blocks(const double* T, const double* R, const double*
   if (perm)
     for (int i = 0; i < 2 * kBlkMaxNB; i++) perm[i] = pl.perm[i];
   if (lanes) *lanes = blk_lanes(pl.nb);
-  // what the automatic dispatch runs: 5 to 8 blocks with p = 1 go to the thread-per-evaluation kernel after the diffuse
+  // what the automatic dispatch runs: 2 to 8 blocks with p = 1 go to the thread-per-evaluation kernel after the diffuse
   // phase (time-invariant Z assumed here: the planner does not see Z)
   if (flop_per_step)
     *flop_per_step = thr_supported(pl.nb, p, false) ? thr_flops_per_step(pl.nb, pl.q_offdiag != 0) : blk_flops_per_step(pl.nb, p);

@@ -3,7 +3,8 @@
 // not fit, in shared memory.
 //
 // Same recursion and model class as loglik_blk.cu (src/LogLikC.cpp:162-207; p = 1, Z / T / R shared by the batch and
-// time-invariant, 5 to 8 blocks: 9 <= m <= 16 -- BASELINE.json config 5 is 7 blocks).  The lane kernel of
+// time-invariant, 2 to 8 blocks: 3 <= m <= 16 -- BASELINE.json config 5 is 7 blocks; up to 4 blocks everything lives in
+// registers at 4 CTAs per SM).  The lane kernel of
 // loglik_blk.cu runs the exact diffuse phase (about d of the N time points, src/LogLikC.cpp:98-159) and leaves the
 // state behind (blk_handoff.cuh); this kernel runs the remaining time points.
 //
@@ -77,7 +78,7 @@ __device__ __forceinline__ int thr_opaque0() {
 
 // S: blocks above the diagonal kept in shared memory (the last S in row-major order)
 template <int NB, int S, bool QOFF>
-__global__ void __launch_bounds__(kThrThreads, 256 / kThrThreads) loglik_thr_kernel(const ThrArgs A) {
+__global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThreads) loglik_thr_kernel(const ThrArgs A) {
   constexpr BlkHandoff HL(NB, QOFF);
   constexpr int NOFF = HL.noff();
   constexpr int RO = NOFF - S;  // blocks above the diagonal in registers
@@ -315,7 +316,10 @@ static int launch_thr_one(const ThrArgs& A, cudaStream_t st) {
   return SSGPU_OK;
 }
 
-bool thr_supported(int nb, int p, bool ztv) { return p == 1 && !ztv && nb >= 5 && nb <= kThrMaxNB; }
+#ifndef SSGPU_THR_MIN_NB
+#define SSGPU_THR_MIN_NB 2
+#endif
+bool thr_supported(int nb, int p, bool ztv) { return p == 1 && !ztv && nb >= SSGPU_THR_MIN_NB && nb <= kThrMaxNB; }
 
 // y, out: of the first series of the launch; hd / hi: filled by the lane kernel for the same E evaluations
 int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* y, long long B, long long E,
@@ -336,12 +340,15 @@ int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double*
   }
   const bool qoff = pl.q_offdiag != 0;
   switch (pl.nb) {
+    case 2: return qoff ? launch_thr_one<2, true>(A, st) : launch_thr_one<2, false>(A, st);
+    case 3: return qoff ? launch_thr_one<3, true>(A, st) : launch_thr_one<3, false>(A, st);
+    case 4: return qoff ? launch_thr_one<4, true>(A, st) : launch_thr_one<4, false>(A, st);
     case 5: return qoff ? launch_thr_one<5, true>(A, st) : launch_thr_one<5, false>(A, st);
     case 6: return qoff ? launch_thr_one<6, true>(A, st) : launch_thr_one<6, false>(A, st);
     case 7: return qoff ? launch_thr_one<7, true>(A, st) : launch_thr_one<7, false>(A, st);
     case 8: return qoff ? launch_thr_one<8, true>(A, st) : launch_thr_one<8, false>(A, st);
   }
-  SS_ARG(false, "thread kernel: 5 to 8 blocks");
+  SS_ARG(false, "thread kernel: 2 to 8 blocks");
 }
 
 }  // namespace ssgpu

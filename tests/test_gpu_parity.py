@@ -360,8 +360,8 @@ def test_batch_blk_kernel(name):
     Pd = np.diag(sm.P_star)[None, :] * scale
     ab = rng.normal(size=(B, m)) * 0.1
     got = api.loglik_batch(y, sm, Q_diag=Qd, P_star_diag=Pd, a=ab, kernel="blk")
-    # 5 to 8 blocks: the lanes run the diffuse phase and hand over to the thread-per-evaluation kernel
-    first = "loglik_thr_kernel<" if 9 <= m <= 16 else "loglik_blk_kernel<"
+    # 2 to 8 blocks: the lanes run the diffuse phase and hand over to the thread-per-evaluation kernel
+    first = "loglik_thr_kernel<" if 3 <= m <= 16 else "loglik_blk_kernel<"
     assert api.last_kernel().startswith(first), api.last_kernel()
     gen = api.loglik_batch(y, sm, Q_diag=Qd, P_star_diag=Pd, a=ab, kernel="generic")
     auto = api.loglik_batch(y, sm, Q_diag=Qd, P_star_diag=Pd, a=ab)
