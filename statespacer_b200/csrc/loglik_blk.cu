@@ -83,6 +83,12 @@ __device__ __forceinline__ double blk_rcp(double x) {
 constexpr int kBlkZStages = 2;
 constexpr int kBlkZRows = 8;
 constexpr int kBlkZRowBytes = 2 * kBlkMaxNB * (int)sizeof(double);
+// Ring of observations (YTMA): per warp kBlkYStages stages of kBlkYRows time points; a row holds the y of the warp's
+// series (at most 32, contiguous in the time-major array) widened to 16-byte alignment: 32 + 2 doubles.  32 time points of
+// look-ahead: a DRAM access is ~800 cycles, a step of the local level model ~100.
+constexpr int kBlkYStages = 4;
+constexpr int kBlkYRows = 8;
+constexpr int kBlkYRowDoubles = 34;
 __device__ __forceinline__ unsigned blk_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void blk_bar_init(unsigned long long* bar) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(blk_smem_u32(bar)));
@@ -117,7 +123,9 @@ __device__ __forceinline__ double2 blk_shfl(double2 x, int src) {
 // ZTV: Z changes with t (explanatory variables, R/Components-Regressors.R:60-78); p = 1 only
 // HO: leave after the diffuse phase and hand the state over (A.hd, A.hi) to the thread kernel
 // ZTMA: the rows of a time-varying Z arrive through the cp.async.bulk ring instead of per-lane loads (SSGPU_BLK_ZTMA=1)
-template <int L, int NB, bool P1, bool QOFF, bool ZTV = false, bool HO = false, bool ZTMA = false>
+// YTMA: the observations of the warp's series arrive through a cp.async.bulk ring (one-lane-per-series models: the step is
+// ~60 instructions and the kernel otherwise waits for DRAM)
+template <int L, int NB, bool P1, bool QOFF, bool ZTV = false, bool HO = false, bool ZTMA = false, bool YTMA = false>
 __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb(NB)) loglik_blk_kernel(const BlkArgs A) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int G = 32 / L;       // evaluations per warp
@@ -206,6 +214,62 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
       }
     }
   };
+  // ring of observations, one per warp (YTMA; p = 1).  The series of the warp's evaluations are b_lo .. b_hi, contiguous
+  // in every row of y; the copy starts at the even index below b_lo and has an even length (16-byte rule of
+  // cp.async.bulk; the launcher has checked that ldy is even and y 16-byte aligned, so no row is overrun).
+  __shared__ __align__(128) double yring_s[YTMA ? BT / 32 : 1][YTMA ? kBlkYStages : 1][YTMA ? kBlkYRows : 1][YTMA ? kBlkYRowDoubles : 1];
+  __shared__ __align__(8) unsigned long long ybar_s[YTMA ? BT / 32 : 1][YTMA ? kBlkYStages : 1];
+  int yblk = -1, ycol = 0;
+  long long ybase = 0;
+  int ybytes = 0;
+  auto y_issue = [&](int blk) {  // lane 0: rows blk * kBlkYRows ... of the warp's column block into stage blk % kBlkYStages
+    const int row0 = blk * kBlkYRows, nr = min(kBlkYRows, N - row0);
+    if (nr <= 0) return;
+    unsigned long long* bar = &ybar_s[warp][blk % kBlkYStages];
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(blk_smem_u32(bar)), "r"(nr * ybytes) : "memory");
+    for (int rr = 0; rr < nr; rr++) {
+      const unsigned d = blk_smem_u32(&yring_s[warp][blk % kBlkYStages][rr][0]);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                   "l"(A.y + ybase + (long long)(row0 + rr) * A.ldy), "r"(ybytes), "r"(blk_smem_u32(bar))
+                   : "memory");
+    }
+  };
+  if constexpr (YTMA) {
+    const long long b_lo = __shfl_sync(FULL, b, 0), b_hi = __shfl_sync(FULL, b, 31);  // evaluations are series-major: b ascends
+    ybase = b_lo & ~1LL;
+    ybytes = (int)(((b_hi - ybase + 1) + 1) & ~1LL) * (int)sizeof(double);
+    ycol = (int)(b - ybase);
+    if (lane == 0) {
+#pragma unroll
+      for (int sg = 0; sg < kBlkYStages; sg++) blk_bar_init(&ybar_s[warp][sg]);
+      blk_bar_fence_init();
+#pragma unroll
+      for (int sg = 0; sg < kBlkYStages; sg++) y_issue(sg);
+    }
+    __syncwarp();
+  }
+  // y of time point t (every t exactly once, ascending): from the ring, or from device memory
+  auto y_get = [&](int t) {
+    if constexpr (YTMA) {
+      const int blk = t / kBlkYRows, sg = blk % kBlkYStages;
+      if (blk != yblk) {
+        blk_bar_wait(&ybar_s[warp][sg], (unsigned)(blk / kBlkYStages) & 1u);
+        yblk = blk;
+      }
+      return yring_s[warp][sg][t & (kBlkYRows - 1)][ycol];
+    } else {
+      return A.y[(long long)t * A.ldy + b];
+    }
+  };
+  auto y_refill = [&](int t) {  // at the end of step t: the block after the last row of a stage has been used
+    if constexpr (YTMA) {
+      if ((t & (kBlkYRows - 1)) == kBlkYRows - 1) {
+        __syncwarp();
+        if (lane == 0) y_issue(t / kBlkYRows + kBlkYStages);
+      }
+    }
+  };
+
   // ---- own blocks of P_star, P_inf, own T blocks, own part of a, own diagonal block of R Q R' ---------------------
   const int i0 = own ? (int)A.perm[2 * I] : -1, i1 = own ? (int)A.perm[2 * I + 1] : -1;
   auto elem = [&](const double* blk, int diag, int i, int k) { return (i >= 0 && k >= 0) ? mat_get(blk, diag, M, i, k) : 0.0; };
@@ -400,7 +464,7 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
     bool init = !group_all(small);  // :49
     while (t < N && __any_sync(FULL, init)) {
       for (int j = 0; j < p; j++) {
-        const double yv = A.y[((long long)t * p + j) * A.ldy + b];
+        const double yv = YTMA ? y_get(t) : A.y[((long long)t * p + j) * A.ldy + b];
         const bool obs = !isnan(yv);  // :88-90
         load_z(t, j);
         const double2 zi = ZK[0];
@@ -477,6 +541,7 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
         if (init && gone) init = false;
       }
       z_refill(t);
+      y_refill(t);
       t++;
     }
   }
@@ -554,14 +619,19 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
     // (T M)_{I+k} is what the lanes ahead hand over and the rank-1 correction comes last.
     if (t < N) {
       // observations are fetched two steps ahead of their use
-      double ynext = A.y[(long long)t * A.ldy + b];
-      double ynext2 = t + 1 < N ? A.y[(long long)(t + 1) * A.ldy + b] : 0.0;
+      double ynext = YTMA ? 0.0 : A.y[(long long)t * A.ldy + b];
+      double ynext2 = (!YTMA && t + 1 < N) ? A.y[(long long)(t + 1) * A.ldy + b] : 0.0;
       double2 ml, u0, c[K];
       double F_star, za;
       for (; t < N - 1; t++) {  // one straight-line block per step
-        const double yv = ynext;
-        ynext = ynext2;
-        if (t + 2 < N) ynext2 = A.y[(long long)(t + 2) * A.ldy + b];
+        double yv;
+        if constexpr (YTMA) {
+          yv = y_get(t);
+        } else {
+          yv = ynext;
+          ynext = ynext2;
+          if (t + 2 < N) ynext2 = A.y[(long long)(t + 2) * A.ldy + b];
+        }
         load_z(t, 0);
         products(P, ml, u0, c);
         innovation_sums(ml, u0, F_star, za);
@@ -584,12 +654,13 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
         a0 = fma(g0, vv, ta0);
         a1 = fma(g1, vv, ta1);
         z_refill(t);
+        y_refill(t);
       }
       // the last observation (:200 -- P and a are not needed afterwards)
       load_z(N - 1, 0);
       products(P, ml, u0, c);
       innovation_sums(ml, u0, F_star, za);
-      observe(ynext, F_star, za);
+      observe(YTMA ? y_get(N - 1) : ynext, F_star, za);
     }
   } else if (t < N) {
     long long idx = (long long)t * p;
@@ -727,8 +798,18 @@ bool blk_eligible(const DModel& md, std::string* why) {
   return true;
 }
 
-template <int L, int NB, bool P1, bool QOFF, bool ZTV = false, bool HO = false, bool ZTMA = false>
+template <int L, int NB, bool P1, bool QOFF, bool ZTV = false, bool HO = false, bool ZTMA = false, bool YTMA = false>
 static void launch_blk_one(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
+  if constexpr (L == 1 && P1 && !ZTV && !HO && !YTMA) {
+    // one lane per series (local level and the like): observations through the bulk-copy ring unless SSGPU_BLK_YTMA=0
+    // (rows must be 16-byte aligned at even series offsets: even number of series, aligned y)
+    static const bool ytma = [] {
+      const char* e = getenv("SSGPU_BLK_YTMA");
+      return !(e && e[0] == '0');
+    }();
+    if (ytma && A.ldy % 2 == 0 && (reinterpret_cast<unsigned long long>(A.y) & 15ull) == 0)
+      return launch_blk_one<L, NB, P1, QOFF, ZTV, HO, ZTMA, true>(A, blocks, st);
+  }
   if constexpr (ZTV && !ZTMA && NB <= 8) {
     // SSGPU_BLK_ZTMA=1: time-varying Z through the bulk-copy ring (measured slower than the per-lane loads: DESIGN.md)
     static const bool ztma = [] {
@@ -744,8 +825,8 @@ static void launch_blk_one(const BlkArgs& A, unsigned blocks, cudaStream_t st) {
     return e ? atoi(e) : 0;
   }();
   if (pad > 0)
-    cudaFuncSetAttribute(loglik_blk_kernel<L, NB, P1, QOFF, ZTV, HO, ZTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
-  loglik_blk_kernel<L, NB, P1, QOFF, ZTV, HO, ZTMA><<<blocks, NB > 8 ? kBlkThreadsCS : kBlkThreads, pad, st>>>(A);
+    cudaFuncSetAttribute(loglik_blk_kernel<L, NB, P1, QOFF, ZTV, HO, ZTMA, YTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad);
+  loglik_blk_kernel<L, NB, P1, QOFF, ZTV, HO, ZTMA, YTMA><<<blocks, NB > 8 ? kBlkThreadsCS : kBlkThreads, pad, st>>>(A);
 }
 
 template <int L, int NB>

@@ -1550,3 +1550,31 @@ np.save(sys.argv[1], got)
         # computed by the other kernel -- equal to rounding, not to the bit
         assert outs[0].shape == (9, 700) and np.allclose(outs[0], outs[1], rtol=1e-12, atol=0, equal_nan=True)
         assert np.isnan(outs[0][:, 699]).all() and np.mean(np.isfinite(outs[0])) > 0.9    # series 699: NA in the reference too
+
+
+@pytest.mark.parametrize("B,N,V", [(64, 100, 1), (1000, 61, 1), (96, 5, 1), (130, 37, 3), (37, 40, 1)])
+def test_local_level_observations_through_bulk_copy_ring(B, N, V):
+    """One lane per series (local level, config 1's model batched): the observations of a warp's series reach it through a
+    ring of shared-memory stages filled by cp.async.bulk with mbarrier completion (TMA), 32 time points ahead -- on when
+    the number of series is even (16-byte rows), plain loads otherwise (B = 37).  Series lengths that are not a multiple
+    of the 8-row stage or shorter than one stage, several parameter vectors per series (narrower rows), missing values;
+    against the oracle and the generic kernel."""
+    rng = np.random.default_rng(B + N)
+    sm = sysmat.nile_local_level(1.3, 0.4)
+    y = np.cumsum(rng.normal(size=(N, B)), axis=0) + rng.normal(size=(N, B))
+    y[rng.uniform(size=y.shape) < 0.1] = np.nan
+    y[:, 3] = np.nan                                      # a series that is never observed: NA
+    sc = rng.uniform(0.5, 2.0, size=(V, B, 1))
+    Qd = np.array([1.3, 0.4])[None, None, :] * sc
+    Pd = np.array([1.3, 0.0])[None, None, :] * sc
+    got = api.loglik_batch(y, sm, V=V, Q_diag=Qd if V > 1 else Qd[0], P_star_diag=Pd if V > 1 else Pd[0], kernel="blk")
+    assert api.last_kernel().startswith("loglik_blk_kernel<L=1,NB=1,"), api.last_kernel()
+    gen = api.loglik_batch(y, sm, V=V, Q_diag=Qd if V > 1 else Qd[0], P_star_diag=Pd if V > 1 else Pd[0], kernel="generic")
+    got, gen = got.reshape(V, B), gen.reshape(V, B)
+    assert np.all(np.isnan(got[:, 3])) and np.all(np.isfinite(np.delete(got, 3, axis=1)))
+    assert np.allclose(got, gen, rtol=1e-12, atol=1e-12, equal_nan=True)
+    for v in range(V):
+        for b in range(0, B, max(1, B // 9)):
+            smb = sysmat.nile_local_level(1.3 * sc[v, b, 0], 0.4 * sc[v, b, 0])
+            want = cport.LogLikC(y[:, b:b + 1], np.isnan(y[:, b:b + 1]), *smb.args())
+            assert (math.isnan(want) and math.isnan(got[v, b])) or abs(got[v, b] - want) <= RTOL * max(1, abs(want)), (v, b)
