@@ -390,6 +390,18 @@ int ssgpu_release(void) {
     SS_CUDA(cudaDeviceGetDefaultMemPool(&pool, c.device));
     SS_CUDA(cudaMemPoolTrimTo(pool, 0));
   }
+  for (int s2 = 0; s2 < kMaxDev; s2++) {  // call arenas (pinned staging + device block per slot)
+    CallArena& ar = g_arena[s2];
+    std::lock_guard<std::mutex> lk(ar.mu);
+    if (!ar.ready) continue;
+    if (g_ctx[s2].ready) cudaSetDevice(g_ctx[s2].device);
+    cudaFreeHost(ar.host);
+    cudaFree(ar.dev);
+    cudaFreeHost(ar.res_host);
+    ar.host = ar.dev = nullptr;
+    ar.res_host = nullptr;
+    ar.ready = false;
+  }
   SS_CUDA(cudaSetDevice(g_ctx[0].device));
   xfer_release();
   return SSGPU_OK;
