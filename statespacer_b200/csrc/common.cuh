@@ -306,8 +306,8 @@ bool thr_supported(int nb, int p, bool ztv);
 size_t thr_handoff_bytes(int nb, bool qoff, long long E);
 int thr_flops_per_step(int nb, bool qoff);
 int thr_smem_blocks_host(int nb);
-int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* y, long long B, long long E,
-                      long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st);
+int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* zt, const double* y, long long B,
+                      long long E, long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st);
 
 // Column-per-thread register kernel (loglik_cols.cu)
 bool cols_eligible(const DModel& md, std::string* why);

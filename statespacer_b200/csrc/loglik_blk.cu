@@ -837,12 +837,18 @@ static void launch_blk_nb(const BlkArgs& A, bool q_offdiag, unsigned blocks, cud
     else
       launch_blk_one<L, NB, true, false>(A, blocks, st);
     return;
-  } else if (A.hd) {  // diffuse prologue of the thread kernel (2 to 8 blocks, p = 1, time-invariant Z)
+  } else if (A.hd) {  // diffuse prologue of the thread kernel (2 to 8 blocks, p = 1)
     if constexpr (NB >= 2) {
-      if (q_offdiag)
+      if (A.zt) {
+        if (q_offdiag)
+          launch_blk_one<L, NB, true, true, true, true>(A, blocks, st);
+        else
+          launch_blk_one<L, NB, true, false, true, true>(A, blocks, st);
+      } else if (q_offdiag) {
         launch_blk_one<L, NB, true, true, false, true>(A, blocks, st);
-      else
+      } else {
         launch_blk_one<L, NB, true, false, false, true>(A, blocks, st);
+      }
     }
   } else if (A.md.p == 1 && A.zt) {
     if (q_offdiag)
@@ -1012,11 +1018,12 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
       Ac.hd = scratch.as<double>();
       Ac.hi = reinterpret_cast<int*>(Ac.hd + (size_t)hl.doubles() * Ec);
       SS_TRY(launch_lanes(Ac));
-      SS_TRY(launch_loglik_thr(pl, &A.z[0][0], Ac.y, Bc, Ec, B, md.N, Ac.hd, Ac.hi, Ac.out, st));
+      SS_TRY(launch_loglik_thr(pl, &A.z[0][0], A.zt, Ac.y, Bc, Ec, B, md.N, Ac.hd, Ac.hi, Ac.out, st));
       count_launch();
     }
-    snprintf(name, sizeof name, "loglik_thr_kernel<NB=%d,S=%d,flop_per_step=%d> after loglik_blk_kernel<L=%d,NB=%d> (diffuse phase)",
-             pl.nb, thr_smem_blocks_host(pl.nb), thr_flops_per_step(pl.nb, pl.q_offdiag != 0), L, pl.nb);
+    snprintf(name, sizeof name, "loglik_thr_kernel<NB=%d,S=%d,flop_per_step=%d>%s after loglik_blk_kernel<L=%d,NB=%d> (diffuse phase)",
+             pl.nb, thr_smem_blocks_host(pl.nb), thr_flops_per_step(pl.nb, pl.q_offdiag != 0), nZ > 1 ? " time-varying Z" : "", L,
+             pl.nb);
     set_last_kernel(name);
     return SSGPU_OK;
   }

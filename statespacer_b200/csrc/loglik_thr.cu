@@ -50,6 +50,7 @@ struct ThrArgs {
   const int* hi;
   double* out;  // [v * ldy + b]
   double cst[kThrMaxNB][6];  // T_I row-major (4), z_I (2): internal order of the block plan
+  const double* zt;          // time-varying Z (explanatory variables): [t][32] in internal order, device memory; else null
 };
 
 __device__ __forceinline__ double thr_rsqrt(double x) {
@@ -77,7 +78,11 @@ __device__ __forceinline__ int thr_opaque0() {
 }
 
 // S: blocks above the diagonal kept in shared memory (the last S in row-major order)
-template <int NB, int S, bool QOFF>
+// ZTV: Z changes with t (R/Components-Regressors.R:60-78): the row of a time point is loaded by every thread for ITS time
+// point (the threads of a warp differ by a few steps at most: a handful of L1-resident lines) into registers that replace
+// the uniform-register copies of z; F = z'M and z'a of a step are formed right behind the sweep that accumulated M, while
+// that row is still at hand, and carried into the next iteration.
+template <int NB, int S, bool QOFF, bool ZTV = false>
 __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThreads) loglik_thr_kernel(const ThrArgs A) {
   constexpr BlkHandoff HL(NB, QOFF);
   constexpr int NOFF = HL.noff();
@@ -121,6 +126,19 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
   double prod = hd[(long long)HL.s() * E], sumq = hd[(long long)(HL.s() + 1) * E];
   int esum = A.hi[E + w], n_upd = 0, n_obs = 0;
 
+  double zr[ZTV ? NB : 1][2];  // ZTV: the row of Z the M being accumulated belongs to
+  auto load_z = [&](int tt) {
+    if constexpr (ZTV) {
+      const double2* zp = reinterpret_cast<const double2*>(A.zt + (size_t)tt * 32);
+#pragma unroll
+      for (int I = 0; I < NB; I++) {
+        const double2 z2 = zp[I];
+        zr[I][0] = z2.x;
+        zr[I][1] = z2.y;
+      }
+    }
+  };
+  load_z(t);
   // M = P z of the first time point (afterwards every sweep leaves the next step's M behind)
   {
     int oi = 0;
@@ -128,12 +146,12 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
     for (int I = 0; I < NB; I++) M[I][0] = M[I][1] = 0.0;
 #pragma unroll
     for (int I = 0; I < NB; I++) {
-      const double zi0 = A.cst[I][4], zi1 = A.cst[I][5];
+      const double zi0 = ZTV ? zr[ZTV ? I : 0][0] : A.cst[I][4], zi1 = ZTV ? zr[ZTV ? I : 0][1] : A.cst[I][5];
       M[I][0] = fma(D[I][1], zi1, fma(D[I][0], zi0, M[I][0]));
       M[I][1] = fma(D[I][2], zi1, fma(D[I][1], zi0, M[I][1]));
 #pragma unroll
       for (int J = I + 1; J < NB; J++, oi++) {
-        const double zj0 = A.cst[J][4], zj1 = A.cst[J][5];
+        const double zj0 = ZTV ? zr[ZTV ? J : 0][0] : A.cst[J][4], zj1 = ZTV ? zr[ZTV ? J : 0][1] : A.cst[J][5];
         double p0, p1, p2, p3;
         if (oi < RO) {
           p0 = O[oi < RO ? oi : 0][0], p1 = O[oi < RO ? oi : 0][1], p2 = O[oi < RO ? oi : 0][2], p3 = O[oi < RO ? oi : 0][3];
@@ -169,32 +187,47 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
 
   const double* yp = A.y + b + (long long)t * A.ldy;
   double ynext = *yp;
+  double Fc = 0.0, zac = 0.0;  // ZTV: F = z'M and z'a of the coming step
+  if constexpr (ZTV) {
+#pragma unroll
+    for (int I = 0; I < NB; I++) {
+      Fc = fma(zr[ZTV ? I : 0][1], M[I][1], fma(zr[ZTV ? I : 0][0], M[I][0], Fc));
+      zac = fma(zr[ZTV ? I : 0][1], SA(2 * I + 1), fma(zr[ZTV ? I : 0][0], SA(2 * I), zac));
+    }
+  }
   for (; t < N - 1; t++) {
     const double yv = ynext;
     yp += A.ldy;
     ynext = *yp;
     // ---- the vectors: tm = T M (in place), F = z'M, z'a, T a
-    double F = 0.0, za = 0.0, ta[NB][2];
+    double F = Fc, za = zac, ta[NB][2];
     const double* const cv0 = &A.cst[0][0] + thr_opaque0();
 #pragma unroll
     for (int I = 0; I < NB; I++) {
-      const double t00 = cv0[I * 6], t01 = cv0[I * 6 + 1], t10 = cv0[I * 6 + 2], t11 = cv0[I * 6 + 3], z0 = cv0[I * 6 + 4], z1 = cv0[I * 6 + 5];
+      const double t00 = cv0[I * 6], t01 = cv0[I * 6 + 1], t10 = cv0[I * 6 + 2], t11 = cv0[I * 6 + 3];
       const double m0 = M[I][0], m1 = M[I][1], a0 = SA(2 * I), a1 = SA(2 * I + 1);
-      F = fma(z1, m1, fma(z0, m0, F));
-      za = fma(z1, a1, fma(z0, a0, za));
+      if constexpr (!ZTV) {
+        const double z0 = cv0[I * 6 + 4], z1 = cv0[I * 6 + 5];
+        F = fma(z1, m1, fma(z0, m0, F));
+        za = fma(z1, a1, fma(z0, a0, za));
+      }
       M[I][0] = fma(t01, m1, t00 * m0);
       M[I][1] = fma(t11, m1, t10 * m0);
       ta[I][0] = fma(t01, a1, t00 * a0);
       ta[I][1] = fma(t11, a1, t10 * a0);
     }
     observe(yv, F, za);
+    load_z(t + 1);  // ZTV: the row the sweep below accumulates the next M with
+    zac = 0.0;
     double s[NB][2];
 #pragma unroll
     for (int I = 0; I < NB; I++) {
       s[I][0] = M[I][0] * r;
       s[I][1] = M[I][1] * r;
-      SA(2 * I) = fma(s[I][0], cv, ta[I][0]);
-      SA(2 * I + 1) = fma(s[I][1], cv, ta[I][1]);
+      const double n0 = fma(s[I][0], cv, ta[I][0]), n1 = fma(s[I][1], cv, ta[I][1]);
+      SA(2 * I) = n0;
+      SA(2 * I + 1) = n1;
+      if constexpr (ZTV) zac = fma(zr[ZTV ? I : 0][1], n1, fma(zr[ZTV ? I : 0][0], n0, zac));
       M[I][0] = 0.0;
       M[I][1] = 0.0;
     }
@@ -203,7 +236,8 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
 #pragma unroll
     for (int I = 0; I < NB; I++) {
       const double* const ci = &A.cst[0][0] + thr_opaque0();
-      const double t00 = ci[I * 6], t01 = ci[I * 6 + 1], t10 = ci[I * 6 + 2], t11 = ci[I * 6 + 3], zi0 = ci[I * 6 + 4], zi1 = ci[I * 6 + 5];
+      const double t00 = ci[I * 6], t01 = ci[I * 6 + 1], t10 = ci[I * 6 + 2], t11 = ci[I * 6 + 3];
+      const double zi0 = ZTV ? zr[ZTV ? I : 0][0] : ci[I * 6 + 4], zi1 = ZTV ? zr[ZTV ? I : 0][1] : ci[I * 6 + 5];
       {
         double p0 = D[I][0], p1 = D[I][1], p3 = D[I][2];
         const double y00 = fma(t01, p1, t00 * p0), y01 = fma(t01, p3, t00 * p1);
@@ -223,7 +257,8 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
 #pragma unroll
       for (int J = I + 1; J < NB; J++, oi++) {
         const double* const cj = &A.cst[0][0] + thr_opaque0();
-        const double u00 = cj[J * 6], u01 = cj[J * 6 + 1], u10 = cj[J * 6 + 2], u11 = cj[J * 6 + 3], zj0 = cj[J * 6 + 4], zj1 = cj[J * 6 + 5];
+        const double u00 = cj[J * 6], u01 = cj[J * 6 + 1], u10 = cj[J * 6 + 2], u11 = cj[J * 6 + 3];
+        const double zj0 = ZTV ? zr[ZTV ? J : 0][0] : cj[J * 6 + 4], zj1 = ZTV ? zr[ZTV ? J : 0][1] : cj[J * 6 + 5];
         double p0, p1, p2, p3;
         if (oi < RO) {
           p0 = O[oi < RO ? oi : 0][0], p1 = O[oi < RO ? oi : 0][1], p2 = O[oi < RO ? oi : 0][2], p3 = O[oi < RO ? oi : 0][3];
@@ -249,13 +284,20 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
         M[J][1] = fma(p3, zi1, fma(p1, zi0, M[J][1]));
       }
     }
+    if constexpr (ZTV) {
+      Fc = 0.0;
+#pragma unroll
+      for (int I = 0; I < NB; I++) Fc = fma(zr[ZTV ? I : 0][1], M[I][1], fma(zr[ZTV ? I : 0][0], M[I][0], Fc));
+    }
   }
   {  // the last observation (src/LogLikC.cpp:200 -- P and a are not needed afterwards)
-    double F = 0.0, za = 0.0;
+    double F = Fc, za = zac;
+    if constexpr (!ZTV) {
 #pragma unroll
-    for (int I = 0; I < NB; I++) {
-      F = fma(A.cst[I][5], M[I][1], fma(A.cst[I][4], M[I][0], F));
-      za = fma(A.cst[I][5], SA(2 * I + 1), fma(A.cst[I][4], SA(2 * I), za));
+      for (int I = 0; I < NB; I++) {
+        F = fma(A.cst[I][5], M[I][1], fma(A.cst[I][4], M[I][0], F));
+        za = fma(A.cst[I][5], SA(2 * I + 1), fma(A.cst[I][4], SA(2 * I), za));
+      }
     }
     observe(ynext, F, za);
   }
@@ -302,16 +344,20 @@ int thr_flops_per_step(int nb, bool qoff) {
   return 2 * fma + mul + add_s;
 }
 
-template <int NB, bool QOFF>
+template <int NB, bool QOFF, bool ZTV = false>
 static int launch_thr_one(const ThrArgs& A, cudaStream_t st) {
-  constexpr int S = thr_smem_blocks(NB);
+  // time-varying Z: 2 NB more vector registers hold the row of Z, so two more blocks move to shared memory (NB >= 5)
+#ifndef SSGPU_THR_ZX
+#define SSGPU_THR_ZX 3
+#endif
+  constexpr int S = thr_smem_blocks(NB) + ((ZTV && NB >= 5) ? (NB >= 7 ? SSGPU_THR_ZX : 2) : 0);
   constexpr BlkHandoff HL(NB, QOFF);
   const size_t smem = (size_t)((2 + HL.qw) * NB + 4 * S) * kThrThreads * sizeof(double);
   // a function attribute belongs to the device it was set on (one slot per device: api.cu)
-  SS_CUDA(cudaFuncSetAttribute(loglik_thr_kernel<NB, S, QOFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SS_CUDA(cudaFuncSetAttribute(loglik_thr_kernel<NB, S, QOFF, ZTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (A.E + kThrThreads - 1) / kThrThreads;
   SS_ARG(blocks < (1LL << 31), "thread kernel: batch too large for one launch");
-  loglik_thr_kernel<NB, S, QOFF><<<(unsigned)blocks, kThrThreads, smem, st>>>(A);
+  loglik_thr_kernel<NB, S, QOFF, ZTV><<<(unsigned)blocks, kThrThreads, smem, st>>>(A);
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;
 }
@@ -319,12 +365,13 @@ static int launch_thr_one(const ThrArgs& A, cudaStream_t st) {
 #ifndef SSGPU_THR_MIN_NB
 #define SSGPU_THR_MIN_NB 2
 #endif
-bool thr_supported(int nb, int p, bool ztv) { return p == 1 && !ztv && nb >= SSGPU_THR_MIN_NB && nb <= kThrMaxNB; }
+bool thr_supported(int nb, int p, bool ztv) { (void)ztv; return p == 1 && nb >= SSGPU_THR_MIN_NB && nb <= kThrMaxNB; }
 
 // y, out: of the first series of the launch; hd / hi: filled by the lane kernel for the same E evaluations
-int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* y, long long B, long long E,
-                      long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st) {
+int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* zt, const double* y, long long B,
+                      long long E, long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st) {
   ThrArgs A{};
+  A.zt = zt;
   A.y = y;
   A.B = B;
   A.E = E;
@@ -339,15 +386,14 @@ int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double*
     A.cst[I][5] = z_internal[2 * I + 1];
   }
   const bool qoff = pl.q_offdiag != 0;
+#define SS_THR_CASE(NBV)                                                                                                  \
+  case NBV:                                                                                                               \
+    return zt ? (qoff ? launch_thr_one<NBV, true, true>(A, st) : launch_thr_one<NBV, false, true>(A, st))                 \
+              : (qoff ? launch_thr_one<NBV, true>(A, st) : launch_thr_one<NBV, false>(A, st));
   switch (pl.nb) {
-    case 2: return qoff ? launch_thr_one<2, true>(A, st) : launch_thr_one<2, false>(A, st);
-    case 3: return qoff ? launch_thr_one<3, true>(A, st) : launch_thr_one<3, false>(A, st);
-    case 4: return qoff ? launch_thr_one<4, true>(A, st) : launch_thr_one<4, false>(A, st);
-    case 5: return qoff ? launch_thr_one<5, true>(A, st) : launch_thr_one<5, false>(A, st);
-    case 6: return qoff ? launch_thr_one<6, true>(A, st) : launch_thr_one<6, false>(A, st);
-    case 7: return qoff ? launch_thr_one<7, true>(A, st) : launch_thr_one<7, false>(A, st);
-    case 8: return qoff ? launch_thr_one<8, true>(A, st) : launch_thr_one<8, false>(A, st);
+    SS_THR_CASE(2) SS_THR_CASE(3) SS_THR_CASE(4) SS_THR_CASE(5) SS_THR_CASE(6) SS_THR_CASE(7) SS_THR_CASE(8)
   }
+#undef SS_THR_CASE
   SS_ARG(false, "thread kernel: 2 to 8 blocks");
 }
 

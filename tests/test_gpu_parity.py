@@ -404,18 +404,24 @@ def test_batch_blk_kernel_time_varying_z(seasonal):
     Qd = np.diag(base.Q[:, :, 0])[None, :] * scale
     got = api.loglik_batch(y, sm, Q_diag=Qd, kernel="blk")
     assert "time-varying Z" in api.last_kernel(), api.last_kernel()
+    # up to 8 blocks the regular phase runs one thread per evaluation (the row of Z loaded per step), beyond on the lanes
+    first = "loglik_thr_kernel<" if m <= 16 else "loglik_blk_kernel<"
+    assert api.last_kernel().startswith(first), api.last_kernel()
+    lanes = api.loglik_batch(y, sm, Q_diag=Qd, kernel="blk_lanes")
+    assert api.last_kernel().startswith("loglik_blk_kernel<") and "time-varying Z" in api.last_kernel()
     gen = api.loglik_batch(y, sm, Q_diag=Qd, kernel="generic")
     auto = api.loglik_batch(y, sm, Q_diag=Qd)
-    assert api.last_kernel().startswith("loglik_blk_kernel<") and np.array_equal(auto, got) and np.all(np.isfinite(got))
+    assert api.last_kernel().startswith(first) and np.array_equal(auto, got) and np.all(np.isfinite(got))
     for b in range(B):
         smb = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=np.diag(Qd[b])[:, :, None], a=sm.a, P_inf=sm.P_inf, P_star=sm.P_star)
         yb = y[:, b:b + 1]
         want, tol = loglik_want(yb, np.isnan(yb), *smb.args())
         assert abs(got[b] - want) <= tol, (b, got[b], want)
+        assert abs(lanes[b] - want) <= tol, (b, lanes[b], want)
         assert abs(gen[b] - want) <= tol, (b, gen[b], want)
         if b < 3:                                     # the single-series entry point takes the same kernel
             one = api.LogLikC(yb, np.isnan(yb), *smb.args())
-            assert api.last_kernel().startswith("loglik_blk_kernel<") and abs(one - got[b]) <= 1e-13 * abs(one)
+            assert api.last_kernel().startswith(first) and abs(one - got[b]) <= 1e-12 * abs(one)
 
 
 def test_batch_blk_kernel_bivariate_dense_blocks():
@@ -1392,8 +1398,8 @@ for N in (61, 5):
                        R=np.concatenate([np.eye(m0), np.zeros((2, m0))], axis=0)[:, :, None], Q=base.Q, a=np.zeros(m),
                        P_inf=sysmat.block_diag(base.P_inf, np.eye(2)), P_star=sysmat.block_diag(base.P_star, np.zeros((2, 2))))
     y = np.stack([simulate_y(rng, base, N, missing=0.08)[:, 0] + X @ np.array([1.5, -0.7]) for _ in range(45)], axis=1)
-    got = api.loglik_batch(y, sm, kernel="blk")
-    assert "time-varying Z" in api.last_kernel()
+    got = api.loglik_batch(y, sm, kernel="blk_lanes")
+    assert "time-varying Z" in api.last_kernel() and api.last_kernel().startswith("loglik_blk_kernel<")
     np.save(sys.argv[1] + "_%%d.npy" %% N, got)
 ''' % (ROOT_DIR, ROOT_DIR)
     import tempfile
