@@ -136,6 +136,7 @@ struct CallArena {
   void* host = nullptr;
   void* dev = nullptr;
   double* res_host = nullptr;
+  size_t used = 0;  // bytes of the blocks taken by the upload of the current call (the rest is free for its results)
   bool ready = false;
   int init() {
     if (ready) return SSGPU_OK;
@@ -153,10 +154,12 @@ struct ArenaLease {
   ArenaLease() {
     CallArena& c = g_arena[t_slot];
     if (c.mu.try_lock()) {
-      if (c.init() == SSGPU_OK)
+      if (c.init() == SSGPU_OK) {
         a = &c;
-      else
+        c.used = 0;
+      } else {
         c.mu.unlock();
+      }
     }
   }
   ~ArenaLease() {
@@ -188,6 +191,7 @@ class Packer {
       std::memcpy(arena->host, buf_.data(), bytes);
       d.borrow(arena->dev);
       SS_CUDA(cudaMemcpyAsync(arena->dev, arena->host, bytes, cudaMemcpyHostToDevice, st));
+      arena->used = bytes;
       return SSGPU_OK;
     }
     SS_TRY(d.alloc(bytes, st));
@@ -464,8 +468,9 @@ int ssgpu_KalmanC(const double* y, const int* y_isna, int N, int p, int m, int r
   SS_TRY(check_single(N, p, m, r, nZ, nT, nR, nQ));
   SS_TRY(ensure_device());
   cudaStream_t st = lib_stream();
+  ArenaLease lease;  // small calls: arguments and results through the per-device arena (one copy each way, no allocator)
   SingleModel S;
-  SS_TRY(stage_single(S, y, y_isna, N, p, m, r, a, P_inf, P_star, Z, nZ, T, nT, R, nR, Q, nQ, st));
+  SS_TRY(stage_single(S, y, y_isna, N, p, m, r, a, P_inf, P_star, Z, nZ, T, nT, R, nR, Q, nQ, st, lease.a));
 
   // one device block for every output + the backward-pass scratch
   const size_t Np = (size_t)N * p, mm = (size_t)m * m;
@@ -511,7 +516,15 @@ int ssgpu_KalmanC(const double* y, const int* y_isna, int N, int p, int m, int r
   const size_t n_diag = diagnostics ? pad(2 * (size_t)N * m * p) : 0;
   const size_t n_scr = pad(Np) * 3 + pad(Np * m) * 2 + pad((size_t)(qtr_tv ? N : 1) * r * m) + pad(Np) + 32 + n_diag;
   DevBuf blk;
-  SS_TRY(blk.alloc((total + n_scr) * sizeof(double), st));
+  // results + scratch behind the uploaded arguments in the arena's device block when they fit: the results then come
+  // back with ONE copy into the arena's pinned block and are handed out from there (27 copies into pageable memory, each
+  // staged and synchronised by the driver, were half of a Nile call's 1.4 ms)
+  const size_t up = lease.a ? (lease.a->used + 255) / 256 * 256 : 0;
+  const bool in_arena = lease.a && lease.a->used > 0 && up + (total + n_scr) * sizeof(double) <= kArenaBytes;
+  if (in_arena)
+    blk.borrow(static_cast<char*>(lease.a->dev) + up);
+  else
+    SS_TRY(blk.alloc((total + n_scr) * sizeof(double), st));
   double* base = blk.as<double>();
   size_t off = 0;
   for (auto& x : f) {
@@ -519,6 +532,7 @@ int ssgpu_KalmanC(const double* y, const int* y_isna, int N, int p, int m, int r
     off += pad(x.n);
   }
   KalmanScratch s{};
+  d.initialisation_steps = reinterpret_cast<int*>(base + off); off += 32;  // right behind the results: one copy takes both
   s.F1 = base + off; off += pad(Np);
   s.F2 = base + off; off += pad(Np);
   s.v = base + off; off += pad(Np);
@@ -526,13 +540,22 @@ int ssgpu_KalmanC(const double* y, const int* y_isna, int N, int p, int m, int r
   s.K1 = base + off; off += pad(Np * m);
   s.QtR = base + off; off += pad((size_t)(qtr_tv ? N : 1) * r * m);
   s.code = reinterpret_cast<int*>(base + off); off += pad(Np);
-  d.initialisation_steps = reinterpret_cast<int*>(base + off); off += 32;
   double* diag_scr = base + off; off += n_diag;
 
   const double* yd = S.dev.as<double>() + S.oy;
   SS_TRY(launch_fwd_generic(S.md, yd, 1, 1, nullptr, &d, &s, st));
   SS_TRY(launch_bwd_generic(S.md, &d, &s, st));
   if (diagnostics) SS_TRY(launch_kalman_diag(S.md, &d, s.code, diag_scr, st));
+  if (in_arena) {
+    char* hb = static_cast<char*>(lease.a->host) + up;
+    SS_CUDA(cudaMemcpyAsync(hb, base, (total + 32) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    SS_CUDA(cudaStreamSynchronize(st));
+    for (auto& x : f)
+      if (*x.host && x.n) std::memcpy(*x.host, hb + ((*x.dev) - base) * sizeof(double), x.n * sizeof(double));
+    if (out->initialisation_steps)
+      std::memcpy(out->initialisation_steps, hb + (reinterpret_cast<double*>(d.initialisation_steps) - base) * sizeof(double), sizeof(int));
+    return SSGPU_OK;
+  }
   for (auto& x : f)
     if (*x.host && x.n)
       SS_CUDA(cudaMemcpyAsync(*x.host, *x.dev, x.n * sizeof(double), cudaMemcpyDeviceToHost, st));

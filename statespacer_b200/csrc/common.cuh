@@ -305,7 +305,7 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
 bool thr_supported(int nb, int p, bool ztv);
 size_t thr_handoff_bytes(int nb, bool qoff, long long E);
 int thr_flops_per_step(int nb, bool qoff);
-int thr_smem_blocks_host(int nb);
+int thr_smem_blocks_host(int nb, bool ztv);
 int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* zt, const double* y, long long B,
                       long long E, long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st);
 

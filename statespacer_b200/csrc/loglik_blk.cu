@@ -1022,7 +1022,7 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
       count_launch();
     }
     snprintf(name, sizeof name, "loglik_thr_kernel<NB=%d,S=%d,flop_per_step=%d>%s after loglik_blk_kernel<L=%d,NB=%d> (diffuse phase)",
-             pl.nb, thr_smem_blocks_host(pl.nb), thr_flops_per_step(pl.nb, pl.q_offdiag != 0), nZ > 1 ? " time-varying Z" : "", L,
+             pl.nb, thr_smem_blocks_host(pl.nb, nZ > 1), thr_flops_per_step(pl.nb, pl.q_offdiag != 0), nZ > 1 ? " time-varying Z" : "", L,
              pl.nb);
     set_last_kernel(name);
     return SSGPU_OK;

@@ -321,8 +321,11 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
 #define SSGPU_THR_S8 17
 #endif
 constexpr int thr_smem_blocks(int nb) { return nb == 8 ? SSGPU_THR_S8 : nb == 7 ? SSGPU_THR_S7 : nb == 6 ? 3 : 0; }
+// time-varying Z: 2 NB more vector registers hold the row of Z, so a few more blocks move to shared memory (0, 1 or 3
+// extra blocks measure the same at 8 blocks: 8.2e9 series*timesteps/s; 5 extra 6.5e9)
+constexpr int thr_smem_blocks_ztv(int nb, bool ztv) { return thr_smem_blocks(nb) + ((ztv && nb >= 5) ? (nb >= 7 ? 3 : 2) : 0); }
 
-int thr_smem_blocks_host(int nb) { return thr_smem_blocks(nb); }
+int thr_smem_blocks_host(int nb, bool ztv) { return thr_smem_blocks_ztv(nb, ztv); }
 
 size_t thr_handoff_bytes(int nb, bool qoff, long long E) {
   const BlkHandoff hl(nb, qoff);
@@ -347,10 +350,7 @@ int thr_flops_per_step(int nb, bool qoff) {
 template <int NB, bool QOFF, bool ZTV = false>
 static int launch_thr_one(const ThrArgs& A, cudaStream_t st) {
   // time-varying Z: 2 NB more vector registers hold the row of Z, so two more blocks move to shared memory (NB >= 5)
-#ifndef SSGPU_THR_ZX
-#define SSGPU_THR_ZX 3
-#endif
-  constexpr int S = thr_smem_blocks(NB) + ((ZTV && NB >= 5) ? (NB >= 7 ? SSGPU_THR_ZX : 2) : 0);
+  constexpr int S = thr_smem_blocks_ztv(NB, ZTV);
   constexpr BlkHandoff HL(NB, QOFF);
   const size_t smem = (size_t)((2 + HL.qw) * NB + 4 * S) * kThrThreads * sizeof(double);
   // a function attribute belongs to the device it was set on (one slot per device: api.cu)
