@@ -447,17 +447,17 @@ int ssgpu_LogLikC(const double* y, const int* y_isna, int N, int p, int m, int r
   SS_TRY(stage_single(S, y, y_isna, N, p, m, r, a, P_inf, P_star, Z, nZ, T, nT, R, nR, Q, nQ, st, lease.a));
   DevBuf out;
   if (lease.a)
-    out.borrow(lease.a->res_dev());
+    out.borrow(lease.a->res_host);  // pinned host memory is device-accessible (unified addressing): the kernel writes the
+                                    // scalar result straight into it and no copy back is enqueued
   else
     SS_TRY(out.alloc(sizeof(double), st));
   // one series is a batch of one: the warp-level kernels serve it when the model qualifies (a few hundred cycles
   // per observation instead of the CTA kernel's barriers), the generic kernel otherwise
   const HostShared hs{nT == 1 ? T : nullptr, nR == 1 ? R : nullptr, nZ == 1 ? Z : nullptr, nQ == 1 ? Q : nullptr};
   SS_TRY(dispatch_batch(S.md, S.dev.as<double>() + S.oy, 1, 1, SSGPU_KERNEL_AUTO, out.as<double>(), st, &hs));
-  double* back = lease.a ? lease.a->res_host : loglik;
-  SS_CUDA(cudaMemcpyAsync(back, out.get(), sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (!lease.a) SS_CUDA(cudaMemcpyAsync(loglik, out.get(), sizeof(double), cudaMemcpyDeviceToHost, st));
   SS_CUDA(cudaStreamSynchronize(st));
-  if (lease.a) *loglik = *back;
+  if (lease.a) *loglik = *lease.a->res_host;
   return SSGPU_OK;
 }
 
