@@ -318,7 +318,7 @@ static bool auto_blk_enabled() {
 }
 
 static int dispatch_batch(const DModel& md, const double* y_dev, long long B, int V, int kernel, double* out_dev,
-                          cudaStream_t st, const HostShared* hs = nullptr) {
+                          cudaStream_t st, const HostShared* hs = nullptr, long long call_evals = 0) {
   SS_ARG(B >= 1 && V >= 1, "B and V must be positive");
   std::string why;
   const double* T_host = hs ? hs->T : nullptr;
@@ -328,7 +328,7 @@ static int dispatch_batch(const DModel& md, const double* y_dev, long long B, in
   if (kernel == SSGPU_KERNEL_BLK_LANES) return launch_loglik_blk(md, y_dev, B, V, out_dev, st, hs, nullptr, true);
   if (kernel == SSGPU_KERNEL_AUTO && auto_blk_enabled() && blk_eligible(md, &why)) {
     bool ran = true;
-    SS_TRY(launch_loglik_blk(md, y_dev, B, V, out_dev, st, hs, &ran));
+    SS_TRY(launch_loglik_blk(md, y_dev, B, V, out_dev, st, hs, &ran, false, call_evals));
     if (ran) return SSGPU_OK;
   }
   const bool mma_ok = mma_eligible(md, &why);
@@ -903,6 +903,7 @@ namespace ssgpu {
 static int grad_batch_slice(const double* y, long long ldy, long long B, const ssgpu_model* model, const double* theta,
                             int k, const int* q_index, const int* p_star_index, double h, int kernel, double* loglik,
                             double* grad) {
+  const long long call_evals = ldy * (1 + 2 * k);  // of the whole call: every range takes the kernel the whole would
   cudaStream_t st = lib_stream();
   const size_t Np = (size_t)model->N * model->p;
   const size_t n_y = Np * (size_t)B;
@@ -927,7 +928,7 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
     SS_CUDA(cudaMemcpyAsync(thd.get(), theta, (size_t)B * k * sizeof(double), cudaMemcpyHostToDevice, st));
     SS_TRY(theta_setup(model, false, B, V, k, thd.as<double>(), q_index, p_star_index, h, 1, W, st));
     SS_TRY(W.out.alloc((size_t)B * V * sizeof(double), st));
-    SS_TRY(dispatch_batch(W.md, yd.as<double>(), B, V, kernel, W.out.as<double>(), st));
+    SS_TRY(dispatch_batch(W.md, yd.as<double>(), B, V, kernel, W.out.as<double>(), st, nullptr, call_evals));
     SS_TRY(launch_fd_gradient(W.out.as<double>(), B, k, h, ll, gr, st));
   } else {
     // A large batch is cut into chunks of series and the upload of chunk c + 1 overlaps the kernels of chunk c (chunk c of
@@ -991,7 +992,7 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
       mdc.P_star.p += b0 * mdc.P_star.sb;
       SS_CUDA(cudaStreamWaitEvent(st, ev[c], 0));
       double* outc = W.out.as<double>() + (size_t)V * b0;
-      SS_TRY(dispatch_batch(mdc, yd.as<double>() + Np * b0, bn, V, kernel, outc, st, &hs));
+      SS_TRY(dispatch_batch(mdc, yd.as<double>() + Np * b0, bn, V, kernel, outc, st, &hs, call_evals));
       SS_TRY(launch_fd_gradient(outc, bn, k, h, ll + b0, gr + b0 * k, st));
     }
   }

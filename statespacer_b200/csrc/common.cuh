@@ -298,7 +298,8 @@ int blk_lanes(int nb);
 int blk_flops_per_step(int nb, int p);
 // applicable != null: a model whose T / R Q R' does not decompose is not an error; *applicable = false, nothing runs
 int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
-                      const HostShared* hs = nullptr, bool* applicable = nullptr, bool lanes_only = false);
+                      const HostShared* hs = nullptr, bool* applicable = nullptr, bool lanes_only = false,
+                      long long call_evals = 0);  // evaluations of the whole API call (a launch may cover a part): kernel choice
 
 // Thread-per-evaluation kernel for the regular phase of the same model class (loglik_thr.cu); the lane kernel
 // above runs the diffuse phase first and hands the state over (blk_handoff.cuh)

@@ -892,7 +892,7 @@ int blk_useful_flops_per_step(int nb, int p) {
 }
 
 int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
-                      const HostShared* hs, bool* applicable, bool lanes_only) {
+                      const HostShared* hs, bool* applicable, bool lanes_only, long long call_evals) {
   std::string why;
   if (applicable) *applicable = true;
   SS_ARG(blk_eligible(md, &why), "block kernel not eligible: " + why);
@@ -994,7 +994,13 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     const char* e = getenv("SSGPU_BLK_THREAD");
     return !(e && e[0] == '0');
   }();
-  if (thr_on && !lanes_only && thr_supported(pl.nb, p, nZ > 1)) {
+  // A few evaluations (a single series in statespacer()'s optim loop: 1 + 2k of them) finish sooner on the lanes: one launch
+  // instead of two, and a step is 243 instructions of a warp instead of 1,134 of a thread.  The automatic dispatch therefore
+  // takes the thread kernel from kThrMinEvals evaluations on (about one wave of the lane kernel); SSGPU_KERNEL_BLK always.
+  constexpr long long kThrMinEvals = 8192;
+  const bool explicit_blk = applicable == nullptr;
+  // (decided on the size of the whole call, so that ranges of one call -- upload chunks, device slots -- agree bit for bit)
+  if (thr_on && !lanes_only && thr_supported(pl.nb, p, nZ > 1) && (explicit_blk || std::max(A.E, call_evals) >= kThrMinEvals)) {
     // Two launches per range of series: the lane kernel runs the exact diffuse phase and leaves the state behind, the
     // thread kernel (loglik_thr.cu) runs the regular phase.  The state record is ~1.1 KB per evaluation at 7 blocks:
     // ranges of series are sized for SSGPU_THR_SCRATCH_MB (default 2048) of scratch.
