@@ -63,8 +63,11 @@ __device__ __forceinline__ double thr_rsqrt(double x) {
   r = fma(r, e, r);
   e = fma(-h * r, r, 0.5);
   r = fma(r, e, r);
+#ifndef SSGPU_THR_NEWTON2
   e = fma(-h * r, r, 0.5);
-  return fma(r, e, r);
+  r = fma(r, e, r);
+#endif
+  return r;
 }
 
 // An offset of zero the optimiser cannot see through.  T and z are read from the kernel parameters through it inside
