@@ -140,13 +140,23 @@ def cpu_sample(n_series, seed=0):
     return sm, yy, Pfull, Qfull
 
 
+try:
+    ORIG_AFFINITY = os.sched_getaffinity(0)     # before any NUMA binding of the GPU legs
+except AttributeError:
+    ORIG_AFFINITY = None
+
+
 def host_cores():
     """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1; the CPU arm is told the
-    real count explicitly (omp_set_num_threads inside the checkers)."""
-    try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
+    real count explicitly (omp_set_num_threads inside the checkers).  The GPU legs bind the process to the NUMA node of
+    its GPU (bind_to_gpu_numa_node); the CPU legs call this first and get every core back."""
+    if ORIG_AFFINITY is not None:
+        try:
+            os.sched_setaffinity(0, ORIG_AFFINITY)
+        except OSError:
+            pass
+        return len(ORIG_AFFINITY)
+    return os.cpu_count() or 1
 
 
 def time_cpu(mod, sm, yy, Pfull, Qfull, threads=0):
@@ -321,10 +331,36 @@ def gpu_setup():
         raise SystemExit("bench.py: no CUDA device (statespacer_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bind_to_gpu_numa_node(torch, local)
     api.set_device(local)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
     return world, rank, local, dev
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """One process per GPU: run on (and therefore first-touch pinned staging memory from) the CPUs of the NUMA node the
+    GPU's PCIe root hangs off -- with 8 ranks each uploading 1 GB per step, copies that cross the socket interconnect are
+    what the end-to-end figure loses.  Best effort: silently skipped where sysfs does not tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:          # nvml pads the domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        cpus = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+        allowed = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            allowed.update(range(int(lo), int(hi or lo) + 1))
+        allowed &= set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:
+        pass
 
 
 def committed_traffic(kernel_prefix, grid):

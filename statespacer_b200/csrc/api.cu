@@ -2,9 +2,14 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <cctype>
 #include <functional>
 #include <mutex>
 #include <thread>
+#ifdef __linux__
+#include <pthread.h>
+#include <sched.h>
+#endif
 
 #include "common.cuh"
 
@@ -43,6 +48,46 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 int dev_slot() { return t_slot; }
+
+// Worker threads of a sharded call run on (and first-touch their pinned staging ring from) the CPUs of the NUMA node
+// their device's PCIe root hangs off: staging copies that cross the socket interconnect are what an 8-GPU call from
+// one process loses first.  Best effort (Linux sysfs); a thread that cannot be placed stays where it is.
+static void bind_thread_to_device_numa(int device) {
+#ifdef __linux__
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+  char path[96];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return;
+  char line[1024] = {0};
+  const bool ok = fgets(line, sizeof line, f) != nullptr;
+  fclose(f);
+  if (!ok) return;
+  cpu_set_t now, want;
+  CPU_ZERO(&want);
+  if (pthread_getaffinity_np(pthread_self(), sizeof now, &now) != 0) return;
+  int n_set = 0;
+  for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int lo = 0, hi = 0;
+    const int got = sscanf(tok, "%d-%d", &lo, &hi);
+    if (got == 1) hi = lo;
+    if (got < 1) continue;
+    for (int c = lo; c <= hi && c < CPU_SETSIZE; c++)
+      if (CPU_ISSET(c, &now)) {
+        CPU_SET(c, &want);
+        n_set++;
+      }
+  }
+  if (n_set > 0) pthread_setaffinity_np(pthread_self(), sizeof want, &want);
+#else
+  (void)device;
+#endif
+}
 
 int ensure_device() {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -93,6 +138,7 @@ int for_each_device(long long n, long long align, const std::function<int(int, l
     th.emplace_back([&, s, lo, hi]() {
       t_slot = s;
       rc[s] = ensure_device();
+      if (rc[s] == SSGPU_OK) bind_thread_to_device_numa(g_ctx[s].device);
       if (rc[s] == SSGPU_OK) rc[s] = fn(s, lo, hi);
       if (rc[s] != SSGPU_OK) msg[s] = g_err;
       kname[s] = g_last_kernel;
