@@ -154,9 +154,10 @@ typedef struct ssgpu_model {
 } ssgpu_model;
 
 /* kernel selection for the batched path */
-#define SSGPU_KERNEL_AUTO 0     /* block-row kernel when the model qualifies, else the tensor kernel (column kernel first
-                                   when p >= 4 and it qualifies), else column kernel, else the warp/shared-memory
-                                   kernel, else generic */
+#define SSGPU_KERNEL_AUTO 0     /* block-row kernel when the model qualifies (the core kernel, below, first when p >= 2
+                                   and the batch is large), else the core kernel, else the tensor kernel (column
+                                   kernel first when p >= 4 and it qualifies), else column kernel, else the
+                                   warp/shared-memory kernel, else generic */
 #define SSGPU_KERNEL_GENERIC 1  /* one CTA per evaluation, any shape */
 #define SSGPU_KERNEL_COLS 2     /* column-per-lane DFMA kernel (m <= 15); SSGPU_E_ARG if not eligible */
 #define SSGPU_KERNEL_MMA 3      /* warp-per-evaluation FP64 tensor (DMMA) kernel (m <= 23); SSGPU_E_ARG if not eligible.
@@ -176,6 +177,15 @@ typedef struct ssgpu_model {
                                    evaluation, runs the regular phase */
 #define SSGPU_KERNEL_BLK_LANES 7 /* the same model class on the lane kernel alone (second implementation the tests
                                    cross-check; A/B runs) */
+
+#define SSGPU_KERNEL_CORE 8     /* one thread per series on the component states alone: the p residual states every
+                                   reference model starts with (Z = [I_p | Z_c], T = blkdiag(0_p, T_c), R Q R' =
+                                   blkdiag(H, W_c), H diagonal; R/GetSysMat.R:1388-1426) are eliminated exactly, the
+                                   dense covariance of the m - p <= 8 remaining states lives in registers (p <= 16,
+                                   everything shared by the batch and time-invariant; exact diffuse phase included).
+                                   BASELINE.json config 3 (dynamic Nelson-Siegel, p = 8, m = 14) is a 6 x 6 problem
+                                   here.  SSGPU_E_ARG if not eligible.  AUTO takes it for batches of 2048 evaluations
+                                   or more: before the block-row kernel when p >= 2, behind it when p = 1 */
 
 /* host pointers everywhere (y, the matrices' data, out); copies in, runs, copies out, synchronises */
 int ssgpu_loglik_batch(const double* y, long long B, int V, const ssgpu_model* model, int kernel,
@@ -348,6 +358,9 @@ int ssgpu_plan_state_order(const double* T, int m, int* perm, unsigned* tile_mas
  * and time step (fma = 2, all lanes). */
 int ssgpu_plan_blocks(const double* T, const double* R, const double* Q, int m, int r, int p, int* perm,
                       int* n_blocks, int* lanes, int* flop_per_step);
+/* FP64 operations (fma = 2) the core kernel (SSGPU_KERNEL_CORE) issues per series and time point of the regular
+ * phase for a model with m states of which p are residuals; 0 when m - p or p is outside the kernel's range. */
+int ssgpu_core_flops_per_step(int m, int p);
 
 /* ---- 7. Measurement helpers ---------------------------------------------------------------
  * FP64 FMA-pipe peak of the current device, measured with a register-resident DFMA chain kernel

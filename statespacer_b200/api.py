@@ -16,11 +16,11 @@ import ctypes as C
 import numpy as np
 
 from . import native
-from .native import (KERNEL_AUTO, KERNEL_BLK, KERNEL_BLK_LANES, KERNEL_COLS, KERNEL_GENERIC, KERNEL_MMA, KERNEL_MMA_DENSE,  # noqa: F401
+from .native import (KERNEL_AUTO, KERNEL_BLK, KERNEL_BLK_LANES, KERNEL_COLS, KERNEL_CORE, KERNEL_GENERIC, KERNEL_MMA, KERNEL_MMA_DENSE,  # noqa: F401
                      KERNEL_WSM)
 
 _KERNELS = {"auto": KERNEL_AUTO, "generic": KERNEL_GENERIC, "cols": KERNEL_COLS, "mma": KERNEL_MMA,
-            "mma_dense": KERNEL_MMA_DENSE, "wsm": KERNEL_WSM, "blk": KERNEL_BLK, "blk_lanes": KERNEL_BLK_LANES}
+            "mma_dense": KERNEL_MMA_DENSE, "wsm": KERNEL_WSM, "blk": KERNEL_BLK, "blk_lanes": KERNEL_BLK_LANES, "core": KERNEL_CORE}
 
 
 def _f(x):
@@ -211,6 +211,11 @@ def ExtractComponentC(a, Z):
     out = np.zeros((N, p, nsim), order="F")
     native.check(native.lib().ssgpu_ExtractComponentC(_ptr(a), m, nsim, N, _ptr(Z), p, Z.shape[2], _ptr(out)))
     return out
+
+
+def core_flops_per_step(m, p):
+    """FP64 operations per series and time point of the core kernel's regular phase (0 = outside its range)."""
+    return int(native.lib().ssgpu_core_flops_per_step(int(m), int(p)))
 
 
 def plan_blocks(T, R, Q=None, p=1):

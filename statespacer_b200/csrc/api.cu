@@ -363,6 +363,15 @@ static bool auto_blk_enabled() {
   return on;
 }
 
+static bool auto_core_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SSGPU_AUTO_CORE");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+constexpr long long kCoreMinEvals = 2048;
+
 static int dispatch_batch(const DModel& md, const double* y_dev, long long B, int V, int kernel, double* out_dev,
                           cudaStream_t st, const HostShared* hs = nullptr, long long call_evals = 0) {
   SS_ARG(B >= 1 && V >= 1, "B and V must be positive");
@@ -372,9 +381,25 @@ static int dispatch_batch(const DModel& md, const double* y_dev, long long B, in
   // 4 m^3 multiply-adds per time update
   if (kernel == SSGPU_KERNEL_BLK) return launch_loglik_blk(md, y_dev, B, V, out_dev, st, hs);
   if (kernel == SSGPU_KERNEL_BLK_LANES) return launch_loglik_blk(md, y_dev, B, V, out_dev, st, hs, nullptr, true);
+  if (kernel == SSGPU_KERNEL_CORE) return launch_loglik_core(md, y_dev, B, V, out_dev, st, hs);
+  // thread-per-series kernel on the component states (residual states eliminated): worth it once the batch fills the
+  // machine with threads; many observations per time point go there before the block-row kernel (p = 1 has the
+  // thread-per-evaluation kernel behind the block planner)
+  const bool core_auto = kernel == SSGPU_KERNEL_AUTO && auto_core_enabled() && std::max(B * V, call_evals) >= kCoreMinEvals &&
+                         core_eligible(md, &why);
+  if (core_auto && md.p >= 2) {
+    bool ran = true;
+    SS_TRY(launch_loglik_core(md, y_dev, B, V, out_dev, st, hs, &ran));
+    if (ran) return SSGPU_OK;
+  }
   if (kernel == SSGPU_KERNEL_AUTO && auto_blk_enabled() && blk_eligible(md, &why)) {
     bool ran = true;
     SS_TRY(launch_loglik_blk(md, y_dev, B, V, out_dev, st, hs, &ran, false, call_evals));
+    if (ran) return SSGPU_OK;
+  }
+  if (core_auto && md.p < 2) {
+    bool ran = true;
+    SS_TRY(launch_loglik_core(md, y_dev, B, V, out_dev, st, hs, &ran));
     if (ran) return SSGPU_OK;
   }
   const bool mma_ok = mma_eligible(md, &why);

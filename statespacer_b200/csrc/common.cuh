@@ -310,6 +310,13 @@ int thr_smem_blocks_host(int nb, bool ztv);
 int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* zt, const double* y, long long B,
                       long long E, long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st);
 
+// Thread-per-series kernel on the component states alone, the p residual states of the reference's layout eliminated
+// (loglik_core.cu): m - p <= 8, p <= 16, everything shared and time-invariant, diagonal H
+bool core_eligible(const DModel& md, std::string* why);
+int core_flops_per_step(int mc, int p);
+int launch_loglik_core(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
+                       const HostShared* hs = nullptr, bool* applicable = nullptr);
+
 // Column-per-thread register kernel (loglik_cols.cu)
 bool cols_eligible(const DModel& md, std::string* why);
 int launch_loglik_cols(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st);

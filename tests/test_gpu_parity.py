@@ -732,6 +732,96 @@ def test_batch_multivariate_dns():
         assert abs(cols[b] - want) <= RTOL * max(1, abs(want)), (b, cols[b], want)
 
 
+def _residual_layout_model(rng, p, mc, d, r_c=None, h_zero=()):
+    """A model in the reference's own state layout (R/GetSysMat.R:1388-1426): [p residuals ; mc component states],
+    dense T_c, Z_c, R_c, Q_c, d diffuse component states, diagonal H (entries in h_zero set to 0)."""
+    r_c = r_c or mc
+    T = rng.normal(size=(mc, mc)) * (0.5 / math.sqrt(mc))
+    T[np.arange(mc), np.arange(mc)] += 0.6
+    T[:d, :] = 0.0
+    T[:, :d] = 0.0
+    T[np.arange(d), np.arange(d)] = 1.0                                   # diffuse states: random walks
+    if d >= 2:
+        T[0, 1] = 1.0                                                     # ... the first one with a slope
+    Z = rng.normal(size=(p, mc)) * (rng.uniform(size=(p, mc)) < 0.8)
+    Z[:, :1] = 1.0
+    A = rng.normal(size=(r_c, r_c))
+    Q = A @ A.T / r_c + 0.05 * np.eye(r_c)
+    R = np.eye(mc)[:, :r_c] if r_c <= mc else rng.normal(size=(mc, r_c)) * 0.5
+    C = rng.normal(size=(mc, mc))
+    P_star = C @ C.T / mc
+    P_star[:d, :] = 0.0
+    P_star[:, :d] = 0.0
+    P_inf = np.zeros((mc, mc))
+    P_inf[np.arange(d), np.arange(d)] = 1.0
+    H = np.diag(rng.uniform(0.05, 0.5, p))
+    for j in h_zero:
+        H[j, j] = 0.0
+    comp = dict(Z=Z, T=T, R=R, Q=Q, a=rng.normal(size=mc), P_inf=P_inf, P_star=P_star)
+    return sysmat._combine(p, H, [comp])
+
+
+@pytest.mark.parametrize("p,mc,d", [(1, 1, 0), (1, 3, 1), (2, 2, 2), (3, 4, 0), (3, 5, 2), (8, 6, 0), (4, 6, 3),
+                                    (2, 7, 1), (5, 8, 2), (16, 3, 1)])
+def test_batch_core_kernel(p, mc, d):
+    """Thread-per-series kernel on the component states (residual states eliminated, loglik_core.cu) against the oracle
+    run on the FULL state: dense T_c / Q_c, exact diffuse phase with d diffuse states, missing observations, a series
+    that is missing throughout a stretch spanning the diffuse phase, one observation without noise (H_jj = 0)."""
+    rng = np.random.default_rng(1000 + 37 * p + 5 * mc + d)
+    N, B = 45, 40
+    sm = _residual_layout_model(rng, p, mc, d, h_zero=(p - 1,) if p >= 3 else ())
+    y = np.stack([simulate_y(rng, sm, N, missing=0.08) for _ in range(B)], axis=2)
+    y[:6, :, 1] = np.nan                                                   # diffuse phase starts late
+    y[:, 0, 2] = np.nan                                                    # first observed variable never seen
+    y[3:, :, 3] = np.nan                                                   # too few observations to leave the diffuse phase
+    got = api.loglik_batch(y, sm, kernel="core")
+    assert api.last_kernel().startswith("loglik_core")
+    other = api.loglik_batch(y, sm, kernel="generic")
+    for b in range(B):
+        yb = y[:, :, b]
+        want, tol = loglik_want(yb, np.isnan(yb), *sm.args())
+        if math.isnan(want):
+            assert math.isnan(got[b]), (b, got[b])
+            continue
+        assert abs(got[b] - want) <= tol, (p, mc, d, b, got[b], want)
+        assert abs(other[b] - want) <= tol
+
+
+def test_batch_core_kernel_dns_and_dispatch():
+    """BASELINE.json config 3 (dynamic Nelson-Siegel on the FedYieldCurve window, p = 8, m = 14, no diffuse states): a
+    6 x 6 problem per thread.  KAT-3 through the kernel, every series against the oracle, automatic choice from 2048
+    series on, refusal of what does not have the residual structure."""
+    fed = load_fed()
+    sm, _ = sysmat.dns_yield_curve(DNS_PARAM)
+    rng = np.random.default_rng(5)
+    B = 2048
+    y = np.stack([fed + (0.01 * rng.normal(size=fed.shape) if b else 0.0) for b in range(B)], axis=2)
+    y[rng.uniform(size=y.shape) < 0.03] = np.nan
+    y[:, :, 0] = fed
+    got = api.loglik_batch(y, sm)
+    assert api.last_kernel().startswith("loglik_core")
+    assert abs(got[0] - 7.005830) < 6e-7 * 7                               # docs/articles/selfspec.html:306-307
+    assert np.array_equal(got, api.loglik_batch(y, sm, kernel="core"))
+    cols = api.loglik_batch(y[:, :, :64], sm)
+    assert api.last_kernel().startswith("loglik_cols")                     # small batches stay on the lane kernels
+    assert np.allclose(cols, got[:64], rtol=1e-11, atol=0)
+    for b in list(range(24)) + [B - 1]:
+        yb = y[:, :, b]
+        want = cport.LogLikC(yb, np.isnan(yb), *sm.args())
+        assert abs(got[b] - want) <= RTOL * max(1, abs(want)), (b, got[b], want)
+    # correlated observation noise (H not diagonal) couples the residual states: refused, AUTO moves on
+    bad = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=sm.Q.copy(), a=sm.a, P_inf=sm.P_inf, P_star=sm.P_star.copy())
+    bad.Q[0, 1, 0] = bad.Q[1, 0, 0] = 1e-4
+    bad.P_star[0, 1] = bad.P_star[1, 0] = 1e-4
+    with pytest.raises(native.SsgpuError):
+        api.loglik_batch(y[:, :, :8], bad, kernel="core")
+    auto = api.loglik_batch(y, bad)
+    assert not api.last_kernel().startswith("loglik_core")
+    yb = y[:, :, 5]
+    want, tol = loglik_want(yb, np.isnan(yb), *bad.args())
+    assert abs(auto[5] - want) <= tol
+
+
 def test_batch_generic_time_varying_and_per_series():
     rng = np.random.default_rng(3)
     N, B, m, p = 20, 6, 7, 2
