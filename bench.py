@@ -1034,7 +1034,7 @@ def model_cases():
     sm1 = sysmat.nile_local_level(15100.252, 1468.724)                     # KAT-1a parameters
     return [("config1", "Nile local level, p=1, N=100, m=2 (batched by replication, SURVEY.md 8d)", sm1, nile, 1_000_000),
             ("config2", "bivariate BSM + 3 shared regressors (stand-in), p=2, N=192, m=34, time-varying Z, 5% missing", c2.sm, c2.y, 16384),
-            ("config3", "dynamic Nelson-Siegel, FedYieldCurve 1985-2000, p=8, N=192, m=14", sm3, load_fed(), 32768),
+            ("config3", "dynamic Nelson-Siegel, FedYieldCurve 1985-2000, p=8, N=192, m=14", sm3, load_fed(), 262144),
             ("config4_loglik", "SARIMA(1,1,1)(0,1,1)12 on log AirPassengers, p=1, N=144, m=28 (companion-form T)", sm4, air, 16384)]
 
 

@@ -30,6 +30,10 @@ namespace ssgpu {
 constexpr int kCoreMaxMC = 8;   // core states (m - p)
 constexpr int kCoreMaxP = 16;   // observations per time point
 constexpr int kCoreThreads = 128;
+#ifndef SSGPU_CORE_AHEAD
+#define SSGPU_CORE_AHEAD 1
+#endif
+constexpr int kCoreAhead = SSGPU_CORE_AHEAD;
 constexpr int kCoreMaxNS = kCoreMaxMC * (kCoreMaxMC + 1) / 2;
 
 struct CoreArgs {
@@ -98,8 +102,12 @@ __device__ __forceinline__ void core_time_update(double (&X)[MC * (MC + 1) / 2],
   for (int i = 0; i < NS; i++) X[i] = Y[i];
 }
 
+// CTAs per SM the register budget is held to (measured on config 3, 6 core states: 124 registers at 4 CTAs 1.22e10
+// series*timesteps/s, left to ptxas 156 - 192 registers and 0.84 - 1.11e10)
+constexpr int core_min_blocks(int mc, bool diff) { return diff ? (mc <= 4 ? 4 : 2) : (mc <= 6 ? 4 : 2); }
+
 template <int MC, bool DIFF>
-__global__ void __launch_bounds__(kCoreThreads) loglik_core_kernel(const CoreArgs A) {
+__global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) loglik_core_kernel(const CoreArgs A) {
   constexpr int NS = MC * (MC + 1) / 2;
   const long long w = (long long)blockIdx.x * kCoreThreads + threadIdx.x;
   if (w >= A.E) return;
@@ -126,23 +134,42 @@ __global__ void __launch_bounds__(kCoreThreads) loglik_core_kernel(const CoreArg
     prod = __hiloint2double(hi - (ex << 20), __double2loint(prod));
   };
 
+  // observations are fetched kCoreAhead univariate steps ahead of their use (a step is ~100 FP64 instructions: one
+  // step of lead does not cover the latency of a load from HBM at 4 warps per scheduler)
   const long long Np = (long long)N * p;
   long long q = 0;
   const double* yp = A.y + b;
-  double ynext = *yp;  // observations are fetched one univariate step ahead of their use
+  double yq[kCoreAhead];
+#pragma unroll
+  for (int i = 0; i < kCoreAhead; i++) yq[i] = i < Np ? yp[(long long)i * A.B] : 0.0;
+  yp += (long long)kCoreAhead * A.B;
   auto take_y = [&]() {
-    const double yv = ynext;
+    const double yv = yq[0];
+#pragma unroll
+    for (int i = 0; i + 1 < kCoreAhead; i++) yq[i] = yq[i + 1];
+    if (q + kCoreAhead < Np) yq[kCoreAhead - 1] = *yp;
+    yp += A.B;
     q++;
-    if (q < Np) {
-      yp += A.B;
-      ynext = *yp;
-    }
     return yv;
   };
 
   // regular update with observation j (src/LogLikC.cpp:162-195); missing or F < 1e-7: a no-op through 1/sqrt(F) := 0
+  // the row of Z_c and H_jj of the coming observation are read one observation ahead (an indexed read of the
+  // constant bank right in front of the dot products that need it costs its latency 8 times per time point)
+  double zc[MC], hc;
+  auto load_z = [&](int j) {
+    const double* const zz = &A.Z[0][0] + j * kCoreMaxMC + core_opaque0();
+#pragma unroll
+    for (int k = 0; k < MC; k++) zc[k] = zz[k];
+    hc = (&A.H[0] + core_opaque0())[j];
+  };
+  load_z(0);
   auto regular_obs = [&](int j, double yv) {
-    const double* const z = &A.Z[0][0] + j * kCoreMaxMC + core_opaque0();
+    double z[MC];
+#pragma unroll
+    for (int k = 0; k < MC; k++) z[k] = zc[k];
+    const double hj = hc;
+    load_z(j + 1 < p ? j + 1 : 0);
     double M[MC];
 #pragma unroll
     for (int k = 0; k < MC; k++) {
@@ -151,7 +178,7 @@ __global__ void __launch_bounds__(kCoreThreads) loglik_core_kernel(const CoreArg
       for (int l = 1; l < MC; l++) acc = fma(C[core_sym(MC, k, l)], z[l], acc);
       M[k] = acc;
     }
-    double F = A.H[j], za = 0.0;
+    double F = hj, za = 0.0;
 #pragma unroll
     for (int k = 0; k < MC; k++) {
       F = fma(z[k], M[k], F);
@@ -212,6 +239,7 @@ __global__ void __launch_bounds__(kCoreThreads) loglik_core_kernel(const CoreArg
       for (int j = 0; j < p; j++) {
         const double yv = take_y();
         if (!init) {
+          load_z(j);  // the diffuse branch below reads its row directly and does not keep the look-ahead current
           regular_obs(j, yv);
           continue;
         }
