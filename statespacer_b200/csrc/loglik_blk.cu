@@ -931,6 +931,63 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     return SSGPU_OK;
   }
   SS_ARG(planned, "block kernel not eligible: " + why);
+  // The residual state of the reference's layout (z = 1, nothing in its row and column of T, uncoupled by R Q R'; p = 1,
+  // time-invariant Z): moved to position 1 of the last block, where the thread kernel drops it (loglik_thr.cu, EPS).  The
+  // kernel assumes P_star[eps, .] = 0 off the diagonal and a[eps] = 0 for a model that starts without a diffuse phase:
+  // P_star stored as a diagonal or checked here, a checked here.
+  static const bool eps_on = [] {
+    const char* e = getenv("SSGPU_THR_EPS");
+    return !(e && e[0] == '0');
+  }();
+  pl.eps = 0;
+  if (eps_on && p == 1 && nZ == 1 && pl.nb >= 2 && pl.nb <= kBlkMaxNB / 2 && md.a.shared() && (md.P_star.diag || md.P_star.shared())) {
+    int e = -1;
+    for (int i = 0; i < m && e < 0; i++) {
+      if (Zh[i] != 1.0) continue;
+      bool lone = true;
+      for (int k = 0; k < m && lone; k++)
+        lone = mat_get(Th.data(), md.T.diag, m, i, k) == 0.0 && mat_get(Th.data(), md.T.diag, m, k, i) == 0.0;
+      if (lone) e = i;
+    }
+    int blk = -1, pos = 0;
+    for (int i = 0; i < 2 * pl.nb && e >= 0; i++)
+      if (pl.perm[i] == e) blk = i / 2, pos = i % 2;
+    // uncoupled: its block is one of the paired-up singles (T and R Q R' off the diagonal of the block are zero)
+    bool ok = blk >= 0 && pl.Tb[blk][1] == 0.0 && pl.Tb[blk][2] == 0.0;
+    if (ok) {
+      const int other = pl.perm[2 * blk + 1 - pos];
+      if (other >= 0)
+        for (int k = 0; k < r && ok; k++) {  // R Q R'[e][other] == 0: no disturbance shared through a non-zero of Q
+          if (mat_get(Rh.data(), md.R.diag, m, e, k) == 0.0) continue;
+          for (int l = 0; l < r && ok; l++) {
+            const bool q = qpat.empty() ? k == l : qpat[k + (size_t)l * r] != 0;
+            ok = !(q && mat_get(Rh.data(), md.R.diag, m, other, l) != 0.0);
+          }
+        }
+    }
+    if (ok) {
+      std::vector<double> ah((size_t)m), Ph;
+      SS_CUDA(cudaMemcpyAsync(ah.data(), md.a.p, ah.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (!md.P_star.diag) {
+        Ph.resize((size_t)m * m);
+        SS_CUDA(cudaMemcpyAsync(Ph.data(), md.P_star.p, Ph.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+      }
+      SS_CUDA(cudaStreamSynchronize(st));
+      ok = ah[e] == 0.0;
+      for (int k = 0; k < m && ok && !Ph.empty(); k++) ok = k == e || (Ph[e + (size_t)k * m] == 0.0 && Ph[k + (size_t)e * m] == 0.0);
+    }
+    if (ok) {
+      const int last = pl.nb - 1;
+      for (int c = 0; c < 2; c++) std::swap(pl.perm[2 * blk + c], pl.perm[2 * last + c]);
+      for (int c = 0; c < 4; c++) std::swap(pl.Tb[blk][c], pl.Tb[last][c]);
+      if (pos == 0) {
+        std::swap(pl.perm[2 * last], pl.perm[2 * last + 1]);
+        std::swap(pl.Tb[last][0], pl.Tb[last][3]);
+        std::swap(pl.Tb[last][1], pl.Tb[last][2]);
+      }
+      pl.eps = 1;
+    }
+  }
   BlkArgs A{};
   A.md = md;
   A.y = y;
@@ -1024,12 +1081,12 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
       Ac.hd = scratch.as<double>();
       Ac.hi = reinterpret_cast<int*>(Ac.hd + (size_t)hl.doubles() * Ec);
       SS_TRY(launch_lanes(Ac));
-      SS_TRY(launch_loglik_thr(pl, &A.z[0][0], A.zt, Ac.y, Bc, Ec, B, md.N, Ac.hd, Ac.hi, Ac.out, st));
+      SS_TRY(launch_loglik_thr(pl, &A.z[0][0], A.zt, Ac.y, Bc, Ec, B, md.N, Ac.hd, Ac.hi, Ac.out, st, pl.eps != 0));
       count_launch();
     }
-    snprintf(name, sizeof name, "loglik_thr_kernel<NB=%d,S=%d,flop_per_step=%d>%s after loglik_blk_kernel<L=%d,NB=%d> (diffuse phase)",
-             pl.nb, thr_smem_blocks_host(pl.nb, nZ > 1), thr_flops_per_step(pl.nb, pl.q_offdiag != 0), nZ > 1 ? " time-varying Z" : "", L,
-             pl.nb);
+    snprintf(name, sizeof name, "loglik_thr_kernel<NB=%d,S=%d,flop_per_step=%d>%s%s after loglik_blk_kernel<L=%d,NB=%d> (diffuse phase)",
+             pl.nb, thr_smem_blocks_host(pl.nb, nZ > 1, pl.eps != 0), thr_flops_per_step(pl.nb, pl.q_offdiag != 0, pl.eps != 0),
+             nZ > 1 ? " time-varying Z" : "", pl.eps ? " residual state dropped" : "", L, pl.nb);
     set_last_kernel(name);
     return SSGPU_OK;
   }

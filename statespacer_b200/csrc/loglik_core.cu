@@ -30,10 +30,17 @@ namespace ssgpu {
 constexpr int kCoreMaxMC = 8;   // core states (m - p)
 constexpr int kCoreMaxP = 16;   // observations per time point
 constexpr int kCoreThreads = 128;
-#ifndef SSGPU_CORE_AHEAD
-#define SSGPU_CORE_AHEAD 1
+// observations are fetched this many univariate steps ahead of their use (a ring in registers).  A thread of a small
+// model finishes a step in a few hundred cycles while a load from HBM takes longer than that: with one load in flight per
+// thread the local level runs at 1.7 TB/s of observations whatever the arithmetic costs.  Large cores hide the load
+// behind the ~100 FP64 instructions of an observation and have no registers to spare.
+#ifndef SSGPU_CORE_AHEAD_SMALL
+#define SSGPU_CORE_AHEAD_SMALL 8
 #endif
-constexpr int kCoreAhead = SSGPU_CORE_AHEAD;
+#ifndef SSGPU_CORE_AHEAD_MID
+#define SSGPU_CORE_AHEAD_MID 4
+#endif
+__host__ __device__ constexpr int core_ahead(int mc) { return mc <= 2 ? SSGPU_CORE_AHEAD_SMALL : mc <= 4 ? SSGPU_CORE_AHEAD_MID : 1; }
 constexpr int kCoreMaxNS = kCoreMaxMC * (kCoreMaxMC + 1) / 2;
 
 struct CoreArgs {
@@ -134,8 +141,7 @@ __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) logli
     prod = __hiloint2double(hi - (ex << 20), __double2loint(prod));
   };
 
-  // observations are fetched kCoreAhead univariate steps ahead of their use (a step is ~100 FP64 instructions: one
-  // step of lead does not cover the latency of a load from HBM at 4 warps per scheduler)
+  constexpr int kCoreAhead = core_ahead(MC);
   const long long Np = (long long)N * p;
   long long q = 0;
   const double* yp = A.y + b;

@@ -85,8 +85,17 @@ __device__ __forceinline__ int thr_opaque0() {
 // point (the threads of a warp differ by a few steps at most: a handful of L1-resident lines) into registers that replace
 // the uniform-register copies of z; F = z'M and z'a of a step are formed right behind the sweep that accumulated M, while
 // that row is still at hand, and carried into the next iteration.
-template <int NB, int S, bool QOFF, bool ZTV = false>
+//
+// EPS: position 1 of the LAST block is the residual state of the reference's layout (z = 1, T row and column zero, no
+// coupling through R Q R': R/GetSysMat.R:1388-1426).  At the start of every time point its row of P is H e' and its
+// entry of a is 0, and its row of T P T' vanishes: the kernel keeps nothing for it -- the last block is the scalar of
+// its partner, the blocks (I, last) are 2 x 1, F gets H added.  At 7 blocks (config 5) that is 738 instead of 861 FP64
+// instructions per series and time step.  Only P[eps, eps] of the FIRST time point is taken from the hand-over (a model
+// without diffuse phase starts from the caller's P_star); the launcher checks what the kernel assumes of P_star and a.
+template <int NB, int S, bool QOFF, bool ZTV = false, bool EPS = false>
 __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThreads) loglik_thr_kernel(const ThrArgs A) {
+  static_assert(!(EPS && ZTV), "residual shortcut: time-invariant Z");
+  constexpr int L = NB - 1;
   constexpr BlkHandoff HL(NB, QOFF);
   constexpr int NOFF = HL.noff();
   constexpr int RO = NOFF - S;  // blocks above the diagonal in registers
@@ -150,6 +159,10 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
 #pragma unroll
     for (int I = 0; I < NB; I++) {
       const double zi0 = ZTV ? zr[ZTV ? I : 0][0] : A.cst[I][4], zi1 = ZTV ? zr[ZTV ? I : 0][1] : A.cst[I][5];
+      if (EPS && I == L) {
+        M[I][0] = fma(D[I][0], zi0, M[I][0]);
+        continue;
+      }
       M[I][0] = fma(D[I][1], zi1, fma(D[I][0], zi0, M[I][0]));
       M[I][1] = fma(D[I][2], zi1, fma(D[I][1], zi0, M[I][1]));
 #pragma unroll
@@ -161,6 +174,12 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
         } else {
           const int o = (oi - RO) * 4;
           p0 = SP(o), p1 = SP(o + 1), p2 = SP(o + 2), p3 = SP(o + 3);
+        }
+        if (EPS && J == L) {
+          M[I][0] = fma(p0, zj0, M[I][0]);
+          M[I][1] = fma(p2, zj0, M[I][1]);
+          M[J][0] = fma(p2, zi1, fma(p0, zi0, M[J][0]));
+          continue;
         }
         M[I][0] = fma(p1, zj1, fma(p0, zj0, M[I][0]));
         M[I][1] = fma(p3, zj1, fma(p2, zj0, M[I][1]));
@@ -190,6 +209,9 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
 
   const double* yp = A.y + b + (long long)t * A.ldy;
   double ynext = *yp;
+  // EPS: P[eps, eps] z_eps, the residual's share of F -- the hand-over's value at the first time point, H afterwards
+  double heps = EPS ? D[L][2] : 0.0;
+  const double hq = EPS ? SQ(QW * L + QW - 1) : 0.0;
   double Fc = 0.0, zac = 0.0;  // ZTV: F = z'M and z'a of the coming step
   if constexpr (ZTV) {
 #pragma unroll
@@ -203,10 +225,19 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
     yp += A.ldy;
     ynext = *yp;
     // ---- the vectors: tm = T M (in place), F = z'M, z'a, T a
-    double F = Fc, za = zac, ta[NB][2];
+    double F = EPS ? heps : Fc, za = zac, ta[NB][2];
+    heps = hq;
     const double* const cv0 = &A.cst[0][0] + thr_opaque0();
 #pragma unroll
     for (int I = 0; I < NB; I++) {
+      if (EPS && I == L) {
+        const double t00 = cv0[I * 6], z0 = cv0[I * 6 + 4], m0 = M[I][0], a0 = SA(2 * I);
+        F = fma(z0, m0, F);
+        za = fma(z0, a0, za);
+        M[I][0] = t00 * m0;
+        ta[I][0] = t00 * a0;
+        continue;
+      }
       const double t00 = cv0[I * 6], t01 = cv0[I * 6 + 1], t10 = cv0[I * 6 + 2], t11 = cv0[I * 6 + 3];
       const double m0 = M[I][0], m1 = M[I][1], a0 = SA(2 * I), a1 = SA(2 * I + 1);
       if constexpr (!ZTV) {
@@ -225,6 +256,12 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
     double s[NB][2];
 #pragma unroll
     for (int I = 0; I < NB; I++) {
+      if (EPS && I == L) {
+        s[I][0] = M[I][0] * r;
+        SA(2 * I) = fma(s[I][0], cv, ta[I][0]);
+        M[I][0] = 0.0;
+        continue;
+      }
       s[I][0] = M[I][0] * r;
       s[I][1] = M[I][1] * r;
       const double n0 = fma(s[I][0], cv, ta[I][0]), n1 = fma(s[I][1], cv, ta[I][1]);
@@ -241,7 +278,14 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
       const double* const ci = &A.cst[0][0] + thr_opaque0();
       const double t00 = ci[I * 6], t01 = ci[I * 6 + 1], t10 = ci[I * 6 + 2], t11 = ci[I * 6 + 3];
       const double zi0 = ZTV ? zr[ZTV ? I : 0][0] : ci[I * 6 + 4], zi1 = ZTV ? zr[ZTV ? I : 0][1] : ci[I * 6 + 5];
-      {
+      if (EPS && I == L) {
+        double p0 = D[I][0];
+        const double y00 = t00 * p0;
+        p0 = fma(y00, t00, SQ(QW * I));
+        p0 = fma(-s[I][0], s[I][0], p0);
+        D[I][0] = p0;
+        M[I][0] = fma(p0, zi0, M[I][0]);
+      } else {
         double p0 = D[I][0], p1 = D[I][1], p3 = D[I][2];
         const double y00 = fma(t01, p1, t00 * p0), y01 = fma(t01, p3, t00 * p1);
         const double y10 = fma(t11, p1, t10 * p0), y11 = fma(t11, p3, t10 * p1);
@@ -269,6 +313,21 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
           const int o = (oi - RO) * 4;
           p0 = SP(o), p1 = SP(o + 1), p2 = SP(o + 2), p3 = SP(o + 3);
         }
+        if (EPS && J == L) {
+          const double y00 = fma(t01, p2, t00 * p0), y10 = fma(t11, p2, t10 * p0);
+          p0 = fma(-s[I][0], s[J][0], y00 * u00);
+          p2 = fma(-s[I][1], s[J][0], y10 * u00);
+          if (oi < RO) {
+            O[oi < RO ? oi : 0][0] = p0, O[oi < RO ? oi : 0][2] = p2;
+          } else {
+            const int o = (oi - RO) * 4;
+            SP(o) = p0, SP(o + 2) = p2;
+          }
+          M[I][0] = fma(p0, zj0, M[I][0]);
+          M[I][1] = fma(p2, zj0, M[I][1]);
+          M[J][0] = fma(p2, zi1, fma(p0, zi0, M[J][0]));
+          continue;
+        }
         const double y00 = fma(t01, p2, t00 * p0), y01 = fma(t01, p3, t00 * p1);
         const double y10 = fma(t11, p2, t10 * p0), y11 = fma(t11, p3, t10 * p1);
         p0 = fma(-s[I][0], s[J][0], fma(y01, u01, y00 * u00));
@@ -294,10 +353,15 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
     }
   }
   {  // the last observation (src/LogLikC.cpp:200 -- P and a are not needed afterwards)
-    double F = Fc, za = zac;
+    double F = EPS ? heps : Fc, za = zac;
     if constexpr (!ZTV) {
 #pragma unroll
       for (int I = 0; I < NB; I++) {
+        if (EPS && I == L) {
+          F = fma(A.cst[I][4], M[I][0], F);
+          za = fma(A.cst[I][4], SA(2 * I), za);
+          continue;
+        }
         F = fma(A.cst[I][5], M[I][1], fma(A.cst[I][4], M[I][0], F));
         za = fma(A.cst[I][5], SA(2 * I + 1), fma(A.cst[I][4], SA(2 * I), za));
       }
@@ -328,7 +392,19 @@ constexpr int thr_smem_blocks(int nb) { return nb == 8 ? SSGPU_THR_S8 : nb == 7 
 // extra blocks measure the same at 8 blocks: 8.2e9 series*timesteps/s; 5 extra 6.5e9)
 constexpr int thr_smem_blocks_ztv(int nb, bool ztv) { return thr_smem_blocks(nb) + ((ztv && nb >= 5) ? (nb >= 7 ? 3 : 2) : 0); }
 
-int thr_smem_blocks_host(int nb, bool ztv) { return thr_smem_blocks_ztv(nb, ztv); }
+// residual shortcut: the nb - 1 blocks next to the last one are 2 x 1 and the last diagonal block is a scalar -- 14 doubles
+// fewer in registers at 7 blocks, so fewer blocks in shared memory (sized with ptxas -v like the others)
+#ifndef SSGPU_THR_S7E
+#define SSGPU_THR_S7E 7
+#endif
+#ifndef SSGPU_THR_S8E
+#define SSGPU_THR_S8E 16
+#endif
+constexpr int thr_smem_blocks_eps(int nb, bool ztv, bool eps) {
+  return !eps ? thr_smem_blocks_ztv(nb, ztv) : nb == 8 ? SSGPU_THR_S8E : nb == 7 ? SSGPU_THR_S7E : nb == 6 ? 1 : 0;
+}
+
+int thr_smem_blocks_host(int nb, bool ztv, bool eps) { return thr_smem_blocks_eps(nb, ztv, eps); }
 
 size_t thr_handoff_bytes(int nb, bool qoff, long long E) {
   const BlkHandoff hl(nb, qoff);
@@ -336,7 +412,7 @@ size_t thr_handoff_bytes(int nb, bool qoff, long long E) {
 }
 
 // FP64 operations (fma = 2) per series and time step: the counts of the SASS of the loop
-int thr_flops_per_step(int nb, bool qoff) {
+int thr_flops_per_step(int nb, bool qoff, bool eps) {
   const int noff = nb * (nb - 1) / 2;
   // vectors: F, z'a 4 fma; tm, T a 2 mul + 2 fma each; s 2 mul; a 2 fma    (per block row)
   const int fma_v = 4 + 4 + 2, mul_v = 4 + 2;
@@ -346,21 +422,28 @@ int thr_flops_per_step(int nb, bool qoff) {
   const int fma_d = 4 + (qoff ? 6 : 5) + 3 + 4, mul_d = 4 + (qoff ? 0 : 1);
   // block above the diagonal: 4 mul + 4 fma, 4 mul + 4 fma, rank-1 4 fma, M 8 fma
   const int fma_o = 4 + 4 + 4 + 8, mul_o = 8;
+  if (eps) {
+    // the last block is a scalar (vectors 3 fma + 3 mul, diagonal 3 fma + 1 mul), the nb - 1 blocks next to it are
+    // 2 x 1 (2 mul + 2 fma, 2 mul, rank-1 2 fma, M 4 fma)
+    const int fma = (nb - 1) * fma_v + 3 + fma_s + (nb - 1) * fma_d + 3 + (noff - (nb - 1)) * fma_o + (nb - 1) * 8;
+    const int mul = (nb - 1) * mul_v + 3 + mul_s + (nb - 1) * mul_d + 1 + (noff - (nb - 1)) * mul_o + (nb - 1) * 4;
+    return 2 * fma + mul + add_s;
+  }
   const int fma = nb * fma_v + fma_s + nb * fma_d + noff * fma_o, mul = nb * mul_v + mul_s + nb * mul_d + noff * mul_o;
   return 2 * fma + mul + add_s;
 }
 
-template <int NB, bool QOFF, bool ZTV = false>
+template <int NB, bool QOFF, bool ZTV = false, bool EPS = false>
 static int launch_thr_one(const ThrArgs& A, cudaStream_t st) {
   // time-varying Z: 2 NB more vector registers hold the row of Z, so two more blocks move to shared memory (NB >= 5)
-  constexpr int S = thr_smem_blocks_ztv(NB, ZTV);
+  constexpr int S = thr_smem_blocks_eps(NB, ZTV, EPS);
   constexpr BlkHandoff HL(NB, QOFF);
   const size_t smem = (size_t)((2 + HL.qw) * NB + 4 * S) * kThrThreads * sizeof(double);
   // a function attribute belongs to the device it was set on (one slot per device: api.cu)
-  SS_CUDA(cudaFuncSetAttribute(loglik_thr_kernel<NB, S, QOFF, ZTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SS_CUDA(cudaFuncSetAttribute(loglik_thr_kernel<NB, S, QOFF, ZTV, EPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (A.E + kThrThreads - 1) / kThrThreads;
   SS_ARG(blocks < (1LL << 31), "thread kernel: batch too large for one launch");
-  loglik_thr_kernel<NB, S, QOFF, ZTV><<<(unsigned)blocks, kThrThreads, smem, st>>>(A);
+  loglik_thr_kernel<NB, S, QOFF, ZTV, EPS><<<(unsigned)blocks, kThrThreads, smem, st>>>(A);
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;
 }
@@ -371,8 +454,10 @@ static int launch_thr_one(const ThrArgs& A, cudaStream_t st) {
 bool thr_supported(int nb, int p, bool ztv) { (void)ztv; return p == 1 && nb >= SSGPU_THR_MIN_NB && nb <= kThrMaxNB; }
 
 // y, out: of the first series of the launch; hd / hi: filled by the lane kernel for the same E evaluations
+// eps: position 1 of the last block of the plan is the residual state (see the kernel), time-invariant Z only
 int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* zt, const double* y, long long B,
-                      long long E, long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st) {
+                      long long E, long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st,
+                      bool eps) {
   ThrArgs A{};
   A.zt = zt;
   A.y = y;
@@ -389,8 +474,10 @@ int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double*
     A.cst[I][5] = z_internal[2 * I + 1];
   }
   const bool qoff = pl.q_offdiag != 0;
+  SS_ARG(!(eps && zt), "thread kernel: the residual shortcut needs a time-invariant Z");
 #define SS_THR_CASE(NBV)                                                                                                  \
   case NBV:                                                                                                               \
+    if (eps) return qoff ? launch_thr_one<NBV, true, false, true>(A, st) : launch_thr_one<NBV, false, false, true>(A, st); \
     return zt ? (qoff ? launch_thr_one<NBV, true, true>(A, st) : launch_thr_one<NBV, false, true>(A, st))                 \
               : (qoff ? launch_thr_one<NBV, true>(A, st) : launch_thr_one<NBV, false>(A, st));
   switch (pl.nb) {

@@ -380,6 +380,55 @@ def test_batch_blk_kernel(name):
         assert abs(gen[b] - want) <= RTOL * max(1, abs(want)), (name, b, gen[b], want)
 
 
+@pytest.mark.parametrize("name", ["level_slope", "level_seasonal4", "bsm12", "bsm12_cycle"])
+def test_thread_kernel_residual_shortcut(name):
+    """The thread-per-evaluation kernel drops the residual state of the reference's layout (loglik_thr.cu, EPS): with a
+    diffuse phase, from a start WITHOUT one (P_inf = 0; P_star[eps, eps] different from H is honoured at the first time
+    point), and not at all when a[eps] != 0 or P_star couples the residual -- every variant against the oracle."""
+    rng = np.random.default_rng(len(name) + 3)
+    comps = {"level_slope": [sysmat.comp_level_slope(0.3, 0.02)],
+             "level_seasonal4": [sysmat.comp_local_level(0.2), sysmat.comp_bsm_trig(4, 0.05)],
+             "bsm12": [sysmat.comp_level_slope(0.1, 0.01), sysmat.comp_bsm_trig(12, 0.05)],
+             "bsm12_cycle": [sysmat.comp_level_slope(0.1, 0.01), sysmat.comp_bsm_trig(12, 0.05),
+                             _cycle(0.9, 0.4, 0.3)]}[name]            # 8 blocks, the residual paired with a seasonal state
+    sm = sysmat._combine(1, [[0.6]], comps)
+    m, N, B = sm.m, 60, 48
+    y = np.stack([simulate_y(rng, sm, N, missing=0.1)[:, 0] for _ in range(B)], axis=1)
+    y[:4, 3] = np.nan
+
+    def check(model, dropped, **kw):
+        got = api.loglik_batch(y, model, kernel="blk", **kw)
+        k = api.last_kernel()
+        assert k.startswith("loglik_thr_kernel<") and ("residual state dropped" in k) == dropped, k
+        for b in range(0, B, 5):
+            mb = model
+            if "P_star_diag" in kw:
+                mb = sysmat.SysMat(Z=model.Z, T=model.T, R=model.R, Q=np.diag(kw["Q_diag"][b])[:, :, None], a=model.a,
+                                   P_inf=model.P_inf, P_star=np.diag(kw["P_star_diag"][b]))
+            yb = y[:, b:b + 1]
+            want = cport.LogLikC(yb, np.isnan(yb), *mb.args())
+            assert math.isfinite(want) and abs(got[b] - want) <= RTOL * max(1, abs(want)), (name, dropped, b, got[b], want)
+        return got
+
+    base = check(sm, True)
+    lanes = api.loglik_batch(y, sm, kernel="blk_lanes")
+    assert np.allclose(base, lanes, rtol=1e-11, atol=0)
+    # no diffuse phase: the kernel starts from the caller's P_star, whose residual entry need not be H
+    P0 = np.diag(rng.uniform(0.5, 2.0, m))
+    P0[0, 0] = 1.7
+    flat = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=sm.Q, a=sm.a, P_inf=np.zeros((m, m)), P_star=P0)
+    check(flat, True)
+    scale = rng.uniform(0.5, 2.0, size=(B, 1))
+    check(flat, True, Q_diag=np.diag(sm.Q[:, :, 0])[None, :] * scale, P_star_diag=np.diag(P0)[None, :] * scale)
+    # what the shortcut assumes does not hold: a[eps] != 0, P_star couples the residual with another state
+    a1 = sm.a.copy()
+    a1[0] = 0.3
+    check(sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=sm.Q, a=a1, P_inf=sm.P_inf, P_star=sm.P_star), False)
+    P1 = P0.copy()
+    P1[0, 1] = P1[1, 0] = 0.2
+    check(sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=sm.Q, a=sm.a, P_inf=np.zeros((m, m)), P_star=P1), False)
+
+
 @pytest.mark.parametrize("seasonal", [12, 4, 24])
 def test_batch_blk_kernel_time_varying_z(seasonal):
     """Univariate structural model with two explanatory variables (R/Components-Regressors.R:60-78: constant, exactly
