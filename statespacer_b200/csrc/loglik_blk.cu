@@ -988,6 +988,28 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
       pl.eps = 1;
     }
   }
+  // A local level with slope, T_J = [[1, 1], [0, 1]] in either order of its two states: moved to block 0, where the
+  // thread kernel replaces its products by sums (loglik_thr.cu, LS)
+  static const bool ls_on = [] {
+    const char* e = getenv("SSGPU_THR_LS");
+    return !(e && e[0] == '0');
+  }();
+  pl.ls = 0;
+  if (ls_on && p == 1 && nZ == 1 && pl.nb >= 2 && pl.nb <= kBlkMaxNB / 2) {
+    for (int J = 0; J < pl.nb - (pl.eps ? 1 : 0) && !pl.ls; J++) {
+      const double* t = pl.Tb[J];
+      const bool upper = t[0] == 1.0 && t[1] == 1.0 && t[2] == 0.0 && t[3] == 1.0;
+      const bool lower = t[0] == 1.0 && t[1] == 0.0 && t[2] == 1.0 && t[3] == 1.0;
+      if (!upper && !lower) continue;
+      if (lower) {
+        std::swap(pl.perm[2 * J], pl.perm[2 * J + 1]);
+        std::swap(pl.Tb[J][1], pl.Tb[J][2]);
+      }
+      for (int c = 0; c < 2; c++) std::swap(pl.perm[2 * J + c], pl.perm[c]);
+      for (int c = 0; c < 4; c++) std::swap(pl.Tb[J][c], pl.Tb[0][c]);
+      pl.ls = 1;
+    }
+  }
   BlkArgs A{};
   A.md = md;
   A.y = y;
@@ -1045,7 +1067,7 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     count_launch();
     return SSGPU_OK;
   };
-  static thread_local char name[160];
+  static thread_local char name[224];
   // SSGPU_BLK_THREAD=0: the lane kernel alone (experiments, A/B runs)
   static const bool thr_on = [] {
     const char* e = getenv("SSGPU_BLK_THREAD");
@@ -1081,12 +1103,15 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
       Ac.hd = scratch.as<double>();
       Ac.hi = reinterpret_cast<int*>(Ac.hd + (size_t)hl.doubles() * Ec);
       SS_TRY(launch_lanes(Ac));
-      SS_TRY(launch_loglik_thr(pl, &A.z[0][0], A.zt, Ac.y, Bc, Ec, B, md.N, Ac.hd, Ac.hi, Ac.out, st, pl.eps != 0));
+      SS_TRY(launch_loglik_thr(pl, &A.z[0][0], A.zt, Ac.y, Bc, Ec, B, md.N, Ac.hd, Ac.hi, Ac.out, st, pl.eps != 0, pl.ls != 0));
       count_launch();
     }
     snprintf(name, sizeof name, "loglik_thr_kernel<NB=%d,S=%d,flop_per_step=%d>%s%s after loglik_blk_kernel<L=%d,NB=%d> (diffuse phase)",
-             pl.nb, thr_smem_blocks_host(pl.nb, nZ > 1, pl.eps != 0), thr_flops_per_step(pl.nb, pl.q_offdiag != 0, pl.eps != 0),
-             nZ > 1 ? " time-varying Z" : "", pl.eps ? " residual state dropped" : "", L, pl.nb);
+             pl.nb, thr_smem_blocks_host(pl.nb, nZ > 1, pl.eps != 0),
+             thr_flops_per_step(pl.nb, pl.q_offdiag != 0, pl.eps != 0, pl.ls != 0), nZ > 1 ? " time-varying Z" : "",
+             pl.eps ? (pl.ls ? " residual state dropped, level + slope block by sums" : " residual state dropped")
+                    : (pl.ls ? " level + slope block by sums" : ""),
+             L, pl.nb);
     set_last_kernel(name);
     return SSGPU_OK;
   }

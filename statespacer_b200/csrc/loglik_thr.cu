@@ -92,9 +92,14 @@ __device__ __forceinline__ int thr_opaque0() {
 // its partner, the blocks (I, last) are 2 x 1, F gets H added.  At 7 blocks (config 5) that is 738 instead of 861 FP64
 // instructions per series and time step.  Only P[eps, eps] of the FIRST time point is taken from the hand-over (a model
 // without diffuse phase starts from the caller's P_star); the launcher checks what the kernel assumes of P_star and a.
-template <int NB, int S, bool QOFF, bool ZTV = false, bool EPS = false>
+//
+// LS: block 0 is a local level with slope, T_0 = [[1, 1], [0, 1]] (R/Components-Unobserved.R:150-159).  Its products are
+// sums: T_0 X = [x0 + x1 ; x1] row-wise -- one DADD where the generic block spends two multiplications and two
+// multiply-adds, bit for bit the same result (1 * x is exact).  48 FP64 instructions fewer per step at 7 blocks.
+template <int NB, int S, bool QOFF, bool ZTV = false, bool EPS = false, bool LS = false>
 __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThreads) loglik_thr_kernel(const ThrArgs A) {
   static_assert(!(EPS && ZTV), "residual shortcut: time-invariant Z");
+  static_assert(!(LS && ZTV), "level + slope shortcut: time-invariant Z");
   constexpr int L = NB - 1;
   constexpr BlkHandoff HL(NB, QOFF);
   constexpr int NOFF = HL.noff();
@@ -238,6 +243,16 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
         ta[I][0] = t00 * a0;
         continue;
       }
+      if (LS && I == 0) {
+        const double z0 = cv0[I * 6 + 4], z1 = cv0[I * 6 + 5];
+        const double m0 = M[I][0], m1 = M[I][1], a0 = SA(2 * I), a1 = SA(2 * I + 1);
+        F = fma(z1, m1, fma(z0, m0, F));
+        za = fma(z1, a1, fma(z0, a0, za));
+        M[I][0] = m0 + m1;
+        ta[I][0] = a0 + a1;
+        ta[I][1] = a1;
+        continue;
+      }
       const double t00 = cv0[I * 6], t01 = cv0[I * 6 + 1], t10 = cv0[I * 6 + 2], t11 = cv0[I * 6 + 3];
       const double m0 = M[I][0], m1 = M[I][1], a0 = SA(2 * I), a1 = SA(2 * I + 1);
       if constexpr (!ZTV) {
@@ -285,6 +300,20 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
         p0 = fma(-s[I][0], s[I][0], p0);
         D[I][0] = p0;
         M[I][0] = fma(p0, zi0, M[I][0]);
+      } else if (LS && I == 0) {
+        double p0 = D[I][0], p1 = D[I][1], p3 = D[I][2];
+        const double y00 = p0 + p1, y01 = p1 + p3;  // T_0 P_00 = [[p0 + p1, p1 + p3], [p1, p3]]
+        p0 = y01 + (y00 + SQ(QW * I));  // the association of the generic block's fma chain: same bits
+        p1 = QOFF ? y01 + SQ(QW * I + 1) : y01;
+        p3 = p3 + SQ(QW * I + QW - 1);
+        p0 = fma(-s[I][0], s[I][0], p0);
+        p1 = fma(-s[I][0], s[I][1], p1);
+        p3 = fma(-s[I][1], s[I][1], p3);
+        D[I][0] = p0;
+        D[I][1] = p1;
+        D[I][2] = p3;
+        M[I][0] = fma(p1, zi1, fma(p0, zi0, M[I][0]));
+        M[I][1] = fma(p3, zi1, fma(p1, zi0, M[I][1]));
       } else {
         double p0 = D[I][0], p1 = D[I][1], p3 = D[I][2];
         const double y00 = fma(t01, p1, t00 * p0), y01 = fma(t01, p3, t00 * p1);
@@ -314,7 +343,8 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
           p0 = SP(o), p1 = SP(o + 1), p2 = SP(o + 2), p3 = SP(o + 3);
         }
         if (EPS && J == L) {
-          const double y00 = fma(t01, p2, t00 * p0), y10 = fma(t11, p2, t10 * p0);
+          const double y00 = (LS && I == 0) ? p0 + p2 : fma(t01, p2, t00 * p0);
+          const double y10 = (LS && I == 0) ? p2 : fma(t11, p2, t10 * p0);
           p0 = fma(-s[I][0], s[J][0], y00 * u00);
           p2 = fma(-s[I][1], s[J][0], y10 * u00);
           if (oi < RO) {
@@ -328,8 +358,10 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
           M[J][0] = fma(p2, zi1, fma(p0, zi0, M[J][0]));
           continue;
         }
-        const double y00 = fma(t01, p2, t00 * p0), y01 = fma(t01, p3, t00 * p1);
-        const double y10 = fma(t11, p2, t10 * p0), y11 = fma(t11, p3, t10 * p1);
+        const double y00 = (LS && I == 0) ? p0 + p2 : fma(t01, p2, t00 * p0);
+        const double y01 = (LS && I == 0) ? p1 + p3 : fma(t01, p3, t00 * p1);
+        const double y10 = (LS && I == 0) ? p2 : fma(t11, p2, t10 * p0);
+        const double y11 = (LS && I == 0) ? p3 : fma(t11, p3, t10 * p1);
         p0 = fma(-s[I][0], s[J][0], fma(y01, u01, y00 * u00));
         p1 = fma(-s[I][0], s[J][1], fma(y01, u11, y00 * u10));
         p2 = fma(-s[I][1], s[J][0], fma(y11, u01, y10 * u00));
@@ -412,7 +444,7 @@ size_t thr_handoff_bytes(int nb, bool qoff, long long E) {
 }
 
 // FP64 operations (fma = 2) per series and time step: the counts of the SASS of the loop
-int thr_flops_per_step(int nb, bool qoff, bool eps) {
+int thr_flops_per_step(int nb, bool qoff, bool eps, bool ls) {
   const int noff = nb * (nb - 1) / 2;
   // vectors: F, z'a 4 fma; tm, T a 2 mul + 2 fma each; s 2 mul; a 2 fma    (per block row)
   const int fma_v = 4 + 4 + 2, mul_v = 4 + 2;
@@ -425,25 +457,37 @@ int thr_flops_per_step(int nb, bool qoff, bool eps) {
   if (eps) {
     // the last block is a scalar (vectors 3 fma + 3 mul, diagonal 3 fma + 1 mul), the nb - 1 blocks next to it are
     // 2 x 1 (2 mul + 2 fma, 2 mul, rank-1 2 fma, M 4 fma)
-    const int fma = (nb - 1) * fma_v + 3 + fma_s + (nb - 1) * fma_d + 3 + (noff - (nb - 1)) * fma_o + (nb - 1) * 8;
-    const int mul = (nb - 1) * mul_v + 3 + mul_s + (nb - 1) * mul_d + 1 + (noff - (nb - 1)) * mul_o + (nb - 1) * 4;
-    return 2 * fma + mul + add_s;
+    int fma = (nb - 1) * fma_v + 3 + fma_s + (nb - 1) * fma_d + 3 + (noff - (nb - 1)) * fma_o + (nb - 1) * 8;
+    int mul = (nb - 1) * mul_v + 3 + mul_s + (nb - 1) * mul_d + 1 + (noff - (nb - 1)) * mul_o + (nb - 1) * 4;
+    int add = add_s;
+    if (ls) {  // block 0 = level + slope: vectors 2 add for 4 mul + 4 fma, diagonal 5 (4 with correlated R Q R': 6) add for
+               // 5 mul + 9 fma (4 mul + 10 fma), full neighbours 2 add for 4 mul + 4 fma, the 2 x 1 neighbour 1 add for 2 + 2
+      fma -= 4 + (qoff ? 10 : 9) + (nb - 2) * 4 + 2;
+      mul -= 4 + (qoff ? 4 : 5) + (nb - 2) * 4 + 2;
+      add += 2 + (qoff ? 6 : 5) + (nb - 2) * 2 + 1;
+    }
+    return 2 * fma + mul + add;
   }
-  const int fma = nb * fma_v + fma_s + nb * fma_d + noff * fma_o, mul = nb * mul_v + mul_s + nb * mul_d + noff * mul_o;
-  return 2 * fma + mul + add_s;
+  int fma = nb * fma_v + fma_s + nb * fma_d + noff * fma_o, mul = nb * mul_v + mul_s + nb * mul_d + noff * mul_o, add = add_s;
+  if (ls) {
+    fma -= 4 + (qoff ? 10 : 9) + (nb - 1) * 4;
+    mul -= 4 + (qoff ? 4 : 5) + (nb - 1) * 4;
+    add += 2 + (qoff ? 6 : 5) + (nb - 1) * 2;
+  }
+  return 2 * fma + mul + add;
 }
 
-template <int NB, bool QOFF, bool ZTV = false, bool EPS = false>
+template <int NB, bool QOFF, bool ZTV = false, bool EPS = false, bool LS = false>
 static int launch_thr_one(const ThrArgs& A, cudaStream_t st) {
   // time-varying Z: 2 NB more vector registers hold the row of Z, so two more blocks move to shared memory (NB >= 5)
   constexpr int S = thr_smem_blocks_eps(NB, ZTV, EPS);
   constexpr BlkHandoff HL(NB, QOFF);
   const size_t smem = (size_t)((2 + HL.qw) * NB + 4 * S) * kThrThreads * sizeof(double);
   // a function attribute belongs to the device it was set on (one slot per device: api.cu)
-  SS_CUDA(cudaFuncSetAttribute(loglik_thr_kernel<NB, S, QOFF, ZTV, EPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SS_CUDA(cudaFuncSetAttribute(loglik_thr_kernel<NB, S, QOFF, ZTV, EPS, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (A.E + kThrThreads - 1) / kThrThreads;
   SS_ARG(blocks < (1LL << 31), "thread kernel: batch too large for one launch");
-  loglik_thr_kernel<NB, S, QOFF, ZTV, EPS><<<(unsigned)blocks, kThrThreads, smem, st>>>(A);
+  loglik_thr_kernel<NB, S, QOFF, ZTV, EPS, LS><<<(unsigned)blocks, kThrThreads, smem, st>>>(A);
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;
 }
@@ -457,7 +501,7 @@ bool thr_supported(int nb, int p, bool ztv) { (void)ztv; return p == 1 && nb >= 
 // eps: position 1 of the last block of the plan is the residual state (see the kernel), time-invariant Z only
 int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* zt, const double* y, long long B,
                       long long E, long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st,
-                      bool eps) {
+                      bool eps, bool ls) {
   ThrArgs A{};
   A.zt = zt;
   A.y = y;
@@ -474,9 +518,12 @@ int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double*
     A.cst[I][5] = z_internal[2 * I + 1];
   }
   const bool qoff = pl.q_offdiag != 0;
-  SS_ARG(!(eps && zt), "thread kernel: the residual shortcut needs a time-invariant Z");
+  SS_ARG(!((eps || ls) && zt), "thread kernel: the residual / level + slope shortcuts need a time-invariant Z");
 #define SS_THR_CASE(NBV)                                                                                                  \
   case NBV:                                                                                                               \
+    if (eps && ls)                                                                                                        \
+      return qoff ? launch_thr_one<NBV, true, false, true, true>(A, st) : launch_thr_one<NBV, false, false, true, true>(A, st); \
+    if (ls) return qoff ? launch_thr_one<NBV, true, false, false, true>(A, st) : launch_thr_one<NBV, false, false, false, true>(A, st); \
     if (eps) return qoff ? launch_thr_one<NBV, true, false, true>(A, st) : launch_thr_one<NBV, false, false, true>(A, st); \
     return zt ? (qoff ? launch_thr_one<NBV, true, true>(A, st) : launch_thr_one<NBV, false, true>(A, st))                 \
               : (qoff ? launch_thr_one<NBV, true>(A, st) : launch_thr_one<NBV, false>(A, st));

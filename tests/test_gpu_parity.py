@@ -1556,6 +1556,42 @@ for N in (61, 5):
         assert np.all(np.isfinite(outs["plain"][0]))
 
 
+def test_thread_kernel_shortcuts_against_the_generic_instantiation():
+    """The thread kernel's two structural shortcuts against its generic instantiation in subprocesses (the switches are
+    read once per process): SSGPU_THR_LS=0 -- the level + slope block by sums is bit for bit the generic product
+    (1 * x is exact) -- and SSGPU_THR_EPS=0 -- dropping the residual state changes only the order of a few sums
+    (1e-12)."""
+    import subprocess
+    import sys
+    import tempfile
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
+from conftest import simulate_y
+from statespacer_b200 import api, sysmat
+rng = np.random.default_rng(8)
+sm = sysmat.bsm12(0.5 * np.log([1.0, 0.1, 0.01, 0.05]))
+y = np.stack([simulate_y(rng, sm, 80, missing=0.05)[:, 0] for _ in range(96)], axis=1)
+got = api.loglik_batch(y, sm, kernel="blk")
+open(sys.argv[1] + ".txt", "w").write(api.last_kernel())
+np.save(sys.argv[1] + ".npy", got)
+''' % (ROOT_DIR, ROOT_DIR)
+    with tempfile.TemporaryDirectory() as d:
+        outs, names = {}, {}
+        for tag, env in (("both", {}), ("no_ls", {"SSGPU_THR_LS": "0"}), ("no_eps", {"SSGPU_THR_EPS": "0", "SSGPU_THR_LS": "0"})):
+            r = subprocess.run([sys.executable, "-c", code, os.path.join(d, tag)], env={**os.environ, **env},
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs[tag] = np.load(os.path.join(d, tag + ".npy"))
+            names[tag] = open(os.path.join(d, tag + ".txt")).read()
+        assert "residual state dropped, level + slope block by sums" in names["both"], names
+        assert "residual state dropped" in names["no_ls"] and "level + slope" not in names["no_ls"], names
+        assert "dropped" not in names["no_eps"] and "level + slope" not in names["no_eps"], names
+        assert np.all(np.isfinite(outs["both"]))
+        assert np.array_equal(outs["both"], outs["no_ls"])
+        assert np.allclose(outs["both"], outs["no_eps"], rtol=1e-12, atol=0)
+
+
 def test_loglik_from_theta_with_ldl_covariance_blocks():
     """SURVEY.md 8f row 1 for multivariate models: the variance matrices are L D L' built ON THE DEVICE from theta
     (R/Cholesky.R:148-167) -- a bivariate local level with correlated observation errors and correlated level
