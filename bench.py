@@ -74,10 +74,11 @@ def executed_flops(kernel_name):
 
 
 def executed_fp64_instructions(kernel_name):
-    """FP64 instructions (DFMA + DMUL + DADD) per series*timestep of the thread-per-evaluation kernel at 7 blocks
-    (loglik_thr.cu thr_flops_per_step: 609 DFMA + 251 DMUL + 1 DADD, the counts of the SASS of its loop and of ncu's
-    smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on); None for the other kernels."""
-    return 861 if (kernel_name or "").startswith("loglik_thr_kernel<NB=7,") else None
+    """FP64 instructions (DFMA + DMUL + DADD, one issue slot each) per series*timestep of the thread-per-evaluation kernel:
+    the library reports the count of its instantiation in the kernel name (loglik_thr.cu thr_flops_per_step -- the counts
+    of the SASS of its loop, profiles/sass_thr_r2_hotloop.txt); None for the other kernels."""
+    m = re.search(r"fp64_instr_per_step=(\d+)", kernel_name or "")
+    return int(m.group(1)) if m else None
 
 
 def variants(theta):

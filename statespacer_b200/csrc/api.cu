@@ -1038,8 +1038,9 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
     SS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     SS_CUDA(cudaEventRecord(ready, st));  // yd exists on the compute stream from here on
     SS_CUDA(cudaStreamWaitEvent(cs, ready, 0));
-    const HostShared hs{model->T.n_slices == 1 ? model->T.data : nullptr, model->R.n_slices == 1 ? model->R.data : nullptr,
-                        model->Z.n_slices == 1 ? model->Z.data : nullptr, nullptr};
+    HostShared hs{model->T.n_slices == 1 ? model->T.data : nullptr, model->R.n_slices == 1 ? model->R.data : nullptr,
+                  model->Z.n_slices == 1 ? model->Z.data : nullptr, nullptr};
+    if (model->a.stride_series == 0 && model->a.stride_variant == 0) hs.a = model->a.data;  // shared: no device round trip
     auto upload = [&](int c) -> int {
       const long long b0 = cb[c], bn = cb[c + 1] - cb[c];
       SS_CUDA(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));

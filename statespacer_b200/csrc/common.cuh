@@ -284,6 +284,7 @@ int launch_fd_gradient(const double* out, long long B, int k, double h, double* 
 // Block-row DFMA kernel for transition matrices that are block diagonal with blocks of at most 2 x 2 (loglik_blk.cu)
 struct HostShared {  // optional host copies of the shared, time-invariant matrices (null = fetch from the device)
   const double *T, *R, *Z, *Q;
+  const double *a = nullptr, *P_star = nullptr;  // in the storage of the device copy (P_star: dense m x m)
 };
 struct BlkPlan {
   int nb;                // number of 2 x 2 blocks (a lone state is padded with an empty partner)
@@ -291,6 +292,7 @@ struct BlkPlan {
   signed char perm[32];  // internal position 2I+e holds state perm[2I+e] of the caller, -1 = padding
   int eps;               // position 1 of the last block is the residual state (set by the launcher, which sees Z)
   int ls;                // block 0 is a local level with slope: T_0 = [[1, 1], [0, 1]] (set by the launcher)
+  int zs;                // z = 0 for the second state of every block (set by the launcher)
   double Tb[16][4];      // T_J[row][col] at [2*row + col]
 };
 bool plan_blocks(const double* Th, int t_diag, const double* Rh, int r_diag, const unsigned char* qpat, int m, int r,
@@ -307,11 +309,11 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
 // above runs the diffuse phase first and hands the state over (blk_handoff.cuh)
 bool thr_supported(int nb, int p, bool ztv);
 size_t thr_handoff_bytes(int nb, bool qoff, long long E);
-int thr_flops_per_step(int nb, bool qoff, bool eps = false, bool ls = false);
+int thr_flops_per_step(int nb, bool qoff, bool eps = false, bool ls = false, bool zs = false, bool instr = false);
 int thr_smem_blocks_host(int nb, bool ztv, bool eps = false);
 int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* zt, const double* y, long long B,
                       long long E, long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st,
-                      bool eps = false, bool ls = false);
+                      bool eps = false, bool ls = false, bool zs = false);
 
 // Thread-per-series kernel on the component states alone, the p residual states of the reference's layout eliminated
 // (loglik_core.cu): m - p <= 8, p <= 16, everything shared and time-invariant, diagonal H

@@ -918,6 +918,18 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     Qh.resize((size_t)r * r);
     SS_TRY(fetch(Qh, hs ? hs->Q : nullptr, md.Q.p));
   }
+  // what the thread kernel's residual shortcut looks at (p = 1, time-invariant Z): a, and a dense P_star, when shared
+  std::vector<double> ah, Psh;
+  if (p == 1 && nZ == 1) {
+    if (md.a.shared()) {
+      ah.resize((size_t)m);
+      SS_TRY(fetch(ah, hs ? hs->a : nullptr, md.a.p));
+    }
+    if (md.P_star.shared() && !md.P_star.diag) {
+      Psh.resize((size_t)m * m);
+      SS_TRY(fetch(Psh, hs ? hs->P_star : nullptr, md.P_star.p));
+    }
+  }
   if (need_sync) SS_CUDA(cudaStreamSynchronize(st));
   if (!md.Q.diag) {
     qpat.resize((size_t)r * r);
@@ -966,15 +978,9 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
         }
     }
     if (ok) {
-      std::vector<double> ah((size_t)m), Ph;
-      SS_CUDA(cudaMemcpyAsync(ah.data(), md.a.p, ah.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-      if (!md.P_star.diag) {
-        Ph.resize((size_t)m * m);
-        SS_CUDA(cudaMemcpyAsync(Ph.data(), md.P_star.p, Ph.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-      }
-      SS_CUDA(cudaStreamSynchronize(st));
-      ok = ah[e] == 0.0;
-      for (int k = 0; k < m && ok && !Ph.empty(); k++) ok = k == e || (Ph[e + (size_t)k * m] == 0.0 && Ph[k + (size_t)e * m] == 0.0);
+      ok = !ah.empty() && ah[e] == 0.0 && (md.P_star.diag || !Psh.empty());
+      for (int k = 0; k < m && ok && !Psh.empty(); k++)
+        ok = k == e || (Psh[e + (size_t)k * m] == 0.0 && Psh[k + (size_t)e * m] == 0.0);
     }
     if (ok) {
       const int last = pl.nb - 1;
@@ -1009,6 +1015,26 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
       for (int c = 0; c < 4; c++) std::swap(pl.Tb[J][c], pl.Tb[0][c]);
       pl.ls = 1;
     }
+  }
+  // z = 0 for the second state of every block (after turning blocks whose FIRST state has the zero around): the thread
+  // kernel leaves those multiply-adds out (loglik_thr.cu, ZS)
+  static const bool zs_on = [] {
+    const char* e = getenv("SSGPU_THR_ZS");
+    return !(e && e[0] == '0');
+  }();
+  pl.zs = 0;
+  if (zs_on && p == 1 && nZ == 1 && pl.eps) {
+    auto zof = [&](int i) { return pl.perm[i] >= 0 ? Zh[pl.perm[i]] : 0.0; };
+    bool all = true;
+    for (int J = 0; J < pl.nb - 1; J++) {  // the last block is (partner, residual): the kernel never reads z of position 1
+      if (zof(2 * J + 1) != 0.0 && zof(2 * J) == 0.0 && !(pl.ls && J == 0)) {
+        std::swap(pl.perm[2 * J], pl.perm[2 * J + 1]);
+        std::swap(pl.Tb[J][0], pl.Tb[J][3]);
+        std::swap(pl.Tb[J][1], pl.Tb[J][2]);
+      }
+      all = all && zof(2 * J + 1) == 0.0;
+    }
+    pl.zs = all ? 1 : 0;
   }
   BlkArgs A{};
   A.md = md;
@@ -1067,7 +1093,7 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     count_launch();
     return SSGPU_OK;
   };
-  static thread_local char name[224];
+  static thread_local char name[288];
   // SSGPU_BLK_THREAD=0: the lane kernel alone (experiments, A/B runs)
   static const bool thr_on = [] {
     const char* e = getenv("SSGPU_BLK_THREAD");
@@ -1103,15 +1129,21 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
       Ac.hd = scratch.as<double>();
       Ac.hi = reinterpret_cast<int*>(Ac.hd + (size_t)hl.doubles() * Ec);
       SS_TRY(launch_lanes(Ac));
-      SS_TRY(launch_loglik_thr(pl, &A.z[0][0], A.zt, Ac.y, Bc, Ec, B, md.N, Ac.hd, Ac.hi, Ac.out, st, pl.eps != 0, pl.ls != 0));
+      SS_TRY(launch_loglik_thr(pl, &A.z[0][0], A.zt, Ac.y, Bc, Ec, B, md.N, Ac.hd, Ac.hi, Ac.out, st, pl.eps != 0, pl.ls != 0, pl.zs != 0));
       count_launch();
     }
-    snprintf(name, sizeof name, "loglik_thr_kernel<NB=%d,S=%d,flop_per_step=%d>%s%s after loglik_blk_kernel<L=%d,NB=%d> (diffuse phase)",
+    snprintf(name, sizeof name,
+             "loglik_thr_kernel<NB=%d,S=%d,flop_per_step=%d,fp64_instr_per_step=%d>%s%s after loglik_blk_kernel<L=%d,NB=%d> (diffuse phase)",
              pl.nb, thr_smem_blocks_host(pl.nb, nZ > 1, pl.eps != 0),
-             thr_flops_per_step(pl.nb, pl.q_offdiag != 0, pl.eps != 0, pl.ls != 0), nZ > 1 ? " time-varying Z" : "",
+             thr_flops_per_step(pl.nb, pl.q_offdiag != 0, pl.eps != 0, pl.ls != 0, pl.zs != 0),
+             thr_flops_per_step(pl.nb, pl.q_offdiag != 0, pl.eps != 0, pl.ls != 0, pl.zs != 0, true), nZ > 1 ? " time-varying Z" : "",
              pl.eps ? (pl.ls ? " residual state dropped, level + slope block by sums" : " residual state dropped")
                     : (pl.ls ? " level + slope block by sums" : ""),
              L, pl.nb);
+    if (pl.zs) {
+      const size_t len = strlen(name);
+      snprintf(name + len, sizeof name - len, ", zero z skipped");
+    }
     set_last_kernel(name);
     return SSGPU_OK;
   }

@@ -96,8 +96,14 @@ __device__ __forceinline__ int thr_opaque0() {
 // LS: block 0 is a local level with slope, T_0 = [[1, 1], [0, 1]] (R/Components-Unobserved.R:150-159).  Its products are
 // sums: T_0 X = [x0 + x1 ; x1] row-wise -- one DADD where the generic block spends two multiplications and two
 // multiply-adds, bit for bit the same result (1 * x is exact).  48 FP64 instructions fewer per step at 7 blocks.
-template <int NB, int S, bool QOFF, bool ZTV = false, bool EPS = false, bool LS = false>
+//
+// ZS: the second state of every block has z = 0 (level + slope, trigonometric seasonal pairs, cycles: Z = (1, 0) per pair,
+// R/Components-Unobserved.R:143,491-500): the multiply-adds with that zero are left out -- fma(x, 0, acc) == acc, so
+// the same bits again.  90 FP64 instructions fewer per step at 7 blocks.
+template <int NB, int S, bool QOFF, bool ZTV = false, bool EPS = false, bool LS = false, bool ZS = false>
 __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThreads) loglik_thr_kernel(const ThrArgs A) {
+  static_assert(!(ZS && ZTV), "sparse-z shortcut: time-invariant Z");
+  auto z1fma = [](double x, double z, double acc) { return ZS ? acc : fma(x, z, acc); };
   static_assert(!(EPS && ZTV), "residual shortcut: time-invariant Z");
   static_assert(!(LS && ZTV), "level + slope shortcut: time-invariant Z");
   constexpr int L = NB - 1;
@@ -168,8 +174,8 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
         M[I][0] = fma(D[I][0], zi0, M[I][0]);
         continue;
       }
-      M[I][0] = fma(D[I][1], zi1, fma(D[I][0], zi0, M[I][0]));
-      M[I][1] = fma(D[I][2], zi1, fma(D[I][1], zi0, M[I][1]));
+      M[I][0] = z1fma(D[I][1], zi1, fma(D[I][0], zi0, M[I][0]));
+      M[I][1] = z1fma(D[I][2], zi1, fma(D[I][1], zi0, M[I][1]));
 #pragma unroll
       for (int J = I + 1; J < NB; J++, oi++) {
         const double zj0 = ZTV ? zr[ZTV ? J : 0][0] : A.cst[J][4], zj1 = ZTV ? zr[ZTV ? J : 0][1] : A.cst[J][5];
@@ -183,13 +189,13 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
         if (EPS && J == L) {
           M[I][0] = fma(p0, zj0, M[I][0]);
           M[I][1] = fma(p2, zj0, M[I][1]);
-          M[J][0] = fma(p2, zi1, fma(p0, zi0, M[J][0]));
+          M[J][0] = z1fma(p2, zi1, fma(p0, zi0, M[J][0]));
           continue;
         }
-        M[I][0] = fma(p1, zj1, fma(p0, zj0, M[I][0]));
-        M[I][1] = fma(p3, zj1, fma(p2, zj0, M[I][1]));
-        M[J][0] = fma(p2, zi1, fma(p0, zi0, M[J][0]));
-        M[J][1] = fma(p3, zi1, fma(p1, zi0, M[J][1]));
+        M[I][0] = z1fma(p1, zj1, fma(p0, zj0, M[I][0]));
+        M[I][1] = z1fma(p3, zj1, fma(p2, zj0, M[I][1]));
+        M[J][0] = z1fma(p2, zi1, fma(p0, zi0, M[J][0]));
+        M[J][1] = z1fma(p3, zi1, fma(p1, zi0, M[J][1]));
       }
     }
   }
@@ -246,8 +252,8 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
       if (LS && I == 0) {
         const double z0 = cv0[I * 6 + 4], z1 = cv0[I * 6 + 5];
         const double m0 = M[I][0], m1 = M[I][1], a0 = SA(2 * I), a1 = SA(2 * I + 1);
-        F = fma(z1, m1, fma(z0, m0, F));
-        za = fma(z1, a1, fma(z0, a0, za));
+        F = z1fma(m1, z1, fma(z0, m0, F));
+        za = z1fma(a1, z1, fma(z0, a0, za));
         M[I][0] = m0 + m1;
         ta[I][0] = a0 + a1;
         ta[I][1] = a1;
@@ -257,8 +263,8 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
       const double m0 = M[I][0], m1 = M[I][1], a0 = SA(2 * I), a1 = SA(2 * I + 1);
       if constexpr (!ZTV) {
         const double z0 = cv0[I * 6 + 4], z1 = cv0[I * 6 + 5];
-        F = fma(z1, m1, fma(z0, m0, F));
-        za = fma(z1, a1, fma(z0, a0, za));
+        F = z1fma(m1, z1, fma(z0, m0, F));
+        za = z1fma(a1, z1, fma(z0, a0, za));
       }
       M[I][0] = fma(t01, m1, t00 * m0);
       M[I][1] = fma(t11, m1, t10 * m0);
@@ -312,8 +318,8 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
         D[I][0] = p0;
         D[I][1] = p1;
         D[I][2] = p3;
-        M[I][0] = fma(p1, zi1, fma(p0, zi0, M[I][0]));
-        M[I][1] = fma(p3, zi1, fma(p1, zi0, M[I][1]));
+        M[I][0] = z1fma(p1, zi1, fma(p0, zi0, M[I][0]));
+        M[I][1] = z1fma(p3, zi1, fma(p1, zi0, M[I][1]));
       } else {
         double p0 = D[I][0], p1 = D[I][1], p3 = D[I][2];
         const double y00 = fma(t01, p1, t00 * p0), y01 = fma(t01, p3, t00 * p1);
@@ -327,8 +333,8 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
         D[I][0] = p0;
         D[I][1] = p1;
         D[I][2] = p3;
-        M[I][0] = fma(p1, zi1, fma(p0, zi0, M[I][0]));
-        M[I][1] = fma(p3, zi1, fma(p1, zi0, M[I][1]));
+        M[I][0] = z1fma(p1, zi1, fma(p0, zi0, M[I][0]));
+        M[I][1] = z1fma(p3, zi1, fma(p1, zi0, M[I][1]));
       }
 #pragma unroll
       for (int J = I + 1; J < NB; J++, oi++) {
@@ -355,7 +361,7 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
           }
           M[I][0] = fma(p0, zj0, M[I][0]);
           M[I][1] = fma(p2, zj0, M[I][1]);
-          M[J][0] = fma(p2, zi1, fma(p0, zi0, M[J][0]));
+          M[J][0] = z1fma(p2, zi1, fma(p0, zi0, M[J][0]));
           continue;
         }
         const double y00 = (LS && I == 0) ? p0 + p2 : fma(t01, p2, t00 * p0);
@@ -372,10 +378,10 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
           const int o = (oi - RO) * 4;
           SP(o) = p0, SP(o + 1) = p1, SP(o + 2) = p2, SP(o + 3) = p3;
         }
-        M[I][0] = fma(p1, zj1, fma(p0, zj0, M[I][0]));
-        M[I][1] = fma(p3, zj1, fma(p2, zj0, M[I][1]));
-        M[J][0] = fma(p2, zi1, fma(p0, zi0, M[J][0]));
-        M[J][1] = fma(p3, zi1, fma(p1, zi0, M[J][1]));
+        M[I][0] = z1fma(p1, zj1, fma(p0, zj0, M[I][0]));
+        M[I][1] = z1fma(p3, zj1, fma(p2, zj0, M[I][1]));
+        M[J][0] = z1fma(p2, zi1, fma(p0, zi0, M[J][0]));
+        M[J][1] = z1fma(p3, zi1, fma(p1, zi0, M[J][1]));
       }
     }
     if constexpr (ZTV) {
@@ -394,8 +400,8 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
           za = fma(A.cst[I][4], SA(2 * I), za);
           continue;
         }
-        F = fma(A.cst[I][5], M[I][1], fma(A.cst[I][4], M[I][0], F));
-        za = fma(A.cst[I][5], SA(2 * I + 1), fma(A.cst[I][4], SA(2 * I), za));
+        F = z1fma(M[I][1], A.cst[I][5], fma(A.cst[I][4], M[I][0], F));
+        za = z1fma(SA(2 * I + 1), A.cst[I][5], fma(A.cst[I][4], SA(2 * I), za));
       }
     }
     observe(ynext, F, za);
@@ -444,7 +450,8 @@ size_t thr_handoff_bytes(int nb, bool qoff, long long E) {
 }
 
 // FP64 operations (fma = 2) per series and time step: the counts of the SASS of the loop
-int thr_flops_per_step(int nb, bool qoff, bool eps, bool ls) {
+// instr: the number of FP64 instructions (fma = mul = add = 1 issue slot) instead of the operations (fma = 2)
+int thr_flops_per_step(int nb, bool qoff, bool eps, bool ls, bool zs, bool instr) {
   const int noff = nb * (nb - 1) / 2;
   // vectors: F, z'a 4 fma; tm, T a 2 mul + 2 fma each; s 2 mul; a 2 fma    (per block row)
   const int fma_v = 4 + 4 + 2, mul_v = 4 + 2;
@@ -466,28 +473,32 @@ int thr_flops_per_step(int nb, bool qoff, bool eps, bool ls) {
       mul -= 4 + (qoff ? 4 : 5) + (nb - 2) * 4 + 2;
       add += 2 + (qoff ? 6 : 5) + (nb - 2) * 2 + 1;
     }
-    return 2 * fma + mul + add;
+    // z = 0 for the second state of every block: 2 (vectors) + 2 (diagonal) fma per full block row, 4 per full block above the
+    // diagonal, 1 per 2 x 1 block
+    if (zs) fma -= (nb - 1) * 4 + (noff - (nb - 1)) * 4 + (nb - 1);
+    return (instr ? fma : 2 * fma) + mul + add;
   }
   int fma = nb * fma_v + fma_s + nb * fma_d + noff * fma_o, mul = nb * mul_v + mul_s + nb * mul_d + noff * mul_o, add = add_s;
+  if (zs) fma -= nb * 4 + noff * 4;
   if (ls) {
     fma -= 4 + (qoff ? 10 : 9) + (nb - 1) * 4;
     mul -= 4 + (qoff ? 4 : 5) + (nb - 1) * 4;
     add += 2 + (qoff ? 6 : 5) + (nb - 1) * 2;
   }
-  return 2 * fma + mul + add;
+  return (instr ? fma : 2 * fma) + mul + add;
 }
 
-template <int NB, bool QOFF, bool ZTV = false, bool EPS = false, bool LS = false>
+template <int NB, bool QOFF, bool ZTV = false, bool EPS = false, bool LS = false, bool ZS = false>
 static int launch_thr_one(const ThrArgs& A, cudaStream_t st) {
   // time-varying Z: 2 NB more vector registers hold the row of Z, so two more blocks move to shared memory (NB >= 5)
   constexpr int S = thr_smem_blocks_eps(NB, ZTV, EPS);
   constexpr BlkHandoff HL(NB, QOFF);
   const size_t smem = (size_t)((2 + HL.qw) * NB + 4 * S) * kThrThreads * sizeof(double);
   // a function attribute belongs to the device it was set on (one slot per device: api.cu)
-  SS_CUDA(cudaFuncSetAttribute(loglik_thr_kernel<NB, S, QOFF, ZTV, EPS, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SS_CUDA(cudaFuncSetAttribute(loglik_thr_kernel<NB, S, QOFF, ZTV, EPS, LS, ZS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long blocks = (A.E + kThrThreads - 1) / kThrThreads;
   SS_ARG(blocks < (1LL << 31), "thread kernel: batch too large for one launch");
-  loglik_thr_kernel<NB, S, QOFF, ZTV, EPS, LS><<<(unsigned)blocks, kThrThreads, smem, st>>>(A);
+  loglik_thr_kernel<NB, S, QOFF, ZTV, EPS, LS, ZS><<<(unsigned)blocks, kThrThreads, smem, st>>>(A);
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;
 }
@@ -501,7 +512,7 @@ bool thr_supported(int nb, int p, bool ztv) { (void)ztv; return p == 1 && nb >= 
 // eps: position 1 of the last block of the plan is the residual state (see the kernel), time-invariant Z only
 int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* zt, const double* y, long long B,
                       long long E, long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st,
-                      bool eps, bool ls) {
+                      bool eps, bool ls, bool zs) {
   ThrArgs A{};
   A.zt = zt;
   A.y = y;
@@ -518,9 +529,16 @@ int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double*
     A.cst[I][5] = z_internal[2 * I + 1];
   }
   const bool qoff = pl.q_offdiag != 0;
-  SS_ARG(!((eps || ls) && zt), "thread kernel: the residual / level + slope shortcuts need a time-invariant Z");
+  SS_ARG(!((eps || ls || zs) && zt), "thread kernel: the structural shortcuts need a time-invariant Z");
+  zs = zs && eps;  // instantiated together with the residual shortcut only (the reference's layout always has the residual)
 #define SS_THR_CASE(NBV)                                                                                                  \
   case NBV:                                                                                                               \
+    if (eps && ls && zs)                                                                                                  \
+      return qoff ? launch_thr_one<NBV, true, false, true, true, true>(A, st)                                             \
+                  : launch_thr_one<NBV, false, false, true, true, true>(A, st);                                           \
+    if (eps && zs)                                                                                                        \
+      return qoff ? launch_thr_one<NBV, true, false, true, false, true>(A, st)                                            \
+                  : launch_thr_one<NBV, false, false, true, false, true>(A, st);                                          \
     if (eps && ls)                                                                                                        \
       return qoff ? launch_thr_one<NBV, true, false, true, true>(A, st) : launch_thr_one<NBV, false, false, true, true>(A, st); \
     if (ls) return qoff ? launch_thr_one<NBV, true, false, false, true>(A, st) : launch_thr_one<NBV, false, false, false, true>(A, st); \

@@ -1559,8 +1559,8 @@ for N in (61, 5):
 def test_thread_kernel_shortcuts_against_the_generic_instantiation():
     """The thread kernel's two structural shortcuts against its generic instantiation in subprocesses (the switches are
     read once per process): SSGPU_THR_LS=0 -- the level + slope block by sums is bit for bit the generic product
-    (1 * x is exact) -- and SSGPU_THR_EPS=0 -- dropping the residual state changes only the order of a few sums
-    (1e-12)."""
+    (1 * x is exact) --, SSGPU_THR_ZS=0 -- so is leaving out the multiply-adds with z = 0 -- and SSGPU_THR_EPS=0 --
+    dropping the residual state changes only the order of a few sums (1e-12)."""
     import subprocess
     import sys
     import tempfile
@@ -1578,13 +1578,16 @@ np.save(sys.argv[1] + ".npy", got)
 ''' % (ROOT_DIR, ROOT_DIR)
     with tempfile.TemporaryDirectory() as d:
         outs, names = {}, {}
-        for tag, env in (("both", {}), ("no_ls", {"SSGPU_THR_LS": "0"}), ("no_eps", {"SSGPU_THR_EPS": "0", "SSGPU_THR_LS": "0"})):
+        for tag, env in (("both", {}), ("no_ls", {"SSGPU_THR_LS": "0"}), ("no_zs", {"SSGPU_THR_ZS": "0"}),
+                         ("no_eps", {"SSGPU_THR_EPS": "0", "SSGPU_THR_LS": "0"})):
             r = subprocess.run([sys.executable, "-c", code, os.path.join(d, tag)], env={**os.environ, **env},
                                capture_output=True, text=True, timeout=600)
             assert r.returncode == 0, r.stderr[-2000:]
             outs[tag] = np.load(os.path.join(d, tag + ".npy"))
             names[tag] = open(os.path.join(d, tag + ".txt")).read()
-        assert "residual state dropped, level + slope block by sums" in names["both"], names
+        assert "residual state dropped, level + slope block by sums" in names["both"] and "zero z skipped" in names["both"], names
+        assert "zero z skipped" not in names["no_zs"] and "level + slope" in names["no_zs"], names
+        assert np.array_equal(outs["both"], outs["no_zs"])                 # fma(x, 0, acc) == acc
         assert "residual state dropped" in names["no_ls"] and "level + slope" not in names["no_ls"], names
         assert "dropped" not in names["no_eps"] and "level + slope" not in names["no_eps"], names
         assert np.all(np.isfinite(outs["both"]))
