@@ -284,7 +284,7 @@ int launch_fd_gradient(const double* out, long long B, int k, double h, double* 
 // Block-row DFMA kernel for transition matrices that are block diagonal with blocks of at most 2 x 2 (loglik_blk.cu)
 struct HostShared {  // optional host copies of the shared, time-invariant matrices (null = fetch from the device)
   const double *T, *R, *Z, *Q;
-  const double *a = nullptr, *P_star = nullptr;  // in the storage of the device copy (P_star: dense m x m)
+  const double *a = nullptr, *P_star = nullptr, *P_inf = nullptr;  // in the storage of the device copy (diag or dense)
 };
 struct BlkPlan {
   int nb;                // number of 2 x 2 blocks (a lone state is padded with an empty partner)
@@ -307,13 +307,23 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
 
 // Thread-per-evaluation kernel for the regular phase of the same model class (loglik_thr.cu); the lane kernel
 // above runs the diffuse phase first and hands the state over (blk_handoff.cuh)
+// The diffuse steps of evaluations without a missing value in the diffuse window share P_inf, F_inf and K0 (they depend
+// on Z, T and P_inf only): per-step constants computed on the host (loglik_blk.cu, launcher), passed by value
+constexpr int kThrMaxDu = 16;
+struct ThrDiffuse {
+  int du;                      // diffuse steps (0 = none)
+  int esumF;                   // prod of F_inf over the steps = prodF * 2^esumF, prodF in [1, 2)
+  double prodF;
+  double F1[kThrMaxDu];        // 1 / F_inf of step t
+  double u[kThrMaxDu][16];     // T M_inf of step t, internal order of the block plan
+};
 bool thr_supported(int nb, int p, bool ztv);
 size_t thr_handoff_bytes(int nb, bool qoff, long long E);
 int thr_flops_per_step(int nb, bool qoff, bool eps = false, bool ls = false, bool zs = false, bool instr = false);
 int thr_smem_blocks_host(int nb, bool ztv, bool eps = false);
 int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* zt, const double* y, long long B,
                       long long E, long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st,
-                      bool eps = false, bool ls = false, bool zs = false);
+                      bool eps = false, bool ls = false, bool zs = false, const ThrDiffuse* ud = nullptr);
 
 // Thread-per-series kernel on the component states alone, the p residual states of the reference's layout eliminated
 // (loglik_core.cu): m - p <= 8, p <= 16, everything shared and time-invariant, diagonal H

@@ -60,6 +60,8 @@ struct BlkArgs {
   double Tb[kBlkMaxNB][4];             // T_J[row][col] at [2*row + col], internal order
   double z[kBlkMaxP][2 * kBlkMaxNB];   // row j of Z, internal order
   const double* zt;                    // time-varying Z (p = 1): [t][2 * kBlkMaxNB] in internal order, device memory
+  int du;                              // hand-over only: an evaluation without a missing value among its first du observations
+                                       // is handed over as it stands at t = 0, marked -1 (the thread kernel runs its diffuse steps)
 };
 
 __device__ __forceinline__ double blk_rcp(double x) {
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
   const long long w0 = ((long long)blockIdx.x * (BT / 32) + warp) * G;
   if (w0 >= A.E) return;  // whole warp
   // every lane stays alive (shuffles): groups beyond the last evaluation shadow it and do not store
-  const bool live = w0 + g < A.E;
+  bool live = w0 + g < A.E;
   const long long w_id = live ? w0 + g : A.E - 1;
   const long long V = A.E / A.B, b = w_id / V, v = w_id % V;
   const long long e_id = v * A.ldy + b;
@@ -453,15 +455,70 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
     }
   };
 
+  // ---- hand-over (HO): the state at the start of time point `tmark` goes to the record of blk_handoff.cuh
+  auto hand_over = [&](int tmark) {
+    constexpr BlkHandoff HL(NB, QOFF);
+    if (live && own) {
+      double* const hd = A.hd + w_id;
+      const long long E = A.E;
+      hd[(HL.a() + 2 * I) * E] = a0;
+      hd[(HL.a() + 2 * I + 1) * E] = a1;
+      hd[(HL.q() + HL.qw * I) * E] = q0;
+      if constexpr (QOFF) hd[(HL.q() + HL.qw * I + 1) * E] = q1;
+      hd[(HL.q() + HL.qw * I + HL.qw - 1) * E] = q3;
+      hd[(HL.d() + 3 * I) * E] = P[0][0];
+      hd[(HL.d() + 3 * I + 1) * E] = P[0][1];
+      hd[(HL.d() + 3 * I + 2) * E] = P[0][3];
+#pragma unroll
+      for (int k = 1; k < K; k++) {
+        if (!keep[k]) continue;
+        const int J = Jk[k];
+        const bool up = J > I;  // held as (I, J): as is; as (I, J) with J < I: the transpose of block (J, I)
+        const int oi = up ? HL.off_index(I, J) : HL.off_index(J, I);
+        double* const ho = hd + (long long)(HL.o() + 4 * oi) * E;
+        ho[0] = P[k][0];
+        ho[E] = up ? P[k][1] : P[k][2];
+        ho[2 * E] = up ? P[k][2] : P[k][1];
+        ho[3 * E] = P[k][3];
+      }
+      if (I == 0) {
+        hd[HL.s() * E] = prod;
+        hd[(HL.s() + 1) * E] = sumq;
+        int* const hi = A.hi + w_id;
+        hi[0] = tmark;
+        hi[E] = esum;
+        hi[2 * E] = n_terms;
+        hi[3 * E] = non_init;
+        hi[4 * E] = F_eq0;
+      }
+    }
+  };
+
   const long long Np = (long long)N * p;
   int t = 0;
+  // The diffuse steps of an evaluation that has no missing value among its first du observations are the same for all
+  // such evaluations up to P_star (P_inf, F_inf and the gains do not depend on the data or the variances): it is handed
+  // over as it stands, marked -1, and the thread kernel runs those steps with P_inf's share as constants
+  // (loglik_thr.cu).  The group then idles through the loop below if another group of its warp needs it.
+  bool handed = false;
+  if constexpr (HO) {
+    if (A.du > 0) {
+      bool clean = true;
+      for (int tt = I; tt < A.du; tt += L) clean = clean && !isnan(A.y[(long long)tt * A.ldy + b]);
+      handed = group_all(clean);
+      if (handed) {
+        hand_over(-1);
+        live = false;
+      }
+    }
+  }
   {
     // ---- exact diffuse phase (src/LogLikC.cpp:98-159), select-based: the groups of a warp may leave it at
     // different time points (missing observations), so every group runs this loop until the last one is done ----
     bool small = true;
 #pragma unroll
     for (int e = 0; e < K * 4; e++) small = small && (fabs(PINF(e)) < kEps);
-    bool init = !group_all(small);  // :49
+    bool init = !group_all(small) && !handed;  // :49
     while (t < N && __any_sync(FULL, init)) {
       for (int j = 0; j < p; j++) {
         const double yv = YTMA ? y_get(t) : A.y[((long long)t * p + j) * A.ldy + b];
@@ -547,44 +604,9 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
   }
 
   if constexpr (HO) {
-    // ---- hand-over: every group of the warp is through the diffuse phase (or at t == N).  The state at the start of
-    // time point t goes to the record of blk_handoff.cuh; an evaluation that is already complete (t == N) writes its
-    // result below as usual and the thread kernel skips it.
-    constexpr BlkHandoff HL(NB, QOFF);
-    if (live && own) {
-      double* const hd = A.hd + w_id;
-      const long long E = A.E;
-      hd[(HL.a() + 2 * I) * E] = a0;
-      hd[(HL.a() + 2 * I + 1) * E] = a1;
-      hd[(HL.q() + HL.qw * I) * E] = q0;
-      if constexpr (QOFF) hd[(HL.q() + HL.qw * I + 1) * E] = q1;
-      hd[(HL.q() + HL.qw * I + HL.qw - 1) * E] = q3;
-      hd[(HL.d() + 3 * I) * E] = P[0][0];
-      hd[(HL.d() + 3 * I + 1) * E] = P[0][1];
-      hd[(HL.d() + 3 * I + 2) * E] = P[0][3];
-#pragma unroll
-      for (int k = 1; k < K; k++) {
-        if (!keep[k]) continue;
-        const int J = Jk[k];
-        const bool up = J > I;  // held as (I, J): as is; as (I, J) with J < I: the transpose of block (J, I)
-        const int oi = up ? HL.off_index(I, J) : HL.off_index(J, I);
-        double* const ho = hd + (long long)(HL.o() + 4 * oi) * E;
-        ho[0] = P[k][0];
-        ho[E] = up ? P[k][1] : P[k][2];
-        ho[2 * E] = up ? P[k][2] : P[k][1];
-        ho[3 * E] = P[k][3];
-      }
-      if (I == 0) {
-        hd[HL.s() * E] = prod;
-        hd[(HL.s() + 1) * E] = sumq;
-        int* const hi = A.hi + w_id;
-        hi[0] = t;
-        hi[E] = esum;
-        hi[2 * E] = n_terms;
-        hi[3 * E] = non_init;
-        hi[4 * E] = F_eq0;
-      }
-    }
+    // every group of the warp is through the diffuse phase (or at t == N).  An evaluation that is already complete
+    // (t == N) writes its result below as usual and the thread kernel skips it.
+    hand_over(t);
     if (t < N) return;
   }
 
@@ -919,7 +941,7 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     SS_TRY(fetch(Qh, hs ? hs->Q : nullptr, md.Q.p));
   }
   // what the thread kernel's residual shortcut looks at (p = 1, time-invariant Z): a, and a dense P_star, when shared
-  std::vector<double> ah, Psh;
+  std::vector<double> ah, Psh, Pih;
   if (p == 1 && nZ == 1) {
     if (md.a.shared()) {
       ah.resize((size_t)m);
@@ -928,6 +950,10 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     if (md.P_star.shared() && !md.P_star.diag) {
       Psh.resize((size_t)m * m);
       SS_TRY(fetch(Psh, hs ? hs->P_star : nullptr, md.P_star.p));
+    }
+    if (md.P_inf.shared()) {
+      Pih.resize((size_t)(md.P_inf.diag ? m : m * m));
+      SS_TRY(fetch(Pih, hs ? hs->P_inf : nullptr, md.P_inf.p));
     }
   }
   if (need_sync) SS_CUDA(cudaStreamSynchronize(st));
@@ -1036,6 +1062,74 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     }
     pl.zs = all ? 1 : 0;
   }
+  // Shared diffuse steps (loglik_thr.cu): P_inf, F_inf and the diffuse gains depend on neither the data nor the
+  // variances, so for an evaluation without a missing value in the diffuse window they are constants of the model.  The
+  // recursion of P_inf alone (src/LogLikC.cpp:101,105,136,143-144,152,204-205) runs here on the host: step t gives
+  // u_t = T M_inf and 1 / F_inf; it ends when P_inf has vanished (du steps), and is given up when some F_inf < 1e-7.
+  static const bool uni_on = [] {
+    const char* e = getenv("SSGPU_THR_SHARED_DIFFUSE");
+    return !(e && e[0] == '0');
+  }();
+  ThrDiffuse ud{};
+  if (uni_on && p == 1 && nZ == 1 && !Pih.empty() && pl.nb >= 2 && pl.nb <= kBlkMaxNB / 2) {
+    std::vector<double> Pi((size_t)m * m), Mi((size_t)m), X((size_t)m * m);
+    for (int i = 0; i < m; i++)
+      for (int k = 0; k < m; k++) Pi[i + (size_t)k * m] = mat_get(Pih.data(), md.P_inf.diag, m, i, k);
+    auto small = [&]() {
+      for (double x : Pi)
+        if (!(std::fabs(x) < kEps)) return false;
+      return true;
+    };
+    bool init = !small(), okd = true;
+    int du = 0;
+    double prodF = 1.0;
+    int esumF = 0;
+    while (init && okd && du < kThrMaxDu && du < md.N - 1) {
+      double Fi = 0.0;
+      for (int i = 0; i < m; i++) {
+        double acc = 0.0;
+        for (int k = 0; k < m; k++) acc += Pi[i + (size_t)k * m] * Zh[k];
+        Mi[i] = acc;
+      }
+      for (int i = 0; i < m; i++) Fi += Zh[i] * Mi[i];
+      if (Fi < kEps) {
+        okd = false;
+        break;
+      }
+      const double F1 = 1.0 / Fi;
+      ud.F1[du] = F1;
+      int ex;
+      prodF = std::frexp(prodF * Fi, &ex) * 2.0;  // mantissa in [1, 2)
+      esumF += ex - 1;
+      for (int i = 0; i < 2 * pl.nb; i++) {  // u = T M_inf, internal order
+        double acc = 0.0;
+        if (pl.perm[i] >= 0)
+          for (int k = 0; k < m; k++) acc += mat_get(Th.data(), md.T.diag, m, pl.perm[i], k) * Mi[k];
+        ud.u[du][i] = acc;
+      }
+      for (int i = 0; i < m; i++)
+        for (int k = 0; k < m; k++) Pi[i + (size_t)k * m] -= Mi[i] * Mi[k] * F1;
+      for (int i = 0; i < m; i++)  // X = T P_inf
+        for (int k = 0; k < m; k++) {
+          double acc = 0.0;
+          for (int l = 0; l < m; l++) acc += mat_get(Th.data(), md.T.diag, m, i, l) * Pi[l + (size_t)k * m];
+          X[i + (size_t)k * m] = acc;
+        }
+      for (int i = 0; i < m; i++)  // P_inf = X T'
+        for (int k = 0; k < m; k++) {
+          double acc = 0.0;
+          for (int l = 0; l < m; l++) acc += X[i + (size_t)l * m] * mat_get(Th.data(), md.T.diag, m, k, l);
+          Pi[i + (size_t)k * m] = acc;
+        }
+      du++;
+      init = !small();
+    }
+    if (okd && !init && du > 0) {
+      ud.du = du;
+      ud.prodF = prodF;
+      ud.esumF = esumF;
+    }
+  }
   BlkArgs A{};
   A.md = md;
   A.y = y;
@@ -1093,7 +1187,7 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     count_launch();
     return SSGPU_OK;
   };
-  static thread_local char name[288];
+  static thread_local char name[320];
   // SSGPU_BLK_THREAD=0: the lane kernel alone (experiments, A/B runs)
   static const bool thr_on = [] {
     const char* e = getenv("SSGPU_BLK_THREAD");
@@ -1128,8 +1222,9 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
       Ac.E = Ec;
       Ac.hd = scratch.as<double>();
       Ac.hi = reinterpret_cast<int*>(Ac.hd + (size_t)hl.doubles() * Ec);
+      Ac.du = ud.du;
       SS_TRY(launch_lanes(Ac));
-      SS_TRY(launch_loglik_thr(pl, &A.z[0][0], A.zt, Ac.y, Bc, Ec, B, md.N, Ac.hd, Ac.hi, Ac.out, st, pl.eps != 0, pl.ls != 0, pl.zs != 0));
+      SS_TRY(launch_loglik_thr(pl, &A.z[0][0], A.zt, Ac.y, Bc, Ec, B, md.N, Ac.hd, Ac.hi, Ac.out, st, pl.eps != 0, pl.ls != 0, pl.zs != 0, &ud));
       count_launch();
     }
     snprintf(name, sizeof name,
@@ -1143,6 +1238,10 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     if (pl.zs) {
       const size_t len = strlen(name);
       snprintf(name + len, sizeof name - len, ", zero z skipped");
+    }
+    if (ud.du > 0) {
+      const size_t len = strlen(name);
+      snprintf(name + len, sizeof name - len, ", %d shared diffuse steps", ud.du);
     }
     set_last_kernel(name);
     return SSGPU_OK;

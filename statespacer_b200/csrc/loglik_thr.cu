@@ -51,6 +51,7 @@ struct ThrArgs {
   double* out;  // [v * ldy + b]
   double cst[kThrMaxNB][6];  // T_I row-major (4), z_I (2): internal order of the block plan
   const double* zt;          // time-varying Z (explanatory variables): [t][32] in internal order, device memory; else null
+  ThrDiffuse ud;             // the shared diffuse steps of evaluations handed over at t = 0 (marked -1); du = 0: none
 };
 
 __device__ __forceinline__ double thr_rsqrt(double x) {
@@ -118,6 +119,10 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
   int t = A.hi[w];
   const int N = A.N;
   if (t >= N) return;  // finished by the lane kernel
+  // handed over as it stood at t = 0: no missing value among its first du observations, so its diffuse steps are the
+  // shared ones (below)
+  const bool pro = t < 0;
+  if (pro) t = 0;
   const long long V = E / A.B, b = w / V, v = w % V;
   extern __shared__ double thr_sm[];  // [slot][thread]: a (2 NB), R Q R' (QW NB), S blocks (4 each)
   double* const smt = thr_sm + threadIdx.x;
@@ -231,46 +236,52 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
       zac = fma(zr[ZTV ? I : 0][1], SA(2 * I + 1), fma(zr[ZTV ? I : 0][0], SA(2 * I), zac));
     }
   }
+  // ---- shared diffuse steps (src/LogLikC.cpp:136-153,200-205).  P_inf, F_inf and K0 = M_inf / F_inf depend on Z, T and
+  // P_inf only: for an evaluation without a missing value in the diffuse window they are constants of the model, computed
+  // on the host (loglik_blk.cu) -- u_t = T M_inf and F1_t = 1 / F_inf per step.  What is left per evaluation is P_star:
+  //     F* = z'M*,  F2 = -F1^2 F*,  v = y - z'a,  w = T M*,  g = F1 w + (F2 / 2) u,
+  //     P* <- T P* T' + R Q R' - u g' - g u'     [= T (P* - F1 (M_inf M*' + M* M_inf') - F2 M_inf M_inf') T' + R Q R'],
+  //     a  <- T a + u F1 v,                       loglik term: -log(F_inf) / 2, a constant of the model.
+  // The same sweep as the regular phase with a rank-2 correction; the residual / level + slope / zero-z shortcuts hold
+  // here as well (u and g vanish in the residual's row like s does).
+  int n_dif = 0;
+  if constexpr (!ZTV) {
+    if (pro) {
+      const int du = A.ud.du;  // < N
+      for (; t < du; t++) {
+        const double yv = ynext;
+        yp += A.ldy;
+        ynext = *yp;
+#include "loglik_thr_vectors.inc"
+        const double* const ut = &A.ud.u[0][0] + t * 16 + thr_opaque0();
+        const double F1 = (&A.ud.F1[0] + thr_opaque0())[t], hF2 = -0.5 * (F1 * F1) * F, gv = F1 * (yv - za);
+        double g[NB][2], uu[NB][2];
+#pragma unroll
+        for (int I = 0; I < NB; I++) {
+          uu[I][0] = ut[2 * I];
+          g[I][0] = fma(F1, M[I][0], hF2 * uu[I][0]);
+          SA(2 * I) = fma(uu[I][0], gv, ta[I][0]);
+          M[I][0] = 0.0;
+          if (EPS && I == L) continue;
+          uu[I][1] = ut[2 * I + 1];
+          g[I][1] = fma(F1, M[I][1], hF2 * uu[I][1]);
+          SA(2 * I + 1) = fma(uu[I][1], gv, ta[I][1]);
+          M[I][1] = 0.0;
+        }
+#define THR_RK(I, a, J, b, x) fma(-g[I][a], uu[J][b], fma(-uu[I][a], g[J][b], (x)))
+#include "loglik_thr_sweep.inc"
+#undef THR_RK
+      }
+      n_dif = du;
+      esum += A.ud.esumF;
+      prod *= A.ud.prodF;
+    }
+  }
   for (; t < N - 1; t++) {
     const double yv = ynext;
     yp += A.ldy;
     ynext = *yp;
-    // ---- the vectors: tm = T M (in place), F = z'M, z'a, T a
-    double F = EPS ? heps : Fc, za = zac, ta[NB][2];
-    heps = hq;
-    const double* const cv0 = &A.cst[0][0] + thr_opaque0();
-#pragma unroll
-    for (int I = 0; I < NB; I++) {
-      if (EPS && I == L) {
-        const double t00 = cv0[I * 6], z0 = cv0[I * 6 + 4], m0 = M[I][0], a0 = SA(2 * I);
-        F = fma(z0, m0, F);
-        za = fma(z0, a0, za);
-        M[I][0] = t00 * m0;
-        ta[I][0] = t00 * a0;
-        continue;
-      }
-      if (LS && I == 0) {
-        const double z0 = cv0[I * 6 + 4], z1 = cv0[I * 6 + 5];
-        const double m0 = M[I][0], m1 = M[I][1], a0 = SA(2 * I), a1 = SA(2 * I + 1);
-        F = z1fma(m1, z1, fma(z0, m0, F));
-        za = z1fma(a1, z1, fma(z0, a0, za));
-        M[I][0] = m0 + m1;
-        ta[I][0] = a0 + a1;
-        ta[I][1] = a1;
-        continue;
-      }
-      const double t00 = cv0[I * 6], t01 = cv0[I * 6 + 1], t10 = cv0[I * 6 + 2], t11 = cv0[I * 6 + 3];
-      const double m0 = M[I][0], m1 = M[I][1], a0 = SA(2 * I), a1 = SA(2 * I + 1);
-      if constexpr (!ZTV) {
-        const double z0 = cv0[I * 6 + 4], z1 = cv0[I * 6 + 5];
-        F = z1fma(m1, z1, fma(z0, m0, F));
-        za = z1fma(a1, z1, fma(z0, a0, za));
-      }
-      M[I][0] = fma(t01, m1, t00 * m0);
-      M[I][1] = fma(t11, m1, t10 * m0);
-      ta[I][0] = fma(t01, a1, t00 * a0);
-      ta[I][1] = fma(t11, a1, t10 * a0);
-    }
+#include "loglik_thr_vectors.inc"
     observe(yv, F, za);
     load_z(t + 1);  // ZTV: the row the sweep below accumulates the next M with
     zac = 0.0;
@@ -292,98 +303,9 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
       M[I][0] = 0.0;
       M[I][1] = 0.0;
     }
-    // ---- one sweep over the blocks on and above the diagonal
-    int oi = 0;
-#pragma unroll
-    for (int I = 0; I < NB; I++) {
-      const double* const ci = &A.cst[0][0] + thr_opaque0();
-      const double t00 = ci[I * 6], t01 = ci[I * 6 + 1], t10 = ci[I * 6 + 2], t11 = ci[I * 6 + 3];
-      const double zi0 = ZTV ? zr[ZTV ? I : 0][0] : ci[I * 6 + 4], zi1 = ZTV ? zr[ZTV ? I : 0][1] : ci[I * 6 + 5];
-      if (EPS && I == L) {
-        double p0 = D[I][0];
-        const double y00 = t00 * p0;
-        p0 = fma(y00, t00, SQ(QW * I));
-        p0 = fma(-s[I][0], s[I][0], p0);
-        D[I][0] = p0;
-        M[I][0] = fma(p0, zi0, M[I][0]);
-      } else if (LS && I == 0) {
-        double p0 = D[I][0], p1 = D[I][1], p3 = D[I][2];
-        const double y00 = p0 + p1, y01 = p1 + p3;  // T_0 P_00 = [[p0 + p1, p1 + p3], [p1, p3]]
-        p0 = y01 + (y00 + SQ(QW * I));  // the association of the generic block's fma chain: same bits
-        p1 = QOFF ? y01 + SQ(QW * I + 1) : y01;
-        p3 = p3 + SQ(QW * I + QW - 1);
-        p0 = fma(-s[I][0], s[I][0], p0);
-        p1 = fma(-s[I][0], s[I][1], p1);
-        p3 = fma(-s[I][1], s[I][1], p3);
-        D[I][0] = p0;
-        D[I][1] = p1;
-        D[I][2] = p3;
-        M[I][0] = z1fma(p1, zi1, fma(p0, zi0, M[I][0]));
-        M[I][1] = z1fma(p3, zi1, fma(p1, zi0, M[I][1]));
-      } else {
-        double p0 = D[I][0], p1 = D[I][1], p3 = D[I][2];
-        const double y00 = fma(t01, p1, t00 * p0), y01 = fma(t01, p3, t00 * p1);
-        const double y10 = fma(t11, p1, t10 * p0), y11 = fma(t11, p3, t10 * p1);
-        p0 = fma(y01, t01, fma(y00, t00, SQ(QW * I)));
-        p1 = QOFF ? fma(y01, t11, fma(y00, t10, SQ(QW * I + 1))) : fma(y01, t11, y00 * t10);
-        p3 = fma(y11, t11, fma(y10, t10, SQ(QW * I + QW - 1)));
-        p0 = fma(-s[I][0], s[I][0], p0);
-        p1 = fma(-s[I][0], s[I][1], p1);
-        p3 = fma(-s[I][1], s[I][1], p3);
-        D[I][0] = p0;
-        D[I][1] = p1;
-        D[I][2] = p3;
-        M[I][0] = z1fma(p1, zi1, fma(p0, zi0, M[I][0]));
-        M[I][1] = z1fma(p3, zi1, fma(p1, zi0, M[I][1]));
-      }
-#pragma unroll
-      for (int J = I + 1; J < NB; J++, oi++) {
-        const double* const cj = &A.cst[0][0] + thr_opaque0();
-        const double u00 = cj[J * 6], u01 = cj[J * 6 + 1], u10 = cj[J * 6 + 2], u11 = cj[J * 6 + 3];
-        const double zj0 = ZTV ? zr[ZTV ? J : 0][0] : cj[J * 6 + 4], zj1 = ZTV ? zr[ZTV ? J : 0][1] : cj[J * 6 + 5];
-        double p0, p1, p2, p3;
-        if (oi < RO) {
-          p0 = O[oi < RO ? oi : 0][0], p1 = O[oi < RO ? oi : 0][1], p2 = O[oi < RO ? oi : 0][2], p3 = O[oi < RO ? oi : 0][3];
-        } else {
-          const int o = (oi - RO) * 4;
-          p0 = SP(o), p1 = SP(o + 1), p2 = SP(o + 2), p3 = SP(o + 3);
-        }
-        if (EPS && J == L) {
-          const double y00 = (LS && I == 0) ? p0 + p2 : fma(t01, p2, t00 * p0);
-          const double y10 = (LS && I == 0) ? p2 : fma(t11, p2, t10 * p0);
-          p0 = fma(-s[I][0], s[J][0], y00 * u00);
-          p2 = fma(-s[I][1], s[J][0], y10 * u00);
-          if (oi < RO) {
-            O[oi < RO ? oi : 0][0] = p0, O[oi < RO ? oi : 0][2] = p2;
-          } else {
-            const int o = (oi - RO) * 4;
-            SP(o) = p0, SP(o + 2) = p2;
-          }
-          M[I][0] = fma(p0, zj0, M[I][0]);
-          M[I][1] = fma(p2, zj0, M[I][1]);
-          M[J][0] = z1fma(p2, zi1, fma(p0, zi0, M[J][0]));
-          continue;
-        }
-        const double y00 = (LS && I == 0) ? p0 + p2 : fma(t01, p2, t00 * p0);
-        const double y01 = (LS && I == 0) ? p1 + p3 : fma(t01, p3, t00 * p1);
-        const double y10 = (LS && I == 0) ? p2 : fma(t11, p2, t10 * p0);
-        const double y11 = (LS && I == 0) ? p3 : fma(t11, p3, t10 * p1);
-        p0 = fma(-s[I][0], s[J][0], fma(y01, u01, y00 * u00));
-        p1 = fma(-s[I][0], s[J][1], fma(y01, u11, y00 * u10));
-        p2 = fma(-s[I][1], s[J][0], fma(y11, u01, y10 * u00));
-        p3 = fma(-s[I][1], s[J][1], fma(y11, u11, y10 * u10));
-        if (oi < RO) {
-          O[oi < RO ? oi : 0][0] = p0, O[oi < RO ? oi : 0][1] = p1, O[oi < RO ? oi : 0][2] = p2, O[oi < RO ? oi : 0][3] = p3;
-        } else {
-          const int o = (oi - RO) * 4;
-          SP(o) = p0, SP(o + 1) = p1, SP(o + 2) = p2, SP(o + 3) = p3;
-        }
-        M[I][0] = z1fma(p1, zj1, fma(p0, zj0, M[I][0]));
-        M[I][1] = z1fma(p3, zj1, fma(p2, zj0, M[I][1]));
-        M[J][0] = z1fma(p2, zi1, fma(p0, zi0, M[J][0]));
-        M[J][1] = z1fma(p3, zi1, fma(p1, zi0, M[J][1]));
-      }
-    }
+#define THR_RK(I, a, J, b, x) fma(-s[I][a], s[J][b], (x))
+#include "loglik_thr_sweep.inc"
+#undef THR_RK
     if constexpr (ZTV) {
       Fc = 0.0;
 #pragma unroll
@@ -406,7 +328,7 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
     }
     observe(ynext, F, za);
   }
-  const int n_terms = A.hi[2 * E + w] + n_upd, non_init = A.hi[3 * E + w] + n_obs, F_eq0 = A.hi[4 * E + w] + (n_obs - n_upd);
+  const int n_terms = A.hi[2 * E + w] + n_upd + n_dif, non_init = A.hi[3 * E + w] + n_obs, F_eq0 = A.hi[4 * E + w] + (n_obs - n_upd);
   double res;
   if (non_init == F_eq0) {
     res = nan("");  // src/LogLikC.cpp:211-213
@@ -512,8 +434,9 @@ bool thr_supported(int nb, int p, bool ztv) { (void)ztv; return p == 1 && nb >= 
 // eps: position 1 of the last block of the plan is the residual state (see the kernel), time-invariant Z only
 int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* zt, const double* y, long long B,
                       long long E, long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st,
-                      bool eps, bool ls, bool zs) {
+                      bool eps, bool ls, bool zs, const ThrDiffuse* ud) {
   ThrArgs A{};
+  if (ud) A.ud = *ud;
   A.zt = zt;
   A.y = y;
   A.B = B;

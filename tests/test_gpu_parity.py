@@ -1560,7 +1560,8 @@ def test_thread_kernel_shortcuts_against_the_generic_instantiation():
     """The thread kernel's two structural shortcuts against its generic instantiation in subprocesses (the switches are
     read once per process): SSGPU_THR_LS=0 -- the level + slope block by sums is bit for bit the generic product
     (1 * x is exact) --, SSGPU_THR_ZS=0 -- so is leaving out the multiply-adds with z = 0 -- and SSGPU_THR_EPS=0 --
-    dropping the residual state changes only the order of a few sums (1e-12)."""
+    dropping the residual state changes only the order of a few sums (1e-12); SSGPU_THR_SHARED_DIFFUSE=0 -- every
+    evaluation's diffuse phase on the lanes instead of the shared diffuse steps in the thread kernel (1e-11)."""
     import subprocess
     import sys
     import tempfile
@@ -1579,6 +1580,7 @@ np.save(sys.argv[1] + ".npy", got)
     with tempfile.TemporaryDirectory() as d:
         outs, names = {}, {}
         for tag, env in (("both", {}), ("no_ls", {"SSGPU_THR_LS": "0"}), ("no_zs", {"SSGPU_THR_ZS": "0"}),
+                         ("no_shared", {"SSGPU_THR_SHARED_DIFFUSE": "0"}),
                          ("no_eps", {"SSGPU_THR_EPS": "0", "SSGPU_THR_LS": "0"})):
             r = subprocess.run([sys.executable, "-c", code, os.path.join(d, tag)], env={**os.environ, **env},
                                capture_output=True, text=True, timeout=600)
@@ -1591,6 +1593,10 @@ np.save(sys.argv[1] + ".npy", got)
         assert "residual state dropped" in names["no_ls"] and "level + slope" not in names["no_ls"], names
         assert "dropped" not in names["no_eps"] and "level + slope" not in names["no_eps"], names
         assert np.all(np.isfinite(outs["both"]))
+        # about half of the 96 series have no missing value among their first 13 observations: their diffuse steps run in
+        # the thread kernel with P_inf's share as constants, the others' on the lanes
+        assert "13 shared diffuse steps" in names["both"] and "shared diffuse" not in names["no_shared"], names
+        assert np.allclose(outs["both"], outs["no_shared"], rtol=1e-11, atol=0)
         assert np.array_equal(outs["both"], outs["no_ls"])
         assert np.allclose(outs["both"], outs["no_eps"], rtol=1e-12, atol=0)
 
