@@ -22,3 +22,11 @@ for i in range(3):
     t0 = time.perf_counter(); call(); print("call %.1f ms" % (1e3 * (time.perf_counter() - t0)))
 yd = torch.empty_like(y)
 torch.cuda.synchronize(); t0 = time.perf_counter(); yd.copy_(y_h, non_blocking=True); torch.cuda.synchronize(); print("plain H2D of y %.1f ms" % (1e3 * (time.perf_counter() - t0)))
+# the same call on pageable host arrays (what R passes): staged through the library's ring of pinned buffers
+y_p = y.cpu().numpy().copy(); th_p = theta.cpu().numpy().copy(); ll_p = np.empty(B); gr_p = np.empty((B, 4))
+def call_p():
+    native.check(native.lib().ssgpu_loglik_grad_batch(y_p.ctypes.data, B, C.byref(hm.c), th_p.ctypes.data, 4, qi.ctypes.data, pi.ctypes.data, 1e-3, 0, ll_p.ctypes.data, gr_p.ctypes.data))
+for i in range(2): call_p()
+for i in range(3):
+    t0 = time.perf_counter(); call_p(); print("pageable call %.1f ms" % (1e3 * (time.perf_counter() - t0)))
+print("pageable == pinned:", np.array_equal(ll_p, ll_h.numpy()))

@@ -990,7 +990,7 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
   // column block of the time-major array: one strided 2-D copy on a second stream; the kernels of chunk c wait for
   // its event only).  1 GB of y at config 5 otherwise sits in front of the first launch for 18 ms of the call.
   const bool pinned = host_is_pinned(y);
-  const int nch = B >= 16384 ? 8 : 1;
+  const int nch = B >= 16384 ? 10 : 1;
   if (getenv("SSGPU_TRACE"))
     fprintf(stderr, "ssgpu_loglik_grad_batch: slot=%d B=%lld of %lld pinned=%d chunks=%d\n", dev_slot(), B, ldy, (int)pinned, nch);
   if (nch == 1) {
@@ -1013,14 +1013,19 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
     SS_CUDA(cudaMemcpyAsync(thd.get(), theta, (size_t)B * k * sizeof(double), cudaMemcpyHostToDevice, st));
     SS_TRY(theta_setup(model, false, B, V, k, thd.as<double>(), q_index, p_star_index, h, 1, W, st));
     SS_TRY(W.out.alloc((size_t)B * V * sizeof(double), st));
-    // chunk sizes 1/16, 1/16, 1/8, 1/4, 1/2 of the batch: the first kernels start after 1/16 of the upload, every later
-    // upload is shorter than the kernels it hides behind, and most of the work runs in large launches (few partial waves)
-    long long cb[9] = {0};  // chunk c covers the series [cb[c], cb[c + 1])
+    // Pinned y: chunk sizes 1/16, 1/16, 1/8, 1/4, 1/2 of the batch -- the first kernels start after 1/16 of the upload,
+    // every later upload (55 GB/s) is shorter than the kernels it hides behind, and most of the work runs in large launches
+    // (few partial waves).  Pageable y: the staged upload runs at about the speed of the kernels (1 GB in ~38 ms against
+    // 43 ms at config 5), so the call ends one chunk's kernels after the last chunk has landed: 1/16, 1/16 and seven
+    // chunks of 1/8 (60.7 -> 56.0 ms per call; with a ring of 4 instead of 8 staging buffers 70.3).
+    long long cb[11] = {0};  // chunk c covers the series [cb[c], cb[c + 1])
     {
       const long long u = (B / 16 + 31) / 32 * 32;
-      const long long cut[5] = {u, 2 * u, 4 * u, 8 * u, B};
-      for (int c = 0; c < 5; c++) cb[c + 1] = std::min<long long>(B, cut[c]);
-      for (int c = 5; c < 8; c++) cb[c + 1] = B;
+      const long long cut_pinned[5] = {u, 2 * u, 4 * u, 8 * u, B};
+      const long long cut_paged[9] = {u, 2 * u, 4 * u, 6 * u, 8 * u, 10 * u, 12 * u, 14 * u, B};
+      const int nc = pinned ? 5 : 9;
+      for (int c = 0; c < nc; c++) cb[c + 1] = std::min<long long>(B, pinned ? cut_pinned[c] : cut_paged[c]);
+      for (int c = nc; c < nch; c++) cb[c + 1] = B;
     }
     // events die with the frame on every return path; the copy stream is drained first so that no queued copy
     // still refers to them (or to the caller's y)

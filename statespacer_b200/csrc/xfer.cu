@@ -3,7 +3,7 @@
 // R allocates its arrays with malloc: a cudaMemcpy from / to them is staged by the driver through one small pinned
 // buffer at 4-6 GB/s, which is what bounds every host-pointer entry point that returns per-draw or per-series arrays
 // (SimSmoother(): 432 MB of results per 12,500 draws).  Here the transfer is cut into chunks that travel through a ring
-// of pinned buffers: the DMA of chunk i runs while helper threads memcpy chunks i-1 .. i-3 between the ring and the
+// of pinned buffers: the DMA of chunk i runs while helper threads memcpy chunks i-1 .. i-7 between the ring and the
 // caller's memory.  Pinned (registered) caller memory and small transfers take the plain cudaMemcpyAsync path.
 #include <cstring>
 #include <future>
@@ -16,12 +16,15 @@ namespace ssgpu {
 
 namespace {
 constexpr size_t kChunk = 8u << 20;  // 8 MB
-constexpr int kRing = 4;
+#ifndef SSGPU_XFER_RING
+#define SSGPU_XFER_RING 8
+#endif
+constexpr int kRing = SSGPU_XFER_RING;  // slots in flight: one DMA + kRing - 1 helper threads copying between the ring and the caller's memory
 constexpr size_t kMinStaged = 4u << 20;
 
 struct Ring {
-  void* buf[kRing] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev[kRing] = {nullptr, nullptr, nullptr, nullptr};
+  void* buf[kRing] = {};
+  cudaEvent_t ev[kRing] = {};
   bool ready = false;
   std::mutex mu;  // one staged transfer at a time (the entry points serialise on the library stream anyway)
   int init() {
