@@ -317,6 +317,15 @@ struct ThrDiffuse {
   double F1[kThrMaxDu];        // 1 / F_inf of step t
   double u[kThrMaxDu][16];     // T M_inf of step t, internal order of the block plan
 };
+// The record of a marked evaluation written from the model itself: see loglik_thr.cu, loglik_thr_setup_kernel
+struct ThrSelf {
+  int on;
+  DMat Q, P_star;             // stored as diagonals (per evaluation or shared)
+  signed char qsrc[16];       // internal position i: R Q R'[i][i] = Q[qsrc[i]] * qscale[i]; -1 = no disturbance
+  signed char psrc[16];       // P_star[i][i] = P_star diag [psrc[i]]; -1 = padding
+  double qscale[16];
+  double a0[16];              // a, internal order (shared by the batch)
+};
 bool thr_supported(int nb, int p, bool ztv);
 size_t thr_handoff_bytes(int nb, bool qoff, long long E);
 int thr_flops_per_step(int nb, bool qoff, bool eps = false, bool ls = false, bool zs = false, bool instr = false);
@@ -324,6 +333,7 @@ int thr_smem_blocks_host(int nb, bool ztv, bool eps = false);
 int launch_loglik_thr(const BlkPlan& pl, const double* z_internal, const double* zt, const double* y, long long B,
                       long long E, long long ldy, int N, const double* hd, const int* hi, double* out, cudaStream_t st,
                       bool eps = false, bool ls = false, bool zs = false, const ThrDiffuse* ud = nullptr);
+int launch_thr_setup(int nb, const ThrSelf& self, long long B, long long E, double* hd, int* hi, cudaStream_t st);
 
 // Thread-per-series kernel on the component states alone, the p residual states of the reference's layout eliminated
 // (loglik_core.cu): m - p <= 8, p <= 16, everything shared and time-invariant, diagonal H

@@ -60,6 +60,7 @@ struct BlkArgs {
   double Tb[kBlkMaxNB][4];             // T_J[row][col] at [2*row + col], internal order
   double z[kBlkMaxP][2 * kBlkMaxNB];   // row j of Z, internal order
   const double* zt;                    // time-varying Z (p = 1): [t][2 * kBlkMaxNB] in internal order, device memory
+  int self_setup;                      // ... and its record is written by loglik_thr_setup_kernel, not here
   int du;                              // hand-over only: an evaluation without a missing value among its first du observations
                                        // is handed over as it stands at t = 0, marked -1 (the thread kernel runs its diffuse steps)
 };
@@ -166,6 +167,24 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
   const long long V = A.E / A.B, b = w_id / V, v = w_id % V;
   const long long e_id = v * A.ldy + b;
   const bool own = I < NB;  // L > NB: the surplus lanes carry zero blocks
+  // Hand-over instantiation: an evaluation that has no missing value among its first du observations does not need the
+  // lanes -- its diffuse steps are the shared ones of the thread kernel (loglik_thr.cu).  It is marked -1; when the
+  // record of such evaluations is written from the model by loglik_thr_setup_kernel (self_setup) nothing else is left to do here,
+  // and a warp made of such evaluations only leaves right away.
+  bool handed = false;
+  if constexpr (HO) {
+    if (A.du > 0) {
+      bool clean = true;
+      for (int tt = I; tt < A.du; tt += L) clean = clean && !isnan(A.y[(long long)tt * A.ldy + b]);
+      const unsigned bal = __ballot_sync(FULL, clean);
+      const unsigned gm = (L == 32 ? FULL : ((1u << L) - 1u)) << (g * L);
+      handed = (bal & gm) == gm;
+      if (A.self_setup) {
+        if (handed && live && I == 0) A.hi[w_id] = -1;
+        if (__all_sync(FULL, handed)) return;
+      }
+    }
+  }
   // block column of the k-th own block; the lane it is shared with; the lane that shares ITS k-th block with this one
   int Jk[K], srcF[K], srcB[K];
   bool keep[K];
@@ -496,20 +515,12 @@ __global__ void __launch_bounds__(NB > 8 ? kBlkThreadsCS : kBlkThreads, blk_minb
 
   const long long Np = (long long)N * p;
   int t = 0;
-  // The diffuse steps of an evaluation that has no missing value among its first du observations are the same for all
-  // such evaluations up to P_star (P_inf, F_inf and the gains do not depend on the data or the variances): it is handed
-  // over as it stands, marked -1, and the thread kernel runs those steps with P_inf's share as constants
-  // (loglik_thr.cu).  The group then idles through the loop below if another group of its warp needs it.
-  bool handed = false;
+  // a marked evaluation (see the top of the kernel): handed over as it stands unless the thread kernel sets it up itself;
+  // its group then idles through the loop below while another group of its warp needs it
   if constexpr (HO) {
-    if (A.du > 0) {
-      bool clean = true;
-      for (int tt = I; tt < A.du; tt += L) clean = clean && !isnan(A.y[(long long)tt * A.ldy + b]);
-      handed = group_all(clean);
-      if (handed) {
-        hand_over(-1);
-        live = false;
-      }
+    if (handed) {
+      if (!A.self_setup) hand_over(-1);
+      live = false;
     }
   }
   {
@@ -1130,6 +1141,39 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
       ud.esumF = esumF;
     }
   }
+  // Marked evaluations: a small kernel writes their hand-over record at t = 0 from the model (loglik_thr.cu) when
+  // that is a matter of look-ups -- a shared, P_star and Q stored as diagonals, R with at most one non-zero per row and
+  // column (so R Q R' = diag(R[i, k]^2 Q[k]): no correlated disturbances)
+  static const bool self_on = [] {
+    const char* e = getenv("SSGPU_THR_SELF_SETUP");
+    return !(e && e[0] == '0');
+  }();
+  ThrSelf self{};
+  if (self_on && ud.du > 0 && !pl.q_offdiag && md.Q.diag && md.P_star.diag && !ah.empty()) {
+    bool ok = true;
+    std::vector<int> col_used((size_t)r, 0);
+    for (int i = 0; i < 2 * pl.nb && ok; i++) {
+      const int st_i = pl.perm[i];
+      self.qsrc[i] = -1;
+      self.psrc[i] = (signed char)st_i;
+      self.qscale[i] = 0.0;
+      self.a0[i] = st_i >= 0 ? ah[st_i] : 0.0;
+      if (st_i < 0) continue;
+      for (int k = 0; k < r && ok; k++) {
+        const double rik = mat_get(Rh.data(), md.R.diag, m, st_i, k);
+        if (rik == 0.0) continue;
+        ok = self.qsrc[i] < 0 && !col_used[k];  // a second non-zero in the row, or the disturbance drives another state too
+        col_used[k] = 1;
+        self.qsrc[i] = (signed char)k;
+        self.qscale[i] = rik * rik;
+      }
+    }
+    if (ok) {
+      self.on = 1;
+      self.Q = md.Q;
+      self.P_star = md.P_star;
+    }
+  }
   BlkArgs A{};
   A.md = md;
   A.y = y;
@@ -1223,7 +1267,15 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
       Ac.hd = scratch.as<double>();
       Ac.hi = reinterpret_cast<int*>(Ac.hd + (size_t)hl.doubles() * Ec);
       Ac.du = ud.du;
+      Ac.self_setup = self.on;
+      ThrSelf selfc = self;  // per-evaluation variances of the range: same strides, shifted base
+      selfc.Q.p += b0 * selfc.Q.sb;
+      selfc.P_star.p += b0 * selfc.P_star.sb;
       SS_TRY(launch_lanes(Ac));
+      if (selfc.on) {
+        SS_TRY(launch_thr_setup(pl.nb, selfc, Bc, Ec, Ac.hd, Ac.hi, st));
+        count_launch();
+      }
       SS_TRY(launch_loglik_thr(pl, &A.z[0][0], A.zt, Ac.y, Bc, Ec, B, md.N, Ac.hd, Ac.hi, Ac.out, st, pl.eps != 0, pl.ls != 0, pl.zs != 0, &ud));
       count_launch();
     }

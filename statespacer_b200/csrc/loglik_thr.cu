@@ -339,6 +339,70 @@ __global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThrea
   A.out[v * A.ldy + b] = res;
 }
 
+// ---- records of the marked evaluations, straight from the model ------------------------------------------------------
+// An evaluation the lane kernel has only marked (-1: no missing value in its diffuse window, loglik_blk.cu) has no
+// hand-over record yet.  When its state at t = 0 is a matter of look-ups -- a shared by the batch, P_star and Q stored as
+// diagonals, R with at most one non-zero per row and column, so that R Q R' = diag(R[i, k]^2 Q[k]) (the launcher has
+// checked all of that) -- this kernel writes the record, one thread per evaluation, every store coalesced; the lanes,
+// 8 per evaluation with their strided stores and their general set-up code, took 1.5 ms for it at config 5, this 0.3 ms.
+// (Building the state inside loglik_thr_kernel instead saved this launch but cost its loop 2 %: ptxas scheduled the
+// same 722 instructions differently.)
+struct ThrSetupArgs {
+  long long B, E;
+  double* hd;
+  int* hi;
+  ThrSelf self;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(128) loglik_thr_setup_kernel(const ThrSetupArgs A) {
+  constexpr BlkHandoff HL(NB, false);
+  const long long w = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (w >= A.E) return;
+  if (A.hi[w] != -1) return;
+  const long long E = A.E, V = E / A.B, b = w / V, v = w % V;
+  const double* const Qb = A.self.Q.block(b, v, 0);
+  const double* const Pb = A.self.P_star.block(b, v, 0);
+  double* const hd = A.hd + w;
+#pragma unroll
+  for (int i = 0; i < 2 * NB; i++) {
+    hd[(long long)(HL.a() + i) * E] = A.self.a0[i];
+    hd[(long long)(HL.q() + i) * E] = A.self.qsrc[i] >= 0 ? Qb[A.self.qsrc[i]] * A.self.qscale[i] : 0.0;
+  }
+#pragma unroll
+  for (int I = 0; I < NB; I++) {
+    hd[(long long)(HL.d() + 3 * I) * E] = A.self.psrc[2 * I] >= 0 ? Pb[A.self.psrc[2 * I]] : 0.0;
+    hd[(long long)(HL.d() + 3 * I + 1) * E] = 0.0;
+    hd[(long long)(HL.d() + 3 * I + 2) * E] = A.self.psrc[2 * I + 1] >= 0 ? Pb[A.self.psrc[2 * I + 1]] : 0.0;
+  }
+#pragma unroll 4
+  for (int i = 0; i < 4 * HL.noff(); i++) hd[(long long)(HL.o() + i) * E] = 0.0;
+  hd[(long long)HL.s() * E] = 1.0;
+  hd[(long long)(HL.s() + 1) * E] = 0.0;
+  A.hi[E + w] = 0;
+  A.hi[2 * E + w] = 0;
+  A.hi[3 * E + w] = 0;
+  A.hi[4 * E + w] = 0;
+}
+
+int launch_thr_setup(int nb, const ThrSelf& self, long long B, long long E, double* hd, int* hi, cudaStream_t st) {
+  ThrSetupArgs A{B, E, hd, hi, self};
+  const long long blocks = (E + 127) / 128;
+  SS_ARG(blocks < (1LL << 31), "thread kernel: batch too large for one launch");
+  switch (nb) {
+#define SS_SETUP_CASE(NBV) \
+  case NBV:                \
+    loglik_thr_setup_kernel<NBV><<<(unsigned)blocks, 128, 0, st>>>(A); \
+    break;
+    SS_SETUP_CASE(2) SS_SETUP_CASE(3) SS_SETUP_CASE(4) SS_SETUP_CASE(5) SS_SETUP_CASE(6) SS_SETUP_CASE(7) SS_SETUP_CASE(8)
+#undef SS_SETUP_CASE
+    default:
+      SS_ARG(false, "thread kernel: 2 to 8 blocks");
+  }
+  SS_CUDA(cudaGetLastError());
+  return SSGPU_OK;
+}
+
 // blocks above the diagonal that go to shared memory: what 255 registers do not hold next to s, the M being
 // accumulated and the temporaries of a block (sized with ptxas -v: no spill at these values)
 #ifndef SSGPU_THR_S7

@@ -1580,7 +1580,7 @@ np.save(sys.argv[1] + ".npy", got)
     with tempfile.TemporaryDirectory() as d:
         outs, names = {}, {}
         for tag, env in (("both", {}), ("no_ls", {"SSGPU_THR_LS": "0"}), ("no_zs", {"SSGPU_THR_ZS": "0"}),
-                         ("no_shared", {"SSGPU_THR_SHARED_DIFFUSE": "0"}),
+                         ("no_shared", {"SSGPU_THR_SHARED_DIFFUSE": "0"}), ("no_self", {"SSGPU_THR_SELF_SETUP": "0"}),
                          ("no_eps", {"SSGPU_THR_EPS": "0", "SSGPU_THR_LS": "0"})):
             r = subprocess.run([sys.executable, "-c", code, os.path.join(d, tag)], env={**os.environ, **env},
                                capture_output=True, text=True, timeout=600)
@@ -1597,6 +1597,9 @@ np.save(sys.argv[1] + ".npy", got)
         # the thread kernel with P_inf's share as constants, the others' on the lanes
         assert "13 shared diffuse steps" in names["both"] and "shared diffuse" not in names["no_shared"], names
         assert np.allclose(outs["both"], outs["no_shared"], rtol=1e-11, atol=0)
+        # ... and without a hand-over record: the thread kernel sets their state up from the model itself (R = I: same bits
+        # as the lane kernel's record)
+        assert np.array_equal(outs["both"], outs["no_self"])
         assert np.array_equal(outs["both"], outs["no_ls"])
         assert np.allclose(outs["both"], outs["no_eps"], rtol=1e-12, atol=0)
 
