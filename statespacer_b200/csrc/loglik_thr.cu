@@ -41,6 +41,9 @@ namespace ssgpu {
 #endif
 constexpr int kThrThreads = SSGPU_THR_THREADS;  // 2 x 128 or 4 x 64 threads per SM: 255 registers either way
 constexpr int kThrMaxNB = 8;
+#ifndef SSGPU_THR_BIG_THREADS
+#define SSGPU_THR_BIG_THREADS 256  // resident threads per SM the kernels of 5 to 8 blocks are sized for (255 registers)
+#endif
 
 struct ThrArgs {
   const double* y;  // [t * ldy + b]
@@ -102,7 +105,7 @@ __device__ __forceinline__ int thr_opaque0() {
 // R/Components-Unobserved.R:143,491-500): the multiply-adds with that zero are left out -- fma(x, 0, acc) == acc, so
 // the same bits again.  90 FP64 instructions fewer per step at 7 blocks.
 template <int NB, int S, bool QOFF, bool ZTV = false, bool EPS = false, bool LS = false, bool ZS = false>
-__global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : 256) / kThrThreads) loglik_thr_kernel(const ThrArgs A) {
+__global__ void __launch_bounds__(kThrThreads, (NB <= 4 ? 512 : SSGPU_THR_BIG_THREADS) / kThrThreads) loglik_thr_kernel(const ThrArgs A) {
   static_assert(!(ZS && ZTV), "sparse-z shortcut: time-invariant Z");
   auto z1fma = [](double x, double z, double acc) { return ZS ? acc : fma(x, z, acc); };
   static_assert(!(EPS && ZTV), "residual shortcut: time-invariant Z");
