@@ -13,8 +13,9 @@
 // idle lane in 8 at 7 blocks, and every lane needs its own copies of T_J and z in vector registers: 1,168
 // FP64 instructions per series and time step.  Here T and z are the same for all 32 lanes at every instruction, so ptxas
 // keeps them in UNIFORM registers (DFMA takes a uniform-register operand) and the vector registers hold P alone;
-// nothing is exchanged, nothing is padded, nothing is computed twice: 861 FP64 instructions per series and time step,
-// 80 % of all instructions of the loop.
+// nothing is exchanged, nothing is padded, nothing is computed twice: 861 FP64 instructions per series and time step
+// in the generic instantiation -- 600 with the structure of a reference model taken out of the arithmetic (EPS, LS, ZS
+// below; config 5), 83 % of all instructions of the loop.
 //
 // One sweep per time step (p = 1): with M = P z known from the previous sweep,
 //     tm = T M,  F = z'M,  v = y - z'a,  s = tm / sqrt(F),  a <- T a + s (v / sqrt(F)),
