@@ -1020,7 +1020,7 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
     // chunks of 1/8 (60.7 -> 56.0 ms per call; with a ring of 4 instead of 8 staging buffers 70.3).
     long long cb[11] = {0};  // chunk c covers the series [cb[c], cb[c + 1])
     {
-      long long u = (B / 16 + 31) / 32 * 32;
+      long long u = (B / 16 + 31) / 32 * 32, wave_u = 0;
       // Whole waves per chunk: the thread-per-evaluation kernel keeps 256 threads per SM resident, and a chunk that ends
       // with a sliver of a wave pays a whole wave's time for it (1.4 ms at config 5, where 1/16 of the batch is 1.86
       // waves).  The unit becomes the multiple of a wave of series closest to 1/16 of the batch.
@@ -1029,12 +1029,17 @@ static int grad_batch_slice(const double* y, long long ldy, long long B, const s
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
             sms > 0) {
           const long long wave = (long long)sms * 256 / V / 32 * 32;  // series per wave, a multiple of 32
-          if (wave >= 32 && B / 16 >= wave) u = std::max<long long>(1, (B / 16 + wave / 2) / wave) * wave;
+          if (wave >= 32 && B / 16 >= wave) {
+            u = std::max<long long>(1, (B / 16 + wave / 2) / wave) * wave;
+            wave_u = wave;
+          }
         }
       }
-      const long long cut_pinned[5] = {u, 2 * u, 4 * u, 8 * u, B};
+      // pinned: the very first chunk is half a unit when that is still whole waves -- the kernels start after 1/32 of the upload
+      const long long first = (wave_u > 0 && (u / wave_u) % 2 == 0) ? u / 2 : u;
+      const long long cut_pinned[6] = {first, u, 2 * u, 4 * u, 8 * u, B};
       const long long cut_paged[9] = {u, 2 * u, 4 * u, 6 * u, 8 * u, 10 * u, 12 * u, 14 * u, B};
-      const int nc = pinned ? 5 : 9;
+      const int nc = pinned ? 6 : 9;
       for (int c = 0; c < nc; c++) cb[c + 1] = std::min<long long>(B, pinned ? cut_pinned[c] : cut_paged[c]);
       for (int c = nc; c < nch; c++) cb[c + 1] = B;
     }
