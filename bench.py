@@ -1111,7 +1111,8 @@ def run_models_gpu(args):
         if api.last_kernel().startswith("loglik_core"):
             # structure-exploiting kernel: its own executed count is the hardware fraction, the dense
             # figure stays beside it as an algorithm-equivalent rate
-            fex = api.core_flops_per_step(sm.m, p)
+            mcore = int(re.search(r"MC=(\d+)", api.last_kernel()).group(1))   # component states left in the recursion
+            fex = api.core_flops_per_step(p + mcore, p)
             rl = line["roofline"]
             rl["dense_algorithm_equivalent_frac"] = rl["frac"]
             rl["achieved"] = value / world * fex / 1e12
@@ -1119,7 +1120,7 @@ def run_models_gpu(args):
             rl["flops_per_series_timestep"] = fex
             rl["dense_flops_per_series_timestep"] = falg
             rl["note"] = ("executed FP64 operations (fma = 2) per series*timestep of loglik_core_kernel: the p residual states "
-                          "are eliminated, the m - p component states are dense; dense_algorithm_equivalent_frac divides the "
+                          "are eliminated, deterministic component states tabulated, the remaining component states dense; dense_algorithm_equivalent_frac divides the "
                           "dense-algorithm count 4m^3 + (4p+3)m^2 + 7pm by the same time and is not a hardware fraction")
         if world == 1 and not args.no_cpu and rank == 0:
             from oracle import cport, ref

@@ -181,10 +181,11 @@ typedef struct ssgpu_model {
 #define SSGPU_KERNEL_CORE 8     /* one thread per series on the component states alone: the p residual states every
                                    reference model starts with (Z = [I_p | Z_c], T = blkdiag(0_p, T_c), R Q R' =
                                    blkdiag(H, W_c), H diagonal; R/GetSysMat.R:1388-1426) are eliminated exactly, the
-                                   dense covariance of the m - p <= 8 remaining states lives in registers (p <= 16,
-                                   everything shared by the batch and time-invariant; exact diffuse phase included).
-                                   BASELINE.json config 3 (dynamic Nelson-Siegel, p = 8, m = 14) is a 6 x 6 problem
-                                   here.  SSGPU_E_ARG if not eligible.  AUTO takes it for batches of 2048 evaluations
+                                   dense covariance of the remaining states lives in registers (p <= 16, m - p <= 16
+                                   of which at most 8 carry a variance: component states with a known start, no
+                                   disturbance and no stochastic driver are tabulated on the host; everything shared
+                                   by the batch and time-invariant; exact diffuse phase included).  BASELINE.json
+                                   config 3 (dynamic Nelson-Siegel, p = 8, m = 14) is a 3 x 3 problem here.  SSGPU_E_ARG if not eligible.  AUTO takes it for batches of 2048 evaluations
                                    or more: before the block-row kernel when p >= 2, behind it when p = 1 */
 
 /* host pointers everywhere (y, the matrices' data, out); copies in, runs, copies out, synchronises */

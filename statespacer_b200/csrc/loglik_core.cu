@@ -38,7 +38,7 @@ constexpr int kCoreThreads = 128;
 #define SSGPU_CORE_AHEAD_SMALL 8
 #endif
 #ifndef SSGPU_CORE_AHEAD_MID
-#define SSGPU_CORE_AHEAD_MID 4
+#define SSGPU_CORE_AHEAD_MID 1
 #endif
 __host__ __device__ constexpr int core_ahead(int mc) { return mc <= 2 ? SSGPU_CORE_AHEAD_SMALL : mc <= 4 ? SSGPU_CORE_AHEAD_MID : 1; }
 constexpr int kCoreMaxNS = kCoreMaxMC * (kCoreMaxMC + 1) / 2;
@@ -53,6 +53,10 @@ struct CoreArgs {
   double Z[kCoreMaxP][kCoreMaxMC];  // Z_c
   double H[kCoreMaxP];
   double a0[kCoreMaxMC], P0[kCoreMaxNS], Pi0[kCoreMaxNS];
+  // deterministic component states taken out of the recursion (see the launcher): their share of z'a per observation,
+  // [t * p + j], and of T a per time update, [t * MC + i]; null = none.  Device memory, the same for every series.
+  const double* coff;
+  const double* boff;
 };
 
 // position of (k, l) in the row-major upper triangle
@@ -111,7 +115,12 @@ __device__ __forceinline__ void core_time_update(double (&X)[MC * (MC + 1) / 2],
 
 // CTAs per SM the register budget is held to (measured on config 3, 6 core states: 124 registers at 4 CTAs 1.22e10
 // series*timesteps/s, left to ptxas 156 - 192 registers and 0.84 - 1.11e10)
-constexpr int core_min_blocks(int mc, bool diff) { return diff ? (mc <= 4 ? 4 : 2) : (mc <= 6 ? 4 : 2); }
+#ifndef SSGPU_CORE_MINB_SMALL
+#define SSGPU_CORE_MINB_SMALL 8
+#endif
+constexpr int core_min_blocks(int mc, bool diff) {
+  return diff ? (mc <= 4 ? 4 : 2) : (mc <= 3 ? SSGPU_CORE_MINB_SMALL : mc <= 6 ? 4 : 2);
+}
 
 template <int MC, bool DIFF>
 __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) loglik_core_kernel(const CoreArgs A) {
@@ -160,6 +169,7 @@ __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) logli
   };
 
   // regular update with observation j (src/LogLikC.cpp:162-195); missing or F < 1e-7: a no-op through 1/sqrt(F) := 0
+  int t = 0;  // time point (the lambdas below index the offset tables with it)
   // the row of Z_c and H_jj of the coming observation are read one observation ahead (an indexed read of the
   // constant bank right in front of the dot products that need it costs its latency 8 times per time point)
   double zc[MC], hc;
@@ -194,7 +204,7 @@ __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) logli
     const bool upd = obs && !(F < kEps);  // :173
     double r = core_rsqrt(upd ? F : 1.0);
     r = upd ? r : 0.0;
-    const double cv = r * (upd ? yv - za : 0.0);
+    const double cv = r * (upd ? yv - za - (A.coff ? A.coff[(long long)t * p + j] : 0.0) : 0.0);
     acc_log(upd ? F : 1.0);
     n_terms += upd;
     non_init += obs;
@@ -224,14 +234,13 @@ __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) logli
       ta[i] = acc;
     }
 #pragma unroll
-    for (int i = 0; i < MC; i++) a[i] = ta[i];
+    for (int i = 0; i < MC; i++) a[i] = ta[i] + (A.boff ? A.boff[(long long)t * MC + i] : 0.0);
     core_time_update<MC, true>(C, Tc, &A.W[0] + core_opaque0());
     if constexpr (DIFF) {
       if (with_inf) core_time_update<MC, false>(Ci, Tc, nullptr);
     }
   };
 
-  int t = 0;
   if constexpr (DIFF) {
     auto inf_small = [&]() {  // all(|P_inf| < 1e-7), NaN compares false (:49,158,205)
       bool ok = true;
@@ -273,7 +282,7 @@ __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) logli
         if (Fi < kEps) {                // :109
           if (Fs < kEps) continue;      // :112
           const double F1 = 1.0 / Fs;   // :117-130
-          const double v = yv - za, g = F1 * v;
+          const double v = yv - za - (A.coff ? A.coff[(long long)t * p + j] : 0.0), g = F1 * v;
 #pragma unroll
           for (int k = 0; k < MC; k++) a[k] = fma(Ms[k], g, a[k]);
 #pragma unroll
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) logli
           continue;
         }
         const double F1 = 1.0 / Fi, F2 = -(F1 * F1) * Fs;  // :136-153
-        const double v = yv - za, g = F1 * v;
+        const double v = yv - za - (A.coff ? A.coff[(long long)t * p + j] : 0.0), g = F1 * v;
 #pragma unroll
         for (int k = 0; k < MC; k++) a[k] = fma(Mi[k], g, a[k]);
 #pragma unroll
@@ -343,7 +352,7 @@ bool core_eligible(const DModel& md, std::string* why) {
     return false;
   };
   const int mc = md.m - md.p;
-  if (mc < 1 || mc > kCoreMaxMC) return no("m - p outside 1 .. 8");
+  if (mc < 1 || mc > 2 * kCoreMaxMC) return no("m - p outside 1 .. 16 (at most 8 of them with a variance)");
   if (md.p < 1 || md.p > kCoreMaxP) return no("p outside 1 .. 16");
   if (!md.Z.shared() || !md.T.shared() || !md.R.shared() || !md.Q.shared() || !md.a.shared() || !md.P_inf.shared() ||
       !md.P_star.shared())
@@ -431,6 +440,44 @@ int launch_loglik_core(const DModel& md, const double* y, long long B, int V, do
     }
     SS_ARG(false, std::string("core kernel not eligible: ") + bad);
   }
+  // Deterministic component states: no initial variance (P_star and P_inf rows zero), no disturbance (R Q R' row zero)
+  // and driven by deterministic states only (T[d, s] = 0 for every other state s).  Their rows of P stay zero for ever
+  // and their values are the same known numbers for every series -- the constants of a VAR with a mean (the dynamic
+  // Nelson-Siegel model of config 3 carries three), fixed effects.  They leave the recursion: what they add to z'a per
+  // observation and to T a per time update is tabulated here once (N x p and N x mc_s doubles) and the kernel runs on
+  // the remaining states.
+  std::vector<int> det((size_t)mc, 1);
+  for (int i = 0; i < mc; i++)
+    for (int k = 0; k < mc && det[i]; k++)
+      if (Psm(p + i, p + k) != 0.0 || Psm(p + k, p + i) != 0.0 || Pim(p + i, p + k) != 0.0 || Pim(p + k, p + i) != 0.0 ||
+          W[(p + i) + (size_t)(p + k) * m] != 0.0 || W[(p + k) + (size_t)(p + i) * m] != 0.0)
+        det[i] = 0;
+  for (bool changed = true; changed;) {
+    changed = false;
+    for (int i = 0; i < mc; i++) {
+      if (!det[i]) continue;
+      for (int k = 0; k < mc; k++)
+        if (!det[k] && Tm(p + i, p + k) != 0.0) {
+          det[i] = 0;
+          changed = true;
+          break;
+        }
+    }
+  }
+  std::vector<int> sidx, didx;  // core indices of the stochastic / deterministic states
+  for (int i = 0; i < mc; i++) (det[i] ? didx : sidx).push_back(i);
+  if (sidx.empty()) {  // nothing stochastic but the residuals: keep one state in the recursion
+    sidx.push_back(didx.back());
+    didx.pop_back();
+  }
+  const int ms = (int)sidx.size(), mdn = (int)didx.size();
+  if (ms > kCoreMaxMC) {
+    if (applicable) {
+      *applicable = false;
+      return SSGPU_OK;
+    }
+    SS_ARG(false, "core kernel not eligible: more than 8 component states with a variance");
+  }
   CoreArgs A{};
   A.y = y;
   A.B = B;
@@ -438,16 +485,47 @@ int launch_loglik_core(const DModel& md, const double* y, long long B, int V, do
   A.N = md.N;
   A.p = p;
   A.out = out;
+  DevBuf offs;  // released stream-ordered behind the kernel
+  if (mdn > 0) {
+    const int N = md.N;
+    std::vector<double> tab((size_t)N * p + (size_t)N * ms), ad((size_t)mdn), nx((size_t)mdn);
+    for (int k = 0; k < mdn; k++) ad[k] = ah[p + didx[k]];
+    for (int t = 0; t < N; t++) {
+      for (int j = 0; j < p; j++) {
+        double acc = 0.0;
+        for (int k = 0; k < mdn; k++) acc += Zm(j, p + didx[k]) * ad[k];
+        tab[(size_t)t * p + j] = acc;
+      }
+      for (int i = 0; i < ms; i++) {
+        double acc = 0.0;
+        for (int k = 0; k < mdn; k++) acc += Tm(p + sidx[i], p + didx[k]) * ad[k];
+        tab[(size_t)N * p + (size_t)t * ms + i] = acc;
+      }
+      for (int i = 0; i < mdn; i++) {
+        double acc = 0.0;
+        for (int k = 0; k < mdn; k++) acc += Tm(p + didx[i], p + didx[k]) * ad[k];
+        nx[i] = acc;
+      }
+      ad = nx;
+    }
+    SS_TRY(offs.alloc(tab.size() * sizeof(double), st));
+    SS_CUDA(cudaMemcpyAsync(offs.get(), tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    SS_CUDA(cudaStreamSynchronize(st));  // the host vector dies with this frame
+    A.coff = offs.as<double>();
+    A.boff = offs.as<double>() + (size_t)N * p;
+  }
   bool diffuse = false;
-  for (int i = 0; i < mc; i++) {
-    A.a0[i] = ah[p + i];
-    for (int k = 0; k < mc; k++) {
-      A.T[i * mc + k] = Tm(p + i, p + k);
+  for (int i = 0; i < ms; i++) {
+    const int ci = p + sidx[i];
+    A.a0[i] = ah[ci];
+    for (int k = 0; k < ms; k++) {
+      const int ck = p + sidx[k];
+      A.T[i * ms + k] = Tm(ci, ck);
       if (k >= i) {
-        const int e = core_sym(mc, i, k);
-        A.W[e] = W[(p + i) + (size_t)(p + k) * m];
-        A.P0[e] = Psm(p + i, p + k);
-        A.Pi0[e] = Pim(p + i, p + k);
+        const int e = core_sym(ms, i, k);
+        A.W[e] = W[ci + (size_t)ck * m];
+        A.P0[e] = Psm(ci, ck);
+        A.Pi0[e] = Pim(ci, ck);
         // all(|P_inf| < 1e-7) with NaN comparing false (src/LogLikC.cpp:49)
         if (!(std::fabs(A.Pi0[e]) < kEps)) diffuse = true;
       }
@@ -455,10 +533,10 @@ int launch_loglik_core(const DModel& md, const double* y, long long B, int V, do
   }
   for (int j = 0; j < p; j++) {
     A.H[j] = W[j + (size_t)j * m];
-    for (int k = 0; k < mc; k++) A.Z[j][k] = Zm(j, p + k);
+    for (int k = 0; k < ms; k++) A.Z[j][k] = Zm(j, p + sidx[k]);
   }
   int rc = SSGPU_E_ARG;
-  switch (mc) {
+  switch (ms) {
 #define SS_CASE(MM)                            \
   case MM:                                     \
     rc = launch_core_mc<MM>(A, diffuse, st);   \
@@ -468,7 +546,10 @@ int launch_loglik_core(const DModel& md, const double* y, long long B, int V, do
   }
   SS_TRY(rc);
   count_launch(1);
-  set_last_kernel("loglik_core_kernel");
+  static thread_local char name[96];
+  snprintf(name, sizeof name, "loglik_core_kernel<MC=%d%s>%s", ms, diffuse ? ",diffuse" : "",
+           mdn > 0 ? " deterministic states tabulated" : "");
+  set_last_kernel(name);
   return SSGPU_OK;
 }
 

@@ -781,7 +781,7 @@ def test_batch_multivariate_dns():
         assert abs(cols[b] - want) <= RTOL * max(1, abs(want)), (b, cols[b], want)
 
 
-def _residual_layout_model(rng, p, mc, d, r_c=None, h_zero=()):
+def _residual_layout_model(rng, p, mc, d, r_c=None, h_zero=(), n_det=0):
     """A model in the reference's own state layout (R/GetSysMat.R:1388-1426): [p residuals ; mc component states],
     dense T_c, Z_c, R_c, Q_c, d diffuse component states, diagonal H (entries in h_zero set to 0)."""
     r_c = r_c or mc
@@ -806,25 +806,41 @@ def _residual_layout_model(rng, p, mc, d, r_c=None, h_zero=()):
     H = np.diag(rng.uniform(0.05, 0.5, p))
     for j in h_zero:
         H[j, j] = 0.0
-    comp = dict(Z=Z, T=T, R=R, Q=Q, a=rng.normal(size=mc), P_inf=P_inf, P_star=P_star)
+    a = rng.normal(size=mc)
+    if n_det:
+        # deterministic states behind the stochastic ones: known start, no disturbance, driven by each other only, feeding
+        # the stochastic states and the observations (the means of a VAR, fixed effects)
+        Tdd = np.eye(n_det) * 0.97 + 0.02 * rng.normal(size=(n_det, n_det))
+        Tsd = rng.normal(size=(mc, n_det)) * 0.2
+        T = np.block([[T, Tsd], [np.zeros((n_det, mc)), Tdd]])
+        Z = np.concatenate([Z, rng.normal(size=(p, n_det))], axis=1)
+        R = np.concatenate([R, np.zeros((n_det, R.shape[1]))], axis=0)
+        P_star = sysmat.block_diag(P_star, np.zeros((n_det, n_det)))
+        P_inf = sysmat.block_diag(P_inf, np.zeros((n_det, n_det)))
+        a = np.concatenate([a, rng.normal(size=n_det)])
+    comp = dict(Z=Z, T=T, R=R, Q=Q, a=a, P_inf=P_inf, P_star=P_star)
     return sysmat._combine(p, H, [comp])
 
 
-@pytest.mark.parametrize("p,mc,d", [(1, 1, 0), (1, 3, 1), (2, 2, 2), (3, 4, 0), (3, 5, 2), (8, 6, 0), (4, 6, 3),
-                                    (2, 7, 1), (5, 8, 2), (16, 3, 1)])
-def test_batch_core_kernel(p, mc, d):
+@pytest.mark.parametrize("p,mc,d,n_det", [(1, 1, 0, 0), (1, 3, 1, 0), (2, 2, 2, 0), (3, 4, 0, 0), (3, 5, 2, 0), (8, 6, 0, 0),
+                                          (4, 6, 3, 0), (2, 7, 1, 0), (5, 8, 2, 0), (16, 3, 1, 0),
+                                          (3, 4, 0, 2), (2, 3, 1, 3), (4, 5, 2, 6), (8, 3, 0, 3)])
+def test_batch_core_kernel(p, mc, d, n_det):
     """Thread-per-series kernel on the component states (residual states eliminated, loglik_core.cu) against the oracle
     run on the FULL state: dense T_c / Q_c, exact diffuse phase with d diffuse states, missing observations, a series
-    that is missing throughout a stretch spanning the diffuse phase, one observation without noise (H_jj = 0)."""
-    rng = np.random.default_rng(1000 + 37 * p + 5 * mc + d)
+    that is missing throughout a stretch spanning the diffuse phase, one observation without noise (H_jj = 0); n_det
+    deterministic component states (known start, no disturbance) that the launcher takes out of the recursion."""
+    rng = np.random.default_rng(1000 + 37 * p + 5 * mc + d + 101 * n_det)
     N, B = 45, 40
-    sm = _residual_layout_model(rng, p, mc, d, h_zero=(p - 1,) if p >= 3 else ())
+    sm = _residual_layout_model(rng, p, mc, d, h_zero=(p - 1,) if p >= 3 else (), n_det=n_det)
     y = np.stack([simulate_y(rng, sm, N, missing=0.08) for _ in range(B)], axis=2)
     y[:6, :, 1] = np.nan                                                   # diffuse phase starts late
     y[:, 0, 2] = np.nan                                                    # first observed variable never seen
     y[3:, :, 3] = np.nan                                                   # too few observations to leave the diffuse phase
     got = api.loglik_batch(y, sm, kernel="core")
-    assert api.last_kernel().startswith("loglik_core")
+    # the n_det deterministic states leave the recursion (tabulated offsets): the kernel runs on mc states
+    assert api.last_kernel().startswith(f"loglik_core_kernel<MC={mc}"), api.last_kernel()
+    assert ("deterministic states tabulated" in api.last_kernel()) == (n_det > 0)
     other = api.loglik_batch(y, sm, kernel="generic")
     for b in range(B):
         yb = y[:, :, b]
@@ -848,7 +864,8 @@ def test_batch_core_kernel_dns_and_dispatch():
     y[rng.uniform(size=y.shape) < 0.03] = np.nan
     y[:, :, 0] = fed
     got = api.loglik_batch(y, sm)
-    assert api.last_kernel().startswith("loglik_core")
+    # 14 states = 8 residuals + 3 factors + their 3 constant means: a 3 x 3 problem per thread
+    assert api.last_kernel().startswith("loglik_core_kernel<MC=3>") and "deterministic states tabulated" in api.last_kernel()
     assert abs(got[0] - 7.005830) < 6e-7 * 7                               # docs/articles/selfspec.html:306-307
     assert np.array_equal(got, api.loglik_batch(y, sm, kernel="core"))
     cols = api.loglik_batch(y[:, :, :64], sm)
