@@ -35,7 +35,7 @@ constexpr int kCoreThreads = 128;
 // thread the local level runs at 1.7 TB/s of observations whatever the arithmetic costs.  Large cores hide the load
 // behind the ~100 FP64 instructions of an observation and have no registers to spare.
 #ifndef SSGPU_CORE_AHEAD_SMALL
-#define SSGPU_CORE_AHEAD_SMALL 8
+#define SSGPU_CORE_AHEAD_SMALL 4
 #endif
 #ifndef SSGPU_CORE_AHEAD_MID
 #define SSGPU_CORE_AHEAD_MID 1
@@ -122,7 +122,8 @@ constexpr int core_min_blocks(int mc, bool diff) {
   return diff ? (mc <= 4 ? 4 : 2) : (mc <= 3 ? SSGPU_CORE_MINB_SMALL : mc <= 6 ? 4 : 2);
 }
 
-template <int MC, bool DIFF>
+// OFF: deterministic component states have been taken out (A.coff / A.boff, see the launcher)
+template <int MC, bool DIFF, bool OFF>
 __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) loglik_core_kernel(const CoreArgs A) {
   constexpr int NS = MC * (MC + 1) / 2;
   const long long w = (long long)blockIdx.x * kCoreThreads + threadIdx.x;
@@ -204,7 +205,9 @@ __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) logli
     const bool upd = obs && !(F < kEps);  // :173
     double r = core_rsqrt(upd ? F : 1.0);
     r = upd ? r : 0.0;
-    const double cv = r * (upd ? yv - za - (A.coff ? A.coff[(long long)t * p + j] : 0.0) : 0.0);
+    double off = 0.0;
+    if constexpr (OFF) off = A.coff[(long long)t * p + j];
+    const double cv = r * (upd ? yv - za - off : 0.0);
     acc_log(upd ? F : 1.0);
     n_terms += upd;
     non_init += obs;
@@ -234,7 +237,10 @@ __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) logli
       ta[i] = acc;
     }
 #pragma unroll
-    for (int i = 0; i < MC; i++) a[i] = ta[i] + (A.boff ? A.boff[(long long)t * MC + i] : 0.0);
+    for (int i = 0; i < MC; i++) {
+      a[i] = ta[i];
+      if constexpr (OFF) a[i] += A.boff[(long long)t * MC + i];
+    }
     core_time_update<MC, true>(C, Tc, &A.W[0] + core_opaque0());
     if constexpr (DIFF) {
       if (with_inf) core_time_update<MC, false>(Ci, Tc, nullptr);
@@ -282,7 +288,9 @@ __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) logli
         if (Fi < kEps) {                // :109
           if (Fs < kEps) continue;      // :112
           const double F1 = 1.0 / Fs;   // :117-130
-          const double v = yv - za - (A.coff ? A.coff[(long long)t * p + j] : 0.0), g = F1 * v;
+          double off = 0.0;
+        if constexpr (OFF) off = A.coff[(long long)t * p + j];
+        const double v = yv - za - off, g = F1 * v;
 #pragma unroll
           for (int k = 0; k < MC; k++) a[k] = fma(Ms[k], g, a[k]);
 #pragma unroll
@@ -297,7 +305,9 @@ __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) logli
           continue;
         }
         const double F1 = 1.0 / Fi, F2 = -(F1 * F1) * Fs;  // :136-153
-        const double v = yv - za - (A.coff ? A.coff[(long long)t * p + j] : 0.0), g = F1 * v;
+        double off = 0.0;
+        if constexpr (OFF) off = A.coff[(long long)t * p + j];
+        const double v = yv - za - off, g = F1 * v;
 #pragma unroll
         for (int k = 0; k < MC; k++) a[k] = fma(Mi[k], g, a[k]);
 #pragma unroll
@@ -365,10 +375,16 @@ template <int MC>
 static int launch_core_mc(const CoreArgs& A, bool diffuse, cudaStream_t st) {
   const long long blocks = (A.E + kCoreThreads - 1) / kCoreThreads;
   SS_ARG(blocks < (1LL << 31), "core kernel: batch too large for one launch");
-  if (diffuse)
-    loglik_core_kernel<MC, true><<<(unsigned)blocks, kCoreThreads, 0, st>>>(A);
+  const unsigned g = (unsigned)blocks;
+  const bool off = A.coff != nullptr;
+  if (diffuse && off)
+    loglik_core_kernel<MC, true, true><<<g, kCoreThreads, 0, st>>>(A);
+  else if (diffuse)
+    loglik_core_kernel<MC, true, false><<<g, kCoreThreads, 0, st>>>(A);
+  else if (off)
+    loglik_core_kernel<MC, false, true><<<g, kCoreThreads, 0, st>>>(A);
   else
-    loglik_core_kernel<MC, false><<<(unsigned)blocks, kCoreThreads, 0, st>>>(A);
+    loglik_core_kernel<MC, false, false><<<g, kCoreThreads, 0, st>>>(A);
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;
 }
