@@ -161,6 +161,14 @@ def test_plan_blocks_host_helper():
     assert api.plan_blocks(np.eye(3), np.eye(3))["n_blocks"] == 2 and api.plan_blocks(np.eye(3), np.eye(3))["lanes"] == 2
 
 
+def test_core_flops_helper():
+    """ssgpu_core_flops_per_step (host only): executed FP64 operations of the core kernel's regular phase -- config 3 with
+    its 6 component states (2,082) and with the 3 deterministic means tabulated (648); 0 outside the kernel's range."""
+    from statespacer_b200 import api
+    assert api.core_flops_per_step(14, 8) == 2082 and api.core_flops_per_step(11, 8) == 648
+    assert api.core_flops_per_step(2, 1) > 0 and api.core_flops_per_step(30, 1) == 0 and api.core_flops_per_step(20, 17) == 0
+
+
 def test_plan_blocks_random_models():
     """Property check of the host planner over random models: a T made of 1x1 and 2x2 blocks, states shuffled, R = I
     and a diagonal Q must decompose into closed blocks covering every state once; one extra coupling that chains three
