@@ -186,7 +186,8 @@ typedef struct ssgpu_model {
                                    disturbance and no stochastic driver are tabulated on the host; everything shared
                                    by the batch and time-invariant; exact diffuse phase included).  BASELINE.json
                                    config 3 (dynamic Nelson-Siegel, p = 8, m = 14) is a 3 x 3 problem here.  SSGPU_E_ARG if not eligible.  AUTO takes it for batches of 2048 evaluations
-                                   or more: before the block-row kernel when p >= 2, behind it when p = 1 */
+                                   or more: before the block-row kernel when p >= 2 or m = 2 (local level), behind it
+                                   otherwise */
 
 /* host pointers everywhere (y, the matrices' data, out); copies in, runs, copies out, synchronises */
 int ssgpu_loglik_batch(const double* y, long long B, int V, const ssgpu_model* model, int kernel,

@@ -387,7 +387,9 @@ static int dispatch_batch(const DModel& md, const double* y_dev, long long B, in
   // thread-per-evaluation kernel behind the block planner)
   const bool core_auto = kernel == SSGPU_KERNEL_AUTO && auto_core_enabled() && std::max(B * V, call_evals) >= kCoreMinEvals &&
                          core_eligible(md, &why);
-  if (core_auto && md.p >= 2) {
+  // ... and so does the local level (m = 2: one component state, p = 1 known at compile time: 2.7e11 series*timesteps/s
+  // against 2.0e11 on the one-lane-per-series instantiation of the block kernel)
+  if (core_auto && (md.p >= 2 || md.m == 2)) {
     bool ran = true;
     SS_TRY(launch_loglik_core(md, y_dev, B, V, out_dev, st, hs, &ran));
     if (ran) return SSGPU_OK;
@@ -397,7 +399,7 @@ static int dispatch_batch(const DModel& md, const double* y_dev, long long B, in
     SS_TRY(launch_loglik_blk(md, y_dev, B, V, out_dev, st, hs, &ran, false, call_evals));
     if (ran) return SSGPU_OK;
   }
-  if (core_auto && md.p < 2) {
+  if (core_auto && md.p < 2 && md.m != 2) {
     bool ran = true;
     SS_TRY(launch_loglik_core(md, y_dev, B, V, out_dev, st, hs, &ran));
     if (ran) return SSGPU_OK;

@@ -123,13 +123,15 @@ constexpr int core_min_blocks(int mc, bool diff) {
 }
 
 // OFF: deterministic component states have been taken out (A.coff / A.boff, see the launcher)
-template <int MC, bool DIFF, bool OFF>
+// P1: one observation per time point (p = 1), known at compile time: no loop over the observations, the one row of Z_c
+// and H are loaded once
+template <int MC, bool DIFF, bool OFF, bool P1>
 __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) loglik_core_kernel(const CoreArgs A) {
   constexpr int NS = MC * (MC + 1) / 2;
   const long long w = (long long)blockIdx.x * kCoreThreads + threadIdx.x;
   if (w >= A.E) return;
   const long long b = w % A.B;
-  const int N = A.N, p = A.p;
+  const int N = A.N, p = P1 ? 1 : A.p;
   double C[NS], a[MC];
   double Ci[DIFF ? NS : 1];
 #pragma unroll
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) logli
 #pragma unroll
     for (int k = 0; k < MC; k++) z[k] = zc[k];
     const double hj = hc;
-    load_z(j + 1 < p ? j + 1 : 0);
+    if constexpr (!P1) load_z(j + 1 < p ? j + 1 : 0);
     double M[MC];
 #pragma unroll
     for (int k = 0; k < MC; k++) {
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(kCoreThreads, core_min_blocks(MC, DIFF)) logli
       for (int j = 0; j < p; j++) {
         const double yv = take_y();
         if (!init) {
-          load_z(j);  // the diffuse branch below reads its row directly and does not keep the look-ahead current
+          if constexpr (!P1) load_z(j);  // the diffuse branch below reads its row directly and does not keep the look-ahead current
           regular_obs(j, yv);
           continue;
         }
@@ -376,15 +378,19 @@ static int launch_core_mc(const CoreArgs& A, bool diffuse, cudaStream_t st) {
   const long long blocks = (A.E + kCoreThreads - 1) / kCoreThreads;
   SS_ARG(blocks < (1LL << 31), "core kernel: batch too large for one launch");
   const unsigned g = (unsigned)blocks;
-  const bool off = A.coff != nullptr;
-  if (diffuse && off)
-    loglik_core_kernel<MC, true, true><<<g, kCoreThreads, 0, st>>>(A);
+  const bool off = A.coff != nullptr, p1 = A.p == 1 && !off;
+  if (diffuse && p1)
+    loglik_core_kernel<MC, true, false, true><<<g, kCoreThreads, 0, st>>>(A);
+  else if (p1)
+    loglik_core_kernel<MC, false, false, true><<<g, kCoreThreads, 0, st>>>(A);
+  else if (diffuse && off)
+    loglik_core_kernel<MC, true, true, false><<<g, kCoreThreads, 0, st>>>(A);
   else if (diffuse)
-    loglik_core_kernel<MC, true, false><<<g, kCoreThreads, 0, st>>>(A);
+    loglik_core_kernel<MC, true, false, false><<<g, kCoreThreads, 0, st>>>(A);
   else if (off)
-    loglik_core_kernel<MC, false, true><<<g, kCoreThreads, 0, st>>>(A);
+    loglik_core_kernel<MC, false, true, false><<<g, kCoreThreads, 0, st>>>(A);
   else
-    loglik_core_kernel<MC, false, false><<<g, kCoreThreads, 0, st>>>(A);
+    loglik_core_kernel<MC, false, false, false><<<g, kCoreThreads, 0, st>>>(A);
   SS_CUDA(cudaGetLastError());
   return SSGPU_OK;
 }
@@ -563,7 +569,7 @@ int launch_loglik_core(const DModel& md, const double* y, long long B, int V, do
   SS_TRY(rc);
   count_launch(1);
   static thread_local char name[96];
-  snprintf(name, sizeof name, "loglik_core_kernel<MC=%d%s>%s", ms, diffuse ? ",diffuse" : "",
+  snprintf(name, sizeof name, "loglik_core_kernel<MC=%d%s%s>%s", ms, diffuse ? ",diffuse" : "", (p == 1 && mdn == 0) ? ",p1" : "",
            mdn > 0 ? " deterministic states tabulated" : "");
   set_last_kernel(name);
   return SSGPU_OK;

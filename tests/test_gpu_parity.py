@@ -875,6 +875,20 @@ def test_batch_core_kernel_dns_and_dispatch():
         yb = y[:, :, b]
         want = cport.LogLikC(yb, np.isnan(yb), *sm.args())
         assert abs(got[b] - want) <= RTOL * max(1, abs(want)), (b, got[b], want)
+    # the local level (config 1 batched): AUTO takes it to the p = 1 instantiation from 2048 series on
+    nile = sysmat.nile_local_level(15100.252, 1468.724)
+    yl = np.cumsum(rng.normal(size=(100, 2048)), axis=0) * 40.0 + 900.0
+    yl[rng.uniform(size=yl.shape) < 0.05] = np.nan
+    yl[:, 7] = np.nan
+    gl = api.loglik_batch(yl, nile)
+    assert api.last_kernel().startswith("loglik_core_kernel<MC=1,diffuse,p1>"), api.last_kernel()
+    lanes = api.loglik_batch(yl, nile, kernel="blk")
+    assert api.last_kernel().startswith("loglik_blk_kernel<L=1,NB=1,")
+    assert np.isnan(gl[7]) and np.allclose(gl, lanes, rtol=1e-12, atol=0, equal_nan=True)
+    for b in range(0, 2048, 199):
+        yb = yl[:, b:b + 1]
+        want = cport.LogLikC(yb, np.isnan(yb), *nile.args())
+        assert (math.isnan(want) and math.isnan(gl[b])) or abs(gl[b] - want) <= RTOL * max(1, abs(want)), (b, gl[b], want)
     # correlated observation noise (H not diagonal) couples the residual states: refused, AUTO moves on
     bad = sysmat.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=sm.Q.copy(), a=sm.a, P_inf=sm.P_inf, P_star=sm.P_star.copy())
     bad.Q[0, 1, 0] = bad.Q[1, 0, 0] = 1e-4
