@@ -360,6 +360,17 @@ int ssgpu_plan_state_order(const double* T, int m, int* perm, unsigned* tile_mas
  * and time step (fma = 2, all lanes). */
 int ssgpu_plan_blocks(const double* T, const double* R, const double* Q, int m, int r, int p, int* perm,
                       int* n_blocks, int* lanes, int* flop_per_step);
+/* Host-only helper (no device needed): what the thread-per-evaluation kernel behind SSGPU_KERNEL_BLK does with a
+ * univariate model (p = 1; Z a row of m, everything column-major and shared by the batch, Q NULL = diagonal):
+ * *n_blocks as ssgpu_plan_blocks (0: the model does not decompose; the other outputs are 0 then, and when the block
+ * count is outside 2 .. 8); *residual_dropped, *level_slope_by_sums, *zero_z_skipped: the structural shortcuts that
+ * apply; *shared_diffuse_steps: the length of the diffuse phase the kernel runs itself for series
+ * without a missing value in it (0: P_inf does not vanish within 16 steps, or some F_inf < 1e-7); *flop_per_step: FP64
+ * operations per series and time step of the resulting instantiation.  Any output pointer may be NULL. */
+int ssgpu_plan_thread_kernel(const double* T, const double* R, const double* Q, const double* Z, const double* a,
+                             const double* P_inf, const double* P_star, int m, int r, int N, int* n_blocks,
+                             int* residual_dropped, int* level_slope_by_sums, int* zero_z_skipped,
+                             int* shared_diffuse_steps, int* flop_per_step);
 /* FP64 operations (fma = 2) the core kernel (SSGPU_KERNEL_CORE) issues per series and time point of the regular
  * phase for a model with m states of which p are residuals; 0 when m - p or p is outside the kernel's range. */
 int ssgpu_core_flops_per_step(int m, int p);

@@ -213,6 +213,19 @@ def ExtractComponentC(a, Z):
     return out
 
 
+def plan_thread_kernel(sm, N):
+    """Host only: what the thread-per-evaluation kernel does with the univariate model `sm` (shared matrices) over N time
+    points -- dict(n_blocks, residual_dropped, level_slope_by_sums, zero_z_skipped, shared_diffuse_steps, flop_per_step)."""
+    f = lambda x: np.asfortranarray(np.asarray(x, dtype=np.float64))
+    T, R, Q, Z = f(sm.T[:, :, 0]), f(sm.R[:, :, 0]), f(sm.Q[:, :, 0]), f(sm.Z[0, :, 0])
+    a, Pi, Ps = f(sm.a), f(sm.P_inf), f(sm.P_star)
+    out = [C.c_int(0) for _ in range(6)]
+    native.check(native.lib().ssgpu_plan_thread_kernel(_ptr(T), _ptr(R), _ptr(Q), _ptr(Z), _ptr(a), _ptr(Pi), _ptr(Ps), T.shape[0],
+                                                       R.shape[1], int(N), *[C.addressof(o) for o in out]))
+    keys = ("n_blocks", "residual_dropped", "level_slope_by_sums", "zero_z_skipped", "shared_diffuse_steps", "flop_per_step")
+    return dict(zip(keys, (o.value for o in out)))
+
+
 def core_flops_per_step(m, p):
     """FP64 operations per series and time point of the core kernel's regular phase (0 = outside its range)."""
     return int(native.lib().ssgpu_core_flops_per_step(int(m), int(p)))

@@ -924,62 +924,14 @@ int blk_useful_flops_per_step(int nb, int p) {
   return (int)((long long)blk_flops_per_step(nb, p) * nb / L);
 }
 
-int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
-                      const HostShared* hs, bool* applicable, bool lanes_only, long long call_evals) {
-  std::string why;
-  if (applicable) *applicable = true;
-  SS_ARG(blk_eligible(md, &why), "block kernel not eligible: " + why);
+// Host side of the thread kernel's structural shortcuts and of the shared diffuse steps (loglik_thr.cu): everything is
+// decided on host copies of the shared matrices.  `md` supplies the storage flags only (shared / diagonal).  The plan's
+// blocks are re-ordered in place; ud and self are filled.
+void plan_thread_shortcuts(const DModel& md, int nZ, const std::vector<double>& Th, const std::vector<double>& Rh,
+                           const std::vector<double>& Zh, const std::vector<double>& ah, const std::vector<double>& Psh,
+                           const std::vector<double>& Pih, const std::vector<unsigned char>& qpat, BlkPlan& pl,
+                           ThrDiffuse& ud, ThrSelf& self) {
   const int m = md.m, r = md.r, p = md.p;
-  // the shared matrices are a few hundred bytes: fetch what the caller has not passed along (host copies)
-  const int nZ = md.Z.tv() ? md.N : 1;
-  std::vector<double> Th((size_t)(md.T.diag ? m : m * m)), Rh((size_t)(md.R.diag ? m : m * r)), Zh((size_t)p * m * nZ), Qh;
-  std::vector<unsigned char> qpat;
-  bool need_sync = false;
-  auto fetch = [&](std::vector<double>& dst, const double* host, const double* dev) -> int {
-    if (host) {
-      std::copy(host, host + dst.size(), dst.begin());
-    } else {
-      SS_CUDA(cudaMemcpyAsync(dst.data(), dev, dst.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-      need_sync = true;
-    }
-    return SSGPU_OK;
-  };
-  SS_TRY(fetch(Th, hs ? hs->T : nullptr, md.T.p));
-  SS_TRY(fetch(Rh, hs ? hs->R : nullptr, md.R.p));
-  SS_TRY(fetch(Zh, (hs && nZ == 1) ? hs->Z : nullptr, md.Z.p));
-  if (!md.Q.diag) {
-    Qh.resize((size_t)r * r);
-    SS_TRY(fetch(Qh, hs ? hs->Q : nullptr, md.Q.p));
-  }
-  // what the thread kernel's residual shortcut looks at (p = 1, time-invariant Z): a, and a dense P_star, when shared
-  std::vector<double> ah, Psh, Pih;
-  if (p == 1 && nZ == 1) {
-    if (md.a.shared()) {
-      ah.resize((size_t)m);
-      SS_TRY(fetch(ah, hs ? hs->a : nullptr, md.a.p));
-    }
-    if (md.P_star.shared() && !md.P_star.diag) {
-      Psh.resize((size_t)m * m);
-      SS_TRY(fetch(Psh, hs ? hs->P_star : nullptr, md.P_star.p));
-    }
-    if (md.P_inf.shared()) {
-      Pih.resize((size_t)(md.P_inf.diag ? m : m * m));
-      SS_TRY(fetch(Pih, hs ? hs->P_inf : nullptr, md.P_inf.p));
-    }
-  }
-  if (need_sync) SS_CUDA(cudaStreamSynchronize(st));
-  if (!md.Q.diag) {
-    qpat.resize((size_t)r * r);
-    for (size_t i = 0; i < qpat.size(); i++) qpat[i] = Qh[i] != 0.0;
-  }
-  BlkPlan pl;
-  const bool planned = plan_blocks(Th.data(), md.T.diag, Rh.data(), md.R.diag, qpat.empty() ? nullptr : qpat.data(), m, r,
-                                   &pl, &why);
-  if (!planned && applicable) {  // automatic dispatch: the caller moves on to the next kernel
-    *applicable = false;
-    return SSGPU_OK;
-  }
-  SS_ARG(planned, "block kernel not eligible: " + why);
   // The residual state of the reference's layout (z = 1, nothing in its row and column of T, uncoupled by R Q R'; p = 1,
   // time-invariant Z): moved to position 1 of the last block, where the thread kernel drops it (loglik_thr.cu, EPS).  The
   // kernel assumes P_star[eps, .] = 0 off the diagonal and a[eps] = 0 for a model that starts without a diffuse phase:
@@ -1081,7 +1033,7 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     const char* e = getenv("SSGPU_THR_SHARED_DIFFUSE");
     return !(e && e[0] == '0');
   }();
-  ThrDiffuse ud{};
+  ud = ThrDiffuse{};
   if (uni_on && p == 1 && nZ == 1 && !Pih.empty() && pl.nb >= 2 && pl.nb <= kBlkMaxNB / 2) {
     std::vector<double> Pi((size_t)m * m), Mi((size_t)m), X((size_t)m * m);
     for (int i = 0; i < m; i++)
@@ -1148,7 +1100,7 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
     const char* e = getenv("SSGPU_THR_SELF_SETUP");
     return !(e && e[0] == '0');
   }();
-  ThrSelf self{};
+  self = ThrSelf{};
   if (self_on && ud.du > 0 && !pl.q_offdiag && md.Q.diag && md.P_star.diag && !ah.empty()) {
     bool ok = true;
     std::vector<int> col_used((size_t)r, 0);
@@ -1174,6 +1126,67 @@ int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, dou
       self.P_star = md.P_star;
     }
   }
+}
+
+int launch_loglik_blk(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
+                      const HostShared* hs, bool* applicable, bool lanes_only, long long call_evals) {
+  std::string why;
+  if (applicable) *applicable = true;
+  SS_ARG(blk_eligible(md, &why), "block kernel not eligible: " + why);
+  const int m = md.m, r = md.r, p = md.p;
+  // the shared matrices are a few hundred bytes: fetch what the caller has not passed along (host copies)
+  const int nZ = md.Z.tv() ? md.N : 1;
+  std::vector<double> Th((size_t)(md.T.diag ? m : m * m)), Rh((size_t)(md.R.diag ? m : m * r)), Zh((size_t)p * m * nZ), Qh;
+  std::vector<unsigned char> qpat;
+  bool need_sync = false;
+  auto fetch = [&](std::vector<double>& dst, const double* host, const double* dev) -> int {
+    if (host) {
+      std::copy(host, host + dst.size(), dst.begin());
+    } else {
+      SS_CUDA(cudaMemcpyAsync(dst.data(), dev, dst.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+      need_sync = true;
+    }
+    return SSGPU_OK;
+  };
+  SS_TRY(fetch(Th, hs ? hs->T : nullptr, md.T.p));
+  SS_TRY(fetch(Rh, hs ? hs->R : nullptr, md.R.p));
+  SS_TRY(fetch(Zh, (hs && nZ == 1) ? hs->Z : nullptr, md.Z.p));
+  if (!md.Q.diag) {
+    Qh.resize((size_t)r * r);
+    SS_TRY(fetch(Qh, hs ? hs->Q : nullptr, md.Q.p));
+  }
+  // what the thread kernel's residual shortcut looks at (p = 1, time-invariant Z): a, and a dense P_star, when shared
+  std::vector<double> ah, Psh, Pih;
+  if (p == 1 && nZ == 1) {
+    if (md.a.shared()) {
+      ah.resize((size_t)m);
+      SS_TRY(fetch(ah, hs ? hs->a : nullptr, md.a.p));
+    }
+    if (md.P_star.shared() && !md.P_star.diag) {
+      Psh.resize((size_t)m * m);
+      SS_TRY(fetch(Psh, hs ? hs->P_star : nullptr, md.P_star.p));
+    }
+    if (md.P_inf.shared()) {
+      Pih.resize((size_t)(md.P_inf.diag ? m : m * m));
+      SS_TRY(fetch(Pih, hs ? hs->P_inf : nullptr, md.P_inf.p));
+    }
+  }
+  if (need_sync) SS_CUDA(cudaStreamSynchronize(st));
+  if (!md.Q.diag) {
+    qpat.resize((size_t)r * r);
+    for (size_t i = 0; i < qpat.size(); i++) qpat[i] = Qh[i] != 0.0;
+  }
+  BlkPlan pl;
+  const bool planned = plan_blocks(Th.data(), md.T.diag, Rh.data(), md.R.diag, qpat.empty() ? nullptr : qpat.data(), m, r,
+                                   &pl, &why);
+  if (!planned && applicable) {  // automatic dispatch: the caller moves on to the next kernel
+    *applicable = false;
+    return SSGPU_OK;
+  }
+  SS_ARG(planned, "block kernel not eligible: " + why);
+  ThrDiffuse ud{};
+  ThrSelf self{};
+  plan_thread_shortcuts(md, nZ, Th, Rh, Zh, ah, Psh, Pih, qpat, pl, ud, self);
   BlkArgs A{};
   A.md = md;
   A.y = y;
@@ -1331,5 +1344,43 @@ extern "C" int ssgpu_plan_blocks(const double* T, const double* R, const double*
   // phase (time-invariant Z assumed here: the planner does not see Z)
   if (flop_per_step)
     *flop_per_step = thr_supported(pl.nb, p, false) ? thr_flops_per_step(pl.nb, pl.q_offdiag != 0) : blk_flops_per_step(pl.nb, p);
+  return SSGPU_OK;
+}
+
+// Host-only helper (no device needed): what the thread-per-evaluation kernel would do with a univariate model whose
+// matrices are shared by the batch -- the structural shortcuts that apply and the number of shared diffuse steps.
+extern "C" int ssgpu_plan_thread_kernel(const double* T, const double* R, const double* Q, const double* Z, const double* a,
+                                        const double* P_inf, const double* P_star, int m, int r, int N, int* n_blocks,
+                                        int* residual_dropped, int* level_slope_by_sums, int* zero_z_skipped,
+                                        int* shared_diffuse_steps, int* flop_per_step) {
+  using namespace ssgpu;
+  SS_ARG(T && R && Z && a && P_inf && P_star && m >= 1 && r >= 1 && N >= 1, "ssgpu_plan_thread_kernel: bad arguments");
+  for (int* o : {n_blocks, residual_dropped, level_slope_by_sums, zero_z_skipped, shared_diffuse_steps, flop_per_step})
+    if (o) *o = 0;
+  BlkPlan pl;
+  std::string why;
+  std::vector<unsigned char> qpat;
+  if (Q) {
+    qpat.resize((size_t)r * r);
+    for (size_t i = 0; i < qpat.size(); i++) qpat[i] = Q[i] != 0.0;
+  }
+  if (m > 2 * kBlkMaxNB || !plan_blocks(T, 0, R, 0, Q ? qpat.data() : nullptr, m, r, &pl, &why)) return SSGPU_OK;
+  if (n_blocks) *n_blocks = pl.nb;
+  if (!thr_supported(pl.nb, 1, false)) return SSGPU_OK;
+  DModel md{};
+  md.N = N;
+  md.p = 1;
+  md.m = m;
+  md.r = r;  // every matrix dense and shared: strides 0, diag 0
+  const std::vector<double> Th(T, T + (size_t)m * m), Rh(R, R + (size_t)m * r), Zh(Z, Z + m), ah(a, a + m),
+      Psh(P_star, P_star + (size_t)m * m), Pih(P_inf, P_inf + (size_t)m * m);
+  ThrDiffuse ud{};
+  ThrSelf self{};
+  plan_thread_shortcuts(md, 1, Th, Rh, Zh, ah, Psh, Pih, qpat, pl, ud, self);
+  if (residual_dropped) *residual_dropped = pl.eps;
+  if (level_slope_by_sums) *level_slope_by_sums = pl.ls;
+  if (zero_z_skipped) *zero_z_skipped = pl.zs;
+  if (shared_diffuse_steps) *shared_diffuse_steps = ud.du;
+  if (flop_per_step) *flop_per_step = thr_flops_per_step(pl.nb, pl.q_offdiag != 0, pl.eps != 0, pl.ls != 0, pl.zs != 0);
   return SSGPU_OK;
 }

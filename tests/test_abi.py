@@ -161,6 +161,39 @@ def test_plan_blocks_host_helper():
     assert api.plan_blocks(np.eye(3), np.eye(3))["n_blocks"] == 2 and api.plan_blocks(np.eye(3), np.eye(3))["lanes"] == 2
 
 
+def test_plan_thread_kernel_host_helper():
+    """ssgpu_plan_thread_kernel (host only): the structural shortcuts of the thread-per-evaluation kernel and its shared
+    diffuse steps, decided on host copies of the matrices.  The number of shared diffuse steps must be the oracle's
+    `initialisation_steps` of a series without missing values (src/KalmanC.cpp:199-222: P_inf vanishes after exactly
+    that many observations)."""
+    from oracle import kalman_np
+    from statespacer_b200 import api, sysmat
+    S = sysmat
+    sm = S.bsm12(0.5 * np.log([1.0, 0.1, 0.01, 0.05]))
+    pl = api.plan_thread_kernel(sm, 1000)
+    assert pl == dict(n_blocks=7, residual_dropped=1, level_slope_by_sums=1, zero_z_skipped=1, shared_diffuse_steps=13,
+                      flop_per_step=992)                                  # 392 DFMA + 189 DMUL + 19 DADD
+    assert api.plan_thread_kernel(sm, 10)["shared_diffuse_steps"] == 0     # shorter than the diffuse phase: the lanes
+    rng = np.random.default_rng(2)
+    models = [sm, S._combine(1, [[0.7]], [S.comp_level_slope(0.3, 0.02)]),
+              S._combine(1, [[0.5]], [S.comp_local_level(0.2), S.comp_bsm_trig(4, 0.05)]),
+              S._combine(1, [[0.5]], [S.comp_level_slope(0.2, 0.01), S.comp_bsm_trig(7, 0.05)])]
+    for mdl in models:
+        N = 40
+        y = rng.normal(size=(N, 1)).cumsum(axis=0)
+        want = int(kalman_np.KalmanC(y, np.isnan(y), *mdl.args(), False)["initialisation_steps"])
+        got = api.plan_thread_kernel(mdl, N)
+        assert got["shared_diffuse_steps"] == want and got["residual_dropped"] == 1 and got["zero_z_skipped"] == 1, (got, want)
+    # one block only (local level): not the thread kernel's; a[residual] != 0: the residual stays, and with it the zero-z
+    # shortcut (instantiated together); a SARIMA companion matrix does not decompose into blocks at all
+    assert api.plan_thread_kernel(S.nile_local_level(2.0, 1.0), 100)["flop_per_step"] == 0
+    a1 = sm.a.copy()
+    a1[0] = 0.3
+    pl = api.plan_thread_kernel(S.SysMat(Z=sm.Z, T=sm.T, R=sm.R, Q=sm.Q, a=a1, P_inf=sm.P_inf, P_star=sm.P_star), 1000)
+    assert (pl["residual_dropped"], pl["level_slope_by_sums"], pl["zero_z_skipped"], pl["shared_diffuse_steps"]) == (0, 1, 0, 13)
+    assert api.plan_thread_kernel(S.airline([0.5 * math.log(0.00135), 0.4, 0.55]), 144)["n_blocks"] == 0
+
+
 def test_core_flops_helper():
     """ssgpu_core_flops_per_step (host only): executed FP64 operations of the core kernel's regular phase -- config 3 with
     its 6 component states (2,082) and with the 3 deterministic means tabulated (648); 0 outside the kernel's range."""
