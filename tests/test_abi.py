@@ -194,6 +194,44 @@ def test_plan_thread_kernel_host_helper():
     assert api.plan_thread_kernel(S.airline([0.5 * math.log(0.00135), 0.4, 0.55]), 144)["n_blocks"] == 0
 
 
+def test_plan_thread_kernel_random_structural_models():
+    """Property check of the host planner over random univariate structural models (level or level + slope, up to two
+    trigonometric seasonals, an optional stationary cycle; 2 to 8 blocks): the shared diffuse steps equal the oracle's
+    `initialisation_steps`, the residual is dropped, the level + slope shortcut applies exactly when the model has a
+    slope, and the zero-loading shortcut as long as no two loaded singles share a block."""
+    from oracle import kalman_np
+    from statespacer_b200 import api, sysmat as S
+    rng = np.random.default_rng(23)
+    seen = 0
+    for trial in range(40):
+        slope = bool(rng.integers(0, 2))
+        comps = [S.comp_level_slope(0.3, 0.02) if slope else S.comp_local_level(0.3)]
+        singles = 0 if slope else 1                      # uncoupled loaded states besides the residual: the level ...
+        for s_ in rng.choice([3, 4, 6, 7, 12], size=rng.integers(0, 3), replace=False):
+            comps.append(S.comp_bsm_trig(int(s_), 0.05))
+            singles += int(s_) % 2 == 0                  # ... and the Nyquist term of an even seasonal
+        if rng.integers(0, 2):
+            c, sn = 0.9 * math.cos(0.4), 0.9 * math.sin(0.4)
+            comps.append(dict(Z=np.array([[1.0, 0.0]]), T=np.array([[c, sn], [-sn, c]]), R=np.eye(2), Q=0.3 * np.eye(2),
+                              a=np.zeros(2), P_inf=np.zeros((2, 2)), P_star=0.3 / (1 - 0.81) * np.eye(2)))
+        sm = S._combine(1, [[0.6]], comps)
+        if sm.m > 16 or sm.m < 3:
+            continue
+        N = 3 * sm.m
+        pl = api.plan_thread_kernel(sm, N)
+        if not 2 <= pl["n_blocks"] <= 8:
+            continue
+        y = rng.normal(size=(N, 1)).cumsum(axis=0)
+        want = int(kalman_np.KalmanC(y, np.isnan(y), *sm.args(), False)["initialisation_steps"])
+        assert pl["shared_diffuse_steps"] == (want if want <= 16 else 0), (trial, pl, want)
+        # the planner pairs the uncoupled states two by two, the residual first: from three loaded singles on, two of them
+        # share a block and the zero-loading shortcut does not apply
+        assert pl["residual_dropped"] == 1 and pl["level_slope_by_sums"] == int(slope), (trial, pl)
+        assert pl["zero_z_skipped"] == int(singles <= 2), (trial, singles, pl)
+        seen += 1
+    assert seen >= 20
+
+
 def test_core_flops_helper():
     """ssgpu_core_flops_per_step (host only): executed FP64 operations of the core kernel's regular phase -- config 3 with
     its 6 component states (2,082) and with the 3 deterministic means tabulated (648); 0 outside the kernel's range."""
