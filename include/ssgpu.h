@@ -371,6 +371,15 @@ int ssgpu_plan_thread_kernel(const double* T, const double* R, const double* Q, 
                              const double* P_inf, const double* P_star, int m, int r, int N, int* n_blocks,
                              int* residual_dropped, int* level_slope_by_sums, int* zero_z_skipped,
                              int* shared_diffuse_steps, int* flop_per_step);
+/* Host-only helper (no device needed): what the core kernel (SSGPU_KERNEL_CORE) does with a model whose matrices (all
+ * dense, column-major, time-invariant) are shared by the batch.  *eligible: the residual structure holds (Z = [I_p | .],
+ * T and P_inf zero in the residual rows and columns, H diagonal and equal in P_star and R Q R', a zero there) and at most
+ * 8 component states carry a variance; *n_stochastic: component states left in the recursion; *n_deterministic: component
+ * states with a known start, no disturbance and no stochastic driver, tabulated on the host; *diffuse: the instantiation
+ * with the exact diffuse phase runs.  Any output pointer may be NULL. */
+int ssgpu_plan_core(const double* T, const double* R, const double* Q, const double* Z, const double* a,
+                    const double* P_inf, const double* P_star, int m, int r, int p, int* eligible, int* n_stochastic,
+                    int* n_deterministic, int* diffuse);
 /* FP64 operations (fma = 2) the core kernel (SSGPU_KERNEL_CORE) issues per series and time point of the regular
  * phase for a model with m states of which p are residuals; 0 when m - p or p is outside the kernel's range. */
 int ssgpu_core_flops_per_step(int m, int p);

@@ -226,6 +226,18 @@ def plan_thread_kernel(sm, N):
     return dict(zip(keys, (o.value for o in out)))
 
 
+def plan_core(sm):
+    """Host only: what the core kernel does with the model `sm` (shared, time-invariant matrices) --
+    dict(eligible, n_stochastic, n_deterministic, diffuse)."""
+    f = lambda x: np.asfortranarray(np.asarray(x, dtype=np.float64))
+    T, R, Q, Z = f(sm.T[:, :, 0]), f(sm.R[:, :, 0]), f(sm.Q[:, :, 0]), f(sm.Z[:, :, 0])
+    a, Pi, Ps = f(sm.a), f(sm.P_inf), f(sm.P_star)
+    out = [C.c_int(0) for _ in range(4)]
+    native.check(native.lib().ssgpu_plan_core(_ptr(T), _ptr(R), _ptr(Q), _ptr(Z), _ptr(a), _ptr(Pi), _ptr(Ps), T.shape[0],
+                                              R.shape[1], Z.shape[0], *[C.addressof(o) for o in out]))
+    return dict(zip(("eligible", "n_stochastic", "n_deterministic", "diffuse"), (o.value for o in out)))
+
+
 def core_flops_per_step(m, p):
     """FP64 operations per series and time point of the core kernel's regular phase (0 = outside its range)."""
     return int(native.lib().ssgpu_core_flops_per_step(int(m), int(p)))

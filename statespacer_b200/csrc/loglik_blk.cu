@@ -1372,7 +1372,7 @@ extern "C" int ssgpu_plan_thread_kernel(const double* T, const double* R, const 
   md.p = 1;
   md.m = m;
   md.r = r;  // every matrix dense and shared: strides 0, diag 0
-  const std::vector<double> Th(T, T + (size_t)m * m), Rh(R, R + (size_t)m * r), Zh(Z, Z + m), ah(a, a + m),
+  const std::vector<double> Th(T, T + (size_t)m * m), Rh(R, R + (size_t)m * r), Zh(Z, Z + (size_t)m), ah(a, a + (size_t)m),
       Psh(P_star, P_star + (size_t)m * m), Pih(P_inf, P_inf + (size_t)m * m);
   ThrDiffuse ud{};
   ThrSelf self{};

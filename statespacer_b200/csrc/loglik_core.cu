@@ -395,34 +395,19 @@ static int launch_core_mc(const CoreArgs& A, bool diffuse, cudaStream_t st) {
   return SSGPU_OK;
 }
 
-// applicable != null: a model without the residual structure is not an error; *applicable = false, nothing runs
-int launch_loglik_core(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
-                       const HostShared* hs, bool* applicable) {
-  std::string why;
-  if (applicable) *applicable = true;
-  SS_ARG(core_eligible(md, &why), "core kernel not eligible: " + why);
+// Host analysis of a model for the core kernel, on host copies of its matrices (`md` supplies the storage flags): R Q R',
+// the residual structure the elimination rests on (bad = why it does not hold, else null), and the split of the
+// component states into those that carry a variance and the deterministic ones.
+struct CoreAnalysis {
+  std::vector<double> W;        // R Q R', m x m
+  std::vector<int> sidx, didx;  // component indices (0 = first state behind the residuals): stochastic / deterministic
+  const char* bad = nullptr;
+};
+
+static void core_analyse(const DModel& md, const std::vector<double>& Th, const std::vector<double>& Rh,
+                         const std::vector<double>& Zh, const std::vector<double>& Qh, const std::vector<double>& ah,
+                         const std::vector<double>& Pih, const std::vector<double>& Psh, CoreAnalysis& out) {
   const int m = md.m, r = md.r, p = md.p, mc = m - p;
-  auto count = [](const DMat& M) { return (size_t)(M.diag ? M.rows : M.rows * M.cols); };
-  std::vector<double> Th(count(md.T)), Rh(count(md.R)), Zh(count(md.Z)), Qh(count(md.Q)), ah(count(md.a)),
-      Pih(count(md.P_inf)), Psh(count(md.P_star));
-  bool need_sync = false;
-  auto fetch = [&](std::vector<double>& dst, const double* host, const double* dev) -> int {
-    if (host) {
-      std::copy(host, host + dst.size(), dst.begin());
-    } else {
-      SS_CUDA(cudaMemcpyAsync(dst.data(), dev, dst.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-      need_sync = true;
-    }
-    return SSGPU_OK;
-  };
-  SS_TRY(fetch(Th, hs ? hs->T : nullptr, md.T.p));
-  SS_TRY(fetch(Rh, hs ? hs->R : nullptr, md.R.p));
-  SS_TRY(fetch(Zh, hs ? hs->Z : nullptr, md.Z.p));
-  SS_TRY(fetch(Qh, hs ? hs->Q : nullptr, md.Q.p));
-  SS_TRY(fetch(ah, nullptr, md.a.p));
-  SS_TRY(fetch(Pih, nullptr, md.P_inf.p));
-  SS_TRY(fetch(Psh, nullptr, md.P_star.p));
-  if (need_sync) SS_CUDA(cudaStreamSynchronize(st));
   auto Tm = [&](int i, int k) { return mat_get(Th.data(), md.T.diag, m, i, k); };
   auto Rm = [&](int i, int k) { return mat_get(Rh.data(), md.R.diag, m, i, k); };
   auto Zm = [&](int i, int k) { return mat_get(Zh.data(), md.Z.diag, p, i, k); };
@@ -430,7 +415,9 @@ int launch_loglik_core(const DModel& md, const double* y, long long B, int V, do
   auto Pim = [&](int i, int k) { return mat_get(Pih.data(), md.P_inf.diag, m, i, k); };
   auto Psm = [&](int i, int k) { return mat_get(Psh.data(), md.P_star.diag, m, i, k); };
   // R Q R' (m x m)
-  std::vector<double> RQ((size_t)m * r, 0.0), W((size_t)m * m, 0.0);
+  std::vector<double> RQ((size_t)m * r, 0.0);
+  std::vector<double>& W = out.W;
+  W.assign((size_t)m * m, 0.0);
   for (int i = 0; i < m; i++)
     for (int k = 0; k < r; k++) {
       const double rik = Rm(i, k);
@@ -455,13 +442,8 @@ int launch_loglik_core(const DModel& md, const double* y, long long B, int V, do
     if (Psm(j, j) != W[j + (size_t)j * m]) bad = "P_star and R Q R' differ in the residual block";
     if (ah[j] != 0.0) bad = "a is not zero in the residual rows";
   }
-  if (bad) {
-    if (applicable) {
-      *applicable = false;
-      return SSGPU_OK;
-    }
-    SS_ARG(false, std::string("core kernel not eligible: ") + bad);
-  }
+  out.bad = bad;
+  if (bad) return;
   // Deterministic component states: no initial variance (P_star and P_inf rows zero), no disturbance (R Q R' row zero)
   // and driven by deterministic states only (T[d, s] = 0 for every other state s).  Their rows of P stay zero for ever
   // and their values are the same known numbers for every series -- the constants of a VAR with a mean (the dynamic
@@ -486,12 +468,61 @@ int launch_loglik_core(const DModel& md, const double* y, long long B, int V, do
         }
     }
   }
-  std::vector<int> sidx, didx;  // core indices of the stochastic / deterministic states
+  std::vector<int>& sidx = out.sidx;
+  std::vector<int>& didx = out.didx;
+  sidx.clear();
+  didx.clear();
   for (int i = 0; i < mc; i++) (det[i] ? didx : sidx).push_back(i);
   if (sidx.empty()) {  // nothing stochastic but the residuals: keep one state in the recursion
     sidx.push_back(didx.back());
     didx.pop_back();
   }
+}
+
+// applicable != null: a model without the residual structure is not an error; *applicable = false, nothing runs
+int launch_loglik_core(const DModel& md, const double* y, long long B, int V, double* out, cudaStream_t st,
+                       const HostShared* hs, bool* applicable) {
+  std::string why;
+  if (applicable) *applicable = true;
+  SS_ARG(core_eligible(md, &why), "core kernel not eligible: " + why);
+  const int m = md.m, p = md.p;
+  auto count = [](const DMat& M) { return (size_t)(M.diag ? M.rows : M.rows * M.cols); };
+  std::vector<double> Th(count(md.T)), Rh(count(md.R)), Zh(count(md.Z)), Qh(count(md.Q)), ah(count(md.a)),
+      Pih(count(md.P_inf)), Psh(count(md.P_star));
+  bool need_sync = false;
+  auto fetch = [&](std::vector<double>& dst, const double* host, const double* dev) -> int {
+    if (host) {
+      std::copy(host, host + dst.size(), dst.begin());
+    } else {
+      SS_CUDA(cudaMemcpyAsync(dst.data(), dev, dst.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+      need_sync = true;
+    }
+    return SSGPU_OK;
+  };
+  SS_TRY(fetch(Th, hs ? hs->T : nullptr, md.T.p));
+  SS_TRY(fetch(Rh, hs ? hs->R : nullptr, md.R.p));
+  SS_TRY(fetch(Zh, hs ? hs->Z : nullptr, md.Z.p));
+  SS_TRY(fetch(Qh, hs ? hs->Q : nullptr, md.Q.p));
+  SS_TRY(fetch(ah, nullptr, md.a.p));
+  SS_TRY(fetch(Pih, nullptr, md.P_inf.p));
+  SS_TRY(fetch(Psh, nullptr, md.P_star.p));
+  if (need_sync) SS_CUDA(cudaStreamSynchronize(st));
+  auto Tm = [&](int i, int k) { return mat_get(Th.data(), md.T.diag, m, i, k); };
+  auto Zm = [&](int i, int k) { return mat_get(Zh.data(), md.Z.diag, p, i, k); };
+  auto Pim = [&](int i, int k) { return mat_get(Pih.data(), md.P_inf.diag, m, i, k); };
+  auto Psm = [&](int i, int k) { return mat_get(Psh.data(), md.P_star.diag, m, i, k); };
+  CoreAnalysis an;
+  core_analyse(md, Th, Rh, Zh, Qh, ah, Pih, Psh, an);
+  const char* const bad = an.bad;
+  if (bad) {
+    if (applicable) {
+      *applicable = false;
+      return SSGPU_OK;
+    }
+    SS_ARG(false, std::string("core kernel not eligible: ") + bad);
+  }
+  const std::vector<double>& W = an.W;
+  const std::vector<int>&sidx = an.sidx, &didx = an.didx;
   const int ms = (int)sidx.size(), mdn = (int)didx.size();
   if (ms > kCoreMaxMC) {
     if (applicable) {
@@ -581,4 +612,35 @@ extern "C" int ssgpu_core_flops_per_step(int m, int p) {
   const int mc = m - p;
   if (mc < 1 || mc > ssgpu::kCoreMaxMC || p < 1 || p > ssgpu::kCoreMaxP) return 0;
   return ssgpu::core_flops_per_step(mc, p);
+}
+
+// Host-only helper (no device needed): what the core kernel does with a model whose matrices are shared by the batch.
+extern "C" int ssgpu_plan_core(const double* T, const double* R, const double* Q, const double* Z, const double* a,
+                               const double* P_inf, const double* P_star, int m, int r, int p, int* eligible,
+                               int* n_stochastic, int* n_deterministic, int* diffuse) {
+  using namespace ssgpu;
+  SS_ARG(T && R && Q && Z && a && P_inf && P_star && m >= 1 && r >= 1 && p >= 1, "ssgpu_plan_core: bad arguments");
+  for (int* o : {eligible, n_stochastic, n_deterministic, diffuse})
+    if (o) *o = 0;
+  DModel md{};
+  md.N = 1;
+  md.p = p;
+  md.m = m;
+  md.r = r;  // every matrix dense, shared and time-invariant: strides 0, diag 0
+  std::string why;
+  if (!core_eligible(md, &why)) return SSGPU_OK;
+  const std::vector<double> Th(T, T + (size_t)m * m), Rh(R, R + (size_t)m * r), Zh(Z, Z + (size_t)p * m),
+      Qh(Q, Q + (size_t)r * r), ah(a, a + (size_t)m), Pih(P_inf, P_inf + (size_t)m * m), Psh(P_star, P_star + (size_t)m * m);
+  CoreAnalysis an;
+  core_analyse(md, Th, Rh, Zh, Qh, ah, Pih, Psh, an);
+  if (an.bad || (int)an.sidx.size() > kCoreMaxMC) return SSGPU_OK;
+  if (eligible) *eligible = 1;
+  if (n_stochastic) *n_stochastic = (int)an.sidx.size();
+  if (n_deterministic) *n_deterministic = (int)an.didx.size();
+  bool dif = false;
+  for (int i : an.sidx)
+    for (int k : an.sidx)
+      if (!(std::fabs(P_inf[(p + i) + (size_t)(p + k) * m]) < kEps)) dif = true;
+  if (diffuse) *diffuse = dif ? 1 : 0;
+  return SSGPU_OK;
 }

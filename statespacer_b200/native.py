@@ -70,7 +70,7 @@ SYMBOLS = ["ssgpu_version", "ssgpu_last_error", "ssgpu_set_device", "ssgpu_devic
            "ssgpu_last_kernel", "ssgpu_fp64_peak", "ssgpu_plan_state_order", "ssgpu_SimulateC_dev",
            "ssgpu_FastSmootherC_dev", "ssgpu_ExtractComponentC_dev", "ssgpu_draw_layout_dev", "ssgpu_last_sim_kernel_ms",
            "ssgpu_loglik_grad_batch", "ssgpu_loglik_grad_batch_dev", "ssgpu_loglik_theta_batch_dev",
-           "ssgpu_SimSmoother", "ssgpu_kalman_batch", "ssgpu_kalman_batch_dev", "ssgpu_collapse", "ssgpu_forecast", "ssgpu_SimulateModel", "ssgpu_plan_blocks", "ssgpu_core_flops_per_step", "ssgpu_plan_thread_kernel",
+           "ssgpu_SimSmoother", "ssgpu_kalman_batch", "ssgpu_kalman_batch_dev", "ssgpu_collapse", "ssgpu_forecast", "ssgpu_SimulateModel", "ssgpu_plan_blocks", "ssgpu_core_flops_per_step", "ssgpu_plan_thread_kernel", "ssgpu_plan_core",
            "ssgpu_use_devices", "ssgpu_devices_in_use", "ssgpu_loglik_cov_batch_dev"]
 
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_COLS, KERNEL_MMA, KERNEL_MMA_DENSE, KERNEL_WSM, KERNEL_BLK, KERNEL_BLK_LANES, KERNEL_CORE = 0, 1, 2, 3, 4, 5, 6, 7, 8
@@ -113,6 +113,7 @@ def lib():
         L.ssgpu_plan_blocks.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp]
         L.ssgpu_core_flops_per_step.argtypes = [i, i]
         L.ssgpu_plan_thread_kernel.argtypes = [vp] * 7 + [i, i, i] + [vp] * 6
+        L.ssgpu_plan_core.argtypes = [vp] * 7 + [i, i, i] + [vp] * 4
         L.ssgpu_collapse.argtypes = [vp, i, i, i, vp, i, vp, i, vp, vp, vp]
         L.ssgpu_forecast.argtypes = [i, i, i, i, vp, vp, vp, i, vp, i, vp, i, vp, i, vp, i, vp, vp, vp, vp]
         L.ssgpu_kalman_batch.argtypes = [vp, ll, C.POINTER(Model), C.POINTER(KalmanOut)]

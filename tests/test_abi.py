@@ -232,6 +232,30 @@ def test_plan_thread_kernel_random_structural_models():
     assert seen >= 20
 
 
+def test_plan_core_host_helper():
+    """ssgpu_plan_core (host only): the residual structure the core kernel rests on and its split of the component states.
+    Config 3 (dynamic Nelson-Siegel: 8 residuals + 3 factors + their 3 constant means) is a 3 x 3 problem without
+    diffuse phase; the local level one diffuse state; 13 component states with a variance, correlated observation noise
+    or a loading matrix that does not start with the identity are refused."""
+    from conftest import DNS_PARAM
+    from statespacer_b200 import api, sysmat as S
+    dns, _ = S.dns_yield_curve(DNS_PARAM)
+    assert api.plan_core(dns) == dict(eligible=1, n_stochastic=3, n_deterministic=3, diffuse=0)
+    assert api.plan_core(S.nile_local_level(2.0, 1.0)) == dict(eligible=1, n_stochastic=1, n_deterministic=0, diffuse=1)
+    assert api.plan_core(S.bsm12(0.5 * np.log([1.0, 0.1, 0.01, 0.05])))["eligible"] == 0
+    bad = S.SysMat(Z=dns.Z, T=dns.T, R=dns.R, Q=dns.Q.copy(), a=dns.a, P_inf=dns.P_inf, P_star=dns.P_star.copy())
+    bad.Q[0, 1, 0] = bad.Q[1, 0, 0] = bad.P_star[0, 1] = bad.P_star[1, 0] = 1e-4
+    assert api.plan_core(bad)["eligible"] == 0
+    Z2 = dns.Z.copy()
+    Z2[0, 1, 0] = 0.5
+    assert api.plan_core(S.SysMat(Z=Z2, T=dns.T, R=dns.R, Q=dns.Q, a=dns.a, P_inf=dns.P_inf, P_star=dns.P_star))["eligible"] == 0
+    # a mean that is driven by a factor is not deterministic any more, and drags the means it drives along
+    T2 = dns.T.copy()
+    T2[8 + 3, 8 + 0, 0] = 0.1
+    pl = api.plan_core(S.SysMat(Z=dns.Z, T=T2, R=dns.R, Q=dns.Q, a=dns.a, P_inf=dns.P_inf, P_star=dns.P_star))
+    assert pl == dict(eligible=1, n_stochastic=4, n_deterministic=2, diffuse=0), pl
+
+
 def test_core_flops_helper():
     """ssgpu_core_flops_per_step (host only): executed FP64 operations of the core kernel's regular phase -- config 3 with
     its 6 component states (2,082) and with the 3 deterministic means tabulated (648); 0 outside the kernel's range."""
